@@ -1,0 +1,320 @@
+/*
+ * mmb.h - C ABI of libmmb_b200.so: the B200 (sm_100a) kernels behind the rollout hot path of
+ * SafeRL-Lab/Massive-MARL-Benchmark (per-step task tensor pipeline + rollout storage).
+ *
+ * The reference has no FFI: its boundary is Python duck typing (VecTask.step / RolloutStorage).  The
+ * Python host classes in massive_marl_benchmark_b200/ keep those interfaces and call the entry
+ * points below through ctypes.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 (MMB_OK) or a negative mmb_status; no exception crosses the ABI;
+ *   - all buffers are caller-owned DEVICE pointers (PyTorch allocates); the library never
+ *     allocates, frees or retains a pointer after returning;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no host sync,
+ *     no host read-back; counts the host may want are written to caller-provided device memory;
+ *   - re-entrant; no global mutable state besides a per-device attribute cache;
+ *   - params structs are plain-old-data, passed by pointer, copied before return;
+ *   - "frames": the PhysX step is out of scope, so state arrives as Isaac-Gym-layout frames.  A call
+ *     may process num_frames >= 1 consecutive frames of the same env set in one launch
+ *     (horizon-batched replay); *_frame_stride are in ELEMENTS of the pointed-to type.
+ *   - `flavor` selects which torch device's fp32 association order is reproduced where the two
+ *     differ (3- and 8-element sum(-1), 3-element norm, division by a Python scalar): the
+ *     reference's arithmetic is "whatever torch does on the device it runs on".
+ */
+#ifndef MMB_H_
+#define MMB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MMB_API __attribute__((visibility("default")))
+#else
+#define MMB_API
+#endif
+
+typedef enum {
+  MMB_OK = 0,
+  MMB_EINVAL = -1,       /* null pointer / non-positive size / inconsistent arguments */
+  MMB_EALIGN = -2,       /* a pointer or stride violates the documented alignment */
+  MMB_ECUDA = -3,        /* the CUDA runtime reported a launch/config error */
+  MMB_EUNSUPPORTED = -4  /* valid request outside what this build implements */
+} mmb_status;
+
+enum { MMB_FLAVOR_CUDA = 0, /* torch eager on CUDA (the reference's production device) */
+       MMB_FLAVOR_CPU = 1 /* torch on CPU (the pinned oracle) */ };
+
+MMB_API int32_t mmb_abi_version(void);
+MMB_API const char* mmb_strerror(int32_t status);
+/* number of kernels launched by this library since load (all threads); bench.py reports deltas */
+MMB_API uint64_t mmb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Task constants: cfg/<Task>.yaml `env:` block + per-task literals     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float dof_vel_scale;        /* env.dofVelocityScale  0.2  */
+  float contact_force_scale;  /* env.contactForceScale 0.1  */
+  float power_scale;          /* env.powerScale        1.0  */
+  float up_weight;            /* env.upWeight          0.1  */
+  float actions_cost;         /* env.actionsCost       0.005 */
+  float energy_cost;          /* env.energyCost        0.05 */
+  float joints_at_limit_cost; /* env.jointsAtLimitCost 0.1  */
+  float death_cost;           /* env.deathCost        -2.0  */
+  float termination_height;   /* env.terminationHeight 0.31 */
+  float dt;                   /* sim.dt                0.0166 */
+  float max_episode_length;   /* env.episodeLength     1000 (compared as progress >= len-1) */
+  float quat_reward_scale;    /* ten_ant.py:57 = 0, one_ant.py:58 = 1 */
+  float ant_dist_reward_scale;  /* 500 */
+  float goal_dist_reward_scale; /* 500 */
+  float x_goal, y_goal, z_goal; /* 0,1,0 (ten_ant.py:199-201) */
+  float dof_lower[8];         /* per-ant DOF limits (rad), lower<=upper (ten_ant.py:590-596) */
+  float dof_upper[8];
+  float joint_gears[8];       /* motor_effort per DOF (nv_ant.xml:83-90 = 15) */
+  float inv_start_rot[4];     /* quat_conjugate(start_rotation) = (-0,-0,-0,1) (ten_ant.py:166) */
+  float initial_dof_pos[8];   /* ten_ant.py:133-137 */
+} mmb_ant_consts;
+
+/* ------------------------------------------------------------------------------------------ */
+/* TenAnt: one or more env-steps of obs + reward + done + progress + carry + action forces.      */
+/* Replaces TenAnt.pre_physics_step / post_physics_step minus reset_idx                           */
+/*   (agents/tasks/ten_ant.py:886-926, :712-808, :635-710, jit fns :935-1393),                   */
+/*   the clamp passes of VecTaskPython.step (agents/tasks/agent_base/vec_task.py:126-131) and     */
+/*   the per-agent split of MultiVecTaskPython.step (agent_base/multi_vec_task.py:94-144).        */
+/* reset_idx (ten_ant.py:810-884) is mmb_reset_compact, to be enqueued BEFORE this call on the    */
+/* same stream (it reads the reset flags this call overwrites).                                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_envs;    /* N */
+  int32_t num_frames;  /* T >= 1 */
+  int32_t flavor;      /* MMB_FLAVOR_* */
+  int32_t obs_layout;  /* 0: obs rows [N][388];  1: per-agent rows [N][10][46] (+ share_obs) */
+  /* inputs, Isaac layout */
+  const float* root;    int64_t root_frame_stride;    /* [T][11N][13] */
+  const float* dof;     int64_t dof_frame_stride;     /* [T][80N][2]  */
+  const float* actions; int64_t actions_frame_stride; /* [T][N][80], before the +-clip_actions clamp */
+  float clip_actions;   /* VecTask clip (1.0); +inf disables */
+  float clip_obs;       /* VecTask 5.0 / MultiVecTask 7.0; +inf disables */
+  /* carry, in/out: values after step -1 on entry, after step T-1 on exit */
+  float* pos_before;      /* [N][10][2] */
+  float* goal_before;     /* [N][10][2] */
+  float* box_before;      /* [N][2]     */
+  int64_t* progress_buf;  /* [N] */
+  int64_t* reset_buf;     /* [N] */
+  /* outputs; any pointer may be NULL to skip that output */
+  float* obs_raw;   int64_t obs_raw_frame_stride;   /* task.obs_buf, unclamped [T][N][388] */
+  float* obs;       int64_t obs_frame_stride;       /* clamped, layout per obs_layout */
+  float* share_obs; int64_t share_obs_frame_stride; /* obs_layout 1: clamped [T][N][388], once per env */
+  float* rewards;   int64_t rewards_frame_stride;   /* [T][N] */
+  int64_t* dones_i64; int64_t dones_i64_frame_stride; /* [T][N] reset_buf after each step */
+  uint8_t* dones_u8;  int64_t dones_u8_frame_stride;  /* [T][N] same, as RolloutStorage.dones */
+  float* forces;    int64_t forces_frame_stride;    /* [T][N][80] clamp(actions)*gear*power_scale */
+  mmb_ant_consts c;
+} mmb_ten_ant_params;
+
+MMB_API int32_t mmb_ten_ant_step(const mmb_ten_ant_params* p, void* stream);
+
+/* Loads the carry (pos_before / goal_before / box_before) from a root tensor, as reset_idx does for
+ * ALL envs from the not-yet-refreshed root_states (ten_ant.py:870-882); needed once, before the
+ * first step (afterwards the step kernel's own carry is value-identical). */
+MMB_API int32_t mmb_ten_ant_load_carry(const float* root /* [11N][13] */, int32_t num_envs, float* pos_before,
+                               float* goal_before, float* box_before, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* OneAnt (agents/tasks/one_ant.py:396-415, :346-361, :314-344, jit fns :429-627)                */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_envs;
+  int32_t num_frames;
+  int32_t flavor;
+  int32_t reserved0;
+  const float* root;    int64_t root_frame_stride;    /* [T][2N][13]: rows 2e ant, 2e+1 box */
+  const float* dof;     int64_t dof_frame_stride;     /* [T][8N][2] */
+  const float* sensor;  int64_t sensor_frame_stride;  /* [T][N][24] (= [4N][6]) */
+  const float* actions; int64_t actions_frame_stride; /* [T][N][8] */
+  float clip_actions;
+  float clip_obs;
+  /* carry in/out */
+  float* pos_before;      /* [N][2] */
+  float* box_before;      /* [N][2] */
+  float* potentials;      /* [N] */
+  float* prev_potentials; /* [N] */
+  int64_t* progress_buf;
+  int64_t* reset_buf;
+  /* outputs (NULL to skip) */
+  float* obs_raw;   int64_t obs_raw_frame_stride;   /* [T][N][60] */
+  float* obs;       int64_t obs_frame_stride;       /* clamped [T][N][60] */
+  float* rewards;   int64_t rewards_frame_stride;
+  int64_t* dones_i64; int64_t dones_i64_frame_stride;
+  uint8_t* dones_u8;  int64_t dones_u8_frame_stride;
+  float* forces;    int64_t forces_frame_stride;    /* [T][N][8] */
+  float* up_vec;       /* [N][3] after the last frame (task.up_vec) */
+  float* heading_vec;  /* [N][3] */
+  float* ant_pos;      /* [N][2] */
+  float* box_pos;      /* [N][2] */
+  float* box_quat;     /* [N][4] */
+  mmb_ant_consts c;
+} mmb_one_ant_params;
+
+MMB_API int32_t mmb_one_ant_step(const mmb_one_ant_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* MultiIngenuity (agents/tasks/multi_ingenuity.py:268-374, jit :381-453)                        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_envs;
+  int32_t num_frames;
+  int32_t flavor;
+  int32_t obs_layout;   /* 0: [N][52];  1: per-agent [N][4][13] is the same memory -> identical */
+  const float* root;    int64_t root_frame_stride;    /* [T][4N][13] */
+  const float* actions; int64_t actions_frame_stride; /* [T][N][24] */
+  float clip_actions;
+  float clip_obs;
+  float dt;
+  float max_episode_length;
+  float thrust_upper_limit;        /* 2000 */
+  float thrust_lateral_component;  /* 0.2  */
+  float thrust_action_speed_scale; /* 2000 */
+  float goals[4][3];               /* multi_ingenuity.py:103-106 */
+  int64_t* progress_buf;
+  int64_t* reset_buf;
+  float* obs_raw;   int64_t obs_raw_frame_stride;   /* [T][N][52] */
+  float* obs;       int64_t obs_frame_stride;       /* clamped */
+  float* rewards;   int64_t rewards_frame_stride;
+  int64_t* dones_i64; int64_t dones_i64_frame_stride;
+  uint8_t* dones_u8;  int64_t dones_u8_frame_stride;
+  float* forces;    int64_t forces_frame_stride;    /* [T][N][24][3] tensor handed to apply_rigid_body_force_tensors */
+  float* forces_state; /* [N][24][3] task.forces after the last frame (rows of envs reset in it zeroed) or NULL */
+} mmb_ingenuity_params;
+
+MMB_API int32_t mmb_ingenuity_step(const mmb_ingenuity_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* reset_idx for all three tasks: ordered compaction of the reset flags (== reset_buf.nonzero()),*/
+/* the int32 actor-index lists of set_actor_root_state_tensor_indexed / set_dof_state_tensor_    */
+/* indexed, and the DOF re-randomisation.  ten_ant.py:810-884, one_ant.py:363-391,              */
+/* multi_ingenuity.py:231-266.  Rows: row f uses flags[f] (batched over replayed frames).         */
+/* ------------------------------------------------------------------------------------------ */
+enum { MMB_TASK_TEN_ANT = 0, MMB_TASK_ONE_ANT = 1, MMB_TASK_INGENUITY = 2 };
+
+typedef struct {
+  int32_t task;        /* MMB_TASK_* */
+  int32_t num_envs;
+  int32_t num_rows;    /* F >= 1 */
+  int32_t noise_mode;  /* 0: rows of noise_pos/noise_vel (row i feeds the i-th reset env); 1: Philox(seed, env, step) */
+  const int64_t* flags_i64; int64_t flags_i64_row_stride; /* one of flags_i64 / flags_u8 */
+  const uint8_t* flags_u8;  int64_t flags_u8_row_stride;
+  int64_t* env_ids;   int64_t env_ids_row_stride;   /* [F][N]      ascending env ids, first count[f] valid */
+  int32_t* index_a;   int64_t index_a_row_stride;   /* [F][N*na]   root call: TenAnt 11/env, OneAnt 2, Ingenuity 4 */
+  int32_t* index_b;   int64_t index_b_row_stride;   /* [F][N*nb]   dof call:  TenAnt 10/env, OneAnt 1, Ingenuity 4 */
+  int32_t* counts;    /* [F] number of reset envs */
+  float* dof_state;   int64_t dof_state_row_stride; /* [F][dofs*N][2] tensor the reset writes into (may be NULL) */
+  const float* noise_pos; const float* noise_vel; int64_t noise_row_stride; /* [F][N][8] */
+  uint64_t seed; uint64_t step;                     /* Philox key / counter base (noise_mode 1) */
+  float* forces_state;                              /* Ingenuity: task.forces rows to zero, or NULL */
+  mmb_ant_consts c;
+} mmb_reset_params;
+
+MMB_API int32_t mmb_reset_compact(const mmb_reset_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Rollout storage: PPO (agents/algorithms/rl/ppo/storage.py)                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* RolloutStorage.add_transitions (storage.py:32-46) for callers that cannot use the step kernel's
+ * direct write into the rollout slot: nine copies fused in one launch, dones int64 -> uint8. */
+typedef struct {
+  int32_t num_envs, obs_dim, states_dim, act_dim;
+  const float* observations; const float* states; const float* actions; const float* rewards;
+  const int64_t* dones; const float* values; const float* actions_log_prob; const float* mu; const float* sigma;
+  float* dst_observations; float* dst_states; float* dst_actions; float* dst_rewards; uint8_t* dst_dones;
+  float* dst_values; float* dst_actions_log_prob; float* dst_mu; float* dst_sigma;   /* slot `step` of each plane */
+} mmb_rollout_add_params;
+MMB_API int32_t mmb_rollout_add(const mmb_rollout_add_params* p, void* stream);
+
+/* RolloutStorage.compute_returns (storage.py:51-65): reverse-time GAE scan, raw advantages, and the
+ * sum / sum-of-squares of the raw advantages (fp64) for the normalisation.  stats[0..2] =
+ * {count, sum, sumsq} are ACCUMULATED (caller zeroes them), so env shards on several GPUs can be
+ * all-reduced before mmb_adv_normalize. */
+typedef struct {
+  int32_t num_envs, num_steps;
+  const float* rewards;      /* [T][N] */
+  const float* values;       /* [T][N] */
+  const uint8_t* dones;      /* [T][N] */
+  const float* last_values;  /* [N] */
+  double gamma, lam;         /* Python floats of cfg/ppo/config.yaml:30-31; each is cast to fp32 where torch does */
+  float* returns;            /* [T][N] */
+  float* advantages;         /* [T][N] raw (returns - values) */
+  double* stats;             /* [3] or NULL */
+} mmb_gae_ppo_params;
+MMB_API int32_t mmb_gae_ppo(const mmb_gae_ppo_params* p, void* stream);
+
+/* (adv - mean) / (std_unbiased + eps) in place; mean/std from stats = {count, sum, sumsq} on device.
+ * eps = 1e-8 (storage.py:65) or 1e-5 (mappo_trainer.py:199). */
+MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, const double* stats, float eps, void* stream);
+
+/* RolloutStorage.get_statistics (storage.py:67-73) on device: out[0] = mean trajectory length,
+ * out[1] = mean reward.  No host sync. */
+MMB_API int32_t mmb_rollout_statistics(const uint8_t* dones, const float* rewards, int32_t num_steps, int32_t num_envs,
+                               float* out2, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Rollout storage: MARL (agents/algorithms/marl/utils/separated_buffer.py:124-168) with the     */
+/* PopArt / ValueNorm denormalisation (popart.py:30-34,64-75) folded in, plus the advantage       */
+/* prologue of mappo_trainer.py:189-199.  Planes may be strided over agents (shared buffer).      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_envs, num_steps, num_agents;
+  int32_t use_gae, use_proper_time_limits, use_denorm, use_popart;
+  /* element (t, env, agent) of plane X lives at X[t*X_t + env*X_e + agent*X_a] */
+  const float* rewards;  int64_t rew_t, rew_e, rew_a;      /* T   steps */
+  float* value_preds;    int64_t val_t, val_e, val_a;      /* T+1 steps; slot T is overwritten by next_value */
+  const float* masks;    int64_t msk_t, msk_e, msk_a;      /* T+1 */
+  const float* bad_masks;int64_t bad_t, bad_e, bad_a;      /* T+1 (proper time limits only) */
+  const float* next_value; int64_t nv_e, nv_a;             /* [N][A] */
+  float* returns;        int64_t ret_t, ret_e, ret_a;      /* T+1 */
+  float* advantages;     int64_t adv_t, adv_e, adv_a;      /* T, raw returns - D(value_preds); NULL to skip */
+  const float* denorm_mean; const float* denorm_var;       /* [A] device scalars (running_mean_var) */
+  double gamma, gae_lambda;  /* Python floats; gamma*gae_lambda is formed in double like the reference does */
+  double* stats;         /* [A][3] accumulated {count, sum, sumsq} per agent, or NULL */
+} mmb_gae_marl_params;
+MMB_API int32_t mmb_gae_marl(const mmb_gae_marl_params* p, void* stream);
+
+/* Runner.insert mask logic (agents/algorithms/marl/runner.py:229-255): dones [N][A] int64 ->
+ * masks, active_masks [N][A] fp32 written straight into slot step+1 of the buffer planes. */
+MMB_API int32_t mmb_marl_masks(const int64_t* dones, int32_t num_envs, int32_t num_agents, float* masks, int64_t m_e,
+                       int64_t m_a, float* active_masks, int64_t am_e, int64_t am_a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Minibatch shuffle + gather: mini_batch_generator + the nine `.view(-1,.)[indices]` gathers of  */
+/* PPO.update (storage.py:75-87, ppo.py:252-264); feed_forward_generator (separated_buffer.py:   */
+/* 170-228).  One launch gathers every field of one minibatch into contiguous buffers.           */
+/* ------------------------------------------------------------------------------------------ */
+#define MMB_MAX_GATHER_FIELDS 16
+typedef struct {
+  int32_t num_fields;
+  int32_t index_mode;  /* 0: indices given (int64, device) ; 1: stateless bijection on [0,total) keyed by seed */
+  int64_t total;       /* T*N rows in the flattened planes */
+  int64_t batch_start; /* first position of this minibatch in the permutation */
+  int64_t batch_size;
+  const int64_t* indices;   /* [batch_size] (mode 0) */
+  uint64_t seed;            /* mode 1 */
+  int64_t* indices_out;     /* [batch_size] the row ids used (mode 1), or NULL */
+  const void* src[MMB_MAX_GATHER_FIELDS];   /* row-major [total][row_bytes] */
+  void* dst[MMB_MAX_GATHER_FIELDS];         /* [batch_size][row_bytes] */
+  int32_t row_bytes[MMB_MAX_GATHER_FIELDS]; /* multiple of 4 (or 1 for byte planes) */
+} mmb_gather_params;
+MMB_API int32_t mmb_shuffle_gather(const mmb_gather_params* p, void* stream);
+/* random permutation of [0,n) on device (fast mode of mini_batch_generator 'random'): the stateless
+ * bijection evaluated for every position; a permutation by construction. */
+MMB_API int32_t mmb_permutation(int64_t n, uint64_t seed, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMB_H_ */

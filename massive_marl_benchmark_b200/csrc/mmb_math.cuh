@@ -1,0 +1,195 @@
+// mmb_math.cuh - fp32 arithmetic that replays the reference's torch rounding sequence op for op.
+//
+// The reference's task functions are chains of separate torch ops, i.e. every add/sub/mul/div/sqrt
+// is individually IEEE-rounded (no FMA contraction across ops).  The rewards are ill-conditioned in
+// fp32 (SURVEY.md finding 11: 500*(l2_before - l2_now) amplifies one-ulp differences), so the
+// kernels use the round-to-nearest intrinsics below in the reference's association order and plain
+// libdevice transcendentals (never --use_fast_math).  Measured on B200 (profiles/r01_probe_torch_cuda.json):
+// libdevice sinf/cosf/atanf/atan2f/fmodf and div.rn/sqrt.rn equal torch's CUDA kernels bit for bit.
+//
+// Where torch's CUDA and CPU kernels associate differently the `FLAVOR` template argument picks
+// (MMB_FLAVOR_CUDA / MMB_FLAVOR_CPU, measured in the same probe):
+//   sum(-1) over 3:  CUDA (a0+a2)+a1          CPU (a0+a1)+a2
+//   sum(-1) over 8:  CUDA ((a0+a4)+(a2+a6))+((a1+a5)+(a3+a7))   CPU sequential
+//   x / python_scalar: CUDA x * (1/s)          CPU x / s
+// Same on both devices: torch.cross = fma(a1,b2,-(a2*b1)); 1x3.3x1 bmm = (a0b0+a1b1)+a2b2 unfused;
+// norm over (x,y,0) = sqrt(x*x+y*y); remainder = fmod then +b on sign mismatch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mmb {
+
+constexpr int FLAVOR_CUDA = 0;
+constexpr int FLAVOR_CPU = 1;
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+struct f3 { float x, y, z; };
+struct f4 { float x, y, z, w; };  // quaternion (x,y,z,w)
+
+// torch.clamp(x, lo, hi) (NaN propagates)
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+template <int FLAVOR>
+__device__ __forceinline__ float sum3(float a0, float a1, float a2) {
+  if (FLAVOR == FLAVOR_CUDA) return fadd(fadd(a0, a2), a1);
+  return fadd(fadd(a0, a1), a2);
+}
+
+template <int FLAVOR>
+__device__ __forceinline__ float sum8(const float* e) {
+  if (FLAVOR == FLAVOR_CUDA) {
+    float t0 = fadd(e[0], e[4]), t1 = fadd(e[1], e[5]), t2 = fadd(e[2], e[6]), t3 = fadd(e[3], e[7]);
+    return fadd(fadd(t0, t2), fadd(t1, t3));
+  }
+  float s = e[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) s = fadd(s, e[j]);
+  return s;
+}
+
+// isaacgym.torch_utils.quat_mul (oracle/isaac_torch_utils.py)
+__device__ __forceinline__ f4 quat_mul(f4 a, f4 b) {
+  float ww = fmul(fadd(a.z, a.x), fadd(b.x, b.y));
+  float yy = fmul(fsub(a.w, a.y), fadd(b.w, b.z));
+  float zz = fmul(fadd(a.w, a.y), fsub(b.w, b.z));
+  float xx = fadd(fadd(ww, yy), zz);
+  float qq = fmul(0.5f, fadd(xx, fmul(fsub(a.z, a.x), fsub(b.x, b.y))));
+  f4 r;
+  r.w = fadd(fsub(qq, ww), fmul(fsub(a.z, a.y), fsub(b.y, b.z)));
+  r.x = fadd(fsub(qq, xx), fmul(fadd(a.x, a.w), fadd(b.x, b.w)));
+  r.y = fadd(fsub(qq, yy), fmul(fsub(a.w, a.x), fadd(b.y, b.z)));
+  r.z = fadd(fsub(qq, zz), fmul(fadd(a.z, a.y), fsub(b.w, b.x)));
+  return r;
+}
+
+// torch.cross(a, b, dim=-1): each component is fma(a_i, b_j, -(a_j * b_i)) on CUDA and CPU
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+  f3 r;
+  r.x = __fmaf_rn(a.y, b.z, -fmul(a.z, b.y));
+  r.y = __fmaf_rn(a.z, b.x, -fmul(a.x, b.z));
+  r.z = __fmaf_rn(a.x, b.y, -fmul(a.y, b.x));
+  return r;
+}
+
+// torch.bmm of [1x3]x[3x1]
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z)); }
+
+// quat_rotate(q, v) = a + b + c   /  quat_rotate_inverse = a - b + c
+template <bool INVERSE>
+__device__ __forceinline__ f3 quat_rot(f4 q, f3 v) {
+  float s = fsub(fmul(2.0f, fmul(q.w, q.w)), 1.0f);
+  f3 qv = {q.x, q.y, q.z};
+  f3 cr = cross3(qv, v);
+  float d = dot3(qv, v);
+  f3 r;
+  {
+    float a = fmul(v.x, s), b = fmul(fmul(cr.x, q.w), 2.0f), c = fmul(fmul(qv.x, d), 2.0f);
+    r.x = fadd(INVERSE ? fsub(a, b) : fadd(a, b), c);
+  }
+  {
+    float a = fmul(v.y, s), b = fmul(fmul(cr.y, q.w), 2.0f), c = fmul(fmul(qv.y, d), 2.0f);
+    r.y = fadd(INVERSE ? fsub(a, b) : fadd(a, b), c);
+  }
+  {
+    float a = fmul(v.z, s), b = fmul(fmul(cr.z, q.w), 2.0f), c = fmul(fmul(qv.z, d), 2.0f);
+    r.z = fadd(INVERSE ? fsub(a, b) : fadd(a, b), c);
+  }
+  return r;
+}
+
+// torch.remainder(a, b) for float: fmod, then + b when non-zero and of opposite sign
+__device__ __forceinline__ float remainderf_torch(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.0f && ((b < 0.0f) != (m < 0.0f))) m = fadd(m, b);
+  return m;
+}
+
+#define MMB_TWO_PI_F 6.28318530717958647692f  // float(2*np.pi): Tensor % python_float casts the scalar to fp32
+
+// roll and yaw of get_euler_xyz (pitch is computed by the reference but never used on the path)
+__device__ __forceinline__ void euler_roll_yaw(f4 q, float& roll, float& yaw) {
+  float sinr = fmul(2.0f, fadd(fmul(q.w, q.x), fmul(q.y, q.z)));
+  float cosr = fadd(fsub(fsub(fmul(q.w, q.w), fmul(q.x, q.x)), fmul(q.y, q.y)), fmul(q.z, q.z));
+  roll = remainderf_torch(atan2f(sinr, cosr), MMB_TWO_PI_F);
+  float siny = fmul(2.0f, fadd(fmul(q.w, q.z), fmul(q.x, q.y)));
+  float cosy = fsub(fsub(fadd(fmul(q.w, q.w), fmul(q.x, q.x)), fmul(q.y, q.y)), fmul(q.z, q.z));
+  yaw = remainderf_torch(atan2f(siny, cosy), MMB_TWO_PI_F);
+}
+
+// l2_dist (ten_ant.py:975-985): sqrt((a-b)_x^2 + (a-b)_y^2)
+__device__ __forceinline__ float l2_dist2(float ax, float ay, float bx, float by) {
+  float c1 = fsub(ax, bx), c2 = fsub(ay, by);
+  return fsqrt(fadd(fmul(c1, c1), fmul(c2, c2)));
+}
+
+// compute_box_quat + compute_box_quat_dist (ten_ant.py:951-973)
+__device__ __forceinline__ float box_quat_dist(f4 q, float xg, float yg, float zg) {
+  float x = fmul(2.0f, fadd(fmul(q.x, q.y), fmul(q.w, q.z)));
+  float y = fsub(1.0f, fmul(2.0f, fadd(fmul(q.x, q.x), fmul(q.z, q.z))));
+  float z = fmul(2.0f, fsub(fmul(q.y, q.z), fmul(q.w, q.x)));
+  float num = fadd(fadd(fmul(x, xg), fmul(y, yg)), fmul(z, zg));
+  float den = fsqrt(fadd(fadd(fmul(x, x), fmul(y, y)), fmul(z, z)));
+  // second divisor is a Python float: sqrt(xg^2+yg^2+zg^2) evaluated in double, then cast
+  float gn = (float)sqrt((double)xg * xg + (double)yg * yg + (double)zg * zg);
+  return fdiv(fdiv(num, den), gn);
+}
+
+// The 38-wide per-ant observation core shared by TenAnt (ten_ant.py:1304-1350) and OneAnt
+// (one_ant.py:563-618): everything except the position prefix / sensors / actions.
+struct AntCore {
+  f3 vel_loc, angvel_loc;
+  float yaw, roll, angle_to_target, up_proj, heading_proj;
+  f3 up_vec, heading_vec;
+};
+
+template <int FLAVOR>
+__device__ __forceinline__ AntCore ant_core(f3 p, f4 q, f3 v, f3 w, f4 inv_start_rot) {
+  AntCore o;
+  // to_target = targets(0,0,0) - torso_position ; z := 0
+  f3 tt = {fsub(0.0f, p.x), fsub(0.0f, p.y), 0.0f};
+  // normalize: x / clamp(norm, 1e-9)
+  float nrm = fsqrt(fadd(fmul(tt.x, tt.x), fmul(tt.y, tt.y)));
+  if (FLAVOR == FLAVOR_CPU) nrm = fsqrt(__fmaf_rn(tt.y, tt.y, fmul(tt.x, tt.x)));  // CPU vectorised norm (99.3% of rows)
+  nrm = nrm < 1e-9f ? 1e-9f : nrm;
+  f3 dir = {fdiv(tt.x, nrm), fdiv(tt.y, nrm), fdiv(tt.z, nrm)};
+  f4 tq = quat_mul(q, inv_start_rot);
+  o.up_vec = quat_rot<false>(tq, f3{0.0f, 0.0f, 1.0f});
+  o.heading_vec = quat_rot<false>(tq, f3{1.0f, 0.0f, 0.0f});
+  o.up_proj = o.up_vec.z;
+  o.heading_proj = dot3(o.heading_vec, dir);
+  o.vel_loc = quat_rot<true>(tq, v);
+  o.angvel_loc = quat_rot<true>(tq, w);
+  euler_roll_yaw(tq, o.roll, o.yaw);
+  float walk = atan2f(fsub(0.0f, p.z), fsub(0.0f, p.x));
+  o.angle_to_target = fsub(walk, o.yaw);
+  return o;
+}
+
+// unscale(x, lower, upper) = (2x - upper - lower) / (upper - lower)
+__device__ __forceinline__ float unscale(float x, float lo, float hi) {
+  return fdiv(fsub(fsub(fmul(2.0f, x), hi), lo), fsub(hi, lo));
+}
+
+// ---- 128-bit global access helpers ---------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cooperative copy global -> shared of n floats (n need not be a multiple of 4)
+__device__ __forceinline__ void tile_load(float* __restrict__ s, const float* __restrict__ g, int n, int tid, int nthreads) {
+  if (aligned16(g)) {
+    int n4 = n >> 2;
+    for (int i = tid; i < n4; i += nthreads) reinterpret_cast<float4*>(s)[i] = ldg4(g + 4 * i);
+    for (int i = (n4 << 2) + tid; i < n; i += nthreads) s[i] = __ldg(g + i);
+  } else {
+    for (int i = tid; i < n; i += nthreads) s[i] = __ldg(g + i);
+  }
+}
+
+}  // namespace mmb

@@ -1,0 +1,150 @@
+// reset.cu - reset_idx for TenAnt / OneAnt / MultiIngenuity as one kernel.
+//
+// Replaces ten_ant.py:810-884, one_ant.py:363-391, multi_ingenuity.py:231-266:
+//   env_ids = reset_buf.nonzero().flatten()                  -> ordered stream compaction
+//   torch.unique(cat(actor_indices[env_ids] ...)).int32      -> ascending {apn*e + j}: no sort needed,
+//                                                               the lists are emitted in order
+//   dof_pos_k[env_ids] = clamp(initial + U(-.2,.2)), dof_vel_k[env_ids] = U(-.1,.1), same noise for all ants
+//   Ingenuity: rotor speeds for ALL envs when any env resets; forces rows of reset envs zeroed.
+// The reference pays a host sync (`len(env_ids)`) and ~45 small kernels per step for this; here the
+// count stays on the device (counts[f]) and nothing is read back.
+//
+// One CTA of 1024 threads per row f (a row = the flags of one frame): warp ballot + popc prefix inside
+// the CTA, running offset across 1024-env chunks.  O(N) flag bytes per row; fine up to ~1M envs per row
+// (one SM streams the flags); a multi-CTA decoupled look-back scan is the planned upgrade for larger N.
+#include "../../include/mmb.h"
+#include "mmb_common.cuh"
+#include "mmb_math.cuh"
+
+namespace mmb {
+namespace {
+
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator torch's CUDA RNG also uses; keyed by
+// (seed), counter = (env, step, block, 0) so that an env-sharded multi-GPU run draws the same numbers as
+// the single-GPU run on the concatenated envs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+struct TaskShape { int apn, na, nb, dofs, ants; };
+__device__ __forceinline__ TaskShape shape_of(int task) {
+  if (task == MMB_TASK_TEN_ANT) return {11, 11, 10, 80, 10};
+  if (task == MMB_TASK_ONE_ANT) return {2, 2, 1, 8, 1};
+  return {4, 4, 4, 16, 0};
+}
+
+__global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb_reset_params p) {
+  __shared__ int warp_tot[32];
+  __shared__ int s_running;
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int N = p.num_envs;
+  const TaskShape sh = shape_of(p.task);
+  const int64_t* f64 = p.flags_i64 ? p.flags_i64 + (int64_t)f * p.flags_i64_row_stride : nullptr;
+  const uint8_t* f8 = p.flags_u8 ? p.flags_u8 + (int64_t)f * p.flags_u8_row_stride : nullptr;
+  int64_t* env_ids = p.env_ids + (int64_t)f * p.env_ids_row_stride;
+  int32_t* ia = p.index_a ? p.index_a + (int64_t)f * p.index_a_row_stride : nullptr;
+  int32_t* ib = p.index_b ? p.index_b + (int64_t)f * p.index_b_row_stride : nullptr;
+
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += 1024) {
+    const int e = base + tid;
+    bool flag = false;
+    if (e < N) flag = f64 ? (f64[e] != 0) : (f8[e] != 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int wprefix = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int running = s_running;
+    int woff = 0, tot = 0;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) {
+      int v = warp_tot[w];
+      woff += (w < wid) ? v : 0;
+      tot += v;
+    }
+    if (flag) {
+      const int i = running + woff + wprefix;
+      env_ids[i] = e;
+      if (ia) for (int j = 0; j < sh.na; ++j) ia[i * sh.na + j] = sh.apn * e + j;
+      if (ib) for (int j = 0; j < sh.nb; ++j) ib[i * sh.nb + j] = sh.apn * e + j;
+    }
+    __syncthreads();
+    if (tid == 0) s_running = running + tot;
+    __syncthreads();
+  }
+  const int count = s_running;
+  if (tid == 0 && p.counts) p.counts[f] = count;
+  if (count == 0) return;
+
+  float* dof = p.dof_state ? p.dof_state + (int64_t)f * p.dof_state_row_stride : nullptr;
+  if (sh.ants > 0 && dof) {
+    // ten_ant.py:822-857 / one_ant.py:371-376: one (pos, vel) pair per (reset env, dof)
+    const float* npos = p.noise_pos ? p.noise_pos + (int64_t)f * p.noise_row_stride : nullptr;
+    const float* nvel = p.noise_vel ? p.noise_vel + (int64_t)f * p.noise_row_stride : nullptr;
+    const int items = count * sh.dofs;
+    for (int it = tid; it < items; it += 1024) {
+      const int i = it / sh.dofs, d = it - i * sh.dofs, j = d & 7;
+      const int e = (int)env_ids[i];
+      float np_, nv_;
+      if (p.noise_mode == 0) {
+        np_ = npos[(int64_t)i * 8 + j];
+        nv_ = nvel[(int64_t)i * 8 + j];
+      } else {  // torch_rand_float(lo, hi) = (hi - lo) * U[0,1) + lo, keyed by env so every ant shares the draw
+        uint4 r = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(p.step + f), (uint32_t)(j >> 1), 0u),
+                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        float up = u01((j & 1) ? r.z : r.x), uv = u01((j & 1) ? r.w : r.y);
+        np_ = fadd(fmul(0.4f, up), -0.2f);
+        nv_ = fadd(fmul(0.2f, uv), -0.1f);
+      }
+      float pos = fadd(p.c.initial_dof_pos[j], np_);
+      pos = fmaxf(fminf(pos, p.c.dof_upper[j]), p.c.dof_lower[j]);  // tensor_clamp = max(min(t, hi), lo)
+      *reinterpret_cast<float2*>(dof + ((int64_t)e * sh.dofs + d) * 2) = make_float2(pos, nv_);
+    }
+  }
+  if (p.task == MMB_TASK_INGENUITY) {
+    if (dof) {  // multi_ingenuity.py:234-241: every env, whenever reset_idx runs
+      for (int it = tid; it < N * 4; it += 1024) {
+        float* d = dof + (int64_t)it * 8;  // 4 dofs x (pos, vel) per helicopter
+        d[3] = -50.0f;
+        d[7] = 50.0f;
+      }
+    }
+    if (p.forces_state) {  // multi_ingenuity.py:243-244
+      const int items = count * 72;
+      for (int it = tid; it < items; it += 1024) {
+        const int i = it / 72, r = it - i * 72;
+        p.forces_state[(int64_t)env_ids[i] * 72 + r] = 0.0f;
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mmb
+
+extern "C" int32_t mmb_reset_compact(const mmb_reset_params* pp, void* stream) {
+  using namespace mmb;
+  if (!pp) return MMB_EINVAL;
+  mmb_reset_params p = *pp;
+  if (p.num_envs <= 0 || p.num_rows <= 0) return MMB_EINVAL;
+  if (p.task < MMB_TASK_TEN_ANT || p.task > MMB_TASK_INGENUITY) return MMB_EINVAL;
+  if ((!p.flags_i64 && !p.flags_u8) || !p.env_ids) return MMB_EINVAL;
+  if (p.task != MMB_TASK_INGENUITY && p.dof_state && p.noise_mode == 0 && (!p.noise_pos || !p.noise_vel)) return MMB_EINVAL;
+  if (p.noise_mode != 0 && p.noise_mode != 1) return MMB_EINVAL;
+  if (p.dof_state && (reinterpret_cast<uintptr_t>(p.dof_state) & 7u)) return MMB_EALIGN;
+  reset_kernel<<<p.num_rows, 1024, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}

@@ -1,0 +1,333 @@
+// storage.cu - rollout-storage kernels: fused add_transitions, reverse-time GAE scans (PPO and MARL
+// with PopArt/ValueNorm denormalisation), advantage statistics + normalisation, device-side
+// get_statistics and the MARL mask logic.
+//
+// Replaces agents/algorithms/rl/ppo/storage.py:32-73, agents/algorithms/marl/utils/separated_buffer.py:
+// 124-168, popart.py:64-75 (denormalize), mappo_trainer.py:189-199, runner.py:229-255.
+//
+// GAE is sequential in t and embarrassingly parallel over envs: one thread per env (or (env, agent)),
+// the [T][N] planes are read as fully coalesced rows, the recurrence is evaluated in the reference's
+// exact op order (bit-identical `returns`), loads of a chunk of steps are issued before the dependent
+// chain so a thread keeps 3 x CHUNK requests in flight.  Sum and sum of squares of the raw advantages
+// are accumulated in fp64 (thread -> warp shuffle -> one atomic per CTA); the caller can all-reduce the
+// three doubles across env shards before mmb_adv_normalize.
+#include "../../include/mmb.h"
+#include "mmb_common.cuh"
+#include "mmb_math.cuh"
+
+namespace mmb {
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of two doubles, result valid in thread 0
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double sa[32], sb[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { sa[wid] = a; sb[wid] = b; }
+  __syncthreads();
+  if (wid == 0) {
+    a = lane < nw ? sa[lane] : 0.0;
+    b = lane < nw ? sb[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RolloutStorage.compute_returns (storage.py:51-65)
+// ------------------------------------------------------------------------------------------------
+constexpr int GAE_CHUNK = 8;
+
+__global__ void __launch_bounds__(256) gae_ppo_kernel(const __grid_constant__ mmb_gae_ppo_params p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = p.num_envs, T = p.num_steps;
+  const float gamma = (float)p.gamma, lam = (float)p.lam;
+  double s1 = 0.0, s2 = 0.0;
+  if (e < N) {
+    float adv = 0.0f;
+    float next_v = __ldg(p.last_values + e);
+    for (int t_hi = T; t_hi > 0; t_hi -= GAE_CHUNK) {
+      const int cnt = t_hi < GAE_CHUNK ? t_hi : GAE_CHUNK;
+      float r[GAE_CHUNK], v[GAE_CHUNK], m[GAE_CHUNK];
+#pragma unroll
+      for (int j = 0; j < GAE_CHUNK; ++j) {
+        if (j < cnt) {
+          const int64_t idx = (int64_t)(t_hi - 1 - j) * N + e;
+          r[j] = __ldg(p.rewards + idx);
+          v[j] = __ldg(p.values + idx);
+          m[j] = fsub(1.0f, (float)__ldg(p.dones + idx));  // next_is_not_terminal = 1.0 - dones.float()
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < GAE_CHUNK; ++j) {
+        if (j < cnt) {
+          const int64_t idx = (int64_t)(t_hi - 1 - j) * N + e;
+          const float mg = fmul(m[j], gamma);
+          const float delta = fsub(fadd(r[j], fmul(mg, next_v)), v[j]);
+          adv = fadd(delta, fmul(fmul(mg, lam), adv));
+          const float ret = fadd(adv, v[j]);
+          p.returns[idx] = ret;
+          const float a = fsub(ret, v[j]);  // self.advantages = self.returns - self.values
+          p.advantages[idx] = a;
+          s1 += (double)a;
+          s2 += (double)a * (double)a;
+          next_v = v[j];
+        }
+      }
+    }
+  }
+  if (p.stats) {
+    block_sum2(s1, s2);
+    if (threadIdx.x == 0) {
+      atomicAdd(p.stats + 1, s1);
+      atomicAdd(p.stats + 2, s2);
+      if (blockIdx.x == 0) atomicAdd(p.stats + 0, (double)N * (double)T);
+    }
+  }
+}
+
+// (adv - mean) / (std_unbiased + eps)
+__global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ adv, int64_t n,
+                                                            const double* __restrict__ stats, float eps) {
+  const double cnt = stats[0], s1 = stats[1], s2 = stats[2];
+  const double mean_d = s1 / cnt;
+  double var_d = (s2 - s1 * mean_d) / (cnt - 1.0);  // torch.std(): unbiased
+  if (var_d < 0.0) var_d = 0.0;
+  const float mean = (float)mean_d;
+  const float denom = fadd((float)sqrt(var_d), eps);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = aligned16(adv) ? (n >> 2) : 0;
+  for (int64_t j = i; j < n4; j += stride) {
+    float4 v = reinterpret_cast<float4*>(adv)[j];
+    v.x = fdiv(fsub(v.x, mean), denom); v.y = fdiv(fsub(v.y, mean), denom);
+    v.z = fdiv(fsub(v.z, mean), denom); v.w = fdiv(fsub(v.w, mean), denom);
+    reinterpret_cast<float4*>(adv)[j] = v;
+  }
+  for (int64_t j = (n4 << 2) + i; j < n; j += stride) adv[j] = fdiv(fsub(adv[j], mean), denom);
+}
+
+// RolloutStorage.get_statistics (storage.py:67-73).  With the last row forced done and the env-major
+// flatten, the trajectory lengths sum to T*N, so the mean length is T*N / (#dones in rows < T-1  +  N).
+__global__ void __launch_bounds__(1024) rollout_statistics_kernel(const uint8_t* __restrict__ dones,
+                                                                   const float* __restrict__ rewards, int T, int N,
+                                                                   float* __restrict__ out2) {
+  double cnt = 0.0, rs = 0.0;
+  const int64_t total = (int64_t)T * N;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    rs += (double)rewards[i];
+    if (i < (int64_t)(T - 1) * N) cnt += dones[i] ? 1.0 : 0.0;
+  }
+  block_sum2(cnt, rs);
+  if (threadIdx.x == 0) {
+    out2[0] = (float)total / (float)(cnt + (double)N);
+    out2[1] = (float)(rs / (double)total);
+  }
+}
+
+// RolloutStorage.add_transitions (storage.py:32-46): nine copies in one launch; blockIdx.y = field
+__global__ void __launch_bounds__(256) rollout_add_kernel(const __grid_constant__ mmb_rollout_add_params p) {
+  const int field = blockIdx.y;
+  const int64_t N = p.num_envs;
+  const float* src = nullptr;
+  float* dst = nullptr;
+  int64_t n = 0;
+  switch (field) {
+    case 0: src = p.observations; dst = p.dst_observations; n = N * p.obs_dim; break;
+    case 1: src = p.states; dst = p.dst_states; n = N * p.states_dim; break;
+    case 2: src = p.actions; dst = p.dst_actions; n = N * p.act_dim; break;
+    case 3: src = p.rewards; dst = p.dst_rewards; n = N; break;
+    case 4: src = p.values; dst = p.dst_values; n = N; break;
+    case 5: src = p.actions_log_prob; dst = p.dst_actions_log_prob; n = N; break;
+    case 6: src = p.mu; dst = p.dst_mu; n = N * p.act_dim; break;
+    case 7: src = p.sigma; dst = p.dst_sigma; n = N * p.act_dim; break;
+    default: break;
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (field == 8) {  // dones int64 -> uint8 (copy_ cast)
+    if (p.dones && p.dst_dones)
+      for (int64_t i = i0; i < N; i += stride) p.dst_dones[i] = (uint8_t)p.dones[i];
+    return;
+  }
+  if (!src || !dst || n == 0) return;
+  if (aligned16(src) && aligned16(dst)) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = i0; i < n4; i += stride) stg4(dst + 4 * i, ldg4(src + 4 * i));
+    for (int64_t i = (n4 << 2) + i0; i < n; i += stride) dst[i] = src[i];
+  } else {
+    for (int64_t i = i0; i < n; i += stride) dst[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SeparatedReplayBuffer.compute_returns (separated_buffer.py:124-168) + advantage prologue
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gae_marl_kernel(const __grid_constant__ mmb_gae_marl_params p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = p.num_envs, T = p.num_steps;
+  const int a = blockIdx.y;
+  const int e = (int)i;
+  double s1 = 0.0, s2 = 0.0;
+  if (e < N) {
+    const float gamma = (float)p.gamma;
+    const float gl = (float)(p.gamma * p.gae_lambda);  // Python float product, then cast by torch
+    float mean = 0.0f, sd = 1.0f;
+    if (p.use_denorm) {
+      mean = __ldg(p.denorm_mean + a);
+      sd = fsqrt(__ldg(p.denorm_var + a));
+    }
+    auto D = [&](float x) { return p.use_denorm ? fadd(fmul(x, sd), mean) : x; };  // popart.py:71
+    const int64_t ro = (int64_t)e * p.rew_e + (int64_t)a * p.rew_a;
+    const int64_t vo = (int64_t)e * p.val_e + (int64_t)a * p.val_a;
+    const int64_t mo = (int64_t)e * p.msk_e + (int64_t)a * p.msk_a;
+    const int64_t bo = (int64_t)e * p.bad_e + (int64_t)a * p.bad_a;
+    const int64_t to = (int64_t)e * p.ret_e + (int64_t)a * p.ret_a;
+    const int64_t ao = (int64_t)e * p.adv_e + (int64_t)a * p.adv_a;
+    const float nv = __ldg(p.next_value + (int64_t)e * p.nv_e + (int64_t)a * p.nv_a);
+    if (p.use_gae) {
+      p.value_preds[(int64_t)T * p.val_t + vo] = nv;  // self.value_preds[-1] = next_value
+      float gae = 0.0f;
+      float v1 = nv;
+      for (int t = T - 1; t >= 0; --t) {
+        const float r = __ldg(p.rewards + (int64_t)t * p.rew_t + ro);
+        const float v0 = p.value_preds[(int64_t)t * p.val_t + vo];
+        const float m1 = __ldg(p.masks + (int64_t)(t + 1) * p.msk_t + mo);
+        const float d0 = D(v0);
+        const float delta = fsub(fadd(r, fmul(fmul(gamma, D(v1)), m1)), d0);
+        gae = fadd(delta, fmul(fmul(gl, m1), gae));
+        if (p.use_proper_time_limits) gae = fmul(gae, __ldg(p.bad_masks + (int64_t)(t + 1) * p.bad_t + bo));
+        const float ret = fadd(gae, d0);
+        p.returns[(int64_t)t * p.ret_t + to] = ret;
+        if (p.advantages) {
+          const float adv = fsub(ret, d0);  // mappo_trainer.py:190-192
+          p.advantages[(int64_t)t * p.adv_t + ao] = adv;
+          s1 += (double)adv;
+          s2 += (double)adv * (double)adv;
+        }
+        v1 = v0;
+      }
+    } else {
+      p.returns[(int64_t)T * p.ret_t + to] = nv;  // self.returns[-1] = next_value
+      float r1 = nv;
+      for (int t = T - 1; t >= 0; --t) {
+        const float r = __ldg(p.rewards + (int64_t)t * p.rew_t + ro);
+        const float m1 = __ldg(p.masks + (int64_t)(t + 1) * p.msk_t + mo);
+        const float v0 = p.value_preds[(int64_t)t * p.val_t + vo];
+        float ret;
+        if (p.use_proper_time_limits) {
+          const float b1 = __ldg(p.bad_masks + (int64_t)(t + 1) * p.bad_t + bo);
+          const float vp = (p.use_popart && p.use_denorm) ? D(v0) : v0;
+          ret = fadd(fmul(fadd(fmul(fmul(r1, gamma), m1), r), b1), fmul(fsub(1.0f, b1), vp));
+        } else {
+          ret = fadd(fmul(fmul(r1, gamma), m1), r);
+        }
+        p.returns[(int64_t)t * p.ret_t + to] = ret;
+        if (p.advantages) {
+          const float adv = fsub(ret, D(v0));
+          p.advantages[(int64_t)t * p.adv_t + ao] = adv;
+          s1 += (double)adv;
+          s2 += (double)adv * (double)adv;
+        }
+        r1 = ret;
+      }
+    }
+  }
+  if (p.stats && p.advantages) {
+    block_sum2(s1, s2);
+    if (threadIdx.x == 0) {
+      atomicAdd(p.stats + 3 * a + 1, s1);
+      atomicAdd(p.stats + 3 * a + 2, s2);
+      if (blockIdx.x == 0) atomicAdd(p.stats + 3 * a + 0, (double)N * (double)T);
+    }
+  }
+}
+
+// Runner.insert (runner.py:229-255)
+__global__ void marl_masks_kernel(const int64_t* __restrict__ dones, int N, int A, float* masks, int64_t m_e, int64_t m_a,
+                                  float* active, int64_t am_e, int64_t am_a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  bool all_done = true;
+  for (int a = 0; a < A; ++a) all_done = all_done && (dones[(int64_t)e * A + a] != 0);
+  for (int a = 0; a < A; ++a) {
+    const bool d = dones[(int64_t)e * A + a] != 0;
+    if (masks) masks[(int64_t)e * m_e + (int64_t)a * m_a] = all_done ? 0.0f : 1.0f;
+    if (active) active[(int64_t)e * am_e + (int64_t)a * am_a] = (d && !all_done) ? 0.0f : 1.0f;
+  }
+}
+
+}  // namespace
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int32_t mmb_gae_ppo(const mmb_gae_ppo_params* pp, void* stream) {
+  if (!pp) return MMB_EINVAL;
+  mmb_gae_ppo_params p = *pp;
+  if (p.num_envs <= 0 || p.num_steps <= 0) return MMB_EINVAL;
+  if (!p.rewards || !p.values || !p.dones || !p.last_values || !p.returns || !p.advantages) return MMB_EINVAL;
+  gae_ppo_kernel<<<(p.num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_adv_normalize(float* advantages, int64_t n, const double* stats, float eps, void* stream) {
+  if (!advantages || !stats || n <= 0) return MMB_EINVAL;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_rollout_statistics(const uint8_t* dones, const float* rewards, int32_t num_steps,
+                                          int32_t num_envs, float* out2, void* stream) {
+  if (!dones || !rewards || !out2 || num_steps <= 0 || num_envs <= 0) return MMB_EINVAL;
+  rollout_statistics_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dones, rewards, num_steps, num_envs, out2);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_rollout_add(const mmb_rollout_add_params* pp, void* stream) {
+  if (!pp) return MMB_EINVAL;
+  mmb_rollout_add_params p = *pp;
+  if (p.num_envs <= 0 || p.obs_dim < 0 || p.states_dim < 0 || p.act_dim < 0) return MMB_EINVAL;
+  int64_t maxn = (int64_t)p.num_envs * (p.obs_dim > p.act_dim ? p.obs_dim : p.act_dim);
+  if (maxn < p.num_envs) maxn = p.num_envs;
+  int64_t bx = (maxn / 4 + 255) / 256;
+  if (bx < 1) bx = 1;
+  if (bx > 148 * 8) bx = 148 * 8;
+  rollout_add_kernel<<<dim3((unsigned)bx, 9), 256, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_gae_marl(const mmb_gae_marl_params* pp, void* stream) {
+  if (!pp) return MMB_EINVAL;
+  mmb_gae_marl_params p = *pp;
+  if (p.num_envs <= 0 || p.num_steps <= 0 || p.num_agents <= 0 || p.num_agents > 65535) return MMB_EINVAL;
+  if (!p.rewards || !p.value_preds || !p.masks || !p.next_value || !p.returns) return MMB_EINVAL;
+  if (p.use_proper_time_limits && !p.bad_masks) return MMB_EINVAL;
+  if (p.use_denorm && (!p.denorm_mean || !p.denorm_var)) return MMB_EINVAL;
+  gae_marl_kernel<<<dim3((p.num_envs + 255) / 256, p.num_agents), 256, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_marl_masks(const int64_t* dones, int32_t num_envs, int32_t num_agents, float* masks, int64_t m_e,
+                                  int64_t m_a, float* active_masks, int64_t am_e, int64_t am_a, void* stream) {
+  if (!dones || num_envs <= 0 || num_agents <= 0) return MMB_EINVAL;
+  marl_masks_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dones, num_envs, num_agents, masks, m_e,
+                                                                             m_a, active_masks, am_e, am_a);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}

@@ -1,0 +1,423 @@
+// ten_ant.cu - fused TenAnt env-step kernel for sm_100a.
+//
+// One CTA = one tile of EPT environments of one frame t (grid = tiles x T): every (tile, t) unit is
+// independent because the carry of step t (pos_before / goal_before) is a pure function of frame
+// t-1, so the horizon-batched launch exposes T*N*10 ant-threads instead of N*10.
+// The only sequential-in-t state, progress_buf / reset_buf, is a 1-byte-per-env-step chain that
+// does not feed obs or reward; it is resolved inline when T == 1 and by ten_ant_chain_kernel
+// otherwise.
+//
+// Data movement per unit (all contiguous because the Isaac layout is env-major):
+//   root tile   EPT*143 floats  global -> smem, 128-bit loads (rows are 52 B: not vector-addressable per ant)
+//   dof         16 floats per ant thread, 4 x LDG.128, consecutive threads -> consecutive 64 B
+//   actions      8 floats per ant thread, 2 x LDG.128
+//   obs tile    EPT*388 floats  smem -> global, 128-bit stores (clamped and/or raw)
+//   forces       8 floats per ant thread, 2 x STG.128
+// Arithmetic: mmb_math.cuh (IEEE round-to-nearest per op in the reference's order).
+//
+// Replaces: ten_ant.py:886-891 (forces), :712-808 + jit :1304-1393 (observations, box goals),
+// :635-710 + jit :988-1301 (reward/reset), :894-926 (progress, carry), vec_task.py:126-131 /
+// multi_vec_task.py:94-144 (clamps and per-agent split).
+#include "../../include/mmb.h"
+#include "mmb_common.cuh"
+#include "mmb_math.cuh"
+
+namespace mmb {
+namespace {
+
+constexpr int A = 10;
+constexpr int ROOT_ENV = 143;  // 11 rows x 13
+constexpr int OBS_ENV = 388;
+constexpr int BOX_W = 12;
+constexpr int PART_W = 6;
+
+template <int EPT>
+struct TenAntSmem {
+  static constexpr int kRoot = EPT * ROOT_ENV;
+  static constexpr int kObs = EPT * OBS_ENV;
+  static constexpr int kBox = EPT * BOX_W;
+  static constexpr int kPart = EPT * A * PART_W;
+  static constexpr int kFloats = kRoot + kObs + kBox + kPart;
+  static constexpr int kBytes = kFloats * 4;
+};
+
+// goal offsets c_j of ten_ant.py:1365-1390 and box_targets_k of ten_ant.py:172-181
+__device__ __forceinline__ float goal_offset(int k) { return 1.5f + 3.0f * (float)(k >> 1); }
+
+// compute_box_angle + (sin, -cos) of compute_box_pos (ten_ant.py:935-947, 1353-1364)
+__device__ __forceinline__ void box_dir(float qz, float qw, float& s, float& c) {
+  float y = fmul(fmul(2.0f, qw), qz);
+  float x = fsub(1.0f, fmul(fmul(2.0f, qz), qz));
+  float ang = atanf(fdiv(y, x));
+  s = sinf(ang);
+  c = -cosf(ang);
+}
+
+__device__ __forceinline__ void goal_of(int k, float bx, float by, float g0x, float g0y, float& gx, float& gy) {
+  float c = goal_offset(k);
+  if ((k & 1) == 0) {
+    gx = fadd(bx, fmul(c, g0x));
+    gy = fadd(by, fmul(c, g0y));
+  } else {
+    gx = fsub(bx, fmul(c, g0x));
+    gy = fsub(by, fmul(c, g0y));
+  }
+}
+
+template <int FLAVOR, int EPT>
+__global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__ mmb_ten_ant_params p) {
+  constexpr int NT = EPT * A;
+  extern __shared__ __align__(16) float smem[];
+  float* root_s = smem;
+  float* obs_s = root_s + TenAntSmem<EPT>::kRoot;
+  float* box_s = obs_s + TenAntSmem<EPT>::kObs;
+  float* part_s = box_s + TenAntSmem<EPT>::kBox;
+
+  const int tid = threadIdx.x;
+  const int t = blockIdx.y;
+  const int N = p.num_envs;
+  const int T = p.num_frames;
+  const int e0 = blockIdx.x * EPT;
+  const int ne = min(EPT, N - e0);
+  const mmb_ant_consts& c = p.c;
+
+  const float* root_t = p.root + (int64_t)t * p.root_frame_stride;
+  tile_load(root_s, root_t + (int64_t)e0 * ROOT_ENV, ne * ROOT_ENV, tid, NT);
+
+  const int el = tid / A, k = tid - el * A;
+  const int e = e0 + el;
+  const bool active = el < ne;
+
+  float dps[8], dvs[8], act[8];
+  float pbx = 0.f, pby = 0.f, gbx = 0.f, gby = 0.f;
+  if (active) {
+    const float* d = p.dof + (int64_t)t * p.dof_frame_stride + ((int64_t)e * 80 + 8 * k) * 2;
+    float raw[16];
+    if (aligned16(d)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 v = ldg4(d + 4 * j);
+        raw[4 * j] = v.x; raw[4 * j + 1] = v.y; raw[4 * j + 2] = v.z; raw[4 * j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) raw[j] = __ldg(d + j);
+    }
+    const float* a = p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
+    if (aligned16(a)) {
+      float4 v0 = ldg4(a), v1 = ldg4(a + 4);
+      act[0] = v0.x; act[1] = v0.y; act[2] = v0.z; act[3] = v0.w;
+      act[4] = v1.x; act[5] = v1.y; act[6] = v1.z; act[7] = v1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) act[j] = __ldg(a + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      act[j] = clampf(act[j], -p.clip_actions, p.clip_actions);     // vec_task.py:127
+      dps[j] = unscale(raw[2 * j], c.dof_lower[j], c.dof_upper[j]);  // ten_ant.py:1333
+      dvs[j] = fmul(raw[2 * j + 1], c.dof_vel_scale);                // ten_ant.py:1347
+    }
+    if (p.forces) {  // ten_ant.py:889: actions * joint_gears * power_scale
+      float* f = p.forces + (int64_t)t * p.forces_frame_stride + (int64_t)e * 80 + 8 * k;
+      float fo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fo[j] = fmul(fmul(act[j], c.joint_gears[j]), c.power_scale);
+      if (aligned16(f)) {
+        stg4(f, make_float4(fo[0], fo[1], fo[2], fo[3]));
+        stg4(f + 4, make_float4(fo[4], fo[5], fo[6], fo[7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fo[j];
+      }
+    }
+    if (t == 0) {
+      const float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
+      const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+      pbx = __ldg(pb); pby = __ldg(pb + 1);
+      gbx = __ldg(gb); gby = __ldg(gb + 1);
+    } else {  // carry of step t = ant xy of frame t-1 (ten_ant.py:905-914)
+      const float* rp = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)e * 11 + k) * 13;
+      pbx = __ldg(rp); pby = __ldg(rp + 1);
+    }
+  }
+  __syncthreads();
+
+  // ---- box phase: goal directions of frame t (and of frame t-1 when it is the carry source) ----
+  if (tid < 2 * EPT) {
+    const int which = tid / EPT, bl = tid - which * EPT;
+    if (bl < ne) {
+      if (which == 0) {
+        const float* b = root_s + bl * ROOT_ENV + 10 * 13;
+        float s, cs;
+        box_dir(b[5], b[6], s, cs);
+        float* bo = box_s + bl * BOX_W;
+        bo[0] = s; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
+        bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
+        float* tail = obs_s + bl * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
+        tail[0] = b[0]; tail[1] = b[1]; tail[2] = b[3]; tail[3] = b[4]; tail[4] = b[5]; tail[5] = b[6];
+        tail[6] = 0.0f; tail[7] = 0.0f;
+      } else if (t > 0) {
+        const float* b = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)(e0 + bl) * 11 + 10) * 13;
+        float s, cs;
+        box_dir(__ldg(b + 5), __ldg(b + 6), s, cs);
+        float* bo = box_s + bl * BOX_W;
+        bo[8] = s; bo[9] = cs; bo[10] = __ldg(b); bo[11] = __ldg(b + 1);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- ant phase ----
+  if (active) {
+    const float* r = root_s + el * ROOT_ENV + k * 13;
+    f3 pos = {r[0], r[1], r[2]};
+    f4 q = {r[3], r[4], r[5], r[6]};
+    f3 v = {r[7], r[8], r[9]};
+    f3 w = {r[10], r[11], r[12]};
+    AntCore o = ant_core<FLAVOR>(pos, q, v, w, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
+    float* ob = obs_s + el * OBS_ENV + k * 38;
+    ob[0] = pos.x; ob[1] = pos.y; ob[2] = pos.z;
+    ob[3] = o.vel_loc.x; ob[4] = o.vel_loc.y; ob[5] = o.vel_loc.z;
+    ob[6] = o.angvel_loc.x; ob[7] = o.angvel_loc.y; ob[8] = o.angvel_loc.z;
+    ob[9] = o.yaw; ob[10] = o.roll; ob[11] = o.angle_to_target; ob[12] = o.up_proj; ob[13] = o.heading_proj;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ob[14 + j] = dps[j]; ob[22 + j] = dvs[j]; ob[30 + j] = act[j]; }
+
+    const float* bo = box_s + el * BOX_W;
+    float gx, gy;
+    goal_of(k, bo[2], bo[3], bo[0], bo[1], gx, gy);
+    if (t > 0) goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
+
+    // ten_ant.py:1073-1081 for ant k
+    float d_now = l2_dist2(pos.x, pos.y, gx, gy);
+    float push = (d_now < 1.5f) ? 0.0f : 1.0f;
+    float ant_dist = fsub(l2_dist2(pbx, pby, gbx, gby), d_now);
+    float adr = fmul(fmul(c.ant_dist_reward_scale, ant_dist), push);
+    float bty = (k & 1) ? goal_offset(k) : -goal_offset(k);
+    float gdb = l2_dist2(0.0f, bty, gbx, gby);
+    float gd = l2_dist2(0.0f, bty, gx, gy);
+    bool arrive = gd < 0.5f;
+    float gdr = fmul(c.goal_dist_reward_scale, fsub(gdb, gd));
+    float up = (o.up_proj > 0.93f) ? fadd(0.0f, c.up_weight) : 0.0f;  // ten_ant.py:1187
+    float el8[8];
+    int lim = 0;
+    float asq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      el8[j] = fabsf(fmul(act[j], dvs[j]));  // ten_ant.py:1242
+      lim += (dps[j] > 0.99f) ? 1 : 0;       // ten_ant.py:1243
+      asq = fadd(asq, fmul(act[j], act[j]));
+    }
+    float elec = sum8<FLAVOR>(el8);
+    bool fallen = pos.z < c.termination_height;
+    float* pt = part_s + (el * A + k) * PART_W;
+    pt[0] = adr; pt[1] = gdr; pt[2] = up; pt[3] = elec; pt[4] = asq;
+    pt[5] = __int_as_float(lim | (arrive ? 0x100 : 0) | (fallen ? 0x200 : 0));
+
+    if (T == 1) {  // carry out (ten_ant.py:905-925); T > 1: ten_ant_load_carry_kernel on the last frame
+      float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
+      float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+      pb[0] = pos.x; pb[1] = pos.y; gb[0] = gx; gb[1] = gy;
+    }
+  }
+  __syncthreads();
+
+  // ---- per-env finish: ordered sums over the ten ants (ten_ant.py:1173-1301) ----
+  if (tid < ne) {
+    const int en = e0 + tid;
+    const float* pt = part_s + tid * A * PART_W;
+    float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
+    int fl = __float_as_int(pt[5]);
+    int lim = fl & 0xff, n_arrive = (fl >> 8) & 1;
+    bool fallen = (fl & 0x200) != 0;
+#pragma unroll
+    for (int kk = 1; kk < A; ++kk) {
+      const float* q = pt + kk * PART_W;
+      adr = fadd(adr, q[0]); gdr = fadd(gdr, q[1]); up = fadd(up, q[2]); elec = fadd(elec, q[3]); asq = fadd(asq, q[4]);
+      int f2 = __float_as_int(q[5]);
+      lim += f2 & 0xff; n_arrive += (f2 >> 8) & 1; fallen = fallen || (f2 & 0x200);
+    }
+    const float* bo = box_s + tid * BOX_W;
+    float quat_dist = bo[4];
+    float total = fadd(5.0f, fmul(up, 10.0f));
+    total = fadd(total, fmul(c.quat_reward_scale, quat_dist));
+    total = fadd(total, adr);
+    total = fadd(total, gdr);
+    total = fadd(total, (float)(2 * n_arrive));
+    total = fadd(total, (quat_dist > 0.9f && n_arrive == A) ? 100.0f : 0.0f);
+    total = fsub(total, fmul(c.actions_cost, asq));
+    total = fsub(total, fmul(c.energy_cost, elec));
+    total = fsub(total, fmul((float)lim, c.joints_at_limit_cost));
+    if (fallen) total = c.death_cost;
+    if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = total;
+    if (T == 1) {
+      p.box_before[(int64_t)en * 2] = bo[2];
+      p.box_before[(int64_t)en * 2 + 1] = bo[3];
+      // ten_ant.py:896-901 (progress += 1; reset_idx zeroes progress/reset of flagged envs) + :1296-1299
+      int64_t prog = p.progress_buf[en] + 1;
+      if (p.reset_buf[en] != 0) prog = 0;
+      int64_t rs = fallen ? 1 : 0;
+      if ((float)prog >= (float)((double)c.max_episode_length - 1.0)) rs = 1;
+      p.progress_buf[en] = prog;
+      p.reset_buf[en] = rs;
+      if (p.dones_i64) p.dones_i64[en] = rs;
+      if (p.dones_u8) p.dones_u8[en] = (uint8_t)rs;
+    } else {  // `fallen` only; ten_ant_chain_kernel finishes the flags
+      if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + en] = fallen ? 1 : 0;
+      else p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + en] = fallen ? 1 : 0;
+    }
+  }
+
+  // ---- obs tile out ----
+  const float clip = p.clip_obs;
+  if (p.obs_raw) {
+    float* g = p.obs_raw + (int64_t)t * p.obs_raw_frame_stride + (int64_t)e0 * OBS_ENV;
+    const int n = ne * OBS_ENV;
+    if (aligned16(g)) {
+      for (int i = tid; i < (n >> 2); i += NT) stg4(g + 4 * i, reinterpret_cast<const float4*>(obs_s)[i]);
+    } else {
+      for (int i = tid; i < n; i += NT) g[i] = obs_s[i];
+    }
+  }
+  if (p.obs_layout == 0) {
+    if (p.obs) {
+      float* g = p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * OBS_ENV;
+      const int n = ne * OBS_ENV;
+      if (aligned16(g)) {
+        for (int i = tid; i < (n >> 2); i += NT) {
+          float4 v = reinterpret_cast<const float4*>(obs_s)[i];
+          v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip);
+          v.z = clampf(v.z, -clip, clip); v.w = clampf(v.w, -clip, clip);
+          stg4(g + 4 * i, v);
+        }
+      } else {
+        for (int i = tid; i < n; i += NT) g[i] = clampf(obs_s[i], -clip, clip);
+      }
+    }
+  } else {
+    if (p.share_obs) {  // multi_vec_task.py:118: clamped 388-wide state, stored once per env
+      float* g = p.share_obs + (int64_t)t * p.share_obs_frame_stride + (int64_t)e0 * OBS_ENV;
+      const int n = ne * OBS_ENV;
+      if (aligned16(g)) {
+        for (int i = tid; i < (n >> 2); i += NT) {
+          float4 v = reinterpret_cast<const float4*>(obs_s)[i];
+          v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip);
+          v.z = clampf(v.z, -clip, clip); v.w = clampf(v.w, -clip, clip);
+          stg4(g + 4 * i, v);
+        }
+      } else {
+        for (int i = tid; i < n; i += NT) g[i] = clampf(obs_s[i], -clip, clip);
+      }
+    }
+    if (p.obs) {  // multi_vec_task.py:105-116: per agent cat(own 38, tail 8) -> [N][10][46]
+      float* g = p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * 460;
+      const int n2 = ne * 230;  // float2 granules: 46 and 38 are even, so a pair never straddles a boundary
+      const bool al8 = (reinterpret_cast<uintptr_t>(g) & 7u) == 0;
+      for (int i = tid; i < n2; i += NT) {
+        int er = i / 230, r2 = i - er * 230;
+        int a = r2 / 23, c2 = r2 - a * 23;
+        int src = er * OBS_ENV + (c2 < 19 ? a * 38 + 2 * c2 : 380 + 2 * (c2 - 19));
+        float2 v = *reinterpret_cast<const float2*>(obs_s + src);
+        v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip);
+        if (al8) *reinterpret_cast<float2*>(g + 2 * i) = v;
+        else { g[2 * i] = v.x; g[2 * i + 1] = v.y; }
+      }
+    }
+  }
+}
+
+// progress / reset chain over the T frames of a horizon-batched launch (ten_ant.py:896-901,1296-1299)
+__global__ void ten_ant_chain_kernel(const __grid_constant__ mmb_ten_ant_params p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.num_envs) return;
+  int64_t prog = p.progress_buf[e];
+  bool flag = p.reset_buf[e] != 0;
+  const float thr = (float)((double)p.c.max_episode_length - 1.0);
+  for (int t = 0; t < p.num_frames; ++t) {
+    prog = flag ? 0 : prog + 1;
+    bool fallen = p.dones_u8 ? (p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + e] != 0)
+                             : (p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + e] != 0);
+    flag = fallen || ((float)prog >= thr);
+    if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + e] = flag ? 1 : 0;
+    if (p.dones_i64) p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + e] = flag ? 1 : 0;
+  }
+  p.progress_buf[e] = prog;
+  p.reset_buf[e] = flag ? 1 : 0;
+}
+
+// ten_ant.py:870-882: carry from a root tensor
+__global__ void ten_ant_load_carry_kernel(const float* __restrict__ root, int N, float* pos_before, float* goal_before,
+                                          float* box_before) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * A) return;
+  const int e = i / A, k = i - e * A;
+  const float* r = root + ((int64_t)e * 11 + k) * 13;
+  const float* b = root + ((int64_t)e * 11 + 10) * 13;
+  float s, cs, gx, gy;
+  box_dir(b[5], b[6], s, cs);
+  goal_of(k, b[0], b[1], s, cs, gx, gy);
+  pos_before[2 * (int64_t)i] = r[0]; pos_before[2 * (int64_t)i + 1] = r[1];
+  goal_before[2 * (int64_t)i] = gx; goal_before[2 * (int64_t)i + 1] = gy;
+  if (k == 0) { box_before[2 * (int64_t)e] = b[0]; box_before[2 * (int64_t)e + 1] = b[1]; }
+}
+
+template <int FLAVOR, int EPT>
+int32_t launch_ten_ant(const mmb_ten_ant_params& p, cudaStream_t st) {
+  auto kern = ten_ant_kernel<FLAVOR, EPT>;
+  static bool attr_done[MMB_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < MMB_MAX_DEVICES && !attr_done[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TenAntSmem<EPT>::kBytes) != cudaSuccess)
+      return MMB_ECUDA;
+    attr_done[dev] = true;
+  }
+  dim3 grid((p.num_envs + EPT - 1) / EPT, p.num_frames);
+  kern<<<grid, EPT * A, TenAntSmem<EPT>::kBytes, st>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+}  // namespace
+}  // namespace mmb
+
+extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) {
+  using namespace mmb;
+  if (!pp) return MMB_EINVAL;
+  mmb_ten_ant_params p = *pp;
+  if (p.num_envs <= 0 || p.num_frames <= 0) return MMB_EINVAL;
+  if (!p.root || !p.dof || !p.actions || !p.pos_before || !p.goal_before || !p.box_before || !p.progress_buf ||
+      !p.reset_buf)
+    return MMB_EINVAL;
+  if (p.num_frames > 65535) return MMB_EUNSUPPORTED;
+  if (p.num_frames > 1 && !p.dones_u8 && !p.dones_i64) return MMB_EINVAL;  // the chain needs a [T][N] plane
+  if (p.obs_layout != 0 && p.obs_layout != 1) return MMB_EINVAL;
+  if (p.flavor != MMB_FLAVOR_CUDA && p.flavor != MMB_FLAVOR_CPU) return MMB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, MMB_TEN_ANT_EPT>(p, st)
+                                             : launch_ten_ant<FLAVOR_CPU, MMB_TEN_ANT_EPT>(p, st);
+  if (rc != MMB_OK) return rc;
+  if (p.num_frames > 1) {
+    ten_ant_chain_kernel<<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
+    // carry after the last frame = f(frame T-1) (a (tile, T-1) CTA must not write what a (tile, 0) CTA reads)
+    const float* last = p.root + (int64_t)(p.num_frames - 1) * p.root_frame_stride;
+    ten_ant_load_carry_kernel<<<(p.num_envs * A + 255) / 256, 256, 0, st>>>(last, p.num_envs, p.pos_before,
+                                                                             p.goal_before, p.box_before);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
+  }
+  return MMB_OK;
+}
+
+extern "C" int32_t mmb_ten_ant_load_carry(const float* root, int32_t num_envs, float* pos_before, float* goal_before,
+                                          float* box_before, void* stream) {
+  using namespace mmb;
+  if (!root || !pos_before || !goal_before || !box_before || num_envs <= 0) return MMB_EINVAL;
+  ten_ant_load_carry_kernel<<<(num_envs * A + 255) / 256, 256, 0, (cudaStream_t)stream>>>(root, num_envs, pos_before,
+                                                                                           goal_before, box_before);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}

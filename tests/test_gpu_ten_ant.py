@@ -1,0 +1,238 @@
+"""GPU parity of the TenAnt path (mmb_ten_ant_step + mmb_reset_compact through the host classes).
+
+Oracles: the committed golden vectors (made from the reference itself, tests/golden/make_golden.py) and
+oracle/ (CPU restatement; also run on CUDA tensors as the torch-eager-on-GPU tier for the fp32-ill-conditioned
+reward, SURVEY.md finding 11).  Integers / indices / dones are bit-exact; floats |d| <= 1e-5*|ref| + 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close_obs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_COLS_38 = (9, 10, 11)  # yaw, roll, angle_to_target (compared modulo 2*pi)
+
+
+def _angle_cols_388():
+    return tuple(38 * k + c for k in range(10) for c in ANGLE_COLS_38)
+
+
+def _make(N, frames, flavor, multi, dev, keep=None):
+    from massive_marl_benchmark_b200 import _lib as L
+    from massive_marl_benchmark_b200.providers import ReplayProvider
+    from massive_marl_benchmark_b200.tasks import TenAnt
+    cfg = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1}
+    prov = ReplayProvider({"root": frames["root"], "dof": frames["dof"]}, device=dev, loop=False)
+    return TenAnt(cfg, None, None, "cuda", 0, True, multi, provider=prov,
+                  flavor=L.FLAVOR_CPU if flavor == "cpu" else L.FLAVOR_CUDA)
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_ten_ant_steps_match_reference_golden(cuda_device, multi):
+    from massive_marl_benchmark_b200.vec_task import MultiVecTaskPython, VecTaskPython
+    g = load_golden("ten_ant_n37")
+    F, N = g["rew"].shape
+    dev = cuda_device
+    task = _make(N, g, "cpu", multi, dev)
+    task.progress_buf.copy_(g["progress0"].to(dev))
+    env = MultiVecTaskPython(task, dev) if multi else VecTaskPython(task, dev, clip_observations=7.0)
+    worst_rew = 0.0
+    for t in range(F):
+        task.reset_noise = (g["noise_pos"][t].to(dev), g["noise_vel"][t].to(dev))
+        a = g["actions"][t].to(dev)
+        n_res = int(g["n_reset"][t])
+        if multi:
+            obs_all, state_all, rew_all, done_all, info_all, _ = env.step([a[:, 8 * k:8 * k + 8] for k in range(10)])
+        else:
+            obs, rew, done, info = env.step(a)
+        torch.cuda.synchronize()
+        # integers: exact
+        assert torch.equal(task.reset_buf.cpu(), g["reset"][t]), "reset_buf t=%d" % t
+        assert torch.equal(task.progress_buf.cpu(), g["progress"][t]), "progress_buf t=%d" % t
+        assert int(task.reset_count.item()) == n_res
+        assert torch.equal(task.env_ids[:n_res].cpu(), g["env_ids"][t][:n_res])
+        assert torch.equal(task.ant_box_indices[:11 * n_res].cpu(), g["ant_box_indices"][t][:11 * n_res])
+        assert torch.equal(task.ant_indices[:10 * n_res].cpu(), g["ant_indices"][t][:10 * n_res])
+        # DOF re-randomisation (given the noise rows): rows of the reset envs, bit-exact
+        ids = g["env_ids"][t][:n_res]
+        if n_res:
+            got = task.dof_reset_staging.view(N, 160).cpu()[ids]
+            want = g["dof_pushed"][t].view(N, 160)[ids]
+            assert torch.equal(got, want), "dof rewrite t=%d" % t
+        # floats
+        assert_close_obs(task.obs_buf, g["obs"][t], angle_cols=_angle_cols_388(), what="obs_buf t=%d" % t)
+        assert torch.equal(task.forces.cpu(), g["forces"][t]), "forces t=%d" % t
+        clamped = torch.clamp(g["obs"][t], -7.0, 7.0)
+        if multi:
+            assert obs_all.shape == (N, 10, 46) and state_all.shape == (N, 10, 388)
+            assert rew_all.shape == (N, 10, 1) and done_all.shape == (N, 10)
+            ac = tuple(46 * k + c for k in range(10) for c in ANGLE_COLS_38)
+            assert_close_obs(obs_all.reshape(N, 460), g["obs_all"][t].reshape(N, 460), angle_cols=ac, what="obs_all")
+            assert_close_obs(state_all[:, 3], clamped, angle_cols=_angle_cols_388(), what="state_all")
+            assert torch.equal(done_all.cpu(), g["done_all"][t])
+            rew = rew_all[:, 0, 0]
+        else:
+            assert_close_obs(obs, clamped, angle_cols=_angle_cols_388(), what="clamped obs")
+            assert torch.equal(done.cpu(), g["reset"][t])
+        # reward: gate on death cost / structure exactly, report conditioning-limited error vs the CPU oracle
+        ref = g["rew"][t]
+        dead = ref == -2.0
+        assert torch.equal((rew.cpu() == -2.0), dead)
+        rel = ((rew.cpu() - ref).abs() / ref.abs().clamp(min=1e-6))[~dead]
+        worst_rew = max(worst_rew, float(rel.max()) if rel.numel() else 0.0)
+        assert float(rel.max()) < 2e-3, "reward vs CPU oracle t=%d: %g" % (t, float(rel.max()))
+    print("TenAnt reward max rel err vs CPU-torch reference (conditioning-limited, finding 11): %.3g" % worst_rew)
+
+
+def test_ten_ant_bitexact_vs_torch_eager_on_gpu(cuda_device):
+    """Second oracle tier: the oracle restatement run on CUDA tensors (torch eager, same libdevice).  With
+    MMB_FLAVOR_CUDA the kernel replays torch-CUDA's rounding sequence: rewards within 1e-5 relative."""
+    from oracle.task_oracle import TenAntOracle
+    from massive_marl_benchmark_b200 import synthetic
+    dev = cuda_device
+    N, F = 1000, 6
+    fr = synthetic.ten_ant_frames(N, F, seed=77, fall_prob=0.002)
+    npos, nvel = synthetic.reset_noise(N, F, seed=78)
+    task = _make(N, fr, "cuda", False, dev)
+    orc = TenAntOracle(N, device="cuda")
+    n_exact = n_tot = 0
+    for t in range(F):
+        a = torch.clamp(fr["actions"][t].to(dev) * 1.1, -1, 1)
+        task.reset_noise = (npos[t].to(dev), nvel[t].to(dev))
+        task.step(a)
+        orc.step(a, fr["root"][t].to(dev), fr["dof"][t].to(dev), noise=(npos[t].to(dev), nvel[t].to(dev)))
+        torch.cuda.synchronize()
+        assert torch.equal(task.reset_buf, orc.reset_buf)
+        assert torch.equal(task.progress_buf, orc.progress_buf)
+        assert_close_obs(task.obs_buf, orc.obs_buf, angle_cols=_angle_cols_388(), what="obs vs eager t=%d" % t)
+        rel = (task.rew_buf - orc.rew_buf).abs() / orc.rew_buf.abs().clamp(min=1e-6)
+        assert float(rel.max()) <= 1e-5, "reward vs torch-eager-GPU t=%d: %g" % (t, float(rel.max()))
+        n_exact += int((task.rew_buf == orc.rew_buf).sum())
+        n_tot += N
+    print("TenAnt rewards bit-identical to torch-eager-GPU: %d / %d" % (n_exact, n_tot))
+
+
+def test_ten_ant_replay_equals_stepwise(cuda_device):
+    """Horizon-batched launch (T frames, one kernel) == T single-step launches, bit for bit."""
+    from massive_marl_benchmark_b200 import synthetic
+    from massive_marl_benchmark_b200.tasks import reset_replay
+    dev = cuda_device
+    N, T = 333, 7
+    fr = synthetic.ten_ant_frames(N, T, seed=5, fall_prob=0.01)
+    fr_dev = {k: v.to(dev) for k, v in fr.items()}
+    a_dev = fr_dev["actions"]
+    step = _make(N, fr, "cuda", False, dev)
+    step.clip_actions, step.clip_obs = 1.0, 5.0
+    prog0 = torch.randint(0, 1000, (N,), device=dev)
+    step.progress_buf.copy_(prog0)
+    obs_s, rew_s, done_s, raw_s = [], [], [], []
+    for t in range(T):
+        step.step(a_dev[t])
+        obs_s.append(step.obs_clamped.clone()); rew_s.append(step.rew_buf.clone()); done_s.append(step.reset_buf.clone())
+        raw_s.append(step.obs_buf.clone())
+    rep = _make(N, fr, "cuda", False, dev)
+    rep.clip_actions, rep.clip_obs = 1.0, 5.0
+    rep.progress_buf.copy_(prog0)
+    obs = torch.zeros(T, N, 388, device=dev); rew = torch.zeros(T, N, device=dev)
+    d8 = torch.zeros(T, N, device=dev, dtype=torch.uint8); d64 = torch.zeros(T, N, device=dev, dtype=torch.long)
+    forces = torch.zeros(T, N, 80, device=dev); raw = torch.zeros(T, N, 388, device=dev)
+    rep.replay(fr_dev, a_dev, obs, rew, d8, d64, forces, obs_raw_out=raw)
+    torch.cuda.synchronize()
+    assert torch.equal(obs, torch.stack(obs_s)) and torch.equal(raw, torch.stack(raw_s))
+    assert torch.equal(rew, torch.stack(rew_s))
+    assert torch.equal(d64, torch.stack(done_s)) and torch.equal(d8.long(), d64)
+    assert torch.equal(rep.progress_buf, step.progress_buf) and torch.equal(rep.reset_buf, step.reset_buf)
+    assert torch.equal(rep.pos_before, step.pos_before) and torch.equal(rep.goal_before, step.goal_before)
+    assert torch.equal(rep.box_before, step.box_before)
+    # batched reset compaction over the emitted flags == nonzero() per row
+    env_ids, ia, ib, counts = reset_replay(rep, d8)
+    for t in range(T):
+        nz = d64[t].nonzero().flatten()
+        assert int(counts[t]) == len(nz) and torch.equal(env_ids[t, :len(nz)], nz)
+        want = (11 * nz[:, None] + torch.arange(11, device=dev)[None]).flatten().int()
+        assert torch.equal(ia[t, :11 * len(nz)], want)
+
+
+def test_ten_ant_full_size_properties(cuda_device):
+    """BASELINE config: N=4096, T=16.  Size-independent properties: dones == (fallen | progress >= 999) recomputed
+    from the inputs, obs prefix == root positions, forces == 15*clamp(a), reward == death cost exactly where fallen,
+    progress chain, and tile-boundary independence (a permuted env order gives permuted outputs)."""
+    from massive_marl_benchmark_b200 import synthetic
+    dev = cuda_device
+    N, T = 4096, 16
+    fr = synthetic.ten_ant_frames(N, T, seed=11, fall_prob=0.001)
+    fr_dev = {k: v.to(dev) for k, v in fr.items()}
+    task = _make(N, fr, "cuda", False, dev)
+    task.clip_actions, task.clip_obs = 1.0, 5.0
+    prog0 = torch.randint(0, 999, (N,), device=dev)
+    task.progress_buf.copy_(prog0)
+    obs = torch.zeros(T, N, 388, device=dev); rew = torch.zeros(T, N, device=dev)
+    d8 = torch.zeros(T, N, device=dev, dtype=torch.uint8); forces = torch.zeros(T, N, 80, device=dev)
+    task.replay(fr_dev, fr_dev["actions"], obs, rew, d8, None, forces)
+    torch.cuda.synchronize()
+    root = fr_dev["root"].view(T, N, 11, 13)
+    fallen = (root[:, :, :10, 2] < 0.31).any(-1)
+    prog = prog0.clone(); flag = torch.ones(N, dtype=torch.bool, device=dev)
+    for t in range(T):
+        prog = torch.where(flag, torch.zeros_like(prog), prog + 1)
+        flag = fallen[t] | (prog >= 999)
+        assert torch.equal(d8[t].bool(), flag), "done chain t=%d" % t
+    assert torch.equal(task.progress_buf, prog)
+    assert torch.equal(rew[fallen], torch.full_like(rew[fallen], -2.0))
+    assert (rew[~fallen] != -2.0).all()
+    pos = torch.clamp(root[:, :, :10, :3], -5, 5)
+    assert torch.equal(obs.view(T, N, 388)[:, :, :380].reshape(T, N, 10, 38)[..., :3], pos)
+    assert torch.equal(forces, torch.clamp(fr_dev["actions"], -1, 1) * 15.0 * 1.0)
+    # env-order independence across tile boundaries
+    perm = torch.randperm(N, device=dev)
+    fr_p = {"root": fr_dev["root"].view(T, N, 143)[:, perm].reshape(T, 11 * N, 13).contiguous(),
+            "dof": fr_dev["dof"].view(T, N, 160)[:, perm].reshape(T, 80 * N, 2).contiguous()}
+    t2 = _make(N, fr, "cuda", False, dev)
+    t2.clip_actions, t2.clip_obs = 1.0, 5.0
+    t2.progress_buf.copy_(prog0[perm])
+    obs2 = torch.zeros_like(obs); rew2 = torch.zeros_like(rew); d82 = torch.zeros_like(d8)
+    t2.replay(fr_p, fr_dev["actions"][:, perm].contiguous(), obs2, rew2, d82, None, None)
+    torch.cuda.synchronize()
+    assert torch.equal(obs2, obs[:, perm]) and torch.equal(rew2, rew[:, perm]) and torch.equal(d82, d8[:, perm])
+
+
+def test_ten_ant_edge_cases(cuda_device):
+    """N=1, N not a multiple of the tile or of 4 (unaligned frames), unaligned base pointers, invalid args."""
+    from massive_marl_benchmark_b200 import _lib as L
+    from massive_marl_benchmark_b200 import synthetic
+    from oracle.task_oracle import TenAntOracle
+    dev = cuda_device
+    for N in (1, 3, 31, 33, 65):
+        T = 3
+        fr = synthetic.ten_ant_frames(N, T, seed=N, fall_prob=0.05)
+        task = _make(N, fr, "cuda", False, dev)
+        orc = TenAntOracle(N, device="cuda")
+        npos, nvel = synthetic.reset_noise(N, T, seed=1)
+        for t in range(T):
+            a = fr["actions"][t].to(dev)
+            task.reset_noise = (npos[t].to(dev), nvel[t].to(dev))
+            task.step(a)
+            orc.step(a, fr["root"][t].to(dev), fr["dof"][t].to(dev), noise=(npos[t].to(dev), nvel[t].to(dev)))
+            assert torch.equal(task.reset_buf, orc.reset_buf) and torch.equal(task.progress_buf, orc.progress_buf)
+            assert_close_obs(task.obs_buf, orc.obs_buf, angle_cols=_angle_cols_388(), what="N=%d" % N)
+            rel = (task.rew_buf - orc.rew_buf).abs() / orc.rew_buf.abs().clamp(min=1e-6)
+            assert float(rel.max()) <= 1e-5
+        # T>1 with N not a multiple of 4: frames t>0 start at unaligned addresses (scalar fallback path)
+        rep = _make(N, fr, "cuda", False, dev)
+        frd = {k: v.to(dev) for k, v in fr.items()}
+        obs = torch.zeros(T, N, 388, device=dev); rew = torch.zeros(T, N, device=dev)
+        d8 = torch.zeros(T, N, device=dev, dtype=torch.uint8)
+        rep.replay(frd, frd["actions"], obs, rew, d8)
+        st = _make(N, fr, "cuda", False, dev)
+        for t in range(T):
+            st.step(frd["actions"][t])
+            assert torch.equal(obs[t], st.obs_buf) and torch.equal(rew[t], st.rew_buf) and torch.equal(d8[t].long(), st.reset_buf)
+    # error behaviour: null pointers / bad sizes are refused with a status, nothing is launched
+    p = L.TenAntParams()
+    assert L.lib().mmb_ten_ant_step(p, None) == -1
+    p.num_envs, p.num_frames = 4, 1
+    assert L.lib().mmb_ten_ant_step(p, None) == -1
+    assert L.lib().mmb_ten_ant_step(None, None) == -1
+    assert b"invalid" in L.lib().mmb_strerror(-1)
