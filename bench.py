@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py - env-steps/sec of the rollout hot path (obs + reward + reset + GAE) at TenAnt 4096 x 10.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (sm_100a kernels)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU torch pipeline (oracle port)
+  N > 1: torchrun launches one rank per GPU (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env).
+
+Workload (BASELINE.json configs[1]): TenAnt, 4096 envs x 10 agents per GPU, horizon T = 16.  One "step" =
+one pass of the hot path over one batch = one rollout of T frames x N envs:
+    mmb_ten_ant_step (T frames in one launch: action scaling, observations, reward, done, written straight
+    into the rollout storage slots) + progress/reset chain + carry + mmb_reset_compact over the T flag rows
+    (reset-index lists + DOF re-randomisation) + mmb_gae_ppo + [all-reduce of the 3 advantage statistics when
+    N > 1] + mmb_adv_normalize.
+`value` = env-steps/s with the state frames already resident in HBM; `e2e` = the same metric through the
+reference-facing API (VecTaskPython.step / RolloutStorage) with the frames and actions in pinned HOST memory
+(H2D every env-step, D2H of reward/done every env-step and of the advantages every rollout).
+Synthetic Isaac-layout frames (PhysX is out of scope); 4 rotating frame/storage sets (> L2) so HBM is measured.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (obs+reward+reset+GAE) at TenAnt 4096x10"
+UNIT = "env-steps/s"
+N_ENVS, HORIZON = 4096, 16
+GAMMA, LAM = 0.96, 0.95
+# algorithmic bytes of one TenAnt env-step in the horizon-batched kernel:
+#   reads  root 572 + dof 640 + actions 320                                   = 1532
+#   writes obs 1552 + forces 320 + reward 4 + done 1                          = 1877
+BYTES_PER_ENV_STEP_KERNEL = 1532 + 1877
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.005):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self._stop_evt, self.ok = [], threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self, t0, t1):
+        names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+                 0x100: "display_clock_setting"}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in names.items() if bits & b], "samples": len(inside)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's torch pipeline on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_rollouts(n_rollouts, warmup, n_envs=N_ENVS, horizon=HORIZON, threads=None):
+    """Times `n_rollouts` rollouts (T TenAnt steps + add_transitions + GAE) of the oracle on the CPU; returns
+    (env-steps/s, seconds per rollout, threads)."""
+    from oracle import storage_oracle as so
+    from oracle.task_oracle import TenAntOracle, vec_task_step
+    from massive_marl_benchmark_b200 import synthetic
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    fr = synthetic.ten_ant_frames(n_envs, horizon, seed=1234)
+    orc = TenAntOracle(n_envs)
+    T, N = horizon, n_envs
+    obs_st = torch.zeros(T, N, 388); act_st = torch.zeros(T, N, 80); rew_st = torch.zeros(T, N, 1)
+    done_st = torch.zeros(T, N, 1, dtype=torch.uint8)
+    val_st = torch.randn(T, N, 1); last_values = torch.randn(N, 1)
+    cur_obs = torch.zeros(N, 388)
+
+    def rollout():
+        for t in range(T):
+            obs, rew, done = vec_task_step(lambda a: orc.step(a, fr["root"][t], fr["dof"][t]), fr["actions"][t], 1.0, 5.0)
+            obs_st[t].copy_(cur_obs); act_st[t].copy_(fr["actions"][t]); rew_st[t].copy_(rew.view(-1, 1))
+            done_st[t].copy_(done.view(-1, 1))
+            cur_obs.copy_(obs)
+        return so.ppo_compute_returns(rew_st, val_st, done_st, last_values, GAMMA, LAM)
+
+    for _ in range(warmup):
+        rollout()
+    t0 = time.perf_counter()
+    for _ in range(n_rollouts):
+        rollout()
+    dt = time.perf_counter() - t0
+    return n_rollouts * T * N / dt, dt / n_rollouts, threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warm = args.steps, max(1, min(args.warmup, 3))
+    value, sec, threads = cpu_rollouts(steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE",
+                       "num_envs": N_ENVS, "num_agents": 10, "horizon": HORIZON,
+                       "note": "reference's torch task pipeline + RolloutStorage on the host CPU (oracle port; the Python "
+                               "reference cannot travel to the GPU box)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d rollouts of %d steps x %d envs + GAE" % (steps, HORIZON, N_ENVS)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from massive_marl_benchmark_b200 import _lib as L
+    from massive_marl_benchmark_b200 import dist as mdist
+    from massive_marl_benchmark_b200 import synthetic
+    from massive_marl_benchmark_b200.providers import HostReplayProvider, ReplayProvider
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    from massive_marl_benchmark_b200.tasks import TenAnt, reset_replay
+    from massive_marl_benchmark_b200.vec_task import VecTaskPython
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    N, T, K, W = N_ENVS, HORIZON, args.steps, max(args.warmup, 3)
+    SETS = 4  # rotating frame/storage sets: 4 x ~225 MB of traffic per step >> 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1 + rank}
+    frames = [synthetic.ten_ant_frames(N, T, seed=1234 + 1000 * rank + s) for s in range(SETS)]
+    dev_frames = [{k: v.to(dev) for k, v in f.items()} for f in frames]
+    task = TenAnt(cfg, provider=ReplayProvider({"root": frames[0]["root"], "dof": frames[0]["dof"]}, device=dev))
+    task.clip_actions, task.clip_obs = 1.0, 5.0
+    storages = [RolloutStorage(N, T, (388,), (0,), (80,), dev, "sequential") for _ in range(SETS)]
+    forces = [torch.zeros(T, N, 80, device=dev) for _ in range(SETS)]
+    dof_push = torch.zeros(T, 80 * N, 2, device=dev)
+    for st in storages:
+        st.values.normal_()
+        st.process_group = True if world > 1 else None
+    last_values = torch.randn(N, 1, device=dev)
+    reset_out = [None]
+
+    def rollout(i):
+        s = i % SETS
+        st, fr = storages[s], dev_frames[s]
+        # observation after step t lands in obs slot t+1; reward/done of step t in slot t (no add_transitions pass)
+        task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), None, forces[s])
+        reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
+        st.compute_returns(last_values, GAMMA, LAM)
+
+    for i in range(W):
+        rollout(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.profile_enable(True)
+    L.profile_collect()
+    launches0 = L.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_host0 = time.perf_counter()
+    ev0.record()
+    for i in range(K):
+        rollout(W + i)
+    ev1.record()
+    barrier()
+    t_host1 = time.perf_counter()
+    sampler.stop()
+    L.profile_enable(False)
+    launches = L.launch_count() - launches0
+    prof = L.profile_collect()
+    ms = mdist.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    value = K * T * N * world / (ms * 1e-3)
+
+    # ---- end-to-end through the reference-facing API with host buffers -----------------------------
+    K2 = max(2, min(K, 20))
+    host_prov = HostReplayProvider({"root": torch.cat([f["root"] for f in frames[:2]]),
+                                    "dof": torch.cat([f["dof"] for f in frames[:2]])}, dev)
+    cfg2 = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 7 + rank}
+    task2 = TenAnt(cfg2, provider=host_prov)
+    task2.keep_raw_obs = False
+    env = VecTaskPython(task2, dev)
+    st2 = RolloutStorage(N, T, (388,), (0,), (80,), dev, "sequential")
+    st2.process_group = True if world > 1 else None
+    h_actions = torch.cat([f["actions"] for f in frames[:2]]).pin_memory()        # [2T, N, 80]
+    d_actions = [torch.empty(N, 80, device=dev) for _ in range(2)]
+    h_rew = torch.empty(N, pin_memory=True); h_done = torch.empty(N, dtype=torch.int64, pin_memory=True)
+    h_adv = torch.empty(T, N, 1, pin_memory=True)
+    values = torch.randn(N, 1, device=dev); logp = torch.randn(N, device=dev)
+    mu = torch.randn(N, 80, device=dev); sigma = torch.randn(N, 80, device=dev); states = torch.zeros(N, 0, device=dev)
+    cur_obs = env.reset().clone()
+
+    def e2e_rollout(j):
+        nonlocal cur_obs
+        for t in range(T):
+            a = d_actions[t & 1]
+            a.copy_(h_actions[(j * T + t) % (2 * T)], non_blocking=True)           # H2D actions
+            obs, rew, done, _ = env.step(a)                                          # H2D frame inside the provider
+            st2.add_transitions(cur_obs, states, a, rew, done, values, logp, mu, sigma)
+            cur_obs = obs
+            h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)  # D2H result of the step
+        st2.compute_returns(last_values, GAMMA, LAM)
+        h_adv.copy_(st2.advantages, non_blocking=True)                              # D2H result of the rollout
+        st2.clear()
+
+    for j in range(2):
+        e2e_rollout(j)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for j in range(K2):
+        e2e_rollout(2 + j)
+    e1.record()
+    barrier()
+    e2e_ms = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_value = K2 * T * N * world / (e2e_ms * 1e-3)
+    h2d = T * (host_prov.h2d_bytes_per_frame + N * 80 * 4)
+    d2h = T * (N * 4 + N * 8) + T * N * 4
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    k_ms, k_n = prof.get("ten_ant", (0.0, 0))
+    per_launch_bytes = BYTES_PER_ENV_STEP_KERNEL * T * N
+    achieved = per_launch_bytes / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+    shares = {k: round(v[0] / max(1e-9, sum(x[0] for x in prof.values())), 4) for k, v in prof.items()}
+    cpu = None
+    if world == 1 or rank == 0:
+        c_val, c_sec, c_thr = cpu_rollouts(args.cpu_rollouts, 1)
+        cpu = {"value": c_val, "unit": UNIT, "cores": c_thr, "kind": "port",
+               "sample": "%d rollouts of %d steps x %d envs + GAE (oracle port of the reference's torch pipeline)" % (
+                   args.cpu_rollouts, T, N)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE",
+                   "num_envs_per_gpu": N, "num_agents": 10, "horizon": T, "env_steps_per_step": T * N,
+                   "l2": "4 rotating frame/storage sets, ~225 MB of traffic per step each, > 126 MB L2",
+                   "parallelism": "env-sharded dp%d" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": K2, "api": "VecTaskPython.step + RolloutStorage.add_transitions/compute_returns, pinned host frames"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "ten_ant_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": k_ms / max(k_n, 1),
+                     "launches_timed": k_n, "kernel_time_shares": shares},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(t_host0, t_host1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rollouts", type=int, default=8)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 20      # each step is a ~1 s CPU rollout: keep the arm within a few minutes
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    if world > 1:
+        from massive_marl_benchmark_b200 import dist as mdist
+        mdist.init_from_env("nccl")
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

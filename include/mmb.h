@@ -55,6 +55,15 @@ MMB_API const char* mmb_strerror(int32_t status);
 /* number of kernels launched by this library since load (all threads); bench.py reports deltas */
 MMB_API uint64_t mmb_launch_count(void);
 
+/* Optional per-kernel device timing (measurement aid, off by default): while enabled every launch is bracketed by
+ * a CUDA event pair on its launch stream; mmb_profile_collect synchronises those events, returns the summed
+ * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
+enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
+       MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_COUNT };
+MMB_API int32_t mmb_profile_enable(int32_t on);
+MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Task constants: cfg/<Task>.yaml `env:` block + per-task literals     */
 /* ------------------------------------------------------------------------------------------ */
@@ -298,7 +307,8 @@ MMB_API int32_t mmb_marl_masks(const int64_t* dones, int32_t num_envs, int32_t n
 #define MMB_MAX_GATHER_FIELDS 16
 typedef struct {
   int32_t num_fields;
-  int32_t index_mode;  /* 0: indices given (int64, device) ; 1: stateless bijection on [0,total) keyed by seed */
+  int32_t index_mode;  /* 0: indices given (int64, device); 1: stateless bijection on [0,total) keyed by seed;
+                          2: identity rows batch_start.. (fused multi-field copy: buffer insert / after_update) */
   int64_t total;       /* T*N rows in the flattened planes */
   int64_t batch_start; /* first position of this minibatch in the permutation */
   int64_t batch_size;

@@ -122,6 +122,8 @@ SYMBOLS = {
     "mmb_abi_version": (c_i32, []),
     "mmb_strerror": (C.c_char_p, [c_i32]),
     "mmb_launch_count": (c_u64, []),
+    "mmb_profile_enable": (c_i32, [c_i32]),
+    "mmb_profile_collect": (c_i32, [c_i32, C.POINTER(c_d), C.POINTER(c_i64)]),
     "mmb_ten_ant_step": (c_i32, [C.POINTER(TenAntParams), c_vp]),
     "mmb_ten_ant_load_carry": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mmb_one_ant_step": (c_i32, [C.POINTER(OneAntParams), c_vp]),
@@ -175,6 +177,25 @@ def check(rc, what):
 
 def launch_count():
     return int(lib().mmb_launch_count())
+
+
+KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
+              "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm")
+
+
+def profile_enable(on=True):
+    lib().mmb_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{kernel name: (total_ms, launches)} since the previous collect (synchronises the recorded events)."""
+    out = {}
+    for i, name in enumerate(KERNEL_IDS):
+        ms, n = c_d(0.0), c_i64(0)
+        check(lib().mmb_profile_collect(i, C.byref(ms), C.byref(n)), "mmb_profile_collect")
+        if n.value:
+            out[name] = (ms.value, n.value)
+    return out
 
 
 def ptr(t):

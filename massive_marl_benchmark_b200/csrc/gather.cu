@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ mmb
   for (int64_t row = warp0; row < p.batch_size; row += nwarps) {
     int64_t src_row;
     if (p.index_mode == 0) src_row = __ldg(p.indices + row);
-    else src_row = bijection_eval(bj, p.batch_start + row);
+    else if (p.index_mode == 1) src_row = bijection_eval(bj, p.batch_start + row);
+    else src_row = p.batch_start + row;  // identity: fused multi-field copy (buffer insert / after_update)
     if (p.indices_out && lane == 0) p.indices_out[row] = src_row;
     for (int f = 0; f < p.num_fields; ++f) {
       const int rb = p.row_bytes[f];
@@ -100,15 +101,17 @@ extern "C" int32_t mmb_shuffle_gather(const mmb_gather_params* pp, void* stream)
   mmb_gather_params p = *pp;
   if (p.num_fields <= 0 || p.num_fields > MMB_MAX_GATHER_FIELDS || p.batch_size <= 0 || p.total <= 0) return MMB_EINVAL;
   if (p.index_mode == 0 && !p.indices) return MMB_EINVAL;
-  if (p.index_mode != 0 && p.index_mode != 1) return MMB_EINVAL;
-  if (p.index_mode == 1 && (p.batch_start < 0 || p.batch_start + p.batch_size > p.total)) return MMB_EINVAL;
+  if (p.index_mode < 0 || p.index_mode > 2) return MMB_EINVAL;
+  if (p.index_mode >= 1 && (p.batch_start < 0 || p.batch_start + p.batch_size > p.total)) return MMB_EINVAL;
   for (int f = 0; f < p.num_fields; ++f)
     if (!p.src[f] || !p.dst[f] || p.row_bytes[f] <= 0) return MMB_EINVAL;
   Bijection bj = make_bijection(p.total, p.seed);
   int64_t blocks = (p.batch_size + 7) / 8;  // 8 warps per CTA, one row per warp per pass
   if (blocks > 148 * 32) blocks = 148 * 32;
-  gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, bj);
-  count_launch();
+  {
+    LaunchScope ls(K_GATHER, (cudaStream_t)stream);
+    gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, bj);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
@@ -117,7 +120,9 @@ extern "C" int32_t mmb_permutation(int64_t n, uint64_t seed, int64_t* out, void*
   Bijection bj = make_bijection(n, seed);
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  permutation_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bj, n, out);
-  count_launch();
+  {
+    LaunchScope ls(K_PERM, (cudaStream_t)stream);
+    permutation_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bj, n, out);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

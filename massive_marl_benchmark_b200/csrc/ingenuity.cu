@@ -180,13 +180,17 @@ extern "C" int32_t mmb_ingenuity_step(const mmb_ingenuity_params* pp, void* stre
   if (p.flavor != MMB_FLAVOR_CUDA && p.flavor != MMB_FLAVOR_CPU) return MMB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((p.num_envs + EPT - 1) / EPT, p.num_frames);
-  if (p.flavor == MMB_FLAVOR_CUDA) ingenuity_kernel<FLAVOR_CUDA><<<grid, NT, 0, st>>>(p);
-  else ingenuity_kernel<FLAVOR_CPU><<<grid, NT, 0, st>>>(p);
-  count_launch();
+  {
+    LaunchScope ls(K_INGENUITY, st);
+    if (p.flavor == MMB_FLAVOR_CUDA) ingenuity_kernel<FLAVOR_CUDA><<<grid, NT, 0, st>>>(p);
+    else ingenuity_kernel<FLAVOR_CPU><<<grid, NT, 0, st>>>(p);
+  }
   if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   if (p.num_frames > 1) {
-    ingenuity_chain_kernel<<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
-    count_launch();
+    {
+      LaunchScope ls(K_INGENUITY_CHAIN, st);
+      ingenuity_chain_kernel<<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
+    }
     if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   }
   return MMB_OK;

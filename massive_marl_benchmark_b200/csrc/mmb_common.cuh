@@ -9,5 +9,21 @@
 #define MMB_MAX_DEVICES 16
 
 namespace mmb {
-void count_launch();  // api.cu: bumps the process-wide launch counter reported by mmb_launch_count()
-}
+
+// kernel classes, as reported by mmb_profile_collect (keep in sync with include/mmb.h MMB_K_*)
+enum KernelId {
+  K_TEN_ANT = 0, K_TEN_ANT_CHAIN, K_TEN_ANT_CARRY, K_ONE_ANT, K_ONE_ANT_CHAIN, K_INGENUITY, K_INGENUITY_CHAIN,
+  K_RESET, K_ROLLOUT_ADD, K_GAE_PPO, K_ADV_NORM, K_STATS, K_GAE_MARL, K_MASKS, K_GATHER, K_PERM, K_COUNT
+};
+
+// Brackets one kernel launch: bumps the launch counter and, while profiling is enabled
+// (mmb_profile_enable), records a CUDA event pair around it on the launch stream.
+struct LaunchScope {
+  LaunchScope(int id, cudaStream_t st);
+  ~LaunchScope();
+  int id_;
+  cudaStream_t st_;
+  cudaEvent_t stop_;
+};
+
+}  // namespace mmb

@@ -230,14 +230,18 @@ extern "C" int32_t mmb_one_ant_step(const mmb_one_ant_params* pp, void* stream) 
   if (p.flavor != MMB_FLAVOR_CUDA && p.flavor != MMB_FLAVOR_CPU) return MMB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((p.num_envs + EPT - 1) / EPT, p.num_frames);
-  if (p.flavor == MMB_FLAVOR_CUDA) one_ant_kernel<FLAVOR_CUDA><<<grid, EPT, 0, st>>>(p);
-  else one_ant_kernel<FLAVOR_CPU><<<grid, EPT, 0, st>>>(p);
-  count_launch();
+  {
+    LaunchScope ls(K_ONE_ANT, st);
+    if (p.flavor == MMB_FLAVOR_CUDA) one_ant_kernel<FLAVOR_CUDA><<<grid, EPT, 0, st>>>(p);
+    else one_ant_kernel<FLAVOR_CPU><<<grid, EPT, 0, st>>>(p);
+  }
   if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   if (p.num_frames > 1) {
-    if (p.flavor == MMB_FLAVOR_CUDA) one_ant_chain_kernel<FLAVOR_CUDA><<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
-    else one_ant_chain_kernel<FLAVOR_CPU><<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
-    count_launch();
+    {
+      LaunchScope ls(K_ONE_ANT_CHAIN, st);
+      if (p.flavor == MMB_FLAVOR_CUDA) one_ant_chain_kernel<FLAVOR_CUDA><<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
+      else one_ant_chain_kernel<FLAVOR_CPU><<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
+    }
     if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   }
   return MMB_OK;

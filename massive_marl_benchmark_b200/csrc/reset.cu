@@ -144,7 +144,9 @@ extern "C" int32_t mmb_reset_compact(const mmb_reset_params* pp, void* stream) {
   if (p.task != MMB_TASK_INGENUITY && p.dof_state && p.noise_mode == 0 && (!p.noise_pos || !p.noise_vel)) return MMB_EINVAL;
   if (p.noise_mode != 0 && p.noise_mode != 1) return MMB_EINVAL;
   if (p.dof_state && (reinterpret_cast<uintptr_t>(p.dof_state) & 7u)) return MMB_EALIGN;
-  reset_kernel<<<p.num_rows, 1024, 0, (cudaStream_t)stream>>>(p);
-  count_launch();
+  {
+    LaunchScope ls(K_RESET, (cudaStream_t)stream);
+    reset_kernel<<<p.num_rows, 1024, 0, (cudaStream_t)stream>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

@@ -274,8 +274,10 @@ extern "C" int32_t mmb_gae_ppo(const mmb_gae_ppo_params* pp, void* stream) {
   mmb_gae_ppo_params p = *pp;
   if (p.num_envs <= 0 || p.num_steps <= 0) return MMB_EINVAL;
   if (!p.rewards || !p.values || !p.dones || !p.last_values || !p.returns || !p.advantages) return MMB_EINVAL;
-  gae_ppo_kernel<<<(p.num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
-  count_launch();
+  {
+    LaunchScope ls(K_GAE_PPO, (cudaStream_t)stream);
+    gae_ppo_kernel<<<(p.num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
@@ -284,16 +286,20 @@ extern "C" int32_t mmb_adv_normalize(float* advantages, int64_t n, const double*
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps);
-  count_launch();
+  {
+    LaunchScope ls(K_ADV_NORM, (cudaStream_t)stream);
+    adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
 extern "C" int32_t mmb_rollout_statistics(const uint8_t* dones, const float* rewards, int32_t num_steps,
                                           int32_t num_envs, float* out2, void* stream) {
   if (!dones || !rewards || !out2 || num_steps <= 0 || num_envs <= 0) return MMB_EINVAL;
-  rollout_statistics_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dones, rewards, num_steps, num_envs, out2);
-  count_launch();
+  {
+    LaunchScope ls(K_STATS, (cudaStream_t)stream);
+    rollout_statistics_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dones, rewards, num_steps, num_envs, out2);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
@@ -306,8 +312,10 @@ extern "C" int32_t mmb_rollout_add(const mmb_rollout_add_params* pp, void* strea
   int64_t bx = (maxn / 4 + 255) / 256;
   if (bx < 1) bx = 1;
   if (bx > 148 * 8) bx = 148 * 8;
-  rollout_add_kernel<<<dim3((unsigned)bx, 9), 256, 0, (cudaStream_t)stream>>>(p);
-  count_launch();
+  {
+    LaunchScope ls(K_ROLLOUT_ADD, (cudaStream_t)stream);
+    rollout_add_kernel<<<dim3((unsigned)bx, 9), 256, 0, (cudaStream_t)stream>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
@@ -318,16 +326,20 @@ extern "C" int32_t mmb_gae_marl(const mmb_gae_marl_params* pp, void* stream) {
   if (!p.rewards || !p.value_preds || !p.masks || !p.next_value || !p.returns) return MMB_EINVAL;
   if (p.use_proper_time_limits && !p.bad_masks) return MMB_EINVAL;
   if (p.use_denorm && (!p.denorm_mean || !p.denorm_var)) return MMB_EINVAL;
-  gae_marl_kernel<<<dim3((p.num_envs + 255) / 256, p.num_agents), 256, 0, (cudaStream_t)stream>>>(p);
-  count_launch();
+  {
+    LaunchScope ls(K_GAE_MARL, (cudaStream_t)stream);
+    gae_marl_kernel<<<dim3((p.num_envs + 255) / 256, p.num_agents), 256, 0, (cudaStream_t)stream>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
 extern "C" int32_t mmb_marl_masks(const int64_t* dones, int32_t num_envs, int32_t num_agents, float* masks, int64_t m_e,
                                   int64_t m_a, float* active_masks, int64_t am_e, int64_t am_a, void* stream) {
   if (!dones || num_envs <= 0 || num_agents <= 0) return MMB_EINVAL;
-  marl_masks_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dones, num_envs, num_agents, masks, m_e,
-                                                                             m_a, active_masks, am_e, am_a);
-  count_launch();
+  {
+    LaunchScope ls(K_MASKS, (cudaStream_t)stream);
+    marl_masks_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dones, num_envs, num_agents, masks, m_e,
+                                                                               m_a, active_masks, am_e, am_a);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

@@ -374,8 +374,10 @@ int32_t launch_ten_ant(const mmb_ten_ant_params& p, cudaStream_t st) {
     attr_done[dev] = true;
   }
   dim3 grid((p.num_envs + EPT - 1) / EPT, p.num_frames);
-  kern<<<grid, EPT * A, TenAntSmem<EPT>::kBytes, st>>>(p);
-  count_launch();
+  {
+    LaunchScope ls(K_TEN_ANT, st);
+    kern<<<grid, EPT * A, TenAntSmem<EPT>::kBytes, st>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
@@ -399,14 +401,18 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
                                              : launch_ten_ant<FLAVOR_CPU, MMB_TEN_ANT_EPT>(p, st);
   if (rc != MMB_OK) return rc;
   if (p.num_frames > 1) {
-    ten_ant_chain_kernel<<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
-    count_launch();
+    {
+      LaunchScope ls(K_TEN_ANT_CHAIN, st);
+      ten_ant_chain_kernel<<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
+    }
     if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
     // carry after the last frame = f(frame T-1) (a (tile, T-1) CTA must not write what a (tile, 0) CTA reads)
     const float* last = p.root + (int64_t)(p.num_frames - 1) * p.root_frame_stride;
-    ten_ant_load_carry_kernel<<<(p.num_envs * A + 255) / 256, 256, 0, st>>>(last, p.num_envs, p.pos_before,
-                                                                             p.goal_before, p.box_before);
-    count_launch();
+    {
+      LaunchScope ls(K_TEN_ANT_CARRY, st);
+      ten_ant_load_carry_kernel<<<(p.num_envs * A + 255) / 256, 256, 0, st>>>(last, p.num_envs, p.pos_before,
+                                                                               p.goal_before, p.box_before);
+    }
     if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   }
   return MMB_OK;
@@ -416,8 +422,10 @@ extern "C" int32_t mmb_ten_ant_load_carry(const float* root, int32_t num_envs, f
                                           float* box_before, void* stream) {
   using namespace mmb;
   if (!root || !pos_before || !goal_before || !box_before || num_envs <= 0) return MMB_EINVAL;
-  ten_ant_load_carry_kernel<<<(num_envs * A + 255) / 256, 256, 0, (cudaStream_t)stream>>>(root, num_envs, pos_before,
-                                                                                           goal_before, box_before);
-  count_launch();
+  {
+    LaunchScope ls(K_TEN_ANT_CARRY, (cudaStream_t)stream);
+    ten_ant_load_carry_kernel<<<(num_envs * A + 255) / 256, 256, 0, (cudaStream_t)stream>>>(root, num_envs, pos_before,
+                                                                                             goal_before, box_before);
+  }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

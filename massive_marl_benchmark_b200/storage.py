@@ -1,0 +1,172 @@
+"""`RolloutStorage` with the reference's interface (agents/algorithms/rl/ppo/storage.py) on the B200 kernels.
+
+Same constructor, same public tensors (`observations, states, rewards, actions, dones(uint8),
+actions_log_prob, values, returns, advantages, mu, sigma`, all `[T, N, .]`), same methods
+(`add_transitions, clear, compute_returns, get_statistics, mini_batch_generator`) and the same
+`AssertionError("Rollout buffer overflow")`, so the reference's unmodified `PPO` runs on it.
+
+What changes underneath:
+  add_transitions      9 copy_ launches            -> 1 launch (mmb_rollout_add)
+  compute_returns      ~8 ops x T + 5 (Python loop) -> 2 launches (mmb_gae_ppo reverse scan with fused
+                                                      fp64 sum/sumsq, mmb_adv_normalize)
+  get_statistics       dones.cpu() host sync        -> 1 launch, result stays on the device
+  mini_batch_generator Python list[int] per batch   -> CUDA int64 index tensors (device permutation);
+                                                      `gather_minibatch` gathers all fields in 1 launch
+
+`observations` is a view of a `[T+1, N, obs]` allocation: the fused task kernels write the observation
+that follows step t straight into slot t+1 (`obs_slots`), so a rollout needs no add_transitions copy of
+the 1.5 KB/env observation at all; `roll_last_obs()` moves slot T to slot 0 between rollouts.
+
+Multi-GPU (env-sharded): set `process_group`; the (count, sum, sumsq) advantage statistics are
+all-reduced (3 doubles, NCCL) between the two launches so every shard normalises with global moments.
+"""
+import torch
+
+from . import _lib as L
+
+
+class _BatchIterable:
+    """What `mini_batch_generator` returns: iterated once per epoch (ppo.py:247-252), reshuffles on every
+    `__iter__` when sampler == 'random' (BatchSampler(SubsetRandomSampler) semantics, drop_last=True)."""
+
+    def __init__(self, storage, mini_batch_size):
+        self.storage = storage
+        self.mb = mini_batch_size
+
+    def __len__(self):
+        return self.storage.batch_size // self.mb
+
+    def __iter__(self):
+        st = self.storage
+        order = st._epoch_order()
+        for i in range(0, st.batch_size - self.mb + 1, self.mb):
+            yield order[i:i + self.mb]
+
+
+class RolloutStorage:
+    def __init__(self, num_envs, num_transitions_per_env, obs_shape, states_shape, actions_shape, device='cuda:0',
+                 sampler='sequential'):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise L.MmbError("RolloutStorage needs a CUDA device (there is no CPU path); got %r" % (device,))
+        L.lib()
+        self.device = device
+        self.sampler = sampler
+        T, N = num_transitions_per_env, num_envs
+        self.obs_slots = torch.zeros(T + 1, N, *obs_shape, device=dev)
+        self.observations = self.obs_slots[:T]
+        self.states = torch.zeros(T, N, *states_shape, device=dev)
+        self.rewards = torch.zeros(T, N, 1, device=dev)
+        self.actions = torch.zeros(T, N, *actions_shape, device=dev)
+        self.dones = torch.zeros(T, N, 1, device=dev, dtype=torch.uint8)
+        self.actions_log_prob = torch.zeros(T, N, 1, device=dev)
+        self.values = torch.zeros(T, N, 1, device=dev)
+        self.returns = torch.zeros(T, N, 1, device=dev)
+        self.advantages = torch.zeros(T, N, 1, device=dev)
+        self.mu = torch.zeros(T, N, *actions_shape, device=dev)
+        self.sigma = torch.zeros(T, N, *actions_shape, device=dev)
+        self.num_transitions_per_env = T
+        self.num_envs = N
+        self.step = 0
+        self.batch_size = T * N
+        self.process_group = None
+        self.adv_stats = torch.zeros(3, device=dev, dtype=torch.float64)
+        self._stats_out = torch.zeros(2, device=dev)
+        self.shuffle_seed = 0
+        self._epoch = 0
+        self.permutation_override = None   # parity mode: a host-supplied permutation (e.g. torch.randperm)
+        self._obs_dim = int(self.obs_slots[0, 0].numel())
+        self._states_dim = int(self.states[0, 0].numel()) if self.states.numel() else 0
+        self._act_dim = int(self.actions[0, 0].numel())
+
+    # ------------------------------------------------------------------------------------------
+    def add_transitions(self, observations, states, actions, rewards, dones, values, actions_log_prob, mu, sigma):
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        s = self.step
+        c = lambda t: t if t.is_contiguous() else t.contiguous()
+        keep = [c(observations), c(states), c(actions), c(rewards), c(dones), c(values), c(actions_log_prob), c(mu), c(sigma)]
+        if keep[4].dtype != torch.int64:
+            keep[4] = keep[4].to(torch.int64)
+        p = L.RolloutAddParams()
+        p.num_envs, p.obs_dim, p.states_dim, p.act_dim = self.num_envs, self._obs_dim, self._states_dim, self._act_dim
+        (p.observations, p.states, p.actions, p.rewards, p.dones, p.values, p.actions_log_prob, p.mu,
+         p.sigma) = [L.ptr(t) if t.numel() else None for t in keep]
+        p.dst_observations = L.ptr(self.observations[s])
+        p.dst_states = L.ptr(self.states[s]) if self._states_dim else None
+        p.dst_actions, p.dst_rewards, p.dst_dones = L.ptr(self.actions[s]), L.ptr(self.rewards[s]), L.ptr(self.dones[s])
+        p.dst_values, p.dst_actions_log_prob = L.ptr(self.values[s]), L.ptr(self.actions_log_prob[s])
+        p.dst_mu, p.dst_sigma = L.ptr(self.mu[s]), L.ptr(self.sigma[s])
+        L.check(L.lib().mmb_rollout_add(p, L.stream_ptr()), "mmb_rollout_add")
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def roll_last_obs(self):
+        """Fused-rollout mode: the observation after the last step becomes slot 0 of the next rollout."""
+        self.obs_slots[0].copy_(self.obs_slots[self.num_transitions_per_env])
+
+    # ------------------------------------------------------------------------------------------
+    def compute_returns(self, last_values, gamma, lam):
+        T, N = self.num_transitions_per_env, self.num_envs
+        lv = last_values if last_values.is_contiguous() else last_values.contiguous()
+        self.adv_stats.zero_()
+        p = L.GaePpoParams()
+        p.num_envs, p.num_steps = N, T
+        p.rewards, p.values, p.dones, p.last_values = L.ptr(self.rewards), L.ptr(self.values), L.ptr(self.dones), L.ptr(lv)
+        p.gamma, p.lam = float(gamma), float(lam)
+        p.returns, p.advantages, p.stats = L.ptr(self.returns), L.ptr(self.advantages), L.ptr(self.adv_stats)
+        L.check(L.lib().mmb_gae_ppo(p, L.stream_ptr()), "mmb_gae_ppo")
+        if self.process_group is not None:
+            from . import dist as mdist
+            mdist.all_reduce_stats(self.adv_stats, self.process_group)
+        L.check(L.lib().mmb_adv_normalize(L.ptr(self.advantages), T * N, L.ptr(self.adv_stats), 1e-8, L.stream_ptr()),
+                "mmb_adv_normalize")
+
+    def get_statistics(self):
+        L.check(L.lib().mmb_rollout_statistics(L.ptr(self.dones), L.ptr(self.rewards), self.num_transitions_per_env,
+                                               self.num_envs, L.ptr(self._stats_out), L.stream_ptr()),
+                "mmb_rollout_statistics")
+        return self._stats_out[0], self._stats_out[1]
+
+    # ------------------------------------------------------------------------------------------
+    def _epoch_order(self):
+        n = self.batch_size
+        dev = self.rewards.device
+        if self.sampler == "sequential":
+            if not hasattr(self, "_arange") or self._arange.numel() != n:
+                self._arange = torch.arange(n, device=dev)
+            return self._arange
+        if self.permutation_override is not None:
+            return torch.as_tensor(self.permutation_override, device=dev, dtype=torch.int64)
+        out = torch.empty(n, device=dev, dtype=torch.int64)
+        seed = (self.shuffle_seed * 0x9E3779B97F4A7C15 + self._epoch) & 0xFFFFFFFFFFFFFFFF
+        self._epoch += 1
+        L.check(L.lib().mmb_permutation(n, seed, L.ptr(out), L.stream_ptr()), "mmb_permutation")
+        return out
+
+    def mini_batch_generator(self, num_mini_batches):
+        mini_batch_size = self.batch_size // num_mini_batches
+        if self.sampler not in ("sequential", "random"):
+            raise ValueError("unknown sampler %r" % (self.sampler,))
+        return _BatchIterable(self, mini_batch_size)
+
+    FIELDS = ("observations", "states", "actions", "values", "returns", "actions_log_prob", "advantages", "mu", "sigma")
+
+    def gather_minibatch(self, indices, out=None):
+        """All fields of one minibatch in ONE launch (the 9 gathers of ppo.py:253-264): dict name -> [B, .]."""
+        B = int(indices.numel())
+        fields = [f for f in self.FIELDS if getattr(self, f).numel()]
+        if out is None:
+            out = {f: torch.empty((B,) + tuple(getattr(self, f).shape[2:]), device=self.rewards.device) for f in fields}
+        p = L.GatherParams()
+        p.num_fields, p.index_mode, p.total, p.batch_start, p.batch_size = len(fields), 0, self.batch_size, 0, B
+        idx = indices if indices.dtype == torch.int64 and indices.is_contiguous() else indices.to(torch.int64).contiguous()
+        p.indices = L.ptr(idx)
+        for i, f in enumerate(fields):
+            src = getattr(self, f)
+            p.src[i], p.dst[i] = src.data_ptr(), out[f].data_ptr()
+            p.row_bytes[i] = int(src[0, 0].numel()) * src.element_size()
+        L.check(L.lib().mmb_shuffle_gather(p, L.stream_ptr()), "mmb_shuffle_gather")
+        return out

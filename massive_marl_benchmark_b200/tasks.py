@@ -420,18 +420,21 @@ class MultiIngenuity(BaseTask):
         self._step_count += T
 
 
-def reset_replay(task, flags_u8, dof_out=None, noise=None):
+def reset_replay(task, flags_u8, dof_out=None, noise=None, out=None):
     """Batched reset_idx over the rows of a [F,N] uint8 flag plane (the done flags a replay emitted): returns
-    (env_ids [F,N], index_a [F,N*na], index_b [F,N*nb] or None, counts [F]).  Row f = the reset that step f+1
-    performs (flags are those left by step f)."""
+    (env_ids [F,N], index_a [F,N*na], index_b [F,N*nb], counts [F]).  Row f = the reset that step f+1
+    performs (flags are those left by step f).  `out` = a previous return value to reuse its buffers."""
     F, N = flags_u8.shape
     dev = flags_u8.device
     kind = {TenAnt: L.TASK_TEN_ANT, OneAnt: L.TASK_ONE_ANT, MultiIngenuity: L.TASK_INGENUITY}[type(task)]
     na, nb = {L.TASK_TEN_ANT: (11, 10), L.TASK_ONE_ANT: (2, 1), L.TASK_INGENUITY: (4, 4)}[kind]
-    env_ids = torch.zeros(F, N, device=dev, dtype=torch.long)
-    ia = torch.zeros(F, N * na, device=dev, dtype=torch.int32)
-    ib = torch.zeros(F, N * nb, device=dev, dtype=torch.int32)
-    counts = torch.zeros(F, device=dev, dtype=torch.int32)
+    if out is not None:
+        env_ids, ia, ib, counts = out
+    else:
+        env_ids = torch.zeros(F, N, device=dev, dtype=torch.long)
+        ia = torch.zeros(F, N * na, device=dev, dtype=torch.int32)
+        ib = torch.zeros(F, N * nb, device=dev, dtype=torch.int32)
+        counts = torch.zeros(F, device=dev, dtype=torch.int32)
     p = L.ResetParams()
     p.task, p.num_envs, p.num_rows = kind, N, F
     p.flags_u8, p.flags_u8_row_stride = L.ptr(flags_u8), flags_u8.stride(0)

@@ -20,7 +20,7 @@ def load_golden(name):
     out = {}
     for k in d.files:
         a = d[k]
-        out[k] = torch.from_numpy(a) if a.dtype.kind in "fiub" and a.ndim > 0 else a
+        out[k] = torch.from_numpy(np.array(a)) if a.dtype.kind in "fiub" else a
     return out
 
 

@@ -46,12 +46,9 @@ def gen_ten_ant(N=37, F=8, seed=101):
     orc = TenAntOracle(N)
     fr = synthetic.ten_ant_frames(N, F, seed=seed, fall_prob=0.01)
     npos, nvel = synthetic.reset_noise(N, F, seed=seed + 1)
-    # exercise the episode-length reset: a few envs start close to max_episode_length
-    prog0 = torch.zeros(N, dtype=torch.long)
-    prog0[3] = 996
-    prog0[17] = 993
-    task.progress_buf[:] = prog0
-    orc.progress_buf[:] = prog0
+    # exercise the episode-length reset: after step 0 (which resets every env because reset_buf starts as ones)
+    # a few envs are moved close to max_episode_length; tests inject the same `progress_after0`
+    prog_bump = {3: 996, 17: 993}
     rec = {k: [] for k in ("obs", "rew", "reset", "progress", "forces", "n_reset", "env_ids", "ant_box_indices",
                            "ant_indices", "dof_pushed", "obs_all", "reward_all", "done_all")}
     from agents.tasks.agent_base.multi_vec_task import MultiVecTaskPython
@@ -104,9 +101,14 @@ def gen_ten_ant(N=37, F=8, seed=101):
         rec["ant_indices"].append(_pad_rows(ai, 10 * N)); rec["dof_pushed"].append(pushed)
         rec["obs_all"].append(obs_all.clone())
         rec["reward_all"].append(rew_all.clone()); rec["done_all"].append(done_all.clone())
+        if t == 0:
+            for e, v in prog_bump.items():
+                task.progress_buf[e] = v
+                orc.progress_buf[e] = v
+            prog_after0 = task.progress_buf.clone()
     out = {k: torch.stack(v) for k, v in rec.items()}
     out.update(root=fr["root"], dof=fr["dof"], actions=fr["actions"] * 1.2, noise_pos=npos, noise_vel=nvel,
-               progress0=prog0, initial_root=orc.initial_root_states)
+               progress_after0=prog_after0, initial_root=orc.initial_root_states)
     return out
 
 
@@ -115,10 +117,7 @@ def gen_one_ant(N=64, F=8, seed=202):
     orc = OneAntOracle(N)
     fr = synthetic.one_ant_frames(N, F, seed=seed, fall_prob=0.03)
     npos, nvel = synthetic.reset_noise(N, F, seed=seed + 1)
-    prog0 = torch.zeros(N, dtype=torch.long)
-    prog0[5] = 997
-    task.progress_buf[:] = prog0
-    orc.progress_buf[:] = prog0
+    prog_bump = {5: 997}
     import agents.tasks.one_ant as oa
     rec = {k: [] for k in ("obs", "obs_clamped", "rew", "reset", "progress", "forces", "n_reset", "env_ids", "ant_box_indices",
                            "ant_indices", "dof_pushed", "potentials", "prev_potentials", "up_vec", "heading_vec")}
@@ -153,9 +152,14 @@ def gen_one_ant(N=64, F=8, seed=202):
         rec["ant_indices"].append(_pad_rows(ai, N)); rec["dof_pushed"].append(pushed)
         rec["potentials"].append(task.potentials.clone()); rec["prev_potentials"].append(task.prev_potentials.clone())
         rec["up_vec"].append(task.up_vec.clone()); rec["heading_vec"].append(task.heading_vec.clone())
+        if t == 0:
+            for e, v in prog_bump.items():
+                task.progress_buf[e] = v
+                orc.progress_buf[e] = v
+            prog_after0 = task.progress_buf.clone()
     out = {k: torch.stack(v) for k, v in rec.items()}
     out.update(root=fr["root"], dof=fr["dof"], sensor=fr["sensor"], actions=fr["actions"] * 1.2, noise_pos=npos,
-               noise_vel=nvel, progress0=prog0, initial_root=orc.initial_root_states)
+               noise_vel=nvel, progress_after0=prog_after0, initial_root=orc.initial_root_states)
     return out
 
 
@@ -163,10 +167,7 @@ def gen_ingenuity(N=33, F=8, seed=303):
     task, g = refshim.make_task("MultiIngenuity", N, False)
     orc = IngenuityOracle(N)
     fr = synthetic.ingenuity_frames(N, F, seed=seed)
-    prog0 = torch.zeros(N, dtype=torch.long)
-    prog0[2] = 995
-    task.progress_buf[:] = prog0
-    orc.progress_buf[:] = prog0
+    prog_bump = {2: 998}
     rec = {k: [] for k in ("obs", "rew", "reset", "progress", "forces", "n_reset", "env_ids", "actor_indices", "dof_pushed")}
     for t in range(F):
         g.push_frame(fr["root"][t])
@@ -190,8 +191,13 @@ def gen_ingenuity(N=33, F=8, seed=303):
         rec["forces"].append(logs["body_forces"][1]); rec["n_reset"].append(torch.tensor(n_res))
         rec["env_ids"].append(_pad_rows(orc.last["env_ids"], N)); rec["actor_indices"].append(_pad_rows(ai, 4 * N))
         rec["dof_pushed"].append(pushed)
+        if t == 0:
+            for e, v in prog_bump.items():
+                task.progress_buf[e] = v
+                orc.progress_buf[e] = v
+            prog_after0 = task.progress_buf.clone()
     out = {k: torch.stack(v) for k, v in rec.items()}
-    out.update(root=fr["root"], actions=fr["actions"], progress0=prog0, initial_root=orc.initial_root_states)
+    out.update(root=fr["root"], actions=fr["actions"], progress_after0=prog_after0, initial_root=orc.initial_root_states)
     return out
 
 
@@ -214,7 +220,12 @@ def gen_storage_ppo(T=8, N=50, seed=404):
     except AssertionError as e:
         overflow_msg = str(e)
     last_values = torch.randn(N, 1, generator=gen)
+    # Reference quirk: get_statistics does `done = self.dones.cpu(); done[-1] = 1` (storage.py:68-69).  On the
+    # reference's production device (CUDA) .cpu() copies; on CPU it ALIASES, so the CPU run would overwrite the
+    # last row of its own dones before compute_returns.  The fixture keeps the device semantics: dones restored.
+    dones_before = st.dones.clone()
     mean_len, mean_rew = st.get_statistics()
+    st.dones.copy_(dones_before)
     st.compute_returns(last_values, 0.96, 0.95)
     ret, adv = so.ppo_compute_returns(st.rewards, st.values, st.dones, last_values, 0.96, 0.95)
     _eq("ppo returns", st.returns, ret)

@@ -1,0 +1,140 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mmb.h declares, the ctypes structs have the
+C layout, host-side logic (providers, spaces, sharding, synthetic layouts) behaves, and the product fails loudly
+without a GPU instead of falling back."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mmb.h")
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from massive_marl_benchmark_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(HEADER).read()
+    declared = set(re.findall(r"MMB_API\s+[\w\s\*]+?\b(mmb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    assert declared == set(built_lib.SYMBOLS), declared ^ set(built_lib.SYMBOLS)
+    lib = ctypes.CDLL(built_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.mmb_abi_version.restype = ctypes.c_int32
+    assert lib.mmb_abi_version() == built_lib.ABI_VERSION
+    lib.mmb_strerror.restype = ctypes.c_char_p
+    assert lib.mmb_strerror(0) == b"ok" and b"alignment" in lib.mmb_strerror(-2)
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert exported == declared, exported ^ declared      # nothing but the ABI is exported
+
+
+def test_ctypes_structs_match_c_layout(built_lib):
+    """Compile a C program against include/mmb.h that prints sizeof/offsetof and compare with ctypes."""
+    L = built_lib
+    probes = [("mmb_ant_consts", L.AntConsts, "initial_dof_pos"), ("mmb_ten_ant_params", L.TenAntParams, "c"),
+              ("mmb_one_ant_params", L.OneAntParams, "c"), ("mmb_ingenuity_params", L.IngenuityParams, "forces_state"),
+              ("mmb_reset_params", L.ResetParams, "c"), ("mmb_rollout_add_params", L.RolloutAddParams, "dst_sigma"),
+              ("mmb_gae_ppo_params", L.GaePpoParams, "stats"), ("mmb_gae_marl_params", L.GaeMarlParams, "stats"),
+              ("mmb_gather_params", L.GatherParams, "row_bytes")]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "mmb.h"\nint main(void){\n'
+    for cname, _, field in probes:
+        src += 'printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (cname, cname, field)
+    src += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
+        out = subprocess.check_output([os.path.join(d, "p")], text=True).split("\n")
+    for (cname, cls, field), line in zip(probes, out):
+        size, off = map(int, line.split())
+        assert ctypes.sizeof(cls) == size, cname
+        assert getattr(cls, field).offset == off, (cname, field)
+
+
+def test_no_cpu_fallback(built_lib):
+    """The product refuses to run without CUDA rather than computing on the CPU."""
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    from massive_marl_benchmark_b200.tasks import TenAnt
+    with pytest.raises(built_lib.MmbError):
+        RolloutStorage(4, 2, (3,), (0,), (2,), "cpu")
+    with pytest.raises(built_lib.MmbError):
+        TenAnt({"env": {"numEnvs": 4}}, None, None, "cpu", 0, True)
+    import massive_marl_benchmark_b200 as pkg
+    for mod in ("tasks", "vec_task", "storage", "separated_buffer", "_lib", "providers", "dist", "synthetic"):
+        text = open(os.path.join(os.path.dirname(pkg.__file__), mod + ".py")).read()
+        assert "import oracle" not in text and "from oracle" not in text, mod
+
+
+def test_missing_library_fails_loudly(built_lib, monkeypatch):
+    monkeypatch.setattr(built_lib, "_lib", None)
+    monkeypatch.setattr(built_lib, "LIB_PATH", "/nonexistent/libmmb_b200.so")
+    with pytest.raises(built_lib.MmbError, match="no CPU fallback"):
+        built_lib.lib()
+
+
+def test_synthetic_layouts_and_providers():
+    from massive_marl_benchmark_b200 import synthetic
+    from massive_marl_benchmark_b200.providers import ReplayProvider
+    fr = synthetic.ten_ant_frames(6, 3, seed=1)
+    assert fr["root"].shape == (3, 66, 13) and fr["dof"].shape == (3, 480, 2) and fr["actions"].shape == (3, 6, 80)
+    assert torch.allclose(fr["root"][:, :, 3:7].norm(dim=-1), torch.ones(3, 66), atol=1e-5)
+    assert (fr["root"][:, 10::11, 2] == 1.0).all() and (fr["root"][:, 10::11, 3:5] == 0).all()
+    lo, hi = synthetic.ant_dof_limits()
+    pos = fr["dof"][..., 0].view(3, 60, 8)
+    assert (pos >= lo - 0.03).all() and (pos <= hi + 0.03).all()
+    assert torch.equal(synthetic.ant_initial_dof_pos(), torch.where(lo > 0, lo, torch.where(hi < 0, hi, torch.zeros(8))))
+    assert synthetic.one_ant_frames(5, 2)["sensor"].shape == (2, 20, 6)
+    assert synthetic.ingenuity_frames(5, 2)["root"].shape == (2, 20, 13)
+    again = synthetic.ten_ant_frames(6, 3, seed=1)
+    assert all(torch.equal(fr[k], again[k]) for k in fr)
+    p = ReplayProvider({"root": fr["root"], "dof": fr["dof"]}, loop=True)
+    with pytest.raises(RuntimeError):
+        p.frame()
+    for t in range(5):
+        p.simulate()
+        assert torch.equal(p.frame()["root"], fr["root"][t % 3])
+    assert p.window(1, 2)["dof"].shape[0] == 2
+    with pytest.raises(IndexError):
+        p.window(2, 2)
+    q = ReplayProvider({"root": fr["root"]}, loop=False)
+    for _ in range(4):
+        q.simulate()
+    with pytest.raises(IndexError):
+        q.frame()
+
+
+def test_spaces_and_shard_ranges():
+    from massive_marl_benchmark_b200 import dist as mdist
+    from massive_marl_benchmark_b200 import spaces
+    b = spaces.Box(low=-np.inf, high=np.inf, shape=(46,))
+    assert b.shape == (46,) and isinstance(b, spaces.Space)
+    assert spaces.Box(np.ones(8) * -1.0, np.ones(8)).shape == (8,)
+    for n, w in ((4096, 8), (16384, 4), (10, 3), (7, 8)):
+        spans = [mdist.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_default_consts_match_reference_yaml():
+    from massive_marl_benchmark_b200 import _lib as L
+    c = L.default_ant_consts()
+    assert abs(c.up_weight - 0.1) < 1e-7 and abs(c.death_cost + 2.0) < 1e-7 and c.max_episode_length == 1000.0
+    assert np.allclose(list(c.initial_dof_pos), [0, 0.5236, 0, -0.5236, 0, -0.5236, 0, 0.5236], atol=1e-4)
+    assert list(c.joint_gears) == [15.0] * 8 and list(c.inv_start_rot)[3] == 1.0
+    assert np.signbit(np.float32(list(c.inv_start_rot)[0]))        # quat_conjugate((0,0,0,1)) has negative zeros
+    c2 = L.default_ant_consts({"upWeight": 0.25, "episodeLength": 500})
+    assert abs(c2.up_weight - 0.25) < 1e-7 and c2.max_episode_length == 500.0

@@ -1,0 +1,166 @@
+"""GPU parity of the rollout-storage path: RolloutStorage (PPO), SeparatedReplayBuffer (MARL), masks,
+shuffle + gather.  Oracles: golden vectors from the reference classes and oracle/storage_oracle.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close_obs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rollout_storage_matches_reference_golden(cuda_device):
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    g = load_golden("storage_ppo")
+    dev = cuda_device
+    T, N = g["in_rew"].shape
+    st = RolloutStorage(N, T, (60,), (0,), (8,), dev, "sequential")
+    for t in range(T):
+        st.add_transitions(g["in_obs"][t].to(dev), torch.zeros(N, 0, device=dev), g["in_act"][t].to(dev),
+                           g["in_rew"][t].to(dev), g["in_done"][t].to(dev), g["in_val"][t].to(dev),
+                           g["in_logp"][t].to(dev), g["in_mu"][t].to(dev), g["in_sig"][t].to(dev))
+    with pytest.raises(AssertionError, match="Rollout buffer overflow"):
+        st.add_transitions(g["in_obs"][0].to(dev), torch.zeros(N, 0, device=dev), g["in_act"][0].to(dev),
+                           g["in_rew"][0].to(dev), g["in_done"][0].to(dev), g["in_val"][0].to(dev),
+                           g["in_logp"][0].to(dev), g["in_mu"][0].to(dev), g["in_sig"][0].to(dev))
+    assert torch.equal(st.observations.cpu(), g["in_obs"]) and torch.equal(st.actions.cpu(), g["in_act"])
+    assert torch.equal(st.dones.cpu(), g["dones_u8"]) and st.dones.dtype == torch.uint8
+    assert torch.equal(st.rewards.cpu()[..., 0], g["in_rew"]) and torch.equal(st.mu.cpu(), g["in_mu"])
+    mean_len, mean_rew = st.get_statistics()
+    assert abs(float(mean_len) - float(g["mean_len"])) <= 1e-5 * float(g["mean_len"])
+    assert abs(float(mean_rew) - float(g["mean_rew"])) <= 1e-6 + 1e-5 * abs(float(g["mean_rew"]))
+    st.compute_returns(g["last_values"].to(dev), 0.96, 0.95)
+    # the scan is elementwise-sequential: returns are bit-identical to the reference
+    assert torch.equal(st.returns.cpu(), g["returns"])
+    assert_close_obs(st.advantages, g["advantages"], rtol=1e-5, atol=1e-6, what="normalised advantages")
+    # minibatch partition: sequential sampler, drop_last
+    parts = [b for b in st.mini_batch_generator(4)]
+    assert [len(b) for b in parts] == g["part4_sizes"].tolist()
+    assert torch.equal(torch.cat(parts).cpu(), torch.arange(T * N))
+    parts3 = [b for b in st.mini_batch_generator(3)]
+    assert [len(b) for b in parts3] == g["part3_sizes"].tolist() and int(parts3[-1][-1]) == int(g["part3_last"])
+    # what the unmodified PPO.update does with an index item
+    obs_batch = st.observations.view(-1, 60)[parts[1]]
+    assert torch.equal(obs_batch.cpu(), g["in_obs"].view(-1, 60)[parts[1].cpu()])
+    st.clear()
+    assert st.step == 0
+
+
+def test_gae_large_and_random_sampler(cuda_device):
+    from oracle import storage_oracle as so
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(5)
+    for T, N in ((16, 4096), (3, 1), (17, 1000), (1, 77)):
+        st = RolloutStorage(N, T, (4,), (0,), (2,), dev, "random")
+        r = torch.randn(T, N, 1, generator=gen); v = torch.randn(T, N, 1, generator=gen)
+        d = (torch.rand(T, N, 1, generator=gen) < 0.05).to(torch.uint8); lv = torch.randn(N, 1, generator=gen)
+        st.rewards.copy_(r); st.values.copy_(v); st.dones.copy_(d)
+        st.compute_returns(lv.to(dev), 0.96, 0.95)
+        ret, adv = so.ppo_compute_returns(r, v, d, lv, 0.96, 0.95)
+        assert torch.equal(st.returns.cpu(), ret), (T, N)
+        if T * N > 1:
+            assert_close_obs(st.advantages, adv, rtol=1e-5, atol=1e-6, what="adv T=%d N=%d" % (T, N))
+        # float64 recursion within 1e-5 (property test of SURVEY.md section 4)
+        adv64, ret64 = torch.zeros(N, 1, dtype=torch.float64), torch.zeros(T, N, 1, dtype=torch.float64)
+        for t in reversed(range(T)):
+            nv = lv.double() if t == T - 1 else v[t + 1].double()
+            m = 1.0 - d[t].double()
+            adv64 = r[t].double() + m * 0.96 * nv - v[t].double() + m * 0.96 * 0.95 * adv64
+            ret64[t] = adv64 + v[t].double()
+        assert_close_obs(st.returns, ret64, rtol=1e-5, atol=1e-5, what="returns vs float64")
+        if T * N < 4:
+            continue
+        # random sampler: every epoch a fresh permutation of [0, T*N) cut into equal minibatches
+        it = st.mini_batch_generator(4)
+        e1 = torch.cat([b for b in it]).cpu(); e2 = torch.cat([b for b in it]).cpu()
+        mb = (T * N) // 4
+        assert e1.numel() == 4 * mb and len(set(e1.tolist())) == e1.numel() and int(e1.max()) < T * N and int(e1.min()) >= 0
+        if T * N > 64:
+            assert not torch.equal(e1, e2)
+        # host-supplied permutation (parity mode): identical minibatches to the oracle partition
+        perm = torch.randperm(T * N, generator=gen)
+        st.permutation_override = perm
+        got = [b.cpu().tolist() for b in st.mini_batch_generator(4)]
+        assert got == so.ppo_minibatch_partition(N, T, 4, perm=perm)
+        st.permutation_override = None
+        # fused gather == per-field indexing
+        idx = torch.randperm(T * N, generator=gen)[: max(1, mb)].to(dev)
+        out = st.gather_minibatch(idx)
+        for f in ("observations", "actions", "values", "returns", "advantages", "mu", "sigma", "actions_log_prob"):
+            src = getattr(st, f)
+            assert torch.equal(out[f], src.view(-1, *src.shape[2:])[idx]), f
+
+
+def test_permutation_is_bijection(cuda_device):
+    from massive_marl_benchmark_b200 import _lib as L
+    dev = cuda_device
+    for n in (1, 2, 3, 17, 1000, 65536, 1_000_003):
+        out = torch.empty(n, device=dev, dtype=torch.int64)
+        L.check(L.lib().mmb_permutation(n, 12345 + n, L.ptr(out), L.stream_ptr()), "perm")
+        s = torch.sort(out).values
+        assert torch.equal(s, torch.arange(n, device=dev)), n
+    a = torch.empty(4096, device=dev, dtype=torch.int64); b = torch.empty_like(a)
+    L.lib().mmb_permutation(4096, 1, L.ptr(a), L.stream_ptr()); L.lib().mmb_permutation(4096, 2, L.ptr(b), L.stream_ptr())
+    assert not torch.equal(a, b)
+    assert float((a == torch.arange(4096, device=dev)).float().mean()) < 0.01
+
+
+def test_separated_buffer_matches_reference_golden(cuda_device):
+    from massive_marl_benchmark_b200 import spaces
+    from massive_marl_benchmark_b200.separated_buffer import SeparatedReplayBuffer, runner_insert_masks
+    g = load_golden("buffer_marl")
+    dev = cuda_device
+    T, N = g["in_rewards"].shape[:2]
+    cfg = dict(episode_length=T, n_rollout_threads=N, hidden_size=16, recurrent_N=1, gamma=0.96, gae_lambda=0.95,
+               use_gae=True, use_popart=True, use_valuenorm=False, use_proper_time_limits=False)
+    ob = spaces.Box(low=-np.inf, high=np.inf, shape=(46,)); sh = spaces.Box(low=-np.inf, high=np.inf, shape=(388,))
+    ac = spaces.Box(low=-np.ones(8), high=np.ones(8))
+
+    class Norm:  # PopArt stand-in exposing running_mean_var() (the update rule stays PyTorch, SURVEY #15)
+        def running_mean_var(self):
+            return g["popart_mean"].to(dev), g["popart_var"].to(dev)
+
+    buf = SeparatedReplayBuffer(cfg, ob, sh, ac, dev)
+    rs = torch.zeros(N, 1, 16, device=dev)
+    for t in range(T):
+        buf.insert(g["in_share_obs"][t].to(dev), g["in_obs"][t].to(dev), rs, rs, g["in_actions"][t].to(dev),
+                   g["in_logp"][t].to(dev), g["in_value_preds"][t].to(dev), g["in_rewards"][t].to(dev),
+                   g["in_masks"][t].to(dev), None, g["in_active_masks"][t].to(dev), None)
+    assert buf.step == 0
+    assert torch.equal(buf.share_obs.cpu(), g["buf_share_obs"]) and torch.equal(buf.obs.cpu(), g["buf_obs"])
+    assert torch.equal(buf.masks.cpu(), g["buf_masks"]) and torch.equal(buf.active_masks.cpu(), g["buf_active_masks"])
+    buf.compute_returns(g["next_value"].to(dev), Norm())
+    assert torch.equal(buf.value_preds.cpu(), g["value_preds_after"])
+    assert torch.equal(buf.returns.cpu(), g["returns"])       # sequential scan: bit-identical
+    adv = buf.normalized_advantages(1e-5)
+    assert_close_obs(adv, g["advantages"], rtol=1e-5, atol=1e-6, what="MARL advantages")
+    # other branches of compute_returns
+    for tag, kw, norm in (("plain", dict(use_popart=False, use_valuenorm=False), None),
+                          ("ptl", dict(use_proper_time_limits=True), Norm())):
+        b2 = SeparatedReplayBuffer(dict(cfg, **kw), ob, sh, ac, dev)
+        b2.rewards.copy_(buf.rewards); b2.masks.copy_(buf.masks)
+        b2.value_preds.copy_(g["value_preds_after"].to(dev)); b2.bad_masks.copy_(g["bad_masks_" + tag].to(dev))
+        b2.value_preds[:-1].copy_(torch.stack([g["in_value_preds"][t] for t in range(T)]).to(dev))
+        b2.compute_returns(g["next_value"].to(dev), norm)
+        assert torch.equal(b2.returns.cpu(), g["returns_" + tag]), tag
+    # feed_forward_generator: 13-tuple, host permutation -> identical rows to direct indexing
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(1))
+    buf.permutation_override = perm
+    batches = list(buf.feed_forward_generator(adv, num_mini_batch=2))
+    assert len(batches) == 2 and len(batches[0]) == 13
+    mb = T * N // 2
+    for i, tup in enumerate(batches):
+        idx = perm[i * mb:(i + 1) * mb].to(dev)
+        assert torch.equal(tup[0], buf.share_obs[:-1].reshape(-1, 388)[idx])
+        assert torch.equal(tup[1], buf.obs[:-1].reshape(-1, 46)[idx])
+        assert torch.equal(tup[4], buf.actions.reshape(-1, 8)[idx])
+        assert torch.equal(tup[6], buf.returns[:-1].reshape(-1, 1)[idx])
+        assert torch.equal(tup[9], buf.action_log_probs.reshape(-1, 8)[idx])
+        assert torch.equal(tup[10], adv.reshape(-1, 1)[idx]) and tup[11] is None
+        assert torch.equal(tup[12], buf.factor.reshape(-1, 1)[idx])
+    buf.after_update()
+    assert torch.equal(buf.share_obs[0], buf.share_obs[-1]) and torch.equal(buf.masks[0], buf.masks[-1])
+    # Runner.insert mask logic
+    masks, active = runner_insert_masks(g["runner_dones"].to(dev))
+    assert torch.equal(masks.cpu(), g["runner_masks"]) and torch.equal(active.cpu(), g["runner_active_masks"])
