@@ -273,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = per_launch_bytes / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
     shares = {k: round(v[0] / max(1e-9, sum(x[0] for x in prof.values())), 4) for k, v in prof.items()}
     cpu = None
-    if world == 1 or rank == 0:
+    if args.cpu_rollouts > 0:
         c_val, c_sec, c_thr = cpu_rollouts(args.cpu_rollouts, 1)
         cpu = {"value": c_val, "unit": UNIT, "cores": c_thr, "kind": "port",
                "sample": "%d rollouts of %d steps x %d envs + GAE (oracle port of the reference's torch pipeline)" % (

@@ -32,8 +32,12 @@ __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
 struct f3 { float x, y, z; };
 struct f4 { float x, y, z, w; };  // quaternion (x,y,z,w)
 
-// torch.clamp(x, lo, hi) (NaN propagates)
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// torch.clamp(x, lo, hi) = min(max(x, lo), hi) with NaN propagation: two FMNMX.NAN instead of compare+select pairs
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+  float r;
+  asm("{\n\t.reg .f32 t;\n\tmax.NaN.f32 t, %1, %2;\n\tmin.NaN.f32 %0, t, %3;\n\t}" : "=f"(r) : "f"(x), "f"(lo), "f"(hi));
+  return r;
+}
 
 template <int FLAVOR>
 __device__ __forceinline__ float sum3(float a0, float a1, float a2) {
@@ -112,14 +116,21 @@ __device__ __forceinline__ float remainderf_torch(float a, float b) {
 
 #define MMB_TWO_PI_F 6.28318530717958647692f  // float(2*np.pi): Tensor % python_float casts the scalar to fp32
 
+// remainder(a, 2*pi) for a = atan2f(..) in [-pi, pi]: |a| < 2*pi, so fmod(a, 2*pi) == a exactly and the
+// torch rule reduces to "add 2*pi when negative" (NaN stays NaN: both comparisons are false).
+__device__ __forceinline__ float wrap_angle_2pi(float a) {
+  return (a != 0.0f && a < 0.0f) ? fadd(a, MMB_TWO_PI_F) : a;
+}
+
 // roll and yaw of get_euler_xyz (pitch is computed by the reference but never used on the path)
 __device__ __forceinline__ void euler_roll_yaw(f4 q, float& roll, float& yaw) {
+  float ww = fmul(q.w, q.w), xx = fmul(q.x, q.x), yy = fmul(q.y, q.y), zz = fmul(q.z, q.z);
   float sinr = fmul(2.0f, fadd(fmul(q.w, q.x), fmul(q.y, q.z)));
-  float cosr = fadd(fsub(fsub(fmul(q.w, q.w), fmul(q.x, q.x)), fmul(q.y, q.y)), fmul(q.z, q.z));
-  roll = remainderf_torch(atan2f(sinr, cosr), MMB_TWO_PI_F);
+  float cosr = fadd(fsub(fsub(ww, xx), yy), zz);
+  roll = wrap_angle_2pi(atan2f(sinr, cosr));
   float siny = fmul(2.0f, fadd(fmul(q.w, q.z), fmul(q.x, q.y)));
-  float cosy = fsub(fsub(fadd(fmul(q.w, q.w), fmul(q.x, q.x)), fmul(q.y, q.y)), fmul(q.z, q.z));
-  yaw = remainderf_torch(atan2f(siny, cosy), MMB_TWO_PI_F);
+  float cosy = fsub(fsub(fadd(ww, xx), yy), zz);
+  yaw = wrap_angle_2pi(atan2f(siny, cosy));
 }
 
 // l2_dist (ten_ant.py:975-985): sqrt((a-b)_x^2 + (a-b)_y^2)
@@ -157,12 +168,23 @@ __device__ __forceinline__ AntCore ant_core(f3 p, f4 q, f3 v, f3 w, f4 inv_start
   float nrm = fsqrt(fadd(fmul(tt.x, tt.x), fmul(tt.y, tt.y)));
   if (FLAVOR == FLAVOR_CPU) nrm = fsqrt(__fmaf_rn(tt.y, tt.y, fmul(tt.x, tt.x)));  // CPU vectorised norm (99.3% of rows)
   nrm = nrm < 1e-9f ? 1e-9f : nrm;
-  f3 dir = {fdiv(tt.x, nrm), fdiv(tt.y, nrm), fdiv(tt.z, nrm)};
+  // dir.z = 0 / nrm = 0, so the z term of the heading dot product is (+-)0 and drops out
+  const float dirx = fdiv(tt.x, nrm), diry = fdiv(tt.y, nrm);
   f4 tq = quat_mul(q, inv_start_rot);
-  o.up_vec = quat_rot<false>(tq, f3{0.0f, 0.0f, 1.0f});
-  o.heading_vec = quat_rot<false>(tq, f3{1.0f, 0.0f, 0.0f});
+  // quat_rotate(tq, e_z) and quat_rotate(tq, e_x) with the products by the basis vector's 0s and 1s folded:
+  // x*1 = x and y + (+-0) = y are exact, so for finite inputs every surviving operation is the reference's
+  // (only the sign of an exact-zero result can differ).
+  {
+    const float s = fsub(fmul(2.0f, fmul(tq.w, tq.w)), 1.0f);
+    o.up_vec.x = fadd(fmul(fmul(tq.y, tq.w), 2.0f), fmul(fmul(tq.x, tq.z), 2.0f));
+    o.up_vec.y = fadd(-fmul(fmul(tq.x, tq.w), 2.0f), fmul(fmul(tq.y, tq.z), 2.0f));
+    o.up_vec.z = fadd(s, fmul(fmul(tq.z, tq.z), 2.0f));
+    o.heading_vec.x = fadd(s, fmul(fmul(tq.x, tq.x), 2.0f));
+    o.heading_vec.y = fadd(fmul(fmul(tq.z, tq.w), 2.0f), fmul(fmul(tq.y, tq.x), 2.0f));
+    o.heading_vec.z = fadd(-fmul(fmul(tq.y, tq.w), 2.0f), fmul(fmul(tq.z, tq.x), 2.0f));
+  }
   o.up_proj = o.up_vec.z;
-  o.heading_proj = dot3(o.heading_vec, dir);
+  o.heading_proj = fadd(fmul(o.heading_vec.x, dirx), fmul(o.heading_vec.y, diry));
   o.vel_loc = quat_rot<true>(tq, v);
   o.angvel_loc = quat_rot<true>(tq, w);
   euler_roll_yaw(tq, o.roll, o.yaw);
@@ -191,5 +213,38 @@ __device__ __forceinline__ void tile_load(float* __restrict__ s, const float* __
     for (int i = tid; i < n; i += nthreads) s[i] = __ldg(g + i);
   }
 }
+
+
+// ---- 1-D TMA (cp.async.bulk) + mbarrier helpers: contiguous tiles move global <-> shared without touching the
+// LSU instruction stream (SASS: UBLKCP / SYNCS) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy writes to shared memory must be fenced before the async proxy (TMA) reads them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 }  // namespace mmb

@@ -18,6 +18,8 @@
 // Replaces: ten_ant.py:886-891 (forces), :712-808 + jit :1304-1393 (observations, box goals),
 // :635-710 + jit :988-1301 (reward/reset), :894-926 (progress, carry), vec_task.py:126-131 /
 // multi_vec_task.py:94-144 (clamps and per-agent split).
+#include <cstdlib>
+
 #include "../../include/mmb.h"
 #include "mmb_common.cuh"
 #include "mmb_math.cuh"
@@ -33,11 +35,13 @@ constexpr int PART_W = 6;
 
 template <int EPT>
 struct TenAntSmem {
-  static constexpr int kRoot = EPT * ROOT_ENV;
+  // [ obs tile | root tile (later reused for the per-ant partial terms) | box terms | mbarrier ]
   static constexpr int kObs = EPT * OBS_ENV;
+  static constexpr int kRoot = EPT * ROOT_ENV;
   static constexpr int kBox = EPT * BOX_W;
   static constexpr int kPart = EPT * A * PART_W;
-  static constexpr int kFloats = kRoot + kObs + kBox + kPart;
+  static_assert(kPart <= kRoot, "partials alias the root tile");
+  static constexpr int kFloats = kObs + kRoot + kBox + 4;
   static constexpr int kBytes = kFloats * 4;
 };
 
@@ -64,14 +68,43 @@ __device__ __forceinline__ void goal_of(int k, float bx, float by, float g0x, fl
   }
 }
 
+// smem tile -> global, 128-bit, optional clamp; trip count known at compile time for full tiles
+template <int NT, int N4_FULL, bool CLAMP>
+__device__ __forceinline__ void tile_store(float* __restrict__ g, const float* __restrict__ s, int n, int tid, float clip) {
+  if (aligned16(g)) {
+    const int n4 = n >> 2;
+    if (n4 == N4_FULL) {
+      constexpr int ITERS = (N4_FULL + NT - 1) / NT;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int i = tid + it * NT;
+        if (it < ITERS - 1 || i < N4_FULL) {
+          float4 v = reinterpret_cast<const float4*>(s)[i];
+          if (CLAMP) { v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip); v.z = clampf(v.z, -clip, clip); v.w = clampf(v.w, -clip, clip); }
+          stg4(g + 4 * i, v);
+        }
+      }
+    } else {
+      for (int i = tid; i < n4; i += NT) {
+        float4 v = reinterpret_cast<const float4*>(s)[i];
+        if (CLAMP) { v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip); v.z = clampf(v.z, -clip, clip); v.w = clampf(v.w, -clip, clip); }
+        stg4(g + 4 * i, v);
+      }
+    }
+  } else {
+    for (int i = tid; i < n; i += NT) g[i] = CLAMP ? clampf(s[i], -clip, clip) : s[i];
+  }
+}
+
 template <int FLAVOR, int EPT>
-__global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__ mmb_ten_ant_params p) {
+__global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(const __grid_constant__ mmb_ten_ant_params p) {
   constexpr int NT = EPT * A;
-  extern __shared__ __align__(16) float smem[];
-  float* root_s = smem;
-  float* obs_s = root_s + TenAntSmem<EPT>::kRoot;
-  float* box_s = obs_s + TenAntSmem<EPT>::kObs;
-  float* part_s = box_s + TenAntSmem<EPT>::kBox;
+  extern __shared__ __align__(128) float smem[];
+  float* obs_s = smem;
+  float* root_s = obs_s + TenAntSmem<EPT>::kObs;
+  float* part_s = root_s;  // aliased: every root read happens before the barrier that precedes the first partial write
+  float* box_s = root_s + TenAntSmem<EPT>::kRoot;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(box_s + TenAntSmem<EPT>::kBox);
 
   const int tid = threadIdx.x;
   const int t = blockIdx.y;
@@ -81,36 +114,57 @@ __global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__
   const int ne = min(EPT, N - e0);
   const mmb_ant_consts& c = p.c;
 
-  const float* root_t = p.root + (int64_t)t * p.root_frame_stride;
-  tile_load(root_s, root_t + (int64_t)e0 * ROOT_ENV, ne * ROOT_ENV, tid, NT);
+  // ---- root tile: one 1-D TMA bulk copy for a full, 16B-aligned tile; cooperative loads otherwise ----
+  const float* root_g = p.root + (int64_t)t * p.root_frame_stride + (int64_t)e0 * ROOT_ENV;
+  const bool use_tma = (ne == EPT) && aligned16(root_g);
+  if (use_tma) {
+    if (tid == 0) {
+      mbar_init(mbar, 1);
+      mbar_expect_tx(mbar, EPT * ROOT_ENV * 4);
+      tma_load_1d(root_s, root_g, EPT * ROOT_ENV * 4, mbar);
+    }
+  } else {
+    tile_load(root_s, root_g, ne * ROOT_ENV, tid, NT);
+  }
 
   const int el = tid / A, k = tid - el * A;
   const int e = e0 + el;
   const bool active = el < ne;
+  // the tile holds clamped values unless the unclamped task.obs_buf is requested as well
+  const bool tile_clamped = (p.obs_raw == nullptr);
+  const float clip = p.clip_obs;
+  const float tclip = tile_clamped ? clip : __int_as_float(0x7f800000);
 
   float dps[8], dvs[8], act[8];
   float pbx = 0.f, pby = 0.f, gbx = 0.f, gby = 0.f;
   if (active) {
     const float* d = p.dof + (int64_t)t * p.dof_frame_stride + ((int64_t)e * 80 + 8 * k) * 2;
+    const float* a = p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
     float raw[16];
-    if (aligned16(d)) {
+    if (aligned16(d) && aligned16(a)) {
+      float4 v[4], w0, w1;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 v = ldg4(d + 4 * j);
-        raw[4 * j] = v.x; raw[4 * j + 1] = v.y; raw[4 * j + 2] = v.z; raw[4 * j + 3] = v.w;
-      }
+      for (int j = 0; j < 4; ++j) v[j] = ldg4(d + 4 * j);
+      w0 = ldg4(a);
+      w1 = ldg4(a + 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { raw[4 * j] = v[j].x; raw[4 * j + 1] = v[j].y; raw[4 * j + 2] = v[j].z; raw[4 * j + 3] = v[j].w; }
+      act[0] = w0.x; act[1] = w0.y; act[2] = w0.z; act[3] = w0.w;
+      act[4] = w1.x; act[5] = w1.y; act[6] = w1.z; act[7] = w1.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) raw[j] = __ldg(d + j);
-    }
-    const float* a = p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
-    if (aligned16(a)) {
-      float4 v0 = ldg4(a), v1 = ldg4(a + 4);
-      act[0] = v0.x; act[1] = v0.y; act[2] = v0.z; act[3] = v0.w;
-      act[4] = v1.x; act[5] = v1.y; act[6] = v1.z; act[7] = v1.w;
-    } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) act[j] = __ldg(a + j);
+    }
+    if (t == 0) {
+      const float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
+      const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+      pbx = __ldg(pb); pby = __ldg(pb + 1);
+      gbx = __ldg(gb); gby = __ldg(gb + 1);
+    } else {  // carry of step t = ant xy of frame t-1 (ten_ant.py:905-914)
+      const float* rp = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)e * 11 + k) * 13;
+      pbx = __ldg(rp); pby = __ldg(rp + 1);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -131,19 +185,20 @@ __global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__
         for (int j = 0; j < 8; ++j) f[j] = fo[j];
       }
     }
-    if (t == 0) {
-      const float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
-      const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
-      pbx = __ldg(pb); pby = __ldg(pb + 1);
-      gbx = __ldg(gb); gby = __ldg(gb + 1);
-    } else {  // carry of step t = ant xy of frame t-1 (ten_ant.py:905-914)
-      const float* rp = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)e * 11 + k) * 13;
-      pbx = __ldg(rp); pby = __ldg(rp + 1);
-    }
   }
-  __syncthreads();
+  __syncthreads();                       // mbarrier initialised (TMA path) / tile stores visible (fallback path)
+  if (use_tma) mbar_wait(mbar, 0);
 
-  // ---- box phase: goal directions of frame t (and of frame t-1 when it is the carry source) ----
+  // ---- every ant thread lifts its root row into registers; box threads derive the goal directions ----
+  f3 pos = {0.f, 0.f, 0.f}, vel = pos, ang = pos;
+  f4 q = {0.f, 0.f, 0.f, 1.f};
+  if (active) {
+    const float* r = root_s + el * ROOT_ENV + k * 13;
+    pos = f3{r[0], r[1], r[2]};
+    q = f4{r[3], r[4], r[5], r[6]};
+    vel = f3{r[7], r[8], r[9]};
+    ang = f3{r[10], r[11], r[12]};
+  }
   if (tid < 2 * EPT) {
     const int which = tid / EPT, bl = tid - which * EPT;
     if (bl < ne) {
@@ -155,7 +210,9 @@ __global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__
         bo[0] = s; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
         bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
         float* tail = obs_s + bl * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
-        tail[0] = b[0]; tail[1] = b[1]; tail[2] = b[3]; tail[3] = b[4]; tail[4] = b[5]; tail[5] = b[6];
+        tail[0] = clampf(b[0], -tclip, tclip); tail[1] = clampf(b[1], -tclip, tclip);
+        tail[2] = clampf(b[3], -tclip, tclip); tail[3] = clampf(b[4], -tclip, tclip);
+        tail[4] = clampf(b[5], -tclip, tclip); tail[5] = clampf(b[6], -tclip, tclip);
         tail[6] = 0.0f; tail[7] = 0.0f;
       } else if (t > 0) {
         const float* b = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)(e0 + bl) * 11 + 10) * 13;
@@ -166,23 +223,23 @@ __global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__
       }
     }
   }
-  __syncthreads();
+  __syncthreads();                       // box terms ready; all reads of the root tile are done (part_s may overwrite it)
 
   // ---- ant phase ----
   if (active) {
-    const float* r = root_s + el * ROOT_ENV + k * 13;
-    f3 pos = {r[0], r[1], r[2]};
-    f4 q = {r[3], r[4], r[5], r[6]};
-    f3 v = {r[7], r[8], r[9]};
-    f3 w = {r[10], r[11], r[12]};
-    AntCore o = ant_core<FLAVOR>(pos, q, v, w, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
+    AntCore o = ant_core<FLAVOR>(pos, q, vel, ang, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
     float* ob = obs_s + el * OBS_ENV + k * 38;
-    ob[0] = pos.x; ob[1] = pos.y; ob[2] = pos.z;
-    ob[3] = o.vel_loc.x; ob[4] = o.vel_loc.y; ob[5] = o.vel_loc.z;
-    ob[6] = o.angvel_loc.x; ob[7] = o.angvel_loc.y; ob[8] = o.angvel_loc.z;
-    ob[9] = o.yaw; ob[10] = o.roll; ob[11] = o.angle_to_target; ob[12] = o.up_proj; ob[13] = o.heading_proj;
+    ob[0] = clampf(pos.x, -tclip, tclip); ob[1] = clampf(pos.y, -tclip, tclip); ob[2] = clampf(pos.z, -tclip, tclip);
+    ob[3] = clampf(o.vel_loc.x, -tclip, tclip); ob[4] = clampf(o.vel_loc.y, -tclip, tclip); ob[5] = clampf(o.vel_loc.z, -tclip, tclip);
+    ob[6] = clampf(o.angvel_loc.x, -tclip, tclip); ob[7] = clampf(o.angvel_loc.y, -tclip, tclip); ob[8] = clampf(o.angvel_loc.z, -tclip, tclip);
+    ob[9] = clampf(o.yaw, -tclip, tclip); ob[10] = clampf(o.roll, -tclip, tclip); ob[11] = clampf(o.angle_to_target, -tclip, tclip);
+    ob[12] = clampf(o.up_proj, -tclip, tclip); ob[13] = clampf(o.heading_proj, -tclip, tclip);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ob[14 + j] = dps[j]; ob[22 + j] = dvs[j]; ob[30 + j] = act[j]; }
+    for (int j = 0; j < 8; ++j) {
+      ob[14 + j] = clampf(dps[j], -tclip, tclip);
+      ob[22 + j] = clampf(dvs[j], -tclip, tclip);
+      ob[30 + j] = clampf(act[j], -tclip, tclip);
+    }
 
     const float* bo = box_s + el * BOX_W;
     float gx, gy;
@@ -221,7 +278,26 @@ __global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__
       pb[0] = pos.x; pb[1] = pos.y; gb[0] = gx; gb[1] = gy;
     }
   }
+  fence_async_smem();                    // obs tile writes -> visible to the TMA store engine
   __syncthreads();
+
+  // ---- obs tile out ----
+  const int n = ne * OBS_ENV;
+  float* obs_dst = nullptr;              // destination served by the TMA bulk store (a verbatim copy of the tile)
+  if (tile_clamped) obs_dst = (p.obs_layout == 0) ? p.obs : p.share_obs;
+  else obs_dst = p.obs_raw;
+  const int64_t dst_stride = tile_clamped ? ((p.obs_layout == 0) ? p.obs_frame_stride : p.share_obs_frame_stride)
+                                          : p.obs_raw_frame_stride;
+  bool tma_stored = false;
+  if (obs_dst) {
+    float* g = obs_dst + (int64_t)t * dst_stride + (int64_t)e0 * OBS_ENV;
+    if (aligned16(g)) {
+      if (tid == 0) tma_store_1d(g, obs_s, (uint32_t)n * 4u);
+      tma_stored = true;
+    } else {
+      tile_store<NT, EPT * OBS_ENV / 4, false>(g, obs_s, n, tid, clip);
+    }
+  }
 
   // ---- per-env finish: ordered sums over the ten ants (ten_ant.py:1173-1301) ----
   if (tid < ne) {
@@ -233,9 +309,9 @@ __global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__
     bool fallen = (fl & 0x200) != 0;
 #pragma unroll
     for (int kk = 1; kk < A; ++kk) {
-      const float* q = pt + kk * PART_W;
-      adr = fadd(adr, q[0]); gdr = fadd(gdr, q[1]); up = fadd(up, q[2]); elec = fadd(elec, q[3]); asq = fadd(asq, q[4]);
-      int f2 = __float_as_int(q[5]);
+      const float* qq = pt + kk * PART_W;
+      adr = fadd(adr, qq[0]); gdr = fadd(gdr, qq[1]); up = fadd(up, qq[2]); elec = fadd(elec, qq[3]); asq = fadd(asq, qq[4]);
+      int f2 = __float_as_int(qq[5]);
       lim += f2 & 0xff; n_arrive += (f2 >> 8) & 1; fallen = fallen || (f2 & 0x200);
     }
     const float* bo = box_s + tid * BOX_W;
@@ -269,62 +345,29 @@ __global__ void __launch_bounds__(EPT* A) ten_ant_kernel(const __grid_constant__
     }
   }
 
-  // ---- obs tile out ----
-  const float clip = p.clip_obs;
-  if (p.obs_raw) {
-    float* g = p.obs_raw + (int64_t)t * p.obs_raw_frame_stride + (int64_t)e0 * OBS_ENV;
-    const int n = ne * OBS_ENV;
-    if (aligned16(g)) {
-      for (int i = tid; i < (n >> 2); i += NT) stg4(g + 4 * i, reinterpret_cast<const float4*>(obs_s)[i]);
-    } else {
-      for (int i = tid; i < n; i += NT) g[i] = obs_s[i];
+  // ---- outputs that are not a verbatim copy of the tile ----
+  if (!tile_clamped) {  // raw tile: clamped outputs need a pass
+    if (p.obs_layout == 0 && p.obs) {
+      tile_store<NT, EPT * OBS_ENV / 4, true>(p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
+    } else if (p.obs_layout == 1 && p.share_obs) {
+      tile_store<NT, EPT * OBS_ENV / 4, true>(p.share_obs + (int64_t)t * p.share_obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
     }
   }
-  if (p.obs_layout == 0) {
-    if (p.obs) {
-      float* g = p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * OBS_ENV;
-      const int n = ne * OBS_ENV;
-      if (aligned16(g)) {
-        for (int i = tid; i < (n >> 2); i += NT) {
-          float4 v = reinterpret_cast<const float4*>(obs_s)[i];
-          v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip);
-          v.z = clampf(v.z, -clip, clip); v.w = clampf(v.w, -clip, clip);
-          stg4(g + 4 * i, v);
-        }
-      } else {
-        for (int i = tid; i < n; i += NT) g[i] = clampf(obs_s[i], -clip, clip);
-      }
-    }
-  } else {
-    if (p.share_obs) {  // multi_vec_task.py:118: clamped 388-wide state, stored once per env
-      float* g = p.share_obs + (int64_t)t * p.share_obs_frame_stride + (int64_t)e0 * OBS_ENV;
-      const int n = ne * OBS_ENV;
-      if (aligned16(g)) {
-        for (int i = tid; i < (n >> 2); i += NT) {
-          float4 v = reinterpret_cast<const float4*>(obs_s)[i];
-          v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip);
-          v.z = clampf(v.z, -clip, clip); v.w = clampf(v.w, -clip, clip);
-          stg4(g + 4 * i, v);
-        }
-      } else {
-        for (int i = tid; i < n; i += NT) g[i] = clampf(obs_s[i], -clip, clip);
-      }
-    }
-    if (p.obs) {  // multi_vec_task.py:105-116: per agent cat(own 38, tail 8) -> [N][10][46]
-      float* g = p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * 460;
-      const int n2 = ne * 230;  // float2 granules: 46 and 38 are even, so a pair never straddles a boundary
-      const bool al8 = (reinterpret_cast<uintptr_t>(g) & 7u) == 0;
-      for (int i = tid; i < n2; i += NT) {
-        int er = i / 230, r2 = i - er * 230;
-        int a = r2 / 23, c2 = r2 - a * 23;
-        int src = er * OBS_ENV + (c2 < 19 ? a * 38 + 2 * c2 : 380 + 2 * (c2 - 19));
-        float2 v = *reinterpret_cast<const float2*>(obs_s + src);
-        v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip);
-        if (al8) *reinterpret_cast<float2*>(g + 2 * i) = v;
-        else { g[2 * i] = v.x; g[2 * i + 1] = v.y; }
-      }
+  if (p.obs_layout == 1 && p.obs) {  // multi_vec_task.py:105-116: per agent cat(own 38, tail 8) -> [N][10][46]
+    float* g = p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * 460;
+    const int n2 = ne * 230;  // float2 granules: 46 and 38 are even, so a pair never straddles a boundary
+    const bool al8 = (reinterpret_cast<uintptr_t>(g) & 7u) == 0;
+    for (int i = tid; i < n2; i += NT) {
+      int er = i / 230, r2 = i - er * 230;
+      int a = r2 / 23, c2 = r2 - a * 23;
+      int src = er * OBS_ENV + (c2 < 19 ? a * 38 + 2 * c2 : 380 + 2 * (c2 - 19));
+      float2 v = *reinterpret_cast<const float2*>(obs_s + src);
+      if (!tile_clamped) { v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip); }
+      if (al8) *reinterpret_cast<float2*>(g + 2 * i) = v;
+      else { g[2 * i] = v.x; g[2 * i + 1] = v.y; }
     }
   }
+  if (tma_stored && tid == 0) tma_store_wait_read();  // the tile must stay intact until the bulk store has read it
 }
 
 // progress / reset chain over the T frames of a horizon-batched launch (ten_ant.py:896-901,1296-1299)
@@ -397,8 +440,13 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
   if (p.obs_layout != 0 && p.obs_layout != 1) return MMB_EINVAL;
   if (p.flavor != MMB_FLAVOR_CUDA && p.flavor != MMB_FLAVOR_CPU) return MMB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  int32_t rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, MMB_TEN_ANT_EPT>(p, st)
-                                             : launch_ten_ant<FLAVOR_CPU, MMB_TEN_ANT_EPT>(p, st);
+  // tile size: 32 envs (320 threads) by default; MMB_TEN_ANT_EPT=16 selects the 16-env tile (tuning knob)
+  static const int ept = [] { const char* v = getenv("MMB_TEN_ANT_EPT"); return (v && atoi(v) == 16) ? 16 : MMB_TEN_ANT_EPT; }();
+  int32_t rc;
+  if (ept == 16)
+    rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, 16>(p, st) : launch_ten_ant<FLAVOR_CPU, 16>(p, st);
+  else
+    rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, 32>(p, st) : launch_ten_ant<FLAVOR_CPU, 32>(p, st);
   if (rc != MMB_OK) return rc;
   if (p.num_frames > 1) {
     {
