@@ -187,38 +187,87 @@ def run_ours(args, rank, world, local_rank):
         st.process_group = True if world > 1 else None
     last_values = torch.randn(N, 1, device=dev)
     reset_out = [None]
+    launches_per_rollout = [0]
+    side = torch.cuda.Stream()
 
     def rollout(i):
         s = i % SETS
         st, fr = storages[s], dev_frames[s]
         # observation after step t lands in obs slot t+1; reward/done of step t in slot t (no add_transitions pass)
         task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), None, forces[s])
-        reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
+        # reset_idx of the T steps and GAE both depend only on the done flags: fork them (side stream joins back)
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
         st.compute_returns(last_values, GAMMA, LAM)
+        main.wait_stream(side)
+
+    _l0 = L.launch_count()
+    rollout(0)
+    launches_per_rollout[0] = L.launch_count() - _l0
+    for i in range(max(W, SETS)):
+        rollout(i)
+    barrier()
+    # The rollout is 5 short launches after the main kernel: capture it once per frame/storage set in a CUDA graph
+    # so the launch-bound tail is replayed without per-launch CPU cost (eager fallback if capture is unavailable).
+    graphs = None
+    if not args.no_graph:
+        try:
+            graphs = []
+            for s_ in range(SETS):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    rollout(s_)
+                graphs.append(g)
+            for s_ in range(SETS):
+                graphs[s_].replay()
+            torch.cuda.synchronize()
+        except Exception as ex:  # pragma: no cover
+            print("cuda graph capture failed, running eagerly: %r" % (ex,), file=sys.stderr)
+            graphs = None
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % SETS].replay()
+        else:
+            rollout(i)
 
     for i in range(W):
-        rollout(i)
+        run_step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    L.profile_enable(True)
-    L.profile_collect()
     launches0 = L.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_host0 = time.perf_counter()
     ev0.record()
     for i in range(K):
-        rollout(W + i)
+        run_step(W + i)
     ev1.record()
     barrier()
     t_host1 = time.perf_counter()
     sampler.stop()
-    L.profile_enable(False)
-    launches = L.launch_count() - launches0
-    prof = L.profile_collect()
+    launches = (L.launch_count() - launches0) if graphs is None else K * launches_per_rollout[0]
     ms = mdist.max_over_ranks(ev0.elapsed_time(ev1), dev)
     value = K * T * N * world / (ms * 1e-3)
+
+    # ---- per-kernel durations: the same rollouts launched eagerly, every kernel bracketed by CUDA events on its
+    # launch stream (library-side, mmb_profile_*); inputs rotate exactly as above ---------------------------------
+    KP = max(3, min(K, 200))
+    L.profile_enable(True)
+    L.profile_collect()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    pe0.record()
+    for i in range(KP):
+        rollout(i)
+    pe1.record()
+    barrier()
+    L.profile_enable(False)
+    prof = L.profile_collect()
+    eager_ms_per_step = pe0.elapsed_time(pe1) / KP
 
     # ---- end-to-end through the reference-facing API with host buffers -----------------------------
     K2 = max(2, min(K, 20))
@@ -280,7 +329,8 @@ def run_ours(args, rank, world, local_rank):
                    args.cpu_rollouts, T, N)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / K, "ms_per_step_eager_profiled": eager_ms_per_step, "cuda_graph": graphs is not None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE",
                    "num_envs_per_gpu": N, "num_agents": 10, "horizon": T, "env_steps_per_step": T * N,
@@ -306,6 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rollouts", type=int, default=8)
+    ap.add_argument("--no-graph", action="store_true", help="launch the rollout eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -124,6 +124,10 @@ typedef struct {
   int64_t* dones_i64; int64_t dones_i64_frame_stride; /* [T][N] reset_buf after each step */
   uint8_t* dones_u8;  int64_t dones_u8_frame_stride;  /* [T][N] same, as RolloutStorage.dones */
   float* forces;    int64_t forces_frame_stride;    /* [T][N][80] clamp(actions)*gear*power_scale */
+  /* T > 1 only, optional: N zero-initialised uint64 words owned by the caller (self-resetting).  With it (and
+   * T <= 32) the progress/reset chain and the carry are resolved inside the main kernel by the thread that delivers
+   * the last frame of an env; without it (NULL) a second small kernel does the same work. */
+  uint64_t* scratch;
   mmb_ant_consts c;
 } mmb_ten_ant_params;
 
@@ -259,13 +263,16 @@ typedef struct {
   double gamma, lam;         /* Python floats of cfg/ppo/config.yaml:30-31; each is cast to fp32 where torch does */
   float* returns;            /* [T][N] */
   float* advantages;         /* [T][N] raw (returns - values) */
-  double* stats;             /* [3] or NULL */
+  double* stats;             /* [4] ({count,sum,sumsq}, [3] reserved) or NULL */
 } mmb_gae_ppo_params;
 MMB_API int32_t mmb_gae_ppo(const mmb_gae_ppo_params* p, void* stream);
 
 /* (adv - mean) / (std_unbiased + eps) in place; mean/std from stats = {count, sum, sumsq} on device.
- * eps = 1e-8 (storage.py:65) or 1e-5 (mappo_trainer.py:199). */
-MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, const double* stats, float eps, void* stream);
+ * eps = 1e-8 (storage.py:65) or 1e-5 (mappo_trainer.py:199).  `stats` has FOUR doubles: [3] is a ticket counter
+ * owned by the library (zero-initialise once).  With clear_stats != 0 the last block to read the statistics
+ * clears them, so the accumulator is ready for the next rollout without a memset launch (CUDA-graph safe). */
+MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, float eps, int32_t clear_stats,
+                                  void* stream);
 
 /* RolloutStorage.get_statistics (storage.py:67-73) on device: out[0] = mean trajectory length,
  * out[1] = mean reward.  No host sync. */
@@ -290,7 +297,7 @@ typedef struct {
   float* advantages;     int64_t adv_t, adv_e, adv_a;      /* T, raw returns - D(value_preds); NULL to skip */
   const float* denorm_mean; const float* denorm_var;       /* [A] device scalars (running_mean_var) */
   double gamma, gae_lambda;  /* Python floats; gamma*gae_lambda is formed in double like the reference does */
-  double* stats;         /* [A][3] accumulated {count, sum, sumsq} per agent, or NULL */
+  double* stats;         /* [A][4] accumulated {count, sum, sumsq, reserved} per agent, or NULL */
 } mmb_gae_marl_params;
 MMB_API int32_t mmb_gae_marl(const mmb_gae_marl_params* p, void* stream);
 

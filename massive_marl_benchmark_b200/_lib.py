@@ -41,7 +41,7 @@ class TenAntParams(C.Structure):
         ("obs_raw", c_vp), ("obs_raw_frame_stride", c_i64), ("obs", c_vp), ("obs_frame_stride", c_i64),
         ("share_obs", c_vp), ("share_obs_frame_stride", c_i64), ("rewards", c_vp), ("rewards_frame_stride", c_i64),
         ("dones_i64", c_vp), ("dones_i64_frame_stride", c_i64), ("dones_u8", c_vp), ("dones_u8_frame_stride", c_i64),
-        ("forces", c_vp), ("forces_frame_stride", c_i64), ("c", AntConsts)]
+        ("forces", c_vp), ("forces_frame_stride", c_i64), ("scratch", c_vp), ("c", AntConsts)]
 
 
 class OneAntParams(C.Structure):
@@ -131,7 +131,7 @@ SYMBOLS = {
     "mmb_reset_compact": (c_i32, [C.POINTER(ResetParams), c_vp]),
     "mmb_rollout_add": (c_i32, [C.POINTER(RolloutAddParams), c_vp]),
     "mmb_gae_ppo": (c_i32, [C.POINTER(GaePpoParams), c_vp]),
-    "mmb_adv_normalize": (c_i32, [c_vp, c_i64, c_vp, c_f, c_vp]),
+    "mmb_adv_normalize": (c_i32, [c_vp, c_i64, c_vp, c_f, c_i32, c_vp]),
     "mmb_rollout_statistics": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mmb_gae_marl": (c_i32, [C.POINTER(GaeMarlParams), c_vp]),
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),

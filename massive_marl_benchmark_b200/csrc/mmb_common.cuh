@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 #ifndef MMB_TEN_ANT_EPT
-#define MMB_TEN_ANT_EPT 32  // environments per CTA tile of the TenAnt kernel (multiple of 4)
+#define MMB_TEN_ANT_EPT 16  // environments per CTA tile of the TenAnt kernel (multiple of 4): 16 or 32
 #endif
 #define MMB_MAX_DEVICES 16
 

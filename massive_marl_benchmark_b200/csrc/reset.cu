@@ -58,31 +58,41 @@ __global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb
 
   if (tid == 0) s_running = 0;
   __syncthreads();
-  for (int base = 0; base < N; base += 1024) {
-    const int e = base + tid;
-    bool flag = false;
-    if (e < N) flag = f64 ? (f64[e] != 0) : (f8[e] != 0);
-    const unsigned bal = __ballot_sync(0xffffffffu, flag);
-    const int wprefix = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[wid] = __popc(bal);
-    __syncthreads();
-    int running = s_running;
-    int woff = 0, tot = 0;
+  constexpr int PRE = 8;  // flag loads of 8 chunks are issued together: one memory latency per 8192 envs
+  for (int base0 = 0; base0 < N; base0 += PRE * 1024) {
+    unsigned pre = 0;
+#pragma unroll
+    for (int c = 0; c < PRE; ++c) {
+      const int e = base0 + c * 1024 + tid;
+      bool fl = false;
+      if (e < N) fl = f64 ? (f64[e] != 0) : (f8[e] != 0);
+      pre |= (fl ? 1u : 0u) << c;
+    }
+    for (int c = 0; c < PRE && base0 + c * 1024 < N; ++c) {
+      const int e = base0 + c * 1024 + tid;
+      const bool flag = (pre >> c) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      const int wprefix = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) warp_tot[wid] = __popc(bal);
+      __syncthreads();
+      const int running = s_running;
+      int woff = 0, tot = 0;
 #pragma unroll 8
-    for (int w = 0; w < 32; ++w) {
-      int v = warp_tot[w];
-      woff += (w < wid) ? v : 0;
-      tot += v;
+      for (int w = 0; w < 32; ++w) {
+        int v = warp_tot[w];
+        woff += (w < wid) ? v : 0;
+        tot += v;
+      }
+      if (flag) {
+        const int i = running + woff + wprefix;
+        env_ids[i] = e;
+        if (ia) for (int j = 0; j < sh.na; ++j) ia[i * sh.na + j] = sh.apn * e + j;
+        if (ib) for (int j = 0; j < sh.nb; ++j) ib[i * sh.nb + j] = sh.apn * e + j;
+      }
+      __syncthreads();
+      if (tid == 0) s_running = running + tot;
+      __syncthreads();
     }
-    if (flag) {
-      const int i = running + woff + wprefix;
-      env_ids[i] = e;
-      if (ia) for (int j = 0; j < sh.na; ++j) ia[i * sh.na + j] = sh.apn * e + j;
-      if (ib) for (int j = 0; j < sh.nb; ++j) ib[i * sh.nb + j] = sh.apn * e + j;
-    }
-    __syncthreads();
-    if (tid == 0) s_running = running + tot;
-    __syncthreads();
   }
   const int count = s_running;
   if (tid == 0 && p.counts) p.counts[f] = count;

@@ -43,7 +43,7 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
 // ------------------------------------------------------------------------------------------------
 // RolloutStorage.compute_returns (storage.py:51-65)
 // ------------------------------------------------------------------------------------------------
-constexpr int GAE_CHUNK = 8;
+constexpr int GAE_CHUNK = 16;  // horizon 16 (the reference's default is 8): all loads of a rollout in flight at once
 
 __global__ void __launch_bounds__(256) gae_ppo_kernel(const __grid_constant__ mmb_gae_ppo_params p) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,10 +93,22 @@ __global__ void __launch_bounds__(256) gae_ppo_kernel(const __grid_constant__ mm
   }
 }
 
-// (adv - mean) / (std_unbiased + eps)
-__global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ adv, int64_t n,
-                                                            const double* __restrict__ stats, float eps) {
+// (adv - mean) / (std_unbiased + eps).  With `clear_stats` the last block to have read the statistics clears them
+// (ticket counter in stats[3]), so the accumulator is ready for the next rollout without a memset launch and
+// the launch sequence can be replayed from a CUDA graph.
+__global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ adv, int64_t n, double* __restrict__ stats,
+                                                            float eps, int clear_stats) {
   const double cnt = stats[0], s1 = stats[1], s2 = stats[2];
+  if (clear_stats) {
+    __syncthreads();  // every thread of this block holds its copy
+    if (threadIdx.x == 0) {
+      unsigned long long* ticket = reinterpret_cast<unsigned long long*>(stats + 3);
+      if (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        stats[0] = 0.0; stats[1] = 0.0; stats[2] = 0.0;
+        *ticket = 0ull;
+      }
+    }
+  }
   const double mean_d = s1 / cnt;
   double var_d = (s2 - s1 * mean_d) / (cnt - 1.0);  // torch.std(): unbiased
   if (var_d < 0.0) var_d = 0.0;
@@ -243,9 +255,9 @@ __global__ void __launch_bounds__(256) gae_marl_kernel(const __grid_constant__ m
   if (p.stats && p.advantages) {
     block_sum2(s1, s2);
     if (threadIdx.x == 0) {
-      atomicAdd(p.stats + 3 * a + 1, s1);
-      atomicAdd(p.stats + 3 * a + 2, s2);
-      if (blockIdx.x == 0) atomicAdd(p.stats + 3 * a + 0, (double)N * (double)T);
+      atomicAdd(p.stats + 4 * a + 1, s1);
+      atomicAdd(p.stats + 4 * a + 2, s2);
+      if (blockIdx.x == 0) atomicAdd(p.stats + 4 * a + 0, (double)N * (double)T);
     }
   }
 }
@@ -281,14 +293,15 @@ extern "C" int32_t mmb_gae_ppo(const mmb_gae_ppo_params* pp, void* stream) {
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
-extern "C" int32_t mmb_adv_normalize(float* advantages, int64_t n, const double* stats, float eps, void* stream) {
+extern "C" int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, float eps, int32_t clear_stats,
+                                     void* stream) {
   if (!advantages || !stats || n <= 0) return MMB_EINVAL;
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
   {
     LaunchScope ls(K_ADV_NORM, (cudaStream_t)stream);
-    adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps);
+    adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps, clear_stats);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

@@ -68,6 +68,63 @@ __device__ __forceinline__ void goal_of(int k, float bx, float by, float g0x, fl
   }
 }
 
+// carry of one (env, ant) from a root tensor (ten_ant.py:870-882)
+__device__ __forceinline__ void load_carry_one(const float* __restrict__ root, int i, float* pos_before, float* goal_before,
+                                               float* box_before) {
+  const int e = i / A, k = i - e * A;
+  const float* r = root + ((int64_t)e * 11 + k) * 13;
+  const float* b = root + ((int64_t)e * 11 + 10) * 13;
+  const float px = __ldg(r), py = __ldg(r + 1), bx = __ldg(b), by = __ldg(b + 1), qz = __ldg(b + 5), qw = __ldg(b + 6);
+  float s, cs, gx, gy;
+  box_dir(qz, qw, s, cs);
+  goal_of(k, bx, by, s, cs, gx, gy);
+  *reinterpret_cast<float2*>(pos_before + 2 * (int64_t)i) = make_float2(px, py);
+  *reinterpret_cast<float2*>(goal_before + 2 * (int64_t)i) = make_float2(gx, gy);
+  if (k == 0) *reinterpret_cast<float2*>(box_before + 2 * (int64_t)e) = make_float2(bx, by);
+}
+
+// progress / reset chain of one env over frames [t0, t0+cnt) given their `fallen` bits
+// (ten_ant.py:896-901 progress += 1 and reset_idx zeroing, :1296-1299 reset rule); writes the final done flags.
+__device__ __forceinline__ void chain_bits(const mmb_ten_ant_params& p, int e, int t0, int cnt, uint32_t fallen_bits,
+                                           int64_t& prog, bool& flag) {
+  const float thr = (float)((double)p.c.max_episode_length - 1.0);
+  uint32_t out_bits = 0;
+  for (int j = 0; j < cnt; ++j) {
+    prog = flag ? 0 : prog + 1;
+    flag = ((fallen_bits >> j) & 1u) || ((float)prog >= thr);
+    out_bits |= (flag ? 1u : 0u) << j;
+  }
+#pragma unroll 8
+  for (int j = 0; j < cnt; ++j) {
+    const int t = t0 + j;
+    const int v = (out_bits >> j) & 1u;
+    if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + e] = (uint8_t)v;
+    if (p.dones_i64) p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + e] = v;
+  }
+}
+
+// chain of one env with the `fallen` flags read back from the done plane (fallback path: T > 32 or no scratch).
+// All flags of a 32-frame chunk are loaded before the dependent chain runs: one memory latency, not T.
+__device__ __forceinline__ void chain_one(const mmb_ten_ant_params& p, int e) {
+  const int T = p.num_frames;
+  int64_t prog = p.progress_buf[e];
+  bool flag = p.reset_buf[e] != 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int cnt = min(32, T - t0);
+    uint32_t fallen_bits = 0;
+#pragma unroll 8
+    for (int j = 0; j < cnt; ++j) {
+      const int t = t0 + j;
+      const bool f = p.dones_u8 ? (__ldcg(p.dones_u8 + (int64_t)t * p.dones_u8_frame_stride + e) != 0)
+                                : (__ldcg(p.dones_i64 + (int64_t)t * p.dones_i64_frame_stride + e) != 0);
+      fallen_bits |= (f ? 1u : 0u) << j;
+    }
+    chain_bits(p, e, t0, cnt, fallen_bits, prog, flag);
+  }
+  p.progress_buf[e] = prog;
+  p.reset_buf[e] = flag ? 1 : 0;
+}
+
 // smem tile -> global, 128-bit, optional clamp; trip count known at compile time for full tiles
 template <int NT, int N4_FULL, bool CLAMP>
 __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* __restrict__ s, int n, int tid, float clip) {
@@ -96,6 +153,20 @@ __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* _
   }
 }
 
+template <int EPT>
+struct UnitIdx {
+  int tile, t, e0, ne;
+  __device__ __forceinline__ UnitIdx(int u, int ntiles, int N) {
+    t = u / ntiles;              // env tile fastest: neighbouring CTAs stream neighbouring memory of one frame
+    tile = u - t * ntiles;
+    e0 = tile * EPT;
+    ne = min(EPT, N - e0);
+  }
+};
+
+// One CTA = one unit = one tile of EPT envs of one frame.  Short-lived CTAs at 64 registers keep 6 (EPT 16) or 3
+// (EPT 32) CTAs = 30 warps per SM resident: the kernel is a long dependent fp32 chain per thread, so it lives on
+// thread-level parallelism (a persistent, register-prefetching variant at 96 registers measured 40% slower).
 template <int FLAVOR, int EPT>
 __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(const __grid_constant__ mmb_ten_ant_params p) {
   constexpr int NT = EPT * A;
@@ -107,11 +178,11 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
   uint64_t* mbar = reinterpret_cast<uint64_t*>(box_s + TenAntSmem<EPT>::kBox);
 
   const int tid = threadIdx.x;
-  const int t = blockIdx.y;
+  const int wid = tid >> 5, lane = tid & 31;
   const int N = p.num_envs;
   const int T = p.num_frames;
-  const int e0 = blockIdx.x * EPT;
-  const int ne = min(EPT, N - e0);
+  const UnitIdx<EPT> ui(blockIdx.x, (N + EPT - 1) / EPT, N);
+  const int t = ui.t, e0 = ui.e0, ne = ui.ne;
   const mmb_ant_consts& c = p.c;
 
   // ---- root tile: one 1-D TMA bulk copy for a full, 16B-aligned tile; cooperative loads otherwise ----
@@ -137,6 +208,12 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
 
   float dps[8], dvs[8], act[8];
   float pbx = 0.f, pby = 0.f, gbx = 0.f, gby = 0.f;
+  float pbq0 = 0.f, pbq1 = 0.f, pbq2 = 0.f, pbq3 = 1.f;  // frame t-1 box row (x, y, qz, qw), warp 1 lanes only
+  const bool prev_box = (wid == 1) && (lane < ne) && (t > 0);
+  if (prev_box) {  // fetched now so that its latency overlaps the wait for the root tile
+    const float* b = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)(e0 + lane) * 11 + 10) * 13;
+    pbq0 = __ldg(b); pbq1 = __ldg(b + 1); pbq2 = __ldg(b + 5); pbq3 = __ldg(b + 6);
+  }
   if (active) {
     const float* d = p.dof + (int64_t)t * p.dof_frame_stride + ((int64_t)e * 80 + 8 * k) * 2;
     const float* a = p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
@@ -189,7 +266,8 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
   __syncthreads();                       // mbarrier initialised (TMA path) / tile stores visible (fallback path)
   if (use_tma) mbar_wait(mbar, 0);
 
-  // ---- every ant thread lifts its root row into registers; box threads derive the goal directions ----
+  // ---- every ant thread lifts its root row into registers; warp 0 / warp 1 derive the goal directions of
+  // frame t / frame t-1 (separate warps: no divergence between the two roles) ----
   f3 pos = {0.f, 0.f, 0.f}, vel = pos, ang = pos;
   f4 q = {0.f, 0.f, 0.f, 1.f};
   if (active) {
@@ -199,29 +277,23 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
     vel = f3{r[7], r[8], r[9]};
     ang = f3{r[10], r[11], r[12]};
   }
-  if (tid < 2 * EPT) {
-    const int which = tid / EPT, bl = tid - which * EPT;
-    if (bl < ne) {
-      if (which == 0) {
-        const float* b = root_s + bl * ROOT_ENV + 10 * 13;
-        float s, cs;
-        box_dir(b[5], b[6], s, cs);
-        float* bo = box_s + bl * BOX_W;
-        bo[0] = s; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
-        bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
-        float* tail = obs_s + bl * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
-        tail[0] = clampf(b[0], -tclip, tclip); tail[1] = clampf(b[1], -tclip, tclip);
-        tail[2] = clampf(b[3], -tclip, tclip); tail[3] = clampf(b[4], -tclip, tclip);
-        tail[4] = clampf(b[5], -tclip, tclip); tail[5] = clampf(b[6], -tclip, tclip);
-        tail[6] = 0.0f; tail[7] = 0.0f;
-      } else if (t > 0) {
-        const float* b = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)(e0 + bl) * 11 + 10) * 13;
-        float s, cs;
-        box_dir(__ldg(b + 5), __ldg(b + 6), s, cs);
-        float* bo = box_s + bl * BOX_W;
-        bo[8] = s; bo[9] = cs; bo[10] = __ldg(b); bo[11] = __ldg(b + 1);
-      }
-    }
+  if (wid == 0 && lane < ne) {
+    const float* b = root_s + lane * ROOT_ENV + 10 * 13;
+    float s, cs;
+    box_dir(b[5], b[6], s, cs);
+    float* bo = box_s + lane * BOX_W;
+    bo[0] = s; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
+    bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
+    float* tail = obs_s + lane * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
+    tail[0] = clampf(b[0], -tclip, tclip); tail[1] = clampf(b[1], -tclip, tclip);
+    tail[2] = clampf(b[3], -tclip, tclip); tail[3] = clampf(b[4], -tclip, tclip);
+    tail[4] = clampf(b[5], -tclip, tclip); tail[5] = clampf(b[6], -tclip, tclip);
+    tail[6] = 0.0f; tail[7] = 0.0f;
+  } else if (prev_box) {
+    float s, cs;
+    box_dir(pbq2, pbq3, s, cs);
+    float* bo = box_s + lane * BOX_W;
+    bo[8] = s; bo[9] = cs; bo[10] = pbq0; bo[11] = pbq1;
   }
   __syncthreads();                       // box terms ready; all reads of the root tile are done (part_s may overwrite it)
 
@@ -272,7 +344,7 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
     pt[0] = adr; pt[1] = gdr; pt[2] = up; pt[3] = elec; pt[4] = asq;
     pt[5] = __int_as_float(lim | (arrive ? 0x100 : 0) | (fallen ? 0x200 : 0));
 
-    if (T == 1) {  // carry out (ten_ant.py:905-925); T > 1: ten_ant_load_carry_kernel on the last frame
+    if (T == 1) {  // carry out (ten_ant.py:905-925); T > 1: written once per env by the chain executor below
       float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
       float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
       pb[0] = pos.x; pb[1] = pos.y; gb[0] = gx; gb[1] = gy;
@@ -316,17 +388,17 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
     }
     const float* bo = box_s + tid * BOX_W;
     float quat_dist = bo[4];
-    float total = fadd(5.0f, fmul(up, 10.0f));
-    total = fadd(total, fmul(c.quat_reward_scale, quat_dist));
-    total = fadd(total, adr);
-    total = fadd(total, gdr);
-    total = fadd(total, (float)(2 * n_arrive));
-    total = fadd(total, (quat_dist > 0.9f && n_arrive == A) ? 100.0f : 0.0f);
-    total = fsub(total, fmul(c.actions_cost, asq));
-    total = fsub(total, fmul(c.energy_cost, elec));
-    total = fsub(total, fmul((float)lim, c.joints_at_limit_cost));
-    if (fallen) total = c.death_cost;
-    if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = total;
+    float total_r = fadd(5.0f, fmul(up, 10.0f));
+    total_r = fadd(total_r, fmul(c.quat_reward_scale, quat_dist));
+    total_r = fadd(total_r, adr);
+    total_r = fadd(total_r, gdr);
+    total_r = fadd(total_r, (float)(2 * n_arrive));
+    total_r = fadd(total_r, (quat_dist > 0.9f && n_arrive == A) ? 100.0f : 0.0f);
+    total_r = fsub(total_r, fmul(c.actions_cost, asq));
+    total_r = fsub(total_r, fmul(c.energy_cost, elec));
+    total_r = fsub(total_r, fmul((float)lim, c.joints_at_limit_cost));
+    if (fallen) total_r = c.death_cost;
+    if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = total_r;
     if (T == 1) {
       p.box_before[(int64_t)en * 2] = bo[2];
       p.box_before[(int64_t)en * 2 + 1] = bo[3];
@@ -339,7 +411,43 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
       p.reset_buf[en] = rs;
       if (p.dones_i64) p.dones_i64[en] = rs;
       if (p.dones_u8) p.dones_u8[en] = (uint8_t)rs;
-    } else {  // `fallen` only; ten_ant_chain_kernel finishes the flags
+    } else if (p.scratch && T <= 32) {
+      // Horizon-batched launch: ONE data-carrying atomic per (env, frame).  The 64-bit word of env `en` collects
+      // the `fallen` bit of every frame (bits 0..31) and the number of frames that have reported (bits 32..).
+      // The thread that sees T-1 earlier reports holds all T bits in its hand: it runs the progress / reset chain
+      // and writes the carry after the last frame.  No fence, no flag read-back, no second kernel; every unit of
+      // the env has passed its own carry reads by the time the last report arrives.
+      const unsigned long long mine = (1ull << 32) | ((unsigned long long)(fallen ? 1u : 0u) << t);
+      const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + en, mine);
+      if ((unsigned)(old >> 32) == (unsigned)T - 1u) {
+        p.scratch[en] = 0ull;            // self-resetting for the next launch / graph replay
+        int64_t prog = p.progress_buf[en];
+        bool flag = p.reset_buf[en] != 0;
+        chain_bits(p, en, 0, T, (uint32_t)(old | mine), prog, flag);
+        p.progress_buf[en] = prog;
+        p.reset_buf[en] = flag ? 1 : 0;
+        const float* last = p.root + (int64_t)(T - 1) * p.root_frame_stride;
+        // carry of the whole env by this thread: the goal direction once, then ten (xy, goal) pairs
+        const float* b = last + ((int64_t)en * 11 + 10) * 13;
+        const float bx = __ldg(b), by = __ldg(b + 1);
+        float xy[2 * A];
+#pragma unroll
+        for (int kk = 0; kk < A; ++kk) {
+          xy[2 * kk] = __ldg(last + ((int64_t)en * 11 + kk) * 13);
+          xy[2 * kk + 1] = __ldg(last + ((int64_t)en * 11 + kk) * 13 + 1);
+        }
+        float s, cs;
+        box_dir(__ldg(b + 5), __ldg(b + 6), s, cs);
+#pragma unroll
+        for (int kk = 0; kk < A; ++kk) {
+          float gx, gy;
+          goal_of(kk, bx, by, s, cs, gx, gy);
+          *reinterpret_cast<float2*>(p.pos_before + ((int64_t)en * A + kk) * 2) = make_float2(xy[2 * kk], xy[2 * kk + 1]);
+          *reinterpret_cast<float2*>(p.goal_before + ((int64_t)en * A + kk) * 2) = make_float2(gx, gy);
+        }
+        *reinterpret_cast<float2*>(p.box_before + (int64_t)en * 2) = make_float2(bx, by);
+      }
+    } else {  // `fallen` only; ten_ant_post_kernel finishes the flags
       if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + en] = fallen ? 1 : 0;
       else p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + en] = fallen ? 1 : 0;
     }
@@ -370,39 +478,19 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
   if (tma_stored && tid == 0) tma_store_wait_read();  // the tile must stay intact until the bulk store has read it
 }
 
-// progress / reset chain over the T frames of a horizon-batched launch (ten_ant.py:896-901,1296-1299)
-__global__ void ten_ant_chain_kernel(const __grid_constant__ mmb_ten_ant_params p) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= p.num_envs) return;
-  int64_t prog = p.progress_buf[e];
-  bool flag = p.reset_buf[e] != 0;
-  const float thr = (float)((double)p.c.max_episode_length - 1.0);
-  for (int t = 0; t < p.num_frames; ++t) {
-    prog = flag ? 0 : prog + 1;
-    bool fallen = p.dones_u8 ? (p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + e] != 0)
-                             : (p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + e] != 0);
-    flag = fallen || ((float)prog >= thr);
-    if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + e] = flag ? 1 : 0;
-    if (p.dones_i64) p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + e] = flag ? 1 : 0;
-  }
-  p.progress_buf[e] = prog;
-  p.reset_buf[e] = flag ? 1 : 0;
+// Fallback for callers that pass no ticket scratch: chain (threads < N) + carry (threads < 10 N) as one kernel.
+__global__ void __launch_bounds__(256) ten_ant_post_kernel(const __grid_constant__ mmb_ten_ant_params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = p.num_envs, T = p.num_frames;
+  if (i < N * A) load_carry_one(p.root + (int64_t)(T - 1) * p.root_frame_stride, i, p.pos_before, p.goal_before, p.box_before);
+  if (i < N) chain_one(p, i);
 }
 
 // ten_ant.py:870-882: carry from a root tensor
 __global__ void ten_ant_load_carry_kernel(const float* __restrict__ root, int N, float* pos_before, float* goal_before,
                                           float* box_before) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * A) return;
-  const int e = i / A, k = i - e * A;
-  const float* r = root + ((int64_t)e * 11 + k) * 13;
-  const float* b = root + ((int64_t)e * 11 + 10) * 13;
-  float s, cs, gx, gy;
-  box_dir(b[5], b[6], s, cs);
-  goal_of(k, b[0], b[1], s, cs, gx, gy);
-  pos_before[2 * (int64_t)i] = r[0]; pos_before[2 * (int64_t)i + 1] = r[1];
-  goal_before[2 * (int64_t)i] = gx; goal_before[2 * (int64_t)i + 1] = gy;
-  if (k == 0) { box_before[2 * (int64_t)e] = b[0]; box_before[2 * (int64_t)e + 1] = b[1]; }
+  if (i < N * A) load_carry_one(root, i, pos_before, goal_before, box_before);
 }
 
 template <int FLAVOR, int EPT>
@@ -411,15 +499,17 @@ int32_t launch_ten_ant(const mmb_ten_ant_params& p, cudaStream_t st) {
   static bool attr_done[MMB_MAX_DEVICES] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < MMB_MAX_DEVICES && !attr_done[dev]) {
+  if (dev >= MMB_MAX_DEVICES) return MMB_EUNSUPPORTED;
+  if (!attr_done[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TenAntSmem<EPT>::kBytes) != cudaSuccess)
       return MMB_ECUDA;
     attr_done[dev] = true;
   }
-  dim3 grid((p.num_envs + EPT - 1) / EPT, p.num_frames);
+  const int64_t units = (int64_t)((p.num_envs + EPT - 1) / EPT) * p.num_frames;
+  if (units > 0x7fffffffLL) return MMB_EUNSUPPORTED;
   {
     LaunchScope ls(K_TEN_ANT, st);
-    kern<<<grid, EPT * A, TenAntSmem<EPT>::kBytes, st>>>(p);
+    kern<<<(unsigned)units, EPT * A, TenAntSmem<EPT>::kBytes, st>>>(p);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
@@ -440,27 +530,18 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
   if (p.obs_layout != 0 && p.obs_layout != 1) return MMB_EINVAL;
   if (p.flavor != MMB_FLAVOR_CUDA && p.flavor != MMB_FLAVOR_CPU) return MMB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  // tile size: 32 envs (320 threads) by default; MMB_TEN_ANT_EPT=16 selects the 16-env tile (tuning knob)
-  static const int ept = [] { const char* v = getenv("MMB_TEN_ANT_EPT"); return (v && atoi(v) == 16) ? 16 : MMB_TEN_ANT_EPT; }();
+  // tile size: 16 envs (160 threads, 6 CTAs/SM) by default; MMB_TEN_ANT_EPT=32 selects the 32-env tile (tuning knob)
+  static const int ept = [] { const char* v = getenv("MMB_TEN_ANT_EPT"); return v ? ((atoi(v) == 32) ? 32 : 16) : MMB_TEN_ANT_EPT; }();
   int32_t rc;
   if (ept == 16)
     rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, 16>(p, st) : launch_ten_ant<FLAVOR_CPU, 16>(p, st);
   else
     rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, 32>(p, st) : launch_ten_ant<FLAVOR_CPU, 32>(p, st);
   if (rc != MMB_OK) return rc;
-  if (p.num_frames > 1) {
-    {
-      LaunchScope ls(K_TEN_ANT_CHAIN, st);
-      ten_ant_chain_kernel<<<(p.num_envs + 255) / 256, 256, 0, st>>>(p);
-    }
-    if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
-    // carry after the last frame = f(frame T-1) (a (tile, T-1) CTA must not write what a (tile, 0) CTA reads)
-    const float* last = p.root + (int64_t)(p.num_frames - 1) * p.root_frame_stride;
-    {
-      LaunchScope ls(K_TEN_ANT_CARRY, st);
-      ten_ant_load_carry_kernel<<<(p.num_envs * A + 255) / 256, 256, 0, st>>>(last, p.num_envs, p.pos_before,
-                                                                               p.goal_before, p.box_before);
-    }
+  if (p.num_frames > 1 && !(p.scratch && p.num_frames <= 32)) {
+    // chain + carry after the last frame (a (tile, T-1) CTA must not write the carry a (tile, 0) CTA reads)
+    LaunchScope ls(K_TEN_ANT_CHAIN, st);
+    ten_ant_post_kernel<<<(p.num_envs * A + 255) / 256, 256, 0, st>>>(p);
     if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   }
   return MMB_OK;

@@ -88,7 +88,8 @@ class SeparatedReplayBuffer(object):
         self.factor = torch.ones(T, N, 1, device=dev)
         self.step = 0
         self.raw_advantages = torch.zeros(T, N, 1, device=dev)
-        self.adv_stats = torch.zeros(3, device=dev, dtype=torch.float64)
+        self._adv_stats4 = torch.zeros(4, device=dev, dtype=torch.float64)
+        self.adv_stats = self._adv_stats4[:3]
         self.process_group = None
         self.permutation_override = None
         self._one = torch.ones(1, device=dev)
@@ -134,8 +135,8 @@ class SeparatedReplayBuffer(object):
         p.next_value, p.nv_e = L.ptr(nv), 1
         p.returns, p.ret_t, p.ret_e = L.ptr(self.returns), N, 1
         if advantages:
-            self.adv_stats.zero_()
-            p.advantages, p.adv_t, p.adv_e, p.stats = L.ptr(self.raw_advantages), N, 1, L.ptr(self.adv_stats)
+            self._adv_stats4.zero_()
+            p.advantages, p.adv_t, p.adv_e, p.stats = L.ptr(self.raw_advantages), N, 1, L.ptr(self._adv_stats4)
         if use_denorm:
             mean, var = value_normalizer.running_mean_var()
             mean, var = mean.reshape(-1).contiguous().float(), var.reshape(-1).contiguous().float()
@@ -150,7 +151,7 @@ class SeparatedReplayBuffer(object):
             from . import dist as mdist
             mdist.all_reduce_stats(self.adv_stats, self.process_group)
         adv = self.raw_advantages.clone()
-        L.check(L.lib().mmb_adv_normalize(L.ptr(adv), adv.numel(), L.ptr(self.adv_stats), eps, L.stream_ptr()),
+        L.check(L.lib().mmb_adv_normalize(L.ptr(adv), adv.numel(), L.ptr(self._adv_stats4), eps, 0, L.stream_ptr()),
                 "mmb_adv_normalize")
         return adv
 

@@ -70,7 +70,8 @@ class RolloutStorage:
         self.step = 0
         self.batch_size = T * N
         self.process_group = None
-        self.adv_stats = torch.zeros(3, device=dev, dtype=torch.float64)
+        self._adv_stats4 = torch.zeros(4, device=dev, dtype=torch.float64)   # count, sum, sumsq + library ticket
+        self.adv_stats = self._adv_stats4[:3]
         self._stats_out = torch.zeros(2, device=dev)
         self.shuffle_seed = 0
         self._epoch = 0
@@ -111,17 +112,17 @@ class RolloutStorage:
     def compute_returns(self, last_values, gamma, lam):
         T, N = self.num_transitions_per_env, self.num_envs
         lv = last_values if last_values.is_contiguous() else last_values.contiguous()
-        self.adv_stats.zero_()
         p = L.GaePpoParams()
         p.num_envs, p.num_steps = N, T
         p.rewards, p.values, p.dones, p.last_values = L.ptr(self.rewards), L.ptr(self.values), L.ptr(self.dones), L.ptr(lv)
         p.gamma, p.lam = float(gamma), float(lam)
-        p.returns, p.advantages, p.stats = L.ptr(self.returns), L.ptr(self.advantages), L.ptr(self.adv_stats)
+        p.returns, p.advantages, p.stats = L.ptr(self.returns), L.ptr(self.advantages), L.ptr(self._adv_stats4)
         L.check(L.lib().mmb_gae_ppo(p, L.stream_ptr()), "mmb_gae_ppo")
         if self.process_group is not None:
             from . import dist as mdist
             mdist.all_reduce_stats(self.adv_stats, self.process_group)
-        L.check(L.lib().mmb_adv_normalize(L.ptr(self.advantages), T * N, L.ptr(self.adv_stats), 1e-8, L.stream_ptr()),
+        # the normalise launch clears the accumulator for the next rollout (no memset launch; graph-replay safe)
+        L.check(L.lib().mmb_adv_normalize(L.ptr(self.advantages), T * N, L.ptr(self._adv_stats4), 1e-8, 1, L.stream_ptr()),
                 "mmb_adv_normalize")
 
     def get_statistics(self):

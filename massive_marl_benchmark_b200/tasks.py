@@ -131,6 +131,7 @@ class TenAnt(BaseTask):
         self.obs_all = self._obs_all_out[0]
         self.keep_raw_obs = True
         self.actions = torch.zeros(N, 80, device=dev)
+        self._chain_words = torch.zeros(N, device=dev, dtype=torch.int64)   # replay(): per-env flag/count words
         # reset_idx at the first step reloads the carry from the not-yet-refreshed root tensor
         L.check(L.lib().mmb_ten_ant_load_carry(L.ptr(self.root_states), N, L.ptr(self.pos_before),
                                                L.ptr(self.goal_before), L.ptr(self.box_before), L.stream_ptr()),
@@ -169,6 +170,7 @@ class TenAnt(BaseTask):
         p.dones_i64, p.dones_u8, p.forces = L.ptr(dones_i64), L.ptr(dones_u8), L.ptr(forces)
         (p.obs_raw_frame_stride, p.obs_frame_stride, p.share_obs_frame_stride, p.rewards_frame_stride,
          p.dones_i64_frame_stride, p.dones_u8_frame_stride, p.forces_frame_stride) = out_strides
+        p.scratch = L.ptr(self._chain_words) if T > 1 else None
         p.c = self.consts
         L.check(L.lib().mmb_ten_ant_step(p, L.stream_ptr()), "mmb_ten_ant_step")
 
