@@ -177,7 +177,8 @@ def run_ours(args, rank, world, local_rank):
     cfg = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1 + rank}
     frames = [synthetic.ten_ant_frames(N, T, seed=1234 + 1000 * rank + s) for s in range(SETS)]
     dev_frames = [{k: v.to(dev) for k, v in f.items()} for f in frames]
-    task = TenAnt(cfg, provider=ReplayProvider({"root": frames[0]["root"], "dof": frames[0]["dof"]}, device=dev))
+    task = TenAnt(cfg, None, None, "cuda", local_rank, True, False,
+                  provider=ReplayProvider({"root": frames[0]["root"], "dof": frames[0]["dof"]}, device=dev))
     task.clip_actions, task.clip_obs = 1.0, 5.0
     storages = [RolloutStorage(N, T, (388,), (0,), (80,), dev, "sequential") for _ in range(SETS)]
     forces = [torch.zeros(T, N, 80, device=dev) for _ in range(SETS)]
@@ -190,18 +191,24 @@ def run_ours(args, rank, world, local_rank):
     launches_per_rollout = [0]
     side = torch.cuda.Stream()
 
-    def rollout(i):
+    def rollout(i, join=True):
+        """One rollout on frame/storage set i % SETS.  Main stream: step kernel -> GAE scan.  Side stream: the reset
+        lists of the T steps, then [statistics all-reduce] + normalisation.  With join=False the side work is left
+        running so that the NEXT rollout's step kernel (another storage set) overlaps it."""
         s = i % SETS
         st, fr = storages[s], dev_frames[s]
+        main = torch.cuda.current_stream()
         # observation after step t lands in obs slot t+1; reward/done of step t in slot t (no add_transitions pass)
         task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), None, forces[s])
-        # reset_idx of the T steps and GAE both depend only on the done flags: fork them (side stream joins back)
-        main = torch.cuda.current_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
             reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
-        st.compute_returns(last_values, GAMMA, LAM)
-        main.wait_stream(side)
+        st.compute_returns_scan(last_values, GAMMA, LAM)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            st.normalize_advantages()
+        if join:
+            main.wait_stream(side)
 
     _l0 = L.launch_count()
     rollout(0)
@@ -212,6 +219,7 @@ def run_ours(args, rank, world, local_rank):
     # The rollout is 5 short launches after the main kernel: capture it once per frame/storage set in a CUDA graph
     # so the launch-bound tail is replayed without per-launch CPU cost (eager fallback if capture is unavailable).
     graphs = None
+    graph_all = None
     if not args.no_graph:
         try:
             graphs = []
@@ -220,18 +228,34 @@ def run_ours(args, rank, world, local_rank):
                 with torch.cuda.graph(g):
                     rollout(s_)
                 graphs.append(g)
+            graph_all = torch.cuda.CUDAGraph()       # SETS consecutive rollouts, side-stream tails joined once at the end
+            with torch.cuda.graph(graph_all):
+                for s_ in range(SETS):
+                    rollout(s_, join=(s_ == SETS - 1))
             for s_ in range(SETS):
                 graphs[s_].replay()
+            graph_all.replay()
             torch.cuda.synchronize()
         except Exception as ex:  # pragma: no cover
             print("cuda graph capture failed, running eagerly: %r" % (ex,), file=sys.stderr)
-            graphs = None
+            graphs = graph_all = None
+
+    def run_steps(first, count):
+        """`count` consecutive rollouts starting at rollout index `first` (a multiple of SETS)."""
+        i = 0
+        while i < count:
+            if graph_all is not None and (first + i) % SETS == 0 and count - i >= SETS:
+                graph_all.replay()
+                i += SETS
+            elif graphs is not None:
+                graphs[(first + i) % SETS].replay()
+                i += 1
+            else:
+                rollout(first + i)
+                i += 1
 
     def run_step(i):
-        if graphs is not None:
-            graphs[i % SETS].replay()
-        else:
-            rollout(i)
+        run_steps(i, 1)
 
     for i in range(W):
         run_step(i)
@@ -243,8 +267,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t_host0 = time.perf_counter()
     ev0.record()
-    for i in range(K):
-        run_step(W + i)
+    run_steps(0, K)
     ev1.record()
     barrier()
     t_host1 = time.perf_counter()
@@ -274,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
     host_prov = HostReplayProvider({"root": torch.cat([f["root"] for f in frames[:2]]),
                                     "dof": torch.cat([f["dof"] for f in frames[:2]])}, dev)
     cfg2 = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 7 + rank}
-    task2 = TenAnt(cfg2, provider=host_prov)
+    task2 = TenAnt(cfg2, None, None, "cuda", local_rank, True, False, provider=host_prov)
     task2.keep_raw_obs = False
     env = VecTaskPython(task2, dev)
     st2 = RolloutStorage(N, T, (388,), (0,), (80,), dev, "sequential")

@@ -110,6 +110,13 @@ class RolloutStorage:
 
     # ------------------------------------------------------------------------------------------
     def compute_returns(self, last_values, gamma, lam):
+        self.compute_returns_scan(last_values, gamma, lam)
+        self.normalize_advantages()
+
+    def compute_returns_scan(self, last_values, gamma, lam):
+        """First half of compute_returns (storage.py:51-62 + the raw `returns - values`): the reverse-time scan and
+        the fp64 (count, sum, sumsq) of the raw advantages.  Split out so a caller can overlap the second half
+        (statistics all-reduce + normalisation) with the next rollout on another stream."""
         T, N = self.num_transitions_per_env, self.num_envs
         lv = last_values if last_values.is_contiguous() else last_values.contiguous()
         p = L.GaePpoParams()
@@ -118,6 +125,10 @@ class RolloutStorage:
         p.gamma, p.lam = float(gamma), float(lam)
         p.returns, p.advantages, p.stats = L.ptr(self.returns), L.ptr(self.advantages), L.ptr(self._adv_stats4)
         L.check(L.lib().mmb_gae_ppo(p, L.stream_ptr()), "mmb_gae_ppo")
+
+    def normalize_advantages(self):
+        """Second half (storage.py:65): [all-reduce of the statistics over env shards] + (adv - mean) / (std + 1e-8)."""
+        T, N = self.num_transitions_per_env, self.num_envs
         if self.process_group is not None:
             from . import dist as mdist
             mdist.all_reduce_stats(self.adv_stats, self.process_group)
