@@ -60,7 +60,7 @@ MMB_API uint64_t mmb_launch_count(void);
  * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
 enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
        MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
-       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_COUNT };
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_COUNT };
 MMB_API int32_t mmb_profile_enable(int32_t on);
 MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
 
@@ -330,6 +330,37 @@ MMB_API int32_t mmb_shuffle_gather(const mmb_gather_params* p, void* stream);
 /* random permutation of [0,n) on device (fast mode of mini_batch_generator 'random'): the stateless
  * bijection evaluated for every position; a permutation by construction. */
 MMB_API int32_t mmb_permutation(int64_t n, uint64_t seed, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Actor-critic MLP forward on tcgen05 tensor cores: one launch per layer                          */
+/*   Y[M,N] = epilogue(X[M,K] . W[N,K]^T + bias)                                                  */
+/* PPO  ActorCritic (agents/algorithms/rl/ppo/module.py:25-55): Linear -> ELU, last Linear plain  */
+/* MARL Actor/Critic (agents/algorithms/marl/actor_critic.py:42-69,149-168, agents/algorithms/    */
+/*      utils/mlp.py:6-65): LayerNorm(in) -> [Linear -> ELU -> LayerNorm] x3 -> Linear             */
+/* Operands are bf16 (fp32 accumulation in TMEM, fp32 epilogue); the reference computes in fp32, so */
+/* outputs agree to bf16 operand precision (tests state the tolerance).                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t M, N, K;      /* rows, output features, input features (unpadded) */
+  int32_t Mpad;         /* rows of x / y buffers: multiple of 128 >= M (pad rows of x are zero) */
+  int32_t Kpad;         /* leading dimension of x and w: multiple of 64 >= K, pad columns are zero */
+  int32_t Npad;         /* rows of w: multiple of n_tile >= N, pad rows are zero */
+  int32_t n_tile;       /* output columns per CTA: multiple of 32, <= 256, or 512 */
+  int32_t epilogue;     /* 0: bias -> fp32;  1: bias+ELU -> bf16;  2: bias+ELU+LayerNorm -> bf16 (n_tile == Npad == N) */
+  const void* x;        /* bf16 [Mpad][Kpad] */
+  const void* w;        /* bf16 [Npad][Kpad] (nn.Linear weight layout, K contiguous) */
+  const float* bias;    /* [N] */
+  const float* ln_gamma; const float* ln_beta; float ln_eps;   /* epilogue 2 */
+  int32_t reserved;
+  void* y;              /* epilogue 0: fp32 [M][y_stride]; else bf16 [Mpad][y_stride] (zero-initialised by the caller) */
+  int64_t y_stride;     /* elements */
+} mmb_mlp_layer_params;
+MMB_API int32_t mmb_mlp_layer(const mmb_mlp_layer_params* p, void* stream);
+
+/* fp32 [M][K] -> optional LayerNorm over K (mlp.py:58-59 feature_norm) -> bf16 [Mpad][Kpad], zero padded: the
+ * A operand of the first layer. */
+MMB_API int32_t mmb_ln_cast(const float* x, int32_t M, int32_t Mpad, int32_t K, int32_t Kpad, const float* gamma,
+                            const float* beta, float eps, int32_t use_ln, void* y_bf16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,12 @@ class GatherParams(C.Structure):
         ("src", c_vp * MAX_GATHER_FIELDS), ("dst", c_vp * MAX_GATHER_FIELDS), ("row_bytes", c_i32 * MAX_GATHER_FIELDS)]
 
 
+class MlpLayerParams(C.Structure):
+    _fields_ = [("M", c_i32), ("N", c_i32), ("K", c_i32), ("Mpad", c_i32), ("Kpad", c_i32), ("Npad", c_i32),
+                ("n_tile", c_i32), ("epilogue", c_i32), ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("ln_gamma", c_vp),
+                ("ln_beta", c_vp), ("ln_eps", c_f), ("reserved", c_i32), ("y", c_vp), ("y_stride", c_i64)]
+
+
 # name -> (restype, argtypes); every symbol include/mmb.h declares
 SYMBOLS = {
     "mmb_abi_version": (c_i32, []),
@@ -137,6 +143,8 @@ SYMBOLS = {
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "mmb_shuffle_gather": (c_i32, [C.POINTER(GatherParams), c_vp]),
     "mmb_permutation": (c_i32, [c_i64, c_u64, c_vp, c_vp]),
+    "mmb_mlp_layer": (c_i32, [C.POINTER(MlpLayerParams), c_vp]),
+    "mmb_ln_cast": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f, c_i32, c_vp, c_vp]),
 }
 
 _lib = None
@@ -180,7 +188,8 @@ def launch_count():
 
 
 KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
-              "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm")
+              "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm", "mlp_layer",
+              "ln_cast")
 
 
 def profile_enable(on=True):

@@ -1,0 +1,148 @@
+"""Actor-critic MLP forward on the tcgen05 kernels (`mmb_mlp_layer`, `mmb_ln_cast`).
+
+Covers the forward passes on the rollout path:
+
+  PPO   `ActorCritic.actor / .critic`  agents/algorithms/rl/ppo/module.py:25-55
+        Linear(obs,1024) ELU Linear(1024,1024) ELU Linear(1024,512) ELU Linear(512,act|1)
+  MARL  `Actor.base + act.action_out.fc_mean`, `Critic.base + v_out`
+        agents/algorithms/marl/actor_critic.py:42-69,149-168, agents/algorithms/utils/mlp.py:6-65
+        LayerNorm(in) [Linear ELU LayerNorm] x3 Linear(512, 8|1)
+
+Weights are taken from the reference's own modules / checkpoints (`from_sequential`, `from_marl_state_dict`), cast
+once to bf16 and zero-padded to the kernel's tile multiples; sampling, log-probs and the distribution quirks
+(PPO's sigma^2 scale_tril, module.py:76-77) stay in PyTorch on top of the returned means / values.
+Numerics: bf16 operands, fp32 accumulation and fp32 bias / ELU / LayerNorm; the reference is fp32 SGEMM, so
+outputs agree to bf16 operand precision (tests/test_gpu_mlp.py states the tolerances).
+"""
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _Layer:
+    def __init__(self, weight, bias, act: bool, ln=None, device="cuda"):
+        N, K = weight.shape
+        self.N, self.K = N, K
+        self.Kpad = _round_up(K, 64)
+        self.act = act
+        self.ln = ln
+        if ln is not None:                       # bias + ELU + LayerNorm over the whole row: one CTA owns full rows
+            if N not in (32, 64, 96, 128, 160, 192, 224, 256, 512):
+                raise L.MmbError("LayerNorm epilogue needs N <= 256 (multiple of 32) or N == 512, got %d" % N)
+            self.n_tile, self.Npad, self.epilogue = N, N, 2
+        elif act:
+            self.n_tile = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 32)
+            self.Npad, self.epilogue = _round_up(N, self.n_tile), 1
+        else:
+            self.Npad = _round_up(N, 32)
+            self.n_tile = self.Npad if self.Npad <= 256 else 32
+            self.Npad = _round_up(N, self.n_tile)
+            self.epilogue = 0
+        w = torch.zeros(self.Npad, self.Kpad, dtype=torch.bfloat16, device=device)
+        w[:N, :K] = weight.detach().to(device=device, dtype=torch.bfloat16)
+        self.w = w
+        self.bias = bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        if ln is not None:
+            self.gamma = ln.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+            self.beta = ln.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+            self.eps = float(ln.eps)
+
+
+class FusedMLP:
+    """A chain of Linear [+ELU [+LayerNorm]] layers, optionally preceded by a LayerNorm of the input."""
+
+    def __init__(self, layers: List[_Layer], in_ln=None, device="cuda"):
+        L.lib()
+        self.layers = layers
+        self.device = torch.device(device)
+        self.in_dim = layers[0].K
+        self.out_dim = layers[-1].N
+        self.in_ln = in_ln
+        if in_ln is not None:
+            self.in_gamma = in_ln.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+            self.in_beta = in_ln.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+            self.in_eps = float(in_ln.eps)
+        self._bufs = {}
+
+    # -- constructors from the reference's modules ------------------------------------------------------
+    @classmethod
+    def from_sequential(cls, seq, device="cuda"):
+        """PPO: nn.Sequential(Linear, ELU, Linear, ELU, ..., Linear) (module.py:25-49)."""
+        mods = list(seq)
+        layers = []
+        i = 0
+        while i < len(mods):
+            lin = mods[i]
+            if not isinstance(lin, torch.nn.Linear):
+                raise L.MmbError("unsupported module in sequential: %r" % (lin,))
+            act = i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.ELU)
+            if i + 1 < len(mods) and not act:
+                raise L.MmbError("only ELU activations are on the reference path (cfg/ppo/config.yaml:9): %r" % (mods[i + 1],))
+            layers.append(_Layer(lin.weight, lin.bias, act, None, device))
+            i += 2 if act else 1
+        return cls(layers, None, device)
+
+    @classmethod
+    def from_marl_state_dict(cls, sd, head="act.action_out.fc_mean", device="cuda"):
+        """MARL Actor / Critic checkpoint (runner.py:319-339 format): base.feature_norm, base.mlp.fc1, base.mlp.fc2.*,
+        then `head` ('act.action_out.fc_mean' for the actor mean, 'v_out' for the critic value)."""
+        def ln_of(prefix):
+            w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+            m = torch.nn.LayerNorm(w.shape[0])
+            m.weight.data.copy_(w); m.bias.data.copy_(b)
+            return m
+        in_ln = ln_of("base.feature_norm") if "base.feature_norm.weight" in sd else None
+        layers = [_Layer(sd["base.mlp.fc1.0.weight"], sd["base.mlp.fc1.0.bias"], True, ln_of("base.mlp.fc1.2"), device)]
+        i = 0
+        while "base.mlp.fc2.%d.0.weight" % i in sd:
+            layers.append(_Layer(sd["base.mlp.fc2.%d.0.weight" % i], sd["base.mlp.fc2.%d.0.bias" % i], True,
+                                 ln_of("base.mlp.fc2.%d.2" % i), device))
+            i += 1
+        layers.append(_Layer(sd[head + ".weight"], sd[head + ".bias"], False, None, device))
+        return cls(layers, in_ln, device)
+
+    # -- forward ---------------------------------------------------------------------------------------------
+    def _buffers(self, M):
+        if M not in self._bufs:
+            Mpad = _round_up(M, 128)
+            acts = [torch.zeros(Mpad, self.layers[0].Kpad, dtype=torch.bfloat16, device=self.device)]
+            for l in self.layers[:-1]:
+                acts.append(torch.zeros(Mpad, _round_up(l.N, 64), dtype=torch.bfloat16, device=self.device))
+            self._bufs[M] = (Mpad, acts)
+        return self._bufs[M]
+
+    def forward(self, x, out=None):
+        """x fp32 [M, in_dim] on the device -> fp32 [M, out_dim]."""
+        if x.device.type != "cuda":
+            raise L.MmbError("FusedMLP runs on CUDA tensors only")
+        M = x.shape[0]
+        x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        Mpad, acts = self._buffers(M)
+        lib, st = L.lib(), L.stream_ptr()
+        l0 = self.layers[0]
+        use_ln = self.in_ln is not None
+        L.check(lib.mmb_ln_cast(L.ptr(x), M, Mpad, l0.K, l0.Kpad, L.ptr(self.in_gamma) if use_ln else None,
+                                L.ptr(self.in_beta) if use_ln else None, self.in_eps if use_ln else 0.0, int(use_ln),
+                                L.ptr(acts[0]), st), "mmb_ln_cast")
+        if out is None:
+            out = torch.empty(M, self.out_dim, dtype=torch.float32, device=self.device)
+        for i, l in enumerate(self.layers):
+            p = L.MlpLayerParams()
+            p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = M, l.N, l.K, Mpad, l.Kpad, l.Npad, l.n_tile, l.epilogue
+            p.x, p.w, p.bias = L.ptr(acts[i]), L.ptr(l.w), L.ptr(l.bias)
+            if l.epilogue == 2:
+                p.ln_gamma, p.ln_beta, p.ln_eps = L.ptr(l.gamma), L.ptr(l.beta), l.eps
+            if i == len(self.layers) - 1:
+                p.y, p.y_stride = L.ptr(out), out.stride(0)
+            else:
+                p.y, p.y_stride = L.ptr(acts[i + 1]), acts[i + 1].stride(0)
+            L.check(lib.mmb_mlp_layer(p, st), "mmb_mlp_layer")
+        return out
+
+    __call__ = forward

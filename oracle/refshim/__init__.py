@@ -334,6 +334,7 @@ def install(reference_root="/root/reference"):
     ns("agents.algorithms.rl.ppo", [os.path.join(ag, "algorithms", "rl", "ppo")])
     ns("agents.algorithms.marl", [os.path.join(ag, "algorithms", "marl")])
     ns("agents.algorithms.marl.utils", [os.path.join(ag, "algorithms", "marl", "utils")])
+    ns("agents.algorithms.utils", [os.path.join(ag, "algorithms", "utils")])
 
 
 def make_cfg(num_envs, env_name):

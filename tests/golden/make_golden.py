@@ -311,6 +311,39 @@ def gen_buffer_marl(T=8, N=24, seed=505):
     return out
 
 
+def marl_mlp_functional(sd, x, head):
+    """fp32 restatement of MLPBase + head (agents/algorithms/utils/mlp.py:31-65, actor_critic.py:60-69,165-168)."""
+    import torch.nn.functional as F
+    h = F.layer_norm(x, (x.shape[1],), sd["base.feature_norm.weight"], sd["base.feature_norm.bias"])
+    h = F.layer_norm(F.elu(F.linear(h, sd["base.mlp.fc1.0.weight"], sd["base.mlp.fc1.0.bias"])), (512,),
+                     sd["base.mlp.fc1.2.weight"], sd["base.mlp.fc1.2.bias"])
+    for i in range(2):
+        h = F.layer_norm(F.elu(F.linear(h, sd["base.mlp.fc2.%d.0.weight" % i], sd["base.mlp.fc2.%d.0.bias" % i])), (512,),
+                         sd["base.mlp.fc2.%d.2.weight" % i], sd["base.mlp.fc2.%d.2.bias" % i])
+    return F.linear(h, sd[head + ".weight"], sd[head + ".bias"])
+
+
+def gen_mlp_marl(reference_root, M=200, seed=606):
+    """The shipped TenAnt MAPPO checkpoint of agent 0's ACTOR (logs/ten_ant/mappo/models_seed-1/actor_agent0.pt: real
+    weights with real dynamic range) + inputs + the fp32 output of the reference's own MLPBase module."""
+    from agents.algorithms.utils.mlp import MLPBase
+    sd = torch.load(os.path.join(reference_root, "logs/ten_ant/mappo/models_seed-1/actor_agent0.pt"), map_location="cpu",
+                    weights_only=False)
+    cfg = dict(use_feature_normalization=True, use_orthogonal=True, use_ReLU=True, stacked_frames=1, layer_N=2, hidden_size=512)
+    base = MLPBase(cfg, (46,))
+    base.load_state_dict({k[len("base."):]: v for k, v in sd.items() if k.startswith("base.")})
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.clamp(torch.randn(M, 46, generator=gen) * 2.0, -7, 7)
+    with torch.no_grad():
+        feat = base(x)
+        mean = torch.nn.functional.linear(feat, sd["act.action_out.fc_mean.weight"], sd["act.action_out.fc_mean.bias"])
+        mine = marl_mlp_functional(sd, x, "act.action_out.fc_mean")
+    _eq("marl mlp functional vs MLPBase", mean, mine)
+    out = {"w_" + k.replace(".", "__"): v for k, v in sd.items()}
+    out.update(x=x, features=feat, mean=mean)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -319,7 +352,8 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
     for name, fn in (("ten_ant_n37", gen_ten_ant), ("one_ant_n64", gen_one_ant), ("ingenuity_n33", gen_ingenuity),
-                     ("storage_ppo", gen_storage_ppo), ("buffer_marl", gen_buffer_marl)):
+                     ("storage_ppo", gen_storage_ppo), ("buffer_marl", gen_buffer_marl),
+                     ("mlp_marl_actor0", lambda: gen_mlp_marl(args.reference))):
         data = fn()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **_np(data))

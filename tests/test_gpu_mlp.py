@@ -1,0 +1,120 @@
+"""GPU parity of the tcgen05 MLP forward (mmb_mlp_layer / mmb_ln_cast through mlp.FusedMLP).
+
+Two references, both plain PyTorch fp32 of the same op:
+  (1) the exact fp32 forward (the reference's SGEMM path; golden outputs of the reference's own MLPBase on the shipped
+      checkpoint for the MARL actor) - tolerance = bf16 operand precision: |d| <= 2e-2 * max|row| (measured ~3e-3);
+  (2) the same forward with operands rounded to bf16 where the kernel rounds them (activations and weights), fp32
+      accumulate - isolates the kernel's arithmetic from the quantisation: |d| <= 2e-3 * max|row| (differences come
+      only from accumulation order and from bf16 re-rounding of near-tie activations).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _rowmax_err(a, b):
+    """max |a-b| per row relative to that row's max |b|, but never to less than the RMS of the whole output (a 1-wide
+    head has rows whose only entry can be arbitrarily close to zero)."""
+    floor = b.pow(2).mean().sqrt().clamp(min=1e-6)
+    return float(((a - b).abs().amax(dim=1) / torch.maximum(b.abs().amax(dim=1), floor)).max())
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _ppo_net(in_dim, hidden, out_dim, gain_last, gen):
+    """module.py:25-49,57-64: Linear/ELU chain, orthogonal init (gain sqrt(2), last layer gain_last)."""
+    dims = [in_dim] + hidden + [out_dim]
+    mods = []
+    for i in range(len(dims) - 1):
+        lin = torch.nn.Linear(dims[i], dims[i + 1])
+        torch.nn.init.orthogonal_(lin.weight, gain=(gain_last if i == len(dims) - 2 else 2 ** 0.5))
+        lin.bias.data.uniform_(-0.1, 0.1, generator=gen)
+        mods.append(lin)
+        if i < len(dims) - 2:
+            mods.append(torch.nn.ELU())
+    return torch.nn.Sequential(*mods)
+
+
+@pytest.mark.parametrize("M", [1, 100, 128, 4096])
+def test_ppo_actor_critic_forward(cuda_device, M):
+    from massive_marl_benchmark_b200.mlp import FusedMLP
+    dev = cuda_device
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator().manual_seed(M)
+    torch.manual_seed(M)
+    for out_dim, gain in ((80, 0.01), (1, 1.0)):      # actor mean head, critic value head
+        net = _ppo_net(388, [1024, 1024, 512], out_dim, gain, gen).to(dev)
+        x = torch.clamp(torch.randn(M, 388, generator=gen) * 2.0, -5, 5).to(dev)
+        fused = FusedMLP.from_sequential(net, dev)
+        y = fused(x)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ref = net(x)
+            h = _bf(x)
+            lins = [m for m in net if isinstance(m, torch.nn.Linear)]
+            for i, lin in enumerate(lins):
+                h = F.linear(h, _bf(lin.weight), lin.bias)
+                if i < len(lins) - 1:
+                    h = _bf(F.elu(h))
+            emu = h
+        assert y.shape == ref.shape and torch.isfinite(y).all()
+        # multi-layer: intermediate activations are re-rounded to bf16, and a near-tie value can round the other way
+        # under a different fp32 accumulation order (1 bf16 ulp = 0.4 %), so the emulation bound is not ulp-tight
+        assert _rowmax_err(y, emu) <= 1e-2, ("vs bf16-operand emulation", M, out_dim, _rowmax_err(y, emu))
+        assert _rowmax_err(y, ref) <= 3e-2, ("vs fp32", M, out_dim, _rowmax_err(y, ref))
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 388, 80), (300, 46, 8), (128, 512, 1), (1000, 1024, 96), (257, 64, 256), (4096, 388, 32)])
+def test_single_layer_gemm_exact(cuda_device, M, K, N):
+    """One Linear layer, fp32 output: no intermediate rounding, so the only difference to fp32 torch on bf16-rounded
+    operands is the accumulation order -> 1e-4.  This pins descriptors, swizzle, TMEM read-back and tile edges."""
+    from massive_marl_benchmark_b200.mlp import FusedMLP
+    dev = cuda_device
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(M + K + N)
+    lin = torch.nn.Linear(K, N).to(dev)
+    x = torch.randn(M, K, device=dev)
+    y = FusedMLP.from_sequential(torch.nn.Sequential(lin), dev)(x)
+    with torch.no_grad():
+        emu = F.linear(_bf(x), _bf(lin.weight), lin.bias)
+    torch.cuda.synchronize()
+    assert _rowmax_err(y, emu) <= 1e-4, _rowmax_err(y, emu)
+
+
+def test_marl_actor_shipped_checkpoint(cuda_device):
+    """Real weights: the shipped TenAnt MAPPO actor of agent 0; expected output = the reference's own MLPBase (fp32)."""
+    from massive_marl_benchmark_b200.mlp import FusedMLP
+    dev = cuda_device
+    g = load_golden("mlp_marl_actor0")
+    sd = {k[2:].replace("__", "."): v for k, v in g.items() if k.startswith("w_")}
+    fused = FusedMLP.from_marl_state_dict(sd, "act.action_out.fc_mean", dev)
+    x = g["x"].to(dev)
+    y = fused(x)
+    torch.cuda.synchronize()
+    assert y.shape == (x.shape[0], 8)
+    err = _rowmax_err(y.cpu(), g["mean"])
+    print("MARL actor mean: max row-relative error vs fp32 reference %.3g" % err)
+    assert err <= 2e-2
+    # bf16-operand emulation with fp32 LayerNorm / ELU, as the kernel does
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    with torch.no_grad():
+        h = _bf(F.layer_norm(x, (46,), sdd["base.feature_norm.weight"], sdd["base.feature_norm.bias"]))
+        for pre in ("base.mlp.fc1", "base.mlp.fc2.0", "base.mlp.fc2.1"):
+            h = F.elu(F.linear(h, _bf(sdd[pre + ".0.weight"]), sdd[pre + ".0.bias"]))
+            h = _bf(F.layer_norm(h, (512,), sdd[pre + ".2.weight"], sdd[pre + ".2.bias"]))
+        emu = F.linear(h, _bf(sdd["act.action_out.fc_mean.weight"]), sdd["act.action_out.fc_mean.bias"])
+    assert _rowmax_err(y, emu) <= 3e-3, _rowmax_err(y, emu)
+
+
+def test_mlp_layer_rejects_bad_arguments(cuda_device):
+    from massive_marl_benchmark_b200 import _lib as L
+    p = L.MlpLayerParams()
+    assert L.lib().mmb_mlp_layer(p, None) == -1
+    assert L.lib().mmb_mlp_layer(None, None) == -1
+    assert L.lib().mmb_ln_cast(None, 1, 128, 4, 64, None, None, 0.0, 0, None, None) == -1
