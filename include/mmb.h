@@ -351,7 +351,7 @@ typedef struct {
   const void* w;        /* bf16 [Npad][Kpad] (nn.Linear weight layout, K contiguous) */
   const float* bias;    /* [N] */
   const float* ln_gamma; const float* ln_beta; float ln_eps;   /* epilogue 2 */
-  int32_t reserved;
+  int32_t stages;       /* set by the library: depth of the shared-memory ring (2..4) */
   void* y;              /* epilogue 0: fp32 [M][y_stride]; else bf16 [Mpad][y_stride] (zero-initialised by the caller) */
   int64_t y_stride;     /* elements */
 } mmb_mlp_layer_params;

@@ -33,6 +33,8 @@ constexpr int BM = 128;       // rows per CTA = TMEM lanes = UMMA_M
 constexpr int BK = 64;        // bf16 elements per k-block (128 bytes)
 constexpr int MLP_THREADS = 128;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_BUDGET = 200 * 1024;
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
 // [0,14), leading byte offset (ignored for swizzled K-major, canonical value 1) in [16,30), stride byte offset =
@@ -78,42 +80,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : expm1f(x); }  // nn.ELU(alpha=1)
 
-// stage `rows` x 64 bf16 (row-major, leading dimension ld) into the swizzled tile at `tile`
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ g, int64_t ld, int rows, int tid) {
+// stage `rows` x 64 bf16 (row-major, leading dimension ld) into the swizzled tile at `tile` with asynchronous 16-byte
+// copies (cp.async / LDGSTS): nothing waits here, the caller commits a group per k-block
+__device__ __forceinline__ void stage_tile_async(uint8_t* tile, const __nv_bfloat16* __restrict__ g, int64_t ld, int rows, int tid) {
   const int chunks = rows * 8;  // 16-byte chunks
-  for (int i0 = tid; i0 < chunks; i0 += MLP_THREADS * 4) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * MLP_THREADS;
-      if (i < chunks) v[u] = __ldg(reinterpret_cast<const uint4*>(g + (int64_t)(i >> 3) * ld + (i & 7) * 8));
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * MLP_THREADS;
-      if (i < chunks) {
-        const int r = i >> 3, c = i & 7;
-        *reinterpret_cast<uint4*>(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v[u];
-      }
-    }
+  const uint32_t base = smem_u32(tile);
+  for (int i = tid; i < chunks; i += MLP_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    const uint32_t dst = base + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + (int64_t)r * ld + c * 8) : "memory");
   }
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_constant__ mmb_mlp_layer_params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t mma_done[2];
+  __shared__ uint64_t mma_done[MAX_STAGES];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.n_tile;
   const int n_tile = p.n_tile;
-  const int b_stage_bytes = n_tile * BK * 2;
-  uint8_t* a_s[2] = {smem, smem + A_STAGE_BYTES};
-  uint8_t* b_s[2] = {smem + 2 * A_STAGE_BYTES, smem + 2 * A_STAGE_BYTES + b_stage_bytes};
+  const int stage_bytes = A_STAGE_BYTES + n_tile * BK * 2;   // [A tile | B tile], both multiples of 1024 B
+  const int S = p.stages;
 
-  if (tid == 0) {
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
-  }
+  if (tid == 0)
+    for (int i = 0; i < S; ++i) mbar_init(&mma_done[i], 1);
   if (warp == 0) {  // one warp allocates all 512 TMEM columns (1 CTA per SM) and publishes the base address
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -128,18 +121,30 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_
   const int nkb = p.Kpad / BK;
   const int umma_n = n_tile > 256 ? 256 : n_tile;
   const uint32_t idesc = umma_idesc_bf16(umma_n);
-  const int rows_a = min(BM, p.Mpad - m0);
 
+  // S-stage ring: k-blocks kb+1 .. kb+S-1 are in flight (cp.async) while the tensor core works on block kb.
+  // A stage is refilled only after the tcgen05.commit of the MMAs that read it has arrived on its mbarrier.
+  auto issue_loads = [&](int kb) {
+    uint8_t* st = smem + (kb % S) * stage_bytes;
+    stage_tile_async(st, X + kb * BK, p.Kpad, BM, tid);
+    stage_tile_async(st + A_STAGE_BYTES, W + kb * BK, p.Kpad, n_tile, tid);
+  };
+  for (int kb = 0; kb < S - 1; ++kb) {
+    if (kb < nkb) issue_loads(kb);
+    cp_async_commit();
+  }
   for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    if (kb >= 2) mbar_wait(&mma_done[s], (uint32_t)(((kb >> 1) - 1) & 1));  // the MMAs that read stage s are done
-    stage_tile(a_s[s], X + kb * BK, p.Kpad, rows_a, tid);
-    stage_tile(b_s[s], W + kb * BK, p.Kpad, n_tile, tid);
-    fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+    const int s = kb % S;
+    cp_async_wait<MAX_STAGES - 2>();   // conservative for S < MAX_STAGES: see the group accounting below
+    if (S < MAX_STAGES) {               // exact wait: all but the newest S-2 groups are complete
+      if (S == 2) cp_async_wait<0>();
+      else if (S == 3) cp_async_wait<1>();
+    }
+    fence_async_smem();  // LDGSTS / generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(a_s[s]), b_addr = smem_u32(b_s[s]);
+      const uint32_t a_addr = smem_u32(smem + s * stage_bytes), b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
       for (int j = 0; j < BK / 16; ++j) {  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
         const bool acc = (kb > 0) || (j > 0);
@@ -149,8 +154,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_
       }
       umma_commit(&mma_done[s]);  // arrives when every MMA issued so far has completed
     }
+    // refill the stage that block kb-1 used with block kb+S-1 (its MMAs were issued one iteration ago)
+    const int kn = kb + S - 1;
+    if (kn < nkb) {
+      if (kb >= 1) mbar_wait(&mma_done[kn % S], (uint32_t)((((kb - 1) / S)) & 1));
+      issue_loads(kn);
+    }
+    cp_async_commit();
   }
-  mbar_wait(&mma_done[(nkb - 1) & 1], (uint32_t)(((nkb - 1) >> 1) & 1));
+  mbar_wait(&mma_done[(nkb - 1) % S], (uint32_t)(((nkb - 1) / S) & 1));
   tc_fence_after();
 
   // ---- epilogue: thread = one accumulator row (TMEM lane 32*warp + lane) ----
@@ -265,14 +277,18 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   if (p.epilogue < 0 || p.epilogue > 2) return MMB_EINVAL;
   if (p.epilogue == 2 && (p.n_tile != p.N || p.Npad != p.N || !p.ln_gamma || !p.ln_beta)) return MMB_EINVAL;
   if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w)) & 15u) return MMB_EALIGN;
-  const int smem = 2 * A_STAGE_BYTES + 2 * p.n_tile * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + p.n_tile * BK * 2;
+  int stages = SMEM_BUDGET / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return MMB_EUNSUPPORTED;
+  p.stages = stages;
+  const int smem = stages * stage_bytes;
   static bool attr_done[MMB_MAX_DEVICES] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= MMB_MAX_DEVICES) return MMB_EUNSUPPORTED;
   if (!attr_done[dev]) {
-    if (cudaFuncSetAttribute(mlp_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE_BYTES + 2 * 512 * BK * 2) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(mlp_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess)
       return MMB_ECUDA;
     attr_done[dev] = true;
   }

@@ -1,0 +1,60 @@
+"""Throughput of the tcgen05 MLP forward vs torch (fp32 SGEMM = the reference's path, and bf16) on one GPU.
+PPO ActorCritic at N = 4096 (obs 388 -> 1024 -> 1024 -> 512 -> 80 / 1) and the MARL actor/critic (512-wide, LayerNorm)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from massive_marl_benchmark_b200 import _lib as L  # noqa: E402
+from massive_marl_benchmark_b200.mlp import FusedMLP  # noqa: E402
+
+
+def net(dims):
+    mods = []
+    for i in range(len(dims) - 1):
+        mods.append(torch.nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            mods.append(torch.nn.ELU())
+    return torch.nn.Sequential(*mods)
+
+
+def timeit(fn, iters=50, warm=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+dev = torch.device("cuda:0")
+torch.backends.cuda.matmul.allow_tf32 = False
+out = {}
+M = 4096
+for name, dims in (("ppo_actor", [388, 1024, 1024, 512, 80]), ("ppo_critic", [388, 1024, 1024, 512, 1])):
+    n = net(dims).to(dev)
+    x = torch.randn(M, dims[0], device=dev)
+    f = FusedMLP.from_sequential(n, dev)
+    flops = 2 * M * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+    with torch.no_grad():
+        t_fp32 = timeit(lambda: n(x))
+        nb = n.to(torch.bfloat16); xb = x.to(torch.bfloat16)
+        t_bf16 = timeit(lambda: nb(xb))
+    t_ours = timeit(lambda: f(x))
+    L.profile_enable(True); L.profile_collect()
+    for _ in range(20):
+        f(x)
+    torch.cuda.synchronize(); L.profile_enable(False)
+    prof = L.profile_collect()
+    out[name] = {"M": M, "dims": dims, "gflop": flops / 1e9, "ours_ms": t_ours, "torch_fp32_ms": t_fp32, "torch_bf16_ms": t_bf16,
+                 "ours_tflops": flops / t_ours / 1e9, "torch_fp32_tflops": flops / t_fp32 / 1e9,
+                 "kernel_ms": {k: v[0] / v[1] for k, v in prof.items()}, "kernel_launches": {k: v[1] / 20 for k, v in prof.items()}}
+print(json.dumps(out, indent=1))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/bench_mlp.json", "w"), indent=1)
