@@ -5,7 +5,7 @@
 // feed_forward_generator (agents/algorithms/marl/utils/separated_buffer.py:170-228).  The reference
 // materialises a Python list of ints per minibatch and performs one indexed gather per field (9-11 launches,
 // each with a host->device copy of the index list).  Here one launch gathers every field of a minibatch into
-// contiguous buffers; one warp per output row, 128-bit accesses.
+// contiguous buffers: blockIdx.y = field, every thread moves 16-byte units with four independent loads in flight.
 //
 // Index modes:  0 = indices supplied (parity mode: the host permutation, e.g. torch.randperm, is the
 // reference's);  1 = a stateless bijection on [0,total) keyed by `seed` (fast mode: position j of the epoch's
@@ -58,32 +58,60 @@ __device__ __forceinline__ int64_t bijection_eval(const Bijection& b, int64_t po
   return (int64_t)x;
 }
 
+template <typename V>
+__device__ __forceinline__ void gather_field(const mmb_gather_params& p, const Bijection& bj, const V* __restrict__ src,
+                                             V* __restrict__ dst, int units_per_row) {
+  // element i of the output = (row i / upr, unit i % upr); consecutive threads write consecutive units (coalesced
+  // stores), the loads of four independent elements are in flight per thread
+  const int64_t total = p.batch_size * units_per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto src_index = [&](int64_t row) -> int64_t {
+    if (p.index_mode == 0) return __ldg(p.indices + row);
+    if (p.index_mode == 1) return bijection_eval(bj, p.batch_start + row);
+    return p.batch_start + row;
+  };
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    V v[4];
+    int64_t off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t e = i + u * stride;
+      const int64_t row = e / units_per_row;
+      const int unit = (int)(e - row * units_per_row);
+      off[u] = src_index(row) * units_per_row + unit;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(src + off[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dst[i + u * stride] = v[u];
+  }
+  for (; i < total; i += stride) {
+    const int64_t row = i / units_per_row;
+    const int unit = (int)(i - row * units_per_row);
+    dst[i] = __ldg(src + src_index(row) * units_per_row + unit);
+  }
+}
+
+// blockIdx.y = field.  Every field is moved in the widest unit its row size and alignment allow (16 / 4 / 1 bytes).
 __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ mmb_gather_params p, const Bijection bj) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp0; row < p.batch_size; row += nwarps) {
-    int64_t src_row;
-    if (p.index_mode == 0) src_row = __ldg(p.indices + row);
-    else if (p.index_mode == 1) src_row = bijection_eval(bj, p.batch_start + row);
-    else src_row = p.batch_start + row;  // identity: fused multi-field copy (buffer insert / after_update)
-    if (p.indices_out && lane == 0) p.indices_out[row] = src_row;
-    for (int f = 0; f < p.num_fields; ++f) {
-      const int rb = p.row_bytes[f];
-      const char* s = static_cast<const char*>(p.src[f]) + src_row * rb;
-      char* d = static_cast<char*>(p.dst[f]) + row * rb;
-      if (((rb & 15) == 0) && aligned16(s) && aligned16(d)) {
-        const int n16 = rb >> 4;
-        for (int i = lane; i < n16; i += 32)
-          reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(s) + i);
-      } else if ((rb & 3) == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 3u) == 0) {
-        const int n4 = rb >> 2;
-        for (int i = lane; i < n4; i += 32) reinterpret_cast<float*>(d)[i] = __ldg(reinterpret_cast<const float*>(s) + i);
-      } else {
-        for (int i = lane; i < rb; i += 32) d[i] = s[i];
-      }
+  const int f = blockIdx.y;
+  const int rb = p.row_bytes[f];
+  const char* s = static_cast<const char*>(p.src[f]);
+  char* d = static_cast<char*>(p.dst[f]);
+  if (f == 0 && p.indices_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.batch_size; row += stride) {
+      int64_t sr = p.index_mode == 0 ? __ldg(p.indices + row) : (p.index_mode == 1 ? bijection_eval(bj, p.batch_start + row) : p.batch_start + row);
+      p.indices_out[row] = sr;
     }
   }
+  if ((rb & 15) == 0 && aligned16(s) && aligned16(d))
+    gather_field<uint4>(p, bj, reinterpret_cast<const uint4*>(s), reinterpret_cast<uint4*>(d), rb >> 4);
+  else if ((rb & 3) == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 3u) == 0)
+    gather_field<uint32_t>(p, bj, reinterpret_cast<const uint32_t*>(s), reinterpret_cast<uint32_t*>(d), rb >> 2);
+  else
+    gather_field<uint8_t>(p, bj, reinterpret_cast<const uint8_t*>(s), reinterpret_cast<uint8_t*>(d), rb);
 }
 
 __global__ void __launch_bounds__(256) permutation_kernel(const Bijection bj, int64_t n, int64_t* __restrict__ out) {
@@ -106,11 +134,14 @@ extern "C" int32_t mmb_shuffle_gather(const mmb_gather_params* pp, void* stream)
   for (int f = 0; f < p.num_fields; ++f)
     if (!p.src[f] || !p.dst[f] || p.row_bytes[f] <= 0) return MMB_EINVAL;
   Bijection bj = make_bijection(p.total, p.seed);
-  int64_t blocks = (p.batch_size + 7) / 8;  // 8 warps per CTA, one row per warp per pass
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  int max_rb = 0;
+  for (int f = 0; f < p.num_fields; ++f) max_rb = p.row_bytes[f] > max_rb ? p.row_bytes[f] : max_rb;
+  int64_t blocks = (p.batch_size * ((max_rb + 15) / 16) + 1023) / 1024;  // ~4 elements per thread for the widest field
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   {
     LaunchScope ls(K_GATHER, (cudaStream_t)stream);
-    gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, bj);
+    gather_kernel<<<dim3((unsigned)blocks, p.num_fields), 256, 0, (cudaStream_t)stream>>>(p, bj);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
