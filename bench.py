@@ -294,16 +294,17 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end-to-end through the reference-facing API with host buffers -----------------------------
     K2 = max(2, min(K, 20))
+    # frames AND actions live in pinned host memory; the provider uploads step t+1's inputs on a copy stream while
+    # step t computes (every byte still crosses PCIe inside the timed region)
     host_prov = HostReplayProvider({"root": torch.cat([f["root"] for f in frames[:2]]),
-                                    "dof": torch.cat([f["dof"] for f in frames[:2]])}, dev)
+                                    "dof": torch.cat([f["dof"] for f in frames[:2]]),
+                                    "actions": torch.cat([f["actions"] for f in frames[:2]])}, dev, extra_keys=("actions",))
     cfg2 = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 7 + rank}
     task2 = TenAnt(cfg2, None, None, "cuda", local_rank, True, False, provider=host_prov)
     task2.keep_raw_obs = False
     env = VecTaskPython(task2, dev)
     st2 = RolloutStorage(N, T, (388,), (0,), (80,), dev, "sequential")
     st2.process_group = True if world > 1 else None
-    h_actions = torch.cat([f["actions"] for f in frames[:2]]).pin_memory()        # [2T, N, 80]
-    d_actions = [torch.empty(N, 80, device=dev) for _ in range(2)]
     h_rew = torch.empty(N, pin_memory=True); h_done = torch.empty(N, dtype=torch.int64, pin_memory=True)
     h_adv = torch.empty(T, N, 1, pin_memory=True)
     values = torch.randn(N, 1, device=dev); logp = torch.randn(N, device=dev)
@@ -313,9 +314,8 @@ def run_ours(args, rank, world, local_rank):
     def e2e_rollout(j):
         nonlocal cur_obs
         for t in range(T):
-            a = d_actions[t & 1]
-            a.copy_(h_actions[(j * T + t) % (2 * T)], non_blocking=True)           # H2D actions
-            obs, rew, done, _ = env.step(a)                                          # H2D frame inside the provider
+            a = host_prov.stage[(host_prov.cursor + 1) & 1]["actions"]               # uploaded with the frame (H2D)
+            obs, rew, done, _ = env.step(a)                                          # waits for that upload only
             st2.add_transitions(cur_obs, states, a, rew, done, values, logp, mu, sigma)
             cur_obs = obs
             h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)  # D2H result of the step
@@ -334,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = K2 * T * N * world / (e2e_ms * 1e-3)
-    h2d = T * (host_prov.h2d_bytes_per_frame + N * 80 * 4)
+    h2d = T * host_prov.h2d_bytes_per_frame
     d2h = T * (N * 4 + N * 8) + T * N * 4
 
     if rank != 0:

@@ -77,25 +77,51 @@ class ReplayProvider(FrameProvider):
 
 
 class HostReplayProvider(FrameProvider):
-    """Frames in pinned host memory; `frame()` uploads the current one (async on the current stream)
-    into one of two device staging sets, so a frame stays valid while the next one is uploaded."""
+    """Frames in pinned host memory.  Frame t+1 is uploaded on a dedicated copy stream while the kernels of step t
+    run (two device staging sets), so the PCIe transfer overlaps compute; `frame()` makes the compute stream wait
+    for the upload of the current frame only."""
 
-    def __init__(self, frames: Dict[str, torch.Tensor], device, loop=True):
+    def __init__(self, frames: Dict[str, torch.Tensor], device, loop=True, extra_keys=()):
         super().__init__()
-        self.host = {k: v.contiguous().pin_memory() for k, v in frames.items() if k in self.keys and v is not None}
+        keys = tuple(self.keys) + tuple(extra_keys)
+        self.host = {k: v.contiguous().pin_memory() for k, v in frames.items() if k in keys and v is not None}
         self.device = device
         self.loop = loop
         self._F = next(iter(self.host.values())).shape[0]
         self.stage = [{k: torch.empty_like(v[0], device=device) for k, v in self.host.items()} for _ in range(2)]
         self.h2d_bytes_per_frame = sum(v[0].numel() * v.element_size() for v in self.host.values())
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]     # upload of the set finished (copy stream)
+        self._free = [torch.cuda.Event(), torch.cuda.Event()]      # kernels that read the set were enqueued (compute stream)
+        self._prefetched = -1
 
     @property
     def num_frames(self):
         return self._F
 
+    def _upload(self, cursor):
+        st = self.stage[cursor & 1]
+        i = cursor % self._F if self.loop else cursor
+        if i >= self._F:
+            return
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._free[cursor & 1])   # the previous user of this staging set is done
+            for k, v in self.host.items():
+                st[k].copy_(v[i], non_blocking=True)
+            self._ready[cursor & 1].record(self.copy_stream)
+        self._prefetched = cursor
+
+    def simulate(self):
+        self.cursor += 1
+        if self._prefetched < self.cursor:
+            self._upload(self.cursor)
+
     def frame(self):
-        i = self.cursor % self._F if self.loop else self.cursor
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[self.cursor & 1])
         st = self.stage[self.cursor & 1]
-        for k, v in self.host.items():
-            st[k].copy_(v[i], non_blocking=True)
+        # the other staging set was last read by the previous step, whose kernels are already enqueued: free it and
+        # start uploading the next frame into it now
+        self._free[(self.cursor + 1) & 1].record(cur)
+        self._upload(self.cursor + 1)
         return st

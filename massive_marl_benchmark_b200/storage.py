@@ -79,6 +79,7 @@ class RolloutStorage:
         self._obs_dim = int(self.obs_slots[0, 0].numel())
         self._states_dim = int(self.states[0, 0].numel()) if self.states.numel() else 0
         self._act_dim = int(self.actions[0, 0].numel())
+        self._p_add = None
 
     # ------------------------------------------------------------------------------------------
     def add_transitions(self, observations, states, actions, rewards, dones, values, actions_log_prob, mu, sigma):
@@ -89,16 +90,20 @@ class RolloutStorage:
         keep = [c(observations), c(states), c(actions), c(rewards), c(dones), c(values), c(actions_log_prob), c(mu), c(sigma)]
         if keep[4].dtype != torch.int64:
             keep[4] = keep[4].to(torch.int64)
-        p = L.RolloutAddParams()
-        p.num_envs, p.obs_dim, p.states_dim, p.act_dim = self.num_envs, self._obs_dim, self._states_dim, self._act_dim
+        p = self._p_add
+        if p is None:   # built once; destination pointers of every slot are precomputed
+            p = self._p_add = L.RolloutAddParams()
+            p.num_envs, p.obs_dim, p.states_dim, p.act_dim = self.num_envs, self._obs_dim, self._states_dim, self._act_dim
+            planes = (self.observations, self.states, self.actions, self.rewards, self.dones, self.values,
+                      self.actions_log_prob, self.mu, self.sigma)
+            self._dst_ptrs = [[(pl[t].data_ptr() if pl.numel() else None) for pl in planes]
+                              for t in range(self.num_transitions_per_env)]
         (p.observations, p.states, p.actions, p.rewards, p.dones, p.values, p.actions_log_prob, p.mu,
-         p.sigma) = [L.ptr(t) if t.numel() else None for t in keep]
-        p.dst_observations = L.ptr(self.observations[s])
-        p.dst_states = L.ptr(self.states[s]) if self._states_dim else None
-        p.dst_actions, p.dst_rewards, p.dst_dones = L.ptr(self.actions[s]), L.ptr(self.rewards[s]), L.ptr(self.dones[s])
-        p.dst_values, p.dst_actions_log_prob = L.ptr(self.values[s]), L.ptr(self.actions_log_prob[s])
-        p.dst_mu, p.dst_sigma = L.ptr(self.mu[s]), L.ptr(self.sigma[s])
+         p.sigma) = [t.data_ptr() if t.numel() else None for t in keep]
+        (p.dst_observations, p.dst_states, p.dst_actions, p.dst_rewards, p.dst_dones, p.dst_values, p.dst_actions_log_prob,
+         p.dst_mu, p.dst_sigma) = self._dst_ptrs[s]
         L.check(L.lib().mmb_rollout_add(p, L.stream_ptr()), "mmb_rollout_add")
+        self._keep_add = keep
         self.step += 1
 
     def clear(self):

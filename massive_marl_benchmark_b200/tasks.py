@@ -132,6 +132,8 @@ class TenAnt(BaseTask):
         self.keep_raw_obs = True
         self.actions = torch.zeros(N, 80, device=dev)
         self._chain_words = torch.zeros(N, device=dev, dtype=torch.int64)   # replay(): per-env flag/count words
+        self._p_reset = None
+        self._p_step = None
         # reset_idx at the first step reloads the carry from the not-yet-refreshed root tensor
         L.check(L.lib().mmb_ten_ant_load_carry(L.ptr(self.root_states), N, L.ptr(self.pos_before),
                                                L.ptr(self.goal_before), L.ptr(self.box_before), L.stream_ptr()),
@@ -140,19 +142,22 @@ class TenAnt(BaseTask):
     # -- reference method names ---------------------------------------------------------------
     def reset_idx(self, env_ids=None):
         """ten_ant.py:810-884 for the envs flagged in `reset_buf` (env_ids is recomputed on the device)."""
-        p = L.ResetParams()
-        p.task, p.num_envs, p.num_rows = L.TASK_TEN_ANT, self.num_envs, 1
-        p.flags_i64 = L.ptr(self.reset_buf)
-        p.env_ids, p.index_a, p.index_b, p.counts = (L.ptr(self.env_ids), L.ptr(self.ant_box_indices),
-                                                     L.ptr(self.ant_indices), L.ptr(self.reset_count))
-        p.dof_state = L.ptr(self.dof_reset_staging)
+        p = self._p_reset
+        if p is None:   # built once: only the noise source and the step counter change between calls
+            p = self._p_reset = L.ResetParams()
+            p.task, p.num_envs, p.num_rows = L.TASK_TEN_ANT, self.num_envs, 1
+            p.flags_i64 = L.ptr(self.reset_buf)
+            p.env_ids, p.index_a, p.index_b, p.counts = (L.ptr(self.env_ids), L.ptr(self.ant_box_indices),
+                                                         L.ptr(self.ant_indices), L.ptr(self.reset_count))
+            p.dof_state = L.ptr(self.dof_reset_staging)
+            p.seed = self.reset_seed
+            p.c = self.consts
         if self.reset_noise is not None:
             p.noise_mode = 0
             self._noise_keep = tuple(t.contiguous() for t in self.reset_noise)
             p.noise_pos, p.noise_vel = L.ptr(self._noise_keep[0]), L.ptr(self._noise_keep[1])
         else:
-            p.noise_mode, p.seed, p.step = 1, self.reset_seed, self._step_count
-        p.c = self.consts
+            p.noise_mode, p.step = 1, self._step_count
         L.check(L.lib().mmb_reset_compact(p, L.stream_ptr()), "mmb_reset_compact")
         self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
         self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
@@ -176,7 +181,6 @@ class TenAnt(BaseTask):
 
     def post_physics_step(self):
         """ten_ant.py:894-926 (+ the fused pre_physics force scaling and wrapper clamps)."""
-        N = self.num_envs
         self.randomize_buf += 1
         self.reset_idx()
         fr = self.provider.frame()
@@ -187,9 +191,20 @@ class TenAnt(BaseTask):
         else:
             obs = self.obs_all = self._clamped_out(self._obs_all_out)
             share = self.obs_clamped = self._obs_out[self._flip]
-        self._launch(self.root_states, self.dof_state, self.actions, 1, (0, 0, 0),
-                     self.obs_buf if self.keep_raw_obs else None, obs, share, self.rew_buf, None, None, self.forces,
-                     (0, 0, 0, 0, 0, 0, 0))
+        p = self._p_step
+        if p is None:   # built once: the per-step call only refreshes the pointers that move
+            p = self._p_step = L.TenAntParams()
+            p.num_envs, p.num_frames, p.flavor = self.num_envs, 1, self.flavor
+            p.pos_before, p.goal_before, p.box_before = L.ptr(self.pos_before), L.ptr(self.goal_before), L.ptr(self.box_before)
+            p.progress_buf, p.reset_buf = L.ptr(self.progress_buf), L.ptr(self.reset_buf)
+            p.rewards, p.forces = L.ptr(self.rew_buf), L.ptr(self.forces)
+            p.c = self.consts
+        p.obs_layout, p.clip_actions, p.clip_obs = self.obs_layout, self.clip_actions, self.clip_obs
+        p.root, p.dof, p.actions = self.root_states.data_ptr(), self.dof_state.data_ptr(), self.actions.data_ptr()
+        p.obs_raw = self.obs_buf.data_ptr() if self.keep_raw_obs else None
+        p.obs = obs.data_ptr()
+        p.share_obs = share.data_ptr() if share is not None else None
+        L.check(L.lib().mmb_ten_ant_step(p, L.stream_ptr()), "mmb_ten_ant_step")
         self.provider.set_dof_actuation_force_tensor(self.forces)
         self._step_count += 1
 
