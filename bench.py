@@ -168,6 +168,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     N, T, K, W = N_ENVS, HORIZON, args.steps, max(args.warmup, 3)
     SETS = 4  # rotating frame/storage sets: 4 x ~225 MB of traffic per step >> 126 MB L2
+    GROUP = 4 * SETS  # rollouts captured per CUDA graph (the side-stream tails are joined once per graph)
 
     def barrier():
         if world > 1:
@@ -191,13 +192,18 @@ def run_ours(args, rank, world, local_rank):
     launches_per_rollout = [0]
     side = torch.cuda.Stream()
 
+    side_done = [None] * SETS   # event: the side-stream tail of the last rollout that used set s has finished
+
     def rollout(i, join=True):
         """One rollout on frame/storage set i % SETS.  Main stream: step kernel -> GAE scan.  Side stream: the reset
         lists of the T steps, then [statistics all-reduce] + normalisation.  With join=False the side work is left
-        running so that the NEXT rollout's step kernel (another storage set) overlaps it."""
+        running so that the NEXT rollouts' step kernels (other storage sets) overlap it; a set is reused only after
+        its previous tail has finished (side_done)."""
         s = i % SETS
         st, fr = storages[s], dev_frames[s]
         main = torch.cuda.current_stream()
+        if side_done[s] is not None:
+            main.wait_event(side_done[s])
         # observation after step t lands in obs slot t+1; reward/done of step t in slot t (no add_transitions pass)
         task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), None, forces[s])
         side.wait_stream(main)
@@ -207,8 +213,13 @@ def run_ours(args, rank, world, local_rank):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             st.normalize_advantages()
+            if not join:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                side_done[s] = ev
         if join:
             main.wait_stream(side)
+            side_done[s] = None
 
     _l0 = L.launch_count()
     rollout(0)
@@ -228,10 +239,12 @@ def run_ours(args, rank, world, local_rank):
                 with torch.cuda.graph(g):
                     rollout(s_)
                 graphs.append(g)
-            graph_all = torch.cuda.CUDAGraph()       # SETS consecutive rollouts, side-stream tails joined once at the end
+            graph_all = torch.cuda.CUDAGraph()       # GROUP consecutive rollouts, side-stream tails joined once at the end
             with torch.cuda.graph(graph_all):
+                for r_ in range(GROUP):
+                    rollout(r_, join=(r_ == GROUP - 1))
                 for s_ in range(SETS):
-                    rollout(s_, join=(s_ == SETS - 1))
+                    side_done[s_] = None
             for s_ in range(SETS):
                 graphs[s_].replay()
             graph_all.replay()
@@ -244,9 +257,9 @@ def run_ours(args, rank, world, local_rank):
         """`count` consecutive rollouts starting at rollout index `first` (a multiple of SETS)."""
         i = 0
         while i < count:
-            if graph_all is not None and (first + i) % SETS == 0 and count - i >= SETS:
+            if graph_all is not None and (first + i) % SETS == 0 and count - i >= GROUP:
                 graph_all.replay()
-                i += SETS
+                i += GROUP
             elif graphs is not None:
                 graphs[(first + i) % SETS].replay()
                 i += 1
