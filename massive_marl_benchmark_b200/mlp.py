@@ -146,3 +146,58 @@ class FusedMLP:
         return out
 
     __call__ = forward
+
+
+class PPOActorCriticForward:
+    """Rollout-time interface of the reference's PPO `ActorCritic` (module.py:73-91): `act(observations, states)
+    -> (actions, log_prob (N,), value (N,1), mean, log_std.repeat(N,1))` and `act_inference(observations) -> mean`,
+    with both MLPs on the tcgen05 kernels.  `evaluate` (needs autograd) stays on the reference module.
+    The reference's quirk is kept: `MultivariateNormal(mean, scale_tril=diag(exp(log_std)^2))`, i.e. the effective
+    standard deviation is sigma^2 (module.py:76-77)."""
+
+    def __init__(self, actor_critic, device="cuda"):
+        self.asymmetric = bool(getattr(actor_critic, "asymmetric", False))
+        self.actor = FusedMLP.from_sequential(actor_critic.actor, device)
+        self.critic = FusedMLP.from_sequential(actor_critic.critic, device)
+        self.log_std = actor_critic.log_std.detach().to(device)
+
+    @torch.no_grad()
+    def act(self, observations, states=None):
+        mean = self.actor(observations)
+        scale = self.log_std.exp() * self.log_std.exp()
+        noise = torch.randn_like(mean)
+        actions = mean + noise * scale
+        # log_prob of a diagonal MultivariateNormal with scale_tril = diag(scale)
+        k = mean.shape[1]
+        log_prob = -0.5 * (noise * noise).sum(-1) - scale.log().sum() - 0.5 * k * 1.8378770664093453  # log(2*pi)
+        value = self.critic(states if self.asymmetric else observations)
+        return actions, log_prob, value, mean, self.log_std.repeat(mean.shape[0], 1)
+
+    @torch.no_grad()
+    def act_inference(self, observations):
+        return self.actor(observations)
+
+
+class MarlPolicyForward:
+    """Rollout-time forward of one MARL agent (mappo_policy.get_actions path: actor_critic.py:42-69,149-168):
+    `get_actions(share_obs, obs, deterministic=False) -> (values (N,1), actions (N,A), action_log_probs (N,A))`.
+    DiagGaussian semantics of agents/algorithms/utils/distributions.py:94-117: std = sigmoid(log_std / std_x_coef) *
+    std_y_coef, per-dimension log-probs (not summed)."""
+
+    def __init__(self, actor_sd, critic_sd, std_x_coef=1.0, std_y_coef=0.5, device="cuda"):
+        self.actor = FusedMLP.from_marl_state_dict(actor_sd, "act.action_out.fc_mean", device)
+        self.critic = FusedMLP.from_marl_state_dict(critic_sd, "v_out", device)
+        log_std = actor_sd["act.action_out.log_std"].detach().to(device)
+        self.std = torch.sigmoid(log_std / std_x_coef) * std_y_coef
+
+    @torch.no_grad()
+    def get_actions(self, share_obs, obs, deterministic=False):
+        mean = self.actor(obs)
+        actions = mean if deterministic else mean + torch.randn_like(mean) * self.std
+        var = self.std * self.std
+        logp = -((actions - mean) ** 2) / (2 * var) - self.std.log() - 0.9189385332046727   # log(sqrt(2*pi))
+        return self.critic(share_obs), actions, logp
+
+    @torch.no_grad()
+    def get_values(self, share_obs):
+        return self.critic(share_obs)

@@ -118,3 +118,53 @@ def test_mlp_layer_rejects_bad_arguments(cuda_device):
     assert L.lib().mmb_mlp_layer(p, None) == -1
     assert L.lib().mmb_mlp_layer(None, None) == -1
     assert L.lib().mmb_ln_cast(None, 1, 128, 4, 64, None, None, 0.0, 0, None, None) == -1
+
+
+def test_ppo_act_interface_matches_reference_semantics(cuda_device):
+    """`act()` returns what module.py:73-87 returns: shapes, the sigma^2 scale quirk, and log-probs that equal
+    torch.distributions.MultivariateNormal's for the sampled actions."""
+    from massive_marl_benchmark_b200.mlp import PPOActorCriticForward
+    from torch.distributions import MultivariateNormal
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(0)
+
+    class AC(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.asymmetric = False
+            self.actor = _ppo_net(60, [256, 128], 8, 0.01, gen)
+            self.critic = _ppo_net(60, [256, 128], 1, 1.0, gen)
+            self.log_std = torch.nn.Parameter(torch.log(torch.tensor(0.8)) * torch.ones(8))
+
+    ac = AC().to(dev)
+    fwd = PPOActorCriticForward(ac, dev)
+    obs = torch.randn(300, 60, device=dev)
+    torch.manual_seed(1)
+    actions, logp, value, mean, log_std = fwd.act(obs, None)
+    assert actions.shape == (300, 8) and logp.shape == (300,) and value.shape == (300, 1) and log_std.shape == (300, 8)
+    dist = MultivariateNormal(mean, scale_tril=torch.diag(ac.log_std.exp() * ac.log_std.exp()))
+    assert torch.allclose(logp, dist.log_prob(actions), rtol=1e-4, atol=1e-4)
+    emp_std = (actions - mean).std(dim=0)
+    assert torch.allclose(emp_std, (ac.log_std.exp() ** 2).detach(), rtol=0.2)          # sigma^2, not sigma
+    assert _rowmax_err(fwd.act_inference(obs), ac.actor(obs).detach()) <= 3e-2
+
+
+def test_marl_policy_forward(cuda_device):
+    from massive_marl_benchmark_b200.mlp import MarlPolicyForward
+    dev = cuda_device
+    g = load_golden("mlp_marl_actor0")
+    sd = {k[2:].replace("__", "."): v for k, v in g.items() if k.startswith("w_")}
+    torch.manual_seed(0)
+    critic_sd = {k: v for k, v in sd.items() if k.startswith("base.mlp")}
+    critic_sd.update({"base.feature_norm.weight": torch.ones(388), "base.feature_norm.bias": torch.zeros(388),
+                      "base.mlp.fc1.0.weight": torch.randn(512, 388) * 0.05, "v_out.weight": torch.randn(1, 512) * 0.05,
+                      "v_out.bias": torch.zeros(1)})
+    pol = MarlPolicyForward(sd, critic_sd, device=dev)
+    obs = g["x"].to(dev); share = torch.randn(obs.shape[0], 388, device=dev)
+    values, actions, logp = pol.get_actions(share, obs)
+    assert values.shape == (obs.shape[0], 1) and actions.shape == (obs.shape[0], 8) and logp.shape == (obs.shape[0], 8)
+    v2, a_det, _ = pol.get_actions(share, obs, deterministic=True)
+    assert _rowmax_err(a_det.cpu(), g["mean"]) <= 2e-2 and torch.equal(values, v2)
+    std = torch.sigmoid(sd["act.action_out.log_std"] / 1.0) * 0.5
+    ref_lp = torch.distributions.Normal(a_det.cpu(), std).log_prob(actions.cpu())
+    assert torch.allclose(logp.cpu(), ref_lp, rtol=1e-4, atol=1e-4)
