@@ -184,13 +184,19 @@ def run_ours(args, rank, world, local_rank):
     storages = [RolloutStorage(N, T, (388,), (0,), (80,), dev, "sequential") for _ in range(SETS)]
     forces = [torch.zeros(T, N, 80, device=dev) for _ in range(SETS)]
     dof_push = torch.zeros(T, 80 * N, 2, device=dev)
+    # cross-shard advantage statistics: "p2p" = the normalise kernel publishes into every rank's mailbox over NVLink and
+    # waits on its own (dist.StatsExchange, no collective launch), "nccl" = all-reduce between the two launches (baseline)
+    mode = args.stats_exchange if world > 1 else "none"   # "none" at N>1 is a diagnostic (shard-local moments), not the product
+    xchg = mdist.StatsExchange() if mode == "p2p" else None
     for st in storages:
         st.values.normal_()
-        st.process_group = True if world > 1 else None
+        st.process_group = True if mode == "nccl" else None
+        st.stats_exchange = xchg
     last_values = torch.randn(N, 1, device=dev)
     reset_out = [None]
     launches_per_rollout = [0]
-    side = torch.cuda.Stream()
+    side = torch.cuda.Stream()       # reset-index lists of the T steps
+    side2 = torch.cuda.Stream()      # statistics exchange wait + normalisation
 
     side_done = [None] * SETS   # event: the side-stream tail of the last rollout that used set s has finished
 
@@ -210,15 +216,16 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.stream(side):
             reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
         st.compute_returns_scan(last_values, GAMMA, LAM)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
+        side2.wait_stream(main)
+        with torch.cuda.stream(side2):
             st.normalize_advantages()
+            side2.wait_stream(side)
             if not join:
                 ev = torch.cuda.Event()
-                ev.record(side)
+                ev.record(side2)
                 side_done[s] = ev
         if join:
-            main.wait_stream(side)
+            main.wait_stream(side2)
             side_done[s] = None
 
     _l0 = L.launch_count()
@@ -286,7 +293,13 @@ def run_ours(args, rank, world, local_rank):
     t_host1 = time.perf_counter()
     sampler.stop()
     launches = (L.launch_count() - launches0) if graphs is None else K * launches_per_rollout[0]
-    ms = mdist.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    my_ms = ev0.elapsed_time(ev1)
+    ms = mdist.max_over_ranks(my_ms, dev)
+    rank_ms = [my_ms]
+    if world > 1:
+        tl = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([my_ms], dtype=torch.float64, device=dev))
+        rank_ms = [float(t.item()) for t in tl]
     value = K * T * N * world / (ms * 1e-3)
 
     # ---- per-kernel durations: the same rollouts launched eagerly, every kernel bracketed by CUDA events on its
@@ -317,7 +330,8 @@ def run_ours(args, rank, world, local_rank):
     task2.keep_raw_obs = False
     env = VecTaskPython(task2, dev)
     st2 = RolloutStorage(N, T, (388,), (0,), (80,), dev, "sequential")
-    st2.process_group = True if world > 1 else None
+    st2.process_group = True if mode == "nccl" else None
+    st2.stats_exchange = xchg
     h_rew = torch.empty(N, pin_memory=True); h_done = torch.empty(N, dtype=torch.int64, pin_memory=True)
     h_adv = torch.empty(T, N, 1, pin_memory=True)
     values = torch.randn(N, 1, device=dev); logp = torch.randn(N, device=dev)
@@ -350,6 +364,9 @@ def run_ours(args, rank, world, local_rank):
     h2d = T * host_prov.h2d_bytes_per_frame
     d2h = T * (N * 4 + N * 8) + T * N * 4
 
+    xchg_errors = int(mdist.sum_over_ranks(float(xchg.errors), dev)) if xchg is not None else 0
+    if xchg_errors:
+        raise RuntimeError("statistics exchange reported %d timed-out / overrun exchanges" % xchg_errors)
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -365,13 +382,15 @@ def run_ours(args, rank, world, local_rank):
                    args.cpu_rollouts, T, N)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "ms_per_step_eager_profiled": eager_ms_per_step, "cuda_graph": graphs is not None,
+        "ms_per_step": ms / K, "ms_per_step_by_rank": [round(x / K, 5) for x in rank_ms], "ms_per_step_eager_profiled": eager_ms_per_step, "cuda_graph": graphs is not None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE",
                    "num_envs_per_gpu": N, "num_agents": 10, "horizon": T, "env_steps_per_step": T * N,
                    "l2": "4 rotating frame/storage sets, ~225 MB of traffic per step each, > 126 MB L2",
-                   "parallelism": "env-sharded dp%d" % world},
+                   "parallelism": "env-sharded dp%d" % world,
+                   "stats_exchange": {"p2p": "NVLink peer-memory mailboxes written and awaited inside the normalise kernel (no collective launch)",
+                                      "nccl": "NCCL all-reduce of 3 doubles", "none": "single shard"}[mode]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": K2, "api": "VecTaskPython.step + RolloutStorage.add_transitions/compute_returns, pinned host frames"},
         "gpu_launches": launches,
@@ -392,6 +411,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rollouts", type=int, default=8)
+    ap.add_argument("--stats-exchange", default="p2p", choices=["p2p", "nccl", "none"],
+                    help="multi-GPU advantage statistics: NVLink peer-memory mailboxes (default) or NCCL all-reduce")
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -60,7 +60,7 @@ MMB_API uint64_t mmb_launch_count(void);
  * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
 enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
        MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
-       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_COUNT };
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_COUNT };
 MMB_API int32_t mmb_profile_enable(int32_t on);
 MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
 
@@ -273,6 +273,45 @@ MMB_API int32_t mmb_gae_ppo(const mmb_gae_ppo_params* p, void* stream);
  * clears them, so the accumulator is ready for the next rollout without a memset launch (CUDA-graph safe). */
 MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, float eps, int32_t clear_stats,
                                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Env-sharded multi-GPU: exchange of the advantage statistics over NVLink peer memory.            */
+/* The reference is single-GPU (storage.py:65 normalises over all envs of the one device); with     */
+/* envs sharded over ranks the same normalisation needs the global {count,sum,sumsq}.  Instead of a */
+/* collective launch between the GAE scan and the normalisation, the normalise kernel does the      */
+/* exchange itself: its first block stores the shard's three doubles + a sequence flag straight     */
+/* into every peer's mailbox, then all blocks wait on their OWN mailbox (local memory) and sum the   */
+/* shards in rank order, so every rank normalises with bit-identical moments.  No host involvement:  */
+/* replayable from a CUDA graph; the NVLink latency sits in the normalise launch, off the scan path. */
+/*                                                                                                  */
+/* Mailbox layout (per rank, device memory of that rank): [slots][world][4] 8-byte words             */
+/* {count, sum, sumsq, seq flag}.  Exchange number q (1, 2, ...) uses slot q % slots; slots >= 2      */
+/* (a rank can be at most one exchange ahead of a peer).  All ranks must issue the same sequence of   */
+/* mmb_adv_normalize_xchg calls on one endpoint.                                                    */
+/* `state` is 8 zero-initialised uint64 of local device memory: [1] exchanges completed, [2] ticket,  */
+/* [3] error count (flag wait timed out or slot overrun), others reserved.                          */
+/* ------------------------------------------------------------------------------------------ */
+#define MMB_MAX_RANKS 16
+typedef struct mmb_xchg {
+  int32_t world, rank, slots, _pad;
+  uint64_t* state;                  /* local, [8] */
+  uint64_t* mailbox[MMB_MAX_RANKS]; /* mailbox[r] = rank r's mailbox as mapped in THIS process (mailbox[rank] is local) */
+} mmb_xchg;
+
+/* Mailbox memory must be shareable between processes, so the library allocates it (the one exception to "never
+ * allocates"): cudaMalloc + zero fill + cudaIpcGetMemHandle.  `handle64` receives the 64-byte IPC handle to send to
+ * the other ranks (any transport; dist.StatsExchange uses torch.distributed.all_gather_object). */
+MMB_API int64_t mmb_xchg_mailbox_bytes(int32_t world, int32_t slots);
+MMB_API int32_t mmb_xchg_alloc(int64_t bytes, void** dev_ptr, uint8_t* handle64);
+MMB_API int32_t mmb_xchg_open(const uint8_t* handle64, void** dev_ptr);  /* map a peer's mailbox (enables peer access) */
+MMB_API int32_t mmb_xchg_close(void* dev_ptr);                            /* unmap a peer's mailbox */
+MMB_API int32_t mmb_xchg_free(void* dev_ptr);                             /* free the local mailbox */
+
+/* Exchange + normalisation: publishes `stats` = this shard's {count,sum,sumsq} (as accumulated by mmb_gae_ppo; cleared
+ * afterwards) to all ranks, waits (bounded spin, ~2 s, then state[3]++) until all `world` shards of the exchange are in
+ * the local mailbox, and applies (adv - mean) / (std_unbiased + eps) in place with the global moments. */
+MMB_API int32_t mmb_adv_normalize_xchg(float* advantages, int64_t n, double* stats, const mmb_xchg* xchg, float eps,
+                                       void* stream);
 
 /* RolloutStorage.get_statistics (storage.py:67-73) on device: out[0] = mean trajectory length,
  * out[1] = mean reward.  No host sync. */

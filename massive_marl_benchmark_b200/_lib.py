@@ -90,6 +90,14 @@ class RolloutAddParams(C.Structure):
                             "dst_dones", "dst_values", "dst_actions_log_prob", "dst_mu", "dst_sigma")]
 
 
+MAX_RANKS = 16
+
+
+class Xchg(C.Structure):
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("slots", c_i32), ("_pad", c_i32), ("state", c_vp),
+                ("mailbox", c_vp * MAX_RANKS)]
+
+
 class GaePpoParams(C.Structure):
     _fields_ = [("num_envs", c_i32), ("num_steps", c_i32), ("rewards", c_vp), ("values", c_vp), ("dones", c_vp),
                 ("last_values", c_vp), ("gamma", c_d), ("lam", c_d), ("returns", c_vp), ("advantages", c_vp),
@@ -138,6 +146,12 @@ SYMBOLS = {
     "mmb_rollout_add": (c_i32, [C.POINTER(RolloutAddParams), c_vp]),
     "mmb_gae_ppo": (c_i32, [C.POINTER(GaePpoParams), c_vp]),
     "mmb_adv_normalize": (c_i32, [c_vp, c_i64, c_vp, c_f, c_i32, c_vp]),
+    "mmb_adv_normalize_xchg": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(Xchg), c_f, c_vp]),
+    "mmb_xchg_mailbox_bytes": (c_i64, [c_i32, c_i32]),
+    "mmb_xchg_alloc": (c_i32, [c_i64, C.POINTER(c_vp), C.POINTER(C.c_uint8)]),
+    "mmb_xchg_open": (c_i32, [C.POINTER(C.c_uint8), C.POINTER(c_vp)]),
+    "mmb_xchg_close": (c_i32, [c_vp]),
+    "mmb_xchg_free": (c_i32, [c_vp]),
     "mmb_rollout_statistics": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mmb_gae_marl": (c_i32, [C.POINTER(GaeMarlParams), c_vp]),
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
@@ -189,7 +203,7 @@ def launch_count():
 
 KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
               "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm", "mlp_layer",
-              "ln_cast")
+              "ln_cast", "adv_norm_xchg")
 
 
 def profile_enable(on=True):

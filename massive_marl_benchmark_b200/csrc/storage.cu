@@ -14,6 +14,7 @@
 #include "../../include/mmb.h"
 #include "mmb_common.cuh"
 #include "mmb_math.cuh"
+#include <cstring>
 
 namespace mmb {
 namespace {
@@ -43,6 +44,47 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
 // ------------------------------------------------------------------------------------------------
 // RolloutStorage.compute_returns (storage.py:51-65)
 // ------------------------------------------------------------------------------------------------
+// ---- statistics exchange over peer memory (mmb.h "Env-sharded multi-GPU") ----------------------
+struct XchgDev {  // kernel-parameter copy of mmb_xchg
+  int world, rank, slots, enabled;
+  unsigned long long* state;
+  unsigned long long* mailbox[MMB_MAX_RANKS];
+};
+
+inline XchgDev make_xchg(const mmb_xchg* x) {
+  XchgDev d{};
+  if (!x) return d;
+  d.world = x->world; d.rank = x->rank; d.slots = x->slots; d.enabled = 1;
+  d.state = reinterpret_cast<unsigned long long*>(x->state);
+  for (int r = 0; r < MMB_MAX_RANKS; ++r) d.mailbox[r] = reinterpret_cast<unsigned long long*>(x->mailbox[r]);
+  return d;
+}
+
+inline bool xchg_valid(const mmb_xchg* x) {
+  if (!x) return true;
+  if (x->world < 1 || x->world > MMB_MAX_RANKS || x->rank < 0 || x->rank >= x->world || x->slots < 2 || !x->state) return false;
+  for (int r = 0; r < x->world; ++r)
+    if (!x->mailbox[r]) return false;
+  return true;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 constexpr int GAE_CHUNK = 16;  // horizon 16 (the reference's default is 8): all loads of a rollout in flight at once
 
 __global__ void __launch_bounds__(256) gae_ppo_kernel(const __grid_constant__ mmb_gae_ppo_params p) {
@@ -89,6 +131,71 @@ __global__ void __launch_bounds__(256) gae_ppo_kernel(const __grid_constant__ mm
       atomicAdd(p.stats + 1, s1);
       atomicAdd(p.stats + 2, s2);
       if (blockIdx.x == 0) atomicAdd(p.stats + 0, (double)N * (double)T);
+    }
+  }
+}
+
+// Statistics exchange + normalisation in one kernel.  Block 0 publishes this shard's {count,sum,sumsq}: thread r
+// stores the three words and then the sequence flag (release, system scope) into rank r's mailbox - `world` NVLink
+// peer stores in flight at once - and clears the accumulator.  Every block then waits for the `world` flags of
+// exchange q = done + 1 in its OWN mailbox (local memory; the peers wrote them over NVLink), sums the shards in rank
+// order (bit-identical on every rank) and normalises its slice.  The last block to finish advances `done`.
+constexpr long long XCHG_SPIN_CYCLES = 4000000000ll;  // ~2 s at 1.9 GHz, then give up and count an error
+
+__global__ void __launch_bounds__(256) adv_normalize_xchg_kernel(float* __restrict__ adv, int64_t n, double* stats,
+                                                                 const __grid_constant__ XchgDev x, float eps) {
+  __shared__ double sh[MMB_MAX_RANKS][3];
+  const unsigned long long q = ld_relaxed_sys(x.state + 1) + 1ull;
+  const size_t slot = (size_t)(q % (unsigned)x.slots) * x.world;
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < x.world) {
+      const unsigned long long* st = reinterpret_cast<const unsigned long long*>(stats);
+      const unsigned long long c = st[0], a = st[1], b = st[2];
+      unsigned long long* box = x.mailbox[threadIdx.x] + (slot + x.rank) * 4;
+      st_relaxed_sys(box + 0, c);
+      st_relaxed_sys(box + 1, a);
+      st_relaxed_sys(box + 2, b);
+      st_release_sys(box + 3, q);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { stats[0] = 0.0; stats[1] = 0.0; stats[2] = 0.0; }
+  }
+  if ((int)threadIdx.x < x.world) {
+    const unsigned long long* box = x.mailbox[x.rank] + (slot + threadIdx.x) * 4;
+    const long long t0 = clock64();
+    unsigned long long f = ld_acquire_sys(box + 3);
+    while (f < q && clock64() - t0 < XCHG_SPIN_CYCLES) {
+      __nanosleep(32);
+      f = ld_acquire_sys(box + 3);
+    }
+    if (f != q && blockIdx.x == 0) atomicAdd(x.state + 3, 1ull);  // timed out, or the slot was overrun
+    sh[threadIdx.x][0] = __longlong_as_double((long long)ld_relaxed_sys(box + 0));
+    sh[threadIdx.x][1] = __longlong_as_double((long long)ld_relaxed_sys(box + 1));
+    sh[threadIdx.x][2] = __longlong_as_double((long long)ld_relaxed_sys(box + 2));
+  }
+  __syncthreads();
+  double cnt = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int r = 0; r < x.world; ++r) { cnt += sh[r][0]; s1 += sh[r][1]; s2 += sh[r][2]; }
+  const double mean_d = s1 / cnt;
+  double var_d = (s2 - s1 * mean_d) / (cnt - 1.0);
+  if (var_d < 0.0) var_d = 0.0;
+  const float mean = (float)mean_d;
+  const float denom = fadd((float)sqrt(var_d), eps);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = aligned16(adv) ? (n >> 2) : 0;
+  for (int64_t j = i; j < n4; j += stride) {
+    float4 v = reinterpret_cast<float4*>(adv)[j];
+    v.x = fdiv(fsub(v.x, mean), denom); v.y = fdiv(fsub(v.y, mean), denom);
+    v.z = fdiv(fsub(v.z, mean), denom); v.w = fdiv(fsub(v.w, mean), denom);
+    reinterpret_cast<float4*>(adv)[j] = v;
+  }
+  for (int64_t j = (n4 << 2) + i; j < n; j += stride) adv[j] = fdiv(fsub(adv[j], mean), denom);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(x.state + 2, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      x.state[2] = 0ull;
+      st_relaxed_sys(x.state + 1, q);
     }
   }
 }
@@ -304,6 +411,56 @@ extern "C" int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats
     adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps, clear_stats);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_adv_normalize_xchg(float* advantages, int64_t n, double* stats, const mmb_xchg* xchg, float eps,
+                                          void* stream) {
+  if (!advantages || !stats || !xchg || n <= 0 || !xchg_valid(xchg)) return MMB_EINVAL;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 4) blocks = 148 * 4;  // all blocks co-resident: each one waits on the mailbox flags
+  const XchgDev xd = make_xchg(xchg);
+  {
+    LaunchScope ls(K_ADV_NORM_XCHG, (cudaStream_t)stream);
+    adv_normalize_xchg_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, xd, eps);
+  }
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int64_t mmb_xchg_mailbox_bytes(int32_t world, int32_t slots) {
+  if (world < 1 || world > MMB_MAX_RANKS || slots < 2) return MMB_EINVAL;
+  return (int64_t)slots * world * 4 * 8;
+}
+
+extern "C" int32_t mmb_xchg_alloc(int64_t bytes, void** dev_ptr, uint8_t* handle64) {
+  if (bytes <= 0 || !dev_ptr || !handle64) return MMB_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return MMB_ECUDA;
+  if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaFree(p); return MMB_ECUDA; }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); (void)cudaGetLastError(); return MMB_ECUDA; }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return MMB_OK;
+}
+
+extern "C" int32_t mmb_xchg_open(const uint8_t* handle64, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return MMB_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  if (cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
+  return MMB_OK;
+}
+
+extern "C" int32_t mmb_xchg_close(void* dev_ptr) {
+  if (!dev_ptr) return MMB_EINVAL;
+  return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_xchg_free(void* dev_ptr) {
+  if (!dev_ptr) return MMB_EINVAL;
+  return cudaFree(dev_ptr) == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
 extern "C" int32_t mmb_rollout_statistics(const uint8_t* dones, const float* rewards, int32_t num_steps,

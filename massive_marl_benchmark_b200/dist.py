@@ -9,8 +9,12 @@ reset / GAE.  Only two reductions cross environments:
      `all_reduce_stats` between mmb_gae_* and mmb_adv_normalize;
   2. the PPO/MAPPO gradient all-reduce after backward - `all_reduce_grads` (sum / world).
 
-Both are plain NCCL all-reduces: neither follows a compute kernel closely enough to fuse (the first is
-24 bytes, latency-bound; the second belongs to autograd, out of scope for the kernels).
+The first has two implementations.  `StatsExchange` is the product path: the normalise kernel's first block
+stores the shard's three doubles + a sequence flag into every rank's mailbox with NVLink peer stores, then all
+blocks wait on their own mailbox and normalise - exchange and compute in ONE launch, no collective kernel, no
+host involvement, CUDA-graph replayable.  `all_reduce_stats` (a plain NCCL all-reduce between
+the two launches) is kept as the baseline it is measured against.  The second belongs to autograd (out of
+scope for the kernels) and is a bucketed NCCL all-reduce.
 """
 import os
 
@@ -92,3 +96,87 @@ def sum_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+class StatsExchange:
+    """Per-process endpoint of the peer-memory statistics exchange (include/mmb.h, `mmb_xchg`).
+
+    `StatsExchange(group)` allocates this rank's mailbox, trades the 64-byte CUDA IPC handles through
+    torch.distributed and maps every peer's mailbox.  Attach it to any number of `RolloutStorage`s
+    (`storage.stats_exchange = xchg`); exchanges are numbered by device-side counters in issue order, so all ranks
+    must issue the same sequence of normalize_advantages calls on storages attached to it.
+
+    `StatsExchange.local(world, slots)` builds `world` endpoints inside ONE process on one device (mailboxes are
+    ordinary local allocations, no IPC) - used by the single-GPU tests of the protocol."""
+
+    def __init__(self, group=None, slots=4, device=None):
+        from . import _lib as L
+        import ctypes as C
+        lib = L.lib()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > L.MAX_RANKS:
+            raise L.MmbError("StatsExchange supports up to %d ranks (one NVLink domain); got %d" % (L.MAX_RANKS, self.world))
+        self.slots = slots
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = lib.mmb_xchg_mailbox_bytes(self.world, slots)
+        if nbytes <= 0:
+            raise L.MmbError("bad exchange geometry world=%d slots=%d" % (self.world, slots))
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        with torch.cuda.device(self.device):
+            L.check(lib.mmb_xchg_alloc(nbytes, C.byref(ptr), handle), "mmb_xchg_alloc")
+            self._local = ptr.value
+            self._opened = []
+            handles = [bytes(handle)]
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            self.state = torch.zeros(8, dtype=torch.int64, device=self.device)
+            self.desc = L.Xchg()
+            self.desc.world, self.desc.rank, self.desc.slots = self.world, self.rank, slots
+            self.desc.state = self.state.data_ptr()
+            for r in range(self.world):
+                if r == self.rank:
+                    self.desc.mailbox[r] = self._local
+                else:
+                    peer, hb = C.c_void_p(), (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                    L.check(lib.mmb_xchg_open(hb, C.byref(peer)), "mmb_xchg_open (rank %d)" % r)
+                    self._opened.append(peer.value)
+                    self.desc.mailbox[r] = peer.value
+            torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=group)      # nobody publishes before every mailbox is mapped
+
+    @classmethod
+    def local(cls, world, slots=4, device="cuda"):
+        """`world` endpoints in this process (protocol tests): returns a list of StatsExchange-like objects."""
+        from . import _lib as L
+        nwords = int(L.lib().mmb_xchg_mailbox_bytes(world, slots)) // 8
+        boxes = [torch.zeros(nwords, dtype=torch.int64, device=device) for _ in range(world)]
+        out = []
+        for r in range(world):
+            x = cls.__new__(cls)
+            x.world, x.rank, x.slots, x.device = world, r, slots, torch.device(device)
+            x._local, x._opened, x._boxes = None, [], boxes
+            x.state = torch.zeros(8, dtype=torch.int64, device=device)
+            x.desc = L.Xchg()
+            x.desc.world, x.desc.rank, x.desc.slots, x.desc.state = world, r, slots, x.state.data_ptr()
+            for k in range(world):
+                x.desc.mailbox[k] = boxes[k].data_ptr()
+            out.append(x)
+        return out
+
+    @property
+    def errors(self) -> int:
+        """Exchanges whose flags timed out or whose slot was overrun (host sync)."""
+        return int(self.state[3].item())
+
+    def close(self):
+        from . import _lib as L
+        lib = L.lib()
+        for p in self._opened:
+            lib.mmb_xchg_close(p)
+        self._opened = []
+        if self._local:
+            lib.mmb_xchg_free(self._local)
+            self._local = None

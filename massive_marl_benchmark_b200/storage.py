@@ -17,8 +17,10 @@ What changes underneath:
 that follows step t straight into slot t+1 (`obs_slots`), so a rollout needs no add_transitions copy of
 the 1.5 KB/env observation at all; `roll_last_obs()` moves slot T to slot 0 between rollouts.
 
-Multi-GPU (env-sharded): set `process_group`; the (count, sum, sumsq) advantage statistics are
-all-reduced (3 doubles, NCCL) between the two launches so every shard normalises with global moments.
+Multi-GPU (env-sharded): every shard normalises with the global moments.  Set `stats_exchange` (a
+`dist.StatsExchange`) and the normalise kernel itself publishes the shard's (count, sum, sumsq) into every rank's
+mailbox over NVLink and waits on its own mailbox for the peers' - no collective launch; or set `process_group`
+for the baseline (NCCL all-reduce of the 3 doubles between the two launches).
 """
 import torch
 
@@ -70,6 +72,7 @@ class RolloutStorage:
         self.step = 0
         self.batch_size = T * N
         self.process_group = None
+        self.stats_exchange = None
         self._adv_stats4 = torch.zeros(4, device=dev, dtype=torch.float64)   # count, sum, sumsq + library ticket
         self.adv_stats = self._adv_stats4[:3]
         self._stats_out = torch.zeros(2, device=dev)
@@ -134,6 +137,10 @@ class RolloutStorage:
     def normalize_advantages(self):
         """Second half (storage.py:65): [all-reduce of the statistics over env shards] + (adv - mean) / (std + 1e-8)."""
         T, N = self.num_transitions_per_env, self.num_envs
+        if self.stats_exchange is not None:
+            L.check(L.lib().mmb_adv_normalize_xchg(L.ptr(self.advantages), T * N, L.ptr(self._adv_stats4), self.stats_exchange.desc, 1e-8,
+                                                   L.stream_ptr()), "mmb_adv_normalize_xchg")
+            return
         if self.process_group is not None:
             from . import dist as mdist
             mdist.all_reduce_stats(self.adv_stats, self.process_group)

@@ -71,3 +71,125 @@ def test_host_provider_equals_device_provider(cuda_device):
         oh, rh, dh, _ = env_h.step(a[t % T])
         assert torch.equal(od, oh) and torch.equal(rd, rh) and torch.equal(dd, dh), t
         assert torch.equal(env_d.task.obs_buf, env_h.task.obs_buf)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# peer-memory statistics exchange (mmb_xchg): the protocol with several endpoints inside one process
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_stats_exchange_equals_unsharded_normalisation(cuda_device, world):
+    """`world` env shards, each with its own storage + exchange endpoint (mailboxes in local memory), must produce
+    the advantages of ONE unsharded storage: same returns bit-for-bit, normalised advantages equal to fp32 rounding
+    of the fp64 moments (the summation order over shards differs from the single accumulator's)."""
+    from massive_marl_benchmark_b200.dist import StatsExchange, shard_range
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    dev = cuda_device
+    T, N = 8, 1000
+    gen = torch.Generator().manual_seed(5)
+    rewards = torch.randn(T, N, 1, generator=gen).to(dev)
+    values = torch.randn(T, N, 1, generator=gen).to(dev)
+    dones = (torch.rand(T, N, 1, generator=gen) < 0.05).to(torch.uint8).to(dev)
+    last = torch.randn(N, 1, generator=gen).to(dev)
+
+    def fill(st, lo, hi):
+        st.rewards.copy_(rewards[:, lo:hi]); st.values.copy_(values[:, lo:hi]); st.dones.copy_(dones[:, lo:hi])
+
+    whole = RolloutStorage(N, T, (4,), (0,), (2,), dev)
+    fill(whole, 0, N)
+    whole.compute_returns(last, 0.99, 0.95)
+
+    ends = StatsExchange.local(world, slots=4, device=dev)
+    shards = []
+    for r in range(world):
+        lo, hi = shard_range(N, r, world)
+        st = RolloutStorage(hi - lo, T, (4,), (0,), (2,), dev)
+        st.stats_exchange = ends[r]
+        shards.append((st, lo, hi))
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for rep in range(6):                      # more exchanges than slots: the ring wraps
+        for st, lo, hi in shards:
+            fill(st, lo, hi)
+            st.compute_returns_scan(last[lo:hi], 0.99, 0.95)
+        torch.cuda.synchronize()
+        for (st, lo, hi), stream in zip(shards, streams):     # one stream per emulated rank: each normalise launch
+            with torch.cuda.stream(stream):                   # waits for the others' publications
+                st.normalize_advantages()
+        torch.cuda.synchronize()
+        for st, lo, hi in shards:
+            assert torch.equal(st.returns, whole.returns[:, lo:hi])
+            assert torch.allclose(st.advantages, whole.advantages[:, lo:hi], rtol=2e-6, atol=2e-6)
+        # every rank normalised with bit-identical moments: shard 0's mean/std reproduce on all shards
+    assert all(e.errors == 0 for e in ends)
+    assert all(int(e.state[1]) == 6 for e in ends)
+    assert all(float(st._adv_stats4.abs().sum()) == 0.0 for st, _, _ in shards)   # accumulator cleared by the exchange
+
+
+@pytest.mark.gpu
+def test_stats_exchange_streams_and_graph_replay(cuda_device):
+    """Normalise kernels enqueued BEFORE the peer's scan (on other streams) wait on the mailbox flag; the whole
+    pattern replays from a CUDA graph (device-side sequence counters, no host arguments change)."""
+    from massive_marl_benchmark_b200.dist import StatsExchange
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    dev = cuda_device
+    T, N = 4, 512
+    ends = StatsExchange.local(2, slots=4, device=dev)
+    sts = [RolloutStorage(N, T, (4,), (0,), (2,), dev) for _ in range(2)]
+    last = torch.randn(N, 1, device=dev)
+    ref = RolloutStorage(2 * N, T, (4,), (0,), (2,), dev)
+    for r, st in enumerate(sts):
+        st.stats_exchange = ends[r]
+        st.rewards.normal_(); st.values.normal_()
+        ref.rewards[:, r * N:(r + 1) * N] = st.rewards; ref.values[:, r * N:(r + 1) * N] = st.values
+    ref.compute_returns(torch.cat([last, last]), 0.99, 0.95)
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda._sleep(1)     # load the delay kernel now: a first launch (lazy module load) would block behind the spinning kernel
+    torch.cuda.synchronize()
+    # rank 0 scans and immediately normalises on s0 (must wait ~ for rank 1), rank 1 follows later on s1
+    with torch.cuda.stream(s0):
+        sts[0].compute_returns(last, 0.99, 0.95)
+    with torch.cuda.stream(s1):
+        torch.cuda._sleep(20_000_000)          # ~10 ms: rank 0's normalise is spinning by now
+        sts[1].compute_returns(last, 0.99, 0.95)
+    torch.cuda.synchronize()
+    for r, st in enumerate(sts):
+        assert torch.allclose(st.advantages, ref.advantages[:, r * N:(r + 1) * N], rtol=2e-6, atol=2e-6)
+    assert ends[0].errors == 0 and ends[1].errors == 0
+
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        main = torch.cuda.current_stream()
+        for st in sts:
+            st.compute_returns_scan(last, 0.99, 0.95)
+        s1.wait_stream(main)
+        sts[0].normalize_advantages()           # the two ranks' exchange kernels on parallel graph branches
+        with torch.cuda.stream(s1):
+            sts[1].normalize_advantages()
+        main.wait_stream(s1)
+    for _ in range(9):                          # wraps the 4-slot ring twice
+        g.replay()
+    torch.cuda.synchronize()
+    for r, st in enumerate(sts):
+        assert torch.allclose(st.advantages, ref.advantages[:, r * N:(r + 1) * N], rtol=2e-6, atol=2e-6)
+    assert ends[0].errors == 0 and ends[1].errors == 0
+
+
+@pytest.mark.gpu
+def test_stats_exchange_ipc_endpoint_single_rank(cuda_device):
+    """The IPC-allocated endpoint (world 1: alloc + handle export, no peers) behaves like the plain path."""
+    from massive_marl_benchmark_b200.dist import StatsExchange
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    dev = cuda_device
+    x = StatsExchange(slots=2, device=dev)
+    a, b = (RolloutStorage(300, 5, (4,), (0,), (2,), dev) for _ in range(2))
+    a.rewards.normal_(); a.values.normal_()
+    b.rewards.copy_(a.rewards); b.values.copy_(a.values)
+    b.stats_exchange = x
+    last = torch.randn(300, 1, device=dev)
+    for _ in range(3):
+        a.compute_returns(last, 0.99, 0.95)
+        b.compute_returns(last, 0.99, 0.95)
+    torch.cuda.synchronize()
+    assert torch.equal(a.returns, b.returns) and torch.equal(a.advantages, b.advantages)
+    assert x.errors == 0
+    x.close()
