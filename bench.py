@@ -164,6 +164,7 @@ def run_ours(args, rank, world, local_rank):
     from massive_marl_benchmark_b200.tasks import TenAnt, reset_replay
     from massive_marl_benchmark_b200.vec_task import VecTaskPython
 
+    numa_bound = mdist.bind_to_gpu_numa(local_rank) if world > 1 else False
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     N, T, K, W = N_ENVS, HORIZON, args.steps, max(args.warmup, 3)
@@ -392,7 +393,7 @@ def run_ours(args, rank, world, local_rank):
                    "stats_exchange": {"p2p": "NVLink peer-memory mailboxes written and awaited inside the normalise kernel (no collective launch)",
                                       "nccl": "NCCL all-reduce of 3 doubles", "none": "single shard"}[mode]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": K2, "api": "VecTaskPython.step + RolloutStorage.add_transitions/compute_returns, pinned host frames"},
+                "steps": K2, "numa_bound": numa_bound, "api": "VecTaskPython.step + RolloutStorage.add_transitions/compute_returns, pinned host frames"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "ten_ant_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,

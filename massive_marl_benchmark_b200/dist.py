@@ -38,6 +38,26 @@ def init_from_env(backend=None):
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa(local_rank: int) -> bool:
+    """Pin this process to the CPU cores NVML reports as local to GPU `local_rank`, so pinned host buffers allocated
+    afterwards are first-touched on the GPU's NUMA node (the host->device path of the end-to-end loop then does not
+    cross the socket interconnect).  Returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def shard_range(num_envs: int, rank: int, world: int):
     """Contiguous env shard of `rank`: [lo, hi).  Remainder envs go to the lowest ranks."""
     base, rem = divmod(num_envs, world)
