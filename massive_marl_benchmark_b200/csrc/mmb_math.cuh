@@ -245,6 +245,11 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
                "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// L2 prefetch of a contiguous global range by the TMA engine (no destination, no registers, no smem): 16 B aligned
+// address, size a multiple of 16 B.
+__device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 }  // namespace mmb

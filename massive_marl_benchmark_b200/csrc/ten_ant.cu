@@ -31,7 +31,7 @@ constexpr int A = 10;
 constexpr int ROOT_ENV = 143;  // 11 rows x 13
 constexpr int OBS_ENV = 388;
 constexpr int BOX_W = 12;
-constexpr int PART_W = 6;
+constexpr int PART_W = 7;  // adr, gdr, up, elec, asq, #joints at limit, arrive/fallen flags (odd stride: conflict-free)
 
 template <int EPT>
 struct TenAntSmem {
@@ -44,6 +44,20 @@ struct TenAntSmem {
   static constexpr int kFloats = kObs + kRoot + kBox + 4;
   static constexpr int kBytes = kFloats * 4;
 };
+
+// prefetch distance in CTAs (launch order); MMB_TEN_ANT_PREFETCH overrides (0 = off).  Swept on B200: flat optimum
+// between 1 and 2 CTAs per SM ahead; a full resident wave ahead is too early (evicted / competes with demand loads).
+inline int prefetch_distance() {
+  static const int dist = [] {
+    const char* v = getenv("MMB_TEN_ANT_PREFETCH");
+    if (v) return atoi(v);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * sms;
+  }();
+  return dist;
+}
 
 // goal offsets c_j of ten_ant.py:1365-1390 and box_targets_k of ten_ant.py:172-181
 __device__ __forceinline__ float goal_offset(int k) { return 1.5f + 3.0f * (float)(k >> 1); }
@@ -153,6 +167,118 @@ __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* _
   }
 }
 
+// Per-env finish by one thread: ordered sums over the ten ants' partial terms (ten_ant.py:1173-1301), reward, and the
+// progress / reset bookkeeping (inline for T == 1, data-carrying atomic + last-reporter chain for T <= 32).
+__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo) {
+  const mmb_ant_consts& c = p.c;
+  const int T = p.num_frames;
+  float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
+  int lim = __float_as_int(pt[5]);
+  int fl = __float_as_int(pt[6]);
+  int n_arrive = fl & 1;
+  bool fallen = (fl & 2) != 0;
+#pragma unroll
+  for (int kk = 1; kk < A; ++kk) {
+    const float* qq = pt + kk * PART_W;
+    adr = fadd(adr, qq[0]); gdr = fadd(gdr, qq[1]); up = fadd(up, qq[2]); elec = fadd(elec, qq[3]); asq = fadd(asq, qq[4]);
+    lim += __float_as_int(qq[5]);
+    int f2 = __float_as_int(qq[6]);
+    n_arrive += f2 & 1; fallen = fallen || (f2 & 2);
+  }
+  float quat_dist = bo[4];
+  float total_r = fadd(5.0f, fmul(up, 10.0f));
+  total_r = fadd(total_r, fmul(c.quat_reward_scale, quat_dist));
+  total_r = fadd(total_r, adr);
+  total_r = fadd(total_r, gdr);
+  total_r = fadd(total_r, (float)(2 * n_arrive));
+  total_r = fadd(total_r, (quat_dist > 0.9f && n_arrive == A) ? 100.0f : 0.0f);
+  total_r = fsub(total_r, fmul(c.actions_cost, asq));
+  total_r = fsub(total_r, fmul(c.energy_cost, elec));
+  total_r = fsub(total_r, fmul((float)lim, c.joints_at_limit_cost));
+  if (fallen) total_r = c.death_cost;
+  if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = total_r;
+  if (T == 1) {
+    p.box_before[(int64_t)en * 2] = bo[2];
+    p.box_before[(int64_t)en * 2 + 1] = bo[3];
+    // ten_ant.py:896-901 (progress += 1; reset_idx zeroes progress/reset of flagged envs) + :1296-1299
+    int64_t prog = p.progress_buf[en] + 1;
+    if (p.reset_buf[en] != 0) prog = 0;
+    int64_t rs = fallen ? 1 : 0;
+    if ((float)prog >= (float)((double)c.max_episode_length - 1.0)) rs = 1;
+    p.progress_buf[en] = prog;
+    p.reset_buf[en] = rs;
+    if (p.dones_i64) p.dones_i64[en] = rs;
+    if (p.dones_u8) p.dones_u8[en] = (uint8_t)rs;
+  } else if (p.scratch && T <= 32) {
+    // Horizon-batched launch: ONE data-carrying atomic per (env, frame).  The 64-bit word of env `en` collects
+    // the `fallen` bit of every frame (bits 0..31) and the number of frames that have reported (bits 32..).
+    // The thread that sees T-1 earlier reports holds all T bits in its hand: it runs the progress / reset chain
+    // and writes the carry after the last frame.  No fence, no flag read-back, no second kernel; every unit of
+    // the env has passed its own carry reads by the time the last report arrives.
+    const unsigned long long mine = (1ull << 32) | ((unsigned long long)(fallen ? 1u : 0u) << t);
+    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + en, mine);
+    if ((unsigned)(old >> 32) == (unsigned)T - 1u) {
+      p.scratch[en] = 0ull;            // self-resetting for the next launch / graph replay
+      int64_t prog = p.progress_buf[en];
+      bool flag = p.reset_buf[en] != 0;
+      chain_bits(p, en, 0, T, (uint32_t)(old | mine), prog, flag);
+      p.progress_buf[en] = prog;
+      p.reset_buf[en] = flag ? 1 : 0;
+      const float* last = p.root + (int64_t)(T - 1) * p.root_frame_stride;
+      // carry of the whole env by this thread: the goal direction once, then ten (xy, goal) pairs
+      const float* b = last + ((int64_t)en * 11 + 10) * 13;
+      const float bx = __ldg(b), by = __ldg(b + 1);
+      float xy[2 * A];
+#pragma unroll
+      for (int kk = 0; kk < A; ++kk) {
+        xy[2 * kk] = __ldg(last + ((int64_t)en * 11 + kk) * 13);
+        xy[2 * kk + 1] = __ldg(last + ((int64_t)en * 11 + kk) * 13 + 1);
+      }
+      float s, cs;
+      box_dir(__ldg(b + 5), __ldg(b + 6), s, cs);
+#pragma unroll
+      for (int kk = 0; kk < A; ++kk) {
+        float gx, gy;
+        goal_of(kk, bx, by, s, cs, gx, gy);
+        *reinterpret_cast<float2*>(p.pos_before + ((int64_t)en * A + kk) * 2) = make_float2(xy[2 * kk], xy[2 * kk + 1]);
+        *reinterpret_cast<float2*>(p.goal_before + ((int64_t)en * A + kk) * 2) = make_float2(gx, gy);
+      }
+      *reinterpret_cast<float2*>(p.box_before + (int64_t)en * 2) = make_float2(bx, by);
+    }
+  } else {  // `fallen` only; ten_ant_post_kernel finishes the flags
+    if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + en] = fallen ? 1 : 0;
+    else p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + en] = fallen ? 1 : 0;
+  }
+}
+
+// Outputs that are not a verbatim copy of the obs tile: clamped copies of a raw tile and the per-agent [N][10][46] view.
+template <int NT, int EPT>
+__device__ __forceinline__ void extra_outputs(const mmb_ten_ant_params& p, int t, int e0, int ne, int tid, const float* obs_s,
+                                              bool tile_clamped, float clip) {
+  const int n = ne * OBS_ENV;
+  if (!tile_clamped) {  // raw tile: clamped outputs need a pass
+    if (p.obs_layout == 0 && p.obs) {
+      tile_store<NT, EPT * OBS_ENV / 4, true>(p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
+    } else if (p.obs_layout == 1 && p.share_obs) {
+      tile_store<NT, EPT * OBS_ENV / 4, true>(p.share_obs + (int64_t)t * p.share_obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
+    }
+  }
+  if (p.obs_layout == 1 && p.obs) {  // multi_vec_task.py:105-116: per agent cat(own 38, tail 8) -> [N][10][46]
+    float* g = p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * 460;
+    const int n2 = ne * 230;  // float2 granules: 46 and 38 are even, so a pair never straddles a boundary
+    const bool al8 = (reinterpret_cast<uintptr_t>(g) & 7u) == 0;
+    for (int i = tid; i < n2; i += NT) {
+      int er = i / 230, r2 = i - er * 230;
+      int a = r2 / 23, c2 = r2 - a * 23;
+      int src = er * OBS_ENV + (c2 < 19 ? a * 38 + 2 * c2 : 380 + 2 * (c2 - 19));
+      float2 v = *reinterpret_cast<const float2*>(obs_s + src);
+      if (!tile_clamped) { v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip); }
+      if (al8) *reinterpret_cast<float2*>(g + 2 * i) = v;
+      else { g[2 * i] = v.x; g[2 * i + 1] = v.y; }
+    }
+  }
+}
+
 template <int EPT>
 struct UnitIdx {
   int tile, t, e0, ne;
@@ -164,11 +290,30 @@ struct UnitIdx {
   }
 };
 
+// L2 prefetch of the inputs of unit `u` (launch order: env tile fastest, then frame) by the TMA engine.  A CTA calls it
+// for the unit about a third of a resident wave ahead: by the time that CTA starts, its root / dof / action tiles sit
+// in L2, so its load phase sees L2 latency instead of a loaded-HBM round trip and HBM requests are issued early.
+// Three instructions in one thread, no registers or shared memory held.  Measured: -9 % kernel time.
+template <int EPT>
+__device__ __forceinline__ void prefetch_unit(const mmb_ten_ant_params& p, int64_t u, int ntiles) {
+  const int64_t t2 = u / ntiles, tile2 = u - t2 * ntiles;
+  if (t2 >= p.num_frames || (tile2 + 1) * EPT > p.num_envs) return;
+  const float* r2 = p.root + t2 * p.root_frame_stride + tile2 * EPT * ROOT_ENV;
+  const float* d2 = p.dof + t2 * p.dof_frame_stride + tile2 * EPT * 160;
+  const float* a2 = p.actions + t2 * p.actions_frame_stride + tile2 * EPT * 80;
+  if (aligned16(r2) && aligned16(d2) && aligned16(a2)) {
+    tma_prefetch_l2(r2, EPT * ROOT_ENV * 4);
+    tma_prefetch_l2(d2, EPT * 160 * 4);
+    tma_prefetch_l2(a2, EPT * 80 * 4);
+  }
+}
+
 // One CTA = one unit = one tile of EPT envs of one frame.  Short-lived CTAs at 64 registers keep 6 (EPT 16) or 3
 // (EPT 32) CTAs = 30 warps per SM resident: the kernel is a long dependent fp32 chain per thread, so it lives on
 // thread-level parallelism (a persistent, register-prefetching variant at 96 registers measured 40% slower).
 template <int FLAVOR, int EPT>
-__global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(const __grid_constant__ mmb_ten_ant_params p) {
+__global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(const __grid_constant__ mmb_ten_ant_params p,
+                                                                              const int prefetch_dist) {
   constexpr int NT = EPT * A;
   extern __shared__ __align__(128) float smem[];
   float* obs_s = smem;
@@ -197,6 +342,8 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
   } else {
     tile_load(root_s, root_g, ne * ROOT_ENV, tid, NT);
   }
+
+  if (prefetch_dist > 0 && tid == 32) prefetch_unit<EPT>(p, (int64_t)blockIdx.x + prefetch_dist, (N + EPT - 1) / EPT);
 
   const int el = tid / A, k = tid - el * A;
   const int e = e0 + el;
@@ -342,7 +489,8 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
     bool fallen = pos.z < c.termination_height;
     float* pt = part_s + (el * A + k) * PART_W;
     pt[0] = adr; pt[1] = gdr; pt[2] = up; pt[3] = elec; pt[4] = asq;
-    pt[5] = __int_as_float(lim | (arrive ? 0x100 : 0) | (fallen ? 0x200 : 0));
+    pt[5] = __int_as_float(lim);
+    pt[6] = __int_as_float((arrive ? 1 : 0) | (fallen ? 2 : 0));
 
     if (T == 1) {  // carry out (ten_ant.py:905-925); T > 1: written once per env by the chain executor below
       float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
@@ -372,110 +520,267 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
   }
 
   // ---- per-env finish: ordered sums over the ten ants (ten_ant.py:1173-1301) ----
-  if (tid < ne) {
-    const int en = e0 + tid;
-    const float* pt = part_s + tid * A * PART_W;
-    float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
-    int fl = __float_as_int(pt[5]);
-    int lim = fl & 0xff, n_arrive = (fl >> 8) & 1;
-    bool fallen = (fl & 0x200) != 0;
-#pragma unroll
-    for (int kk = 1; kk < A; ++kk) {
-      const float* qq = pt + kk * PART_W;
-      adr = fadd(adr, qq[0]); gdr = fadd(gdr, qq[1]); up = fadd(up, qq[2]); elec = fadd(elec, qq[3]); asq = fadd(asq, qq[4]);
-      int f2 = __float_as_int(qq[5]);
-      lim += f2 & 0xff; n_arrive += (f2 >> 8) & 1; fallen = fallen || (f2 & 0x200);
+  if (tid < ne) finish_env(p, t, e0 + tid, part_s + tid * A * PART_W, box_s + tid * BOX_W);
+  extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
+  if (tma_stored && tid == 0) tma_store_wait_read();  // the tile must stay intact until the bulk store has read it
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Role-split variant (default): the per-ant work is a ~1,250-instruction dependent fp32 chain, so the kernel is
+// latency-bound, not DRAM- or issue-bound (ncu: 52 % issue utilisation at 30 resident warps per SM).  Splitting each
+// ant over TWO threads of different warps halves the chain and the registers per thread:
+//   core warps 0-4  (one thread per ant): root row -> ant_core -> obs[0:14]; after the box barrier the goal terms
+//   dof  warps 5-9  (one thread per ant): dof/actions rows -> unscale, clamps, forces, obs[14:38], energy terms;
+//                   warp 5 / warp 6 additionally derive the goal direction of frame t / t-1 while the core warps
+//                   are busy, which takes the box phase off the critical path.
+// CTA = 16 envs x 1 frame = 320 threads, grid = (tiles, T).
+// ------------------------------------------------------------------------------------------------------
+struct SplitSmem {
+  static constexpr int EPT = 16;
+  static constexpr int kObs = EPT * OBS_ENV;
+  static constexpr int kRoot = EPT * ROOT_ENV;
+  static constexpr int kPart = EPT * A * PART_W;
+  static constexpr int kBox = EPT * BOX_W;
+  static constexpr int kFloats = kObs + kRoot + kPart + kBox + 4;
+  static constexpr int kBytes = kFloats * 4;
+};
+
+#ifndef MMB_SPLIT_MIN_CTAS
+#define MMB_SPLIT_MIN_CTAS 4
+#endif
+
+template <int FLAVOR>
+__global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(const __grid_constant__ mmb_ten_ant_params p,
+                                                                                   const int prefetch_dist) {
+  constexpr int EPT = SplitSmem::EPT, NA = EPT * A, NT = 2 * NA;
+  extern __shared__ __align__(128) float smem[];
+  float* obs_s = smem;
+  float* root_s = obs_s + SplitSmem::kObs;
+  float* part_s = root_s + SplitSmem::kRoot;
+  float* box_s = part_s + SplitSmem::kPart;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(box_s + SplitSmem::kBox);
+
+  const int tid = threadIdx.x;
+  const int wid = tid >> 5, lane = tid & 31;
+  const int N = p.num_envs;
+  const int t = blockIdx.y, e0 = blockIdx.x * EPT;
+  const int ne = min(EPT, N - e0);
+  const mmb_ant_consts& c = p.c;
+  const bool dof_role = tid >= NA;       // warp-uniform (NA = 5 warps)
+  const int a = dof_role ? tid - NA : tid;
+  const int el = a / A, k = a - el * A;
+  const int e = e0 + el;
+  const bool active = el < ne;
+  const bool tile_clamped = (p.obs_raw == nullptr);
+  const float clip = p.clip_obs;
+  const float tclip = tile_clamped ? clip : __int_as_float(0x7f800000);
+
+  const float* root_g = p.root + (int64_t)t * p.root_frame_stride + (int64_t)e0 * ROOT_ENV;
+  const bool use_tma = (ne == EPT) && aligned16(root_g);
+  if (use_tma) {
+    if (tid == 0) {
+      mbar_init(mbar, 1);
+      mbar_expect_tx(mbar, EPT * ROOT_ENV * 4);
+      tma_load_1d(root_s, root_g, EPT * ROOT_ENV * 4, mbar);
     }
-    const float* bo = box_s + tid * BOX_W;
-    float quat_dist = bo[4];
-    float total_r = fadd(5.0f, fmul(up, 10.0f));
-    total_r = fadd(total_r, fmul(c.quat_reward_scale, quat_dist));
-    total_r = fadd(total_r, adr);
-    total_r = fadd(total_r, gdr);
-    total_r = fadd(total_r, (float)(2 * n_arrive));
-    total_r = fadd(total_r, (quat_dist > 0.9f && n_arrive == A) ? 100.0f : 0.0f);
-    total_r = fsub(total_r, fmul(c.actions_cost, asq));
-    total_r = fsub(total_r, fmul(c.energy_cost, elec));
-    total_r = fsub(total_r, fmul((float)lim, c.joints_at_limit_cost));
-    if (fallen) total_r = c.death_cost;
-    if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = total_r;
-    if (T == 1) {
-      p.box_before[(int64_t)en * 2] = bo[2];
-      p.box_before[(int64_t)en * 2 + 1] = bo[3];
-      // ten_ant.py:896-901 (progress += 1; reset_idx zeroes progress/reset of flagged envs) + :1296-1299
-      int64_t prog = p.progress_buf[en] + 1;
-      if (p.reset_buf[en] != 0) prog = 0;
-      int64_t rs = fallen ? 1 : 0;
-      if ((float)prog >= (float)((double)c.max_episode_length - 1.0)) rs = 1;
-      p.progress_buf[en] = prog;
-      p.reset_buf[en] = rs;
-      if (p.dones_i64) p.dones_i64[en] = rs;
-      if (p.dones_u8) p.dones_u8[en] = (uint8_t)rs;
-    } else if (p.scratch && T <= 32) {
-      // Horizon-batched launch: ONE data-carrying atomic per (env, frame).  The 64-bit word of env `en` collects
-      // the `fallen` bit of every frame (bits 0..31) and the number of frames that have reported (bits 32..).
-      // The thread that sees T-1 earlier reports holds all T bits in its hand: it runs the progress / reset chain
-      // and writes the carry after the last frame.  No fence, no flag read-back, no second kernel; every unit of
-      // the env has passed its own carry reads by the time the last report arrives.
-      const unsigned long long mine = (1ull << 32) | ((unsigned long long)(fallen ? 1u : 0u) << t);
-      const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + en, mine);
-      if ((unsigned)(old >> 32) == (unsigned)T - 1u) {
-        p.scratch[en] = 0ull;            // self-resetting for the next launch / graph replay
-        int64_t prog = p.progress_buf[en];
-        bool flag = p.reset_buf[en] != 0;
-        chain_bits(p, en, 0, T, (uint32_t)(old | mine), prog, flag);
-        p.progress_buf[en] = prog;
-        p.reset_buf[en] = flag ? 1 : 0;
-        const float* last = p.root + (int64_t)(T - 1) * p.root_frame_stride;
-        // carry of the whole env by this thread: the goal direction once, then ten (xy, goal) pairs
-        const float* b = last + ((int64_t)en * 11 + 10) * 13;
-        const float bx = __ldg(b), by = __ldg(b + 1);
-        float xy[2 * A];
-#pragma unroll
-        for (int kk = 0; kk < A; ++kk) {
-          xy[2 * kk] = __ldg(last + ((int64_t)en * 11 + kk) * 13);
-          xy[2 * kk + 1] = __ldg(last + ((int64_t)en * 11 + kk) * 13 + 1);
-        }
-        float s, cs;
-        box_dir(__ldg(b + 5), __ldg(b + 6), s, cs);
-#pragma unroll
-        for (int kk = 0; kk < A; ++kk) {
-          float gx, gy;
-          goal_of(kk, bx, by, s, cs, gx, gy);
-          *reinterpret_cast<float2*>(p.pos_before + ((int64_t)en * A + kk) * 2) = make_float2(xy[2 * kk], xy[2 * kk + 1]);
-          *reinterpret_cast<float2*>(p.goal_before + ((int64_t)en * A + kk) * 2) = make_float2(gx, gy);
-        }
-        *reinterpret_cast<float2*>(p.box_before + (int64_t)en * 2) = make_float2(bx, by);
-      }
-    } else {  // `fallen` only; ten_ant_post_kernel finishes the flags
-      if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + en] = fallen ? 1 : 0;
-      else p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + en] = fallen ? 1 : 0;
-    }
+  } else {
+    tile_load(root_s, root_g, ne * ROOT_ENV, tid, NT);
   }
 
-  // ---- outputs that are not a verbatim copy of the tile ----
-  if (!tile_clamped) {  // raw tile: clamped outputs need a pass
-    if (p.obs_layout == 0 && p.obs) {
-      tile_store<NT, EPT * OBS_ENV / 4, true>(p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
-    } else if (p.obs_layout == 1 && p.share_obs) {
-      tile_store<NT, EPT * OBS_ENV / 4, true>(p.share_obs + (int64_t)t * p.share_obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
+  if (prefetch_dist > 0 && tid == NA)
+    prefetch_unit<EPT>(p, (int64_t)blockIdx.y * gridDim.x + blockIdx.x + prefetch_dist, (int)gridDim.x);
+
+  if (dof_role) {
+    // ================= dof role =================
+    float raw[16], act[8];
+    float pbq0 = 0.f, pbq1 = 0.f, pbq2 = 0.f, pbq3 = 1.f;
+    const bool cur_box = (wid == 5) && (lane < ne);
+    const bool prev_box = (wid == 6) && (lane < ne) && (t > 0);
+    if (prev_box) {
+      const float* b = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)(e0 + lane) * 11 + 10) * 13;
+      pbq0 = __ldg(b); pbq1 = __ldg(b + 1); pbq2 = __ldg(b + 5); pbq3 = __ldg(b + 6);
+    }
+    if (active) {
+      const float* d = p.dof + (int64_t)t * p.dof_frame_stride + ((int64_t)e * 80 + 8 * k) * 2;
+      const float* ac = p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
+      if (aligned16(d) && aligned16(ac)) {
+        float4 v[4], w0, w1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = ldg4(d + 4 * j);
+        w0 = ldg4(ac);
+        w1 = ldg4(ac + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { raw[4 * j] = v[j].x; raw[4 * j + 1] = v[j].y; raw[4 * j + 2] = v[j].z; raw[4 * j + 3] = v[j].w; }
+        act[0] = w0.x; act[1] = w0.y; act[2] = w0.z; act[3] = w0.w;
+        act[4] = w1.x; act[5] = w1.y; act[6] = w1.z; act[7] = w1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) raw[j] = __ldg(d + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) act[j] = __ldg(ac + j);
+      }
+    }
+    __syncthreads();                     // B1: mbarrier initialised (TMA path) / tile stores visible (fallback path)
+    if (cur_box) {
+      if (use_tma) mbar_wait(mbar, 0);
+      const float* b = root_s + lane * ROOT_ENV + 10 * 13;
+      float sn, cs;
+      box_dir(b[5], b[6], sn, cs);
+      float* bo = box_s + lane * BOX_W;
+      bo[0] = sn; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
+      bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
+      float* tail = obs_s + lane * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
+      tail[0] = clampf(b[0], -tclip, tclip); tail[1] = clampf(b[1], -tclip, tclip);
+      tail[2] = clampf(b[3], -tclip, tclip); tail[3] = clampf(b[4], -tclip, tclip);
+      tail[4] = clampf(b[5], -tclip, tclip); tail[5] = clampf(b[6], -tclip, tclip);
+      tail[6] = 0.0f; tail[7] = 0.0f;
+    } else if (prev_box) {
+      float sn, cs;
+      box_dir(pbq2, pbq3, sn, cs);
+      float* bo = box_s + lane * BOX_W;
+      bo[8] = sn; bo[9] = cs; bo[10] = pbq0; bo[11] = pbq1;
+    }
+    if (active) {
+      float* ob = obs_s + el * OBS_ENV + k * 38;
+      float el8[8];
+      int lim = 0;
+      float asq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float aj = clampf(act[j], -p.clip_actions, p.clip_actions);      // vec_task.py:127
+        const float dp = unscale(raw[2 * j], c.dof_lower[j], c.dof_upper[j]);   // ten_ant.py:1333
+        const float dv = fmul(raw[2 * j + 1], c.dof_vel_scale);                 // ten_ant.py:1347
+        act[j] = aj;
+        ob[14 + j] = clampf(dp, -tclip, tclip);
+        ob[22 + j] = clampf(dv, -tclip, tclip);
+        ob[30 + j] = clampf(aj, -tclip, tclip);
+        el8[j] = fabsf(fmul(aj, dv));        // ten_ant.py:1242
+        lim += (dp > 0.99f) ? 1 : 0;         // ten_ant.py:1243
+        asq = fadd(asq, fmul(aj, aj));
+      }
+      if (p.forces) {  // ten_ant.py:889: actions * joint_gears * power_scale
+        float* f = p.forces + (int64_t)t * p.forces_frame_stride + (int64_t)e * 80 + 8 * k;
+        float fo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fo[j] = fmul(fmul(act[j], c.joint_gears[j]), c.power_scale);
+        if (aligned16(f)) {
+          stg4(f, make_float4(fo[0], fo[1], fo[2], fo[3]));
+          stg4(f + 4, make_float4(fo[4], fo[5], fo[6], fo[7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fo[j];
+        }
+      }
+      float* pt = part_s + a * PART_W;
+      pt[3] = sum8<FLAVOR>(el8);
+      pt[4] = asq;
+      pt[5] = __int_as_float(lim);
+    }
+    __syncthreads();                     // B2: box terms ready
+  } else {
+    // ================= core role =================
+    float pbx = 0.f, pby = 0.f, gbx = 0.f, gby = 0.f;
+    if (active) {
+      if (t == 0) {
+        const float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
+        const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+        pbx = __ldg(pb); pby = __ldg(pb + 1);
+        gbx = __ldg(gb); gby = __ldg(gb + 1);
+      } else {  // carry of step t = ant xy of frame t-1 (ten_ant.py:905-914)
+        const float* rp = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)e * 11 + k) * 13;
+        pbx = __ldg(rp); pby = __ldg(rp + 1);
+      }
+    }
+    __syncthreads();                     // B1
+    if (use_tma) mbar_wait(mbar, 0);
+    float px = 0.f, py = 0.f, pz = 0.f, up_proj = 0.f;
+    if (active) {
+      const float* r = root_s + el * ROOT_ENV + k * 13;
+      const f3 pos = {r[0], r[1], r[2]};
+      const f4 q = {r[3], r[4], r[5], r[6]};
+      const f3 vel = {r[7], r[8], r[9]};
+      const f3 ang = {r[10], r[11], r[12]};
+      AntCore o = ant_core<FLAVOR>(pos, q, vel, ang, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
+      float* ob = obs_s + el * OBS_ENV + k * 38;
+      ob[0] = clampf(pos.x, -tclip, tclip); ob[1] = clampf(pos.y, -tclip, tclip); ob[2] = clampf(pos.z, -tclip, tclip);
+      ob[3] = clampf(o.vel_loc.x, -tclip, tclip); ob[4] = clampf(o.vel_loc.y, -tclip, tclip); ob[5] = clampf(o.vel_loc.z, -tclip, tclip);
+      ob[6] = clampf(o.angvel_loc.x, -tclip, tclip); ob[7] = clampf(o.angvel_loc.y, -tclip, tclip); ob[8] = clampf(o.angvel_loc.z, -tclip, tclip);
+      ob[9] = clampf(o.yaw, -tclip, tclip); ob[10] = clampf(o.roll, -tclip, tclip); ob[11] = clampf(o.angle_to_target, -tclip, tclip);
+      ob[12] = clampf(o.up_proj, -tclip, tclip); ob[13] = clampf(o.heading_proj, -tclip, tclip);
+      px = pos.x; py = pos.y; pz = pos.z; up_proj = o.up_proj;
+    }
+    __syncthreads();                     // B2: box terms ready
+    if (active) {
+      const float* bo = box_s + el * BOX_W;
+      float gx, gy;
+      goal_of(k, bo[2], bo[3], bo[0], bo[1], gx, gy);
+      if (t > 0) goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
+      // ten_ant.py:1073-1081 for ant k
+      float d_now = l2_dist2(px, py, gx, gy);
+      float push = (d_now < 1.5f) ? 0.0f : 1.0f;
+      float ant_dist = fsub(l2_dist2(pbx, pby, gbx, gby), d_now);
+      float adr = fmul(fmul(c.ant_dist_reward_scale, ant_dist), push);
+      float bty = (k & 1) ? goal_offset(k) : -goal_offset(k);
+      float gdb = l2_dist2(0.0f, bty, gbx, gby);
+      float gd = l2_dist2(0.0f, bty, gx, gy);
+      bool arrive = gd < 0.5f;
+      float gdr = fmul(c.goal_dist_reward_scale, fsub(gdb, gd));
+      float up = (up_proj > 0.93f) ? fadd(0.0f, c.up_weight) : 0.0f;  // ten_ant.py:1187
+      bool fallen = pz < c.termination_height;
+      float* pt = part_s + a * PART_W;
+      pt[0] = adr; pt[1] = gdr; pt[2] = up;
+      pt[6] = __int_as_float((arrive ? 1 : 0) | (fallen ? 2 : 0));
+      if (p.num_frames == 1) {  // carry out (ten_ant.py:905-925); T > 1: written once per env by the chain executor
+        float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
+        float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+        pb[0] = px; pb[1] = py; gb[0] = gx; gb[1] = gy;
+      }
     }
   }
-  if (p.obs_layout == 1 && p.obs) {  // multi_vec_task.py:105-116: per agent cat(own 38, tail 8) -> [N][10][46]
-    float* g = p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * 460;
-    const int n2 = ne * 230;  // float2 granules: 46 and 38 are even, so a pair never straddles a boundary
-    const bool al8 = (reinterpret_cast<uintptr_t>(g) & 7u) == 0;
-    for (int i = tid; i < n2; i += NT) {
-      int er = i / 230, r2 = i - er * 230;
-      int a = r2 / 23, c2 = r2 - a * 23;
-      int src = er * OBS_ENV + (c2 < 19 ? a * 38 + 2 * c2 : 380 + 2 * (c2 - 19));
-      float2 v = *reinterpret_cast<const float2*>(obs_s + src);
-      if (!tile_clamped) { v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip); }
-      if (al8) *reinterpret_cast<float2*>(g + 2 * i) = v;
-      else { g[2 * i] = v.x; g[2 * i + 1] = v.y; }
+  fence_async_smem();                    // obs tile writes -> visible to the TMA store engine
+  __syncthreads();                       // B3
+
+  // ---- obs tile out ----
+  const int n = ne * OBS_ENV;
+  float* obs_dst = nullptr;
+  if (tile_clamped) obs_dst = (p.obs_layout == 0) ? p.obs : p.share_obs;
+  else obs_dst = p.obs_raw;
+  const int64_t dst_stride = tile_clamped ? ((p.obs_layout == 0) ? p.obs_frame_stride : p.share_obs_frame_stride)
+                                          : p.obs_raw_frame_stride;
+  bool tma_stored = false;
+  if (obs_dst) {
+    float* g = obs_dst + (int64_t)t * dst_stride + (int64_t)e0 * OBS_ENV;
+    if (aligned16(g)) {
+      if (tid == 0) tma_store_1d(g, obs_s, (uint32_t)n * 4u);
+      tma_stored = true;
+    } else {
+      tile_store<NT, EPT * OBS_ENV / 4, false>(g, obs_s, n, tid, clip);
     }
   }
-  if (tma_stored && tid == 0) tma_store_wait_read();  // the tile must stay intact until the bulk store has read it
+  // the finish runs in the first dof warp: warp 0 has the bulk store to issue and to wait for
+  if (tid >= NA && tid - NA < ne) finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W);
+  extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
+  if (tma_stored && tid == 0) tma_store_wait_read();
+}
+
+template <int FLAVOR>
+int32_t launch_ten_ant_split(const mmb_ten_ant_params& p, cudaStream_t st) {
+  auto kern = ten_ant_split_kernel<FLAVOR>;
+  static bool attr_done[MMB_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= MMB_MAX_DEVICES) return MMB_EUNSUPPORTED;
+  if (!attr_done[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitSmem::kBytes) != cudaSuccess) return MMB_ECUDA;
+    attr_done[dev] = true;
+  }
+  const unsigned tiles = (unsigned)((p.num_envs + SplitSmem::EPT - 1) / SplitSmem::EPT);
+  const int prefetch_dist = prefetch_distance();
+  {
+    LaunchScope ls(K_TEN_ANT, st);
+    kern<<<dim3(tiles, (unsigned)p.num_frames), 2 * SplitSmem::EPT * A, SplitSmem::kBytes, st>>>(p, prefetch_dist);
+  }
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
 // Fallback for callers that pass no ticket scratch: chain (threads < N) + carry (threads < 10 N) as one kernel.
@@ -509,7 +814,7 @@ int32_t launch_ten_ant(const mmb_ten_ant_params& p, cudaStream_t st) {
   if (units > 0x7fffffffLL) return MMB_EUNSUPPORTED;
   {
     LaunchScope ls(K_TEN_ANT, st);
-    kern<<<(unsigned)units, EPT * A, TenAntSmem<EPT>::kBytes, st>>>(p);
+    kern<<<(unsigned)units, EPT * A, TenAntSmem<EPT>::kBytes, st>>>(p, prefetch_distance());
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
@@ -532,8 +837,12 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
   cudaStream_t st = (cudaStream_t)stream;
   // tile size: 16 envs (160 threads, 6 CTAs/SM) by default; MMB_TEN_ANT_EPT=32 selects the 32-env tile (tuning knob)
   static const int ept = [] { const char* v = getenv("MMB_TEN_ANT_EPT"); return v ? ((atoi(v) == 32) ? 32 : 16) : MMB_TEN_ANT_EPT; }();
+  // kernel variant: "split" (two threads per ant, default) or "mono" (one thread per ant; MMB_TEN_ANT_VARIANT=mono)
+  static const bool split = [] { const char* v = getenv("MMB_TEN_ANT_VARIANT"); return !(v && v[0] == 'm'); }();
   int32_t rc;
-  if (ept == 16)
+  if (split)
+    rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant_split<FLAVOR_CUDA>(p, st) : launch_ten_ant_split<FLAVOR_CPU>(p, st);
+  else if (ept == 16)
     rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, 16>(p, st) : launch_ten_ant<FLAVOR_CPU, 16>(p, st);
   else
     rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant<FLAVOR_CUDA, 32>(p, st) : launch_ten_ant<FLAVOR_CPU, 32>(p, st);
