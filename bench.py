@@ -202,10 +202,10 @@ def run_ours(args, rank, world, local_rank):
     side_done = [None] * SETS   # event: the side-stream tail of the last rollout that used set s has finished
 
     def rollout(i, join=True):
-        """One rollout on frame/storage set i % SETS.  Main stream: step kernel -> GAE scan.  Side stream: the reset
-        lists of the T steps, then [statistics all-reduce] + normalisation.  With join=False the side work is left
-        running so that the NEXT rollouts' step kernels (other storage sets) overlap it; a set is reused only after
-        its previous tail has finished (side_done)."""
+        """One rollout on frame/storage set i % SETS.  Main stream: the step kernel (the task-state chain orders
+        consecutive rollouts).  Side streams: the reset lists of the T steps; the GAE scan -> [statistics exchange] ->
+        normalisation.  With join=False the side work is left running so that the NEXT rollouts' step kernels (other
+        storage sets) overlap it; a set is reused only after its previous tails have finished (side_done)."""
         s = i % SETS
         st, fr = storages[s], dev_frames[s]
         main = torch.cuda.current_stream()
@@ -216,9 +216,9 @@ def run_ours(args, rank, world, local_rank):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
-        st.compute_returns_scan(last_values, GAMMA, LAM)
         side2.wait_stream(main)
         with torch.cuda.stream(side2):
+            st.compute_returns_scan(last_values, GAMMA, LAM)
             st.normalize_advantages()
             side2.wait_stream(side)
             if not join:
@@ -319,6 +319,35 @@ def run_ours(args, rank, world, local_rank):
     prof = L.profile_collect()
     eager_ms_per_step = pe0.elapsed_time(pe1) / KP
 
+    # ---- the dominant kernel alone, launched back to back over the same rotating inputs (a CUDA graph of SETS
+    # launches, replayed): its sustained duration without the event-pair and launch gaps of the eager pass -------------
+    def step_only(i):
+        s_ = i % SETS
+        task.replay(dev_frames[s_], dev_frames[s_]["actions"], storages[s_].obs_slots[1:], storages[s_].rewards.view(T, N),
+                    storages[s_].dones.view(T, N), None, forces[s_])
+    sustained_ms, RK = None, 0
+    if not args.no_graph:
+        try:
+            for i in range(SETS):
+                step_only(i)
+            torch.cuda.synchronize()
+            gk = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gk):
+                for i in range(SETS):
+                    step_only(i)
+            gk.replay()
+            RK = max(4, min(K // SETS, 100))
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            k0.record()
+            for _ in range(RK):
+                gk.replay()
+            k1.record()
+            torch.cuda.synchronize()
+            sustained_ms = k0.elapsed_time(k1) / (RK * SETS)
+        except Exception as ex:  # pragma: no cover
+            print("kernel-only graph failed: %r" % (ex,), file=sys.stderr)
+
     # ---- end-to-end through the reference-facing API with host buffers -----------------------------
     K2 = max(2, min(K, 20))
     # frames AND actions live in pinned host memory; the provider uploads step t+1's inputs on a copy stream while
@@ -373,7 +402,9 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     k_ms, k_n = prof.get("ten_ant", (0.0, 0))
     per_launch_bytes = BYTES_PER_ENV_STEP_KERNEL * T * N
-    achieved = per_launch_bytes / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+    eager_launch_ms = k_ms / max(k_n, 1)
+    launch_ms = sustained_ms if sustained_ms else eager_launch_ms
+    achieved = per_launch_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms else None
     shares = {k: round(v[0] / max(1e-9, sum(x[0] for x in prof.values())), 4) for k, v in prof.items()}
     cpu = None
     if args.cpu_rollouts > 0:
@@ -397,8 +428,11 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "ten_ant_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": k_ms / max(k_n, 1),
-                     "launches_timed": k_n, "kernel_time_shares": shares},
+                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": launch_ms,
+                     "timing": ("CUDA events around %d back-to-back launches of the kernel alone (graph of %d launches over the "
+                                "rotating sets, replayed)" % (RK * SETS, SETS)) if sustained_ms else "event pair per launch, eager pass",
+                     "avg_launch_ms_eager_event_pairs": eager_launch_ms,
+                     "launches_timed": (RK * SETS) if sustained_ms else k_n, "kernel_time_shares_eager": shares},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(t_host0, t_host1),
     }

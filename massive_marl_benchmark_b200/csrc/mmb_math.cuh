@@ -193,6 +193,46 @@ __device__ __forceinline__ AntCore ant_core(f3 p, f4 q, f3 v, f3 w, f4 inv_start
   return o;
 }
 
+// ant_core without the roll angle, and the roll angle on its own (recomputes tq = q * inv_start_rot, 28 flops), so
+// that two threads of different warps can share one ant: identical operations in identical order, identical bits.
+struct AntCoreNoRoll {
+  f3 vel_loc, angvel_loc;
+  float yaw, angle_to_target, up_proj, heading_proj;
+};
+template <int FLAVOR>
+__device__ __forceinline__ AntCoreNoRoll ant_core_no_roll(f3 p, f4 q, f3 v, f3 w, f4 inv_start_rot) {
+  AntCoreNoRoll o;
+  f3 tt = {fsub(0.0f, p.x), fsub(0.0f, p.y), 0.0f};
+  float nrm = fsqrt(fadd(fmul(tt.x, tt.x), fmul(tt.y, tt.y)));
+  if (FLAVOR == FLAVOR_CPU) nrm = fsqrt(__fmaf_rn(tt.y, tt.y, fmul(tt.x, tt.x)));
+  nrm = nrm < 1e-9f ? 1e-9f : nrm;
+  const float dirx = fdiv(tt.x, nrm), diry = fdiv(tt.y, nrm);
+  f4 tq = quat_mul(q, inv_start_rot);
+  const float s = fsub(fmul(2.0f, fmul(tq.w, tq.w)), 1.0f);
+  o.up_proj = fadd(s, fmul(fmul(tq.z, tq.z), 2.0f));
+  const float hx = fadd(s, fmul(fmul(tq.x, tq.x), 2.0f));
+  const float hy = fadd(fmul(fmul(tq.z, tq.w), 2.0f), fmul(fmul(tq.y, tq.x), 2.0f));
+  o.heading_proj = fadd(fmul(hx, dirx), fmul(hy, diry));
+  o.vel_loc = quat_rot<true>(tq, v);
+  o.angvel_loc = quat_rot<true>(tq, w);
+  {  // yaw of get_euler_xyz
+    float ww = fmul(tq.w, tq.w), xx = fmul(tq.x, tq.x), yy = fmul(tq.y, tq.y), zz = fmul(tq.z, tq.z);
+    float siny = fmul(2.0f, fadd(fmul(tq.w, tq.z), fmul(tq.x, tq.y)));
+    float cosy = fsub(fsub(fadd(ww, xx), yy), zz);
+    o.yaw = wrap_angle_2pi(atan2f(siny, cosy));
+  }
+  float walk = atan2f(fsub(0.0f, p.z), fsub(0.0f, p.x));
+  o.angle_to_target = fsub(walk, o.yaw);
+  return o;
+}
+__device__ __forceinline__ float ant_roll(f4 q, f4 inv_start_rot) {
+  f4 tq = quat_mul(q, inv_start_rot);
+  float ww = fmul(tq.w, tq.w), xx = fmul(tq.x, tq.x), yy = fmul(tq.y, tq.y), zz = fmul(tq.z, tq.z);
+  float sinr = fmul(2.0f, fadd(fmul(tq.w, tq.x), fmul(tq.y, tq.z)));
+  float cosr = fadd(fsub(fsub(ww, xx), yy), zz);
+  return wrap_angle_2pi(atan2f(sinr, cosr));
+}
+
 // unscale(x, lower, upper) = (2x - upper - lower) / (upper - lower)
 __device__ __forceinline__ float unscale(float x, float lo, float hi) {
   return fdiv(fsub(fsub(fmul(2.0f, x), hi), lo), fsub(hi, lo));

@@ -31,7 +31,7 @@ constexpr int A = 10;
 constexpr int ROOT_ENV = 143;  // 11 rows x 13
 constexpr int OBS_ENV = 388;
 constexpr int BOX_W = 12;
-constexpr int PART_W = 7;  // adr, gdr, up, elec, asq, #joints at limit, arrive/fallen flags (odd stride: conflict-free)
+constexpr int PART_W = 7;  // adr, gdr, up, elec, asq, #joints at limit | arrived << 8, fallen (odd stride: conflict-free)
 
 template <int EPT>
 struct TenAntSmem {
@@ -54,7 +54,7 @@ inline int prefetch_distance() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return 2 * sms;
+    return sms + sms / 2;
   }();
   return dist;
 }
@@ -173,17 +173,15 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
   const mmb_ant_consts& c = p.c;
   const int T = p.num_frames;
   float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
-  int lim = __float_as_int(pt[5]);
-  int fl = __float_as_int(pt[6]);
-  int n_arrive = fl & 1;
-  bool fallen = (fl & 2) != 0;
+  int la = __float_as_int(pt[5]);
+  int lim = la & 0xff, n_arrive = la >> 8;
+  bool fallen = __float_as_int(pt[6]) != 0;
 #pragma unroll
   for (int kk = 1; kk < A; ++kk) {
     const float* qq = pt + kk * PART_W;
     adr = fadd(adr, qq[0]); gdr = fadd(gdr, qq[1]); up = fadd(up, qq[2]); elec = fadd(elec, qq[3]); asq = fadd(asq, qq[4]);
-    lim += __float_as_int(qq[5]);
-    int f2 = __float_as_int(qq[6]);
-    n_arrive += f2 & 1; fallen = fallen || (f2 & 2);
+    int l2 = __float_as_int(qq[5]);
+    lim += l2 & 0xff; n_arrive += l2 >> 8; fallen = fallen || (__float_as_int(qq[6]) != 0);
   }
   float quat_dist = bo[4];
   float total_r = fadd(5.0f, fmul(up, 10.0f));
@@ -489,8 +487,8 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
     bool fallen = pos.z < c.termination_height;
     float* pt = part_s + (el * A + k) * PART_W;
     pt[0] = adr; pt[1] = gdr; pt[2] = up; pt[3] = elec; pt[4] = asq;
-    pt[5] = __int_as_float(lim);
-    pt[6] = __int_as_float((arrive ? 1 : 0) | (fallen ? 2 : 0));
+    pt[5] = __int_as_float(lim | (arrive ? 0x100 : 0));
+    pt[6] = __int_as_float(fallen ? 1 : 0);
 
     if (T == 1) {  // carry out (ten_ant.py:905-925); T > 1: written once per env by the chain executor below
       float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
@@ -594,6 +592,11 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     // ================= dof role =================
     float raw[16], act[8];
     float pbq0 = 0.f, pbq1 = 0.f, pbq2 = 0.f, pbq3 = 1.f;
+    float gbx = 0.f, gby = 0.f;
+    if (active && t == 0) {
+      const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+      gbx = __ldg(gb); gby = __ldg(gb + 1);
+    }
     const bool cur_box = (wid == 5) && (lane < ne);
     const bool prev_box = (wid == 6) && (lane < ne) && (t > 0);
     if (prev_box) {
@@ -640,23 +643,27 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       float* bo = box_s + lane * BOX_W;
       bo[8] = sn; bo[9] = cs; bo[10] = pbq0; bo[11] = pbq1;
     }
+    int lim = 0;
     if (active) {
-      float* ob = obs_s + el * OBS_ENV + k * 38;
+      float* ob = obs_s + el * OBS_ENV + k * 38;   // 152-byte rows: 8-byte aligned, so pairs go out as STS.64 (conflict-free)
       float el8[8];
-      int lim = 0;
       float asq = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float aj = clampf(act[j], -p.clip_actions, p.clip_actions);      // vec_task.py:127
-        const float dp = unscale(raw[2 * j], c.dof_lower[j], c.dof_upper[j]);   // ten_ant.py:1333
-        const float dv = fmul(raw[2 * j + 1], c.dof_vel_scale);                 // ten_ant.py:1347
-        act[j] = aj;
-        ob[14 + j] = clampf(dp, -tclip, tclip);
-        ob[22 + j] = clampf(dv, -tclip, tclip);
-        ob[30 + j] = clampf(aj, -tclip, tclip);
-        el8[j] = fabsf(fmul(aj, dv));        // ten_ant.py:1242
-        lim += (dp > 0.99f) ? 1 : 0;         // ten_ant.py:1243
-        asq = fadd(asq, fmul(aj, aj));
+      for (int j = 0; j < 8; j += 2) {
+        float dp[2], dv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float aj = clampf(act[j + h], -p.clip_actions, p.clip_actions);            // vec_task.py:127
+          dp[h] = unscale(raw[2 * (j + h)], c.dof_lower[j + h], c.dof_upper[j + h]);       // ten_ant.py:1333
+          dv[h] = fmul(raw[2 * (j + h) + 1], c.dof_vel_scale);                             // ten_ant.py:1347
+          act[j + h] = aj;
+          el8[j + h] = fabsf(fmul(aj, dv[h]));   // ten_ant.py:1242
+          lim += (dp[h] > 0.99f) ? 1 : 0;        // ten_ant.py:1243
+          asq = fadd(asq, fmul(aj, aj));
+        }
+        *reinterpret_cast<float2*>(ob + 14 + j) = make_float2(clampf(dp[0], -tclip, tclip), clampf(dp[1], -tclip, tclip));
+        *reinterpret_cast<float2*>(ob + 22 + j) = make_float2(clampf(dv[0], -tclip, tclip), clampf(dv[1], -tclip, tclip));
+        *reinterpret_cast<float2*>(ob + 30 + j) = make_float2(clampf(act[j], -tclip, tclip), clampf(act[j + 1], -tclip, tclip));
       }
       if (p.forces) {  // ten_ant.py:889: actions * joint_gears * power_scale
         float* f = p.forces + (int64_t)t * p.forces_frame_stride + (int64_t)e * 80 + 8 * k;
@@ -674,9 +681,25 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       float* pt = part_s + a * PART_W;
       pt[3] = sum8<FLAVOR>(el8);
       pt[4] = asq;
-      pt[5] = __int_as_float(lim);
+      // the roll angle of this ant (the core thread computes everything else of ant_core)
+      if (use_tma && !cur_box) mbar_wait(mbar, 0);
+      const float* r = root_s + el * ROOT_ENV + k * 13;
+      ob[10] = clampf(ant_roll(f4{r[3], r[4], r[5], r[6]}, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]}),
+                      -tclip, tclip);
     }
     __syncthreads();                     // B2: box terms ready
+    if (active) {  // goal-distance reward term and the arrival flag (ten_ant.py:1073-1081); the core thread has the ant terms
+      const float* bo = box_s + el * BOX_W;
+      float gx, gy;
+      goal_of(k, bo[2], bo[3], bo[0], bo[1], gx, gy);
+      if (t > 0) goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
+      const float bty = (k & 1) ? goal_offset(k) : -goal_offset(k);
+      const float gdb = l2_dist2(0.0f, bty, gbx, gby);
+      const float gd = l2_dist2(0.0f, bty, gx, gy);
+      float* pt = part_s + a * PART_W;
+      pt[1] = fmul(c.goal_dist_reward_scale, fsub(gdb, gd));
+      pt[5] = __int_as_float(lim | ((gd < 0.5f) ? 0x100 : 0));
+    }
   } else {
     // ================= core role =================
     float pbx = 0.f, pby = 0.f, gbx = 0.f, gby = 0.f;
@@ -700,13 +723,16 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       const f4 q = {r[3], r[4], r[5], r[6]};
       const f3 vel = {r[7], r[8], r[9]};
       const f3 ang = {r[10], r[11], r[12]};
-      AntCore o = ant_core<FLAVOR>(pos, q, vel, ang, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
-      float* ob = obs_s + el * OBS_ENV + k * 38;
-      ob[0] = clampf(pos.x, -tclip, tclip); ob[1] = clampf(pos.y, -tclip, tclip); ob[2] = clampf(pos.z, -tclip, tclip);
-      ob[3] = clampf(o.vel_loc.x, -tclip, tclip); ob[4] = clampf(o.vel_loc.y, -tclip, tclip); ob[5] = clampf(o.vel_loc.z, -tclip, tclip);
-      ob[6] = clampf(o.angvel_loc.x, -tclip, tclip); ob[7] = clampf(o.angvel_loc.y, -tclip, tclip); ob[8] = clampf(o.angvel_loc.z, -tclip, tclip);
-      ob[9] = clampf(o.yaw, -tclip, tclip); ob[10] = clampf(o.roll, -tclip, tclip); ob[11] = clampf(o.angle_to_target, -tclip, tclip);
-      ob[12] = clampf(o.up_proj, -tclip, tclip); ob[13] = clampf(o.heading_proj, -tclip, tclip);
+      AntCoreNoRoll o = ant_core_no_roll<FLAVOR>(pos, q, vel, ang, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
+      float* ob = obs_s + el * OBS_ENV + k * 38;   // pairs as STS.64 (rows are 8-byte aligned); ob[10] (roll) comes from the dof thread
+      auto cl = [&](float x) { return clampf(x, -tclip, tclip); };
+      *reinterpret_cast<float2*>(ob + 0) = make_float2(cl(pos.x), cl(pos.y));
+      *reinterpret_cast<float2*>(ob + 2) = make_float2(cl(pos.z), cl(o.vel_loc.x));
+      *reinterpret_cast<float2*>(ob + 4) = make_float2(cl(o.vel_loc.y), cl(o.vel_loc.z));
+      *reinterpret_cast<float2*>(ob + 6) = make_float2(cl(o.angvel_loc.x), cl(o.angvel_loc.y));
+      *reinterpret_cast<float2*>(ob + 8) = make_float2(cl(o.angvel_loc.z), cl(o.yaw));
+      ob[11] = cl(o.angle_to_target);
+      *reinterpret_cast<float2*>(ob + 12) = make_float2(cl(o.up_proj), cl(o.heading_proj));
       px = pos.x; py = pos.y; pz = pos.z; up_proj = o.up_proj;
     }
     __syncthreads();                     // B2: box terms ready
@@ -720,16 +746,11 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       float push = (d_now < 1.5f) ? 0.0f : 1.0f;
       float ant_dist = fsub(l2_dist2(pbx, pby, gbx, gby), d_now);
       float adr = fmul(fmul(c.ant_dist_reward_scale, ant_dist), push);
-      float bty = (k & 1) ? goal_offset(k) : -goal_offset(k);
-      float gdb = l2_dist2(0.0f, bty, gbx, gby);
-      float gd = l2_dist2(0.0f, bty, gx, gy);
-      bool arrive = gd < 0.5f;
-      float gdr = fmul(c.goal_dist_reward_scale, fsub(gdb, gd));
       float up = (up_proj > 0.93f) ? fadd(0.0f, c.up_weight) : 0.0f;  // ten_ant.py:1187
       bool fallen = pz < c.termination_height;
       float* pt = part_s + a * PART_W;
-      pt[0] = adr; pt[1] = gdr; pt[2] = up;
-      pt[6] = __int_as_float((arrive ? 1 : 0) | (fallen ? 2 : 0));
+      pt[0] = adr; pt[2] = up;
+      pt[6] = __int_as_float(fallen ? 1 : 0);
       if (p.num_frames == 1) {  // carry out (ten_ant.py:905-925); T > 1: written once per env by the chain executor
         float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
         float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
