@@ -196,8 +196,10 @@ def run_ours(args, rank, world, local_rank):
     last_values = torch.randn(N, 1, device=dev)
     reset_out = [None]
     launches_per_rollout = [0]
-    side = torch.cuda.Stream()       # reset-index lists of the T steps
-    side2 = torch.cuda.Stream()      # statistics exchange wait + normalisation
+    # high priority: the short tail kernels must get SM slots as soon as their rollout's step kernel has finished, even
+    # though the next step kernel (overlap_prev) is already filling the GPU
+    side = torch.cuda.Stream(priority=-1)       # reset-index lists of the T steps
+    side2 = torch.cuda.Stream(priority=-1)      # GAE scan, statistics exchange wait + normalisation
 
     side_done = [None] * SETS   # event: the side-stream tail of the last rollout that used set s has finished
 
@@ -212,7 +214,9 @@ def run_ours(args, rank, world, local_rank):
         if side_done[s] is not None:
             main.wait_event(side_done[s])
         # observation after step t lands in obs slot t+1; reward/done of step t in slot t (no add_transitions pass)
-        task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), None, forces[s])
+        # consecutive rollouts use different frame / storage sets, so the step kernel may overlap the previous one's tail
+        task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), None, forces[s],
+                    overlap_prev=not args.no_overlap)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
@@ -324,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
     def step_only(i):
         s_ = i % SETS
         task.replay(dev_frames[s_], dev_frames[s_]["actions"], storages[s_].obs_slots[1:], storages[s_].rewards.view(T, N),
-                    storages[s_].dones.view(T, N), None, forces[s_])
+                    storages[s_].dones.view(T, N), None, forces[s_], overlap_prev=not args.no_overlap)
     sustained_ms, RK = None, 0
     if not args.no_graph:
         try:
@@ -448,6 +452,7 @@ def main():
     ap.add_argument("--cpu-rollouts", type=int, default=8)
     ap.add_argument("--stats-exchange", default="p2p", choices=["p2p", "nccl", "none"],
                     help="multi-GPU advantage statistics: NVLink peer-memory mailboxes (default) or NCCL all-reduce")
+    ap.add_argument("--no-overlap", action="store_true", help="ordinary stream order between consecutive step kernels (no PDL)")
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

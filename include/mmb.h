@@ -128,6 +128,14 @@ typedef struct {
    * T <= 32) the progress/reset chain and the carry are resolved inside the main kernel by the thread that delivers
    * the last frame of an env; without it (NULL) a second small kernel does the same work. */
   uint64_t* scratch;
+  /* != 0: programmatic dependent launch.  The kernel may start while the PRECEDING kernel in the stream is still
+   * draining (its tail overlaps this kernel's head); it orders itself behind that kernel only where it touches the
+   * task state (carry, progress_buf, reset_buf, scratch).  The caller asserts that every other tensor of this call -
+   * frames, actions, all outputs - is neither written nor read by the preceding kernel in the stream (true when
+   * consecutive rollouts alternate between frame / storage sets; false when the frames were just produced by a
+   * simulation kernel).  0 = ordinary stream order. */
+  int32_t overlap_prev;
+  int32_t _reserved;
   mmb_ant_consts c;
 } mmb_ten_ant_params;
 

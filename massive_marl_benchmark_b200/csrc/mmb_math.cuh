@@ -285,6 +285,11 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
                "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// programmatic dependent launch (PTX griddepcontrol): let the next kernel in the stream start early / wait until the
+// previous kernel in the stream has completed and its writes are visible
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // L2 prefetch of a contiguous global range by the TMA engine (no destination, no registers, no smem): 16 B aligned
 // address, size a multiple of 16 B.
 __device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t bytes) {

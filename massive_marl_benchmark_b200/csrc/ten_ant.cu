@@ -292,10 +292,11 @@ struct UnitIdx {
 // for the unit about a third of a resident wave ahead: by the time that CTA starts, its root / dof / action tiles sit
 // in L2, so its load phase sees L2 latency instead of a loaded-HBM round trip and HBM requests are issued early.
 // Three instructions in one thread, no registers or shared memory held.  Measured: -9 % kernel time.
-template <int EPT>
+template <int EPT, bool FRAMES_REVERSED = false>
 __device__ __forceinline__ void prefetch_unit(const mmb_ten_ant_params& p, int64_t u, int ntiles) {
-  const int64_t t2 = u / ntiles, tile2 = u - t2 * ntiles;
-  if (t2 >= p.num_frames || (tile2 + 1) * EPT > p.num_envs) return;
+  const int64_t y2 = u / ntiles, tile2 = u - y2 * ntiles;
+  if (y2 >= p.num_frames || (tile2 + 1) * EPT > p.num_envs) return;
+  const int64_t t2 = FRAMES_REVERSED ? p.num_frames - 1 - y2 : y2;
   const float* r2 = p.root + t2 * p.root_frame_stride + tile2 * EPT * ROOT_ENV;
   const float* d2 = p.dof + t2 * p.dof_frame_stride + tile2 * EPT * 160;
   const float* a2 = p.actions + t2 * p.actions_frame_stride + tile2 * EPT * 80;
@@ -564,6 +565,8 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const int t = blockIdx.y, e0 = blockIdx.x * EPT;
   const int ne = min(EPT, N - e0);
   const mmb_ant_consts& c = p.c;
+  const bool pdl = p.overlap_prev != 0;
+  if (pdl) griddep_launch_dependents();  // the next kernel in the stream may start filling SM slots as this one drains
   const bool dof_role = tid >= NA;       // warp-uniform (NA = 5 warps)
   const int a = dof_role ? tid - NA : tid;
   const int el = a / A, k = a - el * A;
@@ -593,10 +596,6 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     float raw[16], act[8];
     float pbq0 = 0.f, pbq1 = 0.f, pbq2 = 0.f, pbq3 = 1.f;
     float gbx = 0.f, gby = 0.f;
-    if (active && t == 0) {
-      const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
-      gbx = __ldg(gb); gby = __ldg(gb + 1);
-    }
     const bool cur_box = (wid == 5) && (lane < ne);
     const bool prev_box = (wid == 6) && (lane < ne) && (t > 0);
     if (prev_box) {
@@ -692,7 +691,14 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       const float* bo = box_s + el * BOX_W;
       float gx, gy;
       goal_of(k, bo[2], bo[3], bo[0], bo[1], gx, gy);
-      if (t > 0) goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
+      if (t > 0) {
+        goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
+      } else {  // frame 0: the carry written by the previous launch (with overlap_prev: wait for that kernel first;
+                // everything above was independent of it)
+        if (pdl) griddep_wait();
+        const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+        gbx = __ldcg(gb); gby = __ldcg(gb + 1);
+      }
       const float bty = (k & 1) ? goal_offset(k) : -goal_offset(k);
       const float gdb = l2_dist2(0.0f, bty, gbx, gby);
       const float gd = l2_dist2(0.0f, bty, gx, gy);
@@ -703,16 +709,9 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   } else {
     // ================= core role =================
     float pbx = 0.f, pby = 0.f, gbx = 0.f, gby = 0.f;
-    if (active) {
-      if (t == 0) {
-        const float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
-        const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
-        pbx = __ldg(pb); pby = __ldg(pb + 1);
-        gbx = __ldg(gb); gby = __ldg(gb + 1);
-      } else {  // carry of step t = ant xy of frame t-1 (ten_ant.py:905-914)
-        const float* rp = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)e * 11 + k) * 13;
-        pbx = __ldg(rp); pby = __ldg(rp + 1);
-      }
+    if (active && t > 0) {  // carry of step t = ant xy of frame t-1 (ten_ant.py:905-914); frame 0: loaded after B2
+      const float* rp = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)e * 11 + k) * 13;
+      pbx = __ldg(rp); pby = __ldg(rp + 1);
     }
     __syncthreads();                     // B1
     if (use_tma) mbar_wait(mbar, 0);
@@ -740,7 +739,15 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       const float* bo = box_s + el * BOX_W;
       float gx, gy;
       goal_of(k, bo[2], bo[3], bo[0], bo[1], gx, gy);
-      if (t > 0) goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
+      if (t > 0) {
+        goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
+      } else {
+        if (pdl) griddep_wait();
+        const float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
+        const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
+        pbx = __ldcg(pb); pby = __ldcg(pb + 1);
+        gbx = __ldcg(gb); gby = __ldcg(gb + 1);
+      }
       // ten_ant.py:1073-1081 for ant k
       float d_now = l2_dist2(px, py, gx, gy);
       float push = (d_now < 1.5f) ? 0.0f : 1.0f;
@@ -779,7 +786,10 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     }
   }
   // the finish runs in the first dof warp: warp 0 has the bulk store to issue and to wait for
-  if (tid >= NA && tid - NA < ne) finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W);
+  if (tid >= NA && tid - NA < ne) {
+    if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
+    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W);
+  }
   extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
   if (tma_stored && tid == 0) tma_store_wait_read();
 }
@@ -799,7 +809,17 @@ int32_t launch_ten_ant_split(const mmb_ten_ant_params& p, cudaStream_t st) {
   const int prefetch_dist = prefetch_distance();
   {
     LaunchScope ls(K_TEN_ANT, st);
-    kern<<<dim3(tiles, (unsigned)p.num_frames), 2 * SplitSmem::EPT * A, SplitSmem::kBytes, st>>>(p, prefetch_dist);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles, (unsigned)p.num_frames);
+    cfg.blockDim = dim3(2 * SplitSmem::EPT * A);
+    cfg.dynamicSmemBytes = SplitSmem::kBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.overlap_prev ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, kern, p, prefetch_dist) != cudaSuccess) return MMB_ECUDA;
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

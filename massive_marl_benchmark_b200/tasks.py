@@ -163,8 +163,9 @@ class TenAnt(BaseTask):
         self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
 
     def _launch(self, root, dof, actions, T, strides, obs_raw, obs, share_obs, rewards, dones_i64, dones_u8, forces,
-                out_strides):
+                out_strides, overlap_prev=False):
         p = L.TenAntParams()
+        p.overlap_prev = 1 if overlap_prev else 0
         p.num_envs, p.num_frames, p.flavor, p.obs_layout = self.num_envs, T, self.flavor, self.obs_layout
         p.root, p.dof, p.actions = L.ptr(root), L.ptr(dof), L.ptr(actions)
         p.root_frame_stride, p.dof_frame_stride, p.actions_frame_stride = strides
@@ -216,20 +217,25 @@ class TenAnt(BaseTask):
 
     # -- horizon-batched replay (B200-native addition, SURVEY.md section 7 hard part 1) ---------
     def replay(self, frames, actions, obs_out, rewards_out, dones_u8_out=None, dones_i64_out=None, forces_out=None,
-               share_obs_out=None, obs_raw_out=None):
+               share_obs_out=None, obs_raw_out=None, overlap_prev=False):
         """Process T consecutive frames in ONE launch (+ the 1-byte/env-step progress chain).
 
         frames: dict root [T,11N,13], dof [T,80N,2]; actions [T,N,80]; outputs are [T, ...] planes, e.g.
         slices of a rollout storage so that obs / reward / done land in their slots without a copy pass.
         Reset side effects (index lists, DOF re-randomisation) of the T steps are produced afterwards by
-        `reset_replay` from the emitted done flags."""
+        `reset_replay` from the emitted done flags.
+
+        overlap_prev=True launches with programmatic stream serialisation: the kernel may begin while the previous
+        kernel in the stream (normally the previous rollout's step kernel) drains, and orders itself behind it only
+        for the task state.  Only valid when frames / actions / outputs are not touched by that previous kernel
+        (include/mmb.h, `overlap_prev`)."""
         T = actions.shape[0]
         root, dof = frames["root"], frames["dof"]
         s = lambda x: 0 if x is None else x.stride(0)
         self._launch(root, dof, actions, T, (root.stride(0), dof.stride(0), actions.stride(0)),
                      obs_raw_out, obs_out, share_obs_out, rewards_out, dones_i64_out, dones_u8_out, forces_out,
                      (s(obs_raw_out), s(obs_out), s(share_obs_out), s(rewards_out), s(dones_i64_out), s(dones_u8_out),
-                      s(forces_out)))
+                      s(forces_out)), overlap_prev=overlap_prev)
         self.root_states, self.dof_state = root[T - 1], dof[T - 1]
         self._step_count += T
 
