@@ -401,6 +401,10 @@ typedef struct {
   int32_t stages;       /* set by the library: depth of the shared-memory ring (2..4) */
   void* y;              /* epilogue 0: fp32 [M][y_stride]; else bf16 [Mpad][y_stride] (zero-initialised by the caller) */
   int64_t y_stride;     /* elements */
+  int32_t overlap_prev; /* != 0: programmatic dependent launch - prologue and the first weight tiles are fetched while the
+                         * preceding kernel in the stream drains; only the loads of x wait for it.  The caller asserts
+                         * that w / bias / ln_* are not written by that preceding kernel (true inside a forward chain). */
+  int32_t _reserved;
 } mmb_mlp_layer_params;
 MMB_API int32_t mmb_mlp_layer(const mmb_mlp_layer_params* p, void* stream);
 

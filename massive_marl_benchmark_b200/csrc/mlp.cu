@@ -18,9 +18,17 @@
 // 16-byte chunk index XOR row%8), described to the tensor core by 64-bit matrix descriptors; a single thread
 // issues tcgen05.mma and tcgen05.commit arrives on an mbarrier when the stage may be overwritten.
 //
-// Round-1 state: correct and validated against fp32 torch; tiles are staged by the threads (LDG -> swizzled STS)
-// rather than by TMA and there is no warp specialisation yet - see DESIGN.md section 7.
+// Two kernels share the descriptors and the epilogue:
+//   mlp_layer_ws_kernel (default)  warp-specialised: warp 0 = TMA producer (2-D tensor maps, SWIZZLE_128B boxes, one
+//                                  elected lane), warp 1 = tcgen05.mma issuer + TMEM owner, warps 2-5 = epilogue
+//                                  (TMEM lane quarter = warp % 4).  full/empty mbarrier ring between producer and MMA,
+//                                  tcgen05.commit frees a stage and finally publishes the accumulator.
+//   mlp_layer_kernel (MMB_MLP_VARIANT=legacy)  first version: all threads stage tiles with cp.async, barrier per k-block.
+#include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
 
 #include "../../include/mmb.h"
 #include "mmb_common.cuh"
@@ -33,7 +41,7 @@ constexpr int BM = 128;       // rows per CTA = TMEM lanes = UMMA_M
 constexpr int BK = 64;        // bf16 elements per k-block (128 bytes)
 constexpr int MLP_THREADS = 128;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;   // ring depth = min(8, smem budget / stage bytes): 4 at n_tile 256, 6 at 128, 8 below
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
@@ -78,7 +86,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : expm1f(x); }  // nn.ELU(alpha=1)
+// nn.ELU(alpha=1).  The negative branch is exp(x) - 1 through ex2.approx (2 ulp): its absolute error of ~1e-7 is far below
+// the bf16 rounding of the stored activation (2^-9 relative) even where x -> 0 and the subtraction cancels; expm1f costs
+// ~35 instructions per element and made the epilogue, not the MMA, the longest phase of a tile.
+__device__ __forceinline__ float elu1(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.0f ? x : e - 1.0f;
+}
+__device__ __forceinline__ void load_bias32(const float* __restrict__ b, float* out) {  // 32 consecutive floats, 16 B aligned
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(b) + i);
+    out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+  }
+}
 
 // stage `rows` x 64 bf16 (row-major, leading dimension ld) into the swizzled tile at `tile` with asynchronous 16-byte
 // copies (cp.async / LDGSTS): nothing waits here, the caller commits a group per k-block
@@ -94,6 +116,8 @@ __device__ __forceinline__ void stage_tile_async(uint8_t* tile, const __nv_bfloa
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint32_t taddr, int m, int n0, int n_tile, int cb, int ce);
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_constant__ mmb_mlp_layer_params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -135,11 +159,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_
   }
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % S;
-    cp_async_wait<MAX_STAGES - 2>();   // conservative for S < MAX_STAGES: see the group accounting below
-    if (S < MAX_STAGES) {               // exact wait: all but the newest S-2 groups are complete
-      if (S == 2) cp_async_wait<0>();
-      else if (S == 3) cp_async_wait<1>();
-    }
+    if (S == 2) cp_async_wait<0>();     // all but the newest S-2 groups are complete
+    else if (S == 3) cp_async_wait<1>();
+    else cp_async_wait<2>();
     fence_async_smem();  // LDGSTS / generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
@@ -166,9 +188,30 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_
   tc_fence_after();
 
   // ---- epilogue: thread = one accumulator row (TMEM lane 32*warp + lane) ----
-  const int row = warp * 32 + lane;
-  const int m = m0 + row;
-  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  epilogue_row(p, tmem + ((uint32_t)(warp * 32) << 16), m0 + warp * 32 + lane, n0, n_tile, 0, n_tile);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// warp-specialised, TMA-fed variant
+// ------------------------------------------------------------------------------------------------------
+constexpr int WS_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, half the columns each)
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// epilogue of columns [cb, ce) of one accumulator row held in a TMEM lane (shared by both kernels; the LayerNorm
+// epilogue needs the whole row: cb = 0, ce = n_tile)
+__device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint32_t taddr, int m, int n0, int n_tile, int cb, int ce) {
   const bool row_ok = m < p.M;
   float v[32];
   if (p.epilogue == 2) {  // bias + ELU + LayerNorm over the whole row (n_tile == N): two passes over TMEM
@@ -189,28 +232,45 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_
       tmem_ld32(taddr + c0, v);
       if (row_ok) {
         __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y) + (int64_t)m * p.y_stride + n0 + c0;
+        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const int n = n0 + c0 + i;
           const float x0 = (elu1(v[i] + __ldg(p.bias + n)) - mean) * rstd * __ldg(p.ln_gamma + n) + __ldg(p.ln_beta + n);
           const float x1 = (elu1(v[i + 1] + __ldg(p.bias + n + 1)) - mean) * rstd * __ldg(p.ln_gamma + n + 1) + __ldg(p.ln_beta + n + 1);
-          *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(x0, x1);
+          __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(y)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
       }
     }
   } else {
-    for (int c0 = 0; c0 < n_tile; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
       tmem_ld32(taddr + c0, v);
       if (!row_ok) continue;
       if (p.epilogue == 1) {  // bias + ELU -> bf16
         __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y) + (int64_t)m * p.y_stride + n0 + c0;
+        if (n0 + c0 + 32 <= p.N) {  // full group: 64 contiguous bytes of the row as four 16-byte stores
+          uint32_t pk[16];
+          float bv[32];
+          load_bias32(p.bias + n0 + c0, bv);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int n = n0 + c0 + i;
-          if (n < p.N) {  // columns >= N of the (zero-initialised, K-padded) activation buffer stay zero
-            const float x0 = elu1(v[i] + __ldg(p.bias + n));
-            const float x1 = (n + 1) < p.N ? elu1(v[i + 1] + __ldg(p.bias + n + 1)) : 0.0f;
-            *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(x0, x1);
+          for (int i = 0; i < 32; i += 2) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(elu1(v[i] + bv[i]), elu1(v[i + 1] + bv[i + 1]));
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(y)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int n = n0 + c0 + i;
+            if (n < p.N) {  // columns >= N of the (zero-initialised, K-padded) activation buffer stay zero
+              const float x0 = elu1(v[i] + __ldg(p.bias + n));
+              const float x1 = (n + 1) < p.N ? elu1(v[i + 1] + __ldg(p.bias + n + 1)) : 0.0f;
+              *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(x0, x1);
+            }
           }
         }
       } else {  // bias -> fp32 (last layer)
@@ -223,9 +283,268 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_layer_kernel(const __grid_
       }
     }
   }
+}
+
+// Epilogue of the warp-specialised kernel: columns [cb, ce) of one accumulator row -> the output tile in shared memory
+// (the drained operand ring), laid out as 128-byte-wide sub-tiles in the TMA SWIZZLE_128B pattern (16-byte chunk index
+// XOR row % 8: conflict-free for the row-per-lane stores), from where ONE thread writes the whole tile with 2-D TMA
+// stores.  Row-per-thread global stores were the longest phase of a tile: every 16-byte store instruction of a warp
+// touched 32 different sectors.  Out-of-range rows / columns are clipped by the tensor map; columns in [N, y_stride)
+// of a bf16 activation buffer are written as zeros (they are the K padding of the next layer).
+template <bool F32>
+__device__ __forceinline__ void stage_out32(uint8_t* tile, int row, int c0, const float* x) {
+  // bf16: 64 columns per 128-byte sub-tile row, this group = 4 chunks; fp32: 32 columns per sub-tile row = 8 chunks
+  if (F32) {
+    uint8_t* sub = tile + (c0 >> 5) * (BM * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+  } else {
+    uint8_t* sub = tile + (c0 >> 6) * (BM * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+    const int cbase = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group inside the 128-byte row
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(x[8 * c + 2 * i], x[8 * c + 2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(sub + (((cbase + c) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& p, uint32_t taddr, int row, int n0, int n_tile,
+                                                    int cb, int ce, uint8_t* tile) {
+  float v[32], bv[32], x[32];
+  if (p.epilogue == 2) {  // bias + ELU + LayerNorm over the whole row (n_tile == N): two passes over TMEM
+    float sum = 0.0f, sumsq = 0.0f;
+    for (int c0 = 0; c0 < n_tile; c0 += 32) {
+      tmem_ld32(taddr + c0, v);
+      load_bias32(p.bias + n0 + c0, bv);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = elu1(v[i] + bv[i]);
+        sum += e;
+        sumsq += e * e;
+      }
+    }
+    const float mean = sum / (float)p.N;
+    const float var = fmaxf(sumsq / (float)p.N - mean * mean, 0.0f);  // biased variance, as nn.LayerNorm
+    const float rstd = rsqrtf(var + p.ln_eps);
+    for (int c0 = 0; c0 < n_tile; c0 += 32) {
+      tmem_ld32(taddr + c0, v);
+      load_bias32(p.bias + n0 + c0, bv);
+      float g[32], b[32];
+      load_bias32(p.ln_gamma + n0 + c0, g);
+      load_bias32(p.ln_beta + n0 + c0, b);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = (elu1(v[i] + bv[i]) - mean) * rstd * g[i] + b[i];
+      stage_out32<false>(tile, row, c0, x);
+    }
+    return;
+  }
+  for (int c0 = cb; c0 < ce; c0 += 32) {
+    tmem_ld32(taddr + c0, v);
+    const int n = n0 + c0;
+    if (n + 32 <= p.N) {
+      load_bias32(p.bias + n, bv);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bv[i] = (n + i < p.N) ? __ldg(p.bias + n + i) : 0.0f;
+    }
+    if (p.epilogue == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = (n + i < p.N) ? elu1(v[i] + bv[i]) : 0.0f;
+      stage_out32<false>(tile, row, c0, x);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = v[i] + bv[i];
+      stage_out32<true>(tile, row, c0, x);
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src_smem)),
+               "r"(c0), "r"(c1) : "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __grid_constant__ mmb_mlp_layer_params p,
+                                                                     const __grid_constant__ CUtensorMap map_x,
+                                                                     const __grid_constant__ CUtensorMap map_w,
+                                                                     const __grid_constant__ CUtensorMap map_y) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.n_tile;
+  const int n_tile = p.n_tile;
+  const int b_bytes = n_tile * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_bytes;   // [A tile | B tile], both multiples of 1024 B
+  const int S = p.stages;
+  const int nkb = p.Kpad / BK;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < n_tile) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+  }
+  if (warp == 1) {  // the MMA warp owns the tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (p.overlap_prev) griddep_launch_dependents();  // the next layer may start its prologue and weight loads now
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      auto load_w = [&](int kb, int s) {
+        uint8_t* st = smem + s * stage_bytes;
+        tma_load_2d(st + A_STAGE_BYTES, &map_w, kb * BK, n0, &full_bar[s]);
+        if (n_tile > 256) tma_load_2d(st + A_STAGE_BYTES + 256 * 128, &map_w, kb * BK, n0 + 256, &full_bar[s]);
+      };
+      // the first ring of weight tiles does not depend on the previous kernel: with overlap_prev it is in flight while
+      // that kernel (the previous layer) is still running; the activation tiles wait for it
+      const int pre = nkb < S ? nkb : S;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(&full_bar[kb], (uint32_t)stage_bytes);
+        load_w(kb, kb);
+      }
+      if (p.overlap_prev) griddep_wait();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S, u = kb / S;
+        if (u > 0) {
+          mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
+          mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          load_w(kb, s);
+        }
+        tma_load_2d(smem + s * stage_bytes, &map_x, kb * BK, m0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const int umma_n = n_tile > 256 ? 256 : n_tile;
+      const uint32_t idesc = umma_idesc_bf16(umma_n);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S, u = kb / S;
+        mbar_wait(&full_bar[s], (uint32_t)(u & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes), b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+          const bool acc = (kb > 0) || (j > 0);
+          umma_bf16(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, acc);
+          if (n_tile > 256)
+            umma_bf16(tmem + 256, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + 256 * 128 + j * 32), idesc, acc);
+        }
+        umma_commit(&empty_bar[s]);            // the stage may be refilled once these MMAs have read it
+      }
+      umma_commit(&accum_bar);                 // every MMA of the tile has completed: accumulator ready
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    int cb = 0, ce = n_tile;
+    if (p.epilogue != 2 && n_tile >= 64) {      // split the columns between the two warps of a lane quarter
+      const int mid = ((n_tile / 32 + 1) / 2) * 32;
+      cb = half ? mid : 0;
+      ce = half ? n_tile : mid;
+    } else if (half) {
+      ce = 0;
+    }
+    // by now every MMA has completed, so every operand stage has been consumed: the ring is free to hold the output tile
+    // staged output needs a TMA-addressable destination: 16-byte aligned base and row pitch; bf16 sub-tiles are 64 wide
+    const bool staged = (p.epilogue == 0) ? (((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0)
+                                          : (n_tile % 64 == 0);
+    if (!staged) {
+      if (cb < ce) epilogue_row(p, tmem + ((uint32_t)(q * 32) << 16), m0 + row, n0, n_tile, cb, ce);
+    } else if (cb < ce) {
+      epilogue_row_staged(p, tmem + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, smem);
+    }
+    fence_async_smem();                                     // generic-proxy tile writes -> visible to the TMA store
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
+    if (staged && tid == 64) {
+      const int sub_cols = (p.epilogue == 0) ? 32 : 64;     // columns per 128-byte sub-tile row (fp32 / bf16)
+      for (int j = 0; j * sub_cols < n_tile; ++j) tma_store_2d(&map_y, smem + j * (BM * 128), n0 + j * sub_cols, m0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      tma_store_wait_read();                                // the tile must stay intact until the stores have read it
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+// ---- host: 2-D tensor maps (rows x Kpad bf16, box = box_rows x 64, SWIZZLE_128B) through the driver entry point ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// Encoding a tensor map costs about a microsecond of host time per call and a layer needs two: a small direct-mapped
+// cache keyed by (base, rows, kpad, box_rows) makes the steady-state launch as cheap as a plain one.
+struct MapCacheEntry {
+  const void* base = nullptr;
+  uint64_t rows = 0, kpad = 0;
+  uint32_t box_rows = 0;
+  CUtensorMap map;
+};
+inline bool make_map_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows);
+inline bool make_map_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows) {
+  constexpr int kEntries = 256;
+  static thread_local MapCacheEntry cache[kEntries];
+  const uint64_t h = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull + rows * 31 + kpad * 7 + box_rows;
+  MapCacheEntry& e = cache[(h >> 32) % kEntries];
+  if (e.base != base || e.rows != rows || e.kpad != kpad || e.box_rows != box_rows) {
+    if (!make_map_bf16_2d_uncached(&e.map, base, rows, kpad, box_rows)) return false;
+    e.base = base; e.rows = rows; e.kpad = kpad; e.box_rows = box_rows;
+  }
+  memcpy(map, &e.map, sizeof(CUtensorMap));
+  return true;
+}
+// fp32 output of the last layer: [rows][cols] with row stride ld elements, box = 128 rows x 32 columns (128 bytes)
+inline bool make_map_f32_out(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool make_map_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {kpad, rows};
+  cuuint64_t strides[1] = {kpad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // fp32 [M][K] -> optional LayerNorm (mlp.py:58-59 feature_norm) -> bf16 [Mpad][Kpad], zero padded: the first
@@ -234,6 +553,7 @@ __global__ void __launch_bounds__(256) ln_cast_kernel(const float* __restrict__ 
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       float eps, int use_ln, __nv_bfloat16* __restrict__ y) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  griddep_launch_dependents();  // a programmatically launched first layer may run its prologue / weight loads meanwhile
   if (warp >= Mpad) return;
   __nv_bfloat16* yr = y + (int64_t)warp * Kpad;
   if (warp >= M) {
@@ -278,8 +598,9 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   if (p.epilogue == 2 && (p.n_tile != p.N || p.Npad != p.N || !p.ln_gamma || !p.ln_beta)) return MMB_EINVAL;
   if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w)) & 15u) return MMB_EALIGN;
   const int stage_bytes = A_STAGE_BYTES + p.n_tile * BK * 2;
+  static const bool legacy = [] { const char* v = getenv("MMB_MLP_VARIANT"); return v && v[0] == 'l'; }();
   int stages = SMEM_BUDGET / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > (legacy ? 4 : MAX_STAGES)) stages = legacy ? 4 : MAX_STAGES;
   if (stages < 2) return MMB_EUNSUPPORTED;
   p.stages = stages;
   const int smem = stages * stage_bytes;
@@ -292,9 +613,46 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
       return MMB_ECUDA;
     attr_done[dev] = true;
   }
-  {
+  if (legacy) {
     LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
     mlp_layer_kernel<<<dim3(p.Mpad / BM, p.Npad / p.n_tile), MLP_THREADS, smem, (cudaStream_t)stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+  }
+  static bool ws_attr_done[MMB_MAX_DEVICES] = {};
+  if (!ws_attr_done[dev]) {
+    if (cudaFuncSetAttribute(mlp_layer_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess)
+      return MMB_ECUDA;
+    ws_attr_done[dev] = true;
+  }
+  CUtensorMap map_x, map_w, map_y;
+  if (!make_map_bf16_2d(&map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
+      !make_map_bf16_2d(&map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)(p.n_tile > 256 ? 256 : p.n_tile)))
+    return MMB_ECUDA;
+  if (p.epilogue == 0 && ((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0) {
+    // fp32 [M][N] rows of y_stride floats with a 16-byte aligned base and pitch: staged in the operand ring, TMA-stored
+    if (!make_map_f32_out(&map_y, p.y, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.y_stride)) return MMB_ECUDA;
+    if ((p.n_tile / 32) * BM * 128 > smem) return MMB_EUNSUPPORTED;
+  } else if (p.epilogue == 0) {
+    map_y = map_x;         // e.g. the critic's [M][1] value column: row-per-thread stores; the map is not used
+  } else if (p.n_tile % 64 == 0) {   // bf16 [Mpad][y_stride]: the next layer's operand (columns >= N are written as zeros)
+    if ((reinterpret_cast<uintptr_t>(p.y) & 15u) || (p.y_stride % 8)) return MMB_EALIGN;
+    if (!make_map_bf16_2d(&map_y, p.y, (uint64_t)p.Mpad, (uint64_t)p.y_stride, BM)) return MMB_ECUDA;
+  } else {
+    map_y = map_x;         // narrow bf16 tiles keep the row-per-thread stores; the map is not used
+  }
+  {
+    LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.Mpad / BM, p.Npad / p.n_tile);
+    cfg.blockDim = dim3(WS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.overlap_prev ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, mlp_layer_ws_kernel, p, map_x, map_w, map_y) != cudaSuccess) return MMB_ECUDA;
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

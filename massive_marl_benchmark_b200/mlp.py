@@ -36,14 +36,10 @@ class _Layer:
             if N not in (32, 64, 96, 128, 160, 192, 224, 256, 512):
                 raise L.MmbError("LayerNorm epilogue needs N <= 256 (multiple of 32) or N == 512, got %d" % N)
             self.n_tile, self.Npad, self.epilogue = N, N, 2
-        elif act:
-            self.n_tile = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 32)
-            self.Npad, self.epilogue = _round_up(N, self.n_tile), 1
-        else:
-            self.Npad = _round_up(N, 32)
-            self.n_tile = self.Npad if self.Npad <= 256 else 32
-            self.Npad = _round_up(N, self.n_tile)
-            self.epilogue = 0
+        else:                                    # n_tile is chosen per call from M (see FusedMLP._n_tile)
+            self.Npad = _round_up(N, 256) if N >= 256 else _round_up(N, 32)
+            self.n_tile = None
+            self.epilogue = 1 if act else 0
         w = torch.zeros(self.Npad, self.Kpad, dtype=torch.bfloat16, device=device)
         w[:N, :K] = weight.detach().to(device=device, dtype=torch.bfloat16)
         self.w = w
@@ -117,6 +113,18 @@ class FusedMLP:
             self._bufs[M] = (Mpad, acts)
         return self._bufs[M]
 
+    @staticmethod
+    def _n_tile(l, Mpad, target_ctas=118):
+        """Output-tile width: the widest of 256/128/64/32 that divides Npad and still gives about one CTA per SM
+        (148 SMs; wide tiles reuse the A tile more, but a 64-CTA grid leaves half the GPU idle)."""
+        if l.n_tile is not None:
+            return l.n_tile
+        cands = [t for t in (256, 128, 64, 32) if l.Npad % t == 0]
+        for t in cands:
+            if (Mpad // 128) * (l.Npad // t) >= target_ctas:
+                return t
+        return cands[-1]
+
     def forward(self, x, out=None):
         """x fp32 [M, in_dim] on the device -> fp32 [M, out_dim]."""
         if x.device.type != "cuda":
@@ -134,10 +142,12 @@ class FusedMLP:
             out = torch.empty(M, self.out_dim, dtype=torch.float32, device=self.device)
         for i, l in enumerate(self.layers):
             p = L.MlpLayerParams()
-            p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = M, l.N, l.K, Mpad, l.Kpad, l.Npad, l.n_tile, l.epilogue
+            p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = (M, l.N, l.K, Mpad, l.Kpad, l.Npad,
+                                                                                 self._n_tile(l, Mpad), l.epilogue)
             p.x, p.w, p.bias = L.ptr(acts[i]), L.ptr(l.w), L.ptr(l.bias)
             if l.epilogue == 2:
                 p.ln_gamma, p.ln_beta, p.ln_eps = L.ptr(l.gamma), L.ptr(l.beta), l.eps
+            p.overlap_prev = 1        # the predecessor in the stream is ln_cast / the previous layer: never writes weights
             if i == len(self.layers) - 1:
                 p.y, p.y_stride = L.ptr(out), out.stride(0)
             else:
