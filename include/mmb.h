@@ -60,7 +60,7 @@ MMB_API uint64_t mmb_launch_count(void);
  * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
 enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
        MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
-       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_COUNT };
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_COUNT };
 MMB_API int32_t mmb_profile_enable(int32_t on);
 MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
 
@@ -325,6 +325,27 @@ MMB_API int32_t mmb_adv_normalize_xchg(float* advantages, int64_t n, double* sta
  * out[1] = mean reward.  No host sync. */
 MMB_API int32_t mmb_rollout_statistics(const uint8_t* dones, const float* rewards, int32_t num_steps, int32_t num_envs,
                                float* out2, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Episode bookkeeping of the PPO runner (agents/algorithms/rl/ppo/ppo.py:143-157,198-220): running */
+/* reward sum / episode length per env over T steps, finished episodes appended in the reference's  */
+/* order (step-major, env ascending) to two rings of `window` entries = the deque(maxlen=100) whose */
+/* mean is logged.  No host sync (the reference does .cpu() per step).                             */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_envs, num_steps, window, _pad;
+  const float* rewards;       int64_t rewards_row_stride;    /* [T][N] */
+  const uint8_t* dones_u8;    int64_t dones_u8_row_stride;   /* [T][N], or NULL and ...            */
+  const int64_t* dones_i64;   int64_t dones_i64_row_stride;  /* ... [T][N] int64 (done when > 0)   */
+  float* cur_reward_sum;      /* [N] in/out (cur_reward_sum, ppo.py:116) */
+  float* cur_episode_length;  /* [N] in/out (cur_episode_length, ppo.py:117; float, as the reference) */
+  float* ep_reward;           /* [T][N] scratch: finished-episode reward where the env was done */
+  float* ep_length;           /* [T][N] scratch */
+  float* reward_ring;         /* [window]: entry k of all finished episodes lives in slot k % window */
+  float* length_ring;         /* [window] */
+  uint64_t* state;            /* [2] zero-initialised: [0] episodes finished so far, [1] library scratch */
+} mmb_episode_params;
+MMB_API int32_t mmb_episode_update(const mmb_episode_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Rollout storage: MARL (agents/algorithms/marl/utils/separated_buffer.py:124-168) with the     */

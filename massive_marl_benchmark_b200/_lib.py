@@ -105,6 +105,13 @@ class GaePpoParams(C.Structure):
                 ("stats", c_vp)]
 
 
+class EpisodeParams(C.Structure):
+    _fields_ = [("num_envs", c_i32), ("num_steps", c_i32), ("window", c_i32), ("_pad", c_i32),
+                ("rewards", c_vp), ("rewards_row_stride", c_i64), ("dones_u8", c_vp), ("dones_u8_row_stride", c_i64),
+                ("dones_i64", c_vp), ("dones_i64_row_stride", c_i64), ("cur_reward_sum", c_vp), ("cur_episode_length", c_vp),
+                ("ep_reward", c_vp), ("ep_length", c_vp), ("reward_ring", c_vp), ("length_ring", c_vp), ("state", c_vp)]
+
+
 class GaeMarlParams(C.Structure):
     _fields_ = [
         ("num_envs", c_i32), ("num_steps", c_i32), ("num_agents", c_i32),
@@ -155,6 +162,7 @@ SYMBOLS = {
     "mmb_xchg_close": (c_i32, [c_vp]),
     "mmb_xchg_free": (c_i32, [c_vp]),
     "mmb_rollout_statistics": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "mmb_episode_update": (c_i32, [C.POINTER(EpisodeParams), c_vp]),
     "mmb_gae_marl": (c_i32, [C.POINTER(GaeMarlParams), c_vp]),
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "mmb_shuffle_gather": (c_i32, [C.POINTER(GatherParams), c_vp]),
@@ -205,7 +213,7 @@ def launch_count():
 
 KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
               "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm", "mlp_layer",
-              "ln_cast", "adv_norm_xchg")
+              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring")
 
 
 def profile_enable(on=True):

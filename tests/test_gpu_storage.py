@@ -164,3 +164,33 @@ def test_separated_buffer_matches_reference_golden(cuda_device):
     # Runner.insert mask logic
     masks, active = runner_insert_masks(g["runner_dones"].to(dev))
     assert torch.equal(masks.cpu(), g["runner_masks"]) and torch.equal(active.cpu(), g["runner_active_masks"])
+
+
+@pytest.mark.parametrize("N,T,p_done", [(257, 1, 0.3), (1000, 16, 0.02), (4096, 16, 0.2), (50, 7, 0.0)])
+def test_episode_tracker_matches_runner_bookkeeping(cuda_device, N, T, p_done):
+    """EpisodeTracker == the reference runner's per-step bookkeeping (ppo.py:143-157): running sums bit-exact, the
+    deque contents (order included) bit-exact, logged means within fp32 rounding; several updates so that the rings
+    wrap, with uint8 and int64 done planes."""
+    from massive_marl_benchmark_b200.episodes import EpisodeTracker
+    from oracle.episode_oracle import EpisodeOracle
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(N + T)
+    tr, orc = EpisodeTracker(N, dev), EpisodeOracle(N)
+    for it in range(5):
+        rew = torch.randn(T, N, generator=gen)
+        done = (torch.rand(T, N, generator=gen) < p_done)
+        if it == 2 and p_done > 0:
+            done[T - 1] = True                      # every env finishes at once: more than `window` entries in one row
+        d = done.to(torch.uint8) if it % 2 == 0 else done.to(torch.int64) * 3
+        orc.update(rew, d)
+        tr.update(rew.to(dev).view(T, N, 1), d.to(dev).view(T, N, 1))
+        torch.cuda.synchronize()
+        assert torch.equal(tr.cur_reward_sum.cpu(), orc.cur_reward_sum)
+        assert torch.equal(tr.cur_episode_length.cpu(), orc.cur_episode_length)
+        assert int(tr.finished) == orc.finished
+        rr, ll = tr.deques()
+        assert rr == [float(x) for x in orc.rewbuffer] and ll == [float(x) for x in orc.lenbuffer]
+        if orc.finished:
+            mr, ml = tr.means()
+            er, el = orc.means()
+            assert abs(float(mr) - er) <= 1e-5 * max(1.0, abs(er)) and abs(float(ml) - el) <= 1e-5 * max(1.0, abs(el))

@@ -55,3 +55,34 @@ def test_one_ant_and_ingenuity_class_bit_equal(shim):
         task.step(fr["actions"][t]); orc.step(fr["actions"][t], fr["root"][t])
         assert torch.equal(task.obs_buf, orc.obs_buf) and torch.equal(task.rew_buf, orc.rew_buf)
         assert torch.equal(task.reset_buf, orc.reset_buf) and torch.equal(task.forces, orc.forces)
+
+
+def test_episode_bookkeeping_oracle_against_the_reference_lines():
+    """The episode bookkeeping lives inline in PPO.run() (ppo.py:143-157) and cannot be called on its own, so the
+    reference's own source lines are executed here (textually extracted, dedented) and the oracle must reproduce
+    the deques and running sums exactly."""
+    import statistics
+    import textwrap
+    from collections import deque
+    from oracle.episode_oracle import EpisodeOracle
+    src = open(os.path.join(REF, "agents/algorithms/rl/ppo/ppo.py")).read().split("\n")
+    start = next(i for i, l in enumerate(src) if l.strip() == "cur_reward_sum[:] += rews")
+    end = next(i for i in range(start, len(src)) if src[i].strip() == "cur_episode_length[new_ids] = 0")
+    body = compile(textwrap.dedent("\n".join(src[start:end + 1])), "ppo.py:%d-%d" % (start + 1, end + 1), "exec")
+    N, T = 37, 9
+    gen = torch.Generator().manual_seed(3)
+    ns = {"cur_reward_sum": torch.zeros(N, dtype=torch.float), "cur_episode_length": torch.zeros(N, dtype=torch.float)}
+    rewbuffer, lenbuffer = deque(maxlen=100), deque(maxlen=100)
+    orc = EpisodeOracle(N)
+    for it in range(6):
+        rew = torch.randn(T, N, generator=gen)
+        done = (torch.rand(T, N, generator=gen) < 0.15).to(torch.int64)
+        ns["reward_sum"], ns["episode_length"] = [], []
+        for t in range(T):                                   # the rollout loop of ppo.py:127
+            ns["rews"], ns["dones"] = rew[t], done[t]
+            exec(body, {}, ns)
+        rewbuffer.extend(ns["reward_sum"]); lenbuffer.extend(ns["episode_length"])     # ppo.py:156-157
+        orc.update(rew, done)
+        assert list(orc.rewbuffer) == list(rewbuffer) and list(orc.lenbuffer) == list(lenbuffer)
+        assert torch.equal(orc.cur_reward_sum, ns["cur_reward_sum"]) and torch.equal(orc.cur_episode_length, ns["cur_episode_length"])
+        assert orc.means() == (statistics.mean(rewbuffer), statistics.mean(lenbuffer))
