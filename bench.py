@@ -89,6 +89,19 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for b, n in names.items() if bits & b], "samples": len(inside)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed summary of
+    the `ncu --set full` capture of this same command (profiles/); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_ten_ant_v6_ncu_summary.csv")
+    try:
+        import csv
+        vals = {r[0]: (float(r[1]), r[2]) for r in csv.reader(open(path)) if len(r) == 3 and r[0].startswith("dram__bytes")}
+        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+        return int(sum(v * scale[u] for v, u in vals.values())), os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -337,10 +350,10 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             gk = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gk):
-                for i in range(SETS):
+                for i in range(GROUP):
                     step_only(i)
             gk.replay()
-            RK = max(4, min(K // SETS, 100))
+            RK = max(2, min(K // GROUP, 25))
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             k0.record()
@@ -348,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
                 gk.replay()
             k1.record()
             torch.cuda.synchronize()
-            sustained_ms = k0.elapsed_time(k1) / (RK * SETS)
+            sustained_ms = k0.elapsed_time(k1) / (RK * GROUP)
         except Exception as ex:  # pragma: no cover
             print("kernel-only graph failed: %r" % (ex,), file=sys.stderr)
 
@@ -404,6 +417,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
+    traffic, traffic_src = ncu_traffic_bytes()
     k_ms, k_n = prof.get("ten_ant", (0.0, 0))
     per_launch_bytes = BYTES_PER_ENV_STEP_KERNEL * T * N
     eager_launch_ms = k_ms / max(k_n, 1)
@@ -430,13 +444,14 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": K2, "numa_bound": numa_bound, "api": "VecTaskPython.step + RolloutStorage.add_transitions/compute_returns, pinned host frames"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "ten_ant_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "ten_ant_split_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": launch_ms,
                      "timing": ("CUDA events around %d back-to-back launches of the kernel alone (graph of %d launches over the "
-                                "rotating sets, replayed)" % (RK * SETS, SETS)) if sustained_ms else "event pair per launch, eager pass",
+                                "rotating sets, replayed)" % (RK * GROUP, GROUP)) if sustained_ms else "event pair per launch, eager pass",
                      "avg_launch_ms_eager_event_pairs": eager_launch_ms,
-                     "launches_timed": (RK * SETS) if sustained_ms else k_n, "kernel_time_shares_eager": shares},
+                     "launches_timed": (RK * GROUP) if sustained_ms else k_n, "kernel_time_shares_eager": shares},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(t_host0, t_host1),
     }

@@ -292,11 +292,10 @@ struct UnitIdx {
 // for the unit about a third of a resident wave ahead: by the time that CTA starts, its root / dof / action tiles sit
 // in L2, so its load phase sees L2 latency instead of a loaded-HBM round trip and HBM requests are issued early.
 // Three instructions in one thread, no registers or shared memory held.  Measured: -9 % kernel time.
-template <int EPT, bool FRAMES_REVERSED = false>
+template <int EPT>
 __device__ __forceinline__ void prefetch_unit(const mmb_ten_ant_params& p, int64_t u, int ntiles) {
-  const int64_t y2 = u / ntiles, tile2 = u - y2 * ntiles;
-  if (y2 >= p.num_frames || (tile2 + 1) * EPT > p.num_envs) return;
-  const int64_t t2 = FRAMES_REVERSED ? p.num_frames - 1 - y2 : y2;
+  const int64_t t2 = u / ntiles, tile2 = u - t2 * ntiles;
+  if (t2 >= p.num_frames || (tile2 + 1) * EPT > p.num_envs) return;
   const float* r2 = p.root + t2 * p.root_frame_stride + tile2 * EPT * ROOT_ENV;
   const float* d2 = p.dof + t2 * p.dof_frame_stride + tile2 * EPT * 160;
   const float* a2 = p.actions + t2 * p.actions_frame_stride + tile2 * EPT * 80;
@@ -562,6 +561,8 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const int tid = threadIdx.x;
   const int wid = tid >> 5, lane = tid & 31;
   const int N = p.num_envs;
+  // (launching the frames as 1..T-1, 0 so that the frame-0 units never wait on the previous kernel was measured: the
+  // frame t-1 carry reads of frame 1 then miss L2 and the kernel is 4 % slower)
   const int t = blockIdx.y, e0 = blockIdx.x * EPT;
   const int ne = min(EPT, N - e0);
   const mmb_ant_consts& c = p.c;
