@@ -169,7 +169,8 @@ __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* _
 
 // Per-env finish by one thread: ordered sums over the ten ants' partial terms (ten_ant.py:1173-1301), reward, and the
 // progress / reset bookkeeping (inline for T == 1, data-carrying atomic + last-reporter chain for T <= 32).
-__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo) {
+__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo,
+                                           bool reported = false, unsigned long long reported_old = 0ull) {
   const mmb_ant_consts& c = p.c;
   const int T = p.num_frames;
   float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
@@ -214,7 +215,9 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
     // and writes the carry after the last frame.  No fence, no flag read-back, no second kernel; every unit of
     // the env has passed its own carry reads by the time the last report arrives.
     const unsigned long long mine = (1ull << 32) | ((unsigned long long)(fallen ? 1u : 0u) << t);
-    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + en, mine);
+    // `reported`: the same report was already delivered by this thread right after the box barrier (its round trip
+    // overlapped the goal-term phase instead of extending the life of the CTA); reported_old is what it returned
+    const unsigned long long old = reported ? reported_old : atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + en, mine);
     if ((unsigned)(old >> 32) == (unsigned)T - 1u) {
       p.scratch[en] = 0ull;            // self-resetting for the next launch / graph replay
       int64_t prog = p.progress_buf[en];
@@ -539,7 +542,7 @@ struct SplitSmem {
   static constexpr int kRoot = EPT * ROOT_ENV;
   static constexpr int kPart = EPT * A * PART_W;
   static constexpr int kBox = EPT * BOX_W;
-  static constexpr int kFloats = kObs + kRoot + kPart + kBox + 4;
+  static constexpr int kFloats = kObs + kRoot + kPart + kBox + EPT + 4;   // + per-env `fallen` flags, + mbarrier
   static constexpr int kBytes = kFloats * 4;
 };
 
@@ -549,14 +552,15 @@ struct SplitSmem {
 
 template <int FLAVOR>
 __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(const __grid_constant__ mmb_ten_ant_params p,
-                                                                                   const int prefetch_dist) {
+                                                                                   const int prefetch_dist, const int opts) {
   constexpr int EPT = SplitSmem::EPT, NA = EPT * A, NT = 2 * NA;
   extern __shared__ __align__(128) float smem[];
   float* obs_s = smem;
   float* root_s = obs_s + SplitSmem::kObs;
   float* part_s = root_s + SplitSmem::kRoot;
   float* box_s = part_s + SplitSmem::kPart;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(box_s + SplitSmem::kBox);
+  int* fall_s = reinterpret_cast<int*>(box_s + SplitSmem::kBox);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(fall_s + SplitSmem::EPT);
 
   const int tid = threadIdx.x;
   const int wid = tid >> 5, lane = tid & 31;
@@ -567,6 +571,8 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const int ne = min(EPT, N - e0);
   const mmb_ant_consts& c = p.c;
   const bool pdl = p.overlap_prev != 0;
+  const bool early_report = (opts & 1) && t > 0 && p.scratch != nullptr && p.num_frames <= 32;   // (t > 0 implies num_frames > 1)
+  unsigned long long reported_old = 0ull;
   if (pdl) griddep_launch_dependents();  // the next kernel in the stream may start filling SM slots as this one drains
   const bool dof_role = tid >= NA;       // warp-uniform (NA = 5 warps)
   const int a = dof_role ? tid - NA : tid;
@@ -577,6 +583,7 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const float clip = p.clip_obs;
   const float tclip = tile_clamped ? clip : __int_as_float(0x7f800000);
 
+  if (tid < EPT) fall_s[tid] = 0;        // set by the core threads after B1, read by the reporting lanes after B2
   const float* root_g = p.root + (int64_t)t * p.root_frame_stride + (int64_t)e0 * ROOT_ENV;
   const bool use_tma = (ne == EPT) && aligned16(root_g);
   if (use_tma) {
@@ -624,25 +631,6 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       }
     }
     __syncthreads();                     // B1: mbarrier initialised (TMA path) / tile stores visible (fallback path)
-    if (cur_box) {
-      if (use_tma) mbar_wait(mbar, 0);
-      const float* b = root_s + lane * ROOT_ENV + 10 * 13;
-      float sn, cs;
-      box_dir(b[5], b[6], sn, cs);
-      float* bo = box_s + lane * BOX_W;
-      bo[0] = sn; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
-      bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
-      float* tail = obs_s + lane * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
-      tail[0] = clampf(b[0], -tclip, tclip); tail[1] = clampf(b[1], -tclip, tclip);
-      tail[2] = clampf(b[3], -tclip, tclip); tail[3] = clampf(b[4], -tclip, tclip);
-      tail[4] = clampf(b[5], -tclip, tclip); tail[5] = clampf(b[6], -tclip, tclip);
-      tail[6] = 0.0f; tail[7] = 0.0f;
-    } else if (prev_box) {
-      float sn, cs;
-      box_dir(pbq2, pbq3, sn, cs);
-      float* bo = box_s + lane * BOX_W;
-      bo[8] = sn; bo[9] = cs; bo[10] = pbq0; bo[11] = pbq1;
-    }
     int lim = 0;
     if (active) {
       float* ob = obs_s + el * OBS_ENV + k * 38;   // 152-byte rows: 8-byte aligned, so pairs go out as STS.64 (conflict-free)
@@ -681,13 +669,36 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       float* pt = part_s + a * PART_W;
       pt[3] = sum8<FLAVOR>(el8);
       pt[4] = asq;
-      // the roll angle of this ant (the core thread computes everything else of ant_core)
-      if (use_tma && !cur_box) mbar_wait(mbar, 0);
-      const float* r = root_s + el * ROOT_ENV + k * 13;
-      ob[10] = clampf(ant_roll(f4{r[3], r[4], r[5], r[6]}, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]}),
-                      -tclip, tclip);
+    }
+    // goal directions after this warp's own dof work: the root tile has landed by now, and warps 5 / 6 no longer reach
+    // the box barrier a full box_dir chain later than everybody else
+    if (cur_box) {
+      if (use_tma) mbar_wait(mbar, 0);
+      const float* b = root_s + lane * ROOT_ENV + 10 * 13;
+      float sn, cs;
+      box_dir(b[5], b[6], sn, cs);
+      float* bo = box_s + lane * BOX_W;
+      bo[0] = sn; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
+      bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
+      float* tail = obs_s + lane * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
+      tail[0] = clampf(b[0], -tclip, tclip); tail[1] = clampf(b[1], -tclip, tclip);
+      tail[2] = clampf(b[3], -tclip, tclip); tail[3] = clampf(b[4], -tclip, tclip);
+      tail[4] = clampf(b[5], -tclip, tclip); tail[5] = clampf(b[6], -tclip, tclip);
+      tail[6] = 0.0f; tail[7] = 0.0f;
+    } else if (prev_box) {
+      float sn, cs;
+      box_dir(pbq2, pbq3, sn, cs);
+      float* bo = box_s + lane * BOX_W;
+      bo[8] = sn; bo[9] = cs; bo[10] = pbq0; bo[11] = pbq1;
     }
     __syncthreads();                     // B2: box terms ready
+    if (early_report && a < ne) {
+      // the per-(env, frame) report of the progress / reset chain, issued now so that its L2 round trip overlaps the
+      // goal-term phase; frame 0 reports late (its CTA must have read the carry before the last reporter rewrites it)
+      if (pdl) griddep_wait();           // the chain words are reset by the previous kernel's last reporters
+      reported_old = atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + (e0 + a),
+                               (1ull << 32) | ((unsigned long long)(fall_s[a] ? 1u : 0u) << t));
+    }
     if (active) {  // goal-distance reward term and the arrival flag (ten_ant.py:1073-1081); the core thread has the ant terms
       const float* bo = box_s + el * BOX_W;
       float gx, gy;
@@ -723,17 +734,18 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       const f4 q = {r[3], r[4], r[5], r[6]};
       const f3 vel = {r[7], r[8], r[9]};
       const f3 ang = {r[10], r[11], r[12]};
-      AntCoreNoRoll o = ant_core_no_roll<FLAVOR>(pos, q, vel, ang, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
-      float* ob = obs_s + el * OBS_ENV + k * 38;   // pairs as STS.64 (rows are 8-byte aligned); ob[10] (roll) comes from the dof thread
+      AntCore o = ant_core<FLAVOR>(pos, q, vel, ang, f4{c.inv_start_rot[0], c.inv_start_rot[1], c.inv_start_rot[2], c.inv_start_rot[3]});
+      float* ob = obs_s + el * OBS_ENV + k * 38;   // pairs as STS.64 (rows are 8-byte aligned)
       auto cl = [&](float x) { return clampf(x, -tclip, tclip); };
       *reinterpret_cast<float2*>(ob + 0) = make_float2(cl(pos.x), cl(pos.y));
       *reinterpret_cast<float2*>(ob + 2) = make_float2(cl(pos.z), cl(o.vel_loc.x));
       *reinterpret_cast<float2*>(ob + 4) = make_float2(cl(o.vel_loc.y), cl(o.vel_loc.z));
       *reinterpret_cast<float2*>(ob + 6) = make_float2(cl(o.angvel_loc.x), cl(o.angvel_loc.y));
       *reinterpret_cast<float2*>(ob + 8) = make_float2(cl(o.angvel_loc.z), cl(o.yaw));
-      ob[11] = cl(o.angle_to_target);
+      *reinterpret_cast<float2*>(ob + 10) = make_float2(cl(o.roll), cl(o.angle_to_target));
       *reinterpret_cast<float2*>(ob + 12) = make_float2(cl(o.up_proj), cl(o.heading_proj));
       px = pos.x; py = pos.y; pz = pos.z; up_proj = o.up_proj;
+      if (pz < c.termination_height) fall_s[el] = 1;   // same predicate as the `fallen` flag of the partial terms
     }
     __syncthreads();                     // B2: box terms ready
     if (active) {
@@ -789,7 +801,7 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   // the finish runs in the first dof warp: warp 0 has the bulk store to issue and to wait for
   if (tid >= NA && tid - NA < ne) {
     if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
-    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W);
+    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, early_report, reported_old);
   }
   extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
   if (tma_stored && tid == 0) tma_store_wait_read();
@@ -820,7 +832,9 @@ int32_t launch_ten_ant_split(const mmb_ten_ant_params& p, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.overlap_prev ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, kern, p, prefetch_dist) != cudaSuccess) return MMB_ECUDA;
+    // opts bit 0: deliver the chain report right after the box barrier (MMB_TEN_ANT_EARLY=0 keeps it in the finish)
+    static const int opts = [] { const char* v = getenv("MMB_TEN_ANT_EARLY"); return (v && atoi(v) == 0) ? 0 : 1; }();
+    if (cudaLaunchKernelEx(&cfg, kern, p, prefetch_dist, opts) != cudaSuccess) return MMB_ECUDA;
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
