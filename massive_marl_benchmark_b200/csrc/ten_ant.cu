@@ -536,6 +536,18 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
 //                   are busy, which takes the box phase off the critical path.
 // CTA = 16 envs x 1 frame = 320 threads, grid = (tiles, T).
 // ------------------------------------------------------------------------------------------------------
+// Optional per-CTA phase timeline (build with `make EXTRA=-DMMB_TRACE`, read with tools/probe/ten_ant_timeline.py): %globaltimer
+// stamps of a few CTAs of frame 5.  Compiled out of the normal library.
+#ifdef MMB_TRACE
+}  // namespace
+__device__ unsigned long long g_trace[64 * 16];
+namespace {
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define MMB_TR(i) do { if ((blockIdx.x % 64) == 0 && blockIdx.y == 5) g_trace[(blockIdx.x / 64) * 16 + (i)] = gtime(); } while (0)
+#else
+#define MMB_TR(i) do { } while (0)
+#endif
+
 struct SplitSmem {
   static constexpr int EPT = 16;
   static constexpr int kObs = EPT * OBS_ENV;
@@ -551,9 +563,9 @@ struct SplitSmem {
 #endif
 
 template <int FLAVOR>
-__global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(const __grid_constant__ mmb_ten_ant_params p,
+__global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(const __grid_constant__ mmb_ten_ant_params p,
                                                                                    const int prefetch_dist, const int opts) {
-  constexpr int EPT = SplitSmem::EPT, NA = EPT * A, NT = 2 * NA;
+  constexpr int EPT = SplitSmem::EPT, NA = EPT * A, NT = 2 * NA + 32;   // core warps 0-4, dof warps 5-9, box warp 10
   extern __shared__ __align__(128) float smem[];
   float* obs_s = smem;
   float* root_s = obs_s + SplitSmem::kObs;
@@ -563,6 +575,7 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   uint64_t* mbar = reinterpret_cast<uint64_t*>(fall_s + SplitSmem::EPT);
 
   const int tid = threadIdx.x;
+  if (tid == 0) MMB_TR(0);
   const int wid = tid >> 5, lane = tid & 31;
   const int N = p.num_envs;
   // (launching the frames as 1..T-1, 0 so that the frame-0 units never wait on the previous kernel was measured: the
@@ -574,11 +587,12 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const bool early_report = (opts & 1) && t > 0 && p.scratch != nullptr && p.num_frames <= 32;   // (t > 0 implies num_frames > 1)
   unsigned long long reported_old = 0ull;
   if (pdl) griddep_launch_dependents();  // the next kernel in the stream may start filling SM slots as this one drains
-  const bool dof_role = tid >= NA;       // warp-uniform (NA = 5 warps)
-  const int a = dof_role ? tid - NA : tid;
+  const bool box_role = tid >= 2 * NA;   // warp 10
+  const bool dof_role = tid >= NA && !box_role;   // warp-uniform (NA = 5 warps)
+  const int a = box_role ? 0 : (dof_role ? tid - NA : tid);
   const int el = a / A, k = a - el * A;
   const int e = e0 + el;
-  const bool active = el < ne;
+  const bool active = !box_role && el < ne;
   const bool tile_clamped = (p.obs_raw == nullptr);
   const float clip = p.clip_obs;
   const float tclip = tile_clamped ? clip : __int_as_float(0x7f800000);
@@ -599,17 +613,30 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   if (prefetch_dist > 0 && tid == NA)
     prefetch_unit<EPT>(p, (int64_t)blockIdx.y * gridDim.x + blockIdx.x + prefetch_dist, (int)gridDim.x);
 
-  if (dof_role) {
+  if (box_role) {
+    // ================= box warp: goal direction of frame t (lanes 0-15) and of frame t-1 (lanes 16-31) =================
+    // both chains (division, atanf, sinf, cosf: ~150 dependent instructions) run side by side in one warp that has no
+    // other work, straight from global memory (L2-prefetched), so nobody reaches the box barrier late because of them
+    const int env_l = lane & 15;
+    const bool prev = lane >= 16;
+    const bool on = env_l < ne && !(prev && t == 0);
+    float b0 = 0.f, b1 = 0.f, b5 = 0.f, b6 = 1.f;
+    if (on) {
+      const float* b = p.root + (int64_t)(prev ? t - 1 : t) * p.root_frame_stride + ((int64_t)(e0 + env_l) * 11 + 10) * 13;
+      b0 = __ldg(b); b1 = __ldg(b + 1); b5 = __ldg(b + 5); b6 = __ldg(b + 6);
+    }
+    __syncthreads();                     // B1
+    if (on) {
+      float sn, cs;
+      box_dir(b5, b6, sn, cs);
+      float* bo = box_s + env_l * BOX_W + (prev ? 8 : 0);
+      bo[0] = sn; bo[1] = cs; bo[2] = b0; bo[3] = b1;
+    }
+    __syncthreads();                     // B2
+  } else if (dof_role) {
     // ================= dof role =================
     float raw[16], act[8];
-    float pbq0 = 0.f, pbq1 = 0.f, pbq2 = 0.f, pbq3 = 1.f;
     float gbx = 0.f, gby = 0.f;
-    const bool cur_box = (wid == 5) && (lane < ne);
-    const bool prev_box = (wid == 6) && (lane < ne) && (t > 0);
-    if (prev_box) {
-      const float* b = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)(e0 + lane) * 11 + 10) * 13;
-      pbq0 = __ldg(b); pbq1 = __ldg(b + 1); pbq2 = __ldg(b + 5); pbq3 = __ldg(b + 6);
-    }
     if (active) {
       const float* d = p.dof + (int64_t)t * p.dof_frame_stride + ((int64_t)e * 80 + 8 * k) * 2;
       const float* ac = p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
@@ -631,6 +658,7 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       }
     }
     __syncthreads();                     // B1: mbarrier initialised (TMA path) / tile stores visible (fallback path)
+    if (tid == 200) MMB_TR(1);
     int lim = 0;
     if (active) {
       float* ob = obs_s + el * OBS_ENV + k * 38;   // 152-byte rows: 8-byte aligned, so pairs go out as STS.64 (conflict-free)
@@ -670,28 +698,20 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       pt[3] = sum8<FLAVOR>(el8);
       pt[4] = asq;
     }
-    // goal directions after this warp's own dof work: the root tile has landed by now, and warps 5 / 6 no longer reach
-    // the box barrier a full box_dir chain later than everybody else
-    if (cur_box) {
+    if (tid == 200) MMB_TR(2);
+    if (wid == 7 && lane < ne) {  // box orientation term and the obs tail (warp 7's share of the per-env work)
       if (use_tma) mbar_wait(mbar, 0);
       const float* b = root_s + lane * ROOT_ENV + 10 * 13;
-      float sn, cs;
-      box_dir(b[5], b[6], sn, cs);
-      float* bo = box_s + lane * BOX_W;
-      bo[0] = sn; bo[1] = cs; bo[2] = b[0]; bo[3] = b[1];
-      bo[4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
+      box_s[lane * BOX_W + 4] = box_quat_dist(f4{b[3], b[4], b[5], b[6]}, c.x_goal, c.y_goal, c.z_goal);
       float* tail = obs_s + lane * OBS_ENV + 380;  // ten_ant.py:806-808: box_pos, box_quat, box_targets(=0)
       tail[0] = clampf(b[0], -tclip, tclip); tail[1] = clampf(b[1], -tclip, tclip);
       tail[2] = clampf(b[3], -tclip, tclip); tail[3] = clampf(b[4], -tclip, tclip);
       tail[4] = clampf(b[5], -tclip, tclip); tail[5] = clampf(b[6], -tclip, tclip);
       tail[6] = 0.0f; tail[7] = 0.0f;
-    } else if (prev_box) {
-      float sn, cs;
-      box_dir(pbq2, pbq3, sn, cs);
-      float* bo = box_s + lane * BOX_W;
-      bo[8] = sn; bo[9] = cs; bo[10] = pbq0; bo[11] = pbq1;
     }
+    if (tid == 160) MMB_TR(3);
     __syncthreads();                     // B2: box terms ready
+    if (tid == 160) MMB_TR(4);
     if (early_report && a < ne) {
       // the per-(env, frame) report of the progress / reset chain, issued now so that its L2 round trip overlaps the
       // goal-term phase; frame 0 reports late (its CTA must have read the carry before the last reporter rewrites it)
@@ -727,6 +747,7 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     }
     __syncthreads();                     // B1
     if (use_tma) mbar_wait(mbar, 0);
+    if (tid == 40) MMB_TR(5);
     float px = 0.f, py = 0.f, pz = 0.f, up_proj = 0.f;
     if (active) {
       const float* r = root_s + el * ROOT_ENV + k * 13;
@@ -747,6 +768,7 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       px = pos.x; py = pos.y; pz = pos.z; up_proj = o.up_proj;
       if (pz < c.termination_height) fall_s[el] = 1;   // same predicate as the `fallen` flag of the partial terms
     }
+    if (tid == 40) MMB_TR(6);
     __syncthreads();                     // B2: box terms ready
     if (active) {
       const float* bo = box_s + el * BOX_W;
@@ -778,8 +800,11 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       }
     }
   }
+  if (tid == 40) MMB_TR(7);
+  if (tid == 200) MMB_TR(8);
   fence_async_smem();                    // obs tile writes -> visible to the TMA store engine
   __syncthreads();                       // B3
+  if (tid == 0) MMB_TR(9);
 
   // ---- obs tile out ----
   const int n = ne * OBS_ENV;
@@ -802,9 +827,11 @@ __global__ void __launch_bounds__(320, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   if (tid >= NA && tid - NA < ne) {
     if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
     finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, early_report, reported_old);
+    if (tid == NA) MMB_TR(10);
   }
   extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
   if (tma_stored && tid == 0) tma_store_wait_read();
+  if (tid == 0) MMB_TR(11);
 }
 
 template <int FLAVOR>
@@ -824,7 +851,7 @@ int32_t launch_ten_ant_split(const mmb_ten_ant_params& p, cudaStream_t st) {
     LaunchScope ls(K_TEN_ANT, st);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles, (unsigned)p.num_frames);
-    cfg.blockDim = dim3(2 * SplitSmem::EPT * A);
+    cfg.blockDim = dim3(2 * SplitSmem::EPT * A + 32);
     cfg.dynamicSmemBytes = SplitSmem::kBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -911,6 +938,12 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
   }
   return MMB_OK;
 }
+
+#ifdef MMB_TRACE
+extern "C" __attribute__((visibility("default"))) int32_t mmb_dbg_trace(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, mmb::g_trace, sizeof(unsigned long long) * 64 * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int32_t mmb_ten_ant_load_carry(const float* root, int32_t num_envs, float* pos_before, float* goal_before,
                                           float* box_before, void* stream) {
