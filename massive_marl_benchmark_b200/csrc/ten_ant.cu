@@ -169,8 +169,7 @@ __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* _
 
 // Per-env finish by one thread: ordered sums over the ten ants' partial terms (ten_ant.py:1173-1301), reward, and the
 // progress / reset bookkeeping (inline for T == 1, data-carrying atomic + last-reporter chain for T <= 32).
-__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo,
-                                           bool reported = false, unsigned long long reported_old = 0ull) {
+__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo) {
   const mmb_ant_consts& c = p.c;
   const int T = p.num_frames;
   float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
@@ -209,20 +208,27 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
     if (p.dones_i64) p.dones_i64[en] = rs;
     if (p.dones_u8) p.dones_u8[en] = (uint8_t)rs;
   } else if (p.scratch && T <= 32) {
-    // Horizon-batched launch: ONE data-carrying atomic per (env, frame).  The 64-bit word of env `en` collects
-    // the `fallen` bit of every frame (bits 0..31) and the number of frames that have reported (bits 32..).
-    // The thread that sees T-1 earlier reports holds all T bits in its hand: it runs the progress / reset chain
-    // and writes the carry after the last frame.  No fence, no flag read-back, no second kernel; every unit of
-    // the env has passed its own carry reads by the time the last report arrives.
+    // Horizon-batched launch: ONE data-carrying 64-bit add per (env, frame).  The word of env `en` collects the `fallen`
+    // bit of every frame (bits 0..31) and the number of frames that have reported (bits 32..).  Frames 0..T-2 use a
+    // fire-and-forget reduction: nothing comes back, so their CTAs retire without waiting for an L2 round trip (a
+    // returning atomic took ~2 us under load and was the tail of every CTA).  The unit of the LAST frame - launched last,
+    // so the others have normally reported long before - adds its own report, waits until all T are in, runs the
+    // progress / reset chain and writes the carry.  No fence, no flag read-back, no second kernel; the frame-0 unit
+    // reports after its carry reads, so the carry is not rewritten under it.
     const unsigned long long mine = (1ull << 32) | ((unsigned long long)(fallen ? 1u : 0u) << t);
-    // `reported`: the same report was already delivered by this thread right after the box barrier (its round trip
-    // overlapped the goal-term phase instead of extending the life of the CTA); reported_old is what it returned
-    const unsigned long long old = reported ? reported_old : atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + en, mine);
-    if ((unsigned)(old >> 32) == (unsigned)T - 1u) {
-      p.scratch[en] = 0ull;            // self-resetting for the next launch / graph replay
+    unsigned long long* word = reinterpret_cast<unsigned long long*>(p.scratch) + en;
+    if (t != T - 1) {
+      asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(word), "l"(mine) : "memory");
+    } else {
+      unsigned long long cur = atomicAdd(word, mine) + mine;
+      for (long long t0 = clock64(); (unsigned)(cur >> 32) != (unsigned)T && clock64() - t0 < 2000000000ll;) {
+        __nanosleep(100);                // earlier-launched units still in flight (forward progress as in a look-back scan)
+        cur = *reinterpret_cast<volatile unsigned long long*>(word);
+      }
+      *word = 0ull;                      // self-resetting for the next launch / graph replay
       int64_t prog = p.progress_buf[en];
       bool flag = p.reset_buf[en] != 0;
-      chain_bits(p, en, 0, T, (uint32_t)(old | mine), prog, flag);
+      chain_bits(p, en, 0, T, (uint32_t)cur, prog, flag);
       p.progress_buf[en] = prog;
       p.reset_buf[en] = flag ? 1 : 0;
       const float* last = p.root + (int64_t)(T - 1) * p.root_frame_stride;
@@ -554,7 +560,7 @@ struct SplitSmem {
   static constexpr int kRoot = EPT * ROOT_ENV;
   static constexpr int kPart = EPT * A * PART_W;
   static constexpr int kBox = EPT * BOX_W;
-  static constexpr int kFloats = kObs + kRoot + kPart + kBox + EPT + 4;   // + per-env `fallen` flags, + mbarrier
+  static constexpr int kFloats = kObs + kRoot + kPart + kBox + 4;
   static constexpr int kBytes = kFloats * 4;
 };
 
@@ -564,15 +570,14 @@ struct SplitSmem {
 
 template <int FLAVOR>
 __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(const __grid_constant__ mmb_ten_ant_params p,
-                                                                                   const int prefetch_dist, const int opts) {
+                                                                                   const int prefetch_dist) {
   constexpr int EPT = SplitSmem::EPT, NA = EPT * A, NT = 2 * NA + 32;   // core warps 0-4, dof warps 5-9, box warp 10
   extern __shared__ __align__(128) float smem[];
   float* obs_s = smem;
   float* root_s = obs_s + SplitSmem::kObs;
   float* part_s = root_s + SplitSmem::kRoot;
   float* box_s = part_s + SplitSmem::kPart;
-  int* fall_s = reinterpret_cast<int*>(box_s + SplitSmem::kBox);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(fall_s + SplitSmem::EPT);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(box_s + SplitSmem::kBox);
 
   const int tid = threadIdx.x;
   if (tid == 0) MMB_TR(0);
@@ -584,8 +589,6 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const int ne = min(EPT, N - e0);
   const mmb_ant_consts& c = p.c;
   const bool pdl = p.overlap_prev != 0;
-  const bool early_report = (opts & 1) && t > 0 && p.scratch != nullptr && p.num_frames <= 32;   // (t > 0 implies num_frames > 1)
-  unsigned long long reported_old = 0ull;
   if (pdl) griddep_launch_dependents();  // the next kernel in the stream may start filling SM slots as this one drains
   const bool box_role = tid >= 2 * NA;   // warp 10
   const bool dof_role = tid >= NA && !box_role;   // warp-uniform (NA = 5 warps)
@@ -597,7 +600,6 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const float clip = p.clip_obs;
   const float tclip = tile_clamped ? clip : __int_as_float(0x7f800000);
 
-  if (tid < EPT) fall_s[tid] = 0;        // set by the core threads after B1, read by the reporting lanes after B2
   const float* root_g = p.root + (int64_t)t * p.root_frame_stride + (int64_t)e0 * ROOT_ENV;
   const bool use_tma = (ne == EPT) && aligned16(root_g);
   if (use_tma) {
@@ -712,13 +714,6 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     if (tid == 160) MMB_TR(3);
     __syncthreads();                     // B2: box terms ready
     if (tid == 160) MMB_TR(4);
-    if (early_report && a < ne) {
-      // the per-(env, frame) report of the progress / reset chain, issued now so that its L2 round trip overlaps the
-      // goal-term phase; frame 0 reports late (its CTA must have read the carry before the last reporter rewrites it)
-      if (pdl) griddep_wait();           // the chain words are reset by the previous kernel's last reporters
-      reported_old = atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + (e0 + a),
-                               (1ull << 32) | ((unsigned long long)(fall_s[a] ? 1u : 0u) << t));
-    }
     if (active) {  // goal-distance reward term and the arrival flag (ten_ant.py:1073-1081); the core thread has the ant terms
       const float* bo = box_s + el * BOX_W;
       float gx, gy;
@@ -766,7 +761,6 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       *reinterpret_cast<float2*>(ob + 10) = make_float2(cl(o.roll), cl(o.angle_to_target));
       *reinterpret_cast<float2*>(ob + 12) = make_float2(cl(o.up_proj), cl(o.heading_proj));
       px = pos.x; py = pos.y; pz = pos.z; up_proj = o.up_proj;
-      if (pz < c.termination_height) fall_s[el] = 1;   // same predicate as the `fallen` flag of the partial terms
     }
     if (tid == 40) MMB_TR(6);
     __syncthreads();                     // B2: box terms ready
@@ -826,7 +820,7 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   // the finish runs in the first dof warp: warp 0 has the bulk store to issue and to wait for
   if (tid >= NA && tid - NA < ne) {
     if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
-    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, early_report, reported_old);
+    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W);
     if (tid == NA) MMB_TR(10);
   }
   extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
@@ -859,9 +853,7 @@ int32_t launch_ten_ant_split(const mmb_ten_ant_params& p, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.overlap_prev ? 1 : 0;
-    // opts bit 0: deliver the chain report right after the box barrier (MMB_TEN_ANT_EARLY=0 keeps it in the finish)
-    static const int opts = [] { const char* v = getenv("MMB_TEN_ANT_EARLY"); return (v && atoi(v) == 0) ? 0 : 1; }();
-    if (cudaLaunchKernelEx(&cfg, kern, p, prefetch_dist, opts) != cudaSuccess) return MMB_ECUDA;
+    if (cudaLaunchKernelEx(&cfg, kern, p, prefetch_dist) != cudaSuccess) return MMB_ECUDA;
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

@@ -23,7 +23,7 @@ lib.mmb_dbg_trace(buf)
 names = ["start", "dof:B1", "dof:own work done", "dof:B2 arrive", "dof:B2 passed", "core:root ready", "core:B2 arrive", "core:postB2 done",
          "dof:postB2 done", "B3 passed", "finish done", "exit"]
 for c in range(4):
-    t = list(buf)[c * 16:c * 16 + 15]
-    print("   core post-B2: goals ready %d, d_now %d, ant_dist %d" % (t[12] - t[0], t[13] - t[0], t[14] - t[0]))
+    t = list(buf)[c * 16:c * 16 + 16]
+    print("   finish: enter %d, after griddep_wait %d, sums done %d, reward stored %d" % (t[14] - t[0], t[15] - t[0], t[12] - t[0], t[13] - t[0]))
     t = t[:12]
     print("tile %3d frame 5 (ns): " % (c * 64) + ", ".join("%s %d" % (n, v - t[0]) for n, v in zip(names, t)))
