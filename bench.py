@@ -92,7 +92,7 @@ class ClockSampler(threading.Thread):
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed summary of
     the `ncu --set full` capture of this same command (profiles/); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_ten_ant_v6_ncu_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r01_ten_ant_v7_ncu_summary.csv")
     try:
         import csv
         vals = {r[0]: (float(r[1]), r[2]) for r in csv.reader(open(path)) if len(r) == 3 and r[0].startswith("dram__bytes")}
