@@ -295,6 +295,10 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+// prefetch [p, p + bytes) into L2 when the range is 16-byte aligned and sized (no-op otherwise)
+__device__ __forceinline__ void prefetch_range_l2(const void* p, int64_t bytes) {
+  if (((reinterpret_cast<uintptr_t>(p) | (uintptr_t)bytes) & 15u) == 0 && bytes > 0) tma_prefetch_l2(p, (uint32_t)bytes);
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 }  // namespace mmb

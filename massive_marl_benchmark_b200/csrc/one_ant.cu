@@ -42,6 +42,16 @@ __global__ void __launch_bounds__(EPT) one_ant_kernel(const __grid_constant__ mm
   const mmb_ant_consts& c = p.c;
 
   tile_load(root_s, p.root + (int64_t)t * p.root_frame_stride + (int64_t)e0 * ROOT_ENV, ne * ROOT_ENV, tid, EPT);
+  if (tid == 32) {  // L2 prefetch of the inputs of the unit two CTAs per SM ahead in launch order (see ten_ant.cu)
+    const int64_t u = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + 2 * 148;
+    const int64_t t2 = u / gridDim.x, tile2 = u - t2 * gridDim.x;
+    if (t2 < T && (tile2 + 1) * EPT <= N) {
+      prefetch_range_l2(p.root + t2 * p.root_frame_stride + tile2 * EPT * ROOT_ENV, EPT * ROOT_ENV * 4);
+      prefetch_range_l2(p.dof + t2 * p.dof_frame_stride + tile2 * EPT * 16, EPT * 16 * 4);
+      prefetch_range_l2(p.sensor + t2 * p.sensor_frame_stride + tile2 * EPT * 24, EPT * 24 * 4);
+      prefetch_range_l2(p.actions + t2 * p.actions_frame_stride + tile2 * EPT * 8, EPT * 8 * 4);
+    }
+  }
 
   float raw[16], sens[24], act[8];
   float pbx = 0.f, pby = 0.f, bbx = 0.f, bby = 0.f;

@@ -34,7 +34,8 @@ def timeit(fn, iters=20, warm=3):
 
 out = {"peak_gbs": PEAK, "gae": [], "gather": [], "tasks": []}
 T = 16
-for N in (65536, 262144, 1048576, 4194304):
+ONLY = os.environ.get("SWEEP_ONLY", "")
+for N in (() if ONLY == "tasks" else (65536, 262144, 1048576, 4194304)):
     st = RolloutStorage(N, T, (60,), (0,), (8,), dev, "random")
     st.rewards.normal_(); st.values.normal_(); st.dones.copy_((torch.rand(T, N, 1, device=dev) < 0.01).to(torch.uint8))
     lv = torch.randn(N, 1, device=dev)
