@@ -194,3 +194,68 @@ def test_episode_tracker_matches_runner_bookkeeping(cuda_device, N, T, p_done):
             mr, ml = tr.means()
             er, el = orc.means()
             assert abs(float(mr) - er) <= 1e-5 * max(1.0, abs(er)) and abs(float(ml) - el) <= 1e-5 * max(1.0, abs(el))
+
+
+@pytest.mark.parametrize("use_popart,ptl", [(True, False), (False, False), (True, True)])
+def test_shared_buffer_equals_per_agent_buffers(cuda_device, use_popart, ptl):
+    """SharedReplayBuffer (share_obs once, agent-major planes, one GAE launch for all agents) against A independent
+    SeparatedReplayBuffers (the reference's arrangement, itself pinned to the golden vectors above) fed the same
+    rollout: every tensor an agent reads, the returns, the advantages and the generator tuples are bit-identical."""
+    from massive_marl_benchmark_b200 import spaces
+    from massive_marl_benchmark_b200.separated_buffer import SeparatedReplayBuffer
+    from massive_marl_benchmark_b200.shared_buffer import SharedReplayBuffer
+    dev = cuda_device
+    T, N, A, O, S, ACT = 6, 50, 4, 46, 388, 8
+    cfg = dict(episode_length=T, n_rollout_threads=N, hidden_size=16, recurrent_N=1, gamma=0.96, gae_lambda=0.95,
+               use_gae=True, use_popart=use_popart, use_valuenorm=False, use_proper_time_limits=ptl)
+    ob = spaces.Box(low=-np.inf, high=np.inf, shape=(O,)); sh = spaces.Box(low=-np.inf, high=np.inf, shape=(S,))
+    ac = spaces.Box(low=-np.ones(ACT), high=np.ones(ACT))
+    gen = torch.Generator().manual_seed(11)
+
+    class Norm:
+        def __init__(self, m, v):
+            self.m, self.v = torch.tensor([m], device=dev), torch.tensor([v], device=dev)
+
+        def running_mean_var(self):
+            return self.m, self.v
+
+    norms = [Norm(0.1 * i, 1.5 + 0.2 * i) for i in range(A)] if use_popart else None
+    shared = SharedReplayBuffer(cfg, A, ob, sh, ac, dev)
+    per = [SeparatedReplayBuffer(cfg, ob, sh, ac, dev) for _ in range(A)]
+    rs = torch.zeros(N, 1, 16, device=dev)
+    for t in range(T):
+        share = torch.randn(N, S, generator=gen).to(dev)
+        obs = torch.randn(N, A, O, generator=gen).to(dev); act = torch.randn(N, A, ACT, generator=gen).to(dev)
+        logp = torch.randn(N, A, ACT, generator=gen).to(dev); val = torch.randn(N, A, 1, generator=gen).to(dev)
+        rew = torch.randn(N, A, 1, generator=gen).to(dev)
+        masks = (torch.rand(N, 1, 1, generator=gen) > 0.1).float().expand(N, A, 1).contiguous().to(dev)
+        bad = (torch.rand(N, A, 1, generator=gen) > 0.05).float().to(dev)
+        active = (torch.rand(N, A, 1, generator=gen) > 0.1).float().to(dev)
+        shared.insert(share, obs, act, logp, val, rew, masks, bad, active)
+        for i in range(A):
+            per[i].insert(share, obs[:, i], rs, rs, act[:, i], logp[:, i], val[:, i], rew[:, i], masks[:, i], bad[:, i], active[:, i])
+    assert shared.step == 0
+    nv = torch.randn(N, A, 1, generator=gen).to(dev)
+    shared.compute_returns(nv, norms)
+    adv_all = shared.normalized_advantages(1e-5)
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(2))
+    for i in range(A):
+        per[i].compute_returns(nv[:, i].contiguous(), norms[i] if norms else None)
+        view = shared.agent(i)
+        for name in ("share_obs", "obs", "value_preds", "returns", "masks", "bad_masks", "active_masks", "actions",
+                     "action_log_probs", "rewards", "raw_advantages"):
+            assert torch.equal(getattr(view, name), getattr(per[i], name)), (i, name)
+        adv_i = per[i].normalized_advantages(1e-5)
+        assert torch.equal(adv_all[i], adv_i)
+        view.permutation_override = per[i].permutation_override = perm
+        for ta, tb in zip(view.feed_forward_generator(adv_all[i], num_mini_batch=2), per[i].feed_forward_generator(adv_i, num_mini_batch=2)):
+            assert len(ta) == len(tb) == 13
+            for x, y in zip(ta, tb):
+                assert (x is None and y is None) or torch.equal(x, y)
+    # the view can also run the per-agent path by itself (what an unmodified trainer does) and stays consistent
+    v0 = shared.agent(0)
+    v0.compute_returns(nv[:, 0].contiguous(), norms[0] if norms else None)
+    assert torch.equal(v0.returns, per[0].returns)
+    shared.after_update()
+    assert torch.equal(shared.share_obs[0], shared.share_obs[-1]) and torch.equal(shared.obs[:, 0], shared.obs[:, -1])
+    assert shared.share_obs.data_ptr() == shared.agent(3).share_obs.data_ptr()       # stored once
