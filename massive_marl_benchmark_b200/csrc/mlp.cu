@@ -203,6 +203,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+// multicast variants for thread-block clusters: the tile lands at the same shared-memory offset, and completes on the
+// mbarrier at the same offset, in every CTA of `cta_mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -387,9 +401,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __gri
   const int nkb = p.Kpad / BK;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < n_tile) tmem_cols <<= 1;
+  // thread-block cluster along M (launch attribute): the CM CTAs of a cluster share one weight tile per k-block - each
+  // loads 1/CM of its rows and multicasts them to all - so the L2 -> SM operand traffic per CTA drops from A + B to
+  // A + B/CM; a stage is free again only when the MMAs of ALL CTAs of the cluster have read it
+  uint32_t cm, crank;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cm));
+  asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(crank));
+  const uint16_t cmask = (uint16_t)((1u << cm) - 1u);
+  const int w_rows = n_tile / (int)cm;     // rows of the weight tile this CTA fetches (host guarantees divisibility by 8)
 
   if (tid == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], cm); }
     mbar_init(&accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -402,6 +424,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
+  if (cm > 1) cluster_sync_all();          // every CTA's barriers are initialised before a peer multicasts into them
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   if (p.overlap_prev) griddep_launch_dependents();  // the next layer may start its prologue and weight loads now
@@ -411,6 +434,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __gri
     if (elect_one()) {
       auto load_w = [&](int kb, int s) {
         uint8_t* st = smem + s * stage_bytes;
+        if (cm > 1) {
+          tma_load_2d_mc(st + A_STAGE_BYTES + (int)crank * w_rows * 128, &map_w, kb * BK, n0 + (int)crank * w_rows, &full_bar[s], cmask);
+          return;
+        }
         tma_load_2d(st + A_STAGE_BYTES, &map_w, kb * BK, n0, &full_bar[s]);
         if (n_tile > 256) tma_load_2d(st + A_STAGE_BYTES + 256 * 128, &map_w, kb * BK, n0 + 256, &full_bar[s]);
       };
@@ -449,7 +476,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __gri
           if (n_tile > 256)
             umma_bf16(tmem + 256, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + 256 * 128 + j * 32), idesc, acc);
         }
-        umma_commit(&empty_bar[s]);            // the stage may be refilled once these MMAs have read it
+        if (cm > 1) umma_commit_mc(&empty_bar[s], cmask);   // ... on every CTA of the cluster: their producers write into this stage too
+        else umma_commit(&empty_bar[s]);       // the stage may be refilled once these MMAs have read it
       }
       umma_commit(&accum_bar);                 // every MMA of the tile has completed: accumulator ready
     }
@@ -487,6 +515,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
+  if (cm > 1) cluster_sync_all();          // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
@@ -624,9 +653,17 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
       return MMB_ECUDA;
     ws_attr_done[dev] = true;
   }
+  // cluster size along M (MMB_MLP_CLUSTER = 2 / 4): the CTAs of a cluster share (multicast) each weight tile.  Off by
+  // default: measured on B200 at M = 4096 it is 5-9 % SLOWER than independent CTAs (18.5 vs 17.6 us for 1024 x 1024),
+  // i.e. the k-loop is not L2-read-bound at these sizes and the cluster launch / sync constraints cost more than the
+  // saved L2 traffic.
+  static const int cluster_pref = [] { const char* v = getenv("MMB_MLP_CLUSTER"); return v ? atoi(v) : 1; }();
+  int cm = 1;
+  for (int c = cluster_pref; c > 1; c >>= 1)
+    if ((p.Mpad / BM) % c == 0 && p.n_tile <= 256 && (p.n_tile / c) % 8 == 0 && p.n_tile % c == 0) { cm = c; break; }
   CUtensorMap map_x, map_w, map_y;
   if (!make_map_bf16_2d(&map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
-      !make_map_bf16_2d(&map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)(p.n_tile > 256 ? 256 : p.n_tile)))
+      !make_map_bf16_2d(&map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)((p.n_tile > 256 ? 256 : p.n_tile) / cm)))
     return MMB_ECUDA;
   if (p.epilogue == 0 && ((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0) {
     // fp32 [M][N] rows of y_stride floats with a 16-byte aligned base and pitch: staged in the operand ring, TMA-stored
@@ -647,12 +684,21 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
     cfg.blockDim = dim3(WS_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cm > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = cm; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (p.overlap_prev) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = p.overlap_prev ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, mlp_layer_ws_kernel, p, map_x, map_w, map_y) != cudaSuccess) return MMB_ECUDA;
+    cfg.numAttrs = na;
+    if (cudaLaunchKernelEx(&cfg, mlp_layer_ws_kernel, p, map_x, map_w, map_y) != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
