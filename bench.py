@@ -148,9 +148,12 @@ def cpu_rollouts(n_rollouts, warmup, n_envs=N_ENVS, horizon=HORIZON, threads=Non
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps, warm = args.steps, max(1, min(args.warmup, 3))
+    # a bounded sample: at most 24 timed rollouts (~0.3 s each on 16 host cores) however large --steps is, so that the arm
+    # finishes within a minute; the per-step figures below are per rollout of the sample
+    steps, warm = max(1, min(args.steps, 24)), max(1, min(args.warmup, 3))
     value, sec, threads = cpu_rollouts(steps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "steps_timed": steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE",
