@@ -103,7 +103,9 @@ typedef struct {
   int32_t num_envs;    /* N */
   int32_t num_frames;  /* T >= 1 */
   int32_t flavor;      /* MMB_FLAVOR_* */
-  int32_t obs_layout;  /* 0: obs rows [N][388];  1: per-agent rows [N][10][46] (+ share_obs) */
+  int32_t obs_layout;  /* 0: obs rows [N][388];  1: per-agent rows [N][10][46] (+ share_obs);  2: agent-major per-agent rows
+                        * obs[a * obs_agent_stride + t * obs_frame_stride + env * 46] (+ share_obs): the planes of a shared
+                        * MARL rollout buffer, written in place */
   /* inputs, Isaac layout */
   const float* root;    int64_t root_frame_stride;    /* [T][11N][13] */
   const float* dof;     int64_t dof_frame_stride;     /* [T][80N][2]  */
@@ -136,6 +138,8 @@ typedef struct {
    * simulation kernel).  0 = ordinary stream order. */
   int32_t overlap_prev;
   int32_t _reserved;
+  /* obs_layout 2 only: element stride between the per-agent planes of `obs` (see obs_layout) */
+  int64_t obs_agent_stride;
   mmb_ant_consts c;
 } mmb_ten_ant_params;
 

@@ -42,7 +42,7 @@ class TenAntParams(C.Structure):
         ("share_obs", c_vp), ("share_obs_frame_stride", c_i64), ("rewards", c_vp), ("rewards_frame_stride", c_i64),
         ("dones_i64", c_vp), ("dones_i64_frame_stride", c_i64), ("dones_u8", c_vp), ("dones_u8_frame_stride", c_i64),
         ("forces", c_vp), ("forces_frame_stride", c_i64), ("scratch", c_vp), ("overlap_prev", c_i32), ("_reserved", c_i32),
-        ("c", AntConsts)]
+        ("obs_agent_stride", c_i64), ("c", AntConsts)]
 
 
 class OneAntParams(C.Structure):

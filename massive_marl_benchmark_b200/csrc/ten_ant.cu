@@ -266,7 +266,7 @@ __device__ __forceinline__ void extra_outputs(const mmb_ten_ant_params& p, int t
   if (!tile_clamped) {  // raw tile: clamped outputs need a pass
     if (p.obs_layout == 0 && p.obs) {
       tile_store<NT, EPT * OBS_ENV / 4, true>(p.obs + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
-    } else if (p.obs_layout == 1 && p.share_obs) {
+    } else if (p.obs_layout >= 1 && p.share_obs) {
       tile_store<NT, EPT * OBS_ENV / 4, true>(p.share_obs + (int64_t)t * p.share_obs_frame_stride + (int64_t)e0 * OBS_ENV, obs_s, n, tid, clip);
     }
   }
@@ -282,6 +282,20 @@ __device__ __forceinline__ void extra_outputs(const mmb_ten_ant_params& p, int t
       if (!tile_clamped) { v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip); }
       if (al8) *reinterpret_cast<float2*>(g + 2 * i) = v;
       else { g[2 * i] = v.x; g[2 * i + 1] = v.y; }
+    }
+  } else if (p.obs_layout == 2 && p.obs) {  // the same rows, agent-major: plane a holds [env][46] (shared MARL buffer slot)
+    const int n2 = ne * 23;  // float2 granules of one agent's rows of this tile
+    for (int a = 0; a < A; ++a) {
+      float* g = p.obs + (int64_t)a * p.obs_agent_stride + (int64_t)t * p.obs_frame_stride + (int64_t)e0 * 46;
+      const bool al8 = (reinterpret_cast<uintptr_t>(g) & 7u) == 0;
+      for (int i = tid; i < n2; i += NT) {
+        int er = i / 23, c2 = i - er * 23;
+        int src = er * OBS_ENV + (c2 < 19 ? a * 38 + 2 * c2 : 380 + 2 * (c2 - 19));
+        float2 v = *reinterpret_cast<const float2*>(obs_s + src);
+        if (!tile_clamped) { v.x = clampf(v.x, -clip, clip); v.y = clampf(v.y, -clip, clip); }
+        if (al8) *reinterpret_cast<float2*>(g + 2 * i) = v;
+        else { g[2 * i] = v.x; g[2 * i + 1] = v.y; }
+      }
     }
   }
 }
@@ -907,7 +921,7 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
     return MMB_EINVAL;
   if (p.num_frames > 65535) return MMB_EUNSUPPORTED;
   if (p.num_frames > 1 && !p.dones_u8 && !p.dones_i64) return MMB_EINVAL;  // the chain needs a [T][N] plane
-  if (p.obs_layout != 0 && p.obs_layout != 1) return MMB_EINVAL;
+  if (p.obs_layout < 0 || p.obs_layout > 2) return MMB_EINVAL;
   if (p.flavor != MMB_FLAVOR_CUDA && p.flavor != MMB_FLAVOR_CPU) return MMB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   // tile size: 16 envs (160 threads, 6 CTAs/SM) by default; MMB_TEN_ANT_EPT=32 selects the 32-env tile (tuning knob)

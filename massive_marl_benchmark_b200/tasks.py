@@ -163,10 +163,12 @@ class TenAnt(BaseTask):
         self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
 
     def _launch(self, root, dof, actions, T, strides, obs_raw, obs, share_obs, rewards, dones_i64, dones_u8, forces,
-                out_strides, overlap_prev=False):
+                out_strides, overlap_prev=False, obs_layout=None, obs_agent_stride=0):
         p = L.TenAntParams()
         p.overlap_prev = 1 if overlap_prev else 0
-        p.num_envs, p.num_frames, p.flavor, p.obs_layout = self.num_envs, T, self.flavor, self.obs_layout
+        p.obs_agent_stride = obs_agent_stride
+        p.num_envs, p.num_frames, p.flavor = self.num_envs, T, self.flavor
+        p.obs_layout = self.obs_layout if obs_layout is None else obs_layout
         p.root, p.dof, p.actions = L.ptr(root), L.ptr(dof), L.ptr(actions)
         p.root_frame_stride, p.dof_frame_stride, p.actions_frame_stride = strides
         p.clip_actions, p.clip_obs = self.clip_actions, self.clip_obs
@@ -217,7 +219,7 @@ class TenAnt(BaseTask):
 
     # -- horizon-batched replay (B200-native addition, SURVEY.md section 7 hard part 1) ---------
     def replay(self, frames, actions, obs_out, rewards_out, dones_u8_out=None, dones_i64_out=None, forces_out=None,
-               share_obs_out=None, obs_raw_out=None, overlap_prev=False):
+               share_obs_out=None, obs_raw_out=None, overlap_prev=False, agent_major_obs_out=None):
         """Process T consecutive frames in ONE launch (+ the 1-byte/env-step progress chain).
 
         frames: dict root [T,11N,13], dof [T,80N,2]; actions [T,N,80]; outputs are [T, ...] planes, e.g.
@@ -228,14 +230,25 @@ class TenAnt(BaseTask):
         overlap_prev=True launches with programmatic stream serialisation: the kernel may begin while the previous
         kernel in the stream (normally the previous rollout's step kernel) drains, and orders itself behind it only
         for the task state.  Only valid when frames / actions / outputs are not touched by that previous kernel
-        (include/mmb.h, `overlap_prev`)."""
+        (include/mmb.h, `overlap_prev`).
+
+        agent_major_obs_out [A, T, N, 46] (instead of obs_out; with share_obs_out [T, N, 388]): the per-agent rows of
+        multi_vec_task.py:105-116 written straight into the agent-major planes of a `SharedReplayBuffer`
+        (`buf.obs[:, 1:]`, `buf.share_obs[1:]`), no insert pass."""
         T = actions.shape[0]
         root, dof = frames["root"], frames["dof"]
         s = lambda x: 0 if x is None else x.stride(0)
+        layout, agent_stride = None, 0
+        if agent_major_obs_out is not None:
+            am = agent_major_obs_out
+            if obs_out is not None or am.dim() != 4 or am.shape[0] != 10 or am.shape[3] != 46 or am.stride(3) != 1 or am.stride(2) != 46:
+                raise ValueError("agent_major_obs_out must be [10, T, N, 46] with contiguous [N, 46] slots (and obs_out None)")
+            layout, agent_stride = 2, am.stride(0)
+            obs_out = am[0]          # [T, N, 46] view of agent 0: base pointer and frame stride
         self._launch(root, dof, actions, T, (root.stride(0), dof.stride(0), actions.stride(0)),
                      obs_raw_out, obs_out, share_obs_out, rewards_out, dones_i64_out, dones_u8_out, forces_out,
                      (s(obs_raw_out), s(obs_out), s(share_obs_out), s(rewards_out), s(dones_i64_out), s(dones_u8_out),
-                      s(forces_out)), overlap_prev=overlap_prev)
+                      s(forces_out)), overlap_prev=overlap_prev, obs_layout=layout, obs_agent_stride=agent_stride)
         self.root_states, self.dof_state = root[T - 1], dof[T - 1]
         self._step_count += T
 

@@ -288,3 +288,35 @@ def test_ten_ant_edge_cases(cuda_device):
     assert L.lib().mmb_ten_ant_step(p, None) == -1
     assert L.lib().mmb_ten_ant_step(None, None) == -1
     assert b"invalid" in L.lib().mmb_strerror(-1)
+
+
+def test_ten_ant_agent_major_layout_equals_per_agent_rows(cuda_device):
+    """obs_layout 2 (agent-major planes of a shared MARL buffer, written in place by the horizon-batched launch) holds
+    exactly the per-agent rows of the MultiVecTask layout (multi_vec_task.py:105-116), and share_obs / rewards / dones
+    are unchanged."""
+    from massive_marl_benchmark_b200 import synthetic
+    dev = cuda_device
+    N, T = 219, 5
+    fr = synthetic.ten_ant_frames(N, T, seed=9, fall_prob=0.02)
+    frd = {k: v.to(dev) for k, v in fr.items()}
+    outs = []
+    for mode in (1, 2):
+        task = _make(N, fr, "cuda", True, dev)
+        task.obs_layout = 1
+        task.clip_actions, task.clip_obs = 1.0, 7.0
+        share = torch.zeros(T, N, 388, device=dev); rew = torch.zeros(T, N, device=dev)
+        d8 = torch.zeros(T, N, device=dev, dtype=torch.uint8)
+        if mode == 1:
+            obs = torch.zeros(T, N, 10, 46, device=dev)
+            task.replay(frd, frd["actions"], obs, rew, d8, None, None, share_obs_out=share)
+            obs = obs.permute(2, 0, 1, 3).contiguous()
+        else:
+            buf = torch.zeros(10, T + 1, N, 46, device=dev)          # as SharedReplayBuffer.obs: slot 0 stays untouched
+            task.replay(frd, frd["actions"], None, rew, d8, None, None, share_obs_out=share, agent_major_obs_out=buf[:, 1:])
+            assert float(buf[:, 0].abs().sum()) == 0.0
+            obs = buf[:, 1:].contiguous()
+        torch.cuda.synchronize()
+        outs.append((obs, share, rew, d8))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    assert float(outs[0][0].abs().sum()) > 0

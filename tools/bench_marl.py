@@ -94,6 +94,58 @@ for name, cls, gen, A, act in (("multi_ingenuity", MultiIngenuity, synthetic.ing
                  "per_agent_buffers_bytes_reference_layout": A * ((T + 1) * N * (S + O + 2 * 512 + 5) + T * N * (2 * act + 2)) * 4}
     del task, env, buf, prov
     torch.cuda.empty_cache()
+# ---- TenAnt MARL, horizon-batched: the step kernel writes the agent-major obs planes, share_obs, reward and done of
+# all T steps straight into the shared buffer (obs_layout 2); the per-agent planes that are replicas (reward, masks) are
+# broadcast copies; then reset lists, GAE for all agents in one launch, per-agent normalisation -------------------------
+fr = synthetic.ten_ant_frames(N, 4 * T, seed=11)
+frd = {k: v.to(dev) for k, v in fr.items()}
+cfg = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1}
+task = TenAnt(cfg, None, None, "cuda", 0, True, True, provider=ReplayProvider({"root": fr["root"], "dof": fr["dof"]}, device=dev))
+task.clip_actions, task.clip_obs = 1.0, 7.0
+A, act = 10, 8
+bcfg = dict(episode_length=T, n_rollout_threads=N, hidden_size=512, recurrent_N=1, gamma=0.96, gae_lambda=0.95,
+            use_gae=True, use_popart=True, use_valuenorm=False, use_proper_time_limits=False)
+bufs = [SharedReplayBuffer(bcfg, A, spaces.Box(low=-np.inf, high=np.inf, shape=(46,)), spaces.Box(low=-np.inf, high=np.inf, shape=(388,)),
+                           spaces.Box(low=-np.ones(act), high=np.ones(act)), dev) for _ in range(2)]
+norms = [Norm(0.3, 2.5) for _ in range(A)]
+rew = [torch.zeros(T, N, device=dev) for _ in range(2)]; d8 = [torch.zeros(T, N, device=dev, dtype=torch.uint8) for _ in range(2)]
+forces = torch.zeros(T, N, 80, device=dev); nv = torch.randn(N, A, 1, device=dev)
+from massive_marl_benchmark_b200.tasks import reset_replay  # noqa: E402
+reset_out = [None]
+
+
+def rollout_batched(r):
+    b = bufs[r % 2]; w = {k: v[(r % 4) * T:(r % 4 + 1) * T] for k, v in frd.items()}
+    task.replay(w, w["actions"], None, rew[r % 2], d8[r % 2], None, forces, share_obs_out=b.share_obs[1:],
+                agent_major_obs_out=b.obs[:, 1:], overlap_prev=True)
+    reset_out[0] = reset_replay(task, d8[r % 2], out=reset_out[0])
+    b.rewards.copy_(rew[r % 2].view(1, T, N, 1).expand(A, T, N, 1))                      # reward_all: the same reward x A
+    b.masks[:, 1:].copy_((1.0 - d8[r % 2].float()).view(1, T, N, 1).expand(A, T, N, 1))  # all agents of an env end together
+    b.actions.copy_(w["actions"].view(T, N, A, act).permute(2, 0, 1, 3))
+    b.compute_returns(nv, norms)
+    adv = b.normalized_advantages(1e-5)
+    b.after_update()
+    return adv
+
+
+for r in range(4):
+    rollout_batched(r)
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for r in range(4):
+        rollout_batched(r)
+g.replay(); torch.cuda.synchronize()
+K = 50
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(K):
+    g.replay()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / (4 * K)
+out["ten_ant_horizon_batched"] = {"envs": N, "agents": A, "horizon": T, "ms_per_rollout": ms, "env_steps_per_s": N * T / ms * 1e3,
+                                  "agent_steps_per_s": N * T * A / ms * 1e3,
+                                  "note": "CUDA graph of 4 rollouts; step kernel with obs_layout 2 writes the shared buffer in place"}
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bench_marl.json", "w"), indent=1)
