@@ -58,38 +58,64 @@ __device__ __forceinline__ int64_t bijection_eval(const Bijection& b, int64_t po
   return (int64_t)x;
 }
 
+// Rows are mapped to lane groups, not elements to threads: with `upr` units (of 16 / 4 / 1 bytes) per row, a warp holds
+// 32 / upr whole rows side by side (lane -> (sub-row, unit) fixed for the whole kernel: no per-element division), the
+// first lane of each group fetches / computes the source row index and shuffles it to its group, four row groups are in
+// flight per warp, and a warp's stores are one contiguous run of the output.  Rows wider than a warp are walked 32 units
+// at a time.
 template <typename V>
 __device__ __forceinline__ void gather_field(const mmb_gather_params& p, const Bijection& bj, const V* __restrict__ src,
-                                             V* __restrict__ dst, int units_per_row) {
-  // element i of the output = (row i / upr, unit i % upr); consecutive threads write consecutive units (coalesced
-  // stores), the loads of four independent elements are in flight per thread
-  const int64_t total = p.batch_size * units_per_row;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                             V* __restrict__ dst, int upr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t B = p.batch_size;
   auto src_index = [&](int64_t row) -> int64_t {
     if (p.index_mode == 0) return __ldg(p.indices + row);
     if (p.index_mode == 1) return bijection_eval(bj, p.batch_start + row);
     return p.batch_start + row;
   };
-  for (; i + 3 * stride < total; i += 4 * stride) {
-    V v[4];
-    int64_t off[4];
+  if (upr <= 32) {
+    const int rpw = 32 / upr;                 // rows per warp pass
+    const int sub = lane / upr, unit = lane - sub * upr;
+    const bool lane_on = sub < rpw;
+    const int leader = sub * upr;
+    constexpr int U = 4;
+    for (int64_t g0 = warp * U; g0 * rpw < B; g0 += nwarps * U) {
+      int64_t srow[U];
+      V v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t e = i + u * stride;
-      const int64_t row = e / units_per_row;
-      const int unit = (int)(e - row * units_per_row);
-      off[u] = src_index(row) * units_per_row + unit;
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = (g0 + u) * rpw + sub;
+        int64_t si = 0;
+        if (lane_on && unit == 0 && row < B) si = src_index(row);
+        srow[u] = __shfl_sync(0xffffffffu, si, lane_on ? leader : 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = (g0 + u) * rpw + sub;
+        if (lane_on && row < B) v[u] = __ldg(src + srow[u] * upr + unit);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = (g0 + u) * rpw + sub;
+        if (lane_on && row < B) dst[row * upr + unit] = v[u];
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(src + off[u]);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) dst[i + u * stride] = v[u];
-  }
-  for (; i < total; i += stride) {
-    const int64_t row = i / units_per_row;
-    const int unit = (int)(i - row * units_per_row);
-    dst[i] = __ldg(src + src_index(row) * units_per_row + unit);
+  } else {
+    for (int64_t row = warp; row < B; row += nwarps) {
+      int64_t si = 0;
+      if (lane == 0) si = src_index(row);
+      si = __shfl_sync(0xffffffffu, si, 0);
+      const V* s = src + si * upr;
+      V* d = dst + row * upr;
+      int u0 = lane;
+      for (; u0 + 96 < upr; u0 += 128) {      // four independent loads in flight
+        V a0 = __ldg(s + u0), a1 = __ldg(s + u0 + 32), a2 = __ldg(s + u0 + 64), a3 = __ldg(s + u0 + 96);
+        d[u0] = a0; d[u0 + 32] = a1; d[u0 + 64] = a2; d[u0 + 96] = a3;
+      }
+      for (; u0 < upr; u0 += 32) d[u0] = __ldg(s + u0);
+    }
   }
 }
 
@@ -136,7 +162,9 @@ extern "C" int32_t mmb_shuffle_gather(const mmb_gather_params* pp, void* stream)
   Bijection bj = make_bijection(p.total, p.seed);
   int max_rb = 0;
   for (int f = 0; f < p.num_fields; ++f) max_rb = p.row_bytes[f] > max_rb ? p.row_bytes[f] : max_rb;
-  int64_t blocks = (p.batch_size * ((max_rb + 15) / 16) + 1023) / 1024;  // ~4 elements per thread for the widest field
+  // one warp pass moves 32 units x 4 row groups of the widest field; 8 warps per block
+  const int64_t units = p.batch_size * ((max_rb + 15) / 16);
+  int64_t blocks = (units + 8 * 128 - 1) / (8 * 128);
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
   {
