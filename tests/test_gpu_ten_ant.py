@@ -320,3 +320,55 @@ def test_ten_ant_agent_major_layout_equals_per_agent_rows(cuda_device):
     for x, y in zip(*outs):
         assert torch.equal(x, y)
     assert float(outs[0][0].abs().sum()) > 0
+
+
+def test_ten_ant_long_horizon_fallback_and_kernel_variants(cuda_device, tmp_path):
+    """(a) T = 40 > 32 frames: the chain / carry fallback kernel path equals T single steps.  (b) The one-thread-per-ant
+    kernel (MMB_TEN_ANT_VARIANT=mono, read once per process, hence a subprocess) produces bit-identical outputs and task
+    state to the default role-split kernel on the same frames."""
+    import os
+    import subprocess
+    import sys
+    from massive_marl_benchmark_b200 import synthetic
+    dev = cuda_device
+    N, T = 77, 40
+    fr = synthetic.ten_ant_frames(N, T, seed=31, fall_prob=0.03)
+    frd = {k: v.to(dev) for k, v in fr.items()}
+    rep = _make(N, fr, "cuda", False, dev)
+    obs = torch.zeros(T, N, 388, device=dev); rew = torch.zeros(T, N, device=dev); d8 = torch.zeros(T, N, device=dev, dtype=torch.uint8)
+    rep.replay(frd, frd["actions"], obs, rew, d8)
+    st = _make(N, fr, "cuda", False, dev)
+    for t in range(T):
+        st.step(frd["actions"][t])
+        assert torch.equal(obs[t], st.obs_buf) and torch.equal(rew[t], st.rew_buf) and torch.equal(d8[t].long(), st.reset_buf)
+    assert torch.equal(rep.progress_buf, st.progress_buf) and torch.equal(rep.pos_before, st.pos_before)
+    assert torch.equal(rep.goal_before, st.goal_before)
+
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from massive_marl_benchmark_b200 import synthetic
+from massive_marl_benchmark_b200.providers import ReplayProvider
+from massive_marl_benchmark_b200.tasks import TenAnt
+dev = torch.device("cuda", 0)
+N, T = 523, 12
+fr = synthetic.ten_ant_frames(N, T, seed=77, fall_prob=0.02)
+frd = {k: v.to(dev) for k, v in fr.items()}
+task = TenAnt({"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1}, None, None, "cuda", 0, True, False,
+              provider=ReplayProvider({"root": fr["root"], "dof": fr["dof"]}, device=dev))
+task.clip_actions, task.clip_obs = 1.0, 5.0
+obs = torch.zeros(T, N, 388, device=dev); rew = torch.zeros(T, N, device=dev); d8 = torch.zeros(T, N, device=dev, dtype=torch.uint8)
+fo = torch.zeros(T, N, 80, device=dev)
+for _ in range(2):
+    task.replay(frd, frd["actions"], obs, rew, d8, None, fo)
+torch.save({"obs": obs.cpu(), "rew": rew.cpu(), "d8": d8.cpu(), "fo": fo.cpu(), "prog": task.progress_buf.cpu(),
+            "pos": task.pos_before.cpu(), "goal": task.goal_before.cpu()}, sys.argv[1])
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    res = {}
+    for variant in ("split", "mono"):
+        out = str(tmp_path / (variant + ".pt"))
+        env = dict(os.environ, MMB_TEN_ANT_VARIANT=variant)
+        subprocess.run([sys.executable, "-c", script, out], check=True, env=env, timeout=300)
+        res[variant] = torch.load(out)
+    for k in res["split"]:
+        assert torch.equal(res["split"][k], res["mono"][k]), k
