@@ -185,7 +185,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     N, T, K, W = N_ENVS, HORIZON, args.steps, max(args.warmup, 3)
     SETS = 4  # rotating frame/storage sets: 4 x ~225 MB of traffic per step >> 126 MB L2
-    GROUP = 4 * SETS  # rollouts captured per CUDA graph (the side-stream tails are joined once per graph)
+    GROUP = int(os.environ.get("MMB_BENCH_GROUP", 8 * SETS))  # rollouts captured per CUDA graph (side-stream tails joined once per graph)
 
     def barrier():
         if world > 1:
