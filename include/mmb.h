@@ -433,10 +433,19 @@ typedef struct {
 } mmb_mlp_layer_params;
 MMB_API int32_t mmb_mlp_layer(const mmb_mlp_layer_params* p, void* stream);
 
+/* The same layer for `count` <= MMB_MAX_GROUP independent problems of identical geometry in ONE launch (grid z = problem):
+ * the per-agent actor / critic networks of the MARL policies (runner.py:205-217 runs 2 x num_agents small forwards per
+ * env step).  `params` is an array of `count` structs; M, N, K, paddings, n_tile, epilogue and y_stride must agree. */
+#define MMB_MAX_GROUP 16
+MMB_API int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t count, void* stream);
+
 /* fp32 [M][K] -> optional LayerNorm over K (mlp.py:58-59 feature_norm) -> bf16 [Mpad][Kpad], zero padded: the
  * A operand of the first layer. */
 MMB_API int32_t mmb_ln_cast(const float* x, int32_t M, int32_t Mpad, int32_t K, int32_t Kpad, const float* gamma,
                             const float* beta, float eps, int32_t use_ln, void* y_bf16, void* stream);
+MMB_API int32_t mmb_ln_cast_group(const float* const* x, int32_t count, int32_t M, int32_t Mpad, int32_t K, int32_t Kpad,
+                                  const float* const* gamma, const float* const* beta, float eps, int32_t use_ln,
+                                  void* const* y_bf16, void* stream);
 
 #ifdef __cplusplus
 }

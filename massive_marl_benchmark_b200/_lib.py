@@ -92,6 +92,7 @@ class RolloutAddParams(C.Structure):
 
 
 MAX_RANKS = 16
+MAX_GROUP = 16
 
 
 class Xchg(C.Structure):
@@ -168,6 +169,9 @@ SYMBOLS = {
     "mmb_shuffle_gather": (c_i32, [C.POINTER(GatherParams), c_vp]),
     "mmb_permutation": (c_i32, [c_i64, c_u64, c_vp, c_vp]),
     "mmb_mlp_layer": (c_i32, [C.POINTER(MlpLayerParams), c_vp]),
+    "mmb_mlp_layer_group": (c_i32, [C.POINTER(MlpLayerParams), c_i32, c_vp]),
+    "mmb_ln_cast_group": (c_i32, [C.POINTER(c_vp), c_i32, c_i32, c_i32, c_i32, c_i32, C.POINTER(c_vp), C.POINTER(c_vp), c_f, c_i32,
+                                  C.POINTER(c_vp), c_vp]),
     "mmb_ln_cast": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f, c_i32, c_vp, c_vp]),
 }
 

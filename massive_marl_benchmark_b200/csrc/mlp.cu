@@ -385,10 +385,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(c0), "r"(c1) : "memory");
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __grid_constant__ mmb_mlp_layer_params p,
-                                                                     const __grid_constant__ CUtensorMap map_x,
-                                                                     const __grid_constant__ CUtensorMap map_w,
-                                                                     const __grid_constant__ CUtensorMap map_y) {
+__device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p, const CUtensorMap& map_x, const CUtensorMap& map_w,
+                                                  const CUtensorMap& map_y) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
   __shared__ uint32_t tmem_slot;
@@ -519,6 +517,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __gri
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __grid_constant__ mmb_mlp_layer_params p,
+                                                                     const __grid_constant__ CUtensorMap map_x,
+                                                                     const __grid_constant__ CUtensorMap map_w,
+                                                                     const __grid_constant__ CUtensorMap map_y) {
+  mlp_layer_ws_body(p, map_x, map_w, map_y);
+}
+
+// Grouped launch: blockIdx.z selects one of up to MMB_MAX_GROUP independent problems of identical geometry (the ten
+// per-agent networks of the MARL policies, actor_critic.py / runner.py:205-217): one launch per layer for the whole team.
+// Parameters and tensor maps travel as one large __grid_constant__ kernel argument (8 KB; CUDA 12.1+ allows 32 KB).
+struct WsGroupArgs {
+  mmb_mlp_layer_params p[MMB_MAX_GROUP];
+  CUtensorMap map_x[MMB_MAX_GROUP], map_w[MMB_MAX_GROUP], map_y[MMB_MAX_GROUP];
+};
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_group_kernel(const __grid_constant__ WsGroupArgs g) {
+  const int a = blockIdx.z;
+  mlp_layer_ws_body(g.p[a], g.map_x[a], g.map_w[a], g.map_y[a]);
+}
+
+struct LnCastGroupArgs {
+  const float* x[MMB_MAX_GROUP];
+  const float* gamma[MMB_MAX_GROUP];
+  const float* beta[MMB_MAX_GROUP];
+  __nv_bfloat16* y[MMB_MAX_GROUP];
+};
+
 // ---- host: 2-D tensor maps (rows x Kpad bf16, box = box_rows x 64, SWIZZLE_128B) through the driver entry point ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -578,9 +602,9 @@ inline bool make_map_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64
 
 // fp32 [M][K] -> optional LayerNorm (mlp.py:58-59 feature_norm) -> bf16 [Mpad][Kpad], zero padded: the first
 // layer's A operand.  One warp per row.
-__global__ void __launch_bounds__(256) ln_cast_kernel(const float* __restrict__ x, int M, int Mpad, int K, int Kpad,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      float eps, int use_ln, __nv_bfloat16* __restrict__ y) {
+__device__ __forceinline__ void ln_cast_body(const float* __restrict__ x, int M, int Mpad, int K, int Kpad,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int use_ln,
+                                             __nv_bfloat16* __restrict__ y) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   griddep_launch_dependents();  // a programmatically launched first layer may run its prologue / weight loads meanwhile
   if (warp >= Mpad) return;
@@ -609,11 +633,99 @@ __global__ void __launch_bounds__(256) ln_cast_kernel(const float* __restrict__ 
     yr[k] = __float2bfloat16(v);
   }
 }
+__global__ void __launch_bounds__(256) ln_cast_kernel(const float* __restrict__ x, int M, int Mpad, int K, int Kpad,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float eps, int use_ln, __nv_bfloat16* __restrict__ y) {
+  ln_cast_body(x, M, Mpad, K, Kpad, gamma, beta, eps, use_ln, y);
+}
+__global__ void __launch_bounds__(256) ln_cast_group_kernel(const __grid_constant__ LnCastGroupArgs g, int M, int Mpad, int K, int Kpad,
+                                                            float eps, int use_ln) {
+  const int a = blockIdx.y;
+  ln_cast_body(g.x[a], M, Mpad, K, Kpad, g.gamma[a], g.beta[a], eps, use_ln, g.y[a]);
+}
 
 }  // namespace
 }  // namespace mmb
 
 using namespace mmb;
+
+extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t count, void* stream) {
+  if (!params || count <= 0 || count > MMB_MAX_GROUP) return MMB_EINVAL;
+  static thread_local WsGroupArgs g;       // 8 KB: not on the stack; the launch copies it
+  const mmb_mlp_layer_params& p0 = params[0];
+  if (p0.n_tile <= 0 || p0.Kpad % BK || p0.Mpad % BM || p0.Npad % p0.n_tile || p0.n_tile % 32 || p0.n_tile > 512) return MMB_EINVAL;
+  const int stage_bytes = A_STAGE_BYTES + p0.n_tile * BK * 2;
+  int stages = SMEM_BUDGET / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return MMB_EUNSUPPORTED;
+  const int smem = stages * stage_bytes;
+  for (int a = 0; a < count; ++a) {
+    mmb_mlp_layer_params p = params[a];
+    if (p.M != p0.M || p.N != p0.N || p.K != p0.K || p.Mpad != p0.Mpad || p.Kpad != p0.Kpad || p.Npad != p0.Npad ||
+        p.n_tile != p0.n_tile || p.epilogue != p0.epilogue || p.y_stride != p0.y_stride)
+      return MMB_EINVAL;                   // one grid for all: identical geometry
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.x || !p.w || !p.bias || !p.y || p.Kpad < p.K || p.Npad < p.N || p.Mpad < p.M) return MMB_EINVAL;
+    if (p.epilogue < 0 || p.epilogue > 2) return MMB_EINVAL;
+    if (p.epilogue == 2 && (p.n_tile != p.N || p.Npad != p.N || !p.ln_gamma || !p.ln_beta)) return MMB_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w)) & 15u) return MMB_EALIGN;
+    p.stages = stages;
+    if (!make_map_bf16_2d(&g.map_x[a], p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
+        !make_map_bf16_2d(&g.map_w[a], p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)(p.n_tile > 256 ? 256 : p.n_tile)))
+      return MMB_ECUDA;
+    if (p.epilogue == 0 && ((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0) {
+      if (!make_map_f32_out(&g.map_y[a], p.y, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.y_stride)) return MMB_ECUDA;
+      if ((p.n_tile / 32) * BM * 128 > smem) return MMB_EUNSUPPORTED;
+    } else if (p.epilogue != 0 && p.n_tile % 64 == 0) {
+      if ((reinterpret_cast<uintptr_t>(p.y) & 15u) || (p.y_stride % 8)) return MMB_EALIGN;
+      if (!make_map_bf16_2d(&g.map_y[a], p.y, (uint64_t)p.Mpad, (uint64_t)p.y_stride, BM)) return MMB_ECUDA;
+    } else {
+      g.map_y[a] = g.map_x[a];
+    }
+    g.p[a] = p;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= MMB_MAX_DEVICES) return MMB_EUNSUPPORTED;
+  static bool attr_done[MMB_MAX_DEVICES] = {};
+  if (!attr_done[dev]) {
+    if (cudaFuncSetAttribute(mlp_layer_ws_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess)
+      return MMB_ECUDA;
+    attr_done[dev] = true;
+  }
+  {
+    LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p0.Mpad / BM, p0.Npad / p0.n_tile, count);
+    cfg.blockDim = dim3(WS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p0.overlap_prev ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, mlp_layer_ws_group_kernel, g) != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
+  }
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_ln_cast_group(const float* const* x, int32_t count, int32_t M, int32_t Mpad, int32_t K, int32_t Kpad,
+                                     const float* const* gamma, const float* const* beta, float eps, int32_t use_ln,
+                                     void* const* y_bf16, void* stream) {
+  if (!x || !y_bf16 || count <= 0 || count > MMB_MAX_GROUP || M <= 0 || Mpad < M || K <= 0 || Kpad < K) return MMB_EINVAL;
+  if (use_ln && (!gamma || !beta)) return MMB_EINVAL;
+  LnCastGroupArgs g = {};
+  for (int a = 0; a < count; ++a) {
+    if (!x[a] || !y_bf16[a] || (use_ln && (!gamma[a] || !beta[a]))) return MMB_EINVAL;
+    g.x[a] = x[a]; g.y[a] = static_cast<__nv_bfloat16*>(y_bf16[a]);
+    g.gamma[a] = use_ln ? gamma[a] : nullptr; g.beta[a] = use_ln ? beta[a] : nullptr;
+  }
+  {
+    LaunchScope ls(K_LN_CAST, (cudaStream_t)stream);
+    ln_cast_group_kernel<<<dim3((Mpad * 32 + 255) / 256, count), 256, 0, (cudaStream_t)stream>>>(g, M, Mpad, K, Kpad, eps, use_ln);
+  }
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
 
 extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   if (!pp) return MMB_EINVAL;

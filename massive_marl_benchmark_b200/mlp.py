@@ -158,6 +158,74 @@ class FusedMLP:
     __call__ = forward
 
 
+class GroupedMLP:
+    """Several `FusedMLP`s of identical architecture run as ONE launch per layer (grid z = network): the per-agent
+    actors (or critics) of the MARL policies, which the reference evaluates one after the other (runner.py:205-217:
+    2 x num_agents forwards of 4 small GEMMs + LayerNorms each, per env step).  `forward(xs)` takes the per-network
+    inputs (list of [M, in] tensors, or one [G, M, in] tensor) and returns a [G, M, out] tensor."""
+
+    def __init__(self, mlps):
+        if not 1 <= len(mlps) <= L.MAX_GROUP:
+            raise L.MmbError("GroupedMLP takes 1..%d networks" % L.MAX_GROUP)
+        a = mlps[0]
+        for m in mlps[1:]:
+            if len(m.layers) != len(a.layers) or (m.in_ln is None) != (a.in_ln is None) or any(
+                    (x.N, x.K, x.epilogue) != (y.N, y.K, y.epilogue) for x, y in zip(m.layers, a.layers)):
+                raise L.MmbError("GroupedMLP needs networks of identical architecture")
+        self.mlps, self.G, self.device = list(mlps), len(mlps), a.device
+        self.in_dim, self.out_dim = a.in_dim, a.out_dim
+        self._bufs = {}
+
+    def _buffers(self, M):
+        if M not in self._bufs:
+            a = self.mlps[0]
+            Mpad = _round_up(M, 128)
+            acts = [torch.zeros(self.G, Mpad, a.layers[0].Kpad, dtype=torch.bfloat16, device=self.device)]
+            for l in a.layers[:-1]:
+                acts.append(torch.zeros(self.G, Mpad, _round_up(l.N, 64), dtype=torch.bfloat16, device=self.device))
+            self._bufs[M] = (Mpad, acts)
+        return self._bufs[M]
+
+    def forward(self, xs, out=None):
+        import ctypes as C
+        if isinstance(xs, torch.Tensor):
+            xs = [xs[g] for g in range(self.G)]
+        xs = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in xs]
+        M = xs[0].shape[0]
+        Mpad, acts = self._buffers(M)
+        a0 = self.mlps[0]
+        lib, st, G = L.lib(), L.stream_ptr(), self.G
+        vp = C.c_void_p * G
+        l0 = a0.layers[0]
+        use_ln = a0.in_ln is not None
+        L.check(lib.mmb_ln_cast_group(vp(*[x.data_ptr() for x in xs]), G, M, Mpad, l0.K, l0.Kpad,
+                                      vp(*[m.in_gamma.data_ptr() for m in self.mlps]) if use_ln else None,
+                                      vp(*[m.in_beta.data_ptr() for m in self.mlps]) if use_ln else None,
+                                      a0.in_eps if use_ln else 0.0, int(use_ln), vp(*[acts[0][g].data_ptr() for g in range(G)]), st),
+                "mmb_ln_cast_group")
+        if out is None:
+            out = torch.empty(G, M, self.out_dim, dtype=torch.float32, device=self.device)
+        nl = len(a0.layers)
+        for i in range(nl):
+            arr = (L.MlpLayerParams * G)()
+            for g, m in enumerate(self.mlps):
+                l, p = m.layers[i], arr[g]
+                p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = (M, l.N, l.K, Mpad, l.Kpad, l.Npad,
+                                                                                 FusedMLP._n_tile(l, Mpad * G), l.epilogue)
+                p.x, p.w, p.bias = acts[i][g].data_ptr(), l.w.data_ptr(), l.bias.data_ptr()
+                if l.epilogue == 2:
+                    p.ln_gamma, p.ln_beta, p.ln_eps = l.gamma.data_ptr(), l.beta.data_ptr(), l.eps
+                p.overlap_prev = 1
+                if i == nl - 1:
+                    p.y, p.y_stride = out[g].data_ptr(), out.stride(1)
+                else:
+                    p.y, p.y_stride = acts[i + 1][g].data_ptr(), acts[i + 1].stride(1)
+            L.check(lib.mmb_mlp_layer_group(arr, G, st), "mmb_mlp_layer_group")
+        return out
+
+    __call__ = forward
+
+
 class PPOActorCriticForward:
     """Rollout-time interface of the reference's PPO `ActorCritic` (module.py:73-91): `act(observations, states)
     -> (actions, log_prob (N,), value (N,1), mean, log_std.repeat(N,1))` and `act_inference(observations) -> mean`,

@@ -168,3 +168,28 @@ def test_marl_policy_forward(cuda_device):
     std = torch.sigmoid(sd["act.action_out.log_std"] / 1.0) * 0.5
     ref_lp = torch.distributions.Normal(a_det.cpu(), std).log_prob(actions.cpu())
     assert torch.allclose(logp.cpu(), ref_lp, rtol=1e-4, atol=1e-4)
+
+
+def test_grouped_mlp_equals_per_network_forward(cuda_device):
+    """GroupedMLP (one launch per layer for all agents) == the same FusedMLPs run one by one, bit for bit, for both the
+    MARL (LayerNorm) and the PPO (plain ELU) architectures."""
+    from massive_marl_benchmark_b200.mlp import FusedMLP, GroupedMLP
+    dev = cuda_device
+    g = load_golden("mlp_marl_actor0")
+    sd0 = {k[2:].replace("__", "."): v for k, v in g.items() if k.startswith("w_")}
+    gen = torch.Generator().manual_seed(4)
+    G, M = 10, 700
+    sds = []
+    for a in range(G):
+        sds.append({k: (v + 0.01 * torch.randn(v.shape, generator=gen)) if v.dtype.is_floating_point else v for k, v in sd0.items()})
+    mlps = [FusedMLP.from_marl_state_dict(sd, "act.action_out.fc_mean", dev) for sd in sds]
+    xs = torch.randn(G, M, mlps[0].in_dim, generator=gen).to(dev)
+    grouped = GroupedMLP(mlps)(xs)
+    for a in range(G):
+        assert torch.equal(grouped[a], mlps[a](xs[a])), a
+    nets = [_ppo_net(60, [256, 128], 8, 0.5, gen).to(dev) for _ in range(3)]
+    fm = [FusedMLP.from_sequential(n, dev) for n in nets]
+    xs = torch.randn(3, 333, 60, generator=gen).to(dev)
+    grouped = GroupedMLP(fm)([xs[0], xs[1], xs[2]])
+    for a in range(3):
+        assert torch.equal(grouped[a], fm[a](xs[a])), a

@@ -58,3 +58,34 @@ for name, dims in (("ppo_actor", [388, 1024, 1024, 512, 80]), ("ppo_critic", [38
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bench_mlp.json", "w"), indent=1)
+
+# ---- MARL: ten per-agent actors (46 -> 512 -> 512 -> 512 -> 8 with LayerNorms) and critics (388 -> ... -> 1) at M = 4096,
+# one network after the other (the reference's loop, runner.py:205-217) vs one grouped launch per layer -----------------
+from massive_marl_benchmark_b200.mlp import GroupedMLP  # noqa: E402
+
+
+def marl_sd(in_dim, out_dim, head, gen):
+    sd = {"base.feature_norm.weight": torch.ones(in_dim), "base.feature_norm.bias": torch.zeros(in_dim)}
+    dims = [in_dim, 512, 512, 512]
+    names = ["base.mlp.fc1", "base.mlp.fc2.0", "base.mlp.fc2.1"]
+    for i, n in enumerate(names):
+        sd[n + ".0.weight"] = torch.randn(512, dims[i], generator=gen) * (1.0 / dims[i] ** 0.5)
+        sd[n + ".0.bias"] = torch.zeros(512)
+        sd[n + ".2.weight"] = torch.ones(512); sd[n + ".2.bias"] = torch.zeros(512)
+    sd[head + ".weight"] = torch.randn(out_dim, 512, generator=gen) * 0.05
+    sd[head + ".bias"] = torch.zeros(out_dim)
+    return sd
+
+
+gen = torch.Generator().manual_seed(0)
+for name, in_dim, out_dim, head in (("marl_actors_x10", 46, 8, "act.action_out.fc_mean"), ("marl_critics_x10", 388, 1, "v_out")):
+    mlps = [FusedMLP.from_marl_state_dict(marl_sd(in_dim, out_dim, head, gen), head, dev) for _ in range(10)]
+    xs = torch.randn(10, M, in_dim, device=dev)
+    grp = GroupedMLP(mlps)
+    t_seq = timeit(lambda: [m(xs[i]) for i, m in enumerate(mlps)], iters=20, warm=5)
+    t_grp = timeit(lambda: grp(xs), iters=20, warm=5)
+    flops = 10 * 2 * M * (in_dim * 512 + 2 * 512 * 512 + 512 * out_dim)
+    out[name] = {"M": M, "agents": 10, "gflop": flops / 1e9, "one_by_one_ms": t_seq, "grouped_ms": t_grp,
+                 "grouped_tflops": flops / t_grp / 1e9, "launches_one_by_one": 50, "launches_grouped": 5}
+print(json.dumps({k: out[k] for k in ("marl_actors_x10", "marl_critics_x10")}, indent=1))
+json.dump(out, open("gpurun_out/bench_mlp.json", "w"), indent=1)
