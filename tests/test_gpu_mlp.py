@@ -193,3 +193,29 @@ def test_grouped_mlp_equals_per_network_forward(cuda_device):
     grouped = GroupedMLP(fm)([xs[0], xs[1], xs[2]])
     for a in range(3):
         assert torch.equal(grouped[a], fm[a](xs[a])), a
+
+
+def test_marl_team_forward_equals_per_agent_policies(cuda_device):
+    from massive_marl_benchmark_b200.mlp import MarlPolicyForward, MarlTeamForward
+    dev = cuda_device
+    g = load_golden("mlp_marl_actor0")
+    sd0 = {k[2:].replace("__", "."): v for k, v in g.items() if k.startswith("w_")}
+    gen = torch.Generator().manual_seed(8)
+    A, N = 4, 300
+    actor_sds, critic_sds = [], []
+    for a in range(A):
+        asd = {k: (v + 0.01 * torch.randn(v.shape, generator=gen)) if v.dtype.is_floating_point else v for k, v in sd0.items()}
+        csd = {k: v for k, v in asd.items() if k.startswith("base.mlp")}
+        csd.update({"base.feature_norm.weight": torch.ones(388), "base.feature_norm.bias": torch.zeros(388),
+                    "base.mlp.fc1.0.weight": torch.randn(512, 388, generator=gen) * 0.05, "v_out.weight": torch.randn(1, 512, generator=gen) * 0.05,
+                    "v_out.bias": torch.zeros(1)})
+        actor_sds.append(asd); critic_sds.append(csd)
+    team = MarlTeamForward(actor_sds, critic_sds, device=dev)
+    obs = torch.randn(N, A, team.actors.in_dim, generator=gen).to(dev)        # (N, A, O) as the wrapper returns it
+    share = torch.randn(N, 388, generator=gen).to(dev)
+    values, actions, logp = team.get_actions(share, obs, deterministic=True)
+    assert values.shape == (A, N, 1) and actions.shape == (A, N, 8) and logp.shape == (A, N, 8)
+    for a in range(A):
+        pol = MarlPolicyForward(actor_sds[a], critic_sds[a], device=dev)
+        v, act, lp = pol.get_actions(share, obs[:, a].contiguous(), deterministic=True)
+        assert torch.equal(values[a], v) and torch.equal(actions[a], act) and torch.allclose(logp[a], lp)
