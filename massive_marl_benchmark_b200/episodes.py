@@ -57,6 +57,18 @@ class EpisodeTracker:
         self._keep = (rewards, dones)
         L.check(L.lib().mmb_episode_update(p, L.stream_ptr()), "mmb_episode_update")
 
+    def update_marl(self, rewards, dones):
+        """The MARL runner's variant (agents/algorithms/marl/runner.py:135-144): per env step `dones_env = all(dones, 1)`,
+        `reward_env = mean(rewards, 1).flatten()`, `train_episode_rewards += reward_env`, finished episodes appended at
+        `dones_env`.  rewards [T, N, A, 1] (or [N, A, 1]), dones [T, N, A] (or [N, A]); the two reductions over the agent
+        axis are the reference's own torch ops, the bookkeeping is `update`."""
+        if rewards.dim() == 3:
+            rewards, dones = rewards.unsqueeze(0), dones.unsqueeze(0)
+        T, N = rewards.shape[0], rewards.shape[1]
+        reward_env = torch.mean(rewards.reshape(T, N, -1), dim=2)
+        dones_env = torch.all(dones.reshape(T, N, -1) != 0, dim=2).to(torch.uint8)
+        self.update(reward_env, dones_env)
+
     @property
     def finished(self):
         """Episodes finished so far: 0-dim int64 device tensor (no sync)."""

@@ -259,3 +259,32 @@ def test_shared_buffer_equals_per_agent_buffers(cuda_device, use_popart, ptl):
     shared.after_update()
     assert torch.equal(shared.share_obs[0], shared.share_obs[-1]) and torch.equal(shared.obs[:, 0], shared.obs[:, -1])
     assert shared.share_obs.data_ptr() == shared.agent(3).share_obs.data_ptr()       # stored once
+
+
+def test_episode_tracker_marl_runner_variant(cuda_device):
+    """update_marl == the bookkeeping lines of the MARL runner (runner.py:135-144) transcribed literally."""
+    from massive_marl_benchmark_b200.episodes import EpisodeTracker
+    dev = cuda_device
+    N, A, T = 123, 4, 9
+    gen = torch.Generator().manual_seed(2)
+    tr = EpisodeTracker(N, dev)
+    train_episode_rewards = torch.zeros(1, N, device=dev)          # the runner keeps it on the training device
+    done_episodes_rewards = []
+    for it in range(4):
+        rewards = torch.randn(T, N, A, 1, generator=gen).to(dev)
+        dones = (torch.rand(T, N, 1, generator=gen) < 0.1).expand(T, N, A).clone().to(dev)
+        dones[:, ::7, 0] = False                                   # some agents not done -> env not done
+        for step in range(T):
+            dones_env = torch.all(dones[step], dim=1)                            # runner.py:135
+            reward_env = torch.mean(rewards[step], dim=1).flatten()              # runner.py:137
+            train_episode_rewards += reward_env                                  # runner.py:139
+            for t in range(N):                                                   # runner.py:141-144
+                if dones_env[t]:
+                    done_episodes_rewards.append(train_episode_rewards[:, t].clone())
+                    train_episode_rewards[:, t] = 0
+        tr.update_marl(rewards, dones)
+        torch.cuda.synchronize()
+        assert torch.equal(tr.cur_reward_sum, train_episode_rewards[0])
+        assert int(tr.finished) == len(done_episodes_rewards)
+        rr, _ = tr.deques()
+        assert rr == [float(x) for x in done_episodes_rewards[-100:]]
