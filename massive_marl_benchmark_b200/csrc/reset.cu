@@ -9,9 +9,10 @@
 // The reference pays a host sync (`len(env_ids)`) and ~45 small kernels per step for this; here the
 // count stays on the device (counts[f]) and nothing is read back.
 //
-// One CTA of 1024 threads per row f (a row = the flags of one frame): warp ballot + popc prefix inside
-// the CTA, running offset across 1024-env chunks.  O(N) flag bytes per row; fine up to ~1M envs per row
-// (one SM streams the flags); a multi-CTA decoupled look-back scan is the planned upgrade for larger N.
+// One CTA of 1024 threads per row f (a row = the flags of one frame), four consecutive envs per thread: shuffle scan of
+// the per-thread counts inside a warp, warp totals scanned by warp 0, running offset across 4096-env passes.  O(N) flag
+// bytes per row; fine up to ~1M envs per row (one SM streams the flags); a multi-CTA decoupled look-back scan is the
+// planned upgrade for larger N.
 #include "../../include/mmb.h"
 #include "mmb_common.cuh"
 #include "mmb_math.cuh"
@@ -45,7 +46,7 @@ __device__ __forceinline__ TaskShape shape_of(int task) {
 
 __global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb_reset_params p) {
   __shared__ int warp_tot[32];
-  __shared__ int s_running;
+  __shared__ int s_running, s_chunk_total;
   const int f = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int N = p.num_envs;
@@ -58,41 +59,57 @@ __global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb
 
   if (tid == 0) s_running = 0;
   __syncthreads();
-  constexpr int PRE = 8;  // flag loads of 8 chunks are issued together: one memory latency per 8192 envs
-  for (int base0 = 0; base0 < N; base0 += PRE * 1024) {
-    unsigned pre = 0;
+  // Four consecutive envs per thread (one 32-bit load of the uint8 flags), 4096 envs per pass: the ordered rank of a
+  // flagged env = running total + exclusive scan of the per-thread counts (shuffle scan inside a warp, the 32 warp totals
+  // scanned by warp 0) + its rank among the thread's four.  One pass and two barriers for N <= 4096.
+  for (int base = 0; base < N; base += 4096) {
+    const int e4 = base + 4 * tid;
+    unsigned bits = 0;
+    if (f8 && e4 + 3 < N && (reinterpret_cast<uintptr_t>(f8 + e4) & 3u) == 0) {
+      const uchar4 v = *reinterpret_cast<const uchar4*>(f8 + e4);
+      bits = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
+    } else {
 #pragma unroll
-    for (int c = 0; c < PRE; ++c) {
-      const int e = base0 + c * 1024 + tid;
-      bool fl = false;
-      if (e < N) fl = f64 ? (f64[e] != 0) : (f8[e] != 0);
-      pre |= (fl ? 1u : 0u) << c;
-    }
-    for (int c = 0; c < PRE && base0 + c * 1024 < N; ++c) {
-      const int e = base0 + c * 1024 + tid;
-      const bool flag = (pre >> c) & 1u;
-      const unsigned bal = __ballot_sync(0xffffffffu, flag);
-      const int wprefix = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) warp_tot[wid] = __popc(bal);
-      __syncthreads();
-      const int running = s_running;
-      int woff = 0, tot = 0;
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) {
-        int v = warp_tot[w];
-        woff += (w < wid) ? v : 0;
-        tot += v;
+      for (int j = 0; j < 4; ++j) {
+        const int e = e4 + j;
+        if (e < N && (f64 ? (f64[e] != 0) : (f8[e] != 0))) bits |= 1u << j;
       }
-      if (flag) {
-        const int i = running + woff + wprefix;
+    }
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int wt = warp_tot[lane];
+      int wincl = wt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += v;
+      }
+      warp_tot[lane] = wincl - wt;          // exclusive prefix of the warp totals
+      if (lane == 31) s_chunk_total = wincl;
+    }
+    __syncthreads();
+    int i = s_running + warp_tot[wid] + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (bits & (1u << j)) {
+        const int e = e4 + j;
         env_ids[i] = e;
-        if (ia) for (int j = 0; j < sh.na; ++j) ia[i * sh.na + j] = sh.apn * e + j;
-        if (ib) for (int j = 0; j < sh.nb; ++j) ib[i * sh.nb + j] = sh.apn * e + j;
+        if (ia) for (int q = 0; q < sh.na; ++q) ia[i * sh.na + q] = sh.apn * e + q;
+        if (ib) for (int q = 0; q < sh.nb; ++q) ib[i * sh.nb + q] = sh.apn * e + q;
+        ++i;
       }
-      __syncthreads();
-      if (tid == 0) s_running = running + tot;
-      __syncthreads();
     }
+    __syncthreads();
+    if (tid == 0) s_running += s_chunk_total;
+    __syncthreads();
   }
   const int count = s_running;
   if (tid == 0 && p.counts) p.counts[f] = count;
