@@ -438,6 +438,9 @@ MMB_API int32_t mmb_mlp_layer(const mmb_mlp_layer_params* p, void* stream);
  * env step).  `params` is an array of `count` structs; M, N, K, paddings, n_tile, epilogue and y_stride must agree. */
 #define MMB_MAX_GROUP 16
 MMB_API int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t count, void* stream);
+/* diagnostic of the experimental cta_group::2 mode (MMB_MLP_PAIR=1): first barrier wait that timed out {code, block x, block y,
+ * parity}, all zero if none; clears the record */
+MMB_API int32_t mmb_mlp_debug_status(uint32_t* out4);
 
 /* fp32 [M][K] -> optional LayerNorm over K (mlp.py:58-59 feature_norm) -> bf16 [Mpad][Kpad], zero padded: the
  * A operand of the first layer. */

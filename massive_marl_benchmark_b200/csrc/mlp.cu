@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -53,8 +54,8 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_byte_addr) {
 }
 
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, dense.
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int umma_n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int umma_n, int umma_m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
@@ -213,6 +214,42 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst_smem, const CUtensorMap
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                "h"(cta_mask) : "memory");
+}
+// ---- cta_group::2 (a CTA pair = the two SMs of a TPC run ONE 256-row MMA): instruction forms as in CUTLASS
+// (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_2D, mma_sm100_umma.hpp SM100_MMA_F16BF16_2x1SM_SS, cutlass/arch/barrier.h
+// umma_arrive_multicast_2x1SM).  Both CTAs load into their own shared memory; the transaction bytes of both land on the
+// LEADER's (rank 0) mbarrier: clearing bit 24 of a shared::cluster address selects the same offset in the pair's CTA 0.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask) : "memory");
+}
+// bounded mbarrier wait for the paired kernel: a protocol error is recorded (first one wins) and the kernel runs on with
+// garbage instead of hanging the GPU; mmb_mlp_debug_status() reads the record
+__device__ unsigned int g_pair_dbg[4];
+__device__ __forceinline__ void mbar_wait_or_flag(uint64_t* bar, uint32_t parity, unsigned code) {
+  const long long t0 = clock64();
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > 100000000ll) {   // ~50 ms
+      if (atomicCAS(&g_pair_dbg[0], 0u, code) == 0u) { g_pair_dbg[1] = blockIdx.x; g_pair_dbg[2] = blockIdx.y; g_pair_dbg[3] = parity; }
+      return;
+    }
+  }
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -385,6 +422,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(c0), "r"(c1) : "memory");
 }
 
+template <bool PAIR>   // PAIR: the cta_group::2 variant; a kernel that contains cta_group::2 instructions can only be launched as a cluster
 __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p, const CUtensorMap& map_x, const CUtensorMap& map_w,
                                                   const CUtensorMap& map_y) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -393,7 +431,10 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.n_tile;
   const int n_tile = p.n_tile;
-  const int b_bytes = n_tile * BK * 2;
+  // p._reserved == 1: cta_group::2 - the CTA pair (cluster of 2 along M) runs one 256 x n_tile MMA; each CTA holds its
+  // 128 rows of A and HALF of the weight tile, so 32 KB instead of 48 KB enter each SM per k-block (the measured bound)
+  constexpr bool pair = PAIR;
+  const int b_bytes = (pair ? n_tile / 2 : n_tile) * BK * 2;
   const int stage_bytes = A_STAGE_BYTES + b_bytes;   // [A tile | B tile], both multiples of 1024 B
   const int S = p.stages;
   const int nkb = p.Kpad / BK;
@@ -409,7 +450,7 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
   const int w_rows = n_tile / (int)cm;     // rows of the weight tile this CTA fetches (host guarantees divisibility by 8)
 
   if (tid == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], cm); }
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], pair ? 1 : cm); }
     mbar_init(&accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -417,8 +458,13 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
   }
   if (warp == 1) {  // the MMA warp owns the tensor memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (pair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -432,6 +478,10 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
     if (elect_one()) {
       auto load_w = [&](int kb, int s) {
         uint8_t* st = smem + s * stage_bytes;
+        if constexpr (pair) {  // this CTA's half of the weight tile into its own shared memory, bytes counted on the leader's barrier
+          tma_load_2d_2sm(st + A_STAGE_BYTES, &map_w, kb * BK, n0 + (int)crank * (n_tile / 2), &full_bar[s]);
+          return;
+        }
         if (cm > 1) {
           tma_load_2d_mc(st + A_STAGE_BYTES + (int)crank * w_rows * 128, &map_w, kb * BK, n0 + (int)crank * w_rows, &full_bar[s], cmask);
           return;
@@ -443,23 +493,42 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
       // that kernel (the previous layer) is still running; the activation tiles wait for it
       const int pre = nkb < S ? nkb : S;
       for (int kb = 0; kb < pre; ++kb) {
-        mbar_expect_tx(&full_bar[kb], (uint32_t)stage_bytes);
+        if (!pair) mbar_expect_tx(&full_bar[kb], (uint32_t)stage_bytes);
+        else if (crank == 0) mbar_expect_tx(&full_bar[kb], 2u * (uint32_t)stage_bytes);   // both CTAs' tiles
         load_w(kb, kb);
       }
       if (p.overlap_prev) griddep_wait();
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S, u = kb / S;
         if (u > 0) {
-          mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
-          mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          if (pair) mbar_wait_or_flag(&empty_bar[s], (uint32_t)((u - 1) & 1), 0x100u + (unsigned)kb);
+          else mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
+          if (!pair) mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          else if (crank == 0) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)stage_bytes);
           load_w(kb, s);
         }
-        tma_load_2d(smem + s * stage_bytes, &map_x, kb * BK, m0, &full_bar[s]);
+        if constexpr (pair) tma_load_2d_2sm(smem + s * stage_bytes, &map_x, kb * BK, m0, &full_bar[s]);
+        else tma_load_2d(smem + s * stage_bytes, &map_x, kb * BK, m0, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (elect_one()) {
+    if constexpr (pair) {
+      if (crank == 0 && elect_one()) {       // only the leader issues; the MMA reads both CTAs' operand tiles
+        const uint32_t idesc = umma_idesc_bf16(n_tile, 2 * BM);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % S, u = kb / S;
+          mbar_wait_or_flag(&full_bar[s], (uint32_t)(u & 1), 0x200u + (unsigned)kb);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes), b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j)
+            umma_bf16_2sm(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
+          umma_commit_2sm(&empty_bar[s], 3);   // frees the stage in both CTAs
+        }
+        umma_commit_2sm(&accum_bar, 3);        // accumulators of both CTAs ready
+      }
+    } else if (elect_one()) {
       const int umma_n = n_tile > 256 ? 256 : n_tile;
       const uint32_t idesc = umma_idesc_bf16(umma_n);
       for (int kb = 0; kb < nkb; ++kb) {
@@ -481,7 +550,8 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
-    mbar_wait(&accum_bar, 0);
+    if (pair) mbar_wait_or_flag(&accum_bar, 0, 0x300u + crank);
+    else mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
@@ -514,14 +584,23 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
   tc_fence_before();
   __syncthreads();
   if (cm > 1) cluster_sync_all();          // no CTA leaves while a peer's commit may still arrive on its barriers
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+  if (warp == 1) {
+    if constexpr (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+  }
 }
 
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_kernel(const __grid_constant__ mmb_mlp_layer_params p,
                                                                      const __grid_constant__ CUtensorMap map_x,
                                                                      const __grid_constant__ CUtensorMap map_w,
                                                                      const __grid_constant__ CUtensorMap map_y) {
-  mlp_layer_ws_body(p, map_x, map_w, map_y);
+  mlp_layer_ws_body<false>(p, map_x, map_w, map_y);
+}
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_pair_kernel(const __grid_constant__ mmb_mlp_layer_params p,
+                                                                          const __grid_constant__ CUtensorMap map_x,
+                                                                          const __grid_constant__ CUtensorMap map_w,
+                                                                          const __grid_constant__ CUtensorMap map_y) {
+  mlp_layer_ws_body<true>(p, map_x, map_w, map_y);
 }
 
 // Grouped launch: blockIdx.z selects one of up to MMB_MAX_GROUP independent problems of identical geometry (the ten
@@ -533,7 +612,7 @@ struct WsGroupArgs {
 };
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_group_kernel(const __grid_constant__ WsGroupArgs g) {
   const int a = blockIdx.z;
-  mlp_layer_ws_body(g.p[a], g.map_x[a], g.map_w[a], g.map_y[a]);
+  mlp_layer_ws_body<false>(g.p[a], g.map_x[a], g.map_w[a], g.map_y[a]);
 }
 
 struct LnCastGroupArgs {
@@ -648,6 +727,12 @@ __global__ void __launch_bounds__(256) ln_cast_group_kernel(const __grid_constan
 }  // namespace mmb
 
 using namespace mmb;
+
+extern "C" __attribute__((visibility("default"))) int32_t mmb_mlp_debug_status(unsigned int* out4) {
+  unsigned int z[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out4, g_pair_dbg, 16) != cudaSuccess) return MMB_ECUDA;
+  return cudaMemcpyToSymbol(g_pair_dbg, z, 16) == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
 
 extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t count, void* stream) {
   if (!params || count <= 0 || count > MMB_MAX_GROUP) return MMB_EINVAL;
@@ -773,9 +858,23 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   int cm = 1;
   for (int c = cluster_pref; c > 1; c >>= 1)
     if ((p.Mpad / BM) % c == 0 && p.n_tile <= 256 && (p.n_tile / c) % 8 == 0 && p.n_tile % c == 0) { cm = c; break; }
+  // cta_group::2 (MMB_MLP_PAIR=1): CTA pairs along M run one 256-row MMA, each CTA holding half of the weight tile.
+  // Parity-tested; measured on the 1024 x 1024 layer at M = 4096: k-loop 8.9 -> 6.1 us per tile, the layer launched alone
+  // 17.8 -> 16.5 us, but the PDL-chained forward 45.1 -> 46.9 us (a pair can only start when BOTH SMs of its TPC are
+  // free, which costs the overlap with the previous layer's drain) - hence opt-in.
+  static const int pair_pref = [] { const char* v = getenv("MMB_MLP_PAIR"); return v ? atoi(v) : 0; }();
+  const bool pair = pair_pref && (p.Mpad / BM) % 2 == 0 && p.n_tile <= 256 && p.n_tile % 32 == 0 && p.n_tile >= 64;
+  p._reserved = pair ? 1 : 0;
+  if (pair) {
+    cm = 2;
+    const int sb = A_STAGE_BYTES + (p.n_tile / 2) * BK * 2;
+    int st = SMEM_BUDGET / sb;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    p.stages = st;
+  }
   CUtensorMap map_x, map_w, map_y;
   if (!make_map_bf16_2d(&map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
-      !make_map_bf16_2d(&map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)((p.n_tile > 256 ? 256 : p.n_tile) / cm)))
+      !make_map_bf16_2d(&map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)((p.n_tile > 256 ? 256 : p.n_tile) / cm)))   // pair: cm == 2
     return MMB_ECUDA;
   if (p.epilogue == 0 && ((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0) {
     // fp32 [M][N] rows of y_stride floats with a 16-byte aligned base and pitch: staged in the operand ring, TMA-stored
@@ -810,7 +909,18 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (cudaLaunchKernelEx(&cfg, mlp_layer_ws_kernel, p, map_x, map_w, map_y) != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
+    static bool pair_attr_done[MMB_MAX_DEVICES] = {};
+    if (pair && !pair_attr_done[dev]) {
+      if (cudaFuncSetAttribute(mlp_layer_ws_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess) return MMB_ECUDA;
+      pair_attr_done[dev] = true;
+    }
+    const cudaError_t le = pair ? cudaLaunchKernelEx(&cfg, mlp_layer_ws_pair_kernel, p, map_x, map_w, map_y)
+                                : cudaLaunchKernelEx(&cfg, mlp_layer_ws_kernel, p, map_x, map_w, map_y);
+    if (le != cudaSuccess) {
+      if (getenv("MMB_DEBUG")) fprintf(stderr, "mmb_mlp_layer: launch failed: %s (cluster %d, pair %d, smem %d)\n", cudaGetErrorString(le), cm, (int)pair, smem);
+      (void)cudaGetLastError();
+      return MMB_ECUDA;
+    }
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
