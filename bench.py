@@ -374,7 +374,8 @@ def run_ours(args, rank, world, local_rank):
     # step t computes (every byte still crosses PCIe inside the timed region)
     host_prov = HostReplayProvider({"root": torch.cat([f["root"] for f in frames[:2]]),
                                     "dof": torch.cat([f["dof"] for f in frames[:2]]),
-                                    "actions": torch.cat([f["actions"] for f in frames[:2]])}, dev, extra_keys=("actions",))
+                                    "actions": torch.cat([f["actions"] for f in frames[:2]])}, dev, extra_keys=("actions",),
+                                   packed=os.environ.get("MMB_HOST_PACKED", "1") != "0")
     cfg2 = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 7 + rank}
     task2 = TenAnt(cfg2, None, None, "cuda", local_rank, True, False, provider=host_prov)
     task2.keep_raw_obs = False

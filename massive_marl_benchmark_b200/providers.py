@@ -81,14 +81,33 @@ class HostReplayProvider(FrameProvider):
     run (two device staging sets), so the PCIe transfer overlaps compute; `frame()` makes the compute stream wait
     for the upload of the current frame only."""
 
-    def __init__(self, frames: Dict[str, torch.Tensor], device, loop=True, extra_keys=()):
+    def __init__(self, frames: Dict[str, torch.Tensor], device, loop=True, extra_keys=(), packed=True):
         super().__init__()
         keys = tuple(self.keys) + tuple(extra_keys)
-        self.host = {k: v.contiguous().pin_memory() for k, v in frames.items() if k in keys and v is not None}
+        src = {k: v.contiguous() for k, v in frames.items() if k in keys and v is not None}
         self.device = device
         self.loop = loop
-        self._F = next(iter(self.host.values())).shape[0]
-        self.stage = [{k: torch.empty_like(v[0], device=device) for k, v in self.host.items()} for _ in range(2)]
+        self._F = next(iter(src.values())).shape[0]
+        self.packed = packed and all(v.dtype == torch.float32 and (v[0].numel() * 4) % 16 == 0 for v in src.values())
+        if self.packed:
+            # one pinned row per frame [root | dof | sensor | extras] and one device staging row per set: a frame is ONE
+            # host->device copy (one DMA descriptor instead of one per tensor); the task sees views into the staging row
+            sizes = {k: v[0].numel() for k, v in src.items()}
+            total = sum(sizes.values())
+            self._packed_host = torch.empty(self._F, total, dtype=torch.float32).pin_memory()
+            self._packed_stage = [torch.empty(total, dtype=torch.float32, device=device) for _ in range(2)]
+            self.host, off = {}, 0
+            self.stage = [{}, {}]
+            for k, v in src.items():
+                n = sizes[k]
+                self._packed_host[:, off:off + n].copy_(v.reshape(self._F, n))
+                self.host[k] = self._packed_host[:, off:off + n].view(v.shape)
+                for s_ in range(2):
+                    self.stage[s_][k] = self._packed_stage[s_][off:off + n].view(v.shape[1:])
+                off += n
+        else:
+            self.host = {k: v.pin_memory() for k, v in src.items()}
+            self.stage = [{k: torch.empty_like(v[0], device=device) for k, v in self.host.items()} for _ in range(2)]
         self.h2d_bytes_per_frame = sum(v[0].numel() * v.element_size() for v in self.host.values())
         self.copy_stream = torch.cuda.Stream(device=device)
         self._ready = [torch.cuda.Event(), torch.cuda.Event()]     # upload of the set finished (copy stream)
@@ -106,8 +125,11 @@ class HostReplayProvider(FrameProvider):
             return
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._free[cursor & 1])   # the previous user of this staging set is done
-            for k, v in self.host.items():
-                st[k].copy_(v[i], non_blocking=True)
+            if self.packed:
+                self._packed_stage[cursor & 1].copy_(self._packed_host[i], non_blocking=True)
+            else:
+                for k, v in self.host.items():
+                    st[k].copy_(v[i], non_blocking=True)
             self._ready[cursor & 1].record(self.copy_stream)
         self._prefetched = cursor
 
