@@ -243,6 +243,10 @@ typedef struct {
   const float* noise_pos; const float* noise_vel; int64_t noise_row_stride; /* [F][N][8] */
   uint64_t seed; uint64_t step;                     /* Philox key / counter base (noise_mode 1) */
   float* forces_state;                              /* Ingenuity: task.forces rows to zero, or NULL */
+  /* Optional, TenAnt / OneAnt: zero-initialised, self-cleaning scratch of num_rows * (ceil(num_envs / 4096) + 1) words.
+   * With it a flag row is scanned by one CTA per 4096 envs (chunk totals published to the scratch, every CTA looks back at
+   * its predecessors) instead of by a single CTA: needed from ~16 k envs per row upwards.  NULL: one CTA per row. */
+  uint64_t* scan_scratch;
   mmb_ant_consts c;
 } mmb_reset_params;
 

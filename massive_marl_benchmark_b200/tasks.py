@@ -33,6 +33,18 @@ def _device_of(device_type, device_id):
     raise L.MmbError("massive_marl_benchmark_b200 runs on CUDA devices only (device_type=%r)" % (device_type,))
 
 
+def _reset_scan_scratch(task, rows):
+    """Zero-initialised, self-cleaning scratch for the multi-CTA reset scan (include/mmb.h, `scan_scratch`): only for flag
+    rows of more than 8192 envs, where one CTA per row would serialise the compaction."""
+    N = task.num_envs
+    if N <= 8192:
+        return None
+    cache = task.__dict__.setdefault("_reset_scratch", {})
+    if rows not in cache:
+        cache[rows] = torch.zeros(rows * ((N + 4095) // 4096 + 1), dtype=torch.int64, device=task.device)
+    return cache[rows]
+
+
 class BaseTask:
     """Buffers and `step` of reference base_task.py:24-149 (viewer / domain randomisation are PhysX-side
     and out of scope)."""
@@ -152,6 +164,7 @@ class TenAnt(BaseTask):
             p.dof_state = L.ptr(self.dof_reset_staging)
             p.seed = self.reset_seed
             p.c = self.consts
+            p.scan_scratch = L.ptr(_reset_scan_scratch(self, 1))
         if self.reset_noise is not None:
             p.noise_mode = 0
             self._noise_keep = tuple(t.contiguous() for t in self.reset_noise)
@@ -317,6 +330,7 @@ class OneAnt(BaseTask):
         else:
             p.noise_mode, p.seed, p.step = 1, self.reset_seed, self._step_count
         p.c = self.consts
+        p.scan_scratch = L.ptr(_reset_scan_scratch(self, 1))
         L.check(L.lib().mmb_reset_compact(p, L.stream_ptr()), "mmb_reset_compact")
         self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
         self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
@@ -487,5 +501,6 @@ def reset_replay(task, flags_u8, dof_out=None, noise=None, out=None):
         p.noise_mode, p.seed, p.step = 1, task.reset_seed, task._step_count
     if kind != L.TASK_INGENUITY:
         p.c = task.consts
+        p.scan_scratch = L.ptr(_reset_scan_scratch(task, F))
     L.check(L.lib().mmb_reset_compact(p, L.stream_ptr()), "mmb_reset_compact")
     return env_ids, ia, ib, counts

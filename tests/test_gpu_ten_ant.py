@@ -372,3 +372,43 @@ torch.save({"obs": obs.cpu(), "rew": rew.cpu(), "d8": d8.cpu(), "fo": fo.cpu(), 
         res[variant] = torch.load(out)
     for k in res["split"]:
         assert torch.equal(res["split"][k], res["mono"][k]), k
+
+
+@pytest.mark.parametrize("N", [8193, 20000, 70001])
+def test_reset_compaction_multi_cta_scan(cuda_device, N):
+    """Rows of more than 8192 envs take the multi-CTA look-back scan: ordered env ids, index lists, counts and the DOF
+    re-randomisation equal nonzero() / the single-CTA kernel, for uint8 rows (batched) and the int64 per-step call,
+    repeatedly (the scratch cleans itself), with dense and sparse flags."""
+    from massive_marl_benchmark_b200 import _lib as L
+    from massive_marl_benchmark_b200 import synthetic
+    from massive_marl_benchmark_b200.tasks import reset_replay
+    dev = cuda_device
+    T = 3
+    fr = synthetic.ten_ant_frames(N, 1, seed=N)
+    task = _make(N, fr, "cuda", False, dev)
+    gen = torch.Generator().manual_seed(N)
+    for rep, pflag in enumerate((0.01, 0.6, 0.0)):
+        flags = (torch.rand(T, N, generator=gen) < pflag).to(torch.uint8).to(dev)
+        dof_multi = torch.zeros(T, 80 * N, 2, device=dev)
+        env_ids, ia, ib, counts = reset_replay(task, flags, dof_out=dof_multi)
+        # single-CTA reference: same call without the scratch
+        save = task.__dict__.pop("_reset_scratch")
+        task.__dict__["_reset_scratch"] = {T: None}
+        dof_single = torch.zeros(T, 80 * N, 2, device=dev)
+        e2, a2, b2, c2 = reset_replay(task, flags, dof_out=dof_single)
+        task.__dict__["_reset_scratch"] = save
+        torch.cuda.synchronize()
+        assert torch.equal(counts, c2)
+        for t in range(T):
+            nz = flags[t].nonzero().flatten()
+            n = len(nz)
+            assert int(counts[t]) == n and torch.equal(env_ids[t, :n], nz) and torch.equal(env_ids[t, :n], e2[t, :n])
+            assert torch.equal(ia[t, :11 * n], a2[t, :11 * n]) and torch.equal(ib[t, :10 * n], b2[t, :10 * n])
+        assert torch.equal(dof_multi, dof_single)
+        assert int(save[T].abs().sum()) == 0                 # scratch cleaned itself
+    # per-step path (int64 reset_buf, one row)
+    task.reset_buf.copy_((torch.rand(N, generator=gen) < 0.05).long().to(dev))
+    want = task.reset_buf.nonzero().flatten()
+    task.reset_idx()
+    torch.cuda.synchronize()
+    assert int(task.reset_count) == len(want) and torch.equal(task.env_ids[:len(want)], want)
