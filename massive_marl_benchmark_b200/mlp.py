@@ -238,17 +238,36 @@ class PPOActorCriticForward:
         self.actor = FusedMLP.from_sequential(actor_critic.actor, device)
         self.critic = FusedMLP.from_sequential(actor_critic.critic, device)
         self.log_std = actor_critic.log_std.detach().to(device)
+        # actor and critic have the same hidden architecture (module.py:25-55); with the critic's 1-wide head zero-padded to
+        # the actor's width the two networks run as ONE grouped launch per layer (grid z = network)
+        self._pair = None
+        a, c = self.actor, self.critic
+        same_hidden = (not self.asymmetric and len(a.layers) == len(c.layers) and a.in_dim == c.in_dim and
+                       all((x.N, x.K) == (y.N, y.K) for x, y in zip(a.layers[:-1], c.layers[:-1])) and
+                       a.layers[-1].K == c.layers[-1].K and c.layers[-1].N <= a.layers[-1].N)
+        if same_hidden:
+            la, lc = a.layers[-1], c.layers[-1]
+            w = torch.zeros(la.N, lc.K, device=device); w[:lc.N] = lc.w[:lc.N, :lc.K].float()
+            b = torch.zeros(la.N, device=device); b[:lc.N] = lc.bias
+            padded = FusedMLP(c.layers[:-1] + [_Layer(w, b, False, None, device)], None, device)
+            self._pair = GroupedMLP([a, padded])
+            self._value_cols = lc.N
+
+    def _mean_value(self, observations, states):
+        if self._pair is not None:
+            out = self._pair([observations, observations])
+            return out[0], out[1][:, :self._value_cols]
+        return self.actor(observations), self.critic(states if self.asymmetric else observations)
 
     @torch.no_grad()
     def act(self, observations, states=None):
-        mean = self.actor(observations)
+        mean, value = self._mean_value(observations, states)
         scale = self.log_std.exp() * self.log_std.exp()
         noise = torch.randn_like(mean)
         actions = mean + noise * scale
         # log_prob of a diagonal MultivariateNormal with scale_tril = diag(scale)
         k = mean.shape[1]
         log_prob = -0.5 * (noise * noise).sum(-1) - scale.log().sum() - 0.5 * k * 1.8378770664093453  # log(2*pi)
-        value = self.critic(states if self.asymmetric else observations)
         return actions, log_prob, value, mean, self.log_std.repeat(mean.shape[0], 1)
 
     @torch.no_grad()

@@ -147,6 +147,9 @@ def test_ppo_act_interface_matches_reference_semantics(cuda_device):
     emp_std = (actions - mean).std(dim=0)
     assert torch.allclose(emp_std, (ac.log_std.exp() ** 2).detach(), rtol=0.2)          # sigma^2, not sigma
     assert _rowmax_err(fwd.act_inference(obs), ac.actor(obs).detach()) <= 3e-2
+    # actor and critic ran as one grouped launch per layer (critic head zero-padded): same numbers as on their own
+    assert fwd._pair is not None
+    assert torch.equal(mean, fwd.actor(obs)) and torch.equal(value, fwd.critic(obs))
 
 
 def test_marl_policy_forward(cuda_device):

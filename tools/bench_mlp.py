@@ -59,6 +59,26 @@ print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bench_mlp.json", "w"), indent=1)
 
+# ---- PPO act(): actor + critic as one grouped launch per layer vs one network after the other -----------------------------
+from massive_marl_benchmark_b200.mlp import PPOActorCriticForward  # noqa: E402
+
+
+class _AC(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.asymmetric = False
+        self.actor, self.critic = net([388, 1024, 1024, 512, 80]), net([388, 1024, 1024, 512, 1])
+        self.log_std = torch.nn.Parameter(torch.zeros(80))
+
+
+ac = _AC().to(dev)
+fwd = PPOActorCriticForward(ac, dev)
+xo = torch.randn(M, 388, device=dev)
+t_pair = timeit(lambda: fwd._mean_value(xo, None))
+t_sep = timeit(lambda: (fwd.actor(xo), fwd.critic(xo)))
+out["ppo_actor_critic"] = {"M": M, "grouped_ms": t_pair, "one_by_one_ms": t_sep, "gflop": 32.6, "grouped_tflops": 32.6 / t_pair}
+print(json.dumps(out["ppo_actor_critic"]))
+
 # ---- MARL: ten per-agent actors (46 -> 512 -> 512 -> 512 -> 8 with LayerNorms) and critics (388 -> ... -> 1) at M = 4096,
 # one network after the other (the reference's loop, runner.py:205-217) vs one grouped launch per layer -----------------
 from massive_marl_benchmark_b200.mlp import GroupedMLP  # noqa: E402
