@@ -169,7 +169,9 @@ __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* _
 
 // Per-env finish by one thread: ordered sums over the ten ants' partial terms (ten_ant.py:1173-1301), reward, and the
 // progress / reset bookkeeping (inline for T == 1, data-carrying atomic + last-reporter chain for T <= 32).
-__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo) {
+// `root_env`: this env's 143-float root block of frame t still intact in shared memory (role-split kernel), or nullptr.
+__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo,
+                                           const float* root_env = nullptr) {
   const mmb_ant_consts& c = p.c;
   const int T = p.num_frames;
   float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
@@ -231,6 +233,19 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
       chain_bits(p, en, 0, T, (uint32_t)cur, prog, flag);
       p.progress_buf[en] = prog;
       p.reset_buf[en] = flag ? 1 : 0;
+      if (root_env) {
+        // the executor is the frame T-1 unit: ant xy, box xy and the goal direction of the last frame are in its shared
+        // memory already (bo[0..3] was computed from the same box row with the same operations)
+#pragma unroll
+        for (int kk = 0; kk < A; ++kk) {
+          float gx, gy;
+          goal_of(kk, bo[2], bo[3], bo[0], bo[1], gx, gy);
+          *reinterpret_cast<float2*>(p.pos_before + ((int64_t)en * A + kk) * 2) = make_float2(root_env[kk * 13], root_env[kk * 13 + 1]);
+          *reinterpret_cast<float2*>(p.goal_before + ((int64_t)en * A + kk) * 2) = make_float2(gx, gy);
+        }
+        *reinterpret_cast<float2*>(p.box_before + (int64_t)en * 2) = make_float2(bo[2], bo[3]);
+        return;
+      }
       const float* last = p.root + (int64_t)(T - 1) * p.root_frame_stride;
       // carry of the whole env by this thread: the goal direction once, then ten (xy, goal) pairs
       const float* b = last + ((int64_t)en * 11 + 10) * 13;
@@ -834,7 +849,7 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   // the finish runs in the first dof warp: warp 0 has the bulk store to issue and to wait for
   if (tid >= NA && tid - NA < ne) {
     if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
-    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W);
+    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, root_s + (tid - NA) * ROOT_ENV);
     if (tid == NA) MMB_TR(10);
   }
   extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
