@@ -60,7 +60,7 @@ MMB_API uint64_t mmb_launch_count(void);
  * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
 enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
        MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
-       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_COUNT };
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_GAUSS_ACT, MMB_K_COUNT };
 MMB_API int32_t mmb_profile_enable(int32_t on);
 MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
 
@@ -333,6 +333,25 @@ MMB_API int32_t mmb_adv_normalize_xchg(float* advantages, int64_t n, double* sta
  * out[1] = mean reward.  No host sync. */
 MMB_API int32_t mmb_rollout_statistics(const uint8_t* dones, const float* rewards, int32_t num_steps, int32_t num_envs,
                                float* out2, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Gaussian policy head of the rollout-time act(): actions = mean + z * std and their log-probs in */
+/* one launch (PPO module.py:73-87 - pass std = exp(log_std)^2, the reference's scale_tril quirk -  */
+/* and MARL distributions.py:94-117 - pass std = sigmoid(log_std / x) * y, per-dimension log-probs). */
+/* z: rows of `noise` if given (parity mode), 0 if `deterministic`, else Philox(seed, step, index)   */
+/* + Box-Muller (same distribution as the reference's generator, a different stream).               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_rows, act_dim, deterministic, _pad;
+  const float* mean; int64_t mean_stride;  /* [rows][act_dim] with row stride */
+  const float* std;                        /* [act_dim] standard deviation actually applied */
+  const float* noise;                      /* [rows][act_dim] standard normal draws, or NULL */
+  uint64_t seed, step;
+  float* actions;                          /* [rows][act_dim] */
+  float* logp_sum;                         /* [rows] sum over dims (PPO), or NULL */
+  float* logp_per_dim;                     /* [rows][act_dim] (MARL), or NULL */
+} mmb_gaussian_act_params;
+MMB_API int32_t mmb_gaussian_act(const mmb_gaussian_act_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Episode bookkeeping of the PPO runner (agents/algorithms/rl/ppo/ppo.py:143-157,198-220): running */

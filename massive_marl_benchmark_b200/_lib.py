@@ -113,6 +113,12 @@ class EpisodeParams(C.Structure):
                 ("ep_reward", c_vp), ("ep_length", c_vp), ("reward_ring", c_vp), ("length_ring", c_vp), ("state", c_vp)]
 
 
+class GaussianActParams(C.Structure):
+    _fields_ = [("num_rows", c_i32), ("act_dim", c_i32), ("deterministic", c_i32), ("_pad", c_i32),
+                ("mean", c_vp), ("mean_stride", c_i64), ("std", c_vp), ("noise", c_vp), ("seed", c_u64), ("step", c_u64),
+                ("actions", c_vp), ("logp_sum", c_vp), ("logp_per_dim", c_vp)]
+
+
 class GaeMarlParams(C.Structure):
     _fields_ = [
         ("num_envs", c_i32), ("num_steps", c_i32), ("num_agents", c_i32),
@@ -163,6 +169,7 @@ SYMBOLS = {
     "mmb_xchg_close": (c_i32, [c_vp]),
     "mmb_xchg_free": (c_i32, [c_vp]),
     "mmb_rollout_statistics": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "mmb_gaussian_act": (c_i32, [C.POINTER(GaussianActParams), c_vp]),
     "mmb_episode_update": (c_i32, [C.POINTER(EpisodeParams), c_vp]),
     "mmb_gae_marl": (c_i32, [C.POINTER(GaeMarlParams), c_vp]),
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
@@ -218,7 +225,7 @@ def launch_count():
 
 KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
               "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm", "mlp_layer",
-              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring")
+              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring", "gauss_act")
 
 
 def profile_enable(on=True):

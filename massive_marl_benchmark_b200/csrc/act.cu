@@ -1,0 +1,79 @@
+// act.cu - Gaussian policy head: sampling and log-probabilities of the rollout-time `act()` in one launch.
+//
+// Replaces, after the actor MLP has produced the mean:
+//   PPO   ActorCritic.act (agents/algorithms/rl/ppo/module.py:73-87): MultivariateNormal(mean, scale_tril = diag(sigma^2))
+//         .sample() and .log_prob() - the reference's quirk keeps: the effective standard deviation is sigma^2
+//   MARL  DiagGaussian / FixedNormal (agents/algorithms/utils/distributions.py:94-117): std = sigmoid(log_std / x) * y,
+//         per-dimension log-probs
+// which torch runs as six to ten small kernels (randn, mul, add, pow, log, sum ...).  The standard normal draws come from
+// Philox4x32-10 keyed by (seed, step) with the element index as counter + Box-Muller: same distribution as the reference's
+// generator, a different stream (exact RNG parity with torch's global generator is not reproducible; the deterministic
+// path, `noise` supplied by the caller, is what the parity tests use).
+#include "../../include/mmb.h"
+#include "mmb_common.cuh"
+#include "mmb_math.cuh"
+
+namespace mmb {
+namespace {
+
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+  const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincosf(6.28318530717958647692f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+// one warp per row: lanes stride over the action dimensions; per-row log-prob sum by shuffle
+__global__ void __launch_bounds__(256) gaussian_act_kernel(const __grid_constant__ mmb_gaussian_act_params p) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= p.num_rows) return;
+  const int A = p.act_dim;
+  const float* mean = p.mean + (int64_t)row * p.mean_stride;
+  float lp_sum = 0.0f;
+  for (int j = lane; j < A; j += 32) {
+    const float sd = __ldg(p.std + j);
+    float z;
+    if (p.noise) {
+      z = __ldg(p.noise + (int64_t)row * A + j);
+    } else if (p.deterministic) {
+      z = 0.0f;
+    } else {
+      const uint64_t idx = (uint64_t)row * (uint64_t)A + (uint64_t)j;
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)(idx >> 1), (uint32_t)(idx >> 33), (uint32_t)p.step, (uint32_t)(p.step >> 32)),
+                                    make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+      const float2 n = box_muller(r.x, r.y);
+      z = (idx & 1) ? n.y : n.x;
+    }
+    const float m = __ldg(mean + j);
+    const float a = m + z * sd;
+    p.actions[(int64_t)row * A + j] = a;
+    // log N(a; m, sd) = -z^2/2 - log(sd) - log(sqrt(2 pi)) with z = (a - m) / sd as the distribution recomputes it
+    const float zz = (a - m) / sd;
+    const float lp = -0.5f * zz * zz - logf(sd) - 0.9189385332046727f;
+    if (p.logp_per_dim) p.logp_per_dim[(int64_t)row * A + j] = lp;
+    lp_sum += lp;
+  }
+  if (p.logp_sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
+    if (lane == 0) p.logp_sum[row] = lp_sum;
+  }
+}
+
+}  // namespace
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* stream) {
+  if (!pp) return MMB_EINVAL;
+  mmb_gaussian_act_params p = *pp;
+  if (p.num_rows <= 0 || p.act_dim <= 0 || !p.mean || !p.std || !p.actions || p.mean_stride < p.act_dim) return MMB_EINVAL;
+  {
+    LaunchScope ls(K_GAUSS_ACT, (cudaStream_t)stream);
+    gaussian_act_kernel<<<(p.num_rows * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}

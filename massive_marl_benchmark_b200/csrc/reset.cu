@@ -20,23 +20,6 @@
 namespace mmb {
 namespace {
 
-// Philox4x32-10 (Salmon et al. 2011), the counter-based generator torch's CUDA RNG also uses; keyed by
-// (seed), counter = (env, step, block, 0) so that an env-sharded multi-GPU run draws the same numbers as
-// the single-GPU run on the concatenated envs.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
-
 struct TaskShape { int apn, na, nb, dofs, ants; };
 __device__ __forceinline__ TaskShape shape_of(int task) {
   if (task == MMB_TASK_TEN_ANT) return {11, 11, 10, 80, 10};

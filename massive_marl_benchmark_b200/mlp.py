@@ -226,6 +226,31 @@ class GroupedMLP:
     __call__ = forward
 
 
+def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False):
+    """actions = mean + z * std and log-probs in one launch (`mmb_gaussian_act`).  mean [M, A] (row stride allowed), std [A].
+    Returns (actions [M, A], logp): logp [M] summed over the action dims, or [M, A] with per_dim=True."""
+    M, A = mean.shape
+    if mean.stride(1) != 1:
+        mean = mean.contiguous()
+    std = std.reshape(-1).float().contiguous()
+    actions = torch.empty(M, A, dtype=torch.float32, device=mean.device)
+    logp = torch.empty((M, A) if per_dim else (M,), dtype=torch.float32, device=mean.device)
+    p = L.GaussianActParams()
+    p.num_rows, p.act_dim, p.deterministic = M, A, int(bool(deterministic))
+    p.mean, p.mean_stride, p.std = mean.data_ptr(), mean.stride(0), std.data_ptr()
+    if noise is not None:
+        noise = noise.float().contiguous()
+        p.noise = noise.data_ptr()
+    p.seed, p.step = int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFFFFFFFFFF
+    p.actions = actions.data_ptr()
+    if per_dim:
+        p.logp_per_dim = logp.data_ptr()
+    else:
+        p.logp_sum = logp.data_ptr()
+    L.check(L.lib().mmb_gaussian_act(p, L.stream_ptr()), "mmb_gaussian_act")
+    return actions, logp
+
+
 class PPOActorCriticForward:
     """Rollout-time interface of the reference's PPO `ActorCritic` (module.py:73-91): `act(observations, states)
     -> (actions, log_prob (N,), value (N,1), mean, log_std.repeat(N,1))` and `act_inference(observations) -> mean`,
@@ -260,14 +285,13 @@ class PPOActorCriticForward:
         return self.actor(observations), self.critic(states if self.asymmetric else observations)
 
     @torch.no_grad()
-    def act(self, observations, states=None):
+    def act(self, observations, states=None, noise=None):
+        """`noise` [N, act]: standard normal draws to use (parity tests); default: in-kernel Philox keyed by (seed, call #)."""
         mean, value = self._mean_value(observations, states)
-        scale = self.log_std.exp() * self.log_std.exp()
-        noise = torch.randn_like(mean)
-        actions = mean + noise * scale
-        # log_prob of a diagonal MultivariateNormal with scale_tril = diag(scale)
-        k = mean.shape[1]
-        log_prob = -0.5 * (noise * noise).sum(-1) - scale.log().sum() - 0.5 * k * 1.8378770664093453  # log(2*pi)
+        # MultivariateNormal with scale_tril = diag(exp(log_std)^2): sample + log_prob (sum over dims) in one launch
+        self._calls = getattr(self, "_calls", 0) + 1
+        actions, log_prob = gaussian_act(mean, self.log_std.exp() * self.log_std.exp(), seed=getattr(self, "seed", 0),
+                                         step=self._calls, noise=noise)
         return actions, log_prob, value, mean, self.log_std.repeat(mean.shape[0], 1)
 
     @torch.no_grad()
@@ -288,11 +312,11 @@ class MarlPolicyForward:
         self.std = torch.sigmoid(log_std / std_x_coef) * std_y_coef
 
     @torch.no_grad()
-    def get_actions(self, share_obs, obs, deterministic=False):
+    def get_actions(self, share_obs, obs, deterministic=False, noise=None):
         mean = self.actor(obs)
-        actions = mean if deterministic else mean + torch.randn_like(mean) * self.std
-        var = self.std * self.std
-        logp = -((actions - mean) ** 2) / (2 * var) - self.std.log() - 0.9189385332046727   # log(sqrt(2*pi))
+        self._calls = getattr(self, "_calls", 0) + 1
+        actions, logp = gaussian_act(mean, self.std, seed=getattr(self, "seed", 0), step=self._calls, noise=noise,
+                                     deterministic=deterministic, per_dim=True)
         return self.critic(share_obs), actions, logp
 
     @torch.no_grad()

@@ -222,3 +222,34 @@ def test_marl_team_forward_equals_per_agent_policies(cuda_device):
         pol = MarlPolicyForward(actor_sds[a], critic_sds[a], device=dev)
         v, act, lp = pol.get_actions(share, obs[:, a].contiguous(), deterministic=True)
         assert torch.equal(values[a], v) and torch.equal(actions[a], act) and torch.allclose(logp[a], lp)
+
+
+def test_gaussian_act_kernel(cuda_device):
+    """mmb_gaussian_act: with supplied noise the actions and log-probs equal torch.distributions (PPO's sigma^2
+    MultivariateNormal and MARL's per-dimension Normal); with the in-kernel Philox stream the draws are standard normal,
+    reproducible for a (seed, step) and different between steps."""
+    from massive_marl_benchmark_b200.mlp import gaussian_act
+    from torch.distributions import MultivariateNormal, Normal
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(0)
+    M, A = 5000, 80
+    mean = torch.randn(M, A, generator=gen).to(dev)
+    std = (0.3 + torch.rand(A, generator=gen)).to(dev)
+    z = torch.randn(M, A, generator=gen).to(dev)
+    act, lp = gaussian_act(mean, std, noise=z)
+    assert torch.allclose(act, mean + z * std, rtol=1e-6, atol=1e-6)
+    ref = MultivariateNormal(mean, scale_tril=torch.diag(std)).log_prob(act)
+    assert torch.allclose(lp, ref, rtol=1e-4, atol=2e-3)
+    act2, lp2 = gaussian_act(mean, std, noise=z, per_dim=True)
+    assert torch.equal(act2, act) and torch.allclose(lp2, Normal(mean, std).log_prob(act), rtol=1e-4, atol=1e-4)
+    det, _ = gaussian_act(mean, std, deterministic=True)
+    assert torch.equal(det, mean)
+    a1, _ = gaussian_act(mean, std, seed=7, step=1)
+    a1b, _ = gaussian_act(mean, std, seed=7, step=1)
+    a2, _ = gaussian_act(mean, std, seed=7, step=2)
+    assert torch.equal(a1, a1b) and not torch.equal(a1, a2)
+    zz = (a1 - mean) / std
+    assert abs(float(zz.mean())) < 0.01 and abs(float(zz.std()) - 1.0) < 0.01
+    assert abs(float((zz ** 3).mean())) < 0.03 and abs(float((zz ** 4).mean()) - 3.0) < 0.1     # skewness, kurtosis
+    rows = zz[:, :40].reshape(-1); nxt = zz[:, 1:41].reshape(-1)
+    assert abs(float((rows * nxt).mean())) < 0.01                                                  # neighbours uncorrelated
