@@ -366,8 +366,12 @@ __device__ __forceinline__ void stage_out32(uint8_t* tile, int row, int c0, cons
   }
 }
 
+// `flush(j)` is called by every thread of the calling warps right after sub-tile j (64 bf16 / 32 fp32 columns) of their
+// rows has been staged: the kernel uses it to hand finished sub-tiles to the TMA store while the next ones are computed.
+template <class Flush>
 __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& p, uint32_t taddr, int row, int n0, int n_tile,
-                                                    int cb, int ce, uint8_t* tile) {
+                                                    int cb, int ce, uint8_t* tile, Flush flush) {
+  const int sub_cols = (p.epilogue == 0) ? 32 : 64;
   float v[32], bv[32], x[32];
   if (p.epilogue == 2) {  // bias + ELU + LayerNorm over the whole row (n_tile == N): two passes over TMEM
     float sum = 0.0f, sumsq = 0.0f;
@@ -393,6 +397,7 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = (elu1(v[i] + bv[i]) - mean) * rstd * g[i] + b[i];
       stage_out32<false>(tile, row, c0, x);
+      if ((c0 + 32) % sub_cols == 0 || c0 + 32 >= n_tile) flush(c0 / sub_cols);
     }
     return;
   }
@@ -414,6 +419,7 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
       for (int i = 0; i < 32; ++i) x[i] = v[i] + bv[i];
       stage_out32<true>(tile, row, c0, x);
     }
+    if ((c0 + 32) % sub_cols == 0 || c0 + 32 >= ce) flush(c0 / sub_cols);
   }
 }
 
@@ -567,18 +573,37 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
     // staged output needs a TMA-addressable destination: 16-byte aligned base and row pitch; bf16 sub-tiles are 64 wide
     const bool staged = (p.epilogue == 0) ? (((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0)
                                           : (n_tile % 64 == 0);
+    const int sub_cols = (p.epilogue == 0) ? 32 : 64;       // columns per 128-byte sub-tile row (fp32 / bf16)
+    // pipelined stores: the four warps of a column half hand every finished sub-tile to the TMA store (their own named
+    // barrier, one issuing lane) while they compute the next one - the 64 KB tile no longer leaves in one burst after the
+    // math.  Needs the halves to own whole sub-tiles; otherwise one store phase after a barrier of all eight warps.
+    const bool pipelined = staged && (p.epilogue == 2 || (cb % sub_cols == 0 && (ce - cb) % sub_cols == 0 && n_tile >= 2 * sub_cols));
     if (!staged) {
       if (cb < ce) epilogue_row(p, tmem + ((uint32_t)(q * 32) << 16), m0 + row, n0, n_tile, cb, ce);
     } else if (cb < ce) {
-      epilogue_row_staged(p, tmem + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, smem);
+      if (pipelined) {
+        epilogue_row_staged(p, tmem + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, smem, [&](int j) {
+          fence_async_smem();
+          if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (q == 0 && lane == 0) {
+            tma_store_2d(&map_y, smem + j * (BM * 128), n0 + j * sub_cols, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        });
+        if (q == 0 && lane == 0) tma_store_wait_read();     // the tile must stay intact until the stores have read it
+      } else {
+        epilogue_row_staged(p, tmem + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, smem, [](int) {});
+      }
     }
-    fence_async_smem();                                     // generic-proxy tile writes -> visible to the TMA store
-    asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
-    if (staged && tid == 64) {
-      const int sub_cols = (p.epilogue == 0) ? 32 : 64;     // columns per 128-byte sub-tile row (fp32 / bf16)
-      for (int j = 0; j * sub_cols < n_tile; ++j) tma_store_2d(&map_y, smem + j * (BM * 128), n0 + j * sub_cols, m0);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      tma_store_wait_read();                                // the tile must stay intact until the stores have read it
+    if (!pipelined) {
+      fence_async_smem();                                   // generic-proxy tile writes -> visible to the TMA store
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // the eight epilogue warps
+      if (staged && tid == 64) {
+        for (int j = 0; j * sub_cols < n_tile; ++j) tma_store_2d(&map_y, smem + j * (BM * 128), n0 + j * sub_cols, m0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        tma_store_wait_read();
+      }
     }
   }
   tc_fence_before();
