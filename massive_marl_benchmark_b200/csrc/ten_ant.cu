@@ -1,18 +1,22 @@
-// ten_ant.cu - fused TenAnt env-step kernel for sm_100a.
+// ten_ant.cu - fused TenAnt env-step kernels for sm_100a.
 //
-// One CTA = one tile of EPT environments of one frame t (grid = tiles x T): every (tile, t) unit is
-// independent because the carry of step t (pos_before / goal_before) is a pure function of frame
-// t-1, so the horizon-batched launch exposes T*N*10 ant-threads instead of N*10.
-// The only sequential-in-t state, progress_buf / reset_buf, is a 1-byte-per-env-step chain that
-// does not feed obs or reward; it is resolved inline when T == 1 and by ten_ant_chain_kernel
-// otherwise.
+// One CTA = one tile of 16 environments of one frame t (grid = tiles x T): every (tile, t) unit is independent because
+// the carry of step t (pos_before / goal_before) is a pure function of frame t-1, so the horizon-batched
+// launch exposes T*N*10 ant-sized work items instead of N*10.  The only sequential-in-t state, progress_buf / reset_buf,
+// is a 1-byte-per-env-step chain that does not feed obs or reward: inline when T == 1; for T <= 32 one data-carrying
+// 64-bit add per (env, frame), executed by the unit of the last frame (finish_env); ten_ant_post_kernel otherwise.
+//
+// Two kernels compute the same thing bit for bit (tests/test_gpu_ten_ant.py):
+//   ten_ant_split_kernel  default: 352 threads in three warp-uniform roles (core / dof / box), see its header below
+//   ten_ant_kernel        one thread per ant (MMB_TEN_ANT_VARIANT=mono), the first version, kept as the simple statement
 //
 // Data movement per unit (all contiguous because the Isaac layout is env-major):
-//   root tile   EPT*143 floats  global -> smem, 128-bit loads (rows are 52 B: not vector-addressable per ant)
-//   dof         16 floats per ant thread, 4 x LDG.128, consecutive threads -> consecutive 64 B
-//   actions      8 floats per ant thread, 2 x LDG.128
-//   obs tile    EPT*388 floats  smem -> global, 128-bit stores (clamped and/or raw)
-//   forces       8 floats per ant thread, 2 x STG.128
+//   root tile   16*143 floats  global -> smem, one 1-D TMA bulk copy + mbarrier (rows are 52 B: not vector-addressable)
+//   dof         16 floats per ant, 4 x LDG.128 by the ant's dof thread, consecutive threads -> consecutive 64 B
+//   actions      8 floats per ant, 2 x LDG.128
+//   obs tile    16*388 floats  smem -> global, one TMA bulk store (plus clamped / per-agent copies when requested)
+//   forces       8 floats per ant, 2 x STG.128
+//   the inputs of the unit 1.5 x SMs CTAs ahead in launch order are pulled into L2 by cp.async.bulk.prefetch.L2
 // Arithmetic: mmb_math.cuh (IEEE round-to-nearest per op in the reference's order).
 //
 // Replaces: ten_ant.py:886-891 (forces), :712-808 + jit :1304-1393 (observations, box goals),
@@ -562,14 +566,17 @@ __global__ void __launch_bounds__(EPT* A, (EPT == 32) ? 3 : 6) ten_ant_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Role-split variant (default): the per-ant work is a ~1,250-instruction dependent fp32 chain, so the kernel is
-// latency-bound, not DRAM- or issue-bound (ncu: 52 % issue utilisation at 30 resident warps per SM).  Splitting each
-// ant over TWO threads of different warps halves the chain and the registers per thread:
-//   core warps 0-4  (one thread per ant): root row -> ant_core -> obs[0:14]; after the box barrier the goal terms
-//   dof  warps 5-9  (one thread per ant): dof/actions rows -> unscale, clamps, forces, obs[14:38], energy terms;
-//                   warp 5 / warp 6 additionally derive the goal direction of frame t / t-1 while the core warps
-//                   are busy, which takes the box phase off the critical path.
-// CTA = 16 envs x 1 frame = 320 threads, grid = (tiles, T).
+// Role-split variant (default).  The per-ant work is a ~1,250-instruction dependent fp32 chain, so the one-thread-per-ant
+// kernel is latency-bound, not DRAM- or issue-bound (ncu: 52 % issue utilisation at 30 resident warps per SM).  Here the
+// work of a tile is spread over three warp-uniform roles, 40 registers per thread, 4 CTAs = 44 warps per SM:
+//   core warps 0-4  (one thread per ant): root row -> ant_core -> obs[0:14]; after the box barrier the ant-distance term
+//   dof  warps 5-9  (one thread per ant): dof / action rows -> unscale, clamps, forces, energy terms -> obs[14:38]; after
+//                   the box barrier the goal-distance term; warp 7 also the box-orientation term and the obs tail;
+//                   16 lanes of warp 5 do the ordered 10-ant sums, the reward and the chain report (finish_env)
+//   box  warp 10    goal direction of frame t (lanes 0-15) and of frame t-1 (lanes 16-31): the two ~150-instruction
+//                   fdiv -> atanf -> sinf / cosf chains side by side, fed straight from L2
+// What the per-CTA %globaltimer timeline (MMB_TRACE) showed on the way here is in DESIGN.md section 4.
+// CTA = 16 envs x 1 frame = 352 threads, grid = (tiles, T).
 // ------------------------------------------------------------------------------------------------------
 // Optional per-CTA phase timeline (build with `make EXTRA=-DMMB_TRACE`, read with tools/probe/ten_ant_timeline.py): %globaltimer
 // stamps of a few CTAs of frame 5.  Compiled out of the normal library.
