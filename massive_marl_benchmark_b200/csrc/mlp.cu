@@ -12,18 +12,26 @@
 //   accumulate fp32 in TMEM (128 lanes x up to 512 columns per CTA)
 //   epilogue   fp32: bias, ELU, optional LayerNorm over the full row (one thread owns one row after tcgen05.ld),
 //              output bf16 (next layer's operand) or fp32 (last layer)
-// CTA = 128 rows x n_tile columns (n_tile <= 512), 128 threads.  K is walked in blocks of 64 (= one 128-byte
-// swizzle row of bf16); a 2-stage shared-memory ring lets the tensor core work on block k while the threads
-// stage block k+1.  Shared-memory tiles use the canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms,
-// 16-byte chunk index XOR row%8), described to the tensor core by 64-bit matrix descriptors; a single thread
-// issues tcgen05.mma and tcgen05.commit arrives on an mbarrier when the stage may be overwritten.
+// CTA = 128 rows x n_tile columns (n_tile <= 512).  K is walked in blocks of 64 (= one 128-byte swizzle row of bf16)
+// through a shared-memory ring of up to 8 stages.  Shared-memory tiles use the canonical K-major SWIZZLE_128B layout
+// (8-row x 128-byte atoms, 16-byte chunk index XOR row%8), described to the tensor core by 64-bit matrix descriptors; a
+// single thread issues tcgen05.mma, and tcgen05.commit arrives on an mbarrier when a stage may be overwritten.
 //
-// Two kernels share the descriptors and the epilogue:
-//   mlp_layer_ws_kernel (default)  warp-specialised: warp 0 = TMA producer (2-D tensor maps, SWIZZLE_128B boxes, one
-//                                  elected lane), warp 1 = tcgen05.mma issuer + TMEM owner, warps 2-5 = epilogue
-//                                  (TMEM lane quarter = warp % 4).  full/empty mbarrier ring between producer and MMA,
-//                                  tcgen05.commit frees a stage and finally publishes the accumulator.
-//   mlp_layer_kernel (MMB_MLP_VARIANT=legacy)  first version: all threads stage tiles with cp.async, barrier per k-block.
+// Kernels (they share the descriptors and the epilogue math):
+//   mlp_layer_ws_kernel (default)  warp-specialised, 320 threads: warp 0 = TMA producer (2-D tensor maps, SWIZZLE_128B
+//       boxes, one elected lane), warp 1 = tcgen05.mma issuer + TMEM owner, warps 2-9 = epilogue (TMEM lane quarter =
+//       warp % 4, two warps per quarter split the columns).  full / empty mbarrier ring between producer and MMA;
+//       tcgen05.commit frees a stage and finally publishes the accumulator.  Epilogue: tcgen05.ld -> bias / ELU
+//       (ex2.approx) / LayerNorm in fp32 -> output tile staged in the drained operand ring in the TMA swizzle -> 2-D TMA
+//       stores, each finished 128-byte-wide sub-tile handed over while the next is computed.  With overlap_prev the launch
+//       is programmatic-dependent: prologue and the first ring of WEIGHT tiles run while the previous layer drains, only
+//       the activation loads wait for it.  Optional modes, measured and off by default:
+//       MMB_MLP_CLUSTER = 2 / 4 (weight tile multicast across a cluster), MMB_MLP_PAIR = 1 (cta_group::2).
+//   mlp_layer_ws_pair_kernel       the cta_group::2 instantiation (a kernel containing cta_group::2 instructions can only
+//       be launched as a cluster, hence its own entry)
+//   mlp_layer_ws_group_kernel      grid z = one of up to 16 independent problems of identical geometry (per-agent nets)
+//   mlp_layer_kernel (MMB_MLP_VARIANT=legacy)  first version: all threads stage tiles with cp.async, barrier per k-block
+//   ln_cast_kernel / ln_cast_group_kernel      fp32 input -> optional LayerNorm -> bf16 zero-padded first operand
 #include <cuda.h>
 #include <cuda_bf16.h>
 

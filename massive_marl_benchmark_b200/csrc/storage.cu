@@ -5,12 +5,12 @@
 // Replaces agents/algorithms/rl/ppo/storage.py:32-73, agents/algorithms/marl/utils/separated_buffer.py:
 // 124-168, popart.py:64-75 (denormalize), mappo_trainer.py:189-199, runner.py:229-255.
 //
-// GAE is sequential in t and embarrassingly parallel over envs: one thread per env (or (env, agent)),
-// the [T][N] planes are read as fully coalesced rows, the recurrence is evaluated in the reference's
-// exact op order (bit-identical `returns`), loads of a chunk of steps are issued before the dependent
-// chain so a thread keeps 3 x CHUNK requests in flight.  Sum and sum of squares of the raw advantages
-// are accumulated in fp64 (thread -> warp shuffle -> one atomic per CTA); the caller can all-reduce the
-// three doubles across env shards before mmb_adv_normalize.
+// GAE is sequential in t and embarrassingly parallel over envs; the recurrence is evaluated in the reference's exact op
+// order (bit-identical `returns`).  Small rollouts: one thread per env, all T loads issued before the dependent chain.
+// From 8192 envs: four consecutive envs per thread with 128-bit accesses, two [t] rows in flight - few, wide, page-sized
+// row streams instead of 80 narrow ones (0.42 -> 0.96 of HBM peak at 64 M transitions).  Sum and sum of squares of the raw
+// advantages are accumulated in fp64 (thread -> warp shuffle -> one atomic per CTA of a capped grid).  Env-sharded
+// multi-GPU: mmb_adv_normalize_xchg exchanges the three doubles over NVLink peer memory inside the normalise kernel.
 #include "../../include/mmb.h"
 #include "mmb_common.cuh"
 #include "mmb_math.cuh"
