@@ -9,8 +9,9 @@ Covers the forward passes on the rollout path (SURVEY.md section 8a rows a18 / a
         LayerNorm(in) [Linear ELU LayerNorm] x3 Linear(512, 8|1)
 
 Weights are taken from the reference's own modules / checkpoints (`from_sequential`, `from_marl_state_dict`), cast
-once to bf16 and zero-padded to the kernel's tile multiples; sampling, log-probs and the distribution quirks
-(PPO's sigma^2 scale_tril, module.py:76-77) stay in PyTorch on top of the returned means / values.
+once to bf16 and zero-padded to the kernel's tile multiples.  On top of the means / values: `gaussian_act` (sampling and
+log-probs in one launch, incl. PPO's sigma^2 scale_tril quirk, module.py:76-77), `PPOActorCriticForward` (actor and critic
+as one grouped launch per layer), `GroupedMLP` / `MarlTeamForward` (all agents' networks in one launch per layer).
 Numerics: bf16 operands, fp32 accumulation and fp32 bias / ELU / LayerNorm; the reference is fp32 SGEMM, so
 outputs agree to bf16 operand precision (tests/test_gpu_mlp.py states the tolerances).
 """
