@@ -351,15 +351,15 @@ __device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint
 // touched 32 different sectors.  Out-of-range rows / columns are clipped by the tensor map; columns in [N, y_stride)
 // of a bf16 activation buffer are written as zeros (they are the K padding of the next layer).
 template <bool F32>
-__device__ __forceinline__ void stage_out32(uint8_t* tile, int row, int c0, const float* x) {
+__device__ __forceinline__ void stage_out32(uint8_t* tile, int row, int c0, const float* x, int sub_stride = BM * 128) {
   // bf16: 64 columns per 128-byte sub-tile row, this group = 4 chunks; fp32: 32 columns per sub-tile row = 8 chunks
   if (F32) {
-    uint8_t* sub = tile + (c0 >> 5) * (BM * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+    uint8_t* sub = tile + (c0 >> 5) * sub_stride + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
       *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
   } else {
-    uint8_t* sub = tile + (c0 >> 6) * (BM * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+    uint8_t* sub = tile + (c0 >> 6) * sub_stride + (row >> 3) * 1024 + (row & 7) * 128;
     const int cbase = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group inside the 128-byte row
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -378,7 +378,7 @@ __device__ __forceinline__ void stage_out32(uint8_t* tile, int row, int c0, cons
 // rows has been staged: the kernel uses it to hand finished sub-tiles to the TMA store while the next ones are computed.
 template <class Flush>
 __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& p, uint32_t taddr, int row, int n0, int n_tile,
-                                                    int cb, int ce, uint8_t* tile, Flush flush) {
+                                                    int cb, int ce, uint8_t* tile, Flush flush, int sub_stride = BM * 128) {
   const int sub_cols = (p.epilogue == 0) ? 32 : 64;
   float v[32], bv[32], x[32];
   if (p.epilogue == 2) {  // bias + ELU + LayerNorm over the whole row (n_tile == N): two passes over TMEM
@@ -404,7 +404,7 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
       load_bias32(p.ln_beta + n0 + c0, b);
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = (elu1(v[i] + bv[i]) - mean) * rstd * g[i] + b[i];
-      stage_out32<false>(tile, row, c0, x);
+      stage_out32<false>(tile, row, c0, x, sub_stride);
       if ((c0 + 32) % sub_cols == 0 || c0 + 32 >= n_tile) flush(c0 / sub_cols);
     }
     return;
@@ -421,11 +421,11 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
     if (p.epilogue == 1) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = (n + i < p.N) ? elu1(v[i] + bv[i]) : 0.0f;
-      stage_out32<false>(tile, row, c0, x);
+      stage_out32<false>(tile, row, c0, x, sub_stride);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = v[i] + bv[i];
-      stage_out32<true>(tile, row, c0, x);
+      stage_out32<true>(tile, row, c0, x, sub_stride);
     }
     if ((c0 + 32) % sub_cols == 0 || c0 + 32 >= ce) flush(c0 / sub_cols);
   }
@@ -634,6 +634,122 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_pair_kernel(const 
                                                                           const __grid_constant__ CUtensorMap map_w,
                                                                           const __grid_constant__ CUtensorMap map_y) {
   mlp_layer_ws_body<true>(p, map_x, map_w, map_y);
+}
+
+// Persistent variant for launches with more tiles than SMs (large batches): one CTA per SM walks tiles m-major, the operand
+// ring runs on across tiles, and TWO accumulators in tensor memory (2 x n_tile <= 512 columns) let the epilogue of tile i
+// (TMEM -> bias / ELU -> staged sub-tiles -> TMA stores) overlap the k-loop of tile i + 1.  Output staging is two 16 KB
+// sub-tile buffers (one per column half) outside the ring.  n_tile <= 256, no LayerNorm epilogue, TMA-addressable output.
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_kernel(const __grid_constant__ mmb_mlp_layer_params p,
+                                                                             const __grid_constant__ CUtensorMap map_x,
+                                                                             const __grid_constant__ CUtensorMap map_w,
+                                                                             const __grid_constant__ CUtensorMap map_y) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = p.n_tile;
+  const int stage_bytes = A_STAGE_BYTES + n_tile * BK * 2;
+  const int S = p.stages;
+  const int nkb = p.Kpad / BK;
+  const int tiles_n = p.Npad / n_tile, tiles_m = p.Mpad / BM, num_tiles = tiles_m * tiles_n;
+  uint8_t* out_buf = smem + S * stage_bytes;          // 2 x 16 KB, 1024-byte aligned (stage_bytes is a multiple of 1024)
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }   // 8 epilogue warps release an accumulator
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (p.overlap_prev) griddep_launch_dependents();
+
+  if (warp == 0) {
+    // ===== TMA producer: the ring position runs on across tiles =====
+    if (elect_one()) {
+      if (p.overlap_prev) griddep_wait();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * n_tile;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S, u = it / S;
+          if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
+          uint8_t* st = smem + s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          tma_load_2d(st, &map_x, kb * BK, m0, &full_bar[s]);
+          tma_load_2d(st + A_STAGE_BYTES, &map_w, kb * BK, n0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator i & 1 =====
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(n_tile);
+      int it = 0, i = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        const int acc = i & 1, use = i >> 1;
+        if (use > 0) mbar_wait(&acc_empty[acc], (uint32_t)((use - 1) & 1));   // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem + (uint32_t)(acc * n_tile);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S, u = it / S;
+          mbar_wait(&full_bar[s], (uint32_t)(u & 1));
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes), b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j)
+            umma_bf16(tacc, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int sub_cols = (p.epilogue == 0) ? 32 : 64;
+    const int mid = n_tile / 2;                         // host guarantees: mid is a multiple of sub_cols
+    const int cb = half ? mid : 0, ce = half ? n_tile : mid;
+    uint8_t* buf = out_buf + half * (BM * 128);
+    int i = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * n_tile;
+      const int acc = i & 1, use = i >> 1;
+      mbar_wait(&acc_full[acc], (uint32_t)(use & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * n_tile);
+      // every finished sub-tile goes out through this half's staging buffer: staged -> barrier -> one lane stores and waits
+      // until the TMA has read the buffer -> barrier -> the buffer is free for the next sub-tile
+      epilogue_row_staged(p, taddr, row, n0, n_tile, cb, ce, buf - (cb / sub_cols) * 0, [&](int j) {
+        fence_async_smem();
+        if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (q == 0 && lane == 0) {
+          tma_store_2d(&map_y, buf, n0 + j * sub_cols, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          tma_store_wait_read();
+        }
+        if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+      }, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 // Grouped launch: blockIdx.z selects one of up to MMB_MAX_GROUP independent problems of identical geometry (the ten
@@ -905,6 +1021,19 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
     if (st > MAX_STAGES) st = MAX_STAGES;
     p.stages = st;
   }
+  // persistent, epilogue-overlapped variant: only worth it when a CTA gets more than one tile
+  static const int persist_pref = [] { const char* v = getenv("MMB_MLP_PERSIST"); return v ? atoi(v) : 1; }();
+  const int num_tiles = (p.Mpad / BM) * (p.Npad / p.n_tile);
+  const bool y_tma = (p.epilogue == 0) ? (((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0) : (p.n_tile % 64 == 0);
+  const int sub_cols_h = (p.epilogue == 0) ? 32 : 64;
+  const bool persist = persist_pref && !pair && cm == 1 && p.epilogue != 2 && p.n_tile <= 256 && y_tma && num_tiles >= 2 * 148 &&
+                       (p.n_tile / 2) % sub_cols_h == 0;
+  if (persist) {
+    const int sb = A_STAGE_BYTES + p.n_tile * BK * 2;
+    int st = (SMEM_BUDGET + 24 * 1024 - 2 * BM * 128) / sb;      // ring + two 16 KB staging buffers within 224 KB
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    p.stages = st;
+  }
   CUtensorMap map_x, map_w, map_y;
   if (!make_map_bf16_2d(&map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
       !make_map_bf16_2d(&map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)((p.n_tile > 256 ? 256 : p.n_tile) / cm)))   // pair: cm == 2
@@ -947,8 +1076,23 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
       if (cudaFuncSetAttribute(mlp_layer_ws_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess) return MMB_ECUDA;
       pair_attr_done[dev] = true;
     }
-    const cudaError_t le = pair ? cudaLaunchKernelEx(&cfg, mlp_layer_ws_pair_kernel, p, map_x, map_w, map_y)
-                                : cudaLaunchKernelEx(&cfg, mlp_layer_ws_kernel, p, map_x, map_w, map_y);
+    cudaError_t le;
+    if (persist) {
+      static bool persist_attr_done[MMB_MAX_DEVICES] = {};
+      const int psmem = p.stages * (A_STAGE_BYTES + p.n_tile * BK * 2) + 2 * BM * 128;
+      if (!persist_attr_done[dev]) {
+        if (cudaFuncSetAttribute(mlp_layer_ws_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return MMB_ECUDA;
+        persist_attr_done[dev] = true;
+      }
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cfg.gridDim = dim3(num_tiles < sms ? num_tiles : sms);
+      cfg.dynamicSmemBytes = psmem;
+      le = cudaLaunchKernelEx(&cfg, mlp_layer_ws_persist_kernel, p, map_x, map_w, map_y);
+    } else {
+      le = pair ? cudaLaunchKernelEx(&cfg, mlp_layer_ws_pair_kernel, p, map_x, map_w, map_y)
+                : cudaLaunchKernelEx(&cfg, mlp_layer_ws_kernel, p, map_x, map_w, map_y);
+    }
     if (le != cudaSuccess) {
       if (getenv("MMB_DEBUG")) fprintf(stderr, "mmb_mlp_layer: launch failed: %s (cluster %d, pair %d, smem %d)\n", cudaGetErrorString(le), cm, (int)pair, smem);
       (void)cudaGetLastError();

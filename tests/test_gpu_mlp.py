@@ -253,3 +253,25 @@ def test_gaussian_act_kernel(cuda_device):
     assert abs(float((zz ** 3).mean())) < 0.03 and abs(float((zz ** 4).mean()) - 3.0) < 0.1     # skewness, kurtosis
     rows = zz[:, :40].reshape(-1); nxt = zz[:, 1:41].reshape(-1)
     assert abs(float((rows * nxt).mean())) < 0.01                                                  # neighbours uncorrelated
+
+
+def test_large_batch_takes_persistent_kernel_and_matches_row_blocks(cuda_device):
+    """At M = 16384 + 100 a layer has more tiles than SMs and runs on the persistent, epilogue-overlapped kernel (two
+    accumulators in tensor memory).  A row's result does not depend on the batch it is in (same K order, same epilogue),
+    so the large-batch output must equal, bit for bit, the outputs of the same rows pushed through in blocks of 4096
+    (which take the one-tile-per-CTA kernel) - and agree with torch fp32 to bf16 operand precision."""
+    from massive_marl_benchmark_b200.mlp import FusedMLP
+    dev = cuda_device
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator().manual_seed(123)
+    net = _ppo_net(388, [1024, 1024, 512], 80, 0.5, gen).to(dev)
+    M = 16384 + 100
+    x = torch.clamp(torch.randn(M, 388, generator=gen) * 2.0, -5, 5).to(dev)
+    fused = FusedMLP.from_sequential(net, dev)
+    y = fused(x).clone()
+    y2 = fused(x).clone()                      # accumulators / barriers are reusable across launches
+    blocks = torch.cat([fused(x[i:i + 4096]).clone() for i in range(0, M, 4096)])
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2) and torch.equal(y, blocks)
+    with torch.no_grad():
+        assert _rowmax_err(y, net(x)) <= 3e-2
