@@ -60,7 +60,7 @@ MMB_API uint64_t mmb_launch_count(void);
  * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
 enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
        MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
-       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_GAUSS_ACT, MMB_K_COUNT };
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_GAUSS_ACT, MMB_K_PPO_LOSS, MMB_K_COUNT };
 MMB_API int32_t mmb_profile_enable(int32_t on);
 MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
 
@@ -352,6 +352,42 @@ typedef struct {
   float* logp_per_dim;                     /* [rows][act_dim] (MARL), or NULL */
 } mmb_gaussian_act_params;
 MMB_API int32_t mmb_gaussian_act(const mmb_gaussian_act_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* PPO minibatch loss, forward + backward in one launch:               */
+/*   ActorCritic.evaluate's distribution part   agents/algorithms/rl/ppo/module.py:95-99,107      */
+/*     (MultivariateNormal(mean, scale_tril = diag(exp(log_std)^2)): log_prob, entropy)           */
+/*   PPO.update                                 agents/algorithms/rl/ppo/ppo.py:270-302           */
+/*     (adaptive-KL estimate, ratio / clipped surrogate, (clipped) value loss, total loss)        */
+/* Inputs are what the two MLPs hand over (mean [B][A], value [B]) and the gathered minibatch     */
+/* rows; outputs are the scalar sums and the gradients of                                         */
+/*   loss = mean(surrogate) + value_loss_coef * mean(value loss) - entropy_coef * mean(entropy)   */
+/* with respect to mean, value and log_std, following torch's autograd rules (max: gradient split */
+/* evenly on exact ties; clamp: passes on the closed interval).  `sums` (4 + act_dim doubles,     */
+/* zeroed by the caller) receives {sum surrogate, sum value loss, sum kl, entropy} and then       */
+/* d loss / d log_std[j].  ratio_lo / ratio_hi = (float)(1.0 -/+ clip_param) as the reference's   */
+/* double-precision Python scalars round.  act_dim <= 256.                                        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_rows, act_dim, use_clipped_value_loss, _pad;
+  const float* mu; int64_t mu_stride;      /* new action mean [B][A], row stride in elements */
+  const float* log_std;                    /* [A] */
+  const float* actions;                    /* [B][A] */
+  const float* old_logp;                   /* [B] */
+  const float* advantages;                 /* [B] */
+  const float* value;                      /* [B] new value */
+  const float* target_values;              /* [B] value at rollout time (clipped value loss), may be NULL otherwise */
+  const float* returns;                    /* [B] */
+  const float* old_mu;                     /* [B][A] or NULL (no KL estimate) */
+  const float* old_sigma;                  /* [B][A] log-std rows stored at rollout time, or NULL */
+  float clip_param, ratio_lo, ratio_hi, value_loss_coef, entropy_coef;
+  float k_log_2pi;                         /* set by the library: (float)(act_dim * log(2 pi)) */
+  float* logp;                             /* [B] new log-probabilities, or NULL */
+  float* grad_mu;                          /* [B][A] d loss / d mean, or NULL */
+  float* grad_value;                       /* [B] d loss / d value, or NULL */
+  double* sums;                            /* [4 + A], zeroed by the caller */
+} mmb_ppo_loss_params;
+MMB_API int32_t mmb_ppo_loss(const mmb_ppo_loss_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Episode bookkeeping of the PPO runner (agents/algorithms/rl/ppo/ppo.py:143-157,198-220): running */

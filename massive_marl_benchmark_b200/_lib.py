@@ -119,6 +119,14 @@ class GaussianActParams(C.Structure):
                 ("actions", c_vp), ("logp_sum", c_vp), ("logp_per_dim", c_vp)]
 
 
+class PpoLossParams(C.Structure):
+    _fields_ = [("num_rows", c_i32), ("act_dim", c_i32), ("use_clipped_value_loss", c_i32), ("_pad", c_i32),
+                ("mu", c_vp), ("mu_stride", c_i64), ("log_std", c_vp), ("actions", c_vp), ("old_logp", c_vp),
+                ("advantages", c_vp), ("value", c_vp), ("target_values", c_vp), ("returns", c_vp), ("old_mu", c_vp),
+                ("old_sigma", c_vp), ("clip_param", c_f), ("ratio_lo", c_f), ("ratio_hi", c_f), ("value_loss_coef", c_f),
+                ("entropy_coef", c_f), ("k_log_2pi", c_f), ("logp", c_vp), ("grad_mu", c_vp), ("grad_value", c_vp), ("sums", c_vp)]
+
+
 class GaeMarlParams(C.Structure):
     _fields_ = [
         ("num_envs", c_i32), ("num_steps", c_i32), ("num_agents", c_i32),
@@ -170,6 +178,7 @@ SYMBOLS = {
     "mmb_xchg_free": (c_i32, [c_vp]),
     "mmb_rollout_statistics": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mmb_gaussian_act": (c_i32, [C.POINTER(GaussianActParams), c_vp]),
+    "mmb_ppo_loss": (c_i32, [C.POINTER(PpoLossParams), c_vp]),
     "mmb_episode_update": (c_i32, [C.POINTER(EpisodeParams), c_vp]),
     "mmb_gae_marl": (c_i32, [C.POINTER(GaeMarlParams), c_vp]),
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
@@ -225,7 +234,7 @@ def launch_count():
 
 KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
               "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm", "mlp_layer",
-              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring", "gauss_act")
+              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring", "gauss_act", "ppo_loss")
 
 
 def profile_enable(on=True):

@@ -1,0 +1,204 @@
+// loss.cu - the PPO minibatch loss (forward value + the gradients autograd would produce) in one launch.
+//
+// Replaces, after the two MLPs have produced the action mean and the value of a minibatch
+// (agents/algorithms/rl/ppo/ppo.py:266-302, module.py:92-107):
+//   MultivariateNormal(mean, scale_tril = diag(exp(log_std)^2)).log_prob / .entropy   (effective std = sigma^2)
+//   the adaptive-schedule KL estimate (ppo.py:271-275)
+//   ratio / clipped surrogate (ppo.py:286-290), clipped value loss (ppo.py:293-300), total loss (ppo.py:302)
+// and their backward pass down to d loss / d mean, d loss / d log_std and d loss / d value - about forty elementwise /
+// reduction kernels in torch.  HBM-bound: 5 rows of A floats per sample (mean, actions, old mean, old sigma in, mean
+// gradient out) + 6 scalars.  Gradient rules follow torch's: `max(a, b)` splits the gradient evenly on exact ties,
+// `clamp` passes it on the closed interval.
+#include "../../include/mmb.h"
+#include "mmb_common.cuh"
+#include "mmb_math.cuh"
+
+namespace mmb {
+namespace {
+
+constexpr int LOSS_THREADS = 256;
+constexpr int LOSS_MAX_K = 8;           // columns per lane: act_dim <= 32 * 8
+constexpr float LOG_2PI = 1.8378770664093453f;
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// G lanes per minibatch row (8 / 16 / 32 by action width); lane `sub` owns the columns sub, sub + G, ...
+template <int G, int KMAX>
+__global__ void __launch_bounds__(LOSS_THREADS) ppo_loss_kernel(const __grid_constant__ mmb_ppo_loss_params p) {
+  __shared__ double s_gls[32 * LOSS_MAX_K];
+  __shared__ double s_sum[3];
+  const int A = p.act_dim, B = p.num_rows;
+  const int tid = threadIdx.x, sub = tid % G;
+  for (int j = tid; j < A; j += LOSS_THREADS) s_gls[j] = 0.0;
+  if (tid < 3) s_sum[tid] = 0.0;
+  __syncthreads();
+
+  // per-column constants of the new policy
+  float ls[KMAX], sd[KMAX], two_var[KMAX], gls[KMAX];
+  float hld_part = 0.0f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = sub + k * G;
+    gls[k] = 0.0f;
+    if (j < A) {
+      ls[k] = __ldg(p.log_std + j);
+      const float e = expf(ls[k]);
+      sd[k] = e * e;                     // module.py:95: diag(exp(log_std) * exp(log_std)) used as scale_tril
+      two_var[k] = 2.0f * (e * e);       // ppo.py:273: 2.0 * square(sigma.exp())
+      hld_part += logf(sd[k]);
+    } else {
+      ls[k] = 0.0f; sd[k] = 1.0f; two_var[k] = 1.0f;
+    }
+  }
+  const float half_log_det = group_sum<G>(hld_part);
+  const float inv_b = 1.0f / (float)B;
+
+  double acc_s = 0.0, acc_v = 0.0, acc_kl = 0.0;
+  const int rows_per_block = LOSS_THREADS / G;
+  // warp-uniform trip count (the group reductions below shuffle with the full mask); rows past the end are predicated off
+  for (int base = blockIdx.x * rows_per_block; base < B; base += gridDim.x * rows_per_block) {
+    const int row = base + tid / G;
+    const bool live = row < B;
+    const int A_live = live ? A : 0;
+    const float* mu = p.mu + (int64_t)row * p.mu_stride;
+    const float* act = p.actions + (int64_t)row * A;
+    float z[KMAX];
+    float maha = 0.0f, kl = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int j = sub + k * G;
+      z[k] = 0.0f;
+      if (j < A_live) {
+        const float m = __ldg(mu + j);
+        z[k] = (__ldg(act + j) - m) / sd[k];
+        maha = __fadd_rn(maha, __fmul_rn(z[k], z[k]));       // pow(2) then sum, as torch rounds them (no FMA contraction)
+        if (p.old_mu) {
+          const float om = __ldcs(p.old_mu + (int64_t)row * A + j), os = __ldcs(p.old_sigma + (int64_t)row * A + j);
+          const float eo = expf(os), d = om - m;
+          // every term is a difference of O(1) numbers: keep the reference's rounding sequence (products rounded before the add)
+          const float t = __fadd_rn(__fadd_rn(ls[k], -os), __fdiv_rn(__fadd_rn(__fmul_rn(eo, eo), __fmul_rn(d, d)), two_var[k]));
+          kl = __fadd_rn(kl, __fadd_rn(t, -0.5f));
+        }
+      }
+    }
+    maha = group_sum<G>(maha);
+    if (p.old_mu) kl = group_sum<G>(kl);
+    const float logp = __fadd_rn(__fmul_rn(-0.5f, __fadd_rn(p.k_log_2pi, maha)), -half_log_det);
+
+    // surrogate (ppo.py:286-290)
+    const float adv = live ? __ldg(p.advantages + row) : 0.0f;
+    const float ratio = expf(logp - (live ? __ldg(p.old_logp + row) : 0.0f));
+    const float clamped = fminf(fmaxf(ratio, p.ratio_lo), p.ratio_hi);
+    const float surr = -adv * ratio, surr_c = -adv * clamped;
+    const bool inside = ratio >= p.ratio_lo && ratio <= p.ratio_hi;
+    const float d_ratio = -adv * ratio;                 // d surr / d logp; also d surr_c / d logp where the clamp passes
+    float g;
+    if (surr > surr_c) g = d_ratio;
+    else if (surr == surr_c) g = 0.5f * d_ratio + (inside ? 0.5f * d_ratio : 0.0f);
+    else g = inside ? d_ratio : 0.0f;
+    g = live ? g * inv_b : 0.0f;          // (a dead row's ratio may overflow: keep 0 * inf out of the column sums)
+
+    if (p.grad_mu) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int j = sub + k * G;
+        if (j < A_live) __stcs(p.grad_mu + (int64_t)row * A + j, g * (z[k] / sd[k]));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) gls[k] += g * (2.0f * z[k] * z[k] - 2.0f);   // d logp / d log_std = 2 z^2 - 2
+
+    if (sub == 0 && live) {
+      // value loss (ppo.py:293-300)
+      const float v = __ldg(p.value + row), ret = __ldg(p.returns + row);
+      float lv, gv;
+      if (p.use_clipped_value_loss) {
+        const float tv = __ldg(p.target_values + row);
+        const float d = v - tv;
+        const float dc = fminf(fmaxf(d, -p.clip_param), p.clip_param);
+        const float vc = tv + dc;
+        const float e1 = v - ret, e2 = vc - ret;
+        const float l1 = e1 * e1, l2 = e2 * e2;
+        const bool in_v = d >= -p.clip_param && d <= p.clip_param;
+        const float g1 = 2.0f * e1, g2 = in_v ? 2.0f * e2 : 0.0f;
+        lv = fmaxf(l1, l2);
+        gv = l1 > l2 ? g1 : (l1 == l2 ? 0.5f * g1 + 0.5f * g2 : g2);
+      } else {
+        const float e = ret - v;
+        lv = e * e;
+        gv = -2.0f * e;
+      }
+      if (p.grad_value) p.grad_value[row] = p.value_loss_coef * gv * inv_b;
+      if (p.logp) p.logp[row] = logp;
+      acc_s += (double)fmaxf(surr, surr_c);
+      acc_v += (double)lv;
+      acc_kl += (double)kl;
+    }
+  }
+
+  // block totals, then one double atomic per slot per block
+  if (sub == 0) {
+    atomicAdd(&s_sum[0], acc_s); atomicAdd(&s_sum[1], acc_v); atomicAdd(&s_sum[2], acc_kl);
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = sub + k * G;
+    if (j < A) atomicAdd(&s_gls[j], (double)gls[k]);
+  }
+  __syncthreads();
+  if (tid < 3) atomicAdd(p.sums + tid, s_sum[tid]);
+  for (int j = tid; j < A; j += LOSS_THREADS) {
+    double v = s_gls[j];
+    if (blockIdx.x == 0) v -= 2.0 * (double)p.entropy_coef;     // entropy = const + sum_j 2 log_std_j, equal on every row
+    atomicAdd(p.sums + 4 + j, v);
+  }
+  if (blockIdx.x == 0 && tid == 0) p.sums[3] = 0.5 * (double)A * (1.0 + (double)LOG_2PI) + (double)half_log_det;
+}
+
+template <int G>
+cudaError_t launch_loss(const mmb_ppo_loss_params& p, int kmax, int grid, cudaStream_t st) {
+  if (G < 32) {                          // narrow groups cover the whole row with one column per lane
+    ppo_loss_kernel<G, 1><<<grid, LOSS_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+  }
+  switch (kmax) {
+    case 1: ppo_loss_kernel<32, 1><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    case 2: ppo_loss_kernel<32, 2><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    case 3: ppo_loss_kernel<32, 3><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    case 4: ppo_loss_kernel<32, 4><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    default: ppo_loss_kernel<32, LOSS_MAX_K><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int32_t mmb_ppo_loss(const mmb_ppo_loss_params* pp, void* stream) {
+  if (!pp) return MMB_EINVAL;
+  mmb_ppo_loss_params p = *pp;
+  if (p.num_rows <= 0 || p.act_dim <= 0 || p.act_dim > 32 * LOSS_MAX_K || p.mu_stride < p.act_dim) return MMB_EINVAL;
+  if (!p.mu || !p.log_std || !p.actions || !p.old_logp || !p.advantages || !p.value || !p.returns || !p.sums) return MMB_EINVAL;
+  if (p.use_clipped_value_loss && !p.target_values) return MMB_EINVAL;
+  if ((p.old_mu == nullptr) != (p.old_sigma == nullptr)) return MMB_EINVAL;
+  p.k_log_2pi = (float)((double)p.act_dim * 1.8378770664093453);   // torch: the Python double k * log(2 pi), then cast
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = p.act_dim <= 8 ? 8 : (p.act_dim <= 16 ? 16 : 32);
+  const int kmax = (p.act_dim + G - 1) / G;
+  const int rows_per_block = LOSS_THREADS / G;
+  int grid = (p.num_rows + rows_per_block - 1) / rows_per_block;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaError_t e;
+  {
+    LaunchScope ls(K_PPO_LOSS, st);
+    e = G == 8 ? launch_loss<8>(p, kmax, grid, st) : (G == 16 ? launch_loss<16>(p, kmax, grid, st) : launch_loss<32>(p, kmax, grid, st));
+  }
+  return e == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}

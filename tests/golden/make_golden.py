@@ -344,16 +344,41 @@ def gen_mlp_marl(reference_root, M=200, seed=606):
     return out
 
 
+def gen_ppo_loss(reference_root):
+    """Three minibatches through the reference's own `ActorCritic.evaluate` + the loss lines of `PPO.update`
+    (oracle/ref_ppo_loss.py executes them): OneAnt width (8), TenAnt width (80), and the unclipped value loss."""
+    from oracle.ppo_loss_oracle import ppo_loss_oracle, synthetic_minibatch
+    from oracle.ref_ppo_loss import reference_ppo_loss
+    out = {}
+    cases = [("a8", 96, 8, 707, dict(clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.0, use_clipped_value_loss=True), 0.15),
+             ("a80", 70, 80, 808, dict(clip_param=0.2, value_loss_coef=2.0, entropy_coef=0.01, use_clipped_value_loss=True), 0.05),
+             ("a8u", 64, 8, 909, dict(clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.0, use_clipped_value_loss=False), 0.15)]
+    for tag, B, A, seed, cfg, spread in cases:
+        mb = synthetic_minibatch(B, A, seed, ratio_spread=spread)
+        ref = reference_ppo_loss(reference_root, mb, **cfg)
+        mine = ppo_loss_oracle(**mb, **cfg)
+        for k in ref:
+            _eq("ppo loss %s %s" % (tag, k), ref[k], mine[k])
+        out.update({"%s__in_%s" % (tag, k): v for k, v in mb.items()})
+        out.update({"%s__out_%s" % (tag, k): v for k, v in ref.items()})
+        out.update({"%s__cfg_%s" % (tag, k): np.float64(v) for k, v in cfg.items()})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--only", default=None, help="regenerate one fixture (by name)")
     args = ap.parse_args()
     refshim.install(args.reference)
     torch.manual_seed(0)
     torch.set_num_threads(1)
     for name, fn in (("ten_ant_n37", gen_ten_ant), ("one_ant_n64", gen_one_ant), ("ingenuity_n33", gen_ingenuity),
                      ("storage_ppo", gen_storage_ppo), ("buffer_marl", gen_buffer_marl),
-                     ("mlp_marl_actor0", lambda: gen_mlp_marl(args.reference))):
+                     ("mlp_marl_actor0", lambda: gen_mlp_marl(args.reference)),
+                     ("ppo_loss", lambda: gen_ppo_loss(args.reference))):
+        if args.only and name != args.only:
+            continue
         data = fn()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **_np(data))

@@ -127,3 +127,20 @@ def test_isaac_helpers_self_consistency():
         assert torch.allclose(got, ang, atol=1e-6)
     x = torch.tensor([[0.5236, 1.7453]]); lo = torch.tensor([0.5236]); hi = torch.tensor([1.7453])
     assert torch.allclose(itu.unscale(x, lo, hi), torch.tensor([[-1.0, 1.0]]), atol=1e-6)
+
+
+def test_ppo_loss_oracle_reproduces_golden():
+    """oracle/ppo_loss_oracle.py against outputs of the reference's own evaluate() + PPO.update loss lines
+    (tests/golden/ppo_loss.npz).  Transcendentals may differ by an ulp between CPUs, hence a tight allclose."""
+    from oracle.ppo_loss_oracle import ppo_loss_oracle
+    g = load_golden("ppo_loss")
+    for tag in ("a8", "a80", "a8u"):
+        mb = {k[len(tag) + 5:]: v for k, v in g.items() if k.startswith(tag + "__in_")}
+        cfg = {k[len(tag) + 6:]: float(v) for k, v in g.items() if k.startswith(tag + "__cfg_")}
+        cfg["use_clipped_value_loss"] = bool(cfg["use_clipped_value_loss"])
+        out = ppo_loss_oracle(**mb, **cfg)
+        for k, v in out.items():
+            ref = g["%s__out_%s" % (tag, k)]
+            assert torch.allclose(v, ref, rtol=2e-5, atol=2e-6 * float(ref.abs().max()) + 1e-9), (tag, k)
+        ratio = torch.exp(out["logp"] - mb["old_logp"].squeeze())
+        assert ((ratio < 0.8).any() and (ratio > 1.2).any() and ((ratio > 0.8) & (ratio < 1.2)).any())   # all clip regimes

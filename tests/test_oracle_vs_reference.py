@@ -86,3 +86,18 @@ def test_episode_bookkeeping_oracle_against_the_reference_lines():
         assert list(orc.rewbuffer) == list(rewbuffer) and list(orc.lenbuffer) == list(lenbuffer)
         assert torch.equal(orc.cur_reward_sum, ns["cur_reward_sum"]) and torch.equal(orc.cur_episode_length, ns["cur_episode_length"])
         assert orc.means() == (statistics.mean(rewbuffer), statistics.mean(lenbuffer))
+
+
+def test_ppo_loss_oracle_against_the_reference_lines(shim):
+    """The PPO minibatch loss: the reference's own `ActorCritic.evaluate` (imported) and the loss block of `PPO.update`
+    (source lines executed, oracle/ref_ppo_loss.py) against oracle/ppo_loss_oracle.py on fresh seeds - losses, KL,
+    log-probs and all three gradients identical."""
+    from oracle.ppo_loss_oracle import ppo_loss_oracle, synthetic_minibatch
+    from oracle.ref_ppo_loss import reference_ppo_loss
+    for B, A, seed, clipped, ec, vc, clip in [(57, 8, 11, True, 0.0, 1.0, 0.2), (31, 80, 12, True, 0.01, 2.0, 0.2),
+                                             (40, 24, 13, False, 0.0, 0.5, 0.1)]:
+        mb = synthetic_minibatch(B, A, seed)
+        ref = reference_ppo_loss(REF, mb, clip, vc, ec, clipped)
+        mine = ppo_loss_oracle(**mb, clip_param=clip, value_loss_coef=vc, entropy_coef=ec, use_clipped_value_loss=clipped)
+        for k in ref:
+            assert torch.equal(ref[k], mine[k]), (A, k)
