@@ -60,7 +60,7 @@ MMB_API uint64_t mmb_launch_count(void);
  * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
 enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
        MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
-       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_GAUSS_ACT, MMB_K_PPO_LOSS, MMB_K_COUNT };
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_GAUSS_ACT, MMB_K_PPO_LOSS, MMB_K_MAPPO_LOSS, MMB_K_COUNT };
 MMB_API int32_t mmb_profile_enable(int32_t on);
 MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
 
@@ -388,6 +388,45 @@ typedef struct {
   double* sums;                            /* [4 + A], zeroed by the caller */
 } mmb_ppo_loss_params;
 MMB_API int32_t mmb_ppo_loss(const mmb_ppo_loss_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* MAPPO minibatch losses of one agent, forward + backward in one launch:      */
+/*   FixedNormal.log_probs (per dimension)        agents/algorithms/utils/distributions.py:32-35  */
+/*   MAPPO.ppo_update                             agents/algorithms/marl/mappo_trainer.py:127-146 */
+/*     imp_weights = exp(sum_j (logp_j - old_logp_j)), clipped surrogate, optional active masks   */
+/*   MAPPO.cal_value_loss                         mappo_trainer.py:62-103                         */
+/*     clipped value prediction, returns normalised with the given (mean, var) (PopArt /          */
+/*     ValueNorm, popart.py:59-60; NULL = raw returns), huber (agents/utils/util.py:23-26, incl.   */
+/*     its missing e < -delta branch) or mse, max with the clipped term, optional active masks    */
+/* `std` is the standard deviation actually applied (sigmoid(log_std / x) * y, computed by the    */
+/* caller so that autograd continues to log_std); the entropy term depends on std only and stays  */
+/* with the caller.  `sums` (2 + act_dim doubles, zeroed by the caller) receives                 */
+/*   {sum_b -min(surr1, surr2) [* active], sum_b value loss [* active]} and d policy_loss/d std[j]; */
+/* gradients are already divided by B or by *mask_sum (= active_masks.sum(), device scalar).      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_rows, act_dim;
+  int32_t use_huber_loss, use_clipped_value_loss, use_value_active_masks, use_policy_active_masks;
+  const float* mean; int64_t mean_stride;  /* new action mean [B][A], row stride in elements */
+  const float* std;                        /* [A] */
+  const float* actions;                    /* [B][A] */
+  const float* old_logp;                   /* [B][A] per-dimension log-probs stored at rollout time */
+  const float* adv_targ;                   /* [B] */
+  const float* values;                     /* [B] new values */
+  const float* value_preds;                /* [B] values at rollout time */
+  const float* returns;                    /* [B] */
+  const float* active_masks;               /* [B], may be NULL when neither mask flag is set */
+  const float* mask_sum;                   /* device scalar active_masks.sum(), may be NULL likewise */
+  const float* ret_mean;                   /* device scalar, or NULL */
+  const float* ret_var;                    /* device scalar, or NULL */
+  float clip_param, ratio_lo, ratio_hi, huber_delta;
+  float* imp_weights;                      /* [B] or NULL */
+  float* logp;                             /* [B][A] new per-dimension log-probs, or NULL */
+  float* grad_mean;                        /* [B][A] d policy_loss / d mean, or NULL */
+  float* grad_values;                      /* [B] d value_loss / d values, or NULL */
+  double* sums;                            /* [2 + A], zeroed by the caller */
+} mmb_mappo_loss_params;
+MMB_API int32_t mmb_mappo_loss(const mmb_mappo_loss_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Episode bookkeeping of the PPO runner (agents/algorithms/rl/ppo/ppo.py:143-157,198-220): running */

@@ -127,6 +127,16 @@ class PpoLossParams(C.Structure):
                 ("entropy_coef", c_f), ("k_log_2pi", c_f), ("logp", c_vp), ("grad_mu", c_vp), ("grad_value", c_vp), ("sums", c_vp)]
 
 
+class MappoLossParams(C.Structure):
+    _fields_ = [("num_rows", c_i32), ("act_dim", c_i32), ("use_huber_loss", c_i32), ("use_clipped_value_loss", c_i32),
+                ("use_value_active_masks", c_i32), ("use_policy_active_masks", c_i32),
+                ("mean", c_vp), ("mean_stride", c_i64), ("std", c_vp), ("actions", c_vp), ("old_logp", c_vp),
+                ("adv_targ", c_vp), ("values", c_vp), ("value_preds", c_vp), ("returns", c_vp), ("active_masks", c_vp),
+                ("mask_sum", c_vp), ("ret_mean", c_vp), ("ret_var", c_vp),
+                ("clip_param", c_f), ("ratio_lo", c_f), ("ratio_hi", c_f), ("huber_delta", c_f),
+                ("imp_weights", c_vp), ("logp", c_vp), ("grad_mean", c_vp), ("grad_values", c_vp), ("sums", c_vp)]
+
+
 class GaeMarlParams(C.Structure):
     _fields_ = [
         ("num_envs", c_i32), ("num_steps", c_i32), ("num_agents", c_i32),
@@ -179,6 +189,7 @@ SYMBOLS = {
     "mmb_rollout_statistics": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mmb_gaussian_act": (c_i32, [C.POINTER(GaussianActParams), c_vp]),
     "mmb_ppo_loss": (c_i32, [C.POINTER(PpoLossParams), c_vp]),
+    "mmb_mappo_loss": (c_i32, [C.POINTER(MappoLossParams), c_vp]),
     "mmb_episode_update": (c_i32, [C.POINTER(EpisodeParams), c_vp]),
     "mmb_gae_marl": (c_i32, [C.POINTER(GaeMarlParams), c_vp]),
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
@@ -234,7 +245,7 @@ def launch_count():
 
 KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
               "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm", "mlp_layer",
-              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring", "gauss_act", "ppo_loss")
+              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring", "gauss_act", "ppo_loss", "mappo_loss")
 
 
 def profile_enable(on=True):

@@ -176,6 +176,145 @@ cudaError_t launch_loss(const mmb_ppo_loss_params& p, int kmax, int grid, cudaSt
   return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MAPPO minibatch losses (agents/algorithms/marl/mappo_trainer.py:62-103,127-168) for one agent: per-dimension Normal
+// log-probs (distributions.py:32-35), importance weight exp(sum_j (logp_j - old_logp_j)), clipped surrogate, huber / mse
+// value loss on (PopArt-)normalised returns, optional active masks - and the gradients of the policy loss with respect to
+// mean / std and of the value loss with respect to the values.  Same thread layout as ppo_loss_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void value_term(float e, float delta, bool huber, float& loss, float& dloss_de) {
+  if (huber) {
+    // agents/utils/util.py:23-26: a = |e| <= d, b = e > d (no branch for e < -d: zero loss, zero gradient - kept)
+    const float a = fabsf(e) <= delta ? 1.0f : 0.0f, b = e > delta ? 1.0f : 0.0f;
+    loss = a * (e * e) / 2.0f + (b * delta) * (fabsf(e) - delta / 2.0f);
+    dloss_de = a * e + b * delta;
+  } else {
+    loss = (e * e) / 2.0f;                                      // util.py:28-29
+    dloss_de = e;
+  }
+}
+
+template <int G, int KMAX>
+__global__ void __launch_bounds__(LOSS_THREADS) mappo_loss_kernel(const __grid_constant__ mmb_mappo_loss_params p) {
+  __shared__ double s_gstd[32 * LOSS_MAX_K];
+  __shared__ double s_sum[2];
+  const int A = p.act_dim, B = p.num_rows;
+  const int tid = threadIdx.x, sub = tid % G;
+  for (int j = tid; j < A; j += LOSS_THREADS) s_gstd[j] = 0.0;
+  if (tid < 2) s_sum[tid] = 0.0;
+  __syncthreads();
+
+  float sd[KMAX], two_var[KMAX], log_sd[KMAX], gstd[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = sub + k * G;
+    gstd[k] = 0.0f;
+    sd[k] = j < A ? __ldg(p.std + j) : 1.0f;
+    two_var[k] = 2.0f * (sd[k] * sd[k]);                         // Normal.log_prob: var = scale ** 2; ... / (2 * var)
+    log_sd[k] = logf(sd[k]);
+  }
+  const float inv_b = 1.0f / (float)B;
+  const float inv_mask_sum = p.mask_sum ? 1.0f / __ldg(p.mask_sum) : 0.0f;
+  float ret_mean = 0.0f, ret_sd = 1.0f;
+  const bool norm_ret = p.ret_mean != nullptr;
+  if (norm_ret) { ret_mean = __ldg(p.ret_mean); ret_sd = sqrtf(__ldg(p.ret_var)); }
+
+  double acc_p = 0.0, acc_v = 0.0;
+  const int rows_per_block = LOSS_THREADS / G;
+  for (int base = blockIdx.x * rows_per_block; base < B; base += gridDim.x * rows_per_block) {
+    const int row = base + tid / G;
+    const bool live = row < B;
+    const int A_live = live ? A : 0;
+    const float* mean = p.mean + (int64_t)row * p.mean_stride;
+    float diff[KMAX];
+    float dsum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int j = sub + k * G;
+      diff[k] = 0.0f;
+      if (j < A_live) {
+        diff[k] = __ldg(p.actions + (int64_t)row * A + j) - __ldg(mean + j);
+        // -((a - m) ** 2) / (2 var) - log(scale) - log(sqrt(2 pi)), rounded like torch's separate kernels
+        const float lp = __fadd_rn(__fadd_rn(__fdiv_rn(-__fmul_rn(diff[k], diff[k]), two_var[k]), -log_sd[k]), -0.9189385332046727f);
+        if (p.logp) __stcs(p.logp + (int64_t)row * A + j, lp);
+        dsum = __fadd_rn(dsum, __fadd_rn(lp, -__ldcs(p.old_logp + (int64_t)row * A + j)));
+      }
+    }
+    dsum = group_sum<G>(dsum);
+    const float imp = expf(dsum);                                // mappo_trainer.py:128
+    const float active = (live && p.active_masks) ? __ldg(p.active_masks + row) : 1.0f;
+    const float adv = live ? __ldg(p.adv_targ + row) : 0.0f;
+    const float clamped = fminf(fmaxf(imp, p.ratio_lo), p.ratio_hi);
+    const float surr1 = imp * adv, surr2 = clamped * adv;
+    const bool inside = imp >= p.ratio_lo && imp <= p.ratio_hi;
+    float dmin;                                                  // d min(surr1, surr2) / d imp
+    if (surr1 < surr2) dmin = adv;
+    else if (surr1 == surr2) dmin = 0.5f * adv + (inside ? 0.5f * adv : 0.0f);
+    else dmin = inside ? adv : 0.0f;
+    const float w_p = p.use_policy_active_masks ? active * inv_mask_sum : inv_b;
+    const float gl = live ? -dmin * imp * w_p : 0.0f;           // d policy_loss / d logp_j, the same for every j
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int j = sub + k * G;
+      const float var = sd[k] * sd[k];
+      if (j < A_live && p.grad_mean) __stcs(p.grad_mean + (int64_t)row * A + j, gl * (diff[k] / var));
+      gstd[k] += gl * ((diff[k] * diff[k]) / (var * sd[k]) - 1.0f / sd[k]);
+    }
+
+    if (sub == 0 && live) {
+      if (p.imp_weights) p.imp_weights[row] = imp;
+      acc_p += (double)(-fminf(surr1, surr2) * (p.use_policy_active_masks ? active : 1.0f));
+      // cal_value_loss, mappo_trainer.py:73-103
+      const float v = __ldg(p.values + row), vp = __ldg(p.value_preds + row);
+      float ret = __ldg(p.returns + row);
+      if (norm_ret) ret = (ret - ret_mean) / ret_sd;        // popart.py:59-60
+      const float d = v - vp;
+      const float vpc = vp + fminf(fmaxf(d, -p.clip_param), p.clip_param);
+      const bool in_v = d >= -p.clip_param && d <= p.clip_param;
+      float lo, go, lc, gc;
+      value_term(ret - v, p.huber_delta, p.use_huber_loss != 0, lo, go);
+      value_term(ret - vpc, p.huber_delta, p.use_huber_loss != 0, lc, gc);
+      go = -go;                                                 // d error / d values = -1 (through the clamp: where it passes)
+      gc = in_v ? -gc : 0.0f;
+      float lv = lo, gv = go;
+      if (p.use_clipped_value_loss) {
+        lv = fmaxf(lo, lc);
+        gv = lo > lc ? go : (lo == lc ? 0.5f * go + 0.5f * gc : gc);
+      }
+      const float w_v = p.use_value_active_masks ? active * inv_mask_sum : inv_b;
+      if (p.grad_values) p.grad_values[row] = gv * w_v;
+      acc_v += (double)(lv * (p.use_value_active_masks ? active : 1.0f));
+    }
+  }
+
+  if (sub == 0) { atomicAdd(&s_sum[0], acc_p); atomicAdd(&s_sum[1], acc_v); }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = sub + k * G;
+    if (j < A) atomicAdd(&s_gstd[j], (double)gstd[k]);
+  }
+  __syncthreads();
+  if (tid < 2) atomicAdd(p.sums + tid, s_sum[tid]);
+  for (int j = tid; j < A; j += LOSS_THREADS) atomicAdd(p.sums + 2 + j, s_gstd[j]);
+}
+
+template <int G>
+cudaError_t launch_mappo_loss(const mmb_mappo_loss_params& p, int kmax, int grid, cudaStream_t st) {
+  if (G < 32) {
+    mappo_loss_kernel<G, 1><<<grid, LOSS_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+  }
+  switch (kmax) {
+    case 1: mappo_loss_kernel<32, 1><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    case 2: mappo_loss_kernel<32, 2><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    case 3: mappo_loss_kernel<32, 3><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    case 4: mappo_loss_kernel<32, 4><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+    default: mappo_loss_kernel<32, LOSS_MAX_K><<<grid, LOSS_THREADS, 0, st>>>(p); break;
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace
 }  // namespace mmb
 
@@ -199,6 +338,29 @@ extern "C" int32_t mmb_ppo_loss(const mmb_ppo_loss_params* pp, void* stream) {
   {
     LaunchScope ls(K_PPO_LOSS, st);
     e = G == 8 ? launch_loss<8>(p, kmax, grid, st) : (G == 16 ? launch_loss<16>(p, kmax, grid, st) : launch_loss<32>(p, kmax, grid, st));
+  }
+  return e == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+extern "C" int32_t mmb_mappo_loss(const mmb_mappo_loss_params* pp, void* stream) {
+  if (!pp) return MMB_EINVAL;
+  const mmb_mappo_loss_params& p = *pp;
+  if (p.num_rows <= 0 || p.act_dim <= 0 || p.act_dim > 32 * LOSS_MAX_K || p.mean_stride < p.act_dim) return MMB_EINVAL;
+  if (!p.mean || !p.std || !p.actions || !p.old_logp || !p.adv_targ || !p.values || !p.value_preds || !p.returns || !p.sums)
+    return MMB_EINVAL;
+  if ((p.use_value_active_masks || p.use_policy_active_masks) && (!p.active_masks || !p.mask_sum)) return MMB_EINVAL;
+  if ((p.ret_mean == nullptr) != (p.ret_var == nullptr)) return MMB_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = p.act_dim <= 8 ? 8 : (p.act_dim <= 16 ? 16 : 32);
+  const int kmax = (p.act_dim + G - 1) / G;
+  const int rows_per_block = LOSS_THREADS / G;
+  int grid = (p.num_rows + rows_per_block - 1) / rows_per_block;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaError_t e;
+  {
+    LaunchScope ls(K_MAPPO_LOSS, st);
+    e = G == 8 ? launch_mappo_loss<8>(p, kmax, grid, st)
+               : (G == 16 ? launch_mappo_loss<16>(p, kmax, grid, st) : launch_mappo_loss<32>(p, kmax, grid, st));
   }
   return e == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

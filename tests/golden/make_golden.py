@@ -365,6 +365,33 @@ def gen_ppo_loss(reference_root):
     return out
 
 
+MAPPO_LOSS_BASE = dict(clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.0, huber_delta=10.0, use_huber_loss=True,
+                       use_clipped_value_loss=True, use_value_active_masks=False, use_policy_active_masks=False,
+                       std_x_coef=1.0, std_y_coef=0.5)                       # cfg/mappo/config.yaml
+
+
+def gen_mappo_loss():
+    """Minibatches through the reference's own `MAPPO.ppo_update` (+ its ACTLayer / DiagGaussian / PopArt,
+    oracle/ref_mappo_loss.py): the shipped configuration, the masked + small-delta variant, the mse / unclipped one."""
+    from oracle.mappo_loss_oracle import mappo_loss_oracle, synthetic_minibatch
+    from oracle.ref_mappo_loss import reference_mappo_loss
+    out = {}
+    cases = [("cfg", 96, 8, 1001, {}),
+             ("mask", 80, 8, 1002, dict(use_value_active_masks=True, use_policy_active_masks=True, entropy_coef=0.01, huber_delta=1.0)),
+             ("mse", 64, 6, 1003, dict(use_huber_loss=False, use_clipped_value_loss=False, value_loss_coef=0.5, clip_param=0.1))]
+    for tag, B, A, seed, over in cases:
+        cfg = dict(MAPPO_LOSS_BASE, **over)
+        mb = synthetic_minibatch(B, A, seed, huber_delta=cfg["huber_delta"])
+        ref, mb = reference_mappo_loss(mb, cfg)
+        mine = mappo_loss_oracle(**mb, **cfg)
+        for k in ref:
+            _eq("mappo loss %s %s" % (tag, k), ref[k], mine[k])
+        out.update({"%s__in_%s" % (tag, k): v for k, v in mb.items()})
+        out.update({"%s__out_%s" % (tag, k): v for k, v in mine.items()})       # (= ref, plus the per-dimension log-probs)
+        out.update({"%s__cfg_%s" % (tag, k): np.float64(v) for k, v in cfg.items()})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -376,7 +403,7 @@ def main():
     for name, fn in (("ten_ant_n37", gen_ten_ant), ("one_ant_n64", gen_one_ant), ("ingenuity_n33", gen_ingenuity),
                      ("storage_ppo", gen_storage_ppo), ("buffer_marl", gen_buffer_marl),
                      ("mlp_marl_actor0", lambda: gen_mlp_marl(args.reference)),
-                     ("ppo_loss", lambda: gen_ppo_loss(args.reference))):
+                     ("ppo_loss", lambda: gen_ppo_loss(args.reference)), ("mappo_loss", gen_mappo_loss)):
         if args.only and name != args.only:
             continue
         data = fn()

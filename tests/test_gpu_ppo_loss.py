@@ -46,8 +46,10 @@ def _check(dev, mb, cfg, want):
     _close(out.kl_mean, on_gpu["kl_mean"], 1e-5, "kl_mean (oracle statements on the GPU)", floor=5e-8)
     _close(mu.grad, on_gpu["grad_mu"], rr, "grad_mu (oracle statements on the GPU)")
     _close(log_std.grad, on_gpu["grad_log_std"], rr, "grad_log_std (oracle statements on the GPU)")
-    _close(out.surrogate_loss, want["surrogate_loss"], rr, "surrogate_loss")
-    _close(out.loss, want["loss"], rr, "loss")
+    # the surrogate is a mean of signed terms that largely cancel: its error scales with the terms, not with the mean
+    term_scale = float((torch.exp(want["logp"] - mb["old_logp"].reshape(-1)) * mb["advantages"].reshape(-1)).abs().mean())
+    _close(out.surrogate_loss, want["surrogate_loss"], rr, "surrogate_loss", floor=rr * term_scale)
+    _close(out.loss, want["loss"], rr, "loss", floor=rr * term_scale)
     _close(mu.grad, want["grad_mu"], rr, "grad_mu")
     _close(log_std.grad, want["grad_log_std"], rr, "grad_log_std")
     assert value.grad.shape == value.shape and log_std.grad.shape == log_std.shape

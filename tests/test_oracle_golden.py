@@ -144,3 +144,32 @@ def test_ppo_loss_oracle_reproduces_golden():
             assert torch.allclose(v, ref, rtol=2e-5, atol=2e-6 * float(ref.abs().max()) + 1e-9), (tag, k)
         ratio = torch.exp(out["logp"] - mb["old_logp"].squeeze())
         assert ((ratio < 0.8).any() and (ratio > 1.2).any() and ((ratio > 0.8) & (ratio < 1.2)).any())   # all clip regimes
+
+
+def _loss_case(g, tag, bool_keys):
+    mb = {k[len(tag) + 5:]: v for k, v in g.items() if k.startswith(tag + "__in_")}
+    cfg = {k[len(tag) + 6:]: float(v) for k, v in g.items() if k.startswith(tag + "__cfg_")}
+    for k in bool_keys:
+        cfg[k] = bool(cfg[k])
+    want = {k[len(tag) + 6:]: v for k, v in g.items() if k.startswith(tag + "__out_")}
+    return mb, cfg, want
+
+
+MAPPO_BOOLS = ("use_huber_loss", "use_clipped_value_loss", "use_value_active_masks", "use_policy_active_masks")
+
+
+def test_mappo_loss_oracle_reproduces_golden():
+    """oracle/mappo_loss_oracle.py against outputs of the reference's own MAPPO.ppo_update (tests/golden/mappo_loss.npz)."""
+    from oracle.mappo_loss_oracle import mappo_loss_oracle
+    g = load_golden("mappo_loss")
+    for tag in ("cfg", "mask", "mse"):
+        mb, cfg, want = _loss_case(g, tag, MAPPO_BOOLS)
+        out = mappo_loss_oracle(**mb, **cfg)
+        for k, v in out.items():
+            assert torch.allclose(v, want[k], rtol=2e-5, atol=2e-6 * float(want[k].abs().max()) + 1e-9), (tag, k)
+        imp = out["imp_weights"]
+        assert (imp < 1 - cfg["clip_param"]).any() and (imp > 1 + cfg["clip_param"]).any()
+        if cfg["use_huber_loss"]:                                 # the fixture reaches all three huber branches
+            ret_n = (mb["returns"] - mb["ret_mean"]) / torch.sqrt(mb["ret_var"])
+            e = ret_n - mb["values"]
+            assert (e > cfg["huber_delta"]).any() and (e < -cfg["huber_delta"]).any() and (e.abs() <= cfg["huber_delta"]).any()

@@ -101,3 +101,25 @@ def test_ppo_loss_oracle_against_the_reference_lines(shim):
         mine = ppo_loss_oracle(**mb, clip_param=clip, value_loss_coef=vc, entropy_coef=ec, use_clipped_value_loss=clipped)
         for k in ref:
             assert torch.equal(ref[k], mine[k]), (A, k)
+
+
+def test_mappo_loss_oracle_against_the_reference_trainer(shim):
+    """The MAPPO minibatch losses: the reference's own `MAPPO.ppo_update` with its own ACTLayer / DiagGaussian / PopArt
+    (oracle/ref_mappo_loss.py; only the MLP trunks are stubbed) against oracle/mappo_loss_oracle.py on fresh seeds -
+    losses, importance weights and all three gradients identical, in every flag combination the trainer has."""
+    import itertools
+    from oracle.mappo_loss_oracle import mappo_loss_oracle, synthetic_minibatch
+    from oracle.ref_mappo_loss import reference_mappo_loss
+    base = dict(clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.01, huber_delta=1.0, std_x_coef=1.0, std_y_coef=0.5)
+    seed = 40
+    for huber, clipped, vmask, pmask, popart in itertools.product((True, False), repeat=5):
+        seed += 1
+        cfg = dict(base, use_huber_loss=huber, use_clipped_value_loss=clipped, use_value_active_masks=vmask,
+                   use_policy_active_masks=pmask)
+        mb = synthetic_minibatch(48, 8 if seed % 2 else 6, seed, huber_delta=1.0)
+        if not popart:
+            mb["ret_mean"] = mb["ret_var"] = None
+        ref, mb = reference_mappo_loss(mb, cfg)
+        mine = mappo_loss_oracle(**mb, **cfg)
+        for k in ref:
+            assert torch.equal(ref[k], mine[k]), (cfg, popart, k)
