@@ -278,7 +278,11 @@ def _stub_modules():
 
     mpl = types.ModuleType("matplotlib")
     plt = types.ModuleType("matplotlib.pyplot")
-    plt.__getattr__ = lambda name: (lambda *a, **k: None)
+    def _plt_attr(name):
+        if name.startswith("__"):               # (inspect.getmodule walks sys.modules and asks for __file__)
+            raise AttributeError(name)
+        return lambda *a, **k: None
+    plt.__getattr__ = _plt_attr
     mpl.pyplot = plt
     sys.modules.setdefault("matplotlib", mpl)
     sys.modules.setdefault("matplotlib.pyplot", plt)

@@ -123,3 +123,60 @@ def test_mappo_loss_oracle_against_the_reference_trainer(shim):
         mine = mappo_loss_oracle(**mb, **cfg)
         for k in ref:
             assert torch.equal(ref[k], mine[k]), (cfg, popart, k)
+
+
+def _fill_rollout(st, ac, T, N, obs_dim, A, seed):
+    """A storage as it looks after a rollout + compute_returns: old policy = the network's current one (plus a little
+    noise so that ratios leave 1), advantages normalised."""
+    g = torch.Generator().manual_seed(seed)
+    st.observations.copy_(torch.randn(T, N, obs_dim, generator=g))
+    with torch.no_grad():
+        mu = ac.actor(st.observations.view(-1, obs_dim)).view(T, N, A) + 0.02 * torch.randn(T, N, A, generator=g)
+        val = ac.critic(st.observations.view(-1, obs_dim)).view(T, N, 1)
+        std = ac.log_std.exp() * ac.log_std.exp()
+        act = mu + std * torch.randn(T, N, A, generator=g)
+        logp = (-0.5 * (((act - mu) / std) ** 2).sum(-1) - std.log().sum() - 0.5 * A * 1.8378770664093453).view(T, N, 1)
+    st.mu.copy_(mu); st.sigma.copy_(ac.log_std.detach().repeat(T, N, 1)); st.actions.copy_(act)
+    st.actions_log_prob.copy_(logp); st.values.copy_(val + 0.1 * torch.randn(T, N, 1, generator=g))
+    st.returns.copy_(val + 0.5 * torch.randn(T, N, 1, generator=g))
+    adv = st.returns - st.values
+    st.advantages.copy_((adv - adv.mean()) / (adv.std() + 1e-8))
+
+
+def test_ppo_update_oracle_against_the_reference_update(shim):
+    """The whole minibatch loop: the reference's own unmodified `PPO.update` on the reference's `ActorCritic` and
+    `RolloutStorage` (sequential sampler) against oracle.ppo_loss_oracle.ppo_update_oracle from the same initial weights -
+    identical parameters, optimiser step size and returned loss means after 2 epochs x 3 minibatches, with Adam and the
+    adaptive-KL schedule as in cfg/ppo/config.yaml."""
+    import contextlib
+    import copy
+    import io
+    import types
+    import agents.algorithms.rl.ppo as pkg                 # a bare namespace under the shim: give it what ppo.py imports from it
+    from agents.algorithms.rl.ppo.module import ActorCritic
+    from agents.algorithms.rl.ppo.storage import RolloutStorage
+    pkg.RolloutStorage, pkg.ActorCritic = RolloutStorage, ActorCritic
+    from agents.algorithms.rl.ppo.ppo import PPO
+    from oracle.ppo_loss_oracle import ppo_update_oracle
+    T, N, obs_dim, A = 6, 20, 12, 8
+    torch.manual_seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ac_ref = ActorCritic((obs_dim,), (0,), (A,), 0.8, {"pi_hid_sizes": [32, 16], "vf_hid_sizes": [32, 16], "activation": "elu"})
+    ac_mine = copy.deepcopy(ac_ref)
+    initial = copy.deepcopy(ac_ref.state_dict())
+    st = RolloutStorage(N, T, (obs_dim,), (0,), (A,), "cpu", "sequential")
+    _fill_rollout(st, ac_ref, T, N, obs_dim, A, seed=70)
+
+    def make(ac):
+        return types.SimpleNamespace(storage=st, actor_critic=ac, optimizer=torch.optim.Adam(ac.parameters(), lr=3e-4),
+                                     num_mini_batches=3, num_learning_epochs=2, clip_param=0.2, value_loss_coef=2.0,
+                                     entropy_coef=0.001, use_clipped_value_loss=True, desired_kl=0.016, schedule="adaptive",
+                                     step_size=3e-4, max_grad_norm=1.0, asymmetric=False)
+
+    ref, mine = make(ac_ref), make(ac_mine)
+    out_ref = PPO.update(ref)
+    out_mine = ppo_update_oracle(mine, [torch.arange(T * N)] * 2)
+    assert out_ref == out_mine and ref.step_size == mine.step_size
+    for (k, a), b in zip(ac_ref.state_dict().items(), ac_mine.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert not torch.equal(ac_ref.state_dict()["actor.0.weight"], initial["actor.0.weight"])      # the update did move them
