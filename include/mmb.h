@@ -419,6 +419,9 @@ typedef struct {
   const float* mask_sum;                   /* device scalar active_masks.sum(), may be NULL likewise */
   const float* ret_mean;                   /* device scalar, or NULL */
   const float* ret_var;                    /* device scalar, or NULL */
+  const float* ret_mean_orig;              /* moments for the UNCLIPPED error term, or NULL = the pair above: the   */
+  const float* ret_var_orig;               /* reference's PopArt updates its running moments on every call and is   */
+                                           /* called once per error term (mappo_trainer.py:80-81, popart.py:38-60)  */
   float clip_param, ratio_lo, ratio_hi, huber_delta;
   float* imp_weights;                      /* [B] or NULL */
   float* logp;                             /* [B][A] new per-dimension log-probs, or NULL */

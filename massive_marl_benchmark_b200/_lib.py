@@ -132,7 +132,7 @@ class MappoLossParams(C.Structure):
                 ("use_value_active_masks", c_i32), ("use_policy_active_masks", c_i32),
                 ("mean", c_vp), ("mean_stride", c_i64), ("std", c_vp), ("actions", c_vp), ("old_logp", c_vp),
                 ("adv_targ", c_vp), ("values", c_vp), ("value_preds", c_vp), ("returns", c_vp), ("active_masks", c_vp),
-                ("mask_sum", c_vp), ("ret_mean", c_vp), ("ret_var", c_vp),
+                ("mask_sum", c_vp), ("ret_mean", c_vp), ("ret_var", c_vp), ("ret_mean_orig", c_vp), ("ret_var_orig", c_vp),
                 ("clip_param", c_f), ("ratio_lo", c_f), ("ratio_hi", c_f), ("huber_delta", c_f),
                 ("imp_weights", c_vp), ("logp", c_vp), ("grad_mean", c_vp), ("grad_values", c_vp), ("sums", c_vp)]
 

@@ -216,9 +216,15 @@ __global__ void __launch_bounds__(LOSS_THREADS) mappo_loss_kernel(const __grid_c
   }
   const float inv_b = 1.0f / (float)B;
   const float inv_mask_sum = p.mask_sum ? 1.0f / __ldg(p.mask_sum) : 0.0f;
-  float ret_mean = 0.0f, ret_sd = 1.0f;
+  // the reference calls its PopArt normaliser once per error term and each call first updates the running moments
+  // (mappo_trainer.py:80-81, popart.py:38-60): the clipped and the original error may see different (mean, var)
+  float ret_mean = 0.0f, ret_sd = 1.0f, ret_mean_o = 0.0f, ret_sd_o = 1.0f;
   const bool norm_ret = p.ret_mean != nullptr;
-  if (norm_ret) { ret_mean = __ldg(p.ret_mean); ret_sd = sqrtf(__ldg(p.ret_var)); }
+  if (norm_ret) {
+    ret_mean = __ldg(p.ret_mean); ret_sd = sqrtf(__ldg(p.ret_var));
+    ret_mean_o = p.ret_mean_orig ? __ldg(p.ret_mean_orig) : ret_mean;
+    ret_sd_o = p.ret_var_orig ? sqrtf(__ldg(p.ret_var_orig)) : ret_sd;
+  }
 
   double acc_p = 0.0, acc_v = 0.0;
   const int rows_per_block = LOSS_THREADS / G;
@@ -267,14 +273,15 @@ __global__ void __launch_bounds__(LOSS_THREADS) mappo_loss_kernel(const __grid_c
       acc_p += (double)(-fminf(surr1, surr2) * (p.use_policy_active_masks ? active : 1.0f));
       // cal_value_loss, mappo_trainer.py:73-103
       const float v = __ldg(p.values + row), vp = __ldg(p.value_preds + row);
-      float ret = __ldg(p.returns + row);
-      if (norm_ret) ret = (ret - ret_mean) / ret_sd;        // popart.py:59-60
+      const float ret_raw = __ldg(p.returns + row);
+      float ret_c = ret_raw, ret_o = ret_raw;
+      if (norm_ret) { ret_c = (ret_raw - ret_mean) / ret_sd; ret_o = (ret_raw - ret_mean_o) / ret_sd_o; }   // popart.py:59-60
       const float d = v - vp;
       const float vpc = vp + fminf(fmaxf(d, -p.clip_param), p.clip_param);
       const bool in_v = d >= -p.clip_param && d <= p.clip_param;
       float lo, go, lc, gc;
-      value_term(ret - v, p.huber_delta, p.use_huber_loss != 0, lo, go);
-      value_term(ret - vpc, p.huber_delta, p.use_huber_loss != 0, lc, gc);
+      value_term(ret_o - v, p.huber_delta, p.use_huber_loss != 0, lo, go);
+      value_term(ret_c - vpc, p.huber_delta, p.use_huber_loss != 0, lc, gc);
       go = -go;                                                 // d error / d values = -1 (through the clamp: where it passes)
       gc = in_v ? -gc : 0.0f;
       float lv = lo, gv = go;
@@ -350,6 +357,7 @@ extern "C" int32_t mmb_mappo_loss(const mmb_mappo_loss_params* pp, void* stream)
     return MMB_EINVAL;
   if ((p.use_value_active_masks || p.use_policy_active_masks) && (!p.active_masks || !p.mask_sum)) return MMB_EINVAL;
   if ((p.ret_mean == nullptr) != (p.ret_var == nullptr)) return MMB_EINVAL;
+  if ((p.ret_mean_orig == nullptr) != (p.ret_var_orig == nullptr) || (p.ret_mean_orig && !p.ret_mean)) return MMB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int G = p.act_dim <= 8 ? 8 : (p.act_dim <= 16 ? 16 : 32);
   const int kmax = (p.act_dim + G - 1) / G;

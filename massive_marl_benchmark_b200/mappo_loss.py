@@ -10,8 +10,10 @@ working unchanged:
     (out.policy_loss - out.dist_entropy * entropy_coef).backward()                     # mappo_trainer.py:146
     (out.value_loss * value_loss_coef).backward()                                      # mappo_trainer.py:168
 
-`ret_mean`, `ret_var` are the PopArt / ValueNorm moments AFTER the reference's running update on this batch
-(`value_normalizer.running_mean_var()` once `value_normalizer(return_batch)`'s update part has run; None = raw returns).
+`ret_mean`, `ret_var` are the PopArt / ValueNorm moments the CLIPPED error term is normalised with, `ret_mean_orig`,
+`ret_var_orig` those of the unclipped one (None = the same pair; all None = raw returns): the reference calls PopArt once
+per error term and each call first updates the running statistics (mappo_trainer.py:80-81, popart.py:38-60), so with
+PopArt pass `running_mean_var()` after the first and after the second call (`mappo_update.mappo_ppo_update` does).
 The entropy depends on `std` only and is computed here with plain torch ops (so its gradient reaches `log_std` through
 autograd).  No CPU path: raises if the CUDA library is missing.
 """
@@ -48,7 +50,7 @@ def _rows(t, B, name):
 
 
 def mappo_loss_raw(mean, std, values, actions, old_logp, adv_targ, value_preds, returns, active_masks=None, ret_mean=None,
-                   ret_var=None, clip_param=0.2, huber_delta=10.0, use_huber_loss=True, use_clipped_value_loss=True,
+                   ret_var=None, ret_mean_orig=None, ret_var_orig=None, clip_param=0.2, huber_delta=10.0, use_huber_loss=True, use_clipped_value_loss=True,
                    use_value_active_masks=False, use_policy_active_masks=False):
     """One `mmb_mappo_loss` launch.  Returns (policy_loss, value_loss [0-dim fp32 tensors], imp_weights [B, 1], logp [B, A],
     grad_mean [B, A], grad_std [A], grad_values [B])."""
@@ -91,9 +93,11 @@ def mappo_loss_raw(mean, std, values, actions, old_logp, adv_targ, value_preds, 
         put("mask_sum", mask_sum)
     if (ret_mean is None) != (ret_var is None):
         raise ValueError("ret_mean and ret_var go together")
-    if ret_mean is not None:
-        put("ret_mean", ret_mean.detach().reshape(-1)[:1].float().contiguous().to(dev))
-        put("ret_var", ret_var.detach().reshape(-1)[:1].float().contiguous().to(dev))
+    if (ret_mean_orig is None) != (ret_var_orig is None) or (ret_mean_orig is not None and ret_mean is None):
+        raise ValueError("ret_mean_orig and ret_var_orig go together, and with ret_mean / ret_var")
+    for name, t in (("ret_mean", ret_mean), ("ret_var", ret_var), ("ret_mean_orig", ret_mean_orig), ("ret_var_orig", ret_var_orig)):
+        if t is not None:
+            put(name, t.detach().reshape(-1)[:1].float().contiguous().to(dev))
     p.clip_param, p.huber_delta = float(clip_param), float(huber_delta)
     p.ratio_lo, p.ratio_hi = 1.0 - clip_param, 1.0 + clip_param
     sums = torch.zeros(2 + A, dtype=torch.float64, device=dev)
@@ -110,14 +114,14 @@ def mappo_loss_raw(mean, std, values, actions, old_logp, adv_targ, value_preds, 
 
 
 def mappo_loss(mean, std, values, actions, old_logp, adv_targ, value_preds, returns, active_masks=None, ret_mean=None,
-               ret_var=None, clip_param=0.2, huber_delta=10.0, use_huber_loss=True, use_clipped_value_loss=True,
+               ret_var=None, ret_mean_orig=None, ret_var_orig=None, clip_param=0.2, huber_delta=10.0, use_huber_loss=True, use_clipped_value_loss=True,
                use_value_active_masks=False, use_policy_active_masks=False):
     """`policy_loss` is differentiable with respect to `mean` [B, A] and `std` [A], `value_loss` with respect to `values`
     [B, 1], `dist_entropy` with respect to `std`; they can be back-propagated separately, in any order, as the reference
     does.  Returns MappoLossOut(policy_loss, value_loss, dist_entropy, imp_weights [B, 1], logp [B, A])."""
     pl, vl, imp, logp, g_mean, g_std, g_values = mappo_loss_raw(
-        mean, std, values, actions, old_logp, adv_targ, value_preds, returns, active_masks, ret_mean, ret_var, clip_param,
-        huber_delta, use_huber_loss, use_clipped_value_loss, use_value_active_masks, use_policy_active_masks)
+        mean, std, values, actions, old_logp, adv_targ, value_preds, returns, active_masks, ret_mean, ret_var, ret_mean_orig,
+        ret_var_orig, clip_param, huber_delta, use_huber_loss, use_clipped_value_loss, use_value_active_masks, use_policy_active_masks)
     policy_loss = _Attach.apply(pl, 2, mean, std, g_mean, g_std.reshape(std.shape))
     value_loss = _Attach.apply(vl, 1, values, g_values.reshape(values.shape))
     # Normal.entropy = 0.5 + 0.5 log(2 pi) + log(scale) per dimension, the same on every row; act.py:157-163: masked mean

@@ -39,7 +39,7 @@ def reference_mappo_loss(mb, cfg):
               "huber_delta": cfg["huber_delta"], "use_valuenorm": False, "use_recurrent_policy": False,
               "use_naive_recurrent_policy": False, "use_max_grad_norm": True,
               "use_clipped_value_loss": cfg["use_clipped_value_loss"], "use_huber_loss": cfg["use_huber_loss"],
-              "use_popart": mb.get("ret_mean") is not None, "use_value_active_masks": cfg["use_value_active_masks"],
+              "use_popart": mb.get("popart_running_mean") is not None, "use_value_active_masks": cfg["use_value_active_masks"],
               "use_policy_active_masks": cfg["use_policy_active_masks"],
               "std_x_coef": cfg["std_x_coef"], "std_y_coef": cfg["std_y_coef"], "actor_gain": 0.01}
     act = ACTLayer(spaces.Box(low=-1.0, high=1.0, shape=(A,)), 4, True, 0.01, config)
@@ -59,16 +59,16 @@ def reference_mappo_loss(mb, cfg):
                                    actor=act, critic=critic)
     trainer = MAPPO(config, policy)
     if config["use_popart"]:
-        # put the normaliser in the state whose debiased moments are (ret_mean, ret_var) and freeze its update, so that
-        # value_normalizer(return_batch) normalises with exactly these (the update itself is host-side torch in both worlds)
+        # start the reference's normaliser from the given running statistics; its two training-mode calls inside
+        # cal_value_loss then update it for real, and the oracle's popart_update must reproduce both sets of moments
+        from oracle.mappo_loss_oracle import popart_update
         pa = trainer.value_normalizer
-        pa.running_mean.fill_(float(mb["ret_mean"]))
-        pa.running_mean_sq.fill_(float(mb["ret_var"]) + float(mb["ret_mean"]) ** 2)
-        pa.debiasing_term.fill_(1.0)
-        m, v = pa.running_mean_var()
-        mb = dict(mb, ret_mean=m.clone(), ret_var=v.clone())
-        orig_forward = pa.forward
-        pa.forward = lambda x, train=True: orig_forward(x, train=False)
+        state = {k: mb["popart_" + k].clone() for k in ("running_mean", "running_mean_sq", "debiasing_term")}
+        pa.running_mean.copy_(state["running_mean"]); pa.running_mean_sq.copy_(state["running_mean_sq"])
+        pa.debiasing_term.copy_(state["debiasing_term"])
+        m1, v1 = popart_update(state, mb["returns"])
+        m2, v2 = popart_update(state, mb["returns"])
+        mb = dict(mb, ret_mean=m1.clone(), ret_var=v1.clone(), ret_mean_orig=m2.clone(), ret_var_orig=v2.clone())
     sample = (None, None, None, None, mb["actions"], mb["value_preds"], mb["returns"], None, mb["active_masks"],
               mb["old_logp"], mb["adv_targ"], None, None)
     value_loss, _, policy_loss, dist_entropy, _, imp_weights = trainer.ppo_update(sample)
@@ -76,4 +76,9 @@ def reference_mappo_loss(mb, cfg):
            "imp_weights": imp_weights.detach(),
            "grad_mean": act.action_out.fc_mean.t.grad.clone(), "grad_log_std": act.action_out.log_std.grad.clone(),
            "grad_values": critic.t.grad.clone()}
-    return out, mb
+    if config["use_popart"]:
+        pa = trainer.value_normalizer
+        for k, t in (("running_mean", pa.running_mean), ("running_mean_sq", pa.running_mean_sq), ("debiasing_term", pa.debiasing_term)):
+            if not torch.equal(t, state[k]):
+                raise AssertionError("popart_update != the reference's PopArt after two calls: " + k)
+    return {k: v for k, v in out.items()}, {k: v for k, v in mb.items() if not k.startswith("popart_")}

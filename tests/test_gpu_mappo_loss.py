@@ -33,7 +33,8 @@ def _check(dev, mb, cfg, want):
     values = d["values"].clone().requires_grad_(True)
     std = torch.sigmoid(log_std / cfg["std_x_coef"]) * cfg["std_y_coef"]                 # distributions.py:116
     out = mappo_loss(mean, std, values, d["actions"], d["old_logp"], d["adv_targ"], d["value_preds"], d["returns"],
-                     d["active_masks"], d["ret_mean"], d["ret_var"], clip_param=cfg["clip_param"],
+                     d["active_masks"], d["ret_mean"], d["ret_var"], d.get("ret_mean_orig"), d.get("ret_var_orig"),
+                     clip_param=cfg["clip_param"],
                      huber_delta=cfg["huber_delta"], use_huber_loss=cfg["use_huber_loss"],
                      use_clipped_value_loss=cfg["use_clipped_value_loss"],
                      use_value_active_masks=cfg["use_value_active_masks"],
@@ -66,7 +67,7 @@ def test_mappo_loss_against_the_reference_fixture(cuda_device):
 @pytest.mark.parametrize("B,A", [(1, 8), (33, 6), (1000, 8), (777, 16), (513, 80), (300, 200), (16384, 8)])
 def test_mappo_loss_against_the_oracle(cuda_device, B, A):
     """Ragged row counts, every lane-group width / columns-per-lane case, the trainer's flag combinations."""
-    from oracle.mappo_loss_oracle import mappo_loss_oracle, synthetic_minibatch
+    from oracle.mappo_loss_oracle import mappo_loss_oracle, synthetic_minibatch, without_popart
     for i, over in enumerate((dict(), dict(use_value_active_masks=True, use_policy_active_masks=True, entropy_coef=0.01,
                                            huber_delta=1.0, clip_param=0.1),
                               dict(use_huber_loss=False, use_clipped_value_loss=False, value_loss_coef=0.5, popart=False),
@@ -76,7 +77,7 @@ def test_mappo_loss_against_the_oracle(cuda_device, B, A):
         mb = synthetic_minibatch(B, A, seed=B + A + i, huber_delta=cfg["huber_delta"])
         mb["active_masks"][0] = 1.0                              # (B = 1: keep the mask sum non-zero)
         if not popart:
-            mb["ret_mean"] = mb["ret_var"] = None
+            mb = without_popart(mb)
         want = mappo_loss_oracle(**mb, **cfg)
         _check(cuda_device, mb, cfg, want)
 
@@ -116,7 +117,7 @@ def test_mappo_loss_argument_errors(cuda_device):
     from oracle.mappo_loss_oracle import synthetic_minibatch
     dev = cuda_device
     mb = synthetic_minibatch(64, 8, seed=3)
-    d = {k: v.to(dev) for k, v in mb.items()}
+    d = {k: v.to(dev) for k, v in mb.items() if not k.startswith("popart_")}
     std = torch.sigmoid(d["log_std"]) * 0.5
     with pytest.raises(ValueError):                                # masks requested, none given
         mappo_loss(d["mean"], std, d["values"], d["actions"], d["old_logp"], d["adv_targ"], d["value_preds"], d["returns"],

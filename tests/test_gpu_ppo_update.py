@@ -103,7 +103,8 @@ def test_ppo_update_matches_the_reference_pinned_oracle(cuda_device, sampler):
         d_cpu = ac_cpu.state_dict()[k] - w0
         d_gpu = ac_gpu.state_dict()[k].cpu() - w0
         scale = float(d_cpu.abs().max())
-        assert float((d_gpu - d_cpu).abs().max()) <= 2e-4 * scale + 1e-9, k
+        ulp = 1.1920929e-07 * float(w0.abs().max())             # the parameter itself is only representable to this
+        assert float((d_gpu - d_cpu).abs().max()) <= 2e-4 * scale + 2 * ulp + 1e-9, k
         moved += scale > 0
     assert moved == len(initial)
 

@@ -170,6 +170,7 @@ def test_mappo_loss_oracle_reproduces_golden():
         imp = out["imp_weights"]
         assert (imp < 1 - cfg["clip_param"]).any() and (imp > 1 + cfg["clip_param"]).any()
         if cfg["use_huber_loss"]:                                 # the fixture reaches all three huber branches
-            ret_n = (mb["returns"] - mb["ret_mean"]) / torch.sqrt(mb["ret_var"])
+            ret_n = (mb["returns"] - mb["ret_mean_orig"]) / torch.sqrt(mb["ret_var_orig"])
             e = ret_n - mb["values"]
+            assert not torch.equal(mb["ret_mean"], mb["ret_mean_orig"])      # the two PopArt calls saw different moments
             assert (e > cfg["huber_delta"]).any() and (e < -cfg["huber_delta"]).any() and (e.abs() <= cfg["huber_delta"]).any()

@@ -108,7 +108,7 @@ def test_mappo_loss_oracle_against_the_reference_trainer(shim):
     (oracle/ref_mappo_loss.py; only the MLP trunks are stubbed) against oracle/mappo_loss_oracle.py on fresh seeds -
     losses, importance weights and all three gradients identical, in every flag combination the trainer has."""
     import itertools
-    from oracle.mappo_loss_oracle import mappo_loss_oracle, synthetic_minibatch
+    from oracle.mappo_loss_oracle import mappo_loss_oracle, synthetic_minibatch, without_popart
     from oracle.ref_mappo_loss import reference_mappo_loss
     base = dict(clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.01, huber_delta=1.0, std_x_coef=1.0, std_y_coef=0.5)
     seed = 40
@@ -118,7 +118,7 @@ def test_mappo_loss_oracle_against_the_reference_trainer(shim):
                    use_policy_active_masks=pmask)
         mb = synthetic_minibatch(48, 8 if seed % 2 else 6, seed, huber_delta=1.0)
         if not popart:
-            mb["ret_mean"] = mb["ret_var"] = None
+            mb = without_popart(mb)
         ref, mb = reference_mappo_loss(mb, cfg)
         mine = mappo_loss_oracle(**mb, **cfg)
         for k in ref:
@@ -180,3 +180,82 @@ def test_ppo_update_oracle_against_the_reference_update(shim):
     for (k, a), b in zip(ac_ref.state_dict().items(), ac_mine.state_dict().values()):
         assert torch.equal(a, b), k
     assert not torch.equal(ac_ref.state_dict()["actor.0.weight"], initial["actor.0.weight"])      # the update did move them
+
+
+def _marl_config(**over):
+    cfg = dict(clip_param=0.2, ppo_epoch=1, num_mini_batch=1, data_chunk_length=None, value_loss_coef=1.0, entropy_coef=0.01,
+               max_grad_norm=10.0, huber_delta=10.0, use_valuenorm=False, use_recurrent_policy=False,
+               use_naive_recurrent_policy=False, use_max_grad_norm=True, use_clipped_value_loss=True, use_huber_loss=True,
+               use_popart=True, use_value_active_masks=False, use_policy_active_masks=False, std_x_coef=1.0, std_y_coef=0.5,
+               actor_gain=0.01, gain=0.01, hidden_size=32, use_orthogonal=True, use_feature_normalization=True,
+               use_ReLU=True, stacked_frames=1, layer_N=2, recurrent_N=1, lr=5e-4, critic_lr=5e-4, opti_eps=1e-5,
+               weight_decay=0.0, algorithm_name="mappo")
+    cfg.update(over)
+    return cfg
+
+
+def _marl_sample(policy, B, obs_dim, share_dim, A, seed):
+    g = torch.Generator().manual_seed(seed)
+    obs, share = torch.randn(B, obs_dim, generator=g), torch.randn(B, share_dim, generator=g)
+    with torch.no_grad():
+        head = policy.actor.act.action_out
+        mean = head.fc_mean(policy.actor.base(obs)) + 0.05 * torch.randn(B, A, generator=g)
+        std = torch.sigmoid(head.log_std / head.std_x_coef) * head.std_y_coef
+        actions = mean + std * torch.randn(B, A, generator=g)
+        old_logp = torch.distributions.Normal(mean, std).log_prob(actions)
+        vals = policy.critic.v_out(policy.critic.base(share))
+    value_preds = vals + 0.1 * torch.randn(B, 1, generator=g)
+    returns = 1.0 + 2.0 * torch.randn(B, 1, generator=g)
+    active = (torch.rand(B, 1, generator=g) > 0.2).float()
+    adv = torch.randn(B, 1, generator=g)
+    return (share, obs, torch.zeros(B, 1, 32), torch.zeros(B, 1, 32), actions, value_preds, returns, torch.ones(B, 1), active,
+            old_logp, adv, None, None)
+
+
+def test_mappo_update_oracle_against_the_reference_trainer(shim):
+    """The whole `MAPPO.ppo_update`: the reference's own trainer, `MAPPO_Policy` (Actor / Critic with MLPBase, ACTLayer,
+    DiagGaussian), PopArt and Adam optimisers against oracle.mappo_loss_oracle.mappo_update_oracle from the same initial
+    state - identical parameters of both networks, PopArt statistics and returned values after three updates."""
+    import contextlib
+    import copy
+    import io
+    import types
+    from agents.algorithms.marl.mappo_policy import MAPPO_Policy
+    from agents.algorithms.marl.mappo_trainer import MAPPO
+    from gym import spaces
+    from oracle.mappo_loss_oracle import mappo_update_oracle
+    obs_dim, share_dim, A, B = 10, 18, 6, 64
+    for over in (dict(), dict(use_value_active_masks=True, use_policy_active_masks=True, huber_delta=0.5),
+                 dict(use_popart=False, use_huber_loss=False, use_clipped_value_loss=False)):
+        cfg = _marl_config(**over)
+        torch.manual_seed(3)
+        box = lambda n: spaces.Box(low=-1.0, high=1.0, shape=(n,))           # noqa: E731
+        with contextlib.redirect_stdout(io.StringIO()):
+            policy = MAPPO_Policy(cfg, box(obs_dim), box(share_dim), box(A))
+        trainer = MAPPO(cfg, policy)
+        mine_policy = types.SimpleNamespace(actor=copy.deepcopy(policy.actor), critic=copy.deepcopy(policy.critic))
+        mine_policy.actor_optimizer = torch.optim.Adam(mine_policy.actor.parameters(), lr=cfg["lr"], eps=cfg["opti_eps"])
+        mine_policy.critic_optimizer = torch.optim.Adam(mine_policy.critic.parameters(), lr=cfg["critic_lr"], eps=cfg["opti_eps"])
+        mine = types.SimpleNamespace(policy=mine_policy, clip_param=cfg["clip_param"], value_loss_coef=cfg["value_loss_coef"],
+                                     entropy_coef=cfg["entropy_coef"], max_grad_norm=cfg["max_grad_norm"],
+                                     huber_delta=cfg["huber_delta"], _use_popart=cfg["use_popart"],
+                                     _use_huber_loss=cfg["use_huber_loss"], _use_clipped_value_loss=cfg["use_clipped_value_loss"],
+                                     _use_value_active_masks=cfg["use_value_active_masks"],
+                                     _use_policy_active_masks=cfg["use_policy_active_masks"], popart=None)
+        if cfg["use_popart"]:
+            pa = trainer.value_normalizer
+            mine.popart = dict(running_mean=pa.running_mean.clone(), running_mean_sq=pa.running_mean_sq.clone(),
+                               debiasing_term=pa.debiasing_term.clone())
+        for it in range(3):
+            sample = _marl_sample(policy, B, obs_dim, share_dim, A, seed=100 + it)
+            ref = trainer.ppo_update(sample)
+            out = mappo_update_oracle(mine, sample)
+            for a, b in zip(ref, out):
+                assert torch.equal(torch.as_tensor(a), torch.as_tensor(b)), (over, it)
+        for net_ref, net_mine in ((policy.actor, mine_policy.actor), (policy.critic, mine_policy.critic)):
+            for (k, a), b in zip(net_ref.state_dict().items(), net_mine.state_dict().values()):
+                assert torch.equal(a, b), (over, k)
+        if cfg["use_popart"]:
+            pa = trainer.value_normalizer
+            assert torch.equal(pa.running_mean, mine.popart["running_mean"]) and torch.equal(pa.debiasing_term, mine.popart["debiasing_term"])
+            assert float(pa.debiasing_term) > 0
