@@ -10,8 +10,10 @@ distribution, both losses and their backward on one kernel,
     (policy_loss - dist_entropy * entropy_coef).backward(); clip; actor_optimizer.step()        unchanged
     (value_loss * value_loss_coef).backward(); clip; critic_optimizer.step()                    unchanged
 
-Use:  `MAPPO.ppo_update = mappo_ppo_update`.  Recurrent policies, discrete actions and `available_actions` are outside the
-benchmark's configurations and raise.
+Use:  `MAPPO.ppo_update = mappo_ppo_update`, `IPPO.ppo_update = ippo_ppo_update` (agents/algorithms/marl/ippo_trainer.py:
+the same update; its value normaliser - ValueNorm in cfg/ippo/config.yaml - is updated once and both error terms are
+normalised with the same moments, ippo_trainer.py:74-77).  Recurrent policies, discrete actions and `available_actions`
+are outside the benchmark's configurations and raise.
 """
 import torch
 import torch.nn as nn
@@ -34,6 +36,14 @@ def _t(x, like):
 
 
 def mappo_ppo_update(self, sample, update_actor=True):
+    return _ppo_update(self, sample, update_actor, ippo=False)
+
+
+def ippo_ppo_update(self, sample, update_actor=True):
+    return _ppo_update(self, sample, update_actor, ippo=True)
+
+
+def _ppo_update(self, sample, update_actor, ippo):
     (share_obs_batch, obs_batch, _rnn_a, _rnn_c, actions_batch, value_preds_batch, return_batch, _masks_batch,
      active_masks_batch, old_action_log_probs_batch, adv_targ, available_actions_batch, _) = sample
     actor, critic = self.policy.actor, self.policy.critic
@@ -51,10 +61,15 @@ def mappo_ppo_update(self, sample, update_actor=True):
     values = critic.v_out(critic.base(share_obs_batch))                          # actor_critic.py:163-166
 
     moments = [None, None, None, None]
-    if self._use_valuenorm:                                                      # mappo_trainer.py:75-78: the statistics are
+    if ippo:
+        if self._use_popart or self._use_valuenorm:                              # ippo_trainer.py:74-77: one update, one pair
+            self.value_normalizer.update(return_batch)
+            m, v = self.value_normalizer.running_mean_var()
+            moments = [m.clone(), v.clone(), None, None]
+    elif self._use_valuenorm:                                                    # mappo_trainer.py:75-78: the statistics are
         self.value_normalizer.update(return_batch)                               # updated, but the errors normalised there are
                                                                                  # overwritten by the else branch at :83-85
-    if self._use_popart:                                                         # mappo_trainer.py:80-82: two training-mode calls,
+    if self._use_popart and not ippo:                                            # mappo_trainer.py:80-82: two training-mode calls,
         self.value_normalizer(return_batch)                                      # the first normalises the clipped error,
         m1, v1 = self.value_normalizer.running_mean_var()
         self.value_normalizer(return_batch)                                      # the second the original one

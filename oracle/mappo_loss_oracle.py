@@ -128,19 +128,26 @@ def mappo_loss_oracle(mean, log_std, values, actions, old_logp, adv_targ, value_
             "grad_mean": g_mean, "grad_log_std": g_ls, "grad_values": g_v}
 
 
-def mappo_update_oracle(tr, sample, update_actor=True):
+def mappo_update_oracle(tr, sample, update_actor=True, ippo=False):
     """`MAPPO.ppo_update` (mappo_trainer.py:106-172) for the feed-forward Box-action policy on an object `tr` with the
     trainer's attributes (policy.actor / .critic / .actor_optimizer / .critic_optimizer, clip_param, value_loss_coef,
     entropy_coef, max_grad_norm, huber_delta, the _use_* flags) and `tr.popart` = the PopArt state dict (see
     `popart_update`) or None.  `sample` is the generator's tuple (separated_buffer.py:225-228).  Returns
-    (value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, imp_weights)."""
+    (value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, imp_weights).
+    `ippo=True`: `IPPO.ppo_update` (ippo_trainer.py:101-170) - the same update except that its normaliser (ValueNorm, whose
+    update is arithmetically PopArt's, valuenorm.py:39-55) is updated ONCE and both error terms share the moments
+    (ippo_trainer.py:74-77); `tr.popart` then holds the ValueNorm state and `tr._use_valuenorm` says whether it is on."""
     (share_obs, obs, _ra, _rc, actions, value_preds, returns, _masks, active_masks, old_logp, adv_targ, _avail, _f) = sample
     actor, critic = tr.policy.actor, tr.policy.critic
     head = actor.act.action_out
     mean = head.fc_mean(actor.base(obs))                                         # actor_critic.py:95, distributions.py:115
     values = critic.v_out(critic.base(share_obs))                                # actor_critic.py:163-166
     moments = (None, None, None, None)
-    if tr._use_popart:                                                           # two calls, two updates (see the header)
+    if ippo:
+        if tr._use_popart or tr._use_valuenorm:
+            m, v = popart_update(tr.popart, returns)
+            moments = (m.clone(), v.clone(), None, None)
+    elif tr._use_popart:                                                         # two calls, two updates (see the header)
         m1, v1 = popart_update(tr.popart, returns)
         m1, v1 = m1.clone(), v1.clone()
         m2, v2 = popart_update(tr.popart, returns)

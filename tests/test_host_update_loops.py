@@ -110,3 +110,48 @@ def test_mappo_update_host_loop_equals_the_pinned_oracle(monkeypatch):
             assert torch.allclose(x, y, rtol=1e-5, atol=1e-7), over
         if not nopop:                                    # PopArt was called exactly as often on both sides
             assert all(torch.equal(ora.popart[k], drop.popart[k]) for k in ora.popart)
+
+
+def test_ippo_update_host_loop_equals_the_pinned_oracle(monkeypatch):
+    """IPPO's normaliser protocol (one `update`, both error terms on the same moments) through the drop-in."""
+    t = importlib.import_module("test_gpu_mappo_update")
+    from massive_marl_benchmark_b200 import mappo_update as mu
+    from massive_marl_benchmark_b200.mappo_loss import MappoLossOut
+    from oracle.mappo_loss_oracle import mappo_loss_terms, mappo_update_oracle, popart_update
+
+    seen = []
+
+    def stand_in(mean, std, values, actions, old_logp, adv, vp, ret, active, m1=None, v1=None, m2=None, v2=None, **cfg):
+        seen.append((m1 is not None, m2 is not None))
+        ls = torch.log(std / 0.5 / (1 - std / 0.5))
+        pl, ent, vl, imp, lp = mappo_loss_terms(mean, ls, values, actions, old_logp, adv, vp, ret, active, m1, v1, m2, v2, **cfg)
+        return MappoLossOut(pl, vl, ent, imp.detach(), lp.detach())
+
+    class _ValueNorm(t._PopArt):                         # valuenorm.py:39-55: update() only, no normalising call
+        def update(self, x):
+            popart_update(self.state, x)
+
+        def __call__(self, x):
+            raise AssertionError("IPPO never calls the normaliser in training mode")
+
+    monkeypatch.setattr(mu, "mappo_loss", stand_in)
+    torch.manual_seed(6)
+    a1, c1 = t._Actor(12, 6, hidden=16), t._Critic(12, hidden=16)
+    a2, c2 = copy.deepcopy(a1), copy.deepcopy(c1)
+
+    def state():
+        return {"running_mean": torch.zeros(1), "running_mean_sq": torch.zeros(1), "debiasing_term": torch.tensor(0.0)}
+
+    ora = t._trainer(a1, c1, state(), _use_popart=False, _use_valuenorm=True)
+    drop = t._trainer(a2, c2, state(), _use_popart=False, _use_valuenorm=True)
+    drop.value_normalizer = _ValueNorm(drop.popart)
+    for it in range(3):
+        s = t._sample(a1, c1, 64, 12, 12, 6, 400 + it)
+        want, got = mappo_update_oracle(ora, s, ippo=True), mu.ippo_ppo_update(drop, s)
+        for x, y in zip(want[:5], got[:5]):
+            assert abs(float(x) - float(y)) <= 1e-6 * abs(float(x))
+    assert seen == [(True, False)] * 3
+    assert all(torch.equal(ora.popart[k], drop.popart[k]) for k in ora.popart) and float(ora.popart["debiasing_term"]) > 0
+    for x, y in zip(list(a1.state_dict().values()) + list(c1.state_dict().values()),
+                    list(a2.state_dict().values()) + list(c2.state_dict().values())):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-7)

@@ -259,3 +259,52 @@ def test_mappo_update_oracle_against_the_reference_trainer(shim):
             pa = trainer.value_normalizer
             assert torch.equal(pa.running_mean, mine.popart["running_mean"]) and torch.equal(pa.debiasing_term, mine.popart["debiasing_term"])
             assert float(pa.debiasing_term) > 0
+
+
+def test_ippo_update_oracle_against_the_reference_trainer(shim):
+    """`IPPO.ppo_update` (decentralised critic, ValueNorm as in cfg/ippo/config.yaml): the reference's own IPPO trainer +
+    IPPO_Policy + ValueNorm + Adam against mappo_update_oracle(ippo=True) - identical parameters, normaliser statistics and
+    returned values after three updates."""
+    import contextlib
+    import copy
+    import io
+    import types
+    from agents.algorithms.marl.ippo_policy import IPPO_Policy
+    from agents.algorithms.marl.ippo_trainer import IPPO
+    from gym import spaces
+    from oracle.mappo_loss_oracle import mappo_update_oracle
+    obs_dim, A, B = 10, 6, 64
+    for over in (dict(use_popart=False, use_valuenorm=True), dict(use_popart=False, use_valuenorm=False, use_huber_loss=False)):
+        cfg = _marl_config(algorithm_name="ippo", **over)
+        torch.manual_seed(5)
+        box = lambda n: spaces.Box(low=-1.0, high=1.0, shape=(n,))           # noqa: E731
+        with contextlib.redirect_stdout(io.StringIO()):
+            policy = IPPO_Policy(cfg, box(obs_dim), box(obs_dim), box(A))     # use_centralized_V False: the critic sees obs
+        trainer = IPPO(cfg, policy)
+        mine_policy = types.SimpleNamespace(actor=copy.deepcopy(policy.actor), critic=copy.deepcopy(policy.critic))
+        mine_policy.actor_optimizer = torch.optim.Adam(mine_policy.actor.parameters(), lr=cfg["lr"], eps=cfg["opti_eps"])
+        mine_policy.critic_optimizer = torch.optim.Adam(mine_policy.critic.parameters(), lr=cfg["critic_lr"], eps=cfg["opti_eps"])
+        mine = types.SimpleNamespace(policy=mine_policy, clip_param=cfg["clip_param"], value_loss_coef=cfg["value_loss_coef"],
+                                     entropy_coef=cfg["entropy_coef"], max_grad_norm=cfg["max_grad_norm"],
+                                     huber_delta=cfg["huber_delta"], _use_popart=cfg["use_popart"],
+                                     _use_valuenorm=cfg["use_valuenorm"], _use_huber_loss=cfg["use_huber_loss"],
+                                     _use_clipped_value_loss=cfg["use_clipped_value_loss"],
+                                     _use_value_active_masks=cfg["use_value_active_masks"],
+                                     _use_policy_active_masks=cfg["use_policy_active_masks"], popart=None)
+        if cfg["use_valuenorm"]:
+            vn = trainer.value_normalizer
+            mine.popart = dict(running_mean=vn.running_mean.clone(), running_mean_sq=vn.running_mean_sq.clone(),
+                               debiasing_term=vn.debiasing_term.clone())
+        for it in range(3):
+            sample = _marl_sample(policy, B, obs_dim, obs_dim, A, seed=300 + it)
+            sample = (sample[1],) + sample[1:]                               # share_obs = obs
+            ref = trainer.ppo_update(sample)
+            out = mappo_update_oracle(mine, sample, ippo=True)
+            for a, b in zip(ref, out):
+                assert torch.equal(torch.as_tensor(a), torch.as_tensor(b)), (over, it)
+        for net_ref, net_mine in ((policy.actor, mine_policy.actor), (policy.critic, mine_policy.critic)):
+            for (k, a), b in zip(net_ref.state_dict().items(), net_mine.state_dict().values()):
+                assert torch.equal(a, b), (over, k)
+        if cfg["use_valuenorm"]:
+            vn = trainer.value_normalizer
+            assert torch.equal(vn.running_mean, mine.popart["running_mean"]) and float(vn.debiasing_term) > 0
