@@ -10,7 +10,9 @@ distribution, both losses and their backward on one kernel,
     (policy_loss - dist_entropy * entropy_coef).backward(); clip; actor_optimizer.step()        unchanged
     (value_loss * value_loss_coef).backward(); clip; critic_optimizer.step()                    unchanged
 
-Use:  `MAPPO.ppo_update = mappo_ppo_update`, `IPPO.ppo_update = ippo_ppo_update` (agents/algorithms/marl/ippo_trainer.py:
+Use:  `MAPPO.ppo_update = mappo_ppo_update`, `HAPPO.ppo_update = happo_ppo_update` (agents/algorithms/marl/happo_trainer.py:
+MAPPO's update with the factor of the previously updated agents inside the surrogate; it is positive, so it folds into the
+advantage), `IPPO.ppo_update = ippo_ppo_update` (agents/algorithms/marl/ippo_trainer.py:
 the same update; its value normaliser - ValueNorm in cfg/ippo/config.yaml - is updated once and both error terms are
 normalised with the same moments, ippo_trainer.py:74-77).  Recurrent policies, discrete actions and `available_actions`
 are outside the benchmark's configurations and raise.
@@ -36,16 +38,20 @@ def _t(x, like):
 
 
 def mappo_ppo_update(self, sample, update_actor=True):
-    return _ppo_update(self, sample, update_actor, ippo=False)
+    return _ppo_update(self, sample, update_actor)
 
 
 def ippo_ppo_update(self, sample, update_actor=True):
     return _ppo_update(self, sample, update_actor, ippo=True)
 
 
-def _ppo_update(self, sample, update_actor, ippo):
+def happo_ppo_update(self, sample, update_actor=True):
+    return _ppo_update(self, sample, update_actor, happo=True)
+
+
+def _ppo_update(self, sample, update_actor, ippo=False, happo=False):
     (share_obs_batch, obs_batch, _rnn_a, _rnn_c, actions_batch, value_preds_batch, return_batch, _masks_batch,
-     active_masks_batch, old_action_log_probs_batch, adv_targ, available_actions_batch, _) = sample
+     active_masks_batch, old_action_log_probs_batch, adv_targ, available_actions_batch, factor_batch) = sample
     actor, critic = self.policy.actor, self.policy.critic
     if getattr(self, "_use_recurrent_policy", False) or getattr(self, "_use_naive_recurrent", False):
         raise NotImplementedError("recurrent policies are outside the benchmark's configurations")
@@ -66,7 +72,7 @@ def _ppo_update(self, sample, update_actor, ippo):
             self.value_normalizer.update(return_batch)
             m, v = self.value_normalizer.running_mean_var()
             moments = [m.clone(), v.clone(), None, None]
-    elif self._use_valuenorm:                                                    # mappo_trainer.py:75-78: the statistics are
+    elif getattr(self, "_use_valuenorm", False):                                 # mappo_trainer.py:75-78: the statistics are
         self.value_normalizer.update(return_batch)                               # updated, but the errors normalised there are
                                                                                  # overwritten by the else branch at :83-85
     if self._use_popart and not ippo:                                            # mappo_trainer.py:80-82: two training-mode calls,
@@ -76,7 +82,14 @@ def _ppo_update(self, sample, update_actor, ippo):
         m2, v2 = self.value_normalizer.running_mean_var()
         moments = [m1.clone(), v1.clone(), m2.clone(), v2.clone()]
 
-    out = mappo_loss(mean, std, values, _t(actions_batch, ref), _t(old_action_log_probs_batch, ref), _t(adv_targ, ref),
+    adv_targ = _t(adv_targ, ref)
+    if happo:
+        # happo_trainer.py:135-141: -sum_j factor[b, j] * min(surr1, surr2)[b].  The factor is a product of probability ratios,
+        # hence positive, and min(w * a * f, clamp(w) * a * f) = f * min(w * a, clamp(w) * a) for f > 0: the row factor
+        # folds into the advantage and the same kernel serves
+        adv_targ = adv_targ * _t(factor_batch, ref).sum(dim=-1, keepdim=True)
+
+    out = mappo_loss(mean, std, values, _t(actions_batch, ref), _t(old_action_log_probs_batch, ref), adv_targ,
                      _t(value_preds_batch, ref), return_batch,
                      None if active_masks_batch is None else _t(active_masks_batch, ref), *moments,
                      clip_param=self.clip_param, huber_delta=self.huber_delta, use_huber_loss=self._use_huber_loss,

@@ -54,9 +54,11 @@ def popart_update(state, batch, beta=0.99999, epsilon=1e-5):
 def mappo_loss_terms(mean, log_std, values, actions, old_logp, adv_targ, value_preds, returns, active_masks,
                      ret_mean=None, ret_var=None, ret_mean_orig=None, ret_var_orig=None, clip_param=0.2, huber_delta=10.0,
                      use_huber_loss=True, use_clipped_value_loss=True, use_value_active_masks=False,
-                     use_policy_active_masks=False, std_x_coef=1.0, std_y_coef=0.5):
+                     use_policy_active_masks=False, std_x_coef=1.0, std_y_coef=0.5, factor=None):
     """The statements themselves, on whatever graph `mean`, `log_std`, `values` belong to.  Returns
-    (policy_loss, dist_entropy, value_loss, imp_weights, action_log_probs)."""
+    (policy_loss, dist_entropy, value_loss, imp_weights, action_log_probs).  `factor` [B,A]: HAPPO's product of the
+    previously updated agents' probability ratios, multiplied into the surrogate before the sum over the last dimension
+    (happo_trainer.py:135-141); None = MAPPO / IPPO."""
     action_std = torch.sigmoid(log_std / std_x_coef) * std_y_coef                        # distributions.py:116
     dist = torch.distributions.Normal(mean, action_std)                                  # FixedNormal
     action_log_probs = dist.log_prob(actions)                                            # distributions.py:34
@@ -68,7 +70,12 @@ def mappo_loss_terms(mean, log_std, values, actions, old_logp, adv_targ, value_p
     imp_weights = torch.exp((action_log_probs - old_logp).sum(dim=-1, keepdim=True))     # mappo_trainer.py:128
     surr1 = imp_weights * adv_targ
     surr2 = torch.clamp(imp_weights, 1.0 - clip_param, 1.0 + clip_param) * adv_targ
-    if use_policy_active_masks:
+    if factor is not None:                                                               # happo_trainer.py:135-141
+        if use_policy_active_masks:
+            policy_action_loss = (-torch.sum(factor * torch.min(surr1, surr2), dim=-1, keepdim=True) * active_masks).sum() / active_masks.sum()
+        else:
+            policy_action_loss = -torch.sum(factor * torch.min(surr1, surr2), dim=-1, keepdim=True).mean()
+    elif use_policy_active_masks:
         policy_action_loss = (-torch.sum(torch.min(surr1, surr2), dim=-1, keepdim=True) * active_masks).sum() / active_masks.sum()
     else:
         policy_action_loss = -torch.sum(torch.min(surr1, surr2), dim=-1, keepdim=True).mean()
@@ -128,7 +135,7 @@ def mappo_loss_oracle(mean, log_std, values, actions, old_logp, adv_targ, value_
             "grad_mean": g_mean, "grad_log_std": g_ls, "grad_values": g_v}
 
 
-def mappo_update_oracle(tr, sample, update_actor=True, ippo=False):
+def mappo_update_oracle(tr, sample, update_actor=True, ippo=False, happo=False):
     """`MAPPO.ppo_update` (mappo_trainer.py:106-172) for the feed-forward Box-action policy on an object `tr` with the
     trainer's attributes (policy.actor / .critic / .actor_optimizer / .critic_optimizer, clip_param, value_loss_coef,
     entropy_coef, max_grad_norm, huber_delta, the _use_* flags) and `tr.popart` = the PopArt state dict (see
@@ -136,8 +143,10 @@ def mappo_update_oracle(tr, sample, update_actor=True, ippo=False):
     (value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, imp_weights).
     `ippo=True`: `IPPO.ppo_update` (ippo_trainer.py:101-170) - the same update except that its normaliser (ValueNorm, whose
     update is arithmetically PopArt's, valuenorm.py:39-55) is updated ONCE and both error terms share the moments
-    (ippo_trainer.py:74-77); `tr.popart` then holds the ValueNorm state and `tr._use_valuenorm` says whether it is on."""
-    (share_obs, obs, _ra, _rc, actions, value_preds, returns, _masks, active_masks, old_logp, adv_targ, _avail, _f) = sample
+    (ippo_trainer.py:74-77); `tr.popart` then holds the ValueNorm state and `tr._use_valuenorm` says whether it is on.
+    `happo=True`: `HAPPO.ppo_update` (happo_trainer.py:93-170) - MAPPO's update with the sample's 13th entry, the factor
+    [B,A], inside the surrogate."""
+    (share_obs, obs, _ra, _rc, actions, value_preds, returns, _masks, active_masks, old_logp, adv_targ, _avail, factor) = sample
     actor, critic = tr.policy.actor, tr.policy.critic
     head = actor.act.action_out
     mean = head.fc_mean(actor.base(obs))                                         # actor_critic.py:95, distributions.py:115
@@ -156,7 +165,8 @@ def mappo_update_oracle(tr, sample, update_actor=True, ippo=False):
         mean, head.log_std, values, actions, old_logp, adv_targ, value_preds, returns, active_masks, *moments,
         clip_param=tr.clip_param, huber_delta=tr.huber_delta, use_huber_loss=tr._use_huber_loss,
         use_clipped_value_loss=tr._use_clipped_value_loss, use_value_active_masks=tr._use_value_active_masks,
-        use_policy_active_masks=tr._use_policy_active_masks, std_x_coef=head.std_x_coef, std_y_coef=head.std_y_coef)
+        use_policy_active_masks=tr._use_policy_active_masks, std_x_coef=head.std_x_coef, std_y_coef=head.std_y_coef,
+        factor=factor if happo else None)
     tr.policy.actor_optimizer.zero_grad()                                        # mappo_trainer.py:143-153
     if update_actor:
         (policy_loss - dist_entropy * tr.entropy_coef).backward()

@@ -155,3 +155,42 @@ def test_ippo_update_host_loop_equals_the_pinned_oracle(monkeypatch):
     for x, y in zip(list(a1.state_dict().values()) + list(c1.state_dict().values()),
                     list(a2.state_dict().values()) + list(c2.state_dict().values())):
         assert torch.allclose(x, y, rtol=1e-5, atol=1e-7)
+
+
+def test_happo_update_host_loop_equals_the_pinned_oracle(monkeypatch):
+    """HAPPO's factor folded into the advantage (positive factor) against the oracle that keeps it inside the surrogate
+    as the reference does."""
+    t = importlib.import_module("test_gpu_mappo_update")
+    from massive_marl_benchmark_b200 import mappo_update as mu
+    from massive_marl_benchmark_b200.mappo_loss import MappoLossOut
+    from oracle.mappo_loss_oracle import mappo_loss_terms, mappo_update_oracle
+
+    def stand_in(mean, std, values, actions, old_logp, adv, vp, ret, active, m1=None, v1=None, m2=None, v2=None, **cfg):
+        ls = torch.log(std / 0.5 / (1 - std / 0.5))
+        pl, ent, vl, imp, lp = mappo_loss_terms(mean, ls, values, actions, old_logp, adv, vp, ret, active, m1, v1, m2, v2, **cfg)
+        return MappoLossOut(pl, vl, ent, imp.detach(), lp.detach())
+
+    monkeypatch.setattr(mu, "mappo_loss", stand_in)
+    for over in (dict(), dict(_use_policy_active_masks=True)):
+        torch.manual_seed(7)
+        a1, c1 = t._Actor(12, 6, hidden=16), t._Critic(20, hidden=16)
+        a2, c2 = copy.deepcopy(a1), copy.deepcopy(c1)
+
+        def state():
+            deb = torch.tensor(1.0 - 0.99999 ** 300)
+            return {"running_mean": torch.tensor([0.9]) * deb, "running_mean_sq": torch.tensor([4.5]) * deb,
+                    "debiasing_term": deb.clone()}
+
+        ora, drop = t._trainer(a1, c1, state(), **over), t._trainer(a2, c2, state(), **over)
+        del drop._use_valuenorm                           # the HAPPO trainer has no such attribute (happo_trainer.py:30-42)
+        for it in range(3):
+            s = t._sample(a1, c1, 64, 12, 20, 6, 700 + it)
+            g = torch.Generator().manual_seed(800 + it)
+            factor = torch.exp(0.3 * torch.randn(64, 1, generator=g))
+            s = s[:12] + (factor if it else factor.repeat(1, 6) / 6,)
+            want, got = mappo_update_oracle(ora, s, happo=True), mu.happo_ppo_update(drop, s)
+            for x, y in zip(want[:5], got[:5]):
+                assert abs(float(x) - float(y)) <= 2e-6 * abs(float(x)) + 1e-8, over
+        for x, y in zip(list(a1.state_dict().values()) + list(c1.state_dict().values()),
+                        list(a2.state_dict().values()) + list(c2.state_dict().values())):
+            assert torch.allclose(x, y, rtol=1e-5, atol=2e-7), over

@@ -308,3 +308,51 @@ def test_ippo_update_oracle_against_the_reference_trainer(shim):
         if cfg["use_valuenorm"]:
             vn = trainer.value_normalizer
             assert torch.equal(vn.running_mean, mine.popart["running_mean"]) and float(vn.debiasing_term) > 0
+
+
+def test_happo_update_oracle_against_the_reference_trainer(shim):
+    """`HAPPO.ppo_update` (the factor of the previously updated agents inside the surrogate, PopArt): the reference's own
+    HAPPO trainer + HAPPO_Policy against mappo_update_oracle(happo=True)."""
+    import contextlib
+    import copy
+    import io
+    import types
+    from agents.algorithms.marl.happo_policy import HAPPO_Policy
+    from agents.algorithms.marl.happo_trainer import HAPPO
+    from gym import spaces
+    from oracle.mappo_loss_oracle import mappo_update_oracle
+    obs_dim, share_dim, A, B = 10, 18, 6, 64
+    for over in (dict(), dict(use_policy_active_masks=True, use_value_active_masks=True, use_popart=False)):
+        cfg = _marl_config(algorithm_name="happo", **over)
+        torch.manual_seed(8)
+        box = lambda n: spaces.Box(low=-1.0, high=1.0, shape=(n,))           # noqa: E731
+        with contextlib.redirect_stdout(io.StringIO()):
+            policy = HAPPO_Policy(cfg, box(obs_dim), box(share_dim), box(A))
+        trainer = HAPPO(cfg, policy)
+        mine_policy = types.SimpleNamespace(actor=copy.deepcopy(policy.actor), critic=copy.deepcopy(policy.critic))
+        mine_policy.actor_optimizer = torch.optim.Adam(mine_policy.actor.parameters(), lr=cfg["lr"], eps=cfg["opti_eps"])
+        mine_policy.critic_optimizer = torch.optim.Adam(mine_policy.critic.parameters(), lr=cfg["critic_lr"], eps=cfg["opti_eps"])
+        mine = types.SimpleNamespace(policy=mine_policy, clip_param=cfg["clip_param"], value_loss_coef=cfg["value_loss_coef"],
+                                     entropy_coef=cfg["entropy_coef"], max_grad_norm=cfg["max_grad_norm"],
+                                     huber_delta=cfg["huber_delta"], _use_popart=cfg["use_popart"], _use_valuenorm=False,
+                                     _use_huber_loss=cfg["use_huber_loss"], _use_clipped_value_loss=cfg["use_clipped_value_loss"],
+                                     _use_value_active_masks=cfg["use_value_active_masks"],
+                                     _use_policy_active_masks=cfg["use_policy_active_masks"], popart=None)
+        if cfg["use_popart"]:
+            pa = trainer.value_normalizer
+            mine.popart = dict(running_mean=pa.running_mean.clone(), running_mean_sq=pa.running_mean_sq.clone(),
+                               debiasing_term=pa.debiasing_term.clone())
+        for it in range(3):
+            sample = _marl_sample(policy, B, obs_dim, share_dim, A, seed=500 + it)
+            g = torch.Generator().manual_seed(600 + it)
+            factor = torch.exp(0.2 * torch.randn(B, 1, generator=g))                   # runner.py:271,312-313: [T, N, 1], exp(...)
+            if it == 2:
+                factor = factor.repeat(1, A) / A                                        # (the trainer also takes one column per dim)
+            sample = sample[:12] + (factor,)
+            ref = trainer.ppo_update(sample)
+            out = mappo_update_oracle(mine, sample, happo=True)
+            for a, b in zip(ref, out):
+                assert torch.equal(torch.as_tensor(a), torch.as_tensor(b)), (over, it)
+        for net_ref, net_mine in ((policy.actor, mine_policy.actor), (policy.critic, mine_policy.critic)):
+            for (k, a), b in zip(net_ref.state_dict().items(), net_mine.state_dict().values()):
+                assert torch.equal(a, b), (over, k)
