@@ -141,3 +141,32 @@ def test_default_consts_match_reference_yaml():
     assert np.signbit(np.float32(list(c.inv_start_rot)[0]))        # quat_conjugate((0,0,0,1)) has negative zeros
     c2 = L.default_ant_consts({"upWeight": 0.25, "episodeLength": 500})
     assert abs(c2.up_weight - 0.25) < 1e-7 and c2.max_episode_length == 500.0
+
+
+def test_ppo_checkpoint_format(tmp_path):
+    """`model_{it}.pt` = the state dict of two Sequentials with Linear layers at the even indices + `log_std`
+    (ppo.py:90-97, module.py:25-55): written, read back, sizes inferred from the tensors, malformed files refused."""
+    import pytest
+    import torch
+    from massive_marl_benchmark_b200 import checkpoints as ck
+    m = ck.PPOModules([60, 1024, 1024, 512, 8], [60, 1024, 1024, 512, 1], 8)
+    assert sorted(m.state_dict()) == sorted(["log_std"] + ["%s.%d.%s" % (n, i, p) for n in ("actor", "critic")
+                                                           for i in (0, 2, 4, 6) for p in ("weight", "bias")])
+    with torch.no_grad():
+        m.log_std.fill_(-0.3)
+    path = ck.save_ppo(m, str(tmp_path), 42)
+    m2, it = ck.load_ppo(path)
+    assert it == 42 and not m2.asymmetric
+    x = torch.randn(3, 60)
+    assert torch.equal(m2.actor(x), m.actor(x)) and torch.equal(m2.critic(x), m.critic(x)) and float(m2.log_std[0]) == float(m.log_std[0])
+    assert [tuple(l.weight.shape) for l in m2.actor if hasattr(l, "weight")] == [(1024, 60), (1024, 1024), (512, 1024), (8, 512)]
+    sd = dict(m.state_dict())
+    bad = dict(sd); bad.pop("actor.2.weight")
+    with pytest.raises(ValueError):
+        ck.ppo_modules_from_state_dict(bad)
+    bad = dict(sd); bad["log_std"] = torch.zeros(3)
+    with pytest.raises(ValueError):
+        ck.ppo_modules_from_state_dict(bad)
+    bad = dict(sd); bad["critic.6.weight"] = torch.zeros(2, 512); bad["critic.6.bias"] = torch.zeros(2)
+    with pytest.raises(ValueError):
+        ck.ppo_modules_from_state_dict(bad)

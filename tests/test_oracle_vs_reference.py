@@ -356,3 +356,42 @@ def test_happo_update_oracle_against_the_reference_trainer(shim):
         for net_ref, net_mine in ((policy.actor, mine_policy.actor), (policy.critic, mine_policy.critic)):
             for (k, a), b in zip(net_ref.state_dict().items(), net_mine.state_dict().values()):
                 assert torch.equal(a, b), (over, k)
+
+
+def test_checkpoint_formats_round_trip_with_the_reference_classes(shim, tmp_path):
+    """PPO: a `model_{it}.pt` written by the reference's `PPO.save` loads into checkpoints.load_ppo with identical
+    forward outputs, and a file written by checkpoints.save_ppo loads into the reference's ActorCritic (strict keys).
+    MARL: the shipped TenAnt MAPPO checkpoints (logs/ten_ant/mappo/models_seed-1) load into the reference's Actor / Critic
+    and through checkpoints.load_marl_agents with the same tensors."""
+    import contextlib
+    import io
+    import types
+    import agents.algorithms.rl.ppo as pkg
+    from agents.algorithms.rl.ppo.module import ActorCritic
+    from agents.algorithms.rl.ppo.storage import RolloutStorage
+    pkg.RolloutStorage, pkg.ActorCritic = RolloutStorage, ActorCritic
+    from agents.algorithms.rl.ppo.ppo import PPO
+    from massive_marl_benchmark_b200 import checkpoints as ck
+    cfg = {"pi_hid_sizes": [48, 24, 12], "vf_hid_sizes": [40, 20], "activation": "elu"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ActorCritic((17,), (23,), (5,), 0.7, cfg, asymmetric=True)
+    path = str(tmp_path / "model_1200.pt")
+    PPO.save(types.SimpleNamespace(actor_critic=ref), path)                       # ppo.py:96-97
+    mine, it = ck.load_ppo(path)
+    assert it == 1200 and mine.asymmetric
+    x, s = torch.randn(9, 17), torch.randn(9, 23)
+    assert torch.equal(mine.actor(x), ref.actor(x)) and torch.equal(mine.critic(s), ref.critic(s))
+    assert torch.equal(mine.log_std, ref.log_std)
+    back = ck.save_ppo(mine, str(tmp_path), 7)
+    assert back.endswith("model_7.pt")
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref2 = ActorCritic((17,), (23,), (5,), 1.0, cfg, asymmetric=True)
+    loader = types.SimpleNamespace(actor_critic=ref2, current_learning_iteration=0)
+    PPO.load(loader, back)                                                        # ppo.py:90-94
+    assert loader.current_learning_iteration == 7 and torch.equal(ref2.actor(x), ref.actor(x))
+
+    model_dir = os.path.join(REF, "logs/ten_ant/mappo/models_seed-1")
+    actors, critics = ck.load_marl_agents(model_dir, 10)
+    assert len(actors) == len(critics) == 10
+    assert actors[3]["act.action_out.fc_mean.weight"].shape == (8, 512) and critics[3]["v_out.weight"].shape == (1, 512)
+    assert actors[0]["base.mlp.fc1.0.weight"].shape == (512, 46) and critics[0]["base.mlp.fc1.0.weight"].shape == (512, 388)
