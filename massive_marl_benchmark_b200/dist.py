@@ -101,6 +101,16 @@ def all_reduce_grads(parameters, group=None, bucket_bytes=64 << 20):
     flush()
 
 
+def mean_over_ranks(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Average of a (scalar) tensor over the shards - e.g. the KL estimate that drives the adaptive step size, which every
+    rank must see identically.  Returns a new tensor; identity without a process group."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return t
+    out = t.detach().clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out / dist.get_world_size(group)
+
+
 def max_over_ranks(value: float, device) -> float:
     """Device-timed durations are reported as the max over ranks."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

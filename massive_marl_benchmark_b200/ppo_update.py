@@ -11,6 +11,11 @@ and one host read-back per minibatch (the adaptive-KL decision, which the refere
 three.  Use:  `PPO.update = ppo_update`  (or call `ppo_update(ppo)`); `ppo` needs the attributes `PPO.__init__` sets
 (ppo.py:30-97): storage, actor_critic, optimizer, num_mini_batches, num_learning_epochs, clip_param, value_loss_coef,
 entropy_coef, use_clipped_value_loss, desired_kl, schedule, step_size, max_grad_norm, asymmetric.
+
+Env-sharded data parallel (one process per GPU, each with its own envs and storage): set `ppo.grad_sync =
+dist.all_reduce_grads` and `ppo.scalar_sync = dist.mean_over_ranks`.  Gradients are averaged after `backward()` and before
+the clipping, the KL estimate before the step-size decision, so every rank takes the same step and the result equals the
+single-process update on the concatenated minibatches (equal shard sizes; tests/test_dist_gloo.py, world 2).
 """
 import torch
 import torch.nn as nn
@@ -31,6 +36,7 @@ def ppo_update(self):
     value_loss_sum = torch.zeros((), dtype=torch.float64, device=ac.log_std.device)
     surrogate_loss_sum = torch.zeros_like(value_loss_sum)
     adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+    grad_sync, scalar_sync = getattr(self, "grad_sync", None), getattr(self, "scalar_sync", None)
 
     batch = st.mini_batch_generator(self.num_mini_batches)
     for _epoch in range(self.num_learning_epochs):
@@ -46,7 +52,7 @@ def ppo_update(self):
                            entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss)
 
             if adaptive:                                                          # ppo.py:270-283
-                kl_mean = float(out.kl_mean)
+                kl_mean = float(out.kl_mean if scalar_sync is None else scalar_sync(out.kl_mean))
                 if kl_mean > self.desired_kl * 2.0:
                     self.step_size = max(1e-5, self.step_size / 1.5)
                 elif kl_mean < self.desired_kl / 2.0 and kl_mean > 0.0:
@@ -56,6 +62,8 @@ def ppo_update(self):
 
             self.optimizer.zero_grad()                                            # ppo.py:305-308
             out.loss.backward()
+            if grad_sync is not None:
+                grad_sync(list(ac.parameters()))
             nn.utils.clip_grad_norm_(ac.parameters(), self.max_grad_norm)
             self.optimizer.step()
 
@@ -63,5 +71,8 @@ def ppo_update(self):
             surrogate_loss_sum += out.surrogate_loss.double()
 
     num_updates = self.num_learning_epochs * self.num_mini_batches
-    sums = torch.stack([value_loss_sum, surrogate_loss_sum]).cpu()
+    sums = torch.stack([value_loss_sum, surrogate_loss_sum])
+    if scalar_sync is not None:
+        sums = scalar_sync(sums)
+    sums = sums.cpu()
     return float(sums[0]) / num_updates, float(sums[1]) / num_updates

@@ -47,3 +47,69 @@ def test_stats_allreduce_world2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _update_worker(rank, world, port, out_dir):
+    """Env-sharded PPO update: each rank updates on its own envs with averaged gradients / KL; the parameters must equal
+    the single-process update on the concatenated minibatches."""
+    import copy
+    import sys
+    import types
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_gpu_ppo_update as t
+    from massive_marl_benchmark_b200 import dist as mdist
+    from massive_marl_benchmark_b200 import ppo_update as pu
+    from massive_marl_benchmark_b200.ppo_loss import PpoLossOut
+    from oracle.ppo_loss_oracle import ppo_loss_terms, ppo_update_oracle
+
+    def stand_in(mu, log_std, value, actions, old_logp, adv, tv, ret, old_mu, old_sigma, **cfg):     # the kernel's job, on CPU
+        loss, s, v, kl, logp, ent = ppo_loss_terms(mu, log_std, value, actions, old_logp, adv, tv, ret, old_mu, old_sigma, **cfg)
+        return PpoLossOut(loss, s.detach(), v.detach(), kl.detach(), logp.detach(), ent.detach()[0])
+
+    pu.ppo_loss = stand_in
+    mdist.init_from_env("gloo")
+    T, N, obs_dim, A, n_mb = 6, 48, 12, 8, 3
+    torch.manual_seed(31)
+    ac_full = t._ActorCritic(obs_dim, A, hidden=(16, 8))
+    ac_mine = copy.deepcopy(ac_full)
+    names = ("observations", "actions", "actions_log_prob", "values", "returns", "advantages", "mu", "sigma")
+    widths = {"observations": obs_dim, "actions": A, "mu": A, "sigma": A}
+    full = types.SimpleNamespace(num_envs=N, num_transitions_per_env=T, states=torch.zeros(T, N, 0))
+    for k in names:
+        setattr(full, k, torch.zeros(T, N, widths.get(k, 1)))
+    t._fill(full, ac_full, T, N, obs_dim, A, seed=41)
+
+    lo, hi = mdist.shard_range(N, rank, world)
+    n = hi - lo
+    shard = types.SimpleNamespace(num_envs=n, num_transitions_per_env=T, states=torch.zeros(T, n, 0))
+    for k in names:
+        setattr(shard, k, getattr(full, k)[:, lo:hi].contiguous())
+    mb = (T * n) // n_mb
+    shard.mini_batch_generator = lambda k: [torch.arange(T * n)[i * mb:(i + 1) * mb] for i in range(k)]
+    mine = t._ppo(shard, ac_mine, torch.optim.SGD(ac_mine.parameters(), lr=1e-2), num_mini_batches=n_mb)
+    mine.grad_sync, mine.scalar_sync = mdist.all_reduce_grads, mdist.mean_over_ranks
+    out_mine = pu.ppo_update(mine)
+
+    # the single-process update whose minibatch b is the union of every shard's minibatch b
+    def global_ids(r):
+        l, h = mdist.shard_range(N, r, world)
+        local = torch.arange(T * (h - l))
+        return (local // (h - l)) * N + l + local % (h - l)
+    per_rank = [global_ids(r) for r in range(world)]
+    order = torch.cat([torch.cat([g[b * mb:(b + 1) * mb] for g in per_rank]) for b in range(n_mb)])
+    whole = t._ppo(full, ac_full, torch.optim.SGD(ac_full.parameters(), lr=1e-2), num_mini_batches=n_mb)
+    out_full = ppo_update_oracle(whole, [order, order])
+    assert mine.step_size == whole.step_size != 2e-3
+    assert abs(out_mine[0] - out_full[0]) < 1e-5 * abs(out_full[0]) and abs(out_mine[1] - out_full[1]) < 1e-6
+    for a, b in zip(ac_mine.state_dict().values(), ac_full.state_dict().values()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, "upd%d" % rank), "w").write("1")
+
+
+def test_env_sharded_ppo_update_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_update_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "upd0").exists() and (tmp_path / "upd1").exists()
