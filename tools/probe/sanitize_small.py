@@ -1,4 +1,6 @@
-"""Small invocation of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""Small invocation of every kernel family, sized for compute-sanitizer (memcheck / racecheck / synccheck) on a
+workstation GPU.  NOT for the shared B200 pool: compute-sanitizer is closed there (runs under it have left GPUs needing a
+reset); on the pool this script only serves as a plain smoke run of all kernel families."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from massive_marl_benchmark_b200 import synthetic
