@@ -2,24 +2,33 @@
 """bench.py - env-steps/sec of the rollout hot path (obs + reward + reset + GAE) at TenAnt 4096 x 10.
 
   python bench.py --gpus N --steps K --warmup W            our arm (sm_100a kernels)
-  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU torch pipeline (oracle port)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU torch pipeline (baseline/_ref)
   N > 1: torchrun launches one rank per GPU (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env).
 
 Workload (BASELINE.json configs[1]): TenAnt, 4096 envs x 10 agents per GPU, horizon T = 16.  One "step" =
 one pass of the hot path over one batch = one rollout of T frames x N envs:
-    mmb_ten_ant_step (T frames in one launch: action scaling, observations, reward, done, written straight
-    into the rollout storage slots) + progress/reset chain + carry + mmb_reset_compact over the T flag rows
-    (reset-index lists + DOF re-randomisation) + mmb_gae_ppo + [all-reduce of the 3 advantage statistics when
-    N > 1] + mmb_adv_normalize.
+    mmb_ten_ant_step   T frames in one launch: action scaling, observations, reward, done written straight into the
+                       rollout storage slots; progress / reset chain, carry and the GAE scan of RolloutStorage.
+                       compute_returns (returns, raw advantages, their fp64 statistics) in the unit that closes an env
+  + mmb_reset_compact  over the T flag rows (reset-index lists + DOF re-randomisation)             [side stream]
+  + mmb_adv_normalize  (N > 1: mmb_adv_normalize_xchg, statistics exchanged over NVLink in-kernel)  [side stream]
 `value` = env-steps/s with the state frames already resident in HBM; `e2e` = the same metric through the
 reference-facing API (VecTaskPython.step / RolloutStorage) with the frames and actions in pinned HOST memory
 (H2D every env-step, D2H of reward/done every env-step and of the advantages every rollout).
 Synthetic Isaac-layout frames (PhysX is out of scope); 4 rotating frame/storage sets (> L2) so HBM is measured.
+The timed region is a CUDA graph of min(K, 32) rollouts (replayed K / 32 times + a remainder graph): the result does
+not depend on K.
 """
-import argparse
-import json
 import os
 import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the CPU arm uses every host core; torchrun exports OMP_NUM_THREADS=1 before torch is imported
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_k, None)
+
+import argparse
+import json
 import threading
 import time
 
@@ -30,12 +39,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "env-steps/sec (obs+reward+reset+GAE) at TenAnt 4096x10"
 UNIT = "env-steps/s"
+WORKLOAD = "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE"
 N_ENVS, HORIZON = 4096, 16
 GAMMA, LAM = 0.96, 0.95
 # algorithmic bytes of one TenAnt env-step in the horizon-batched kernel:
-#   reads  root 572 + dof 640 + actions 320                                   = 1532
-#   writes obs 1552 + forces 320 + reward 4 + done 1                          = 1877
-BYTES_PER_ENV_STEP_KERNEL = 1532 + 1877
+#   reads  root 572 + dof 640 + actions 320 + value 4                          = 1536
+#   writes obs 1552 + forces 320 + reward 4 + done 1 + return 4 + advantage 4   = 1885
+BYTES_PER_ENV_STEP_KERNEL = 1536 + 1885
+BYTES_PER_ENV_STEP_KERNEL_UNFUSED = 1532 + 1877   # --no-fused-gae: without the value read and the two GAE planes
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 class ClockSampler(threading.Thread):
@@ -91,15 +103,18 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed summary of
-    the `ncu --set full` capture of this same command (profiles/); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_ten_ant_v7_ncu_summary.csv")
-    try:
-        import csv
-        vals = {r[0]: (float(r[1]), r[2]) for r in csv.reader(open(path)) if len(r) == 3 and r[0].startswith("dram__bytes")}
-        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
-        return int(sum(v * scale[u] for v, u in vals.values())), os.path.relpath(path, ROOT)
-    except Exception:
-        return None, None
+    the `ncu --set full` capture of this same command (profiles/); the newest round's summary wins; None if missing."""
+    import csv
+    for name in ("r02_ten_ant_ncu_summary.csv", "r01_ten_ant_v7_ncu_summary.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            vals = {r[0]: (float(r[1]), r[2]) for r in csv.reader(open(path)) if len(r) == 3 and r[0].startswith("dram__bytes")}
+            scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+            if vals:
+                return int(sum(v * scale[u] for v, u in vals.values())), os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak():
@@ -110,15 +125,66 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's torch pipeline on the host cores
+# reference arm / cpu_baseline: the reference's own torch pipeline on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_rollouts(n_rollouts, warmup, n_envs=N_ENVS, horizon=HORIZON, threads=None):
-    """Times `n_rollouts` rollouts (T TenAnt steps + add_transitions + GAE) of the oracle on the CPU; returns
-    (env-steps/s, seconds per rollout, threads)."""
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_rollouts_reference(n_rollouts, warmup, n_envs, horizon, threads):
+    """The reference's OWN code from baseline/_ref (installed unmodified by baseline/make_ref.py): its `TenAnt` task
+    class stepped through its `VecTaskPython.step` (agents/tasks/agent_base/vec_task.py:126-131), its `RolloutStorage.
+    add_transitions / compute_returns` (agents/algorithms/rl/ppo/storage.py:32-65) and the obs copy of `PPO.run`
+    (ppo.py:138), on the same synthetic Isaac-layout frames the GPU arm consumes, served by the FakeGym frame provider of
+    oracle/refshim in place of PhysX (out of scope).  TenAnt only constructs in its 10-agent mode (ten_ant.py:91 views
+    the sensor tensor as [N * num_agents, 24]); its step takes the flat (N, 80) actions either way."""
+    import contextlib
+    import io
+    from oracle import refshim
+    from massive_marl_benchmark_b200 import synthetic
+    torch.set_num_threads(threads)
+    refshim.install(REF_DIR)
+    task, gym = refshim.make_task("TenAnt", n_envs, True)
+    from agents.algorithms.rl.ppo.storage import RolloutStorage
+    from agents.tasks.agent_base.vec_task import VecTaskPython
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = VecTaskPython(task, "cpu")
+    T, N = horizon, n_envs
+    st = RolloutStorage(N, T, (388,), (0,), (80,), "cpu", "sequential")
+    fr = synthetic.ten_ant_frames(N, T, seed=1234)
+    gym.frames = [dict(root=fr["root"][t], dof=fr["dof"][t], sensor=None) for t in range(T)]
+    values = torch.randn(N, 1); logp = torch.randn(N); mu = torch.randn(N, 80); sigma = torch.randn(N, 80)
+    states = torch.zeros(N, 0); last_values = torch.randn(N, 1)
+    gym.cursor = -1
+    cur = env.step(fr["actions"][0])[0].clone()
+
+    def rollout():
+        gym.cursor = -1                     # FakeGym serves frame t at step t
+        gym.log.clear()
+        for t in range(T):
+            obs, rew, done, _ = env.step(fr["actions"][t])
+            st.add_transitions(cur, states, fr["actions"][t], rew, done, values, logp, mu, sigma)
+            cur.copy_(obs)
+        st.compute_returns(last_values, GAMMA, LAM)
+        st.clear()
+
+    for _ in range(warmup):
+        rollout()
+    t0 = time.perf_counter()
+    for _ in range(n_rollouts):
+        rollout()
+    dt = time.perf_counter() - t0
+    return n_rollouts * T * N / dt, dt / n_rollouts, torch.get_num_threads()
+
+
+def cpu_rollouts_port(n_rollouts, warmup, n_envs, horizon, threads):
+    """Fallback when baseline/_ref is absent: the oracle port of the same pipeline."""
     from oracle import storage_oracle as so
     from oracle.task_oracle import TenAntOracle, vec_task_step
     from massive_marl_benchmark_b200 import synthetic
-    threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     fr = synthetic.ten_ant_frames(n_envs, horizon, seed=1234)
     orc = TenAntOracle(n_envs)
@@ -142,26 +208,38 @@ def cpu_rollouts(n_rollouts, warmup, n_envs=N_ENVS, horizon=HORIZON, threads=Non
     for _ in range(n_rollouts):
         rollout()
     dt = time.perf_counter() - t0
-    return n_rollouts * T * N / dt, dt / n_rollouts, threads
+    return n_rollouts * T * N / dt, dt / n_rollouts, torch.get_num_threads()
+
+
+def cpu_rollouts(n_rollouts, warmup, n_envs=N_ENVS, horizon=HORIZON, threads=None):
+    """(env-steps/s, seconds per rollout, threads used, kind)"""
+    threads = threads or _host_threads()
+    if os.path.isdir(os.path.join(REF_DIR, "agents")):
+        return cpu_rollouts_reference(n_rollouts, warmup, n_envs, horizon, threads) + ("reference",)
+    return cpu_rollouts_port(n_rollouts, warmup, n_envs, horizon, threads) + ("port",)
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: rank 0 alone runs; the others exit at once (no process group is ever created)."""
     if rank != 0:
         return
-    # a bounded sample: at most 24 timed rollouts (~0.3 s each on 16 host cores) however large --steps is, so that the arm
-    # finishes within a minute; the per-step figures below are per rollout of the sample
-    steps, warm = max(1, min(args.steps, 24)), max(1, min(args.warmup, 3))
-    value, sec, threads = cpu_rollouts(steps, warm)
+    # the same config as our arm: 4096 envs per GPU of the job, i.e. --gpus x 4096 envs in the one CPU pipeline.
+    # A bounded sample of it: at most ~40 / gpus timed rollouts whatever --steps is (a rollout of 4096 envs is ~0.3-0.5 s
+    # on 8-32 host cores), same warm-up rule as our arm (>= 3).
+    n_envs = N_ENVS * max(1, args.gpus)
+    steps = max(1, min(args.steps, max(3, 40 // max(1, args.gpus))))
+    warm = min(max(args.warmup, 3), 10)
+    value, sec, threads, kind = cpu_rollouts(steps, warm, n_envs=n_envs)
+    note = ("the reference's own TenAnt.step + VecTaskPython.step + RolloutStorage from baseline/_ref on the host CPU (FakeGym frame "
+            "provider in place of PhysX)") if kind == "reference" else \
+           "oracle port of the reference's torch pipeline on the host CPU (baseline/_ref absent)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "steps_timed": steps,
-            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE",
-                       "num_envs": N_ENVS, "num_agents": 10, "horizon": HORIZON,
-                       "note": "reference's torch task pipeline + RolloutStorage on the host CPU (oracle port; the Python "
-                               "reference cannot travel to the GPU box)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d rollouts of %d steps x %d envs + GAE" % (steps, HORIZON, N_ENVS)},
+            "steps_timed": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "num_envs_per_gpu": N_ENVS, "num_agents": 10, "horizon": HORIZON,
+                       "env_steps_per_step": HORIZON * n_envs, "note": note},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "%d rollouts of %d steps x %d envs + GAE (after %d warm-up rollouts)" % (steps, HORIZON, n_envs, warm)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -186,6 +264,7 @@ def run_ours(args, rank, world, local_rank):
     N, T, K, W = N_ENVS, HORIZON, args.steps, max(args.warmup, 3)
     SETS = 4  # rotating frame/storage sets: 4 x ~225 MB of traffic per step >> 126 MB L2
     GROUP = int(os.environ.get("MMB_BENCH_GROUP", 8 * SETS))  # rollouts captured per CUDA graph (side-stream tails joined once per graph)
+    fused = not args.no_fused_gae
 
     def barrier():
         if world > 1:
@@ -215,15 +294,16 @@ def run_ours(args, rank, world, local_rank):
     # high priority: the short tail kernels must get SM slots as soon as their rollout's step kernel has finished, even
     # though the next step kernel (overlap_prev) is already filling the GPU
     side = torch.cuda.Stream(priority=-1)       # reset-index lists of the T steps
-    side2 = torch.cuda.Stream(priority=-1)      # GAE scan, statistics exchange wait + normalisation
+    side2 = torch.cuda.Stream(priority=-1)      # [GAE scan when not fused,] statistics exchange wait + normalisation
 
     side_done = [None] * SETS   # event: the side-stream tail of the last rollout that used set s has finished
 
     def rollout(i, join=True):
         """One rollout on frame/storage set i % SETS.  Main stream: the step kernel (the task-state chain orders
-        consecutive rollouts).  Side streams: the reset lists of the T steps; the GAE scan -> [statistics exchange] ->
-        normalisation.  With join=False the side work is left running so that the NEXT rollouts' step kernels (other
-        storage sets) overlap it; a set is reused only after its previous tails have finished (side_done)."""
+        consecutive rollouts; with the fused GAE it also leaves returns / raw advantages / statistics).  Side streams:
+        the reset lists of the T steps; [statistics exchange] -> normalisation.  With join=False the side work is left
+        running so that the NEXT rollouts' step kernels (other storage sets) overlap it; a set is reused only after its
+        previous tails have finished (side_done)."""
         s = i % SETS
         st, fr = storages[s], dev_frames[s]
         main = torch.cuda.current_stream()
@@ -232,13 +312,14 @@ def run_ours(args, rank, world, local_rank):
         # observation after step t lands in obs slot t+1; reward/done of step t in slot t (no add_transitions pass)
         # consecutive rollouts use different frame / storage sets, so the step kernel may overlap the previous one's tail
         task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), None, forces[s],
-                    overlap_prev=not args.no_overlap)
+                    overlap_prev=not args.no_overlap, gae=st.fused_gae(last_values, GAMMA, LAM) if fused else None)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             reset_out[0] = reset_replay(task, st.dones.view(T, N), dof_out=dof_push, out=reset_out[0])
         side2.wait_stream(main)
         with torch.cuda.stream(side2):
-            st.compute_returns_scan(last_values, GAMMA, LAM)
+            if not fused:
+                st.compute_returns_scan(last_values, GAMMA, LAM)
             st.normalize_advantages()
             side2.wait_stream(side)
             if not join:
@@ -255,51 +336,48 @@ def run_ours(args, rank, world, local_rank):
     for i in range(max(W, SETS)):
         rollout(i)
     barrier()
-    # The rollout is 5 short launches after the main kernel: capture it once per frame/storage set in a CUDA graph
-    # so the launch-bound tail is replayed without per-launch CPU cost (eager fallback if capture is unavailable).
-    graphs = None
-    graph_all = None
-    if not args.no_graph:
-        try:
-            graphs = []
-            for s_ in range(SETS):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    rollout(s_)
-                graphs.append(g)
-            graph_all = torch.cuda.CUDAGraph()       # GROUP consecutive rollouts, side-stream tails joined once at the end
-            with torch.cuda.graph(graph_all):
-                for r_ in range(GROUP):
-                    rollout(r_, join=(r_ == GROUP - 1))
+
+    # The timed region replays CUDA graphs of `n` consecutive rollouts whose side-stream tails are joined ONCE, at the end
+    # of the graph: n = min(K, GROUP) for the bulk and K mod n for the remainder, so the measurement is the same for any K.
+    graph_cache = {}
+
+    def group_graph(n):
+        if n not in graph_cache:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for r_ in range(n):
+                    rollout(r_, join=(r_ == n - 1))
                 for s_ in range(SETS):
                     side_done[s_] = None
-            for s_ in range(SETS):
-                graphs[s_].replay()
-            graph_all.replay()
+            graph_cache[n] = g
+        return graph_cache[n]
+
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            n_main = max(1, min(K, GROUP))
+            for n_ in {n_main, K % n_main, max(1, min(W, GROUP)), W % max(1, min(W, GROUP))} - {0}:
+                group_graph(n_).replay()
             torch.cuda.synchronize()
         except Exception as ex:  # pragma: no cover
             print("cuda graph capture failed, running eagerly: %r" % (ex,), file=sys.stderr)
-            graphs = graph_all = None
+            use_graph = False
 
-    def run_steps(first, count):
-        """`count` consecutive rollouts starting at rollout index `first` (a multiple of SETS)."""
-        i = 0
-        while i < count:
-            if graph_all is not None and (first + i) % SETS == 0 and count - i >= GROUP:
-                graph_all.replay()
-                i += GROUP
-            elif graphs is not None:
-                graphs[(first + i) % SETS].replay()
-                i += 1
-            else:
-                rollout(first + i)
-                i += 1
+    def run_steps(count):
+        """`count` consecutive rollouts."""
+        if not use_graph:
+            for i in range(count):
+                rollout(i, join=(i == count - 1))
+            for s_ in range(SETS):
+                side_done[s_] = None
+            return
+        n = max(1, min(count, GROUP))
+        for _ in range(count // n):
+            group_graph(n).replay()
+        if count % n:
+            group_graph(count % n).replay()
 
-    def run_step(i):
-        run_steps(i, 1)
-
-    for i in range(W):
-        run_step(i)
+    run_steps(W)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -308,12 +386,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t_host0 = time.perf_counter()
     ev0.record()
-    run_steps(0, K)
+    run_steps(K)
     ev1.record()
     barrier()
     t_host1 = time.perf_counter()
     sampler.stop()
-    launches = (L.launch_count() - launches0) if graphs is None else K * launches_per_rollout[0]
+    launches = (L.launch_count() - launches0) if not use_graph else K * launches_per_rollout[0]
     my_ms = ev0.elapsed_time(ev1)
     ms = mdist.max_over_ranks(my_ms, dev)
     rank_ms = [my_ms]
@@ -322,6 +400,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_gather(tl, torch.tensor([my_ms], dtype=torch.float64, device=dev))
         rank_ms = [float(t.item()) for t in tl]
     value = K * T * N * world / (ms * 1e-3)
+    chain_errors = task.chain_errors()
 
     # ---- per-kernel durations: the same rollouts launched eagerly, every kernel bracketed by CUDA events on its
     # launch stream (library-side, mmb_profile_*); inputs rotate exactly as above ---------------------------------
@@ -339,12 +418,14 @@ def run_ours(args, rank, world, local_rank):
     prof = L.profile_collect()
     eager_ms_per_step = pe0.elapsed_time(pe1) / KP
 
-    # ---- the dominant kernel alone, launched back to back over the same rotating inputs (a CUDA graph of SETS
+    # ---- the dominant kernel alone, launched back to back over the same rotating inputs (a CUDA graph of GROUP
     # launches, replayed): its sustained duration without the event-pair and launch gaps of the eager pass -------------
     def step_only(i):
         s_ = i % SETS
-        task.replay(dev_frames[s_], dev_frames[s_]["actions"], storages[s_].obs_slots[1:], storages[s_].rewards.view(T, N),
-                    storages[s_].dones.view(T, N), None, forces[s_], overlap_prev=not args.no_overlap)
+        st_ = storages[s_]
+        task.replay(dev_frames[s_], dev_frames[s_]["actions"], st_.obs_slots[1:], st_.rewards.view(T, N),
+                    st_.dones.view(T, N), None, forces[s_], overlap_prev=not args.no_overlap,
+                    gae=st_.fused_gae(last_values, GAMMA, LAM) if fused else None)
     sustained_ms, RK = None, 0
     if not args.no_graph:
         try:
@@ -365,6 +446,8 @@ def run_ours(args, rank, world, local_rank):
             k1.record()
             torch.cuda.synchronize()
             sustained_ms = k0.elapsed_time(k1) / (RK * GROUP)
+            for st_ in storages:      # the statistics this pass accumulated were never consumed: start clean
+                st_._adv_stats4.zero_()
         except Exception as ex:  # pragma: no cover
             print("kernel-only graph failed: %r" % (ex,), file=sys.stderr)
 
@@ -387,15 +470,15 @@ def run_ours(args, rank, world, local_rank):
     h_adv = torch.empty(T, N, 1, pin_memory=True)
     values = torch.randn(N, 1, device=dev); logp = torch.randn(N, device=dev)
     mu = torch.randn(N, 80, device=dev); sigma = torch.randn(N, 80, device=dev); states = torch.zeros(N, 0, device=dev)
-    cur_obs = env.reset().clone()
+    cur_obs = env.reset()
 
     def e2e_rollout(j):
-        nonlocal cur_obs
+        # the loop of the reference's PPO.run (ppo.py:127-139): step -> add_transitions(current_obs, ...) -> current_obs.copy_(next_obs)
         for t in range(T):
             a = host_prov.stage[(host_prov.cursor + 1) & 1]["actions"]               # uploaded with the frame (H2D)
             obs, rew, done, _ = env.step(a)                                          # waits for that upload only
             st2.add_transitions(cur_obs, states, a, rew, done, values, logp, mu, sigma)
-            cur_obs = obs
+            cur_obs.copy_(obs)
             h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)  # D2H result of the step
         st2.compute_returns(last_values, GAMMA, LAM)
         h_adv.copy_(st2.advantages, non_blocking=True)                              # D2H result of the rollout
@@ -416,37 +499,55 @@ def run_ours(args, rank, world, local_rank):
     d2h = T * (N * 4 + N * 8) + T * N * 4
 
     xchg_errors = int(mdist.sum_over_ranks(float(xchg.errors), dev)) if xchg is not None else 0
+    chain_errors = int(mdist.sum_over_ranks(float(chain_errors), dev))
     if xchg_errors:
         raise RuntimeError("statistics exchange reported %d timed-out / overrun exchanges" % xchg_errors)
+    if chain_errors:
+        raise RuntimeError("the in-kernel progress / reset chain timed out %d times" % chain_errors)
     if rank != 0:
         return
     peak, peak_src = measured_peak()
     traffic, traffic_src = ncu_traffic_bytes()
     k_ms, k_n = prof.get("ten_ant", (0.0, 0))
-    per_launch_bytes = BYTES_PER_ENV_STEP_KERNEL * T * N
+    per_launch_bytes = (BYTES_PER_ENV_STEP_KERNEL if fused else BYTES_PER_ENV_STEP_KERNEL_UNFUSED) * T * N
     eager_launch_ms = k_ms / max(k_n, 1)
     launch_ms = sustained_ms if sustained_ms else eager_launch_ms
     achieved = per_launch_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms else None
     shares = {k: round(v[0] / max(1e-9, sum(x[0] for x in prof.values())), 4) for k, v in prof.items()}
+    # the whole timed step against the same roofline: every algorithmic byte of the rollout (step kernel + normalise pass
+    # 8 B per transition + the flag rows the reset compaction reads) over the driver-visible time per step
+    step_bytes = per_launch_bytes + T * N * (8 + 1) + (0 if fused else T * N * 17)
     cpu = None
-    if args.cpu_rollouts > 0:
-        c_val, c_sec, c_thr = cpu_rollouts(args.cpu_rollouts, 1)
-        cpu = {"value": c_val, "unit": UNIT, "cores": c_thr, "kind": "port",
-               "sample": "%d rollouts of %d steps x %d envs + GAE (oracle port of the reference's torch pipeline)" % (
-                   args.cpu_rollouts, T, N)}
+    if args.cpu_rollouts > 0 and world == 1:
+        # only on a single-process run: under torchrun the other ranks would spin in a collective for the duration, and
+        # torchrun's OMP_NUM_THREADS=1 starves the CPU arm (see --impl reference, which handles both)
+        c_val, c_sec, c_thr, c_kind = cpu_rollouts(args.cpu_rollouts, 1)
+        cpu = {"value": c_val, "unit": UNIT, "cores": c_thr, "kind": c_kind,
+               "sample": "%d rollouts of %d steps x %d envs + GAE (%s)" % (
+                   args.cpu_rollouts, T, N, "the reference's own TenAnt / VecTaskPython / RolloutStorage from baseline/_ref"
+                   if c_kind == "reference" else "oracle port of the reference's torch pipeline")}
+    elif world > 1:
+        cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "skipped",
+               "sample": "rank 0 at N = 1 only (run `bench.py --impl reference --gpus %d` for the CPU arm of this job size)" % world}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "ms_per_step_by_rank": [round(x / K, 5) for x in rank_ms], "ms_per_step_eager_profiled": eager_ms_per_step, "cuda_graph": graphs is not None,
+        "ms_per_step": ms / K, "ms_per_step_by_rank": [round(x / K, 5) for x in rank_ms], "ms_per_step_eager_profiled": eager_ms_per_step,
+        "cuda_graph": use_graph,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TenAnt PPO 4096 envs x 10 agents, obs/reward/reset + horizon-16 GAE",
+        "config": {"workload": WORKLOAD,
                    "num_envs_per_gpu": N, "num_agents": 10, "horizon": T, "env_steps_per_step": T * N,
                    "l2": "4 rotating frame/storage sets, ~225 MB of traffic per step each, > 126 MB L2",
                    "parallelism": "env-sharded dp%d" % world,
+                   "timed_region": "CUDA graphs of min(steps, %d) rollouts, side-stream tails joined once per graph" % GROUP,
+                   "gae": "fused into the step kernel's chain executor" if fused else "mmb_gae_ppo on a side stream",
+                   "stored_planes": "obs, rewards, dones, returns, advantages, forces (values are inputs; actions / mu / sigma / log-prob "
+                                    "planes belong to the policy forward, not to this metric, and are not written)",
                    "stats_exchange": {"p2p": "NVLink peer-memory mailboxes written and awaited inside the normalise kernel (no collective launch)",
                                       "nccl": "NCCL all-reduce of 3 doubles", "none": "single shard"}[mode]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": K2, "numa_bound": numa_bound, "api": "VecTaskPython.step + RolloutStorage.add_transitions/compute_returns, pinned host frames"},
+                "steps": K2, "numa_bound": numa_bound, "api": "VecTaskPython.step + RolloutStorage.add_transitions/compute_returns "
+                "in the loop of the reference's PPO.run (current_obs.copy_(next_obs)), pinned host frames"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "ten_ant_split_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
@@ -455,7 +556,9 @@ def run_ours(args, rank, world, local_rank):
                      "timing": ("CUDA events around %d back-to-back launches of the kernel alone (graph of %d launches over the "
                                 "rotating sets, replayed)" % (RK * GROUP, GROUP)) if sustained_ms else "event pair per launch, eager pass",
                      "avg_launch_ms_eager_event_pairs": eager_launch_ms,
-                     "launches_timed": (RK * GROUP) if sustained_ms else k_n, "kernel_time_shares_eager": shares},
+                     "launches_timed": (RK * GROUP) if sustained_ms else k_n, "kernel_time_shares_eager": shares,
+                     "whole_step": {"algorithmic_bytes": step_bytes, "ms": ms / K,
+                                    "achieved": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak}},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(t_host0, t_host1),
     }
@@ -468,17 +571,18 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-rollouts", type=int, default=32, help="rollouts of the CPU baseline sample (~0.3 s each on 16 cores)")
+    ap.add_argument("--cpu-rollouts", type=int, default=32, help="rollouts of the CPU baseline sample (~0.3 s each on 16 cores); N = 1 only")
     ap.add_argument("--stats-exchange", default="p2p", choices=["p2p", "nccl", "none"],
                     help="multi-GPU advantage statistics: NVLink peer-memory mailboxes (default) or NCCL all-reduce")
     ap.add_argument("--no-overlap", action="store_true", help="ordinary stream order between consecutive step kernels (no PDL)")
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-fused-gae", action="store_true", help="GAE scan as its own launch (mmb_gae_ppo) instead of inside the step kernel")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)      # times a bounded sample (<= 24 rollouts) whatever --steps is
+        run_reference(args, rank, world)      # rank 0 only; no process group, no GPU
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")

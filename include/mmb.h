@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMB_ABI_VERSION 1
+#define MMB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MMB_API __attribute__((visibility("default")))
@@ -126,9 +126,12 @@ typedef struct {
   int64_t* dones_i64; int64_t dones_i64_frame_stride; /* [T][N] reset_buf after each step */
   uint8_t* dones_u8;  int64_t dones_u8_frame_stride;  /* [T][N] same, as RolloutStorage.dones */
   float* forces;    int64_t forces_frame_stride;    /* [T][N][80] clamp(actions)*gear*power_scale */
-  /* T > 1 only, optional: N zero-initialised uint64 words owned by the caller (self-resetting).  With it (and
-   * T <= 32) the progress/reset chain and the carry are resolved inside the main kernel by the thread that delivers
-   * the last frame of an env; without it (NULL) a second small kernel does the same work. */
+  /* T > 1 only, optional: N + 1 zero-initialised uint64 words owned by the caller (words 0..N-1 are self-resetting; word N
+   * counts chain time-outs, see below).  With it (and T <= 32) the progress/reset chain and the carry are resolved inside
+   * the main kernel by the unit that processes the last frame of an env; without it (NULL) a second small kernel does the
+   * same work.  The last-frame unit waits for the reports of the env's other frames (units launched before it); if they
+   * have not all arrived after ~1 s (preemption, a debugger) it does NOT guess: it adds 1 to word N, leaves the env's flags
+   * and carry untouched, and the host (TenAnt.chain_errors) raises. */
   uint64_t* scratch;
   /* != 0: programmatic dependent launch.  The kernel may start while the PRECEDING kernel in the stream is still
    * draining (its tail overlaps this kernel's head); it orders itself behind that kernel only where it touches the
@@ -140,6 +143,22 @@ typedef struct {
   int32_t _reserved;
   /* obs_layout 2 only: element stride between the per-agent planes of `obs` (see obs_layout) */
   int64_t obs_agent_stride;
+  /* Fused RolloutStorage.compute_returns (storage.py:51-62 + `returns - values`), horizon-batched launches only
+   * (2 <= T <= 32, `scratch` given, `dones_u8` given).  gae_values == NULL: off.  The unit of the env's last frame already
+   * gathers the T `fallen` bits; with this block the other frames hand it their reward in the same 64-bit word
+   * (gae_scratch: T*N zero-initialised, self-resetting words, [T][N]), and it runs the reverse-time scan of mmb_gae_ppo
+   * for its 16 envs right after the progress/reset chain: same operations in the same order, bit-identical `returns`.
+   * Raw advantages go to gae_advantages, their {sum, sumsq} (fp64) to the slot area of gae_stats (one atomic pair per
+   * tile, spread over MMB_STAT_SLOTS lines), the count to gae_stats[0]; normalise with MMB_NORM_SLOTS.
+   * `values` / `last_values` must be final before the launch (replayed values; the interactive per-step path keeps
+   * mmb_gae_ppo). */
+  const float* gae_values;  int64_t gae_values_frame_stride;         /* [T][N] */
+  const float* gae_last_values;                                      /* [N] */
+  float* gae_returns;       int64_t gae_returns_frame_stride;        /* [T][N] */
+  float* gae_advantages;    int64_t gae_advantages_frame_stride;     /* [T][N] raw */
+  double* gae_stats;        /* [MMB_ADV_STATS_EXT_DOUBLES], zero-initialised once */
+  uint64_t* gae_scratch;    /* [T][N] */
+  float gae_gamma, gae_lam; /* already rounded to fp32 (float(gamma)) */
   mmb_ant_consts c;
 } mmb_ten_ant_params;
 
@@ -285,9 +304,16 @@ MMB_API int32_t mmb_gae_ppo(const mmb_gae_ppo_params* p, void* stream);
 
 /* (adv - mean) / (std_unbiased + eps) in place; mean/std from stats = {count, sum, sumsq} on device.
  * eps = 1e-8 (storage.py:65) or 1e-5 (mappo_trainer.py:199).  `stats` has FOUR doubles: [3] is a ticket counter
- * owned by the library (zero-initialise once).  With clear_stats != 0 the last block to read the statistics
- * clears them, so the accumulator is ready for the next rollout without a memset launch (CUDA-graph safe). */
-MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, float eps, int32_t clear_stats,
+ * owned by the library (zero-initialise once).  flags & MMB_NORM_CLEAR: the last block to read the statistics
+ * clears them, so the accumulator is ready for the next rollout without a memset launch (CUDA-graph safe).
+ * flags & MMB_NORM_SLOTS: `stats` is the extended accumulator of MMB_ADV_STATS_EXT_DOUBLES doubles - the four words
+ * above followed by MMB_STAT_SLOTS slots of MMB_STAT_SLOT_STRIDE doubles ({sum, sumsq} at the start of each 128-byte
+ * line) - filled by the fused GAE of mmb_ten_ant_step; the slots are summed in index order and cleared with the rest. */
+#define MMB_STAT_SLOTS 32
+#define MMB_STAT_SLOT_STRIDE 16
+#define MMB_ADV_STATS_EXT_DOUBLES (4 + MMB_STAT_SLOTS * MMB_STAT_SLOT_STRIDE)
+enum { MMB_NORM_CLEAR = 1, MMB_NORM_SLOTS = 2 };
+MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, float eps, int32_t flags,
                                   void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
@@ -309,7 +335,8 @@ MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, f
 /* ------------------------------------------------------------------------------------------ */
 #define MMB_MAX_RANKS 16
 typedef struct mmb_xchg {
-  int32_t world, rank, slots, _pad;
+  int32_t world, rank, slots;
+  int32_t timeout_ms;               /* wait for the peers' flags: 0 = default (10 s), < 0 = wait for ever */
   uint64_t* state;                  /* local, [8] */
   uint64_t* mailbox[MMB_MAX_RANKS]; /* mailbox[r] = rank r's mailbox as mapped in THIS process (mailbox[rank] is local) */
 } mmb_xchg;
@@ -323,11 +350,14 @@ MMB_API int32_t mmb_xchg_open(const uint8_t* handle64, void** dev_ptr);  /* map 
 MMB_API int32_t mmb_xchg_close(void* dev_ptr);                            /* unmap a peer's mailbox */
 MMB_API int32_t mmb_xchg_free(void* dev_ptr);                             /* free the local mailbox */
 
-/* Exchange + normalisation: publishes `stats` = this shard's {count,sum,sumsq} (as accumulated by mmb_gae_ppo; cleared
- * afterwards) to all ranks, waits (bounded spin, ~2 s, then state[3]++) until all `world` shards of the exchange are in
- * the local mailbox, and applies (adv - mean) / (std_unbiased + eps) in place with the global moments. */
+/* Exchange + normalisation: publishes `stats` = this shard's {count,sum,sumsq} (as accumulated by mmb_gae_ppo or the
+ * fused GAE; cleared afterwards) to all ranks, waits until all `world` shards of the exchange are in the local mailbox,
+ * and applies (adv - mean) / (std_unbiased + eps) in place with the global moments.  The wait is bounded
+ * (xchg->timeout_ms).  On a time-out or an overrun slot NOTHING is normalised with partial moments: state[3]++ and the
+ * whole advantages plane of this shard is filled with NaN, so the failure is loud in the very next loss; the caller
+ * (RolloutStorage.check_exchange) raises.  flags: MMB_NORM_SLOTS as for mmb_adv_normalize (clearing is implied). */
 MMB_API int32_t mmb_adv_normalize_xchg(float* advantages, int64_t n, double* stats, const mmb_xchg* xchg, float eps,
-                                       void* stream);
+                                       int32_t flags, void* stream);
 
 /* RolloutStorage.get_statistics (storage.py:67-73) on device: out[0] = mean trajectory length,
  * out[1] = mean reward.  No host sync. */

@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmb_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_GATHER_FIELDS = 16
 
 FLAVOR_CUDA, FLAVOR_CPU = 0, 1
@@ -42,7 +42,12 @@ class TenAntParams(C.Structure):
         ("share_obs", c_vp), ("share_obs_frame_stride", c_i64), ("rewards", c_vp), ("rewards_frame_stride", c_i64),
         ("dones_i64", c_vp), ("dones_i64_frame_stride", c_i64), ("dones_u8", c_vp), ("dones_u8_frame_stride", c_i64),
         ("forces", c_vp), ("forces_frame_stride", c_i64), ("scratch", c_vp), ("overlap_prev", c_i32), ("_reserved", c_i32),
-        ("obs_agent_stride", c_i64), ("c", AntConsts)]
+        ("obs_agent_stride", c_i64),
+        ("gae_values", c_vp), ("gae_values_frame_stride", c_i64), ("gae_last_values", c_vp),
+        ("gae_returns", c_vp), ("gae_returns_frame_stride", c_i64),
+        ("gae_advantages", c_vp), ("gae_advantages_frame_stride", c_i64),
+        ("gae_stats", c_vp), ("gae_scratch", c_vp), ("gae_gamma", c_f), ("gae_lam", c_f),
+        ("c", AntConsts)]
 
 
 class OneAntParams(C.Structure):
@@ -93,10 +98,13 @@ class RolloutAddParams(C.Structure):
 
 MAX_RANKS = 16
 MAX_GROUP = 16
+STAT_SLOTS, STAT_SLOT_STRIDE = 32, 16
+ADV_STATS_EXT_DOUBLES = 4 + STAT_SLOTS * STAT_SLOT_STRIDE
+NORM_CLEAR, NORM_SLOTS = 1, 2
 
 
 class Xchg(C.Structure):
-    _fields_ = [("world", c_i32), ("rank", c_i32), ("slots", c_i32), ("_pad", c_i32), ("state", c_vp),
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("slots", c_i32), ("timeout_ms", c_i32), ("state", c_vp),
                 ("mailbox", c_vp * MAX_RANKS)]
 
 
@@ -180,7 +188,7 @@ SYMBOLS = {
     "mmb_rollout_add": (c_i32, [C.POINTER(RolloutAddParams), c_vp]),
     "mmb_gae_ppo": (c_i32, [C.POINTER(GaePpoParams), c_vp]),
     "mmb_adv_normalize": (c_i32, [c_vp, c_i64, c_vp, c_f, c_i32, c_vp]),
-    "mmb_adv_normalize_xchg": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(Xchg), c_f, c_vp]),
+    "mmb_adv_normalize_xchg": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(Xchg), c_f, c_i32, c_vp]),
     "mmb_xchg_mailbox_bytes": (c_i64, [c_i32, c_i32]),
     "mmb_xchg_alloc": (c_i32, [c_i64, C.POINTER(c_vp), C.POINTER(C.c_uint8)]),
     "mmb_xchg_open": (c_i32, [C.POINTER(C.c_uint8), C.POINTER(c_vp)]),

@@ -15,6 +15,19 @@ struct EvPair { cudaEvent_t a, b; };
 std::vector<EvPair> g_events[K_COUNT];
 }  // namespace
 
+int sm_count() {
+  static std::atomic<int> cache[MMB_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= MMB_MAX_DEVICES) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 LaunchScope::LaunchScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (g_profile.load(std::memory_order_relaxed)) {

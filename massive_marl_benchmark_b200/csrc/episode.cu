@@ -123,7 +123,7 @@ extern "C" int32_t mmb_episode_update(const mmb_episode_params* pp, void* stream
   {
     LaunchScope ls(K_EPISODE_SCAN, st);
     int blocks = (p.num_envs + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     episode_scan_kernel<<<blocks, 256, 0, st>>>(p);
   }
   if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;

@@ -166,7 +166,7 @@ extern "C" int32_t mmb_shuffle_gather(const mmb_gather_params* pp, void* stream)
   const int64_t units = p.batch_size * ((max_rb + 15) / 16);
   int64_t blocks = (units + 8 * 128 - 1) / (8 * 128);
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   {
     LaunchScope ls(K_GATHER, (cudaStream_t)stream);
     gather_kernel<<<dim3((unsigned)blocks, p.num_fields), 256, 0, (cudaStream_t)stream>>>(p, bj);
@@ -178,7 +178,7 @@ extern "C" int32_t mmb_permutation(int64_t n, uint64_t seed, int64_t* out, void*
   if (n <= 0 || !out) return MMB_EINVAL;
   Bijection bj = make_bijection(n, seed);
   int64_t blocks = (n + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   {
     LaunchScope ls(K_PERM, (cudaStream_t)stream);
     permutation_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bj, n, out);

@@ -23,7 +23,7 @@ constexpr int ROOT_ENV = 52;
 constexpr int FORCE_ENV = 72;
 
 template <int FLAVOR>
-__global__ void __launch_bounds__(NT) ingenuity_kernel(const __grid_constant__ mmb_ingenuity_params p) {
+__global__ void __launch_bounds__(NT) ingenuity_kernel(const __grid_constant__ mmb_ingenuity_params p, const int pf_dist) {
   __shared__ __align__(16) float root_s[EPT * ROOT_ENV];
   __shared__ __align__(16) float force_s[EPT * FORCE_ENV];
   __shared__ unsigned char flagged_s[EPT];  // env had its reset flag set on entry (T == 1 only)
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(NT) ingenuity_kernel(const __grid_constant__ m
 
   tile_load(root_s, p.root + (int64_t)t * p.root_frame_stride + (int64_t)e0 * ROOT_ENV, ne * ROOT_ENV, tid, NT);
   if (tid == 32) {  // L2 prefetch of the inputs of the unit two CTAs per SM ahead in launch order (see ten_ant.cu)
-    const int64_t u = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + 2 * 148;
+    const int64_t u = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + pf_dist;
     const int64_t t2 = u / gridDim.x, tile2 = u - t2 * gridDim.x;
     if (t2 < T && (tile2 + 1) * EPT <= N) {
       prefetch_range_l2(p.root + t2 * p.root_frame_stride + tile2 * EPT * ROOT_ENV, EPT * ROOT_ENV * 4);
@@ -190,8 +190,8 @@ extern "C" int32_t mmb_ingenuity_step(const mmb_ingenuity_params* pp, void* stre
   dim3 grid((p.num_envs + EPT - 1) / EPT, p.num_frames);
   {
     LaunchScope ls(K_INGENUITY, st);
-    if (p.flavor == MMB_FLAVOR_CUDA) ingenuity_kernel<FLAVOR_CUDA><<<grid, NT, 0, st>>>(p);
-    else ingenuity_kernel<FLAVOR_CPU><<<grid, NT, 0, st>>>(p);
+    if (p.flavor == MMB_FLAVOR_CUDA) ingenuity_kernel<FLAVOR_CUDA><<<grid, NT, 0, st>>>(p, 2 * sm_count());
+    else ingenuity_kernel<FLAVOR_CPU><<<grid, NT, 0, st>>>(p, 2 * sm_count());
   }
   if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   if (p.num_frames > 1) {

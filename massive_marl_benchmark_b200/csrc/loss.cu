@@ -340,7 +340,7 @@ extern "C" int32_t mmb_ppo_loss(const mmb_ppo_loss_params* pp, void* stream) {
   const int kmax = (p.act_dim + G - 1) / G;
   const int rows_per_block = LOSS_THREADS / G;
   int grid = (p.num_rows + rows_per_block - 1) / rows_per_block;
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
   cudaError_t e;
   {
     LaunchScope ls(K_PPO_LOSS, st);
@@ -363,7 +363,7 @@ extern "C" int32_t mmb_mappo_loss(const mmb_mappo_loss_params* pp, void* stream)
   const int kmax = (p.act_dim + G - 1) / G;
   const int rows_per_block = LOSS_THREADS / G;
   int grid = (p.num_rows + rows_per_block - 1) / rows_per_block;
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
   cudaError_t e;
   {
     LaunchScope ls(K_MAPPO_LOSS, st);

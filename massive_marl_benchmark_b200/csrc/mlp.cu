@@ -1026,7 +1026,7 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   const int num_tiles = (p.Mpad / BM) * (p.Npad / p.n_tile);
   const bool y_tma = (p.epilogue == 0) ? (((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0) : (p.n_tile % 64 == 0);
   const int sub_cols_h = (p.epilogue == 0) ? 32 : 64;
-  const bool persist = persist_pref && !pair && cm == 1 && p.epilogue != 2 && p.n_tile <= 256 && y_tma && num_tiles >= 2 * 148 &&
+  const bool persist = persist_pref && !pair && cm == 1 && p.epilogue != 2 && p.n_tile <= 256 && y_tma && num_tiles >= 2 * sm_count() &&
                        (p.n_tile / 2) % sub_cols_h == 0;
   if (persist) {
     const int sb = A_STAGE_BYTES + p.n_tile * BK * 2;
@@ -1084,8 +1084,7 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
         if (cudaFuncSetAttribute(mlp_layer_ws_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return MMB_ECUDA;
         persist_attr_done[dev] = true;
       }
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int sms = sm_count();
       cfg.gridDim = dim3(num_tiles < sms ? num_tiles : sms);
       cfg.dynamicSmemBytes = psmem;
       le = cudaLaunchKernelEx(&cfg, mlp_layer_ws_persist_kernel, p, map_x, map_w, map_y);

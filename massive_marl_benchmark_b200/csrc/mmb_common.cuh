@@ -18,6 +18,9 @@ enum KernelId {
 
 // Brackets one kernel launch: bumps the launch counter and, while profiling is enabled
 // (mmb_profile_enable), records a CUDA event pair around it on the launch stream.
+// SMs of the current device (cached per device; the grid caps below are multiples of it)
+int sm_count();
+
 struct LaunchScope {
   LaunchScope(int id, cudaStream_t st);
   ~LaunchScope();

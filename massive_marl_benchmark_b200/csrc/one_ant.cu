@@ -30,7 +30,7 @@ __device__ __forceinline__ float potential_of(float bx, float by, float dt) {
 }
 
 template <int FLAVOR>
-__global__ void __launch_bounds__(EPT) one_ant_kernel(const __grid_constant__ mmb_one_ant_params p) {
+__global__ void __launch_bounds__(EPT) one_ant_kernel(const __grid_constant__ mmb_one_ant_params p, const int pf_dist) {
   __shared__ __align__(16) float root_s[EPT * ROOT_ENV];
   __shared__ __align__(16) float obs_s[EPT * OBS_PAD];
   const int tid = threadIdx.x, t = blockIdx.y;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(EPT) one_ant_kernel(const __grid_constant__ mm
 
   tile_load(root_s, p.root + (int64_t)t * p.root_frame_stride + (int64_t)e0 * ROOT_ENV, ne * ROOT_ENV, tid, EPT);
   if (tid == 32) {  // L2 prefetch of the inputs of the unit two CTAs per SM ahead in launch order (see ten_ant.cu)
-    const int64_t u = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + 2 * 148;
+    const int64_t u = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + pf_dist;
     const int64_t t2 = u / gridDim.x, tile2 = u - t2 * gridDim.x;
     if (t2 < T && (tile2 + 1) * EPT <= N) {
       prefetch_range_l2(p.root + t2 * p.root_frame_stride + tile2 * EPT * ROOT_ENV, EPT * ROOT_ENV * 4);
@@ -242,8 +242,8 @@ extern "C" int32_t mmb_one_ant_step(const mmb_one_ant_params* pp, void* stream) 
   dim3 grid((p.num_envs + EPT - 1) / EPT, p.num_frames);
   {
     LaunchScope ls(K_ONE_ANT, st);
-    if (p.flavor == MMB_FLAVOR_CUDA) one_ant_kernel<FLAVOR_CUDA><<<grid, EPT, 0, st>>>(p);
-    else one_ant_kernel<FLAVOR_CPU><<<grid, EPT, 0, st>>>(p);
+    if (p.flavor == MMB_FLAVOR_CUDA) one_ant_kernel<FLAVOR_CUDA><<<grid, EPT, 0, st>>>(p, 2 * sm_count());
+    else one_ant_kernel<FLAVOR_CPU><<<grid, EPT, 0, st>>>(p, 2 * sm_count());
   }
   if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   if (p.num_frames > 1) {

@@ -9,16 +9,23 @@
 // The reference pays a host sync (`len(env_ids)`) and ~45 small kernels per step for this; here the
 // count stays on the device (counts[f]) and nothing is read back.
 //
-// One CTA of 1024 threads per row f (a row = the flags of one frame), four consecutive envs per thread: shuffle scan of
-// the per-thread counts inside a warp, warp totals scanned by warp 0, running offset across 4096-env passes.  O(N) flag
-// bytes per row; fine up to ~1M envs per row (one SM streams the flags); a multi-CTA decoupled look-back scan is the
-// planned upgrade for larger N.
+// One CTA of 256 threads per 4096 envs of a flag row, SIXTEEN consecutive envs per thread (one 128-bit load of the uint8
+// flags): shuffle scan of the per-thread counts inside a warp, the 8 warp totals scanned by warp 0.  The first version used
+// 1024-thread CTAs with 4 flags per thread: next to a running step kernel (4 x 352 threads resident per SM) such a CTA
+// waits until two step CTAs of one SM have retired before it can start at all; a 256-thread CTA fits into the slack of
+// any SM.  The DOF re-randomisation runs one item per (reset env, DOF pair): one Philox call feeds the two DOFs of the
+// pair for all ten ants (the reference draws ONE (len, 8) noise tensor for all ants, ten_ant.py:822-826), instead of one
+// call per (env, ant, dof) as before.
 #include "../../include/mmb.h"
 #include "mmb_common.cuh"
 #include "mmb_math.cuh"
 
 namespace mmb {
 namespace {
+
+constexpr int RNT = 256;       // threads per CTA
+constexpr int RFPT = 16;       // flags per thread
+constexpr int RCHUNK = RNT * RFPT;   // 4096 envs per pass / per CTA of the multi-CTA scan
 
 struct TaskShape { int apn, na, nb, dofs, ants; };
 __device__ __forceinline__ TaskShape shape_of(int task) {
@@ -27,11 +34,107 @@ __device__ __forceinline__ TaskShape shape_of(int task) {
   return {4, 4, 4, 16, 0};
 }
 
-__global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb_reset_params p) {
-  __shared__ int warp_tot[32];
-  __shared__ int s_running, s_chunk_total;
+// the 16 flags of envs [e0, e0 + 16) as a bit mask
+__device__ __forceinline__ unsigned load_flags16(const int64_t* f64, const uint8_t* f8, int e0, int N) {
+  unsigned bits = 0;
+  if (e0 >= N) return 0;
+  if (f8 && e0 + RFPT <= N && (reinterpret_cast<uintptr_t>(f8 + e0) & 15u) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(f8 + e0);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if ((w[q] >> (8 * b)) & 0xffu) bits |= 1u << (4 * q + b);
+  } else {
+#pragma unroll
+    for (int j = 0; j < RFPT; ++j) {
+      const int e = e0 + j;
+      if (e < N && (f64 ? (f64[e] != 0) : (f8[e] != 0))) bits |= 1u << j;
+    }
+  }
+  return bits;
+}
+
+// exclusive rank of this thread's first flagged env inside the CTA's 4096-env pass; *total = flagged envs of the pass
+__device__ __forceinline__ int block_exclusive_scan(int cnt, int* warp_tot, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int wt = lane < RNT / 32 ? warp_tot[lane] : 0;
+    int wincl = wt;
+#pragma unroll
+    for (int o = 1; o < RNT / 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wincl, o);
+      if (lane >= o) wincl += v;
+    }
+    if (lane < RNT / 32) warp_tot[lane] = wincl - wt;   // exclusive prefix of the warp totals
+    if (lane == RNT / 32 - 1) *total = wincl;
+  }
+  __syncthreads();
+  return warp_tot[wid] + incl - cnt;
+}
+
+__device__ __forceinline__ void write_lists(unsigned bits, int e0, int i, const TaskShape& sh, int64_t* env_ids, int32_t* ia,
+                                            int32_t* ib) {
+  while (bits) {
+    const int j = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int e = e0 + j;
+    env_ids[i] = e;
+    if (ia) for (int q = 0; q < sh.na; ++q) ia[i * sh.na + q] = sh.apn * e + q;
+    if (ib) for (int q = 0; q < sh.nb; ++q) ib[i * sh.nb + q] = sh.apn * e + q;
+    ++i;
+  }
+}
+
+// ten_ant.py:822-857 / one_ant.py:371-376 for the reset envs with row ordinals [seg0, seg0 + count): one item per
+// (reset env, DOF pair); the pair's (pos, vel, pos, vel) goes out as one 128-bit store per ant
+__device__ __forceinline__ void rerandomise_dofs(const mmb_reset_params& p, const TaskShape& sh, int f, int seg0, int count,
+                                                 const int64_t* env_ids, float* dof) {
+  const float* npos = p.noise_pos ? p.noise_pos + (int64_t)f * p.noise_row_stride : nullptr;
+  const float* nvel = p.noise_vel ? p.noise_vel + (int64_t)f * p.noise_row_stride : nullptr;
+  const bool al16 = (reinterpret_cast<uintptr_t>(dof) & 15u) == 0;
+  for (int it = threadIdx.x; it < count * 4; it += blockDim.x) {
+    const int i = seg0 + (it >> 2), jp = it & 3, j0 = 2 * jp;
+    const int e = (int)env_ids[i];
+    float np0, np1, nv0, nv1;
+    if (p.noise_mode == 0) {
+      np0 = npos[(int64_t)i * 8 + j0]; np1 = npos[(int64_t)i * 8 + j0 + 1];
+      nv0 = nvel[(int64_t)i * 8 + j0]; nv1 = nvel[(int64_t)i * 8 + j0 + 1];
+    } else {  // torch_rand_float(lo, hi) = (hi - lo) * U[0,1) + lo, keyed by env so every ant shares the draw
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(p.step + f), (uint32_t)jp, 0u),
+                                    make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+      np0 = fadd(fmul(0.4f, u01(r.x)), -0.2f); nv0 = fadd(fmul(0.2f, u01(r.y)), -0.1f);
+      np1 = fadd(fmul(0.4f, u01(r.z)), -0.2f); nv1 = fadd(fmul(0.2f, u01(r.w)), -0.1f);
+    }
+    // tensor_clamp = max(min(t, hi), lo)
+    const float pos0 = fmaxf(fminf(fadd(p.c.initial_dof_pos[j0], np0), p.c.dof_upper[j0]), p.c.dof_lower[j0]);
+    const float pos1 = fmaxf(fminf(fadd(p.c.initial_dof_pos[j0 + 1], np1), p.c.dof_upper[j0 + 1]), p.c.dof_lower[j0 + 1]);
+    for (int a = 0; a < sh.ants; ++a) {
+      float* d = dof + ((int64_t)e * sh.dofs + a * 8 + j0) * 2;
+      if (al16) {
+        stg4(d, make_float4(pos0, nv0, pos1, nv1));
+      } else {
+        *reinterpret_cast<float2*>(d) = make_float2(pos0, nv0);
+        *reinterpret_cast<float2*>(d + 2) = make_float2(pos1, nv1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_reset_params p) {
+  __shared__ int warp_tot[RNT / 32];
+  __shared__ int s_chunk_total;
   const int f = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x;
   const int N = p.num_envs;
   const TaskShape sh = shape_of(p.task);
   const int64_t* f64 = p.flags_i64 ? p.flags_i64 + (int64_t)f * p.flags_i64_row_stride : nullptr;
@@ -40,92 +143,27 @@ __global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb
   int32_t* ia = p.index_a ? p.index_a + (int64_t)f * p.index_a_row_stride : nullptr;
   int32_t* ib = p.index_b ? p.index_b + (int64_t)f * p.index_b_row_stride : nullptr;
 
-  if (tid == 0) s_running = 0;
-  __syncthreads();
-  // Four consecutive envs per thread (one 32-bit load of the uint8 flags), 4096 envs per pass: the ordered rank of a
-  // flagged env = running total + exclusive scan of the per-thread counts (shuffle scan inside a warp, the 32 warp totals
-  // scanned by warp 0) + its rank among the thread's four.  One pass and two barriers for N <= 4096.
-  for (int base = 0; base < N; base += 4096) {
-    const int e4 = base + 4 * tid;
-    unsigned bits = 0;
-    if (f8 && e4 + 3 < N && (reinterpret_cast<uintptr_t>(f8 + e4) & 3u) == 0) {
-      const uchar4 v = *reinterpret_cast<const uchar4*>(f8 + e4);
-      bits = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = e4 + j;
-        if (e < N && (f64 ? (f64[e] != 0) : (f8[e] != 0))) bits |= 1u << j;
-      }
-    }
-    const int cnt = __popc(bits);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      const int wt = warp_tot[lane];
-      int wincl = wt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, wincl, o);
-        if (lane >= o) wincl += v;
-      }
-      warp_tot[lane] = wincl - wt;          // exclusive prefix of the warp totals
-      if (lane == 31) s_chunk_total = wincl;
-    }
-    __syncthreads();
-    int i = s_running + warp_tot[wid] + incl - cnt;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (bits & (1u << j)) {
-        const int e = e4 + j;
-        env_ids[i] = e;
-        if (ia) for (int q = 0; q < sh.na; ++q) ia[i * sh.na + q] = sh.apn * e + q;
-        if (ib) for (int q = 0; q < sh.nb; ++q) ib[i * sh.nb + q] = sh.apn * e + q;
-        ++i;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) s_running += s_chunk_total;
-    __syncthreads();
+  // ordered rank of a flagged env = flagged envs of the earlier passes + exclusive scan of the per-thread counts + its
+  // rank among the thread's sixteen.  One pass and two barriers for N <= 4096.
+  int running = 0;
+  for (int base = 0; base < N; base += RCHUNK) {
+    const int e0 = base + RFPT * tid;
+    const unsigned bits = load_flags16(f64, f8, e0, N);
+    const int excl = block_exclusive_scan(__popc(bits), warp_tot, &s_chunk_total);
+    write_lists(bits, e0, running + excl, sh, env_ids, ia, ib);
+    running += s_chunk_total;
+    __syncthreads();                      // warp_tot / s_chunk_total are rewritten by the next pass
   }
-  const int count = s_running;
+  const int count = running;
   if (tid == 0 && p.counts) p.counts[f] = count;
   if (count == 0) return;
+  __syncthreads();                        // env_ids of this row (written by this CTA) are read back below
 
   float* dof = p.dof_state ? p.dof_state + (int64_t)f * p.dof_state_row_stride : nullptr;
-  if (sh.ants > 0 && dof) {
-    // ten_ant.py:822-857 / one_ant.py:371-376: one (pos, vel) pair per (reset env, dof)
-    const float* npos = p.noise_pos ? p.noise_pos + (int64_t)f * p.noise_row_stride : nullptr;
-    const float* nvel = p.noise_vel ? p.noise_vel + (int64_t)f * p.noise_row_stride : nullptr;
-    const int items = count * sh.dofs;
-    for (int it = tid; it < items; it += 1024) {
-      const int i = it / sh.dofs, d = it - i * sh.dofs, j = d & 7;
-      const int e = (int)env_ids[i];
-      float np_, nv_;
-      if (p.noise_mode == 0) {
-        np_ = npos[(int64_t)i * 8 + j];
-        nv_ = nvel[(int64_t)i * 8 + j];
-      } else {  // torch_rand_float(lo, hi) = (hi - lo) * U[0,1) + lo, keyed by env so every ant shares the draw
-        uint4 r = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(p.step + f), (uint32_t)(j >> 1), 0u),
-                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-        float up = u01((j & 1) ? r.z : r.x), uv = u01((j & 1) ? r.w : r.y);
-        np_ = fadd(fmul(0.4f, up), -0.2f);
-        nv_ = fadd(fmul(0.2f, uv), -0.1f);
-      }
-      float pos = fadd(p.c.initial_dof_pos[j], np_);
-      pos = fmaxf(fminf(pos, p.c.dof_upper[j]), p.c.dof_lower[j]);  // tensor_clamp = max(min(t, hi), lo)
-      *reinterpret_cast<float2*>(dof + ((int64_t)e * sh.dofs + d) * 2) = make_float2(pos, nv_);
-    }
-  }
+  if (sh.ants > 0 && dof) rerandomise_dofs(p, sh, f, 0, count, env_ids, dof);
   if (p.task == MMB_TASK_INGENUITY) {
     if (dof) {  // multi_ingenuity.py:234-241: every env, whenever reset_idx runs
-      for (int it = tid; it < N * 4; it += 1024) {
+      for (int it = tid; it < N * 4; it += RNT) {
         float* d = dof + (int64_t)it * 8;  // 4 dofs x (pos, vel) per helicopter
         d[3] = -50.0f;
         d[7] = 50.0f;
@@ -133,7 +171,7 @@ __global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb
     }
     if (p.forces_state) {  // multi_ingenuity.py:243-244
       const int items = count * 72;
-      for (int it = tid; it < items; it += 1024) {
+      for (int it = tid; it < items; it += RNT) {
         const int i = it / 72, r = it - i * 72;
         p.forces_state[(int64_t)env_ids[i] * 72 + r] = 0.0f;
       }
@@ -145,12 +183,12 @@ __global__ void __launch_bounds__(1024) reset_kernel(const __grid_constant__ mmb
 // to the caller's scratch, sums the totals of the chunks before it (earlier CTAs in launch order: forward progress as in
 // any single-pass scan), and writes its own ordered segment.  The CTA that completes the row's look-backs last clears
 // the scratch for the next launch / graph replay.
-__global__ void __launch_bounds__(1024) reset_scan_kernel(const __grid_constant__ mmb_reset_params p) {
-  __shared__ int warp_tot[32];
+__global__ void __launch_bounds__(RNT) reset_scan_kernel(const __grid_constant__ mmb_reset_params p) {
+  __shared__ int warp_tot[RNT / 32];
   __shared__ int s_running, s_chunk_total;
   const int f = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   unsigned long long* status = reinterpret_cast<unsigned long long*>(p.scan_scratch) + (size_t)f * (chunks + 1);   // [chunks] totals, [chunks] done counter
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int N = p.num_envs;
   const TaskShape sh = shape_of(p.task);
   const int64_t* f64 = p.flags_i64 ? p.flags_i64 + (int64_t)f * p.flags_i64_row_stride : nullptr;
@@ -159,77 +197,28 @@ __global__ void __launch_bounds__(1024) reset_scan_kernel(const __grid_constant_
   int32_t* ia = p.index_a ? p.index_a + (int64_t)f * p.index_a_row_stride : nullptr;
   int32_t* ib = p.index_b ? p.index_b + (int64_t)f * p.index_b_row_stride : nullptr;
 
-  if (tid == 0) s_running = 0;
-  __syncthreads();
-  // Four consecutive envs per thread (one 32-bit load of the uint8 flags), 4096 envs per pass: the ordered rank of a
-  // flagged env = running total + exclusive scan of the per-thread counts (shuffle scan inside a warp, the 32 warp totals
-  // scanned by warp 0) + its rank among the thread's four.  One pass and two barriers for N <= 4096.
-  {
-    const int base = chunk * 4096;
-    const int e4 = base + 4 * tid;
-    unsigned bits = 0;
-    if (f8 && e4 + 3 < N && (reinterpret_cast<uintptr_t>(f8 + e4) & 3u) == 0) {
-      const uchar4 v = *reinterpret_cast<const uchar4*>(f8 + e4);
-      bits = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = e4 + j;
-        if (e < N && (f64 ? (f64[e] != 0) : (f8[e] != 0))) bits |= 1u << j;
-      }
-    }
-    const int cnt = __popc(bits);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      const int wt = warp_tot[lane];
-      int wincl = wt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, wincl, o);
-        if (lane >= o) wincl += v;
-      }
-      warp_tot[lane] = wincl - wt;          // exclusive prefix of the warp totals
-      if (lane == 31) s_chunk_total = wincl;
-    }
-    __syncthreads();
-    if (tid == 0) {                       // publish this chunk's total: bit 63 = valid
-      *reinterpret_cast<volatile unsigned long long*>(status + chunk) = (1ull << 63) | (unsigned long long)s_chunk_total;
-      s_running = 0;
-    }
-    __syncthreads();
-    {                                     // look back: totals of chunks 0..chunk-1
-      int part = 0;
-      for (int j = tid; j < chunk; j += 1024) {
-        unsigned long long v;
-        do { v = *reinterpret_cast<volatile unsigned long long*>(status + j); } while (!(v >> 63));
-        part += (int)(v & 0xffffffffu);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0 && part) atomicAdd(&s_running, part);
-    }
-    __syncthreads();
-    int i = s_running + warp_tot[wid] + incl - cnt;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (bits & (1u << j)) {
-        const int e = e4 + j;
-        env_ids[i] = e;
-        if (ia) for (int q = 0; q < sh.na; ++q) ia[i * sh.na + q] = sh.apn * e + q;
-        if (ib) for (int q = 0; q < sh.nb; ++q) ib[i * sh.nb + q] = sh.apn * e + q;
-        ++i;
-      }
-    }
-    __syncthreads();
+  const int e0 = chunk * RCHUNK + RFPT * tid;
+  const unsigned bits = load_flags16(f64, f8, e0, N);
+  const int excl = block_exclusive_scan(__popc(bits), warp_tot, &s_chunk_total);
+  if (tid == 0) {                         // publish this chunk's total: bit 63 = valid
+    *reinterpret_cast<volatile unsigned long long*>(status + chunk) = (1ull << 63) | (unsigned long long)s_chunk_total;
+    s_running = 0;
   }
+  __syncthreads();
+  {                                       // look back: totals of chunks 0..chunk-1
+    int part = 0;
+    for (int j = tid; j < chunk; j += RNT) {
+      unsigned long long v;
+      do { v = *reinterpret_cast<volatile unsigned long long*>(status + j); } while (!(v >> 63));
+      part += (int)(v & 0xffffffffu);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0 && part) atomicAdd(&s_running, part);
+  }
+  __syncthreads();
   const int seg0 = s_running, seg_n = s_chunk_total;   // this CTA's ordered segment of the row's lists
+  write_lists(bits, e0, seg0 + excl, sh, env_ids, ia, ib);
   if (tid == 0) {
     if (chunk == chunks - 1 && p.counts) p.counts[f] = seg0 + seg_n;
     __threadfence();
@@ -237,34 +226,11 @@ __global__ void __launch_bounds__(1024) reset_scan_kernel(const __grid_constant_
       for (int j = 0; j <= chunks; ++j) status[j] = 0ull;
     }
   }
-  const int count = seg_n;
-  if (count == 0) return;
+  if (seg_n == 0) return;
+  __syncthreads();                        // this CTA's env_ids segment is read back below
 
   float* dof = p.dof_state ? p.dof_state + (int64_t)f * p.dof_state_row_stride : nullptr;
-  if (sh.ants > 0 && dof) {
-    // ten_ant.py:822-857 / one_ant.py:371-376: one (pos, vel) pair per (reset env, dof)
-    const float* npos = p.noise_pos ? p.noise_pos + (int64_t)f * p.noise_row_stride : nullptr;
-    const float* nvel = p.noise_vel ? p.noise_vel + (int64_t)f * p.noise_row_stride : nullptr;
-    const int items = count * sh.dofs;
-    for (int it = tid; it < items; it += 1024) {
-      const int i = seg0 + it / sh.dofs, d = it - (it / sh.dofs) * sh.dofs, j = d & 7;   // i: ordinal in the row
-      const int e = (int)env_ids[i];
-      float np_, nv_;
-      if (p.noise_mode == 0) {
-        np_ = npos[(int64_t)i * 8 + j];
-        nv_ = nvel[(int64_t)i * 8 + j];
-      } else {  // torch_rand_float(lo, hi) = (hi - lo) * U[0,1) + lo, keyed by env so every ant shares the draw
-        uint4 r = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(p.step + f), (uint32_t)(j >> 1), 0u),
-                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-        float up = u01((j & 1) ? r.z : r.x), uv = u01((j & 1) ? r.w : r.y);
-        np_ = fadd(fmul(0.4f, up), -0.2f);
-        nv_ = fadd(fmul(0.2f, uv), -0.1f);
-      }
-      float pos = fadd(p.c.initial_dof_pos[j], np_);
-      pos = fmaxf(fminf(pos, p.c.dof_upper[j]), p.c.dof_lower[j]);  // tensor_clamp = max(min(t, hi), lo)
-      *reinterpret_cast<float2*>(dof + ((int64_t)e * sh.dofs + d) * 2) = make_float2(pos, nv_);
-    }
-  }
+  if (sh.ants > 0 && dof) rerandomise_dofs(p, sh, f, seg0, seg_n, env_ids, dof);
 }
 
 }  // namespace
@@ -282,11 +248,11 @@ extern "C" int32_t mmb_reset_compact(const mmb_reset_params* pp, void* stream) {
   if (p.dof_state && (reinterpret_cast<uintptr_t>(p.dof_state) & 7u)) return MMB_EALIGN;
   {
     LaunchScope ls(K_RESET, (cudaStream_t)stream);
-    const int chunks = (p.num_envs + 4095) / 4096;
+    const int chunks = (p.num_envs + RCHUNK - 1) / RCHUNK;
     if (p.scan_scratch && chunks > 1 && p.task != MMB_TASK_INGENUITY)
-      reset_scan_kernel<<<dim3(chunks, p.num_rows), 1024, 0, (cudaStream_t)stream>>>(p);
+      reset_scan_kernel<<<dim3(chunks, p.num_rows), RNT, 0, (cudaStream_t)stream>>>(p);
     else
-      reset_kernel<<<p.num_rows, 1024, 0, (cudaStream_t)stream>>>(p);
+      reset_kernel<<<p.num_rows, RNT, 0, (cudaStream_t)stream>>>(p);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

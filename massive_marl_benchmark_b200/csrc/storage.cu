@@ -48,6 +48,7 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
 // ---- statistics exchange over peer memory (mmb.h "Env-sharded multi-GPU") ----------------------
 struct XchgDev {  // kernel-parameter copy of mmb_xchg
   int world, rank, slots, enabled;
+  long long spin_ns;   // bound of the flag wait in ns (%globaltimer); < 0: wait for ever
   unsigned long long* state;
   unsigned long long* mailbox[MMB_MAX_RANKS];
 };
@@ -56,6 +57,7 @@ inline XchgDev make_xchg(const mmb_xchg* x) {
   XchgDev d{};
   if (!x) return d;
   d.world = x->world; d.rank = x->rank; d.slots = x->slots; d.enabled = 1;
+  d.spin_ns = x->timeout_ms < 0 ? -1ll : (x->timeout_ms == 0 ? 10000ll : (long long)x->timeout_ms) * 1000000ll;
   d.state = reinterpret_cast<unsigned long long*>(x->state);
   for (int r = 0; r < MMB_MAX_RANKS; ++r) d.mailbox[r] = reinterpret_cast<unsigned long long*>(x->mailbox[r]);
   return d;
@@ -84,6 +86,33 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// {count, sum, sumsq} of an accumulator: the three base words, plus (MMB_NORM_SLOTS) the slot area the fused GAE of
+// mmb_ten_ant_step fills, summed in index order
+__device__ __forceinline__ void read_stats(const double* stats, bool slots, double& cnt, double& s1, double& s2) {
+  cnt = stats[0]; s1 = stats[1]; s2 = stats[2];
+  if (slots) {
+    double a[MMB_STAT_SLOTS], b[MMB_STAT_SLOTS];
+#pragma unroll
+    for (int i = 0; i < MMB_STAT_SLOTS; ++i) {
+      a[i] = __ldcg(stats + 4 + i * MMB_STAT_SLOT_STRIDE);
+      b[i] = __ldcg(stats + 4 + i * MMB_STAT_SLOT_STRIDE + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < MMB_STAT_SLOTS; ++i) { s1 += a[i]; s2 += b[i]; }
+  }
+}
+__device__ __forceinline__ void clear_stats_words(double* stats, bool slots) {
+  stats[0] = 0.0; stats[1] = 0.0; stats[2] = 0.0;
+  if (slots)
+    for (int i = 0; i < MMB_STAT_SLOTS; ++i) { stats[4 + i * MMB_STAT_SLOT_STRIDE] = 0.0; stats[4 + i * MMB_STAT_SLOT_STRIDE + 1] = 0.0; }
 }
 
 constexpr int GAE_CHUNK = 16;  // horizon 16 (the reference's default is 8): all loads of a rollout in flight at once
@@ -156,35 +185,39 @@ __device__ __forceinline__ void normalize_span(float* __restrict__ adv, int64_t 
 // peer stores in flight at once - and clears the accumulator.  Every block then waits for the `world` flags of
 // exchange q = done + 1 in its OWN mailbox (local memory; the peers wrote them over NVLink), sums the shards in rank
 // order (bit-identical on every rank) and normalises its slice.  The last block to finish advances `done`.
-constexpr long long XCHG_SPIN_CYCLES = 4000000000ll;  // ~2 s at 1.9 GHz, then give up and count an error
-
 __global__ void __launch_bounds__(256) adv_normalize_xchg_kernel(float* __restrict__ adv, int64_t n, double* stats,
-                                                                 const __grid_constant__ XchgDev x, float eps) {
+                                                                 const __grid_constant__ XchgDev x, float eps, int slots_on) {
   __shared__ double sh[MMB_MAX_RANKS][3];
+  __shared__ int s_bad;
   const unsigned long long q = ld_relaxed_sys(x.state + 1) + 1ull;
   const size_t slot = (size_t)(q % (unsigned)x.slots) * x.world;
+  if (threadIdx.x == 0) s_bad = 0;
   if (blockIdx.x == 0) {
     if ((int)threadIdx.x < x.world) {
-      const unsigned long long* st = reinterpret_cast<const unsigned long long*>(stats);
-      const unsigned long long c = st[0], a = st[1], b = st[2];
+      double cd, ad, bd;
+      read_stats(stats, slots_on != 0, cd, ad, bd);
       unsigned long long* box = x.mailbox[threadIdx.x] + (slot + x.rank) * 4;
-      st_relaxed_sys(box + 0, c);
-      st_relaxed_sys(box + 1, a);
-      st_relaxed_sys(box + 2, b);
+      st_relaxed_sys(box + 0, (unsigned long long)__double_as_longlong(cd));
+      st_relaxed_sys(box + 1, (unsigned long long)__double_as_longlong(ad));
+      st_relaxed_sys(box + 2, (unsigned long long)__double_as_longlong(bd));
       st_release_sys(box + 3, q);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { stats[0] = 0.0; stats[1] = 0.0; stats[2] = 0.0; }
+    if (threadIdx.x == 0) clear_stats_words(stats, slots_on != 0);
   }
+  __syncthreads();
   if ((int)threadIdx.x < x.world) {
     const unsigned long long* box = x.mailbox[x.rank] + (slot + threadIdx.x) * 4;
-    const long long t0 = clock64();
+    const unsigned long long t0 = globaltimer_ns();
     unsigned long long f = ld_acquire_sys(box + 3);
-    while (f < q && clock64() - t0 < XCHG_SPIN_CYCLES) {
+    while (f < q && (x.spin_ns < 0 || (long long)(globaltimer_ns() - t0) < x.spin_ns)) {
       __nanosleep(32);
       f = ld_acquire_sys(box + 3);
     }
-    if (f != q && blockIdx.x == 0) atomicAdd(x.state + 3, 1ull);  // timed out, or the slot was overrun
+    if (f != q) {   // timed out, or the slot was overrun: no partial moments are ever used (see below)
+      s_bad = 1;
+      if (blockIdx.x == 0) atomicAdd(x.state + 3, 1ull);
+    }
     sh[threadIdx.x][0] = __longlong_as_double((long long)ld_relaxed_sys(box + 0));
     sh[threadIdx.x][1] = __longlong_as_double((long long)ld_relaxed_sys(box + 1));
     sh[threadIdx.x][2] = __longlong_as_double((long long)ld_relaxed_sys(box + 2));
@@ -195,8 +228,9 @@ __global__ void __launch_bounds__(256) adv_normalize_xchg_kernel(float* __restri
   const double mean_d = s1 / cnt;
   double var_d = (s2 - s1 * mean_d) / (cnt - 1.0);
   if (var_d < 0.0) var_d = 0.0;
-  const float mean = (float)mean_d;
-  const float denom = fadd((float)sqrt(var_d), eps);
+  float mean = (float)mean_d;
+  float denom = fadd((float)sqrt(var_d), eps);
+  if (s_bad) mean = denom = __int_as_float(0x7fc00000);   // loud: the whole plane becomes NaN
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n4 = aligned16(adv) ? (n >> 2) : 0;
@@ -273,15 +307,16 @@ __global__ void __launch_bounds__(256) gae_ppo_vec4_kernel(const __grid_constant
 // (adv - mean) / (std_unbiased + eps).  With `clear_stats` the last block to have read the statistics clears them
 // (ticket counter in stats[3]), so the accumulator is ready for the next rollout without a memset launch and
 // the launch sequence can be replayed from a CUDA graph.
-__global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ adv, int64_t n, double* __restrict__ stats,
-                                                            float eps, int clear_stats) {
-  const double cnt = stats[0], s1 = stats[1], s2 = stats[2];
-  if (clear_stats) {
+__global__ void __launch_bounds__(256) adv_normalize_kernel(float* __restrict__ adv, int64_t n, double* stats,
+                                                            float eps, int flags) {
+  double cnt, s1, s2;
+  read_stats(stats, (flags & MMB_NORM_SLOTS) != 0, cnt, s1, s2);
+  if (flags & MMB_NORM_CLEAR) {
     __syncthreads();  // every thread of this block holds its copy
     if (threadIdx.x == 0) {
       unsigned long long* ticket = reinterpret_cast<unsigned long long*>(stats + 3);
       if (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull) {
-        stats[0] = 0.0; stats[1] = 0.0; stats[2] = 0.0;
+        clear_stats_words(stats, (flags & MMB_NORM_SLOTS) != 0);
         *ticket = 0ull;
       }
     }
@@ -465,43 +500,48 @@ extern "C" int32_t mmb_gae_ppo(const mmb_gae_ppo_params* pp, void* stream) {
     if (p.num_envs >= 8192 && (p.num_envs & 3) == 0 && (al & 15u) == 0 && (reinterpret_cast<uintptr_t>(p.dones) & 3u) == 0 &&
         vec_chunk > 0) {
       int blocks = (p.num_envs / 4 + 255) / 256;
-      if (blocks > 148 * 8) blocks = 148 * 8;
+      if (blocks > sm_count() * 8) blocks = sm_count() * 8;
       if (vec_chunk == 8) gae_ppo_vec4_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
       else if (vec_chunk == 2) gae_ppo_vec4_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
       else if (vec_chunk == 16) gae_ppo_vec4_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
       else gae_ppo_vec4_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
     } else {
-      int blocks = (p.num_envs + 255) / 256;
-      if (blocks > 148 * 8) blocks = 148 * 8;
-      gae_ppo_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+      // small rollouts: 64-thread CTAs, so that 4096 envs are 64 CTAs on 64 SMs instead of 16 on 16 (the scan is a
+      // latency chain per thread; spreading it costs nothing and finds free SM slots next to a running step kernel)
+      const int bs = p.num_envs >= 256 * sm_count() ? 256 : 64;
+      int blocks = (p.num_envs + bs - 1) / bs;
+      if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+      gae_ppo_kernel<<<blocks, bs, 0, (cudaStream_t)stream>>>(p);
     }
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
-extern "C" int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, float eps, int32_t clear_stats,
+extern "C" int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, float eps, int32_t flags,
                                      void* stream) {
-  if (!advantages || !stats || n <= 0) return MMB_EINVAL;
+  if (!advantages || !stats || n <= 0 || (flags & ~(MMB_NORM_CLEAR | MMB_NORM_SLOTS))) return MMB_EINVAL;
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   {
     LaunchScope ls(K_ADV_NORM, (cudaStream_t)stream);
-    adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps, clear_stats);
+    adv_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, eps, flags);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
 extern "C" int32_t mmb_adv_normalize_xchg(float* advantages, int64_t n, double* stats, const mmb_xchg* xchg, float eps,
-                                          void* stream) {
-  if (!advantages || !stats || !xchg || n <= 0 || !xchg_valid(xchg)) return MMB_EINVAL;
+                                          int32_t flags, void* stream) {
+  if (!advantages || !stats || !xchg || n <= 0 || !xchg_valid(xchg) || (flags & ~(MMB_NORM_CLEAR | MMB_NORM_SLOTS)))
+    return MMB_EINVAL;
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;  // all blocks co-resident: each one waits on the mailbox flags
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;  // all blocks co-resident: each one waits on the mailbox flags
   const XchgDev xd = make_xchg(xchg);
   {
     LaunchScope ls(K_ADV_NORM_XCHG, (cudaStream_t)stream);
-    adv_normalize_xchg_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, xd, eps);
+    adv_normalize_xchg_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, stats, xd, eps,
+                                                                                 (flags & MMB_NORM_SLOTS) ? 1 : 0);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
@@ -560,7 +600,7 @@ extern "C" int32_t mmb_rollout_add(const mmb_rollout_add_params* pp, void* strea
   if (maxn < p.num_envs) maxn = p.num_envs;
   int64_t bx = (maxn / 4 + 255) / 256;
   if (bx < 1) bx = 1;
-  if (bx > 148 * 8) bx = 148 * 8;
+  if (bx > sm_count() * 8) bx = sm_count() * 8;
   {
     LaunchScope ls(K_ROLLOUT_ADD, (cudaStream_t)stream);
     rollout_add_kernel<<<dim3((unsigned)bx, 9), 256, 0, (cudaStream_t)stream>>>(p);
@@ -578,7 +618,7 @@ extern "C" int32_t mmb_gae_marl(const mmb_gae_marl_params* pp, void* stream) {
   {
     LaunchScope ls(K_GAE_MARL, (cudaStream_t)stream);
     int bx = (p.num_envs + 255) / 256;
-    const int cap = (148 * 8 + p.num_agents - 1) / p.num_agents;
+    const int cap = (sm_count() * 8 + p.num_agents - 1) / p.num_agents;
     if (bx > cap) bx = cap;
     gae_marl_kernel<<<dim3(bx, p.num_agents), 256, 0, (cudaStream_t)stream>>>(p);
   }

@@ -55,9 +55,7 @@ inline int prefetch_distance() {
   static const int dist = [] {
     const char* v = getenv("MMB_TEN_ANT_PREFETCH");
     if (v) return atoi(v);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     return sms + sms / 2;
   }();
   return dist;
@@ -103,8 +101,8 @@ __device__ __forceinline__ void load_carry_one(const float* __restrict__ root, i
 
 // progress / reset chain of one env over frames [t0, t0+cnt) given their `fallen` bits
 // (ten_ant.py:896-901 progress += 1 and reset_idx zeroing, :1296-1299 reset rule); writes the final done flags.
-__device__ __forceinline__ void chain_bits(const mmb_ten_ant_params& p, int e, int t0, int cnt, uint32_t fallen_bits,
-                                           int64_t& prog, bool& flag) {
+__device__ __forceinline__ uint32_t chain_bits(const mmb_ten_ant_params& p, int e, int t0, int cnt, uint32_t fallen_bits,
+                                               int64_t& prog, bool& flag) {
   const float thr = (float)((double)p.c.max_episode_length - 1.0);
   uint32_t out_bits = 0;
   for (int j = 0; j < cnt; ++j) {
@@ -119,7 +117,10 @@ __device__ __forceinline__ void chain_bits(const mmb_ten_ant_params& p, int e, i
     if (p.dones_u8) p.dones_u8[(int64_t)t * p.dones_u8_frame_stride + e] = (uint8_t)v;
     if (p.dones_i64) p.dones_i64[(int64_t)t * p.dones_i64_frame_stride + e] = v;
   }
+  return out_bits;
 }
+
+constexpr long long CHAIN_SPIN_CYCLES = 2000000000ll;  // ~1 s: then count an error (scratch word N) instead of guessing
 
 // chain of one env with the `fallen` flags read back from the done plane (fallback path: T > 32 or no scratch).
 // All flags of a 32-frame chunk are loaded before the dependent chain runs: one memory latency, not T.
@@ -174,10 +175,8 @@ __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* _
 // Per-env finish by one thread: ordered sums over the ten ants' partial terms (ten_ant.py:1173-1301), reward, and the
 // progress / reset bookkeeping (inline for T == 1, data-carrying atomic + last-reporter chain for T <= 32).
 // `root_env`: this env's 143-float root block of frame t still intact in shared memory (role-split kernel), or nullptr.
-__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo,
-                                           const float* root_env = nullptr) {
-  const mmb_ant_consts& c = p.c;
-  const int T = p.num_frames;
+// ordered sums over the ten ants' partial terms and the reward of one env (ten_ant.py:1173-1301)
+__device__ __forceinline__ float env_reward(const mmb_ant_consts& c, const float* pt, const float* bo, bool& fallen_out) {
   float adr = pt[0], gdr = pt[1], up = pt[2], elec = pt[3], asq = pt[4];
   int la = __float_as_int(pt[5]);
   int lim = la & 0xff, n_arrive = la >> 8;
@@ -200,6 +199,29 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
   total_r = fsub(total_r, fmul(c.energy_cost, elec));
   total_r = fsub(total_r, fmul((float)lim, c.joints_at_limit_cost));
   if (fallen) total_r = c.death_cost;
+  fallen_out = fallen;
+  return total_r;
+}
+
+// carry of one env from the last frame's tile in shared memory (the executor is the frame T-1 unit: ant xy, box xy and
+// the goal direction of the last frame are there already; bo[0..3] was computed from the same box row, same operations)
+__device__ __forceinline__ void carry_from_tile(const mmb_ten_ant_params& p, int en, const float* bo, const float* root_env) {
+#pragma unroll
+  for (int kk = 0; kk < A; ++kk) {
+    float gx, gy;
+    goal_of(kk, bo[2], bo[3], bo[0], bo[1], gx, gy);
+    *reinterpret_cast<float2*>(p.pos_before + ((int64_t)en * A + kk) * 2) = make_float2(root_env[kk * 13], root_env[kk * 13 + 1]);
+    *reinterpret_cast<float2*>(p.goal_before + ((int64_t)en * A + kk) * 2) = make_float2(gx, gy);
+  }
+  *reinterpret_cast<float2*>(p.box_before + (int64_t)en * 2) = make_float2(bo[2], bo[3]);
+}
+
+__device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, int en, const float* pt, const float* bo,
+                                           const float* root_env = nullptr) {
+  const mmb_ant_consts& c = p.c;
+  const int T = p.num_frames;
+  bool fallen;
+  const float total_r = env_reward(c, pt, bo, fallen);
   if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = total_r;
   if (T == 1) {
     p.box_before[(int64_t)en * 2] = bo[2];
@@ -227,9 +249,13 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
       asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(word), "l"(mine) : "memory");
     } else {
       unsigned long long cur = atomicAdd(word, mine) + mine;
-      for (long long t0 = clock64(); (unsigned)(cur >> 32) != (unsigned)T && clock64() - t0 < 2000000000ll;) {
+      for (long long t0 = clock64(); (unsigned)(cur >> 32) != (unsigned)T && clock64() - t0 < CHAIN_SPIN_CYCLES;) {
         __nanosleep(100);                // earlier-launched units still in flight (forward progress as in a look-back scan)
         cur = *reinterpret_cast<volatile unsigned long long*>(word);
+      }
+      if ((unsigned)(cur >> 32) != (unsigned)T) {   // reports missing after ~1 s: flag it, guess nothing (mmb.h, `scratch`)
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + p.num_envs, 1ull);
+        return;
       }
       *word = 0ull;                      // self-resetting for the next launch / graph replay
       int64_t prog = p.progress_buf[en];
@@ -238,16 +264,7 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
       p.progress_buf[en] = prog;
       p.reset_buf[en] = flag ? 1 : 0;
       if (root_env) {
-        // the executor is the frame T-1 unit: ant xy, box xy and the goal direction of the last frame are in its shared
-        // memory already (bo[0..3] was computed from the same box row with the same operations)
-#pragma unroll
-        for (int kk = 0; kk < A; ++kk) {
-          float gx, gy;
-          goal_of(kk, bo[2], bo[3], bo[0], bo[1], gx, gy);
-          *reinterpret_cast<float2*>(p.pos_before + ((int64_t)en * A + kk) * 2) = make_float2(root_env[kk * 13], root_env[kk * 13 + 1]);
-          *reinterpret_cast<float2*>(p.goal_before + ((int64_t)en * A + kk) * 2) = make_float2(gx, gy);
-        }
-        *reinterpret_cast<float2*>(p.box_before + (int64_t)en * 2) = make_float2(bo[2], bo[3]);
+        carry_from_tile(p, en, bo, root_env);
         return;
       }
       const float* last = p.root + (int64_t)(T - 1) * p.root_frame_stride;
@@ -596,9 +613,28 @@ struct SplitSmem {
   static constexpr int kRoot = EPT * ROOT_ENV;
   static constexpr int kPart = EPT * A * PART_W;
   static constexpr int kBox = EPT * BOX_W;
-  static constexpr int kFloats = kObs + kRoot + kPart + kBox + 4;
+  // fused GAE (executor units only): values [EPT][33] (T <= 32 frames + bootstrap), rewards [EPT][33] (odd stride:
+  // conflict-free), fallen bits [EPT], error flag
+  static constexpr int GAE_LD = 33;
+  static constexpr int kGae = 2 * EPT * GAE_LD + EPT + 4;
+  static constexpr int kFloats = kObs + kRoot + kPart + kBox + 4 + kGae;
   static constexpr int kBytes = kFloats * 4;
 };
+
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 #ifndef MMB_SPLIT_MIN_CTAS
 #define MMB_SPLIT_MIN_CTAS 4
@@ -614,6 +650,10 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   float* part_s = root_s + SplitSmem::kRoot;
   float* box_s = part_s + SplitSmem::kPart;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(box_s + SplitSmem::kBox);
+  constexpr int GLD = SplitSmem::GAE_LD;
+  float* vals_s = box_s + SplitSmem::kBox + 4;
+  float* rew_s = vals_s + SplitSmem::EPT * GLD;
+  unsigned* fallen_s = reinterpret_cast<unsigned*>(rew_s + SplitSmem::EPT * GLD);   // [EPT] fallen bits, [EPT] error flag
 
   const int tid = threadIdx.x;
   if (tid == 0) MMB_TR(0);
@@ -650,6 +690,21 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
 
   if (prefetch_dist > 0 && tid == NA)
     prefetch_unit<EPT>(p, (int64_t)blockIdx.y * gridDim.x + blockIdx.x + prefetch_dist, (int)gridDim.x);
+
+  // fused GAE (mmb.h, gae_*): the unit of the LAST frame is the executor of its 16 envs; it stages their T values and the
+  // bootstrap value in shared memory now (cp.async: no registers held), long before it needs them
+  const bool gae_on = p.gae_values != nullptr;
+  const bool gae_exec = gae_on && t == p.num_frames - 1;
+  if (gae_exec) {
+    const int T = p.num_frames;
+    for (int j = tid; j < (T + 1) * EPT; j += NT) {
+      const int tt = j >> 4, e2 = j & (EPT - 1);
+      if (e2 < ne)
+        cp_async4(vals_s + e2 * GLD + tt, (tt < T) ? p.gae_values + (int64_t)tt * p.gae_values_frame_stride + e0 + e2
+                                                   : p.gae_last_values + e0 + e2);
+    }
+    if (tid <= EPT) fallen_s[tid] = 0u;
+  }
 
   if (box_role) {
     // ================= box warp: goal direction of frame t (lanes 0-15) and of frame t-1 (lanes 16-31) =================
@@ -832,6 +887,7 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   }
   if (tid == 40) MMB_TR(7);
   if (tid == 200) MMB_TR(8);
+  if (gae_exec) cp_async_commit_wait_all();   // this thread's staged values have landed (visible to the CTA after B3)
   fence_async_smem();                    // obs tile writes -> visible to the TMA store engine
   __syncthreads();                       // B3
   if (tid == 0) MMB_TR(9);
@@ -854,9 +910,104 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     }
   }
   // the finish runs in the first dof warp: warp 0 has the bulk store to issue and to wait for
-  if (tid >= NA && tid - NA < ne) {
-    if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
-    finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, root_s + (tid - NA) * ROOT_ENV);
+  if (!gae_on) {
+    if (tid >= NA && tid - NA < ne) {
+      if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
+      finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, root_s + (tid - NA) * ROOT_ENV);
+      if (tid == NA) MMB_TR(10);
+    }
+  } else if (!gae_exec) {
+    // frames 0..T-2: reward + fallen bit of (env, frame) travel to the executor in ONE fire-and-forget 64-bit store
+    // (data and flag are the same word: no fence, nothing comes back, the CTA retires at once)
+    if (tid >= NA && tid - NA < ne) {
+      if (pdl) griddep_wait();             // the previous launch's executor must have consumed (zeroed) the word
+      const int en = e0 + (tid - NA);
+      bool fallen;
+      const float r = env_reward(c, part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, fallen);
+      if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = r;
+      st_relaxed_gpu_u64(reinterpret_cast<unsigned long long*>(p.gae_scratch) + (int64_t)t * N + en,
+                         (1ull << 63) | ((unsigned long long)(fallen ? 1u : 0u) << 32) | (unsigned long long)__float_as_uint(r));
+    }
+  } else if (dof_role) {
+    // executor of this tile's envs (frame T-1, launched last): the five dof warps collect the (T-1) x 16 words in one
+    // round trip, then one thread per env runs the progress / reset chain (ten_ant.py:896-901,1296-1299), the GAE
+    // recurrence (storage.py:51-62, same operations in the same order as mmb_gae_ppo) and writes the carry
+    const int T = p.num_frames;
+    const int idx = tid - NA;
+    unsigned long long* words = reinterpret_cast<unsigned long long*>(p.gae_scratch);
+    if (pdl) griddep_wait();
+    if (idx < ne) {
+      bool fallen;
+      const float r = env_reward(c, part_s + idx * A * PART_W, box_s + idx * BOX_W, fallen);
+      if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + e0 + idx] = r;
+      rew_s[idx * GLD + T - 1] = r;
+      if (fallen) atomicOr(fallen_s + idx, 1u << (T - 1));
+    }
+    for (int j = idx; j < (T - 1) * EPT; j += NA) {
+      const int tt = j >> 4, e2 = j & (EPT - 1);
+      if (e2 < ne) {
+        unsigned long long* w = words + (int64_t)tt * N + e0 + e2;
+        unsigned long long v = ld_relaxed_gpu_u64(w);
+        for (long long c0 = clock64(); !(v >> 63) && clock64() - c0 < CHAIN_SPIN_CYCLES;) {
+          __nanosleep(64);               // units launched before this one, still in flight
+          v = ld_relaxed_gpu_u64(w);
+        }
+        if (v >> 63) {
+          rew_s[e2 * GLD + tt] = __uint_as_float((unsigned)v);
+          if ((v >> 32) & 1ull) atomicOr(fallen_s + e2, 1u << tt);
+          st_relaxed_gpu_u64(w, 0ull);   // self-resetting for the next launch / graph replay
+        } else {
+          fallen_s[EPT] = 1u;            // reports missing after ~1 s: flag it, guess nothing (mmb.h, `scratch`)
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NA) : "memory");
+    if (idx < EPT) {                     // lanes 0-15 of warp 5
+      const bool bad = fallen_s[EPT] != 0u;
+      const bool on = idx < ne && !bad;
+      const int en = e0 + idx;
+      double s1 = 0.0, s2 = 0.0;
+      if (on) {
+        int64_t prog = p.progress_buf[en];
+        bool flag = p.reset_buf[en] != 0;
+        const uint32_t done_bits = chain_bits(p, en, 0, T, fallen_s[idx], prog, flag);
+        p.progress_buf[en] = prog;
+        p.reset_buf[en] = flag ? 1 : 0;
+        const float gamma = p.gae_gamma, lam = p.gae_lam;
+        float adv = 0.0f;
+        float next_v = vals_s[idx * GLD + T];
+#pragma unroll 1
+        for (int tt = T - 1; tt >= 0; --tt) {
+          const float r = rew_s[idx * GLD + tt], v = vals_s[idx * GLD + tt];
+          const float mg = fmul(fsub(1.0f, (float)((done_bits >> tt) & 1u)), gamma);   // (1 - dones.float()) * gamma
+          const float delta = fsub(fadd(r, fmul(mg, next_v)), v);
+          adv = fadd(delta, fmul(fmul(mg, lam), adv));
+          const float ret = fadd(adv, v);
+          const float a = fsub(ret, v);                                                // advantages = returns - values
+          p.gae_returns[(int64_t)tt * p.gae_returns_frame_stride + en] = ret;
+          p.gae_advantages[(int64_t)tt * p.gae_advantages_frame_stride + en] = a;
+          s1 += (double)a;
+          s2 += (double)a * (double)a;
+          next_v = v;
+        }
+        carry_from_tile(p, en, box_s + idx * BOX_W, root_s + idx * ROOT_ENV);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0x0000ffffu, s1, o);
+        s2 += __shfl_xor_sync(0x0000ffffu, s2, o);
+      }
+      if (idx == 0) {
+        if (bad) {
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + N, 1ull);
+        } else if (p.gae_stats) {        // one fire-and-forget pair per tile, spread over MMB_STAT_SLOTS lines
+          double* slot = p.gae_stats + 4 + (size_t)(blockIdx.x % MMB_STAT_SLOTS) * MMB_STAT_SLOT_STRIDE;
+          asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(slot), "d"(s1) : "memory");
+          asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(slot + 1), "d"(s2) : "memory");
+          if (blockIdx.x == 0) atomicAdd(p.gae_stats, (double)N * (double)T);
+        }
+      }
+    }
     if (tid == NA) MMB_TR(10);
   }
   extra_outputs<NT, EPT>(p, t, e0, ne, tid, obs_s, tile_clamped, clip);
@@ -945,12 +1096,20 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
   if (p.num_frames > 1 && !p.dones_u8 && !p.dones_i64) return MMB_EINVAL;  // the chain needs a [T][N] plane
   if (p.obs_layout < 0 || p.obs_layout > 2) return MMB_EINVAL;
   if (p.flavor != MMB_FLAVOR_CUDA && p.flavor != MMB_FLAVOR_CPU) return MMB_EINVAL;
+  if (p.gae_values) {  // fused GAE: horizon-batched launches whose chain is resolved in-kernel
+    if (p.num_frames < 2 || p.num_frames > 32 || !p.scratch || !p.gae_scratch || !p.gae_last_values || !p.gae_returns ||
+        !p.gae_advantages)
+      return MMB_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(p.gae_scratch) & 7u) || (p.gae_stats && (reinterpret_cast<uintptr_t>(p.gae_stats) & 7u)))
+      return MMB_EALIGN;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // tile size: 16 envs (160 threads, 6 CTAs/SM) by default; MMB_TEN_ANT_EPT=32 selects the 32-env tile (tuning knob)
   static const int ept = [] { const char* v = getenv("MMB_TEN_ANT_EPT"); return v ? ((atoi(v) == 32) ? 32 : 16) : MMB_TEN_ANT_EPT; }();
   // kernel variant: "split" (two threads per ant, default) or "mono" (one thread per ant; MMB_TEN_ANT_VARIANT=mono)
   static const bool split = [] { const char* v = getenv("MMB_TEN_ANT_VARIANT"); return !(v && v[0] == 'm'); }();
   int32_t rc;
+  if (p.gae_values && !split) return MMB_EUNSUPPORTED;   // the one-thread-per-ant variant has no fused GAE
   if (split)
     rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant_split<FLAVOR_CUDA>(p, st) : launch_ten_ant_split<FLAVOR_CPU>(p, st);
   else if (ept == 16)

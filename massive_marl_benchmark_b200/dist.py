@@ -139,7 +139,7 @@ class StatsExchange:
     `StatsExchange.local(world, slots)` builds `world` endpoints inside ONE process on one device (mailboxes are
     ordinary local allocations, no IPC) - used by the single-GPU tests of the protocol."""
 
-    def __init__(self, group=None, slots=4, device=None):
+    def __init__(self, group=None, slots=4, device=None, timeout_ms=0):
         from . import _lib as L
         import ctypes as C
         lib = L.lib()
@@ -164,6 +164,7 @@ class StatsExchange:
             self.state = torch.zeros(8, dtype=torch.int64, device=self.device)
             self.desc = L.Xchg()
             self.desc.world, self.desc.rank, self.desc.slots = self.world, self.rank, slots
+            self.desc.timeout_ms = int(timeout_ms)     # 0: library default (10 s); < 0: wait for ever (what NCCL would do)
             self.desc.state = self.state.data_ptr()
             for r in range(self.world):
                 if r == self.rank:
@@ -178,7 +179,7 @@ class StatsExchange:
             dist.barrier(group=group)      # nobody publishes before every mailbox is mapped
 
     @classmethod
-    def local(cls, world, slots=4, device="cuda"):
+    def local(cls, world, slots=4, device="cuda", timeout_ms=0):
         """`world` endpoints in this process (protocol tests): returns a list of StatsExchange-like objects."""
         from . import _lib as L
         nwords = int(L.lib().mmb_xchg_mailbox_bytes(world, slots)) // 8
@@ -191,6 +192,7 @@ class StatsExchange:
             x.state = torch.zeros(8, dtype=torch.int64, device=device)
             x.desc = L.Xchg()
             x.desc.world, x.desc.rank, x.desc.slots, x.desc.state = world, r, slots, x.state.data_ptr()
+            x.desc.timeout_ms = int(timeout_ms)
             for k in range(world):
                 x.desc.mailbox[k] = boxes[k].data_ptr()
             out.append(x)

@@ -73,8 +73,12 @@ class RolloutStorage:
         self.batch_size = T * N
         self.process_group = None
         self.stats_exchange = None
-        self._adv_stats4 = torch.zeros(4, device=dev, dtype=torch.float64)   # count, sum, sumsq + library ticket
+        # count, sum, sumsq + library ticket, then the slot area the fused GAE of the step kernel accumulates into
+        # (include/mmb.h, MMB_ADV_STATS_EXT_DOUBLES)
+        self._adv_stats4 = torch.zeros(L.ADV_STATS_EXT_DOUBLES, device=dev, dtype=torch.float64)
         self.adv_stats = self._adv_stats4[:3]
+        self._gae_words = None            # [T, N] uint64 hand-over words of the fused GAE (allocated on first use)
+        self._stats_in_slots = False      # the pending statistics sit in the slot area (fused GAE) -> MMB_NORM_SLOTS
         self._stats_out = torch.zeros(2, device=dev)
         self.shuffle_seed = 0
         self._epoch = 0
@@ -122,6 +126,7 @@ class RolloutStorage:
         self.normalize_advantages()
 
     def compute_returns_scan(self, last_values, gamma, lam):
+        self._stats_in_slots = False
         """First half of compute_returns (storage.py:51-62 + the raw `returns - values`): the reverse-time scan and
         the fp64 (count, sum, sumsq) of the raw advantages.  Split out so a caller can overlap the second half
         (statistics all-reduce + normalisation) with the next rollout on another stream."""
@@ -134,19 +139,52 @@ class RolloutStorage:
         p.returns, p.advantages, p.stats = L.ptr(self.returns), L.ptr(self.advantages), L.ptr(self._adv_stats4)
         L.check(L.lib().mmb_gae_ppo(p, L.stream_ptr()), "mmb_gae_ppo")
 
+    def fused_gae(self, last_values, gamma, lam):
+        """Arguments for `TenAnt.replay(..., gae=...)`: the step kernel then runs compute_returns_scan itself, in the unit
+        that resolves the progress / reset chain of an env (include/mmb.h, `gae_*`), so a horizon-batched rollout is ONE
+        launch + normalize_advantages.  `values` (this storage's plane) and `last_values` must be final before the
+        launch."""
+        T, N = self.num_transitions_per_env, self.num_envs
+        if self._gae_words is None:
+            self._gae_words = torch.zeros(T, N, device=self.rewards.device, dtype=torch.int64)
+        lv = last_values if last_values.is_contiguous() else last_values.contiguous()
+        self._stats_in_slots = True
+        return {"values": self.values.view(T, N), "last_values": lv, "returns": self.returns.view(T, N),
+                "advantages": self.advantages.view(T, N), "stats": self._adv_stats4, "scratch": self._gae_words,
+                "gamma": float(gamma), "lam": float(lam)}
+
     def normalize_advantages(self):
         """Second half (storage.py:65): [all-reduce of the statistics over env shards] + (adv - mean) / (std + 1e-8)."""
         T, N = self.num_transitions_per_env, self.num_envs
+        flags = L.NORM_CLEAR | (L.NORM_SLOTS if self._stats_in_slots else 0)
         if self.stats_exchange is not None:
             L.check(L.lib().mmb_adv_normalize_xchg(L.ptr(self.advantages), T * N, L.ptr(self._adv_stats4), self.stats_exchange.desc, 1e-8,
-                                                   L.stream_ptr()), "mmb_adv_normalize_xchg")
+                                                   flags, L.stream_ptr()), "mmb_adv_normalize_xchg")
+            self._xchg_pending = True
             return
         if self.process_group is not None:
             from . import dist as mdist
+            if self._stats_in_slots:   # fold the slot area into the three base words first (one tiny torch op; baseline path)
+                sl = self._adv_stats4[4:].view(L.STAT_SLOTS, L.STAT_SLOT_STRIDE)
+                self._adv_stats4[1:3] += sl[:, :2].sum(0)
+                sl.zero_()
+                flags = L.NORM_CLEAR
             mdist.all_reduce_stats(self.adv_stats, self.process_group)
         # the normalise launch clears the accumulator for the next rollout (no memset launch; graph-replay safe)
-        L.check(L.lib().mmb_adv_normalize(L.ptr(self.advantages), T * N, L.ptr(self._adv_stats4), 1e-8, 1, L.stream_ptr()),
+        L.check(L.lib().mmb_adv_normalize(L.ptr(self.advantages), T * N, L.ptr(self._adv_stats4), 1e-8, flags, L.stream_ptr()),
                 "mmb_adv_normalize")
+
+    def check_exchange(self):
+        """Raises if a peer-memory statistics exchange of this storage's endpoint timed out or was overrun (the kernel
+        then filled the advantages with NaN instead of normalising with partial moments).  One host sync; called once per
+        update from `mini_batch_generator`."""
+        if self.stats_exchange is not None and getattr(self, "_xchg_pending", False):
+            self._xchg_pending = False
+            n = self.stats_exchange.errors
+            if n:
+                raise L.MmbError("advantage-statistics exchange failed %d time(s): a peer did not publish its moments within "
+                                 "the time-out (or a mailbox slot was overrun); the advantages of that rollout are NaN. "
+                                 "Raise StatsExchange(timeout_ms=...) or fall back to process_group (NCCL all-reduce)." % n)
 
     def get_statistics(self):
         L.check(L.lib().mmb_rollout_statistics(L.ptr(self.dones), L.ptr(self.rewards), self.num_transitions_per_env,
@@ -174,6 +212,7 @@ class RolloutStorage:
         mini_batch_size = self.batch_size // num_mini_batches
         if self.sampler not in ("sequential", "random"):
             raise ValueError("unknown sampler %r" % (self.sampler,))
+        self.check_exchange()
         return _BatchIterable(self, mini_batch_size)
 
     FIELDS = ("observations", "states", "actions", "values", "returns", "actions_log_prob", "advantages", "mu", "sigma")

@@ -72,7 +72,6 @@ class BaseTask:
         self.clip_actions = INF
         self.clip_obs = INF
         self.obs_layout = 0
-        self._flip = 0
         self.reset_count = torch.zeros(1, device=dev, dtype=torch.int32)
         self.env_ids = torch.zeros(N, device=dev, dtype=torch.long)
         self.reset_noise = None          # parity mode: (positions [N,8], velocities [N,8]); None -> Philox
@@ -95,9 +94,12 @@ class BaseTask:
         if not self.actions.is_contiguous():
             self.actions = self.actions.contiguous()
 
-    def _clamped_out(self, bufs):
-        self._flip ^= 1
-        return bufs[self._flip]
+    def _fresh_out(self, *shape):
+        """Output tensor of one step, owned by the CALLER from then on: the reference returns a fresh `torch.clamp(...)`
+        tensor per step (vec_task.py:130) and its PPO.run keeps and mutates it (`current_obs = reset()`, then
+        `current_obs.copy_(next_obs)` every step, ppo.py:128-139), so the task must never write into a tensor it has
+        handed out.  The caching allocator recycles the block once the caller drops it: no copy, no kernel."""
+        return torch.empty(shape, device=self.device, dtype=torch.float)
 
 
 class TenAnt(BaseTask):
@@ -137,13 +139,11 @@ class TenAnt(BaseTask):
         self.forces = torch.zeros(N, 80, device=dev)
         self.ant_box_indices = torch.zeros(11 * N, device=dev, dtype=torch.int32)
         self.ant_indices = torch.zeros(10 * N, device=dev, dtype=torch.int32)
-        self._obs_out = [torch.zeros(N, 388, device=dev) for _ in range(2)]
-        self._obs_all_out = [torch.zeros(N, 10, 46, device=dev) for _ in range(2)]
-        self.obs_clamped = self._obs_out[0]
-        self.obs_all = self._obs_all_out[0]
+        self.obs_clamped = torch.zeros(N, 388, device=dev)
+        self.obs_all = torch.zeros(N, 10, 46, device=dev)
         self.keep_raw_obs = True
         self.actions = torch.zeros(N, 80, device=dev)
-        self._chain_words = torch.zeros(N, device=dev, dtype=torch.int64)   # replay(): per-env flag/count words
+        self._chain_words = torch.zeros(N + 1, device=dev, dtype=torch.int64)   # replay(): per-env flag/count words + error count
         self._p_reset = None
         self._p_step = None
         # reset_idx at the first step reloads the carry from the not-yet-refreshed root tensor
@@ -175,9 +175,22 @@ class TenAnt(BaseTask):
         self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
         self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
 
+    def chain_errors(self) -> int:
+        """Horizon-batched launches whose in-kernel progress / reset chain gave up waiting for a frame's report (~1 s:
+        preemption, a debugger); the affected envs' flags, carry and returns were left untouched.  Host sync."""
+        return int(self._chain_words[self.num_envs].item())
+
     def _launch(self, root, dof, actions, T, strides, obs_raw, obs, share_obs, rewards, dones_i64, dones_u8, forces,
-                out_strides, overlap_prev=False, obs_layout=None, obs_agent_stride=0):
+                out_strides, overlap_prev=False, obs_layout=None, obs_agent_stride=0, gae=None):
         p = L.TenAntParams()
+        if gae is not None:
+            v, r, a = gae["values"], gae["returns"], gae["advantages"]
+            p.gae_values, p.gae_values_frame_stride = L.ptr(v), v.stride(0)
+            p.gae_last_values = L.ptr(gae["last_values"])
+            p.gae_returns, p.gae_returns_frame_stride = L.ptr(r), r.stride(0)
+            p.gae_advantages, p.gae_advantages_frame_stride = L.ptr(a), a.stride(0)
+            p.gae_stats, p.gae_scratch = L.ptr(gae["stats"]), L.ptr(gae["scratch"])
+            p.gae_gamma, p.gae_lam = gae["gamma"], gae["lam"]
         p.overlap_prev = 1 if overlap_prev else 0
         p.obs_agent_stride = obs_agent_stride
         p.num_envs, p.num_frames, p.flavor = self.num_envs, T, self.flavor
@@ -202,11 +215,11 @@ class TenAnt(BaseTask):
         fr = self.provider.frame()
         self.root_states, self.dof_state = fr["root"], fr["dof"]
         if self.obs_layout == 0:
-            obs = self.obs_clamped = self._clamped_out(self._obs_out)
+            obs = self.obs_clamped = self._fresh_out(self.num_envs, 388)
             share = None
         else:
-            obs = self.obs_all = self._clamped_out(self._obs_all_out)
-            share = self.obs_clamped = self._obs_out[self._flip]
+            obs = self.obs_all = self._fresh_out(self.num_envs, 10, 46)
+            share = self.obs_clamped = self._fresh_out(self.num_envs, 388)
         p = self._p_step
         if p is None:   # built once: the per-step call only refreshes the pointers that move
             p = self._p_step = L.TenAntParams()
@@ -232,8 +245,11 @@ class TenAnt(BaseTask):
 
     # -- horizon-batched replay (B200-native addition, SURVEY.md section 7 hard part 1) ---------
     def replay(self, frames, actions, obs_out, rewards_out, dones_u8_out=None, dones_i64_out=None, forces_out=None,
-               share_obs_out=None, obs_raw_out=None, overlap_prev=False, agent_major_obs_out=None):
+               share_obs_out=None, obs_raw_out=None, overlap_prev=False, agent_major_obs_out=None, gae=None):
         """Process T consecutive frames in ONE launch (+ the 1-byte/env-step progress chain).
+
+        gae = `RolloutStorage.fused_gae(last_values, gamma, lam)`: the same launch also runs the storage's
+        compute_returns scan (returns, raw advantages, their statistics) - follow it with `normalize_advantages()`.
 
         frames: dict root [T,11N,13], dof [T,80N,2]; actions [T,N,80]; outputs are [T, ...] planes, e.g.
         slices of a rollout storage so that obs / reward / done land in their slots without a copy pass.
@@ -261,7 +277,7 @@ class TenAnt(BaseTask):
         self._launch(root, dof, actions, T, (root.stride(0), dof.stride(0), actions.stride(0)),
                      obs_raw_out, obs_out, share_obs_out, rewards_out, dones_i64_out, dones_u8_out, forces_out,
                      (s(obs_raw_out), s(obs_out), s(share_obs_out), s(rewards_out), s(dones_i64_out), s(dones_u8_out),
-                      s(forces_out)), overlap_prev=overlap_prev, obs_layout=layout, obs_agent_stride=agent_stride)
+                      s(forces_out)), overlap_prev=overlap_prev, obs_layout=layout, obs_agent_stride=agent_stride, gae=gae)
         self.root_states, self.dof_state = root[T - 1], dof[T - 1]
         self._step_count += T
 
@@ -310,8 +326,7 @@ class OneAnt(BaseTask):
         self.forces = torch.zeros(N, 8, device=dev)
         self.ant_box_indices = torch.zeros(2 * N, device=dev, dtype=torch.int32)
         self.ant_indices = torch.zeros(N, device=dev, dtype=torch.int32)
-        self._obs_out = [torch.zeros(N, 60, device=dev) for _ in range(2)]
-        self.obs_clamped = self._obs_out[0]
+        self.obs_clamped = torch.zeros(N, 60, device=dev)
         self.keep_raw_obs = True
         self.actions = torch.zeros(N, 8, device=dev)
 
@@ -361,7 +376,7 @@ class OneAnt(BaseTask):
         fr = self.provider.frame()
         self.root_states, self.dof_state = fr["root"], fr["dof"]
         self.vec_sensor_tensor = fr["sensor"].view(self.num_envs, 24)
-        obs = self.obs_clamped = self._clamped_out(self._obs_out)
+        obs = self.obs_clamped = self._fresh_out(self.num_envs, 60)
         self._launch(self.root_states, self.dof_state, self.vec_sensor_tensor, self.actions, 1, (0, 0, 0, 0),
                      self.obs_buf if self.keep_raw_obs else None, obs, self.rew_buf, None, None, self.forces,
                      (0, 0, 0, 0, 0, 0))
@@ -409,8 +424,7 @@ class MultiIngenuity(BaseTask):
         self.forces = torch.zeros(N, 24, 3, device=dev)            # task.forces (post-step state)
         self.forces_applied = torch.zeros(N, 24, 3, device=dev)    # tensor handed to apply_rigid_body_force_tensors
         self.actor_indices = torch.zeros(4 * N, device=dev, dtype=torch.int32)
-        self._obs_out = [torch.zeros(N, 52, device=dev) for _ in range(2)]
-        self.obs_clamped = self._obs_out[0]
+        self.obs_clamped = torch.zeros(N, 52, device=dev)
         self.keep_raw_obs = True
         self.goals = ((4.0, 2.0, 1.0), (4.0, -2.0, 1.0), (4.0, 6.0, 1.0), (4.0, -6.0, 1.0))
         self.actions = torch.zeros(N, 24, device=dev)
@@ -452,7 +466,7 @@ class MultiIngenuity(BaseTask):
         self.reset_idx()
         fr = self.provider.frame()
         self.root_states = fr["root"]
-        obs = self.obs_clamped = self._clamped_out(self._obs_out)
+        obs = self.obs_clamped = self._fresh_out(self.num_envs, 52)
         self._launch(self.root_states, self.actions, 1, (0, 0), self.obs_buf if self.keep_raw_obs else None, obs,
                      self.rew_buf, None, None, self.forces_applied, (0, 0, 0, 0, 0, 0))
         self.provider.apply_rigid_body_force_tensors(self.forces_applied)

@@ -15,9 +15,11 @@ reference's 10x replicated copies; 15.5 KB per env-step less traffic for TenAnt)
 The multi-agent wrapper is parametric in (num_agents, per-agent width, shared tail) instead of being
 hard-coded to TenAnt (SURVEY finding 7), so MultiIngenuity passes through it as well.
 
-Aliasing: returned observation tensors are owned by the task and ping-pong between two buffers, i.e. a
-returned tensor stays valid until the second-next step (the reference allocates a fresh tensor per
-step; `current_obs.copy_(next_obs)` in ppo.py:138 works unchanged).
+Ownership: every tensor `step` / `reset` returns for the observations is a fresh allocation the task never
+writes again (the step kernel writes the clamped observation straight into it), exactly like the reference's
+`torch.clamp(...)` result: the reference's PPO.run keeps the tensor `reset()` returned as `current_obs` and
+overwrites it in place every step (`current_obs.copy_(next_obs)`, ppo.py:128-139).  `rew` / `done` are the
+task's own `rew_buf` / `reset_buf`, as in the reference (vec_task.py:130 returns them without a copy).
 """
 import numpy as np
 import torch
