@@ -9,7 +9,9 @@ Covers the forward passes on the rollout path (SURVEY.md section 8a rows a18 / a
         LayerNorm(in) [Linear ELU LayerNorm] x3 Linear(512, 8|1)
 
 Weights are taken from the reference's own modules / checkpoints (`from_sequential`, `from_marl_state_dict`), cast
-once to bf16 and zero-padded to the kernel's tile multiples.  On top of the means / values: `gaussian_act` (sampling and
+to bf16 and zero-padded to the kernel's tile multiples, and kept in step with the live parameters: every forward compares
+the source tensors' version counters with those of the last cast and re-casts in place after an `optimizer.step()` /
+`load_state_dict` (`refresh_from` re-binds to another module / state dict of the same architecture).  On top of the means / values: `gaussian_act` (sampling and
 log-probs in one launch, incl. PPO's sigma^2 scale_tril quirk, module.py:76-77), `PPOActorCriticForward` (actor and critic
 as one grouped launch per layer), `GroupedMLP` / `MarlTeamForward` (all agents' networks in one launch per layer).
 Numerics: bf16 operands, fp32 accumulation and fp32 bias / ELU / LayerNorm; the reference is fp32 SGEMM, so
@@ -26,14 +28,30 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def _ln_parts(ln):
+    """(weight, bias, eps) of a LayerNorm given as an nn.LayerNorm or as that tuple (live tensors, not copies)."""
+    if ln is None:
+        return None
+    if isinstance(ln, (tuple, list)):
+        return ln[0], ln[1], float(ln[2])
+    return ln.weight, ln.bias, float(ln.eps)
+
+
 class _Layer:
-    def __init__(self, weight, bias, act: bool, ln=None, device="cuda"):
-        N, K = weight.shape
-        self.N, self.K = N, K
+    """One Linear [+ELU [+LayerNorm]]: the kernel-side copies (bf16 weight zero-padded to the tile multiples, fp32 bias /
+    gamma / beta) and the LIVE source tensors they were cast from.  `stale()` compares the sources' version counters
+    with those seen at the last cast (an in-place optimizer step or load_state_dict bumps them); `refresh()` re-casts in
+    place into the existing buffers, so cached activation buffers / CUDA graphs built on them stay valid.
+    `n_out` > weight.shape[0] zero-pads the output width (the critic's 1-wide head run next to the actor's)."""
+
+    def __init__(self, weight, bias, act: bool, ln=None, device="cuda", n_out=None):
+        n_src, K = weight.shape
+        N = n_src if n_out is None else int(n_out)
+        self.N, self.K, self.n_src = N, K, n_src
         self.Kpad = _round_up(K, 64)
         self.act = act
-        self.ln = ln
-        if ln is not None:                       # bias + ELU + LayerNorm over the whole row: one CTA owns full rows
+        self.ln = _ln_parts(ln)
+        if self.ln is not None:                  # bias + ELU + LayerNorm over the whole row: one CTA owns full rows
             if N not in (32, 64, 96, 128, 160, 192, 224, 256, 512):
                 raise L.MmbError("LayerNorm epilogue needs N <= 256 (multiple of 32) or N == 512, got %d" % N)
             self.n_tile, self.Npad, self.epilogue = N, N, 2
@@ -41,14 +59,37 @@ class _Layer:
             self.Npad = _round_up(N, 256) if N >= 256 else _round_up(N, 32)
             self.n_tile = None
             self.epilogue = 1 if act else 0
-        w = torch.zeros(self.Npad, self.Kpad, dtype=torch.bfloat16, device=device)
-        w[:N, :K] = weight.detach().to(device=device, dtype=torch.bfloat16)
-        self.w = w
-        self.bias = bias.detach().to(device=device, dtype=torch.float32).contiguous()
-        if ln is not None:
-            self.gamma = ln.weight.detach().to(device=device, dtype=torch.float32).contiguous()
-            self.beta = ln.bias.detach().to(device=device, dtype=torch.float32).contiguous()
-            self.eps = float(ln.eps)
+        self.w = torch.zeros(self.Npad, self.Kpad, dtype=torch.bfloat16, device=device)
+        self.bias = torch.zeros(N, dtype=torch.float32, device=device)
+        if self.ln is not None:
+            self.gamma = torch.zeros(N, dtype=torch.float32, device=device)
+            self.beta = torch.zeros(N, dtype=torch.float32, device=device)
+            self.eps = self.ln[2]
+        self._src, self._ver = None, None
+        self.refresh(weight, bias, ln)
+
+    def _sources(self):
+        return [t for t in (self._src[0], self._src[1]) + ((self.ln[0], self.ln[1]) if self.ln is not None else ())]
+
+    def stale(self):
+        return tuple(t._version for t in self._sources()) != self._ver
+
+    @torch.no_grad()
+    def refresh(self, weight=None, bias=None, ln=None):
+        """Re-cast from the (given or remembered) source tensors into the existing kernel-side buffers."""
+        if weight is not None:
+            if tuple(weight.shape) != (self.n_src, self.K):
+                raise L.MmbError("refresh: weight shape %r does not match the layer (%d, %d)" % (tuple(weight.shape), self.n_src, self.K))
+            self._src = (weight, bias)
+            if self.ln is not None and ln is not None:
+                self.ln = _ln_parts(ln)
+        w, b = self._src
+        self.w[:self.n_src, :self.K].copy_(w.detach(), non_blocking=True)       # fp32 -> bf16 in the copy kernel
+        self.bias[:self.n_src].copy_(b.detach(), non_blocking=True)
+        if self.ln is not None:
+            self.gamma.copy_(self.ln[0].detach(), non_blocking=True)
+            self.beta.copy_(self.ln[1].detach(), non_blocking=True)
+        self._ver = tuple(t._version for t in self._sources())
 
 
 class FusedMLP:
@@ -60,12 +101,54 @@ class FusedMLP:
         self.device = torch.device(device)
         self.in_dim = layers[0].K
         self.out_dim = layers[-1].N
-        self.in_ln = in_ln
-        if in_ln is not None:
-            self.in_gamma = in_ln.weight.detach().to(device=device, dtype=torch.float32).contiguous()
-            self.in_beta = in_ln.bias.detach().to(device=device, dtype=torch.float32).contiguous()
-            self.in_eps = float(in_ln.eps)
+        self.in_ln = _ln_parts(in_ln)
+        if self.in_ln is not None:
+            self.in_gamma = torch.zeros(self.in_dim, dtype=torch.float32, device=device)
+            self.in_beta = torch.zeros(self.in_dim, dtype=torch.float32, device=device)
+            self.in_eps = self.in_ln[2]
+        self._in_ver = None
         self._bufs = {}
+        self.auto_refresh = True      # forward() re-casts the weights when their source tensors have changed
+        self._refresh_in_ln()
+
+    # -- keeping the kernel-side copies in step with the live parameters ----------------------------------
+    @torch.no_grad()
+    def _refresh_in_ln(self):
+        if self.in_ln is not None:
+            self.in_gamma.copy_(self.in_ln[0].detach(), non_blocking=True)
+            self.in_beta.copy_(self.in_ln[1].detach(), non_blocking=True)
+            self._in_ver = (self.in_ln[0]._version, self.in_ln[1]._version)
+
+    def stale(self):
+        """True when a source parameter was modified in place since the last cast (optimizer.step(), load_state_dict)."""
+        if self.in_ln is not None and (self.in_ln[0]._version, self.in_ln[1]._version) != self._in_ver:
+            return True
+        return any(l.stale() for l in self.layers)
+
+    def refresh(self):
+        """Re-cast every layer from its source tensors, in place (buffers, pointers and captured graphs stay valid)."""
+        self._refresh_in_ln()
+        for l in self.layers:
+            l.refresh()
+
+    def refresh_from_sequential(self, seq):
+        """Re-bind to (and re-cast from) another nn.Sequential of the same architecture, e.g. after the module object was
+        replaced; in place."""
+        lins = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        if len(lins) != len(self.layers):
+            raise L.MmbError("refresh_from_sequential: %d Linear layers, expected %d" % (len(lins), len(self.layers)))
+        for l, lin in zip(self.layers, lins):
+            l.refresh(lin.weight, lin.bias)
+
+    def refresh_from_marl_state_dict(self, sd, head="act.action_out.fc_mean"):
+        """Re-bind to (and re-cast from) another Actor / Critic state dict of the same architecture; in place."""
+        if self.in_ln is not None:
+            self.in_ln = (sd["base.feature_norm.weight"], sd["base.feature_norm.bias"], self.in_eps)
+            self._refresh_in_ln()
+        names = ["base.mlp.fc1"] + ["base.mlp.fc2.%d" % i for i in range(len(self.layers) - 2)]
+        for l, n in zip(self.layers[:-1], names):
+            l.refresh(sd[n + ".0.weight"], sd[n + ".0.bias"], (sd[n + ".2.weight"], sd[n + ".2.bias"], l.eps))
+        self.layers[-1].refresh(sd[head + ".weight"], sd[head + ".bias"])
 
     # -- constructors from the reference's modules ------------------------------------------------------
     @classmethod
@@ -89,11 +172,8 @@ class FusedMLP:
     def from_marl_state_dict(cls, sd, head="act.action_out.fc_mean", device="cuda"):
         """MARL Actor / Critic checkpoint (runner.py:319-339 format): base.feature_norm, base.mlp.fc1, base.mlp.fc2.*,
         then `head` ('act.action_out.fc_mean' for the actor mean, 'v_out' for the critic value)."""
-        def ln_of(prefix):
-            w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
-            m = torch.nn.LayerNorm(w.shape[0])
-            m.weight.data.copy_(w); m.bias.data.copy_(b)
-            return m
+        def ln_of(prefix):      # live tensors (a module's state_dict() shares storage and version counters with its parameters)
+            return sd[prefix + ".weight"], sd[prefix + ".bias"], 1e-5
         in_ln = ln_of("base.feature_norm") if "base.feature_norm.weight" in sd else None
         layers = [_Layer(sd["base.mlp.fc1.0.weight"], sd["base.mlp.fc1.0.bias"], True, ln_of("base.mlp.fc1.2"), device)]
         i = 0
@@ -130,6 +210,8 @@ class FusedMLP:
         """x fp32 [M, in_dim] on the device -> fp32 [M, out_dim]."""
         if x.device.type != "cuda":
             raise L.MmbError("FusedMLP runs on CUDA tensors only")
+        if self.auto_refresh and self.stale():
+            self.refresh()
         M = x.shape[0]
         x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
         Mpad, acts = self._buffers(M)
@@ -176,6 +258,14 @@ class GroupedMLP:
         self.mlps, self.G, self.device = list(mlps), len(mlps), a.device
         self.in_dim, self.out_dim = a.in_dim, a.out_dim
         self._bufs = {}
+        self.auto_refresh = True
+
+    def stale(self):
+        return any(m.stale() for m in self.mlps)
+
+    def refresh(self):
+        for m in self.mlps:
+            m.refresh()
 
     def _buffers(self, M):
         if M not in self._bufs:
@@ -189,6 +279,8 @@ class GroupedMLP:
 
     def forward(self, xs, out=None):
         import ctypes as C
+        if self.auto_refresh and self.stale():
+            self.refresh()
         if isinstance(xs, torch.Tensor):
             xs = [xs[g] for g in range(self.G)]
         xs = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in xs]
@@ -273,11 +365,25 @@ class PPOActorCriticForward:
                        a.layers[-1].K == c.layers[-1].K and c.layers[-1].N <= a.layers[-1].N)
         if same_hidden:
             la, lc = a.layers[-1], c.layers[-1]
-            w = torch.zeros(la.N, lc.K, device=device); w[:lc.N] = lc.w[:lc.N, :lc.K].float()
-            b = torch.zeros(la.N, device=device); b[:lc.N] = lc.bias
-            padded = FusedMLP(c.layers[:-1] + [_Layer(w, b, False, None, device)], None, device)
+            head = [m for m in actor_critic.critic if isinstance(m, torch.nn.Linear)][-1]
+            padded = FusedMLP(c.layers[:-1] + [_Layer(head.weight, head.bias, False, None, device, n_out=la.N)], None, device)
             self._pair = GroupedMLP([a, padded])
             self._value_cols = lc.N
+
+    def refresh_from(self, actor_critic=None):
+        """Re-cast the kernel-side weights from the module's CURRENT parameters, in place.  Not needed after an in-place
+        `optimizer.step()` / `load_state_dict` on the module this object was built from (every forward checks the
+        parameters' version counters and refreshes by itself); pass another `ActorCritic` of the same architecture to
+        re-bind to it (e.g. a freshly constructed module after a restart)."""
+        if actor_critic is None:
+            for m in (self.actor, self.critic) + ((self._pair.mlps[1],) if self._pair is not None else ()):
+                m.refresh()
+            return
+        self.actor.refresh_from_sequential(actor_critic.actor)
+        self.critic.refresh_from_sequential(actor_critic.critic)
+        if self._pair is not None:
+            self._pair.mlps[1].refresh_from_sequential(actor_critic.critic)
+        self.log_std = actor_critic.log_std.detach().to(self.actor.device)
 
     def _mean_value(self, observations, states):
         if self._pair is not None:
@@ -309,11 +415,33 @@ class MarlPolicyForward:
     def __init__(self, actor_sd, critic_sd, std_x_coef=1.0, std_y_coef=0.5, device="cuda"):
         self.actor = FusedMLP.from_marl_state_dict(actor_sd, "act.action_out.fc_mean", device)
         self.critic = FusedMLP.from_marl_state_dict(critic_sd, "v_out", device)
-        log_std = actor_sd["act.action_out.log_std"].detach().to(device)
-        self.std = torch.sigmoid(log_std / std_x_coef) * std_y_coef
+        self._std_coef = (std_x_coef, std_y_coef)
+        self._log_std = actor_sd["act.action_out.log_std"]       # live: the std below is recomputed when it changes
+        self._set_std()
+
+    def _set_std(self):
+        ls = self._log_std.detach().to(self.actor.device)
+        self.std = torch.sigmoid(ls / self._std_coef[0]) * self._std_coef[1]
+        self._std_ver = self._log_std._version
+
+    def refresh_from(self, actor_sd=None, critic_sd=None):
+        """As `PPOActorCriticForward.refresh_from`: in-place updates of the tensors the state dicts came from are picked up
+        automatically; pass new state dicts (same architecture) to re-bind."""
+        if actor_sd is not None:
+            self.actor.refresh_from_marl_state_dict(actor_sd, "act.action_out.fc_mean")
+            self._log_std = actor_sd["act.action_out.log_std"]
+        else:
+            self.actor.refresh()
+        if critic_sd is not None:
+            self.critic.refresh_from_marl_state_dict(critic_sd, "v_out")
+        else:
+            self.critic.refresh()
+        self._set_std()
 
     @torch.no_grad()
     def get_actions(self, share_obs, obs, deterministic=False, noise=None):
+        if self._log_std._version != self._std_ver:
+            self._set_std()
         mean = self.actor(obs)
         self._calls = getattr(self, "_calls", 0) + 1
         actions, logp = gaussian_act(mean, self.std, seed=getattr(self, "seed", 0), step=self._calls, noise=noise,
@@ -334,9 +462,31 @@ class MarlTeamForward:
     def __init__(self, actor_sds, critic_sds, std_x_coef=1.0, std_y_coef=0.5, device="cuda"):
         self.actors = GroupedMLP([FusedMLP.from_marl_state_dict(sd, "act.action_out.fc_mean", device) for sd in actor_sds])
         self.critics = GroupedMLP([FusedMLP.from_marl_state_dict(sd, "v_out", device) for sd in critic_sds])
-        log_std = torch.stack([sd["act.action_out.log_std"].detach().to(device) for sd in actor_sds])      # [A, act]
-        self.std = (torch.sigmoid(log_std / std_x_coef) * std_y_coef).unsqueeze(1)                           # [A, 1, act]
+        self._std_coef = (std_x_coef, std_y_coef)
+        self._log_stds = [sd["act.action_out.log_std"] for sd in actor_sds]                                  # live
         self.A = len(actor_sds)
+        self._set_std()
+
+    def _set_std(self):
+        log_std = torch.stack([t.detach().to(self.actors.device) for t in self._log_stds])                  # [A, act]
+        self.std = (torch.sigmoid(log_std / self._std_coef[0]) * self._std_coef[1]).unsqueeze(1)             # [A, 1, act]
+        self._std_ver = tuple(t._version for t in self._log_stds)
+
+    def refresh_from(self, actor_sds=None, critic_sds=None):
+        """In-place updates of the source tensors are picked up automatically at the next forward; pass new lists of state
+        dicts (same architectures) to re-bind."""
+        if actor_sds is not None:
+            for m, sd in zip(self.actors.mlps, actor_sds):
+                m.refresh_from_marl_state_dict(sd, "act.action_out.fc_mean")
+            self._log_stds = [sd["act.action_out.log_std"] for sd in actor_sds]
+        else:
+            self.actors.refresh()
+        if critic_sds is not None:
+            for m, sd in zip(self.critics.mlps, critic_sds):
+                m.refresh_from_marl_state_dict(sd, "v_out")
+        else:
+            self.critics.refresh()
+        self._set_std()
 
     def _agent_major(self, x, width):
         if x.dim() == 2:                                  # one shared row per env: the same input for every critic
@@ -347,6 +497,8 @@ class MarlTeamForward:
 
     @torch.no_grad()
     def get_actions(self, share_obs, obs, deterministic=False):
+        if tuple(t._version for t in self._log_stds) != self._std_ver:
+            self._set_std()
         mean = self.actors(self._agent_major(obs, self.actors.in_dim))
         actions = mean if deterministic else mean + torch.randn_like(mean) * self.std
         logp = -((actions - mean) ** 2) / (2 * self.std * self.std) - self.std.log() - 0.9189385332046727

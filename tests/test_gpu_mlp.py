@@ -275,3 +275,59 @@ def test_large_batch_takes_persistent_kernel_and_matches_row_blocks(cuda_device)
     assert torch.equal(y, y2) and torch.equal(y, blocks)
     with torch.no_grad():
         assert _rowmax_err(y, net(x)) <= 3e-2
+
+
+def test_forward_follows_the_parameters_across_optimizer_steps(cuda_device):
+    """The rollout forward must act with the CURRENT policy: after `optimizer.step()` (in-place parameter update) the
+    kernel-side bf16 copies are re-cast automatically (version counters), in place (same buffers); `refresh_from` re-binds
+    to another module of the same architecture.  PPO pair (actor + zero-padded critic head) and a MARL state dict."""
+    from massive_marl_benchmark_b200.mlp import MarlPolicyForward, PPOActorCriticForward
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(0)
+
+    class AC(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.asymmetric = False
+            self.actor = _ppo_net(60, [256, 128], 8, 0.5, gen)
+            self.critic = _ppo_net(60, [256, 128], 1, 1.0, gen)
+            self.log_std = torch.nn.Parameter(torch.log(torch.tensor(0.8)) * torch.ones(8))
+
+    ac = AC().to(dev)
+    fwd = PPOActorCriticForward(ac, dev)
+    obs = torch.randn(300, 60, device=dev)
+    ptr_before = fwd.actor.layers[0].w.data_ptr()
+    _, _, v0, m0, _ = fwd.act(obs, None)
+    opt = torch.optim.Adam(ac.parameters(), lr=5e-2)
+    for _ in range(3):
+        opt.zero_grad()
+        (ac.actor(obs).pow(2).mean() + ac.critic(obs).pow(2).mean() + ac.log_std.sum()).backward()
+        opt.step()
+    _, _, v1, m1, ls1 = fwd.act(obs, None)
+    with torch.no_grad():
+        assert _rowmax_err(m1, ac.actor(obs)) <= 3e-2 and _rowmax_err(v1, ac.critic(obs)) <= 3e-2
+        assert _rowmax_err(m0, ac.actor(obs)) > 0.1, "the optimizer steps were meant to move the policy visibly"
+        assert torch.equal(ls1[0], ac.log_std.detach())
+    assert fwd.actor.layers[0].w.data_ptr() == ptr_before, "refresh must be in place"
+    assert torch.equal(m1, fwd.actor(obs)) and torch.equal(v1, fwd.critic(obs))
+    ac2 = AC().to(dev)                                   # another module object of the same architecture
+    fwd.refresh_from(ac2)
+    _, _, v2, m2, _ = fwd.act(obs, None)
+    with torch.no_grad():
+        assert _rowmax_err(m2, ac2.actor(obs)) <= 3e-2 and _rowmax_err(v2, ac2.critic(obs)) <= 3e-2
+    # MARL: state dicts of live modules share storage and version counters with the parameters
+    g = load_golden("mlp_marl_actor0")
+    sd = {k[2:].replace("__", "."): torch.nn.Parameter(v.to(dev)) if v.dtype.is_floating_point else v for k, v in g.items() if k.startswith("w_")}
+    critic_sd = {k: v for k, v in sd.items() if k.startswith("base.mlp")}
+    critic_sd.update({"base.feature_norm.weight": torch.ones(388, device=dev), "base.feature_norm.bias": torch.zeros(388, device=dev),
+                      "base.mlp.fc1.0.weight": torch.randn(512, 388, device=dev) * 0.05, "v_out.weight": torch.randn(1, 512, device=dev) * 0.05,
+                      "v_out.bias": torch.zeros(1, device=dev)})
+    pol = MarlPolicyForward(sd, critic_sd, device=dev)
+    o = g["x"].to(dev); share = torch.randn(o.shape[0], 388, device=dev)
+    _, a0, _ = pol.get_actions(share, o, deterministic=True)
+    with torch.no_grad():
+        sd["act.action_out.fc_mean.bias"].add_(0.25)         # what an optimizer step does
+        sd["act.action_out.log_std"].add_(0.5)
+    _, a1, _ = pol.get_actions(share, o, deterministic=True)
+    assert torch.allclose(a1, a0 + 0.25, atol=1e-6)
+    assert torch.allclose(pol.std, torch.sigmoid(sd["act.action_out.log_std"].detach()) * 0.5)
