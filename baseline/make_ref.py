@@ -48,6 +48,10 @@ def make(reference="/root/reference", quiet=True):
             raise RuntimeError("pip install of the reference failed:\n" + res.stdout + res.stderr)
         if not quiet:
             print(res.stdout[-400:])
+        # setup.py's find_packages() skips directories without an __init__.py (agents/algorithms/utils, .../marl/utils, ...),
+        # which the reference imports as namespace packages when run from its checkout: complete the tree from the source
+        shutil.copytree(os.path.join(reference, "agents"), os.path.join(DEST, "agents"), dirs_exist_ok=True,
+                        ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
         if os.path.isdir(os.path.join(reference, "cfg")):
             shutil.copytree(os.path.join(reference, "cfg"), os.path.join(DEST, "cfg"), dirs_exist_ok=True)
         for root, dirs, _ in os.walk(DEST):

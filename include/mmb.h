@@ -528,11 +528,18 @@ typedef struct {
   const void* src[MMB_MAX_GATHER_FIELDS];   /* row-major [total][row_bytes] */
   void* dst[MMB_MAX_GATHER_FIELDS];         /* [batch_size][row_bytes] */
   int32_t row_bytes[MMB_MAX_GATHER_FIELDS]; /* multiple of 4 (or 1 for byte planes) */
+  /* mode 1 only: 0 / 1 = the bijection permutes single rows (every random access moves row_bytes: a 4-byte plane costs a
+   * whole 32-byte DRAM sector per row).  2, 4, 8, 16 = grouped shuffle: the bijection permutes GROUPS of `group` consecutive
+   * rows and each group is read with its rows rotated by a hash of the group id - still a permutation of [0, total), every
+   * minibatch a random set of row groups (consecutive rows are consecutive envs of one step: independent samples), and
+   * every random access moves group * row_bytes contiguous bytes.  total, batch_start and batch_size must be multiples. */
+  int32_t group;
+  int32_t _reserved;
 } mmb_gather_params;
 MMB_API int32_t mmb_shuffle_gather(const mmb_gather_params* p, void* stream);
 /* random permutation of [0,n) on device (fast mode of mini_batch_generator 'random'): the stateless
  * bijection evaluated for every position; a permutation by construction. */
-MMB_API int32_t mmb_permutation(int64_t n, uint64_t seed, int64_t* out, void* stream);
+MMB_API int32_t mmb_permutation(int64_t n, uint64_t seed, int32_t group, int64_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Actor-critic MLP forward on tcgen05 tensor cores: one launch per layer                          */

@@ -163,7 +163,8 @@ class GatherParams(C.Structure):
     _fields_ = [
         ("num_fields", c_i32), ("index_mode", c_i32), ("total", c_i64), ("batch_start", c_i64), ("batch_size", c_i64),
         ("indices", c_vp), ("seed", c_u64), ("indices_out", c_vp),
-        ("src", c_vp * MAX_GATHER_FIELDS), ("dst", c_vp * MAX_GATHER_FIELDS), ("row_bytes", c_i32 * MAX_GATHER_FIELDS)]
+        ("src", c_vp * MAX_GATHER_FIELDS), ("dst", c_vp * MAX_GATHER_FIELDS), ("row_bytes", c_i32 * MAX_GATHER_FIELDS),
+        ("group", c_i32), ("_reserved", c_i32)]
 
 
 class MlpLayerParams(C.Structure):
@@ -202,7 +203,7 @@ SYMBOLS = {
     "mmb_gae_marl": (c_i32, [C.POINTER(GaeMarlParams), c_vp]),
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "mmb_shuffle_gather": (c_i32, [C.POINTER(GatherParams), c_vp]),
-    "mmb_permutation": (c_i32, [c_i64, c_u64, c_vp, c_vp]),
+    "mmb_permutation": (c_i32, [c_i64, c_u64, c_i32, c_vp, c_vp]),
     "mmb_mlp_layer": (c_i32, [C.POINTER(MlpLayerParams), c_vp]),
     "mmb_mlp_debug_status": (c_i32, [C.POINTER(C.c_uint32)]),
     "mmb_mlp_layer_group": (c_i32, [C.POINTER(MlpLayerParams), c_i32, c_vp]),

@@ -95,19 +95,27 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // {count, sum, sumsq} of an accumulator: the three base words, plus (MMB_NORM_SLOTS) the slot area the fused GAE of
-// mmb_ten_ant_step fills, summed in index order
+// mmb_ten_ant_step fills.  Block-wide: lane i of warp 0 reads slot i (one 16-byte load), a fixed shuffle tree adds them
+// (the same order in every block and on every rank), the result goes to all threads through shared memory.  Must be
+// called by every thread of the block.
 __device__ __forceinline__ void read_stats(const double* stats, bool slots, double& cnt, double& s1, double& s2) {
-  cnt = stats[0]; s1 = stats[1]; s2 = stats[2];
-  if (slots) {
-    double a[MMB_STAT_SLOTS], b[MMB_STAT_SLOTS];
+  __shared__ double sh[3];
+  if (threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    if (slots) {
+      static_assert(MMB_STAT_SLOTS == 32, "one slot per lane");
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(stats + 4 + threadIdx.x * MMB_STAT_SLOT_STRIDE));
+      a = v.x; b = v.y;
 #pragma unroll
-    for (int i = 0; i < MMB_STAT_SLOTS; ++i) {
-      a[i] = __ldcg(stats + 4 + i * MMB_STAT_SLOT_STRIDE);
-      b[i] = __ldcg(stats + 4 + i * MMB_STAT_SLOT_STRIDE + 1);
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
     }
-#pragma unroll
-    for (int i = 0; i < MMB_STAT_SLOTS; ++i) { s1 += a[i]; s2 += b[i]; }
+    if (threadIdx.x == 0) { sh[0] = __ldcg(stats); sh[1] = __ldcg(stats + 1) + a; sh[2] = __ldcg(stats + 2) + b; }
   }
+  __syncthreads();
+  cnt = sh[0]; s1 = sh[1]; s2 = sh[2];
 }
 __device__ __forceinline__ void clear_stats_words(double* stats, bool slots) {
   stats[0] = 0.0; stats[1] = 0.0; stats[2] = 0.0;
@@ -193,9 +201,9 @@ __global__ void __launch_bounds__(256) adv_normalize_xchg_kernel(float* __restri
   const size_t slot = (size_t)(q % (unsigned)x.slots) * x.world;
   if (threadIdx.x == 0) s_bad = 0;
   if (blockIdx.x == 0) {
+    double cd, ad, bd;
+    read_stats(stats, slots_on != 0, cd, ad, bd);
     if ((int)threadIdx.x < x.world) {
-      double cd, ad, bd;
-      read_stats(stats, slots_on != 0, cd, ad, bd);
       unsigned long long* box = x.mailbox[threadIdx.x] + (slot + x.rank) * 4;
       st_relaxed_sys(box + 0, (unsigned long long)__double_as_longlong(cd));
       st_relaxed_sys(box + 1, (unsigned long long)__double_as_longlong(ad));

@@ -936,6 +936,24 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     const int idx = tid - NA;
     unsigned long long* words = reinterpret_cast<unsigned long long*>(p.gae_scratch);
     if (pdl) griddep_wait();
+    // Everything that needs a trip to L2 is requested FIRST and consumed later, so the executor's critical path is one round
+    // trip, not four: the env's progress / reset state (written by the previous launch, complete after the wait above) and
+    // this thread's (at most two, T <= 32) hand-over words.
+    int64_t prog = 0;
+    bool flag = false;
+    if (idx < ne) {
+      prog = __ldcg(p.progress_buf + e0 + idx);
+      flag = __ldcg(p.reset_buf + e0 + idx) != 0;
+    }
+    const int nwords = (T - 1) * EPT;
+    const int j0 = idx, j1 = idx + NA, j2 = idx + 2 * NA;     // three words per thread cover T <= 31
+    const bool on0 = j0 < nwords && (j0 & (EPT - 1)) < ne, on1 = j1 < nwords && (j1 & (EPT - 1)) < ne,
+               on2 = j2 < nwords && (j2 & (EPT - 1)) < ne;
+    unsigned long long* w0 = words + (int64_t)(j0 >> 4) * N + e0 + (j0 & (EPT - 1));
+    unsigned long long* w1 = words + (int64_t)(j1 >> 4) * N + e0 + (j1 & (EPT - 1));
+    unsigned long long* w2 = words + (int64_t)(j2 >> 4) * N + e0 + (j2 & (EPT - 1));
+    unsigned long long v0 = on0 ? ld_relaxed_gpu_u64(w0) : 0ull, v1 = on1 ? ld_relaxed_gpu_u64(w1) : 0ull,
+                       v2 = on2 ? ld_relaxed_gpu_u64(w2) : 0ull;
     if (idx < ne) {
       bool fallen;
       const float r = env_reward(c, part_s + idx * A * PART_W, box_s + idx * BOX_W, fallen);
@@ -943,22 +961,27 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       rew_s[idx * GLD + T - 1] = r;
       if (fallen) atomicOr(fallen_s + idx, 1u << (T - 1));
     }
-    for (int j = idx; j < (T - 1) * EPT; j += NA) {
-      const int tt = j >> 4, e2 = j & (EPT - 1);
-      if (e2 < ne) {
-        unsigned long long* w = words + (int64_t)tt * N + e0 + e2;
-        unsigned long long v = ld_relaxed_gpu_u64(w);
-        for (long long c0 = clock64(); !(v >> 63) && clock64() - c0 < CHAIN_SPIN_CYCLES;) {
-          __nanosleep(64);               // units launched before this one, still in flight
-          v = ld_relaxed_gpu_u64(w);
-        }
-        if (v >> 63) {
-          rew_s[e2 * GLD + tt] = __uint_as_float((unsigned)v);
-          if ((v >> 32) & 1ull) atomicOr(fallen_s + e2, 1u << tt);
-          st_relaxed_gpu_u64(w, 0ull);   // self-resetting for the next launch / graph replay
-        } else {
-          fallen_s[EPT] = 1u;            // reports missing after ~1 s: flag it, guess nothing (mmb.h, `scratch`)
-        }
+    auto take = [&](bool on, int j, unsigned long long* w, unsigned long long v) {
+      if (!on) return;
+      for (long long c0 = clock64(); !(v >> 63) && clock64() - c0 < CHAIN_SPIN_CYCLES;) {
+        __nanosleep(64);                 // a unit launched before this one is still in flight
+        v = ld_relaxed_gpu_u64(w);
+      }
+      if (v >> 63) {
+        rew_s[(j & (EPT - 1)) * GLD + (j >> 4)] = __uint_as_float((unsigned)v);
+        if ((v >> 32) & 1ull) atomicOr(fallen_s + (j & (EPT - 1)), 1u << (j >> 4));
+        st_relaxed_gpu_u64(w, 0ull);     // self-resetting for the next launch / graph replay
+      } else {
+        fallen_s[EPT] = 1u;              // reports missing after ~1 s: flag it, guess nothing (mmb.h, `scratch`)
+      }
+    };
+    take(on0, j0, w0, v0);
+    take(on1, j1, w1, v1);
+    take(on2, j2, w2, v2);
+    for (int j = idx + 3 * NA; j < nwords; j += NA) {          // T = 32 only: 16 more words than 3 x 160 threads
+      if ((j & (EPT - 1)) < ne) {
+        unsigned long long* w = words + (int64_t)(j >> 4) * N + e0 + (j & (EPT - 1));
+        take(true, j, w, ld_relaxed_gpu_u64(w));
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NA) : "memory");
@@ -966,10 +989,16 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       const bool bad = fallen_s[EPT] != 0u;
       const bool on = idx < ne && !bad;
       const int en = e0 + idx;
-      double s1 = 0.0, s2 = 0.0;
+      // sum and sum of squares of the raw advantages, exact to ~1e-14 without the fp64 pipe (64x slower than fp32 here; a
+      // 16-step dependent DADD chain was the longest part of the executor): compensated fp32 sums (Neumaier) of a and of
+      // the exact product a * a = p + fma(a, a, -p); converted to double once, after the loop
+      float s1 = 0.f, c1 = 0.f, s2 = 0.f, c2 = 0.f;
+      auto acc = [](float& s, float& c, float x) {
+        const float t2 = __fadd_rn(s, x);
+        c = __fadd_rn(c, (fabsf(s) >= fabsf(x)) ? __fadd_rn(__fsub_rn(s, t2), x) : __fadd_rn(__fsub_rn(x, t2), s));
+        s = t2;
+      };
       if (on) {
-        int64_t prog = p.progress_buf[en];
-        bool flag = p.reset_buf[en] != 0;
         const uint32_t done_bits = chain_bits(p, en, 0, T, fallen_s[idx], prog, flag);
         p.progress_buf[en] = prog;
         p.reset_buf[en] = flag ? 1 : 0;
@@ -986,24 +1015,27 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
           const float a = fsub(ret, v);                                                // advantages = returns - values
           p.gae_returns[(int64_t)tt * p.gae_returns_frame_stride + en] = ret;
           p.gae_advantages[(int64_t)tt * p.gae_advantages_frame_stride + en] = a;
-          s1 += (double)a;
-          s2 += (double)a * (double)a;
+          const float sq = __fmul_rn(a, a);
+          acc(s1, c1, a);
+          acc(s2, c2, sq);
+          acc(s2, c2, __fmaf_rn(a, a, -sq));
           next_v = v;
         }
         carry_from_tile(p, en, box_s + idx * BOX_W, root_s + idx * ROOT_ENV);
       }
+      double d1 = (double)s1 + (double)c1, d2 = (double)s2 + (double)c2;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0x0000ffffu, s1, o);
-        s2 += __shfl_xor_sync(0x0000ffffu, s2, o);
+        d1 += __shfl_xor_sync(0x0000ffffu, d1, o);
+        d2 += __shfl_xor_sync(0x0000ffffu, d2, o);
       }
       if (idx == 0) {
         if (bad) {
           atomicAdd(reinterpret_cast<unsigned long long*>(p.scratch) + N, 1ull);
         } else if (p.gae_stats) {        // one fire-and-forget pair per tile, spread over MMB_STAT_SLOTS lines
           double* slot = p.gae_stats + 4 + (size_t)(blockIdx.x % MMB_STAT_SLOTS) * MMB_STAT_SLOT_STRIDE;
-          asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(slot), "d"(s1) : "memory");
-          asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(slot + 1), "d"(s2) : "memory");
+          asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(slot), "d"(d1) : "memory");
+          asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(slot + 1), "d"(d2) : "memory");
           if (blockIdx.x == 0) atomicAdd(p.gae_stats, (double)N * (double)T);
         }
       }

@@ -81,6 +81,11 @@ class RolloutStorage:
         self._stats_in_slots = False      # the pending statistics sit in the slot area (fused GAE) -> MMB_NORM_SLOTS
         self._stats_out = torch.zeros(2, device=dev)
         self.shuffle_seed = 0
+        # 'random' sampler, device shuffle: 1 = the bijection permutes single transitions; 2 / 4 / 8 / 16 = grouped shuffle
+        # (include/mmb.h, mmb_gather_params.group): groups of that many consecutive envs of one step travel together, so a
+        # gathered minibatch reads whole DRAM sectors of every plane (the 4-byte planes at group 8) instead of one 32-byte
+        # sector per 4-byte value.  Every minibatch is still a random subset; the order inside it is irrelevant to the loss.
+        self.shuffle_group = 1
         self._epoch = 0
         self.permutation_override = None   # parity mode: a host-supplied permutation (e.g. torch.randperm)
         self._obs_dim = int(self.obs_slots[0, 0].numel())
@@ -205,8 +210,14 @@ class RolloutStorage:
         out = torch.empty(n, device=dev, dtype=torch.int64)
         seed = (self.shuffle_seed * 0x9E3779B97F4A7C15 + self._epoch) & 0xFFFFFFFFFFFFFFFF
         self._epoch += 1
-        L.check(L.lib().mmb_permutation(n, seed, L.ptr(out), L.stream_ptr()), "mmb_permutation")
+        L.check(L.lib().mmb_permutation(n, seed, self._group(), L.ptr(out), L.stream_ptr()), "mmb_permutation")
         return out
+
+    def _group(self):
+        g = int(self.shuffle_group)
+        if g not in (1, 2, 4, 8, 16) or self.batch_size % g:
+            raise ValueError("shuffle_group must be 1, 2, 4, 8 or 16 and divide T * N = %d (got %r)" % (self.batch_size, self.shuffle_group))
+        return g
 
     def mini_batch_generator(self, num_mini_batches):
         mini_batch_size = self.batch_size // num_mini_batches
@@ -216,6 +227,41 @@ class RolloutStorage:
         return _BatchIterable(self, mini_batch_size)
 
     FIELDS = ("observations", "states", "actions", "values", "returns", "actions_log_prob", "advantages", "mu", "sigma")
+
+    def new_epoch(self):
+        """Draws the seed of the next epoch's device permutation for `gather_epoch_minibatch` (the analogue of re-iterating
+        the BatchSampler, ppo.py:248-252)."""
+        self._epoch_seed = (self.shuffle_seed * 0x9E3779B97F4A7C15 + self._epoch) & 0xFFFFFFFFFFFFFFFF
+        self._epoch += 1
+        return self._epoch_seed
+
+    def gather_epoch_minibatch(self, k, num_mini_batches, out=None, want_indices=False):
+        """Minibatch k of the current epoch (`new_epoch()`), shuffle AND gather in one launch and without an index array:
+        position j of the epoch's permutation is computed inside the gather kernel (stateless bijection, include/mmb.h
+        index_mode 1, grouped by `shuffle_group`).  Equals `gather_minibatch(order[k*mb:(k+1)*mb])` for the `order` that
+        `mini_batch_generator` would have materialised with the same seed.  Returns the dict of `gather_minibatch` (plus
+        "indices" with want_indices)."""
+        mb = self.batch_size // num_mini_batches
+        g = self._group()
+        if mb % g:
+            raise ValueError("minibatch size %d is not a multiple of shuffle_group %d" % (mb, g))
+        fields = [f for f in self.FIELDS if getattr(self, f).numel()]
+        dev = self.rewards.device
+        if out is None:
+            out = {f: torch.empty((mb,) + tuple(getattr(self, f).shape[2:]), device=dev) for f in fields}
+        p = L.GatherParams()
+        p.num_fields, p.index_mode, p.total, p.batch_start, p.batch_size = len(fields), 1, self.batch_size, k * mb, mb
+        p.seed, p.group = self._epoch_seed, g
+        if want_indices:
+            if "indices" not in out:
+                out["indices"] = torch.empty(mb, device=dev, dtype=torch.int64)
+            p.indices_out = L.ptr(out["indices"])
+        for i, f in enumerate(fields):
+            src = getattr(self, f)
+            p.src[i], p.dst[i] = src.data_ptr(), out[f].data_ptr()
+            p.row_bytes[i] = int(src[0, 0].numel()) * src.element_size()
+        L.check(L.lib().mmb_shuffle_gather(p, L.stream_ptr()), "mmb_shuffle_gather")
+        return out
 
     def gather_minibatch(self, indices, out=None):
         """All fields of one minibatch in ONE launch (the 9 gathers of ppo.py:253-264): dict name -> [B, .]."""

@@ -82,8 +82,12 @@ from massive_marl_benchmark_b200.providers import ReplayProvider
 from massive_marl_benchmark_b200.storage import RolloutStorage
 from massive_marl_benchmark_b200.tasks import OneAnt
 from massive_marl_benchmark_b200.vec_task import VecTaskPython
+import importlib
+ns = sys.modules["agents.algorithms.rl.ppo"]            # refshim registers the package as a bare namespace (its __init__ pulls PPO in)
+ns.ActorCritic = importlib.import_module("agents.algorithms.rl.ppo.module").ActorCritic      # ppo/__init__.py:2, unchanged
+ns.RolloutStorage = RolloutStorage                      # ppo/__init__.py:1: the ONE import swapped (INTEGRATION.md section 1)
 import agents.algorithms.rl.ppo.ppo as refppo           # the reference's own, unmodified PPO
-refppo.RolloutStorage = RolloutStorage                  # INTEGRATION.md section 1: the one import swapped in ppo.py:15
+assert refppo.RolloutStorage is RolloutStorage
 
 dev = torch.device("cuda", 0)
 N, ITERS = 64, 3

@@ -97,13 +97,54 @@ def test_permutation_is_bijection(cuda_device):
     dev = cuda_device
     for n in (1, 2, 3, 17, 1000, 65536, 1_000_003):
         out = torch.empty(n, device=dev, dtype=torch.int64)
-        L.check(L.lib().mmb_permutation(n, 12345 + n, L.ptr(out), L.stream_ptr()), "perm")
+        L.check(L.lib().mmb_permutation(n, 12345 + n, 1, L.ptr(out), L.stream_ptr()), "perm")
         s = torch.sort(out).values
         assert torch.equal(s, torch.arange(n, device=dev)), n
     a = torch.empty(4096, device=dev, dtype=torch.int64); b = torch.empty_like(a)
-    L.lib().mmb_permutation(4096, 1, L.ptr(a), L.stream_ptr()); L.lib().mmb_permutation(4096, 2, L.ptr(b), L.stream_ptr())
+    L.lib().mmb_permutation(4096, 1, 1, L.ptr(a), L.stream_ptr()); L.lib().mmb_permutation(4096, 2, 1, L.ptr(b), L.stream_ptr())
     assert not torch.equal(a, b)
     assert float((a == torch.arange(4096, device=dev)).float().mean()) < 0.01
+
+
+@pytest.mark.parametrize("group", [1, 2, 4, 8, 16])
+def test_grouped_shuffle_is_a_permutation_and_matches_the_fused_gather(cuda_device, group):
+    """Grouped shuffle (mmb_gather_params.group): a bijection on [0, T*N) whose aligned groups of `group` positions hold one
+    aligned source group, rotated; the index-free fused path (`gather_epoch_minibatch`: shuffle + gather in one launch) returns
+    exactly the rows the materialised order selects, for every field width (1552 / 320 / 4-byte planes) and minibatch."""
+    from massive_marl_benchmark_b200 import _lib as L
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    dev = cuda_device
+    for n in (group * 1, group * 37, 65536, group * 62501):
+        out = torch.empty(n, device=dev, dtype=torch.int64)
+        L.check(L.lib().mmb_permutation(n, 999 + n, group, L.ptr(out), L.stream_ptr()), "perm")
+        assert torch.equal(torch.sort(out).values, torch.arange(n, device=dev)), n
+        grp = out.view(-1, group)
+        assert torch.equal(grp // group, (grp[:, :1] // group).expand_as(grp)), "positions of a group read one source group"
+        rot = (grp - grp[:, :1]) % group
+        assert torch.equal(rot, torch.arange(group, device=dev).expand_as(rot)), "rows of a group keep their cyclic order"
+    assert L.lib().mmb_permutation(group * 3 + 1, 1, group, L.ptr(out), L.stream_ptr()) == (0 if group == 1 else -1)
+    T, N = 5, 96
+    st = RolloutStorage(N, T, (388,), (0,), (80,), dev, "random")
+    for f in st.FIELDS:
+        t = getattr(st, f)
+        if t.numel():
+            t.copy_(torch.randn(t.shape, device=dev))
+    st.shuffle_group, st.shuffle_seed = group, 7
+    for n_mb in (1, 3, 5):
+        st._epoch = 3
+        order = st._epoch_order()                 # epoch 3's materialised order
+        st._epoch = 3
+        st.new_epoch()
+        mb = T * N // n_mb
+        for k in range(n_mb):
+            got = st.gather_epoch_minibatch(k, n_mb, want_indices=True)
+            idx = order[k * mb:(k + 1) * mb]
+            assert torch.equal(got["indices"], idx)
+            want = st.gather_minibatch(idx)
+            for f, v in want.items():
+                assert torch.equal(got[f], v), (f, n_mb, k)
+                src = getattr(st, f)
+                assert torch.equal(v, src.reshape(-1, *src.shape[2:])[idx]), f
 
 
 def test_separated_buffer_matches_reference_golden(cuda_device):
