@@ -60,7 +60,7 @@ MMB_API uint64_t mmb_launch_count(void);
  * duration and the number of launches of one kernel class since the previous collect, and releases the events. */
 enum { MMB_K_TEN_ANT = 0, MMB_K_TEN_ANT_CHAIN, MMB_K_TEN_ANT_CARRY, MMB_K_ONE_ANT, MMB_K_ONE_ANT_CHAIN,
        MMB_K_INGENUITY, MMB_K_INGENUITY_CHAIN, MMB_K_RESET, MMB_K_ROLLOUT_ADD, MMB_K_GAE_PPO, MMB_K_ADV_NORM,
-       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_GAUSS_ACT, MMB_K_PPO_LOSS, MMB_K_MAPPO_LOSS, MMB_K_COUNT };
+       MMB_K_STATS, MMB_K_GAE_MARL, MMB_K_MASKS, MMB_K_GATHER, MMB_K_PERM, MMB_K_MLP_LAYER, MMB_K_LN_CAST, MMB_K_ADV_NORM_XCHG, MMB_K_EPISODE_SCAN, MMB_K_EPISODE_RING, MMB_K_GAUSS_ACT, MMB_K_PPO_LOSS, MMB_K_MAPPO_LOSS, MMB_K_ADAM_NORM, MMB_K_ADAM, MMB_K_COUNT };
 MMB_API int32_t mmb_profile_enable(int32_t on);
 MMB_API int32_t mmb_profile_collect(int32_t kernel_id, double* total_ms, int64_t* count);
 
@@ -587,6 +587,38 @@ MMB_API int32_t mmb_ln_cast(const float* x, int32_t M, int32_t Mpad, int32_t K, 
 MMB_API int32_t mmb_ln_cast_group(const float* const* x, int32_t count, int32_t M, int32_t Mpad, int32_t K, int32_t Kpad,
                                   const float* const* gamma, const float* const* beta, float eps, int32_t use_ln,
                                   void* const* y_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Grouped optimiser step: clip_grad_norm_ + torch.optim.Adam for MANY networks in two launches.   */
+/* Replaces the 2 x num_agents Adam instances of the MARL policies                                  */
+/* (agents/algorithms/marl/mappo_policy.py:32-37, ippo_policy.py:39-45, happo_policy.py) and the     */
+/* per-network clip + step of mappo_trainer.py:143-170 / ippo_trainer.py / happo_trainer.py.         */
+/* All parameters / gradients / moments are slices of four flat fp32 buffers; group g = one network  */
+/* = elements [group_start[g], group_start[g+1]) (slices start at multiples of 4 elements; padding   */
+/* elements have zero gradient and stay zero).  Arithmetic: torch.optim.Adam (amsgrad off) after      */
+/* clip_grad_norm_(max_norm, 2); see csrc/adam.cu.  The host passes the per-step scalars              */
+/* (step_size = lr / (1 - beta1^step), bc2_sqrt = sqrt(1 - beta2^step)) computed in double.           */
+/* ------------------------------------------------------------------------------------------ */
+#define MMB_ADAM_MAX_GROUPS 64
+typedef struct {
+  int32_t num_groups, _pad;
+  int64_t total;                            /* elements in each flat buffer (multiple of 4) */
+  int64_t group_start[MMB_ADAM_MAX_GROUPS]; /* ascending, [0] = 0 */
+  float* params;                            /* [total], 16-byte aligned */
+  const float* grads;                       /* [total] */
+  float* exp_avg;                           /* [total] */
+  float* exp_avg_sq;                        /* [total] */
+  double* sumsq;                            /* [num_groups]: mmb_grad_sumsq_group ACCUMULATES into it (caller zeroes);
+                                               mmb_adam_group reads it for the clip coefficient */
+  float step_size[MMB_ADAM_MAX_GROUPS];     /* lr / bias_correction1 */
+  float bc2_sqrt[MMB_ADAM_MAX_GROUPS];      /* sqrt(bias_correction2) */
+  float eps[MMB_ADAM_MAX_GROUPS];
+  float weight_decay[MMB_ADAM_MAX_GROUPS];
+  float max_grad_norm[MMB_ADAM_MAX_GROUPS]; /* <= 0: no clipping for that group */
+  float one_minus_beta1, beta2, one_minus_beta2, _pad2;
+} mmb_adam_params;
+MMB_API int32_t mmb_grad_sumsq_group(const mmb_adam_params* p, void* stream);
+MMB_API int32_t mmb_adam_group(const mmb_adam_params* p, void* stream);
 
 #ifdef __cplusplus
 }

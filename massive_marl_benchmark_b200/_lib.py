@@ -167,6 +167,17 @@ class GatherParams(C.Structure):
         ("group", c_i32), ("_reserved", c_i32)]
 
 
+ADAM_MAX_GROUPS = 64
+
+
+class AdamParams(C.Structure):
+    _fields_ = [("num_groups", c_i32), ("_pad", c_i32), ("total", c_i64), ("group_start", c_i64 * ADAM_MAX_GROUPS),
+                ("params", c_vp), ("grads", c_vp), ("exp_avg", c_vp), ("exp_avg_sq", c_vp), ("sumsq", c_vp),
+                ("step_size", c_f * ADAM_MAX_GROUPS), ("bc2_sqrt", c_f * ADAM_MAX_GROUPS), ("eps", c_f * ADAM_MAX_GROUPS),
+                ("weight_decay", c_f * ADAM_MAX_GROUPS), ("max_grad_norm", c_f * ADAM_MAX_GROUPS),
+                ("one_minus_beta1", c_f), ("beta2", c_f), ("one_minus_beta2", c_f), ("_pad2", c_f)]
+
+
 class MlpLayerParams(C.Structure):
     _fields_ = [("M", c_i32), ("N", c_i32), ("K", c_i32), ("Mpad", c_i32), ("Kpad", c_i32), ("Npad", c_i32),
                 ("n_tile", c_i32), ("epilogue", c_i32), ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("ln_gamma", c_vp),
@@ -204,6 +215,8 @@ SYMBOLS = {
     "mmb_marl_masks": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "mmb_shuffle_gather": (c_i32, [C.POINTER(GatherParams), c_vp]),
     "mmb_permutation": (c_i32, [c_i64, c_u64, c_i32, c_vp, c_vp]),
+    "mmb_grad_sumsq_group": (c_i32, [C.POINTER(AdamParams), c_vp]),
+    "mmb_adam_group": (c_i32, [C.POINTER(AdamParams), c_vp]),
     "mmb_mlp_layer": (c_i32, [C.POINTER(MlpLayerParams), c_vp]),
     "mmb_mlp_debug_status": (c_i32, [C.POINTER(C.c_uint32)]),
     "mmb_mlp_layer_group": (c_i32, [C.POINTER(MlpLayerParams), c_i32, c_vp]),
@@ -254,7 +267,7 @@ def launch_count():
 
 KERNEL_IDS = ("ten_ant", "ten_ant_chain", "ten_ant_carry", "one_ant", "one_ant_chain", "ingenuity", "ingenuity_chain",
               "reset", "rollout_add", "gae_ppo", "adv_norm", "stats", "gae_marl", "masks", "gather", "perm", "mlp_layer",
-              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring", "gauss_act", "ppo_loss", "mappo_loss")
+              "ln_cast", "adv_norm_xchg", "episode_scan", "episode_ring", "gauss_act", "ppo_loss", "mappo_loss", "adam_norm", "adam")
 
 
 def profile_enable(on=True):

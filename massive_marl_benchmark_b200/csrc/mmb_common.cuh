@@ -13,7 +13,7 @@ namespace mmb {
 // kernel classes, as reported by mmb_profile_collect (keep in sync with include/mmb.h MMB_K_*)
 enum KernelId {
   K_TEN_ANT = 0, K_TEN_ANT_CHAIN, K_TEN_ANT_CARRY, K_ONE_ANT, K_ONE_ANT_CHAIN, K_INGENUITY, K_INGENUITY_CHAIN,
-  K_RESET, K_ROLLOUT_ADD, K_GAE_PPO, K_ADV_NORM, K_STATS, K_GAE_MARL, K_MASKS, K_GATHER, K_PERM, K_MLP_LAYER, K_LN_CAST, K_ADV_NORM_XCHG, K_EPISODE_SCAN, K_EPISODE_RING, K_GAUSS_ACT, K_PPO_LOSS, K_MAPPO_LOSS, K_COUNT
+  K_RESET, K_ROLLOUT_ADD, K_GAE_PPO, K_ADV_NORM, K_STATS, K_GAE_MARL, K_MASKS, K_GATHER, K_PERM, K_MLP_LAYER, K_LN_CAST, K_ADV_NORM_XCHG, K_EPISODE_SCAN, K_EPISODE_RING, K_GAUSS_ACT, K_PPO_LOSS, K_MAPPO_LOSS, K_ADAM_NORM, K_ADAM, K_COUNT
 };
 
 // Brackets one kernel launch: bumps the launch counter and, while profiling is enabled

@@ -613,20 +613,16 @@ struct SplitSmem {
   static constexpr int kRoot = EPT * ROOT_ENV;
   static constexpr int kPart = EPT * A * PART_W;
   static constexpr int kBox = EPT * BOX_W;
-  // fused GAE (executor units only): values [EPT][33] (T <= 32 frames + bootstrap), rewards [EPT][33] (odd stride:
-  // conflict-free), fallen bits [EPT], error flag
+  // fused GAE (executor units only): values [EPT][33] (T <= 32 frames + bootstrap) and rewards [EPT][33] (odd stride:
+  // conflict-free) ALIAS the per-ant partial terms, which are dead once the env rewards are in registers (any extra shared
+  // memory costs every CTA of the launch L1 capacity: +4 KB per CTA measured +4 % kernel time); the fallen bits and the
+  // error flag sit in unused words of the box rows
   static constexpr int GAE_LD = 33;
-  static constexpr int kGae = 2 * EPT * GAE_LD + EPT + 4;
-  static constexpr int kFloats = kObs + kRoot + kPart + kBox + 4 + kGae;
+  static_assert(2 * EPT * GAE_LD <= kPart, "GAE staging aliases the partial terms");
+  static constexpr int kFloats = kObs + kRoot + kPart + kBox + 4;
   static constexpr int kBytes = kFloats * 4;
 };
 
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -651,9 +647,8 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   float* box_s = part_s + SplitSmem::kPart;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(box_s + SplitSmem::kBox);
   constexpr int GLD = SplitSmem::GAE_LD;
-  float* vals_s = box_s + SplitSmem::kBox + 4;
-  float* rew_s = vals_s + SplitSmem::EPT * GLD;
-  unsigned* fallen_s = reinterpret_cast<unsigned*>(rew_s + SplitSmem::EPT * GLD);   // [EPT] fallen bits, [EPT] error flag
+  float* vals_s = part_s;                              // executor units, after the env rewards have left part_s
+  float* rew_s = part_s + SplitSmem::EPT * GLD;
 
   const int tid = threadIdx.x;
   if (tid == 0) MMB_TR(0);
@@ -691,20 +686,9 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   if (prefetch_dist > 0 && tid == NA)
     prefetch_unit<EPT>(p, (int64_t)blockIdx.y * gridDim.x + blockIdx.x + prefetch_dist, (int)gridDim.x);
 
-  // fused GAE (mmb.h, gae_*): the unit of the LAST frame is the executor of its 16 envs; it stages their T values and the
-  // bootstrap value in shared memory now (cp.async: no registers held), long before it needs them
+  // fused GAE (mmb.h, gae_*): the unit of the LAST frame is the executor of its 16 envs
   const bool gae_on = p.gae_values != nullptr;
   const bool gae_exec = gae_on && t == p.num_frames - 1;
-  if (gae_exec) {
-    const int T = p.num_frames;
-    for (int j = tid; j < (T + 1) * EPT; j += NT) {
-      const int tt = j >> 4, e2 = j & (EPT - 1);
-      if (e2 < ne)
-        cp_async4(vals_s + e2 * GLD + tt, (tt < T) ? p.gae_values + (int64_t)tt * p.gae_values_frame_stride + e0 + e2
-                                                   : p.gae_last_values + e0 + e2);
-    }
-    if (tid <= EPT) fallen_s[tid] = 0u;
-  }
 
   if (box_role) {
     // ================= box warp: goal direction of frame t (lanes 0-15) and of frame t-1 (lanes 16-31) =================
@@ -887,7 +871,6 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   }
   if (tid == 40) MMB_TR(7);
   if (tid == 200) MMB_TR(8);
-  if (gae_exec) cp_async_commit_wait_all();   // this thread's staged values have landed (visible to the CTA after B3)
   fence_async_smem();                    // obs tile writes -> visible to the TMA store engine
   __syncthreads();                       // B3
   if (tid == 0) MMB_TR(9);
@@ -935,58 +918,65 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     const int T = p.num_frames;
     const int idx = tid - NA;
     unsigned long long* words = reinterpret_cast<unsigned long long*>(p.gae_scratch);
+    unsigned* fallen_w = reinterpret_cast<unsigned*>(box_s);   // env el: word el * BOX_W + 5 (unused by the box terms); error flag: word 6
     if (pdl) griddep_wait();
     // Everything that needs a trip to L2 is requested FIRST and consumed later, so the executor's critical path is one round
-    // trip, not four: the env's progress / reset state (written by the previous launch, complete after the wait above) and
-    // this thread's (at most two, T <= 32) hand-over words.
+    // trip: the env's progress / reset state (written by the previous launch, complete after the wait above), this
+    // thread's (at most three) hand-over words and (at most four) of the tile's T + 1 value rows.
     int64_t prog = 0;
     bool flag = false;
     if (idx < ne) {
       prog = __ldcg(p.progress_buf + e0 + idx);
       flag = __ldcg(p.reset_buf + e0 + idx) != 0;
     }
-    const int nwords = (T - 1) * EPT;
-    const int j0 = idx, j1 = idx + NA, j2 = idx + 2 * NA;     // three words per thread cover T <= 31
-    const bool on0 = j0 < nwords && (j0 & (EPT - 1)) < ne, on1 = j1 < nwords && (j1 & (EPT - 1)) < ne,
-               on2 = j2 < nwords && (j2 & (EPT - 1)) < ne;
-    unsigned long long* w0 = words + (int64_t)(j0 >> 4) * N + e0 + (j0 & (EPT - 1));
-    unsigned long long* w1 = words + (int64_t)(j1 >> 4) * N + e0 + (j1 & (EPT - 1));
-    unsigned long long* w2 = words + (int64_t)(j2 >> 4) * N + e0 + (j2 & (EPT - 1));
-    unsigned long long v0 = on0 ? ld_relaxed_gpu_u64(w0) : 0ull, v1 = on1 ? ld_relaxed_gpu_u64(w1) : 0ull,
-                       v2 = on2 ? ld_relaxed_gpu_u64(w2) : 0ull;
+    const int nwords = (T - 1) * EPT, nvals = (T + 1) * EPT;
+    const int j0 = idx, j1 = idx + NA, j2 = idx + 2 * NA, j3 = idx + 3 * NA;     // 3 x 160 words cover T <= 31, 4 x 160 values T <= 39
+    auto on_w = [&](int j) { return j < nwords && (j & (EPT - 1)) < ne; };
+    auto on_v = [&](int j) { return j < nvals && (j & (EPT - 1)) < ne; };
+    auto word_at = [&](int j) { return words + (int64_t)(j >> 4) * N + e0 + (j & (EPT - 1)); };
+    auto value_at = [&](int j) {
+      const int tt = j >> 4, e2 = j & (EPT - 1);
+      return (tt < T) ? p.gae_values + (int64_t)tt * p.gae_values_frame_stride + e0 + e2 : p.gae_last_values + e0 + e2;
+    };
+    unsigned long long v0 = on_w(j0) ? ld_relaxed_gpu_u64(word_at(j0)) : 0ull, v1 = on_w(j1) ? ld_relaxed_gpu_u64(word_at(j1)) : 0ull,
+                       v2 = on_w(j2) ? ld_relaxed_gpu_u64(word_at(j2)) : 0ull;
+    const float x0 = on_v(j0) ? __ldg(value_at(j0)) : 0.f, x1 = on_v(j1) ? __ldg(value_at(j1)) : 0.f,
+                x2 = on_v(j2) ? __ldg(value_at(j2)) : 0.f, x3 = on_v(j3) ? __ldg(value_at(j3)) : 0.f;
+    float r_own = 0.f;
+    bool fallen_own = false;
+    if (idx < ne) r_own = env_reward(c, part_s + idx * A * PART_W, box_s + idx * BOX_W, fallen_own);
+    if (idx < EPT) fallen_w[idx * BOX_W + 5] = fallen_own ? (1u << (T - 1)) : 0u;
+    if (idx == 0) fallen_w[6] = 0u;
+    asm volatile("bar.sync 1, %0;" ::"n"(NA) : "memory");   // the partial terms are dead: part_s becomes the GAE staging
     if (idx < ne) {
-      bool fallen;
-      const float r = env_reward(c, part_s + idx * A * PART_W, box_s + idx * BOX_W, fallen);
-      if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + e0 + idx] = r;
-      rew_s[idx * GLD + T - 1] = r;
-      if (fallen) atomicOr(fallen_s + idx, 1u << (T - 1));
+      if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + e0 + idx] = r_own;
+      rew_s[idx * GLD + T - 1] = r_own;
     }
-    auto take = [&](bool on, int j, unsigned long long* w, unsigned long long v) {
-      if (!on) return;
+    auto put_v = [&](int j, float x) { if (on_v(j)) vals_s[(j & (EPT - 1)) * GLD + (j >> 4)] = x; };
+    put_v(j0, x0); put_v(j1, x1); put_v(j2, x2); put_v(j3, x3);
+    auto take = [&](int j, unsigned long long v, bool fresh) {
+      if (!on_w(j)) return;
+      unsigned long long* w = word_at(j);
+      if (fresh) v = ld_relaxed_gpu_u64(w);
       for (long long c0 = clock64(); !(v >> 63) && clock64() - c0 < CHAIN_SPIN_CYCLES;) {
         __nanosleep(64);                 // a unit launched before this one is still in flight
         v = ld_relaxed_gpu_u64(w);
       }
       if (v >> 63) {
         rew_s[(j & (EPT - 1)) * GLD + (j >> 4)] = __uint_as_float((unsigned)v);
-        if ((v >> 32) & 1ull) atomicOr(fallen_s + (j & (EPT - 1)), 1u << (j >> 4));
+        if ((v >> 32) & 1ull) atomicOr(fallen_w + (j & (EPT - 1)) * BOX_W + 5, 1u << (j >> 4));
         st_relaxed_gpu_u64(w, 0ull);     // self-resetting for the next launch / graph replay
       } else {
-        fallen_s[EPT] = 1u;              // reports missing after ~1 s: flag it, guess nothing (mmb.h, `scratch`)
+        fallen_w[6] = 1u;                // reports missing after ~1 s: flag it, guess nothing (mmb.h, `scratch`)
       }
     };
-    take(on0, j0, w0, v0);
-    take(on1, j1, w1, v1);
-    take(on2, j2, w2, v2);
-    for (int j = idx + 3 * NA; j < nwords; j += NA) {          // T = 32 only: 16 more words than 3 x 160 threads
-      if ((j & (EPT - 1)) < ne) {
-        unsigned long long* w = words + (int64_t)(j >> 4) * N + e0 + (j & (EPT - 1));
-        take(true, j, w, ld_relaxed_gpu_u64(w));
-      }
-    }
+    take(j0, v0, false);
+    take(j1, v1, false);
+    take(j2, v2, false);
+    for (int j = j3; j < nwords; j += NA) take(j, 0ull, true);          // T = 32 only: 16 more words than 3 x 160 threads
     asm volatile("bar.sync 1, %0;" ::"n"(NA) : "memory");
     if (idx < EPT) {                     // lanes 0-15 of warp 5
-      const bool bad = fallen_s[EPT] != 0u;
+      const bool bad = fallen_w[6] != 0u;
       const bool on = idx < ne && !bad;
       const int en = e0 + idx;
       // sum and sum of squares of the raw advantages, exact to ~1e-14 without the fp64 pipe (64x slower than fp32 here; a
@@ -999,7 +989,7 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
         s = t2;
       };
       if (on) {
-        const uint32_t done_bits = chain_bits(p, en, 0, T, fallen_s[idx], prog, flag);
+        const uint32_t done_bits = chain_bits(p, en, 0, T, fallen_w[idx * BOX_W + 5], prog, flag);
         p.progress_buf[en] = prog;
         p.reset_buf[en] = flag ? 1 : 0;
         const float gamma = p.gae_gamma, lam = p.gae_lam;

@@ -101,6 +101,135 @@ def all_reduce_grads(parameters, group=None, bucket_bytes=64 << 20):
     flush()
 
 
+def _avg_op(group=None):
+    """ReduceOp.AVG where the backend has it (NCCL: the division happens inside the collective), else None (SUM + div_)."""
+    try:
+        return dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else None
+    except Exception:
+        return None
+
+
+class FlatGradReducer:
+    """Asynchronous all-reduce (average) of slices of ONE flat gradient buffer - `GroupedAdam.flat_grads` - so that the
+    collective of one network overlaps the forward / backward of the next:
+
+        red = FlatGradReducer(opt.flat_grads)
+        for agent in team:                      # per-agent loop of the update
+            loss(agent).backward(); opt.collect_grads(groups_of(agent))
+            red.reduce_async(*slice_of(agent))  # NCCL runs on its own stream, behind this agent's gradient writes only
+        red.wait()                              # before opt.step()
+
+    No flatten / unflatten copies: the slice IS the communication buffer.  `bytes_reduced` / `calls` feed the bench's bus
+    bandwidth figure.  Identity without a process group (world 1)."""
+
+    def __init__(self, flat, group=None):
+        self.flat, self.group = flat, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._works = []
+        self.bytes_reduced, self.calls = 0, 0
+
+    def reduce_async(self, lo, hi):
+        if self.world == 1 or hi <= lo:
+            return
+        view = self.flat[lo:hi]
+        avg = _avg_op(self.group)
+        work = dist.all_reduce(view, op=avg if avg is not None else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._works.append((work, view, avg is None))
+        self.bytes_reduced += view.numel() * view.element_size()
+        self.calls += 1
+
+    def wait(self):
+        for work, view, need_div in self._works:
+            work.wait()
+            if need_div:
+                view.div_(self.world)
+        self._works = []
+
+
+class OverlappedGradAllReduce:
+    """Bucketed gradient all-reduce (average) overlapped with backward, for one network trained data-parallel over env
+    shards (the PPO `ActorCritic`, 16 MB of fp32 gradients): a `post_accumulate_grad_hook` on every parameter counts the
+    bucket down; the moment the last gradient of a bucket exists the bucket is packed (one multi-tensor copy into its
+    slice of a flat buffer) and its all-reduce is issued asynchronously, while autograd keeps producing the gradients of
+    the earlier layers.  `finish()` (after `backward()`) waits for the collectives and points every `.grad` at its reduced
+    slice - no copy back.  Buckets are filled in reverse parameter order (the order backward produces gradients) and
+    sized for launch latency and overlap, not link count (NVSwitch gives every peer full bandwidth).
+    Identity without a process group."""
+
+    def __init__(self, parameters, group=None, bucket_bytes=4 << 20):
+        self.params = [p for p in parameters if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bytes_reduced, self.calls = 0, 0
+        self._handles, self._works = [], []
+        if self.world == 1 or not self.params:
+            self.buckets = []
+            return
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=dev, dtype=dtype)
+        self.buckets, cur, cur_bytes, off = [], [], 0, 0
+        for p in reversed(self.params):
+            cur.append((p, off, p.numel()))
+            off += p.numel()
+            cur_bytes += p.numel() * p.element_size()
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._pending = [len(b) for b in self.buckets]
+        for bi, b in enumerate(self.buckets):
+            for p, _, _ in b:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _make_hook(self, bi):
+        def hook(_param):
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    @torch.no_grad()
+    def _launch(self, bi):
+        b = self.buckets[bi]
+        lo, hi = b[0][1], b[-1][1] + b[-1][2]
+        views = [self.flat[o:o + n].view(p.shape) for p, o, n in b]
+        torch._foreach_copy_(views, [p.grad for p, _, _ in b])
+        avg = _avg_op(self.group)
+        work = dist.all_reduce(self.flat[lo:hi], op=avg if avg is not None else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._works.append((work, bi, views, avg is None))
+        self.bytes_reduced += (hi - lo) * self.flat.element_size()
+        self.calls += 1
+
+    @torch.no_grad()
+    def finish(self):
+        """Call after `backward()`: buckets whose hooks did not all fire (parameters without a gradient this step) are
+        flushed with zeros for the missing ones, every collective is awaited, `.grad` = the averaged slice."""
+        if self.world == 1:
+            return
+        for bi, n in enumerate(self._pending):
+            if n != 0 and n != len(self.buckets[bi]):       # partially produced bucket: reduce what exists (others: zeros)
+                for p, o, m in self.buckets[bi]:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+                self._launch(bi)
+        for work, bi, views, need_div in self._works:
+            work.wait()
+            if need_div:
+                lo, hi = self.buckets[bi][0][1], self.buckets[bi][-1][1] + self.buckets[bi][-1][2]
+                self.flat[lo:hi].div_(self.world)
+            for (p, _, _), v in zip(self.buckets[bi], views):
+                p.grad = v
+        self._works = []
+        self._pending = [len(b) for b in self.buckets]
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def mean_over_ranks(t: torch.Tensor, group=None) -> torch.Tensor:
     """Average of a (scalar) tensor over the shards - e.g. the KL estimate that drives the adaptive step size, which every
     rank must see identically.  Returns a new tensor; identity without a process group."""

@@ -49,7 +49,23 @@ def happo_ppo_update(self, sample, update_actor=True):
     return _ppo_update(self, sample, update_actor, happo=True)
 
 
-def _ppo_update(self, sample, update_actor, ippo=False, happo=False):
+def _norm_input(self, return_batch):
+    """What the value normaliser's running statistics are updated with.  Single process: the minibatch returns, as in the
+    reference.  Env-sharded data parallel (`self.moment_sync` set, e.g. `dist.mean_over_ranks`): PopArt / ValueNorm update
+    from the batch mean and mean square only (popart.py:46-57, valuenorm.py:44-55), so every rank feeds the reference's own
+    update a two-element surrogate [mu + s, mu - s] carrying the moments averaged over ALL shards - the replicas' running
+    statistics (and PopArt's output-layer rescaling) stay bit-identical without touching the reference's classes."""
+    sync = getattr(self, "moment_sync", None)
+    if sync is None:
+        return return_batch
+    m = sync(torch.stack([return_batch.mean(), (return_batch * return_batch).mean()]))
+    sd = (m[1] - m[0] * m[0]).clamp(min=0.0).sqrt()
+    return torch.stack([m[0] + sd, m[0] - sd]).reshape(2, 1)
+
+
+def evaluate_losses(self, sample, ippo=False, happo=False):
+    """Forward of one agent's actor and critic on a minibatch + the fused loss kernel: everything of `ppo_update` up to the
+    two `backward()` calls.  Returns the `MappoLossOut`."""
     (share_obs_batch, obs_batch, _rnn_a, _rnn_c, actions_batch, value_preds_batch, return_batch, _masks_batch,
      active_masks_batch, old_action_log_probs_batch, adv_targ, available_actions_batch, factor_batch) = sample
     actor, critic = self.policy.actor, self.policy.critic
@@ -67,18 +83,19 @@ def _ppo_update(self, sample, update_actor, ippo=False, happo=False):
     values = critic.v_out(critic.base(share_obs_batch))                          # actor_critic.py:163-166
 
     moments = [None, None, None, None]
+    norm_in = _norm_input(self, return_batch)
     if ippo:
         if self._use_popart or self._use_valuenorm:                              # ippo_trainer.py:74-77: one update, one pair
-            self.value_normalizer.update(return_batch)
+            self.value_normalizer.update(norm_in)
             m, v = self.value_normalizer.running_mean_var()
             moments = [m.clone(), v.clone(), None, None]
     elif getattr(self, "_use_valuenorm", False):                                 # mappo_trainer.py:75-78: the statistics are
-        self.value_normalizer.update(return_batch)                               # updated, but the errors normalised there are
+        self.value_normalizer.update(norm_in)                                    # updated, but the errors normalised there are
                                                                                  # overwritten by the else branch at :83-85
     if self._use_popart and not ippo:                                            # mappo_trainer.py:80-82: two training-mode calls,
-        self.value_normalizer(return_batch)                                      # the first normalises the clipped error,
+        self.value_normalizer(norm_in)                                           # the first normalises the clipped error,
         m1, v1 = self.value_normalizer.running_mean_var()
-        self.value_normalizer(return_batch)                                      # the second the original one
+        self.value_normalizer(norm_in)                                           # the second the original one
         m2, v2 = self.value_normalizer.running_mean_var()
         moments = [m1.clone(), v1.clone(), m2.clone(), v2.clone()]
 
@@ -96,6 +113,12 @@ def _ppo_update(self, sample, update_actor, ippo=False, happo=False):
                      use_clipped_value_loss=self._use_clipped_value_loss,
                      use_value_active_masks=self._use_value_active_masks,
                      use_policy_active_masks=self._use_policy_active_masks)
+    return out
+
+
+def _ppo_update(self, sample, update_actor, ippo=False, happo=False):
+    out = evaluate_losses(self, sample, ippo, happo)
+    actor, critic = self.policy.actor, self.policy.critic
 
     # actor update, mappo_trainer.py:143-153
     self.policy.actor_optimizer.zero_grad()

@@ -268,3 +268,113 @@ print("DROPIN_MARL_OK episodes=%d" % EPISODES)
 def test_reference_marl_runner_drives_the_dropins(cuda_device, tmp_path):
     res = subprocess.run([sys.executable, "-c", _MARL_SCRIPT, ROOT, REF, str(tmp_path)], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "DROPIN_MARL_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+_IPPO_SCRIPT = r'''
+import contextlib, io, os, sys, torch, yaml
+ROOT, REF, OUT, ALGO, FUSED = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] == "1"
+sys.path.insert(0, ROOT)
+from oracle import refshim
+refshim.install(REF)
+from massive_marl_benchmark_b200 import _lib as L, synthetic
+from massive_marl_benchmark_b200.providers import ReplayProvider
+from massive_marl_benchmark_b200.runner import Runner, process_MultiAgentRL, resolve_algorithm
+from massive_marl_benchmark_b200.tasks import TenAnt
+from massive_marl_benchmark_b200.vec_task import MultiVecTaskPython
+
+dev = torch.device("cuda", 0)
+N, EPISODES = 32, 2
+config = yaml.safe_load(open(os.path.join(REF, "cfg", ALGO, "config.yaml")))
+T = config["episode_length"]
+config.update(n_rollout_threads=N, n_eval_rollout_threads=N, num_env_steps=EPISODES * T * N, run_dir=os.path.join(OUT, "run"),
+              experiment_name="dropin", save_interval=1, log_interval=1, use_eval=False, ppo_epoch=2)
+F = 1 + EPISODES * T
+fr = synthetic.ten_ant_frames(N, F, seed=321, fall_prob=0.05)
+cfg = {"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1}
+task = TenAnt(cfg, None, None, "cuda", 0, True, True, provider=ReplayProvider({"root": fr["root"], "dof": fr["dof"]}, device=dev, loop=False),
+              flavor=L.FLAVOR_CPU)
+env = MultiVecTaskPython(task, "cuda:0")
+rec = {"actions": [], "first": None}
+task_step = task.step
+def recording_step(a):
+    rec["actions"].append(a.detach().clone().cpu())
+    return task_step(a)
+task.step = recording_step
+torch.manual_seed(0)
+class Args: algo = ALGO
+with contextlib.redirect_stdout(io.StringIO()):
+    runner = Runner(vec_env=env, config=config, model_dir="", fused_update=FUSED)
+TrainAlgo, Policy = resolve_algorithm(ALGO)
+assert all(isinstance(t, TrainAlgo) for t in runner.trainer) and all(isinstance(p, Policy) for p in runner.policy)
+compute = runner.compute
+def snapshot_compute():
+    compute()
+    if rec["first"] is None:
+        rec["first"] = [{k: getattr(b, k).detach().clone().cpu() for k in ("share_obs", "obs", "rewards", "masks", "active_masks", "actions", "returns", "value_preds")}
+                        for b in runner.buffer]
+runner.compute = snapshot_compute
+before = [p.actor.base.mlp.fc1[0].weight.detach().clone() for p in runner.policy]
+with contextlib.redirect_stdout(io.StringIO()) as log:
+    runner.run()
+torch.cuda.synchronize()
+assert len(rec["actions"]) == F
+save_dir = os.path.join(OUT, "run", "ten_ant", ALGO, "models_seed1")
+assert all(os.path.exists(os.path.join(save_dir, "%s_agent%d.pt" % (k, a))) for a in range(10) for k in ("actor", "critic"))
+for p, w0 in zip(runner.policy, before):
+    w1 = p.actor.base.mlp.fc1[0].weight
+    assert torch.isfinite(w1).all() and not torch.equal(w1, w0), "the update must have moved every agent's actor"
+
+# env side of the first episode against the reference's OWN TenAnt + MultiVecTaskPython on the recorded actions
+ref_task, gym = refshim.make_task("TenAnt", N, True)
+from agents.tasks.agent_base.multi_vec_task import MultiVecTaskPython as RefMulti
+with contextlib.redirect_stdout(io.StringIO()):
+    ref_env = RefMulti(ref_task, "cpu")
+for t in range(T + 1):
+    gym.push_frame(fr["root"][t], fr["dof"][t])
+obs, share, _ = ref_env.reset()
+first = rec["first"]
+centralized = config["use_centralized_V"]
+
+def close(a, b, what, w):
+    import math
+    d = (a.double() - b.double()).abs()
+    for k in range(a.shape[-1] // w if w == 38 else 1):
+        for c in (9, 10, 11):
+            d[..., k * w + c] = torch.minimum(d[..., k * w + c], (d[..., k * w + c] - 2 * math.pi).abs())
+    bad = d > 1e-5 * b.double().abs() + 1e-6
+    assert not bad.any(), "%s: %d / %d out of tolerance (max %g)" % (what, int(bad.sum()), bad.numel(), float(d.max()))
+
+n_done_env = 0
+for t in range(T + 1):
+    if t > 0:
+        acts = rec["actions"][t]
+        obs, share, rew, done, info, _ = ref_env.step([acts[:, 8 * a:8 * a + 8] for a in range(10)])
+        dones_env = torch.all(done, dim=1)
+        n_done_env += int(dones_env.sum())
+    for a in range(10):
+        close(first[a]["obs"][t], obs[:, a], "obs[%d] agent %d" % (t, a), 46)
+        if centralized:
+            close(first[a]["share_obs"][t], share[:, a], "share_obs[%d] agent %d" % (t, a), 38)
+        else:                                            # IPPO: the critic sees the agent's own observation (runner.py:190-191)
+            assert torch.equal(first[a]["share_obs"][t], first[a]["obs"][t])
+        if t > 0:
+            want_mask = torch.ones(N, 1); want_mask[dones_env] = 0.0
+            assert torch.equal(first[a]["masks"][t], want_mask)
+            rel = (first[a]["rewards"][t - 1] - rew[:, a]).abs() / rew[:, a].abs().clamp(min=1e-6)
+            assert float(rel.max()) <= 1e-5, "reward[%d] agent %d: %g" % (t - 1, a, float(rel.max()))
+assert n_done_env > 0, "the frames were meant to end some episodes inside the first rollout"
+assert "some episodes done" in log.getvalue()
+print("RUNNER_OK algo=%s fused=%s episodes=%d" % (ALGO, FUSED, EPISODES))
+'''
+
+
+@needs_ref
+@pytest.mark.parametrize("algo,fused", [("ippo", False), ("ippo", True), ("mappo", True), ("happo", True)])
+def test_runner_mirror_with_ippo_dispatch(cuda_device, tmp_path, algo, fused):
+    """`runner.Runner` (the reference's Runner interface + the `ippo` branch its dispatch lacks, device-side insert masks and
+    episode bookkeeping) trains TenAnt for 2 episodes with the reference's own trainers / policies - optionally with this
+    library's fused update bodies - and the first episode it stored equals the reference's own env classes on the same
+    frames and actions."""
+    res = subprocess.run([sys.executable, "-c", _IPPO_SCRIPT, ROOT, REF, str(tmp_path), algo, "1" if fused else "0"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "RUNNER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
