@@ -245,6 +245,53 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def mlp_forward_bench(dev, M, iters=200):
+    """PPO `ActorCritic.act` forward (actor + critic as one grouped launch per layer, sampling + log-prob kernel) at batch M:
+    ms per call (CUDA events around `iters` back-to-back calls), TFLOP/s of the two MLPs and the fraction of the measured
+    sustained bf16 peak.  Secondary figure: the headline metric does not include the policy forward."""
+    from massive_marl_benchmark_b200.mlp import PPOActorCriticForward
+
+    def net(out_dim, gain):
+        dims, mods = [388, 1024, 1024, 512, out_dim], []
+        for i in range(4):
+            lin = torch.nn.Linear(dims[i], dims[i + 1])
+            torch.nn.init.orthogonal_(lin.weight, gain=(gain if i == 3 else 2 ** 0.5))
+            mods.append(lin)
+            if i < 3:
+                mods.append(torch.nn.ELU())
+        return torch.nn.Sequential(*mods)
+
+    class AC(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.asymmetric = False
+            self.actor, self.critic = net(80, 0.01), net(1, 1.0)
+            self.log_std = torch.nn.Parameter(torch.log(torch.tensor(0.8)) * torch.ones(80))
+
+    torch.manual_seed(0)
+    fwd = PPOActorCriticForward(AC().to(dev), dev)
+    obs = torch.clamp(torch.randn(M, 388, device=dev) * 2.0, -5, 5)
+    for _ in range(5):
+        fwd.act(obs, None)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fwd.act(obs, None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * M * ((388 * 1024 + 1024 * 1024 + 1024 * 512 + 512 * 80) + (388 * 1024 + 1024 * 1024 + 1024 * 512 + 512 * 1))
+    peak = None
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        peak = float(json.load(open(pth)).get("bf16_tflops_sustained", 0.0)) or None
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"op": "PPO ActorCritic.act forward (actor + critic, bf16 operands / fp32 accumulate, tcgen05)", "batch": M, "ms": ms,
+            "tflops": tf, "peak_tflops": peak, "frac": (tf / peak) if peak else None,
+            "note": "eager back-to-back calls incl. input cast, 4 grouped layer launches and the sampling kernel; not part of the headline metric"}
+
+
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
@@ -498,6 +545,15 @@ def run_ours(args, rank, world, local_rank):
     h2d = T * host_prov.h2d_bytes_per_frame
     d2h = T * (N * 4 + N * 8) + T * N * 4
 
+    # ---- the one dense contraction on the path: the actor-critic MLP forward the rollout calls once per env step
+    # (module.py:25-55,73-87: 388 -> 1024 -> 1024 -> 512 -> 80 and -> 1, ELU) on the tcgen05 kernels, at this config's batch ----
+    mlp = None
+    if world == 1 and not args.no_mlp:
+        try:
+            mlp = mlp_forward_bench(dev, N)
+        except Exception as ex:  # pragma: no cover
+            mlp = {"error": repr(ex)}
+
     xchg_errors = int(mdist.sum_over_ranks(float(xchg.errors), dev)) if xchg is not None else 0
     chain_errors = int(mdist.sum_over_ranks(float(chain_errors), dev))
     if xchg_errors:
@@ -560,6 +616,7 @@ def run_ours(args, rank, world, local_rank):
                      "whole_step": {"algorithmic_bytes": step_bytes, "ms": ms / K,
                                     "achieved": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak}},
         "cpu_baseline": cpu,
+        "mlp_forward": mlp,
         "clocks": sampler.summary(t_host0, t_host1),
     }
     print(json.dumps(line), flush=True)
@@ -576,6 +633,7 @@ def main():
                     help="multi-GPU advantage statistics: NVLink peer-memory mailboxes (default) or NCCL all-reduce")
     ap.add_argument("--no-overlap", action="store_true", help="ordinary stream order between consecutive step kernels (no PDL)")
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-mlp", action="store_true", help="skip the secondary MLP-forward figure")
     ap.add_argument("--no-fused-gae", action="store_true", help="GAE scan as its own launch (mmb_gae_ppo) instead of inside the step kernel")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

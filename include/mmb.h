@@ -151,7 +151,15 @@ typedef struct {
    * Raw advantages go to gae_advantages, their {sum, sumsq} (fp64) to the slot area of gae_stats (one atomic pair per
    * tile, spread over MMB_STAT_SLOTS lines), the count to gae_stats[0]; normalise with MMB_NORM_SLOTS.
    * `values` / `last_values` must be final before the launch (replayed values; the interactive per-step path keeps
-   * mmb_gae_ppo). */
+   * mmb_gae_ppo).  gae_scratch / gae_stats / gae_returns / gae_advantages belong to the call's outputs in the sense of
+   * overlap_prev: the preceding kernel in the stream must not touch them (use one set per storage). */
+  /* Optional: the root tensor [11N][13] of the frame that PRECEDED frame 0 of this call (the task's root_states before the
+   * call).  The carry of a step is a pure function of the previous frame (ant xy, box row -> goals; ten_ant.py:870-882,
+   * 905-914), so with it frame 0 is processed exactly like frames 1..T-1 and never reads pos_before / goal_before (still
+   * written on exit): no unit but the executors of the last frame then depends on the previous launch, and with
+   * overlap_prev the next rollout's head runs under this rollout's tail without stalling.  NULL: frame 0 reads the carry
+   * arrays (and, with overlap_prev, waits for the preceding kernel).  Role-split kernel only. */
+  const float* prev_root;
   const float* gae_values;  int64_t gae_values_frame_stride;         /* [T][N] */
   const float* gae_last_values;                                      /* [N] */
   float* gae_returns;       int64_t gae_returns_frame_stride;        /* [T][N] */

@@ -661,6 +661,11 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   const mmb_ant_consts& c = p.c;
   const bool pdl = p.overlap_prev != 0;
   if (pdl) griddep_launch_dependents();  // the next kernel in the stream may start filling SM slots as this one drains
+  // the frame the carry of step t comes from (ten_ant.py:870-882,905-914): frame t - 1 of this launch, or - frame 0 - the
+  // frame that preceded the launch (mmb.h, prev_root).  Without prev_root frame 0 reads the carry arrays the previous
+  // launch's executors wrote, i.e. waits for that whole kernel.
+  const bool has_prev = t > 0 || p.prev_root != nullptr;
+  const float* prev_frame = t > 0 ? p.root + (int64_t)(t - 1) * p.root_frame_stride : p.prev_root;
   const bool box_role = tid >= 2 * NA;   // warp 10
   const bool dof_role = tid >= NA && !box_role;   // warp-uniform (NA = 5 warps)
   const int a = box_role ? 0 : (dof_role ? tid - NA : tid);
@@ -696,10 +701,11 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     // other work, straight from global memory (L2-prefetched), so nobody reaches the box barrier late because of them
     const int env_l = lane & 15;
     const bool prev = lane >= 16;
-    const bool on = env_l < ne && !(prev && t == 0);
+    const bool on = env_l < ne && !(prev && !has_prev);
     float b0 = 0.f, b1 = 0.f, b5 = 0.f, b6 = 1.f;
     if (on) {
-      const float* b = p.root + (int64_t)(prev ? t - 1 : t) * p.root_frame_stride + ((int64_t)(e0 + env_l) * 11 + 10) * 13;
+      const float* fr = prev ? prev_frame : p.root + (int64_t)t * p.root_frame_stride;
+      const float* b = fr + ((int64_t)(e0 + env_l) * 11 + 10) * 13;
       b0 = __ldg(b); b1 = __ldg(b + 1); b5 = __ldg(b + 5); b6 = __ldg(b + 6);
     }
     __syncthreads();                     // B1
@@ -793,10 +799,10 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       const float* bo = box_s + el * BOX_W;
       float gx, gy;
       goal_of(k, bo[2], bo[3], bo[0], bo[1], gx, gy);
-      if (t > 0) {
+      if (has_prev) {
         goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
-      } else {  // frame 0: the carry written by the previous launch (with overlap_prev: wait for that kernel first;
-                // everything above was independent of it)
+      } else {  // frame 0 without prev_root: the carry written by the previous launch (with overlap_prev: wait for that
+                // kernel first; everything above was independent of it)
         if (pdl) griddep_wait();
         const float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
         gbx = __ldcg(gb); gby = __ldcg(gb + 1);
@@ -811,8 +817,8 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   } else {
     // ================= core role =================
     float pbx = 0.f, pby = 0.f, gbx = 0.f, gby = 0.f;
-    if (active && t > 0) {  // carry of step t = ant xy of frame t-1 (ten_ant.py:905-914); frame 0: loaded after B2
-      const float* rp = p.root + (int64_t)(t - 1) * p.root_frame_stride + ((int64_t)e * 11 + k) * 13;
+    if (active && has_prev) {  // carry of step t = ant xy of the previous frame (ten_ant.py:905-914); else: loaded after B2
+      const float* rp = prev_frame + ((int64_t)e * 11 + k) * 13;
       pbx = __ldg(rp); pby = __ldg(rp + 1);
     }
     __syncthreads();                     // B1
@@ -843,7 +849,7 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       const float* bo = box_s + el * BOX_W;
       float gx, gy;
       goal_of(k, bo[2], bo[3], bo[0], bo[1], gx, gy);
-      if (t > 0) {
+      if (has_prev) {
         goal_of(k, bo[10], bo[11], bo[8], bo[9], gbx, gby);
       } else {
         if (pdl) griddep_wait();
@@ -902,8 +908,9 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   } else if (!gae_exec) {
     // frames 0..T-2: reward + fallen bit of (env, frame) travel to the executor in ONE fire-and-forget 64-bit store
     // (data and flag are the same word: no fence, nothing comes back, the CTA retires at once)
+    // No wait on the previous kernel here: the words belong to this call's storage set, which by the overlap_prev contract
+    // (mmb.h) the preceding kernel neither reads nor writes - their last consumer finished before this launch was issued.
     if (tid >= NA && tid - NA < ne) {
-      if (pdl) griddep_wait();             // the previous launch's executor must have consumed (zeroed) the word
       const int en = e0 + (tid - NA);
       bool fallen;
       const float r = env_reward(c, part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, fallen);

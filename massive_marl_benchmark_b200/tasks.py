@@ -16,6 +16,7 @@ MARL runners work unchanged.  Two deliberate differences, both documented in DES
 There is no CPU path: every method that computes calls the CUDA library and fails loudly without it.
 """
 import math
+import os
 from typing import Optional
 
 import torch
@@ -25,6 +26,7 @@ from . import synthetic
 from .providers import FrameProvider, ReplayProvider
 
 INF = float("inf")
+_TEN_ANT_MONO = os.environ.get("MMB_TEN_ANT_VARIANT", "")[:1] == "m"   # the one-thread-per-ant kernel reads the carry arrays
 
 
 def _device_of(device_type, device_id):
@@ -144,6 +146,7 @@ class TenAnt(BaseTask):
         self.keep_raw_obs = True
         self.actions = torch.zeros(N, 80, device=dev)
         self._chain_words = torch.zeros(N + 1, device=dev, dtype=torch.int64)   # replay(): per-env flag/count words + error count
+        self.use_prev_root = True
         self._p_reset = None
         self._p_step = None
         # reset_idx at the first step reloads the carry from the not-yet-refreshed root tensor
@@ -175,14 +178,26 @@ class TenAnt(BaseTask):
         self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
         self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
 
+    def _prev_root_for_replay(self):
+        """The frame that preceded the replay = the task's current `root_states` (the last frame processed, or the initial
+        root before the first step): frame 0's carry is computed from it inside the kernel (include/mmb.h, prev_root), which
+        equals the stored carry bit for bit.  Only the role-split kernel takes it; it must be a contiguous [11N, 13] tensor
+        that stays untouched until the launch has run (frames of a replay set / provider are)."""
+        r = self.root_states
+        if _TEN_ANT_MONO or r is None or not r.is_contiguous() or r.shape != (11 * self.num_envs, 13) or not self.use_prev_root:
+            return None
+        self._prev_root_keep = r
+        return r
+
     def chain_errors(self) -> int:
         """Horizon-batched launches whose in-kernel progress / reset chain gave up waiting for a frame's report (~1 s:
         preemption, a debugger); the affected envs' flags, carry and returns were left untouched.  Host sync."""
         return int(self._chain_words[self.num_envs].item())
 
     def _launch(self, root, dof, actions, T, strides, obs_raw, obs, share_obs, rewards, dones_i64, dones_u8, forces,
-                out_strides, overlap_prev=False, obs_layout=None, obs_agent_stride=0, gae=None):
+                out_strides, overlap_prev=False, obs_layout=None, obs_agent_stride=0, gae=None, prev_root=None):
         p = L.TenAntParams()
+        p.prev_root = L.ptr(prev_root)
         if gae is not None:
             v, r, a = gae["values"], gae["returns"], gae["advantages"]
             p.gae_values, p.gae_values_frame_stride = L.ptr(v), v.stride(0)
@@ -277,7 +292,8 @@ class TenAnt(BaseTask):
         self._launch(root, dof, actions, T, (root.stride(0), dof.stride(0), actions.stride(0)),
                      obs_raw_out, obs_out, share_obs_out, rewards_out, dones_i64_out, dones_u8_out, forces_out,
                      (s(obs_raw_out), s(obs_out), s(share_obs_out), s(rewards_out), s(dones_i64_out), s(dones_u8_out),
-                      s(forces_out)), overlap_prev=overlap_prev, obs_layout=layout, obs_agent_stride=agent_stride, gae=gae)
+                      s(forces_out)), overlap_prev=overlap_prev, obs_layout=layout, obs_agent_stride=agent_stride, gae=gae,
+                     prev_root=self._prev_root_for_replay())
         self.root_states, self.dof_state = root[T - 1], dof[T - 1]
         self._step_count += T
 

@@ -113,3 +113,57 @@ def test_env_sharded_ppo_update_world2(tmp_path):
     port = _free_port()
     mp.spawn(_update_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "upd0").exists() and (tmp_path / "upd1").exists()
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    """Bucketed all-reduce overlapped with backward (hooks) and the flat-slice reducer: averaged gradients equal the mean of
+    the per-rank gradients, `.grad` ends up as views of the flat buffer, repeated steps and partially used networks work."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from massive_marl_benchmark_b200 import dist as mdist
+    mdist.init_from_env("gloo")
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ELU(), torch.nn.Linear(16, 16), torch.nn.ELU(), torch.nn.Linear(16, 3))
+    unused = torch.nn.Linear(4, 2)                     # never takes part in the loss: its bucket gets no gradient
+    params = list(net.parameters()) + list(unused.parameters())
+    import copy
+    ref = copy.deepcopy(net)                           # hook-free twin for the expected values
+    red = mdist.OverlappedGradAllReduce(params, bucket_bytes=256)       # three buckets
+    assert len(red.buckets) >= 3
+    for step in range(3):
+        xs = [torch.randn(8, 6, generator=torch.Generator().manual_seed(100 * step + r)) for r in range(world)]
+        want = None
+        for r in range(world):                         # what the average must be: every rank's gradient, computed locally
+            ref.zero_grad()
+            ref(xs[r]).pow(2).mean().backward()
+            g = [p.grad.clone() for p in ref.parameters()]
+            want = g if want is None else [a + b for a, b in zip(want, g)]
+        want = [w / world for w in want]
+        for p in params:
+            p.grad = None
+        net(xs[rank]).pow(2).mean().backward()          # hooks fire bucket by bucket while backward runs
+        red.finish()
+        for p, w in zip(net.parameters(), want):
+            assert torch.allclose(p.grad, w, rtol=1e-6, atol=1e-8)
+            lo = red.flat.data_ptr()
+            assert lo <= p.grad.data_ptr() < lo + red.flat.numel() * 4, ".grad must be a view of the flat buffer"
+        # a parameter without a gradient that shares a bucket with produced ones travels as zeros (documented in finish())
+        assert all(p.grad is not None and float(p.grad.abs().sum()) == 0.0 for p in unused.parameters())
+    assert red.calls >= 3 * 3 and red.bytes_reduced > 0
+    red.remove()
+    # slices of one flat buffer, asynchronously
+    flat = torch.arange(40, dtype=torch.float32) * (rank + 1)
+    fr = mdist.FlatGradReducer(flat)
+    fr.reduce_async(0, 16)
+    fr.reduce_async(16, 40)
+    fr.wait()
+    assert torch.allclose(flat, torch.arange(40, dtype=torch.float32) * (sum(range(1, world + 1)) / world))
+    assert fr.calls == 2 and fr.bytes_reduced == 160
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, "ovl%d" % rank), "w").write("1")
+
+
+def test_overlapped_gradient_allreduce_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_overlap_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ovl0").exists() and (tmp_path / "ovl1").exists()
