@@ -140,7 +140,10 @@ typedef struct {
    * consecutive rollouts alternate between frame / storage sets; false when the frames were just produced by a
    * simulation kernel).  0 = ordinary stream order. */
   int32_t overlap_prev;
-  int32_t _reserved;
+  /* != 0 (with overlap_prev): `scratch` belongs to this call's frame / storage set like its outputs - the preceding kernel
+   * in the stream does not touch it - so the chain reports of frames 0..T-2 need not wait for that kernel either.
+   * 0: `scratch` is shared by consecutive launches (one per task) and every unit orders its report behind them. */
+  int32_t scratch_per_set;
   /* obs_layout 2 only: element stride between the per-agent planes of `obs` (see obs_layout) */
   int64_t obs_agent_stride;
   /* Fused RolloutStorage.compute_returns (storage.py:51-62 + `returns - values`), horizon-batched launches only

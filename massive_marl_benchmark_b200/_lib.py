@@ -41,7 +41,7 @@ class TenAntParams(C.Structure):
         ("obs_raw", c_vp), ("obs_raw_frame_stride", c_i64), ("obs", c_vp), ("obs_frame_stride", c_i64),
         ("share_obs", c_vp), ("share_obs_frame_stride", c_i64), ("rewards", c_vp), ("rewards_frame_stride", c_i64),
         ("dones_i64", c_vp), ("dones_i64_frame_stride", c_i64), ("dones_u8", c_vp), ("dones_u8_frame_stride", c_i64),
-        ("forces", c_vp), ("forces_frame_stride", c_i64), ("scratch", c_vp), ("overlap_prev", c_i32), ("_reserved", c_i32),
+        ("forces", c_vp), ("forces_frame_stride", c_i64), ("scratch", c_vp), ("overlap_prev", c_i32), ("scratch_per_set", c_i32),
         ("obs_agent_stride", c_i64), ("prev_root", c_vp),
         ("gae_values", c_vp), ("gae_values_frame_stride", c_i64), ("gae_last_values", c_vp),
         ("gae_returns", c_vp), ("gae_returns_frame_stride", c_i64),

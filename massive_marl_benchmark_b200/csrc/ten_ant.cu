@@ -901,7 +901,9 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
   // the finish runs in the first dof warp: warp 0 has the bulk store to issue and to wait for
   if (!gae_on) {
     if (tid >= NA && tid - NA < ne) {
-      if (pdl) griddep_wait();             // progress / reset / chain words: behind the previous kernel
+      // progress / reset / carry outputs (executor, T == 1) and the chain words are ordered behind the previous kernel;
+      // with a per-set scratch (mmb.h, scratch_per_set) the reports of frames 0..T-2 need no such order
+      if (pdl && (t == p.num_frames - 1 || !p.scratch_per_set || !p.scratch)) griddep_wait();
       finish_env(p, t, e0 + (tid - NA), part_s + (tid - NA) * A * PART_W, box_s + (tid - NA) * BOX_W, root_s + (tid - NA) * ROOT_ENV);
       if (tid == NA) MMB_TR(10);
     }

@@ -158,6 +158,13 @@ class RolloutStorage:
                 "advantages": self.advantages.view(T, N), "stats": self._adv_stats4, "scratch": self._gae_words,
                 "gamma": float(gamma), "lam": float(lam)}
 
+    def chain_scratch(self):
+        """[N + 1] int64 words for `TenAnt.replay(..., chain_scratch=...)`: the in-kernel progress / reset chain of a
+        horizon-batched launch into this storage (include/mmb.h, `scratch` / `scratch_per_set`)."""
+        if getattr(self, "_chain_scratch", None) is None:
+            self._chain_scratch = torch.zeros(self.num_envs + 1, device=self.rewards.device, dtype=torch.int64)
+        return self._chain_scratch
+
     def normalize_advantages(self):
         """Second half (storage.py:65): [all-reduce of the statistics over env shards] + (adv - mean) / (std + 1e-8)."""
         T, N = self.num_transitions_per_env, self.num_envs

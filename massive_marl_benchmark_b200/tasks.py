@@ -192,10 +192,13 @@ class TenAnt(BaseTask):
     def chain_errors(self) -> int:
         """Horizon-batched launches whose in-kernel progress / reset chain gave up waiting for a frame's report (~1 s:
         preemption, a debugger); the affected envs' flags, carry and returns were left untouched.  Host sync."""
-        return int(self._chain_words[self.num_envs].item())
+        n = int(self._chain_words[self.num_envs].item())
+        for w in getattr(self, "_extra_chain_words", ()):
+            n += int(w[self.num_envs].item())
+        return n
 
     def _launch(self, root, dof, actions, T, strides, obs_raw, obs, share_obs, rewards, dones_i64, dones_u8, forces,
-                out_strides, overlap_prev=False, obs_layout=None, obs_agent_stride=0, gae=None, prev_root=None):
+                out_strides, overlap_prev=False, obs_layout=None, obs_agent_stride=0, gae=None, prev_root=None, chain_scratch=None):
         p = L.TenAntParams()
         p.prev_root = L.ptr(prev_root)
         if gae is not None:
@@ -219,7 +222,12 @@ class TenAnt(BaseTask):
         p.dones_i64, p.dones_u8, p.forces = L.ptr(dones_i64), L.ptr(dones_u8), L.ptr(forces)
         (p.obs_raw_frame_stride, p.obs_frame_stride, p.share_obs_frame_stride, p.rewards_frame_stride,
          p.dones_i64_frame_stride, p.dones_u8_frame_stride, p.forces_frame_stride) = out_strides
-        p.scratch = L.ptr(self._chain_words) if T > 1 else None
+        if chain_scratch is not None:     # a [N + 1] int64 scratch of the caller's frame / storage set (see replay)
+            p.scratch, p.scratch_per_set = L.ptr(chain_scratch), 1
+            self._chain_words_last = chain_scratch
+        else:
+            p.scratch = L.ptr(self._chain_words) if T > 1 else None
+            self._chain_words_last = self._chain_words
         p.c = self.consts
         L.check(L.lib().mmb_ten_ant_step(p, L.stream_ptr()), "mmb_ten_ant_step")
 
@@ -260,11 +268,15 @@ class TenAnt(BaseTask):
 
     # -- horizon-batched replay (B200-native addition, SURVEY.md section 7 hard part 1) ---------
     def replay(self, frames, actions, obs_out, rewards_out, dones_u8_out=None, dones_i64_out=None, forces_out=None,
-               share_obs_out=None, obs_raw_out=None, overlap_prev=False, agent_major_obs_out=None, gae=None):
+               share_obs_out=None, obs_raw_out=None, overlap_prev=False, agent_major_obs_out=None, gae=None, chain_scratch=None):
         """Process T consecutive frames in ONE launch (+ the 1-byte/env-step progress chain).
 
         gae = `RolloutStorage.fused_gae(last_values, gamma, lam)`: the same launch also runs the storage's
         compute_returns scan (returns, raw advantages, their statistics) - follow it with `normalize_advantages()`.
+
+        chain_scratch = `RolloutStorage.chain_scratch()`: the in-kernel progress / reset chain collects its per-frame reports
+        in words of the storage set instead of the task's; with overlap_prev the reports then need not wait for the preceding
+        launch (which uses another set).
 
         frames: dict root [T,11N,13], dof [T,80N,2]; actions [T,N,80]; outputs are [T, ...] planes, e.g.
         slices of a rollout storage so that obs / reward / done land in their slots without a copy pass.
@@ -293,7 +305,9 @@ class TenAnt(BaseTask):
                      obs_raw_out, obs_out, share_obs_out, rewards_out, dones_i64_out, dones_u8_out, forces_out,
                      (s(obs_raw_out), s(obs_out), s(share_obs_out), s(rewards_out), s(dones_i64_out), s(dones_u8_out),
                       s(forces_out)), overlap_prev=overlap_prev, obs_layout=layout, obs_agent_stride=agent_stride, gae=gae,
-                     prev_root=self._prev_root_for_replay())
+                     prev_root=self._prev_root_for_replay(), chain_scratch=chain_scratch)
+        if chain_scratch is not None and all(chain_scratch is not w for w in self.__dict__.setdefault("_extra_chain_words", [])):
+            self._extra_chain_words.append(chain_scratch)
         self.root_states, self.dof_state = root[T - 1], dof[T - 1]
         self._step_count += T
 

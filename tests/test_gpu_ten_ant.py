@@ -439,7 +439,8 @@ def test_ten_ant_fused_gae_equals_separate_kernels(cuda_device, N, T):
 
         def rollout():
             task.replay(frd, frd["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N),
-                        gae=st.fused_gae(lv, 0.96, 0.95) if fused else None)
+                        gae=st.fused_gae(lv, 0.96, 0.95) if fused else None, overlap_prev=graph,
+                        chain_scratch=st.chain_scratch() if graph else None)   # graph runs: per-set chain words + PDL
             if not fused:
                 st.compute_returns_scan(lv, 0.96, 0.95)
             raw = st.advantages.clone()
@@ -511,7 +512,7 @@ def test_ten_ant_bench_config_vs_oracle(cuda_device):
         s = r % 2
         st, fr = sts[s], sets_dev[s]
         task.replay(fr, fr["actions"], st.obs_slots[1:], st.rewards.view(T, N), st.dones.view(T, N), overlap_prev=True,
-                    gae=st.fused_gae(lv, 0.96, 0.95))
+                    gae=st.fused_gae(lv, 0.96, 0.95), chain_scratch=st.chain_scratch())
         main = torch.cuda.current_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
