@@ -8,10 +8,11 @@
 Workload (BASELINE.json configs[1]): TenAnt, 4096 envs x 10 agents per GPU, horizon T = 16.  One "step" =
 one pass of the hot path over one batch = one rollout of T frames x N envs:
     mmb_ten_ant_step   T frames in one launch: action scaling, observations, reward, done written straight into the
-                       rollout storage slots; progress / reset chain, carry and the GAE scan of RolloutStorage.
-                       compute_returns (returns, raw advantages, their fp64 statistics) in the unit that closes an env
+                       rollout storage slots; progress / reset chain and carry in the unit that closes an env
   + mmb_reset_compact  over the T flag rows (reset-index lists + DOF re-randomisation)             [side stream]
-  + mmb_adv_normalize  (N > 1: mmb_adv_normalize_xchg, statistics exchanged over NVLink in-kernel)  [side stream]
+  + mmb_gae_ppo        reverse-time scan of RolloutStorage.compute_returns + fp64 statistics        [side stream 2]
+  + mmb_adv_normalize  (N > 1: mmb_adv_normalize_xchg, statistics exchanged over NVLink in-kernel)  [side stream 2]
+(--fused-gae folds the scan into the step kernel's chain executor instead: one launch fewer, measured slower.)
 `value` = env-steps/s with the state frames already resident in HBM; `e2e` = the same metric through the
 reference-facing API (VecTaskPython.step / RolloutStorage) with the frames and actions in pinned HOST memory
 (H2D every env-step, D2H of reward/done every env-step and of the advantages every rollout).
@@ -330,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
     N, T, K, W = N_ENVS, HORIZON, args.steps, max(args.warmup, 3)
     SETS = 4  # rotating frame/storage sets: 4 x ~225 MB of traffic per step >> 126 MB L2
     GROUP = int(os.environ.get("MMB_BENCH_GROUP", 8 * SETS))  # rollouts captured per CUDA graph (side-stream tails joined once per graph)
-    fused = not args.no_fused_gae
+    fused = args.fused_gae
 
     def barrier():
         if world > 1:
@@ -654,7 +655,10 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="ordinary stream order between consecutive step kernels (no PDL)")
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-mlp", action="store_true", help="skip the secondary MLP-forward figure")
-    ap.add_argument("--no-fused-gae", action="store_true", help="GAE scan as its own launch (mmb_gae_ppo) instead of inside the step kernel")
+    ap.add_argument("--fused-gae", action="store_true",
+                    help="GAE scan inside the step kernel's chain executor instead of its own launch (mmb_gae_ppo on a side stream, the "
+                         "default: measured 1.5 us per rollout faster, DESIGN.md section 4)")
+    ap.add_argument("--no-fused-gae", action="store_true", help="(default; kept for older command lines)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
