@@ -331,18 +331,21 @@ MMB_API int32_t mmb_adv_normalize(float* advantages, int64_t n, double* stats, f
 /* Env-sharded multi-GPU: exchange of the advantage statistics over NVLink peer memory.            */
 /* The reference is single-GPU (storage.py:65 normalises over all envs of the one device); with     */
 /* envs sharded over ranks the same normalisation needs the global {count,sum,sumsq}.  Instead of a */
-/* collective launch between the GAE scan and the normalisation, the normalise kernel does the      */
-/* exchange itself: its first block stores the shard's three doubles + a sequence flag straight     */
-/* into every peer's mailbox, then all blocks wait on their OWN mailbox (local memory) and sum the   */
-/* shards in rank order, so every rank normalises with bit-identical moments.  No host involvement:  */
-/* replayable from a CUDA graph; the NVLink latency sits in the normalise launch, off the scan path. */
+/* collective launch between the GAE scan and the normalisation, a one-warp kernel does the         */
+/* exchange itself: lane r stores the shard's three doubles + a sequence flag straight into rank     */
+/* r's mailbox, then waits on rank r's flag in its OWN mailbox (local memory) and the shards are      */
+/* summed in rank order, so every rank normalises with bit-identical moments.  No host involvement:  */
+/* replayable from a CUDA graph; the NVLink latency sits in that warp, off the scan path, and the     */
+/* normalise launch that follows finds the global moments ready.                                     */
 /*                                                                                                  */
 /* Mailbox layout (per rank, device memory of that rank): [slots][world][4] 8-byte words             */
 /* {count, sum, sumsq, seq flag}.  Exchange number q (1, 2, ...) uses slot q % slots; slots >= 2      */
 /* (a rank can be at most one exchange ahead of a peer).  All ranks must issue the same sequence of   */
 /* mmb_adv_normalize_xchg calls on one endpoint.                                                    */
-/* `state` is 8 zero-initialised uint64 of local device memory: [1] exchanges completed, [2] ticket,  */
-/* [3] error count (flag wait timed out or slot overrun), others reserved.                          */
+/* `state` is 8 zero-initialised uint64 of local device memory: [1] exchanges completed, [3] error   */
+/* count (flag wait timed out or slot overrun), [4..6] the global {count,sum,sumsq} of the last      */
+/* exchange (doubles), others reserved.  Calls on one endpoint must be ordered (one stream, or        */
+/* events): exchange q's moments are consumed by its normalise launch before exchange q + 1 starts.  */
 /* ------------------------------------------------------------------------------------------ */
 #define MMB_MAX_RANKS 16
 typedef struct mmb_xchg {

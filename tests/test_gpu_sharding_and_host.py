@@ -193,3 +193,25 @@ def test_stats_exchange_ipc_endpoint_single_rank(cuda_device):
     assert torch.equal(a.returns, b.returns) and torch.equal(a.advantages, b.advantages)
     assert x.errors == 0
     x.close()
+
+
+@pytest.mark.gpu
+def test_stats_exchange_timeout_is_loud(cuda_device):
+    """A peer that never publishes: after the (configurable) time-out the exchange does NOT normalise with partial moments -
+    the shard's advantages become NaN, the endpoint counts an error and `RolloutStorage.check_exchange` (called from
+    `mini_batch_generator`, once per update) raises."""
+    from massive_marl_benchmark_b200 import _lib as L
+    from massive_marl_benchmark_b200.dist import StatsExchange
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    dev = cuda_device
+    ends = StatsExchange.local(2, slots=4, device=dev, timeout_ms=30)
+    st = RolloutStorage(256, 4, (4,), (0,), (2,), dev)
+    st.stats_exchange = ends[0]
+    st.rewards.normal_(); st.values.normal_()
+    st.compute_returns(torch.randn(256, 1, device=dev), 0.99, 0.95)       # rank 1 stays silent
+    torch.cuda.synchronize()
+    assert torch.isnan(st.advantages).all(), "a failed exchange must not leave plausible numbers behind"
+    assert ends[0].errors == 1
+    with pytest.raises(L.MmbError, match="exchange failed"):
+        st.mini_batch_generator(4)
+    assert torch.isfinite(st.returns).all()

@@ -6,7 +6,6 @@
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-export NCCL_DEBUG=WARN
 timeout 300 $TR --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_scale_${N}.json 2> gpurun_out/r2_scale_${N}.err
 if [ "$N" -lt 8 ]; then
 timeout 300 $TR --master-port 29512 bench.py --gpus $N --steps 2000 --warmup 20 > gpurun_out/r2_scale_${N}_k2000.json 2> gpurun_out/r2_scale_${N}_k2000.err
