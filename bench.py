@@ -453,6 +453,12 @@ def run_ours(args, rank, world, local_rank):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_host0 = time.perf_counter()
+    # The K steps are timed ON THE DEVICE.  A ~0.2 ms delay kernel in front of the first event keeps the GPU busy while the
+    # host enqueues the (graph) launches, so the interval between the two events is the device executing K steps back to back
+    # - not the host's launch latency of the first graph (tens of microseconds, which at the driver's --steps 20 = 0.8 ms of
+    # device work would otherwise be billed as ~1.5 us per step, and more with 8 processes sharing the host).
+    if not args.no_prime:
+        torch.cuda._sleep(int(2.0e5 * 1.9))
     ev0.record()
     run_steps(K)
     ev1.record()
@@ -616,7 +622,8 @@ def run_ours(args, rank, world, local_rank):
                    "num_envs_per_gpu": N, "num_agents": 10, "horizon": T, "env_steps_per_step": T * N,
                    "l2": "4 rotating frame/storage sets, ~225 MB of traffic per step each, > 126 MB L2",
                    "parallelism": "env-sharded dp%d" % world,
-                   "timed_region": "CUDA graphs of min(steps, %d) rollouts, side-stream tails joined once per graph" % GROUP,
+                   "timed_region": ("CUDA graphs of min(steps, %d) rollouts, side-stream tails joined once per graph; device time between two "
+                                    "CUDA events%s") % (GROUP, "" if args.no_prime else ", launches enqueued behind a 0.2 ms delay kernel (host launch latency excluded)"),
                    "gae": "fused into the step kernel's chain executor" if fused else "mmb_gae_ppo on a side stream",
                    "stored_planes": "obs, rewards, dones, returns, advantages, forces (values are inputs; actions / mu / sigma / log-prob "
                                     "planes belong to the policy forward, not to this metric, and are not written)",
@@ -654,6 +661,7 @@ def main():
                     help="multi-GPU advantage statistics: NVLink peer-memory mailboxes (default) or NCCL all-reduce")
     ap.add_argument("--no-overlap", action="store_true", help="ordinary stream order between consecutive step kernels (no PDL)")
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-prime", action="store_true", help="no delay kernel in front of the timed region (host launch latency then counts)")
     ap.add_argument("--no-mlp", action="store_true", help="skip the secondary MLP-forward figure")
     ap.add_argument("--fused-gae", action="store_true",
                     help="GAE scan inside the step kernel's chain executor instead of its own launch (mmb_gae_ppo on a side stream, the "

@@ -12,7 +12,7 @@ kernel=${2:-ten_ant_split_kernel}
 out=gpurun_out
 mkdir -p $out
 # --no-graph: eager launches, so that ncu sees ordinary kernel launches (graph replays need --graph-profiling node)
-short="python bench.py --steps 8 --warmup 3 --cpu-rollouts 0 --no-graph"
+short="python bench.py --steps 8 --warmup 3 --cpu-rollouts 0 --no-graph --no-mlp"
 
 python bench.py --steps 2000 --warmup 20 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench.err || { echo "bench failed"; tail -5 $out/${tag}_bench.err; exit 1; }
 tail -c 600 $out/${tag}_bench_1gpu.json; echo
@@ -24,3 +24,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kernel -s 40 -c 1 \
     -o $out/${tag}_ten_ant -f $short > $out/${tag}_ncu_full.log 2>&1 || echo "--set full pass failed (see ${tag}_ncu_full.log)"
 ls -la $out | tail -8
+
+# the gather kernel (shuffle_group 8 then 1, 16 M transitions): launches 1-8 = group 8, 9-16 = group 1
+gcase="python tools/probe/gather_case.py"
+$gcase > $out/${tag}_gather_plain.log 2>&1 && \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:gather_kernel -s 4 -c 1 -o $out/${tag}_gather_g8 -f $gcase > $out/${tag}_ncu_gather8.log 2>&1 || echo "gather g8 pass failed"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:gather_kernel -s 12 -c 1 -o $out/${tag}_gather_g1 -f $gcase > $out/${tag}_ncu_gather1.log 2>&1 || echo "gather g1 pass failed"
+ls -la $out | grep ${tag}
