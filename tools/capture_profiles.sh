@@ -21,7 +21,7 @@ $short > $out/${tag}_plain.log 2>&1 || { echo "short bench failed"; tail -5 $out
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     $short > $out/${tag}_ncu_launches.log 2>&1 || echo "launch-list pass failed (see ${tag}_ncu_launches.log)"
 
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kernel -s 40 -c 1 \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kernel -s 10 -c 1 \
     -o $out/${tag}_ten_ant -f $short > $out/${tag}_ncu_full.log 2>&1 || echo "--set full pass failed (see ${tag}_ncu_full.log)"
 ls -la $out | tail -8
 
