@@ -590,6 +590,15 @@ MMB_API int32_t mmb_mlp_layer(const mmb_mlp_layer_params* p, void* stream);
  * env step).  `params` is an array of `count` structs; M, N, K, paddings, n_tile, epilogue and y_stride must agree. */
 #define MMB_MAX_GROUP 16
 MMB_API int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t count, void* stream);
+/* The whole Linear-ELU chain of a PPO network (module.py:25-55) in ONE launch: `layers` holds `count` networks x
+ * `num_layers` layer descriptions (row-major; network 0 defines the geometry, the others must agree: actor and critic side
+ * by side).  Layer l + 1's `x` must be layer l's `y` (bf16 [Mpad][y_stride], y_stride = Kpad of the next layer); hidden
+ * layers: epilogue 1, N a multiple of 256 and <= 1024; last layer: epilogue 0, fp32 y with 16-byte aligned base and pitch.
+ * `n_tile`, `stages` are ignored (a cluster of 4 CTAs per 128-row block splits every layer's columns four ways; the layer
+ * boundary is a cluster barrier, activations pass through L2).  `overlap_prev` of layers[0] as in mmb_mlp_layer.
+ * MMB_EUNSUPPORTED for other geometries: run the layers with mmb_mlp_layer / mmb_mlp_layer_group instead. */
+#define MMB_MLP_MAX_LAYERS 6
+MMB_API int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, void* stream);
 /* diagnostic of the experimental cta_group::2 mode (MMB_MLP_PAIR=1): first barrier wait that timed out {code, block x, block y,
  * parity}, all zero if none; clears the record */
 MMB_API int32_t mmb_mlp_debug_status(uint32_t* out4);

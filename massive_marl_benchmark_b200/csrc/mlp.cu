@@ -771,6 +771,161 @@ struct LnCastGroupArgs {
   __nv_bfloat16* y[MMB_MAX_GROUP];
 };
 
+
+// ------------------------------------------------------------------------------------------------------
+// Whole-MLP forward in ONE launch (PPO ActorCritic.actor / .critic: Linear-ELU chains, module.py:25-55).
+// A cluster of 4 CTAs owns one 128-row block for ALL layers; CTA r of the cluster computes columns [r * N_l / 4, (r + 1) *
+// N_l / 4) of every layer l.  Layer l + 1 of a row block needs exactly the four column slices its own cluster produced, so
+// the layer boundary is a `barrier.cluster` instead of a kernel boundary: activations travel through L2 (TMA store ->
+// cp.async.bulk.wait_group 0 -> cluster barrier -> TMA load), the operand ring and its mbarrier phases run on across the
+// layers, the next layer's first weight tiles are already in flight while this layer's epilogue runs (the output is staged
+// outside the ring), and launch prologue / pipeline drain are paid once per forward instead of once per layer.
+// Same warp roles as mlp_layer_ws_kernel (TMA producer, MMA issuer, 8 epilogue warps), one accumulator in tensor memory.
+// grid = (4 x row blocks, 1, networks): blockIdx.z selects one of up to two networks of identical geometry (actor and
+// critic side by side).  Geometry: hidden widths multiples of 256, <= 1024; TMA-addressable fp32 output.
+// ------------------------------------------------------------------------------------------------------
+constexpr int CHAIN_CLUSTER = 4;
+constexpr int CHAIN_STAGES = 4;
+constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BK * 2;   // 48 KB: the widest slice (256 columns)
+constexpr int CHAIN_SMEM = CHAIN_STAGES * CHAIN_STAGE_BYTES + 2 * BM * 128;   // ring + two 16 KB output staging buffers = 224 KB
+constexpr int CHAIN_MAX_NETS = 2;
+struct ChainLayer {
+  CUtensorMap map_x, map_w, map_y;
+  const float* bias;
+  int N, nkb, n_tile, epilogue;
+  int pad_[10];     // keeps the next element's tensor maps 64-byte aligned
+};
+static_assert(sizeof(ChainLayer) % 64 == 0, "tensor maps need 64-byte alignment");
+struct ChainArgs {
+  ChainLayer l[CHAIN_MAX_NETS][MMB_MLP_MAX_LAYERS];
+  int num_layers, M, overlap_prev, pad_;
+};
+
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[CHAIN_STAGES], empty_bar[CHAIN_STAGES], acc_bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr int S = CHAIN_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(crank));
+  const int m0 = (blockIdx.x / CHAIN_CLUSTER) * BM;
+  const ChainLayer* Ls = g.l[blockIdx.z];
+  const int L = g.num_layers;
+  uint8_t* out_buf = smem + S * CHAIN_STAGE_BYTES;
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int l = 0; l < L; ++l) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&Ls[l].map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&Ls[l].map_w) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&Ls[l].map_y) : "memory");
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  int it_p = 0, it_m = 0;          // ring positions of the producer / the MMA issuer: they run on across the layers
+  for (int l = 0; l < L; ++l) {
+    const ChainLayer& C = Ls[l];
+    const int nkb = C.nkb, n_tile = C.n_tile, n0 = (int)crank * n_tile;
+    if (warp == 0) {
+      // ===== TMA producer =====
+      if (elect_one()) {
+        auto load_w = [&](const ChainLayer& D, int kb, int itx) {   // claims ring slot itx for k-block kb of layer D: weight slice now
+          const int s = itx % S, u = itx / S;
+          if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
+          mbar_expect_tx(&full_bar[s], (uint32_t)(A_STAGE_BYTES + D.n_tile * BK * 2));
+          tma_load_2d(smem + s * CHAIN_STAGE_BYTES + A_STAGE_BYTES, &D.map_w, kb * BK, (int)crank * D.n_tile, &full_bar[s]);
+        };
+        const int pre = nkb < S ? nkb : S;   // k-blocks whose weight slices were requested ahead (before the data they multiply existed)
+        if (l == 0) {
+          for (int kb = 0; kb < pre; ++kb) load_w(C, kb, it_p + kb);
+          if (g.overlap_prev) griddep_wait();                 // the input cast is the previous kernel in the stream
+        } else {
+          asm volatile("fence.proxy.async;" ::: "memory");    // peers' TMA stores (ordered by the cluster barrier) before our TMA loads
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int itx = it_p + kb;
+          if (kb >= pre) load_w(C, kb, itx);
+          tma_load_2d(smem + (itx % S) * CHAIN_STAGE_BYTES, &C.map_x, kb * BK, m0, &full_bar[itx % S]);
+        }
+        if (l + 1 < L) {          // the next layer's first weight slices: in flight while this layer computes and stores
+          const ChainLayer& D = Ls[l + 1];
+          const int pre1 = D.nkb < S ? D.nkb : S;
+          for (int kb = 0; kb < pre1; ++kb) load_w(D, kb, it_p + nkb + kb);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ===== MMA issuer =====
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_bf16(n_tile);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int itx = it_m + kb, s = itx % S, u = itx / S;
+          mbar_wait(&full_bar[s], (uint32_t)(u & 1));
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * CHAIN_STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j)
+            umma_bf16(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_bar);
+      }
+      __syncwarp();
+    } else {
+      // ===== epilogue warps: TMEM lane quarter = warp % 4, two warps per quarter split the columns =====
+      mbar_wait(&acc_bar, (uint32_t)(l & 1));
+      tc_fence_after();
+      const int q = warp & 3, half = (warp - 2) >> 2;
+      const int row = q * 32 + lane;
+      const int sub_cols = (C.epilogue == 0) ? 32 : 64;
+      int cb = 0, ce = half ? 0 : n_tile;
+      if (n_tile >= 2 * sub_cols) { cb = half ? n_tile / 2 : 0; ce = half ? n_tile : n_tile / 2; }
+      mmb_mlp_layer_params p = {};
+      p.M = g.M; p.N = C.N; p.epilogue = C.epilogue; p.bias = C.bias;
+      uint8_t* buf = out_buf + half * (BM * 128);
+      if (cb < ce) {
+        epilogue_row_staged(p, tmem + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, buf, [&](int j) {
+          fence_async_smem();
+          if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (q == 0 && lane == 0) {
+            tma_store_2d(&C.map_y, buf, n0 + j * sub_cols, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            tma_store_wait_read();
+          }
+          if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+        }, 0);
+        // the slice must have LANDED (not only left shared memory) before the peers are told to read it
+        if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+    }
+    it_p += nkb;
+    it_m += nkb;
+    if (l + 1 < L) {             // layer boundary: every thread of the four CTAs (release / acquire at cluster scope)
+      tc_fence_before();
+      cluster_sync_all();
+      tc_fence_after();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
 // ---- host: 2-D tensor maps (rows x Kpad bf16, box = box_rows x 64, SWIZZLE_128B) through the driver entry point ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1094,6 +1249,84 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
     }
     if (le != cudaSuccess) {
       if (getenv("MMB_DEBUG")) fprintf(stderr, "mmb_mlp_layer: launch failed: %s (cluster %d, pair %d, smem %d)\n", cudaGetErrorString(le), cm, (int)pair, smem);
+      (void)cudaGetLastError();
+      return MMB_ECUDA;
+    }
+  }
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
+
+extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, void* stream) {
+  if (!layers || num_layers < 2 || num_layers > MMB_MLP_MAX_LAYERS || count < 1) return MMB_EINVAL;
+  if (count > CHAIN_MAX_NETS) return MMB_EUNSUPPORTED;
+  static thread_local ChainArgs g;
+  const mmb_mlp_layer_params& f = layers[0];
+  if (f.M <= 0 || f.Mpad % BM || f.Mpad < f.M) return MMB_EINVAL;
+  for (int a = 0; a < count; ++a) {
+    for (int l = 0; l < num_layers; ++l) {
+      const mmb_mlp_layer_params& p = layers[a * num_layers + l];
+      const mmb_mlp_layer_params& r = layers[l];                       // network 0 defines the geometry
+      if (!p.x || !p.w || !p.bias || !p.y || p.M != f.M || p.Mpad != f.Mpad || p.N <= 0 || p.K <= 0) return MMB_EINVAL;
+      if (p.N != r.N || p.K != r.K || p.Kpad != r.Kpad || p.epilogue != r.epilogue || p.y_stride != r.y_stride) return MMB_EINVAL;
+      if (p.Kpad % BK || p.Kpad < p.K) return MMB_EINVAL;
+      if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.y)) & 15u) return MMB_EALIGN;
+      const bool last = l == num_layers - 1;
+      ChainLayer& c = g.l[a][l];
+      c.bias = p.bias; c.N = p.N; c.nkb = p.Kpad / BK; c.epilogue = p.epilogue;
+      if (!last) {
+        // hidden layer: bias + ELU -> bf16, the next layer's operand; its four column slices must be whole 64-column sub-tiles
+        if (p.epilogue != 1 || p.N % (CHAIN_CLUSTER * 64) || p.N > CHAIN_CLUSTER * 256) return MMB_EUNSUPPORTED;
+        const mmb_mlp_layer_params& nx = layers[a * num_layers + l + 1];
+        if (nx.x != p.y || nx.Kpad != p.y_stride || p.y_stride < p.N || p.y_stride % 8) return MMB_EINVAL;
+        c.n_tile = p.N / CHAIN_CLUSTER;
+        if (!make_map_bf16_2d(&c.map_y, p.y, (uint64_t)p.Mpad, (uint64_t)p.y_stride, BM)) return MMB_ECUDA;
+      } else {
+        // last layer: bias -> fp32 [M][N], TMA-addressable; the cluster splits round_up(N, 128) columns
+        if (p.epilogue != 0 || (p.y_stride & 3) || p.y_stride < p.N) return MMB_EUNSUPPORTED;
+        const int npad = (p.N + 127) / 128 * 128;
+        if (npad > CHAIN_CLUSTER * 256) return MMB_EUNSUPPORTED;
+        c.n_tile = npad / CHAIN_CLUSTER;
+        if (!make_map_f32_out(&c.map_y, p.y, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.y_stride)) return MMB_ECUDA;
+      }
+      // weights [Npad rows >= N][Kpad]: slices beyond the allocated rows are zero-filled by the TMA (out-of-bounds box rows)
+      if (p.Npad < p.N) return MMB_EINVAL;
+      if (!make_map_bf16_2d(&c.map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
+          !make_map_bf16_2d(&c.map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)c.n_tile))
+        return MMB_ECUDA;
+    }
+  }
+  g.num_layers = num_layers; g.M = f.M; g.overlap_prev = f.overlap_prev;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= MMB_MAX_DEVICES) return MMB_EUNSUPPORTED;
+  static bool attr_done[MMB_MAX_DEVICES] = {};
+  if (!attr_done[dev]) {
+    if (cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) != cudaSuccess) return MMB_ECUDA;
+    attr_done[dev] = true;
+  }
+  {
+    LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CHAIN_CLUSTER * (f.Mpad / BM), 1, count);
+    cfg.blockDim = dim3(WS_THREADS);
+    cfg.dynamicSmemBytes = CHAIN_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CHAIN_CLUSTER; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (f.overlap_prev) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, mlp_chain_kernel, g);
+    if (le != cudaSuccess) {
+      if (getenv("MMB_DEBUG")) fprintf(stderr, "mmb_mlp_chain: launch failed: %s\n", cudaGetErrorString(le));
       (void)cudaGetLastError();
       return MMB_ECUDA;
     }

@@ -17,6 +17,7 @@ as one grouped launch per layer), `GroupedMLP` / `MarlTeamForward` (all agents' 
 Numerics: bf16 operands, fp32 accumulation and fp32 bias / ELU / LayerNorm; the reference is fp32 SGEMM, so
 outputs agree to bf16 operand precision (tests/test_gpu_mlp.py states the tolerances).
 """
+import os
 from typing import List, Optional
 
 import torch
@@ -90,6 +91,25 @@ class _Layer:
             self.gamma.copy_(self.ln[0].detach(), non_blocking=True)
             self.beta.copy_(self.ln[1].detach(), non_blocking=True)
         self._ver = tuple(t._version for t in self._sources())
+
+
+_CHAIN_ENABLED = os.environ.get("MMB_MLP_CHAIN", "1") != "0"
+
+
+def _chain_launch(owner, arr, num_layers, count, stream):
+    """The whole chain in ONE launch (`mmb_mlp_chain`: a cluster of 4 CTAs per 128-row block walks all layers) when the
+    geometry allows it - plain Linear-ELU chains with hidden widths that are multiples of 256 (the PPO networks) - else False
+    and the caller launches layer by layer.  The verdict of the library is remembered per object."""
+    if not _CHAIN_ENABLED or owner.__dict__.get("_chain_ok") is False or num_layers < 2:
+        return False
+    rc = L.lib().mmb_mlp_chain(arr, num_layers, count, stream)
+    if rc == 0:
+        owner._chain_ok = True
+        return True
+    if rc != -4:                      # MMB_EUNSUPPORTED: geometry outside the fused kernel; anything else is an error
+        L.check(rc, "mmb_mlp_chain")
+    owner._chain_ok = False
+    return False
 
 
 class FusedMLP:
@@ -223,19 +243,24 @@ class FusedMLP:
                                 L.ptr(acts[0]), st), "mmb_ln_cast")
         if out is None:
             out = torch.empty(M, self.out_dim, dtype=torch.float32, device=self.device)
+        nl = len(self.layers)
+        arr = (L.MlpLayerParams * nl)()
         for i, l in enumerate(self.layers):
-            p = L.MlpLayerParams()
+            p = arr[i]
             p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = (M, l.N, l.K, Mpad, l.Kpad, l.Npad,
                                                                                  self._n_tile(l, Mpad), l.epilogue)
             p.x, p.w, p.bias = L.ptr(acts[i]), L.ptr(l.w), L.ptr(l.bias)
             if l.epilogue == 2:
                 p.ln_gamma, p.ln_beta, p.ln_eps = L.ptr(l.gamma), L.ptr(l.beta), l.eps
             p.overlap_prev = 1        # the predecessor in the stream is ln_cast / the previous layer: never writes weights
-            if i == len(self.layers) - 1:
+            if i == nl - 1:
                 p.y, p.y_stride = L.ptr(out), out.stride(0)
             else:
                 p.y, p.y_stride = L.ptr(acts[i + 1]), acts[i + 1].stride(0)
-            L.check(lib.mmb_mlp_layer(p, st), "mmb_mlp_layer")
+        if _chain_launch(self, arr, nl, 1, st):
+            return out
+        for i in range(nl):
+            L.check(lib.mmb_mlp_layer(arr[i], st), "mmb_mlp_layer")
         return out
 
     __call__ = forward
@@ -299,20 +324,31 @@ class GroupedMLP:
         if out is None:
             out = torch.empty(G, M, self.out_dim, dtype=torch.float32, device=self.device)
         nl = len(a0.layers)
+
+        def fill(p, g, i):
+            l = self.mlps[g].layers[i]
+            p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = (M, l.N, l.K, Mpad, l.Kpad, l.Npad,
+                                                                             FusedMLP._n_tile(l, Mpad * G), l.epilogue)
+            p.x, p.w, p.bias = acts[i][g].data_ptr(), l.w.data_ptr(), l.bias.data_ptr()
+            if l.epilogue == 2:
+                p.ln_gamma, p.ln_beta, p.ln_eps = l.gamma.data_ptr(), l.beta.data_ptr(), l.eps
+            p.overlap_prev = 1
+            if i == nl - 1:
+                p.y, p.y_stride = out[g].data_ptr(), out.stride(1)
+            else:
+                p.y, p.y_stride = acts[i + 1][g].data_ptr(), acts[i + 1].stride(1)
+
+        if G <= 2 and self.__dict__.get("_chain_ok") is not False:       # network-major array: [G][layers]
+            net_major = (L.MlpLayerParams * (G * nl))()
+            for g in range(G):
+                for i in range(nl):
+                    fill(net_major[g * nl + i], g, i)
+            if _chain_launch(self, net_major, nl, G, st):
+                return out
         for i in range(nl):
             arr = (L.MlpLayerParams * G)()
-            for g, m in enumerate(self.mlps):
-                l, p = m.layers[i], arr[g]
-                p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = (M, l.N, l.K, Mpad, l.Kpad, l.Npad,
-                                                                                 FusedMLP._n_tile(l, Mpad * G), l.epilogue)
-                p.x, p.w, p.bias = acts[i][g].data_ptr(), l.w.data_ptr(), l.bias.data_ptr()
-                if l.epilogue == 2:
-                    p.ln_gamma, p.ln_beta, p.ln_eps = l.gamma.data_ptr(), l.beta.data_ptr(), l.eps
-                p.overlap_prev = 1
-                if i == nl - 1:
-                    p.y, p.y_stride = out[g].data_ptr(), out.stride(1)
-                else:
-                    p.y, p.y_stride = acts[i + 1][g].data_ptr(), acts[i + 1].stride(1)
+            for g in range(G):
+                fill(arr[g], g, i)
             L.check(lib.mmb_mlp_layer_group(arr, G, st), "mmb_mlp_layer_group")
         return out
 

@@ -331,3 +331,39 @@ def test_forward_follows_the_parameters_across_optimizer_steps(cuda_device):
     _, a1, _ = pol.get_actions(share, o, deterministic=True)
     assert torch.allclose(a1, a0 + 0.25, atol=1e-6)
     assert torch.allclose(pol.std, torch.sigmoid(sd["act.action_out.log_std"].detach()) * 0.5)
+
+
+@pytest.mark.parametrize("M", [1, 130, 4096, 5000])
+def test_single_launch_chain_equals_layer_by_layer(cuda_device, M):
+    """`mmb_mlp_chain` (one launch: clusters of 4 CTAs walk all layers, cluster barrier at the layer boundaries) gives the
+    numbers of the layer-by-layer launches bit for bit - same operands, same k order, same epilogue - for one network and
+    for the actor / critic pair; geometries outside the fused kernel fall back silently."""
+    from massive_marl_benchmark_b200 import mlp as mm
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(M)
+    torch.manual_seed(M)
+    actor = _ppo_net(388, [1024, 1024, 512], 80, 0.01, gen).to(dev)
+    critic = _ppo_net(388, [1024, 1024, 512], 80, 1.0, gen).to(dev)
+    x = torch.clamp(torch.randn(M, 388, generator=gen) * 2.0, -5, 5).to(dev)
+    outs = {}
+    for chain in (True, False):
+        mm._CHAIN_ENABLED = chain
+        fa, fc = mm.FusedMLP.from_sequential(actor, dev), mm.FusedMLP.from_sequential(critic, dev)
+        y = fa(x)
+        pair = mm.GroupedMLP([fa, fc])([x, x])
+        torch.cuda.synchronize()
+        assert fa.__dict__.get("_chain_ok") is (True if chain else None)
+        outs[chain] = (y.clone(), pair.clone())
+    mm._CHAIN_ENABLED = True
+    assert torch.equal(outs[True][0], outs[False][0]), float((outs[True][0] - outs[False][0]).abs().max())
+    assert torch.equal(outs[True][1], outs[False][1])
+    with torch.no_grad():
+        assert _rowmax_err(outs[True][0], actor(x)) <= 3e-2
+    # a geometry the fused kernel does not take (hidden width 96): falls back, same interface
+    small = _ppo_net(60, [96, 96], 8, 0.5, gen).to(dev)
+    fs = mm.FusedMLP.from_sequential(small, dev)
+    xs = torch.randn(M, 60, generator=gen).to(dev)
+    ys = fs(xs)
+    assert fs._chain_ok is False
+    with torch.no_grad():
+        assert _rowmax_err(ys, small(xs)) <= 3e-2
