@@ -308,19 +308,26 @@ class GroupedMLP:
             self.refresh()
         if isinstance(xs, torch.Tensor):
             xs = [xs[g] for g in range(self.G)]
-        xs = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in xs]
+        shared_input = all(x is xs[0] for x in xs)           # e.g. actor and critic of one policy on the same observations
+        xs = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in ([xs[0]] if shared_input else xs)]
         M = xs[0].shape[0]
         Mpad, acts = self._buffers(M)
         a0 = self.mlps[0]
         lib, st, G = L.lib(), L.stream_ptr(), self.G
-        vp = C.c_void_p * G
         l0 = a0.layers[0]
         use_ln = a0.in_ln is not None
-        L.check(lib.mmb_ln_cast_group(vp(*[x.data_ptr() for x in xs]), G, M, Mpad, l0.K, l0.Kpad,
-                                      vp(*[m.in_gamma.data_ptr() for m in self.mlps]) if use_ln else None,
-                                      vp(*[m.in_beta.data_ptr() for m in self.mlps]) if use_ln else None,
-                                      a0.in_eps if use_ln else 0.0, int(use_ln), vp(*[acts[0][g].data_ptr() for g in range(G)]), st),
-                "mmb_ln_cast_group")
+        shared_input = shared_input and not use_ln           # per-network input LayerNorms make the operands differ
+        if shared_input:                                     # one cast serves every network: slot 0 of the first operand buffer
+            L.check(lib.mmb_ln_cast(xs[0].data_ptr(), M, Mpad, l0.K, l0.Kpad, None, None, 0.0, 0, acts[0][0].data_ptr(), st), "mmb_ln_cast")
+        else:
+            if len(xs) != G:
+                xs = xs * G
+            vp = C.c_void_p * G
+            L.check(lib.mmb_ln_cast_group(vp(*[x.data_ptr() for x in xs]), G, M, Mpad, l0.K, l0.Kpad,
+                                          vp(*[m.in_gamma.data_ptr() for m in self.mlps]) if use_ln else None,
+                                          vp(*[m.in_beta.data_ptr() for m in self.mlps]) if use_ln else None,
+                                          a0.in_eps if use_ln else 0.0, int(use_ln), vp(*[acts[0][g].data_ptr() for g in range(G)]), st),
+                    "mmb_ln_cast_group")
         if out is None:
             out = torch.empty(G, M, self.out_dim, dtype=torch.float32, device=self.device)
         nl = len(a0.layers)
@@ -329,7 +336,7 @@ class GroupedMLP:
             l = self.mlps[g].layers[i]
             p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = (M, l.N, l.K, Mpad, l.Kpad, l.Npad,
                                                                              FusedMLP._n_tile(l, Mpad * G), l.epilogue)
-            p.x, p.w, p.bias = acts[i][g].data_ptr(), l.w.data_ptr(), l.bias.data_ptr()
+            p.x, p.w, p.bias = acts[i][0 if (i == 0 and shared_input) else g].data_ptr(), l.w.data_ptr(), l.bias.data_ptr()
             if l.epilogue == 2:
                 p.ln_gamma, p.ln_beta, p.ln_eps = l.gamma.data_ptr(), l.beta.data_ptr(), l.eps
             p.overlap_prev = 1
