@@ -163,6 +163,9 @@ typedef struct {
    * overlap_prev the next rollout's head runs under this rollout's tail without stalling.  NULL: frame 0 reads the carry
    * arrays (and, with overlap_prev, waits for the preceding kernel).  Role-split kernel only. */
   const float* prev_root;
+  /* Optional, T == 1: the ten per-agent action tensors [N][8] exactly as the policies return them, instead of `actions`
+   * (which must then be NULL): the hstack of multi_vec_task.py:94-103 is never materialised.  Role-split kernel only. */
+  const float* agent_actions[10];
   const float* gae_values;  int64_t gae_values_frame_stride;         /* [T][N] */
   const float* gae_last_values;                                      /* [N] */
   float* gae_returns;       int64_t gae_returns_frame_stride;        /* [T][N] */
@@ -281,6 +284,10 @@ typedef struct {
 } mmb_reset_params;
 
 MMB_API int32_t mmb_reset_compact(const mmb_reset_params* p, void* stream);
+
+/* TenAnt.post_physics_step as ONE host call (ten_ant.py:894-926): mmb_reset_compact(reset) followed by
+ * mmb_ten_ant_step(step) on `stream` - the interactive per-step path is bound by host time per call, not by the kernels. */
+MMB_API int32_t mmb_ten_ant_env_step(const mmb_reset_params* reset, const mmb_ten_ant_params* step, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Rollout storage: PPO (agents/algorithms/rl/ppo/storage.py)                                    */

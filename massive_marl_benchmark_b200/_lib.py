@@ -42,7 +42,7 @@ class TenAntParams(C.Structure):
         ("share_obs", c_vp), ("share_obs_frame_stride", c_i64), ("rewards", c_vp), ("rewards_frame_stride", c_i64),
         ("dones_i64", c_vp), ("dones_i64_frame_stride", c_i64), ("dones_u8", c_vp), ("dones_u8_frame_stride", c_i64),
         ("forces", c_vp), ("forces_frame_stride", c_i64), ("scratch", c_vp), ("overlap_prev", c_i32), ("scratch_per_set", c_i32),
-        ("obs_agent_stride", c_i64), ("prev_root", c_vp),
+        ("obs_agent_stride", c_i64), ("prev_root", c_vp), ("agent_actions", c_vp * 10),
         ("gae_values", c_vp), ("gae_values_frame_stride", c_i64), ("gae_last_values", c_vp),
         ("gae_returns", c_vp), ("gae_returns_frame_stride", c_i64),
         ("gae_advantages", c_vp), ("gae_advantages_frame_stride", c_i64),
@@ -197,6 +197,7 @@ SYMBOLS = {
     "mmb_one_ant_step": (c_i32, [C.POINTER(OneAntParams), c_vp]),
     "mmb_ingenuity_step": (c_i32, [C.POINTER(IngenuityParams), c_vp]),
     "mmb_reset_compact": (c_i32, [C.POINTER(ResetParams), c_vp]),
+    "mmb_ten_ant_env_step": (c_i32, [C.POINTER(ResetParams), C.POINTER(TenAntParams), c_vp]),
     "mmb_rollout_add": (c_i32, [C.POINTER(RolloutAddParams), c_vp]),
     "mmb_gae_ppo": (c_i32, [C.POINTER(GaePpoParams), c_vp]),
     "mmb_adv_normalize": (c_i32, [c_vp, c_i64, c_vp, c_f, c_i32, c_vp]),

@@ -357,6 +357,10 @@ __device__ __forceinline__ void prefetch_unit(const mmb_ten_ant_params& p, int64
   if (t2 >= p.num_frames || (tile2 + 1) * EPT > p.num_envs) return;
   const float* r2 = p.root + t2 * p.root_frame_stride + tile2 * EPT * ROOT_ENV;
   const float* d2 = p.dof + t2 * p.dof_frame_stride + tile2 * EPT * 160;
+  if (!p.actions) {          // per-agent action tensors (T == 1): ten short rows per env, not worth a bulk prefetch
+    if (aligned16(r2) && aligned16(d2)) { tma_prefetch_l2(r2, EPT * ROOT_ENV * 4); tma_prefetch_l2(d2, EPT * 160 * 4); }
+    return;
+  }
   const float* a2 = p.actions + t2 * p.actions_frame_stride + tile2 * EPT * 80;
   if (aligned16(r2) && aligned16(d2) && aligned16(a2)) {
     tma_prefetch_l2(r2, EPT * ROOT_ENV * 4);
@@ -722,7 +726,10 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
     float gbx = 0.f, gby = 0.f;
     if (active) {
       const float* d = p.dof + (int64_t)t * p.dof_frame_stride + ((int64_t)e * 80 + 8 * k) * 2;
-      const float* ac = p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
+      // actions: one [N][80] tensor, or (per-step multi-agent path) the ten per-agent [N][8] tensors as they come from the
+      // policies - the hstack of multi_vec_task.py:94-103 never materialises
+      const float* ac = p.agent_actions[0] ? p.agent_actions[k] + (int64_t)e * 8
+                                           : p.actions + (int64_t)t * p.actions_frame_stride + (int64_t)e * 80 + 8 * k;
       if (aligned16(d) && aligned16(ac)) {
         float4 v[4], w0, w1;
 #pragma unroll
@@ -1120,9 +1127,15 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
   if (!pp) return MMB_EINVAL;
   mmb_ten_ant_params p = *pp;
   if (p.num_envs <= 0 || p.num_frames <= 0) return MMB_EINVAL;
-  if (!p.root || !p.dof || !p.actions || !p.pos_before || !p.goal_before || !p.box_before || !p.progress_buf ||
-      !p.reset_buf)
+  if (!p.root || !p.dof || !p.pos_before || !p.goal_before || !p.box_before || !p.progress_buf || !p.reset_buf)
     return MMB_EINVAL;
+  if (p.agent_actions[0]) {    // ten per-agent [N][8] tensors instead of `actions`: single-frame launches of the role-split kernel
+    if (p.num_frames != 1 || p.actions) return MMB_EINVAL;
+    for (int k = 0; k < 10; ++k)
+      if (!p.agent_actions[k]) return MMB_EINVAL;
+  } else if (!p.actions) {
+    return MMB_EINVAL;
+  }
   if (p.num_frames > 65535) return MMB_EUNSUPPORTED;
   if (p.num_frames > 1 && !p.dones_u8 && !p.dones_i64) return MMB_EINVAL;  // the chain needs a [T][N] plane
   if (p.obs_layout < 0 || p.obs_layout > 2) return MMB_EINVAL;
@@ -1140,7 +1153,7 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
   // kernel variant: "split" (two threads per ant, default) or "mono" (one thread per ant; MMB_TEN_ANT_VARIANT=mono)
   static const bool split = [] { const char* v = getenv("MMB_TEN_ANT_VARIANT"); return !(v && v[0] == 'm'); }();
   int32_t rc;
-  if (p.gae_values && !split) return MMB_EUNSUPPORTED;   // the one-thread-per-ant variant has no fused GAE
+  if ((p.gae_values || p.agent_actions[0]) && !split) return MMB_EUNSUPPORTED;   // role-split kernel only
   if (split)
     rc = (p.flavor == MMB_FLAVOR_CUDA) ? launch_ten_ant_split<FLAVOR_CUDA>(p, st) : launch_ten_ant_split<FLAVOR_CPU>(p, st);
   else if (ept == 16)
@@ -1155,6 +1168,15 @@ extern "C" int32_t mmb_ten_ant_step(const mmb_ten_ant_params* pp, void* stream) 
     if (cudaGetLastError() != cudaSuccess) return MMB_ECUDA;
   }
   return MMB_OK;
+}
+
+// One host call for the interactive per-step path: reset_idx of the flagged envs, then the step (TenAnt.post_physics_step,
+// ten_ant.py:894-926).  Two launches, one ABI transition: at N = 4096 the step is host-bound, not kernel-bound.
+extern "C" int32_t mmb_ten_ant_env_step(const mmb_reset_params* reset, const mmb_ten_ant_params* step, void* stream) {
+  if (!reset || !step) return MMB_EINVAL;
+  const int32_t rc = mmb_reset_compact(reset, stream);
+  if (rc != MMB_OK) return rc;
+  return mmb_ten_ant_step(step, stream);
 }
 
 #ifdef MMB_TRACE

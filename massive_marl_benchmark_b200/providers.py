@@ -56,6 +56,7 @@ class ReplayProvider(FrameProvider):
                        if k in self.keys and v is not None}
         self.loop = loop
         self._F = next(iter(self.frames.values())).shape[0]
+        self._views = [None] * self._F       # per-frame dicts of views, built on first use (the per-step path is host-bound)
 
     @property
     def num_frames(self):
@@ -67,7 +68,10 @@ class ReplayProvider(FrameProvider):
         i = self.cursor % self._F if self.loop else self.cursor
         if i >= self._F:
             raise IndexError("replay exhausted (%d frames)" % self._F)
-        return {k: v[i] for k, v in self.frames.items()}
+        fr = self._views[i]
+        if fr is None:
+            fr = self._views[i] = {k: v[i] for k, v in self.frames.items()}
+        return fr
 
     def window(self, start, length):
         """`length` consecutive frames starting at `start` as [T, ...] views (horizon-batched launches)."""

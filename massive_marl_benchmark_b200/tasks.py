@@ -66,7 +66,8 @@ class BaseTask:
         self.rew_buf = torch.zeros(N, device=dev, dtype=torch.float)
         self.reset_buf = torch.ones(N, device=dev, dtype=torch.long)
         self.progress_buf = torch.zeros(N, device=dev, dtype=torch.long)
-        self.randomize_buf = torch.zeros(N, device=dev, dtype=torch.long)
+        self._randomize_buf = torch.zeros(N, device=dev, dtype=torch.long)
+        self._randomize_pending = 0      # `randomize_buf += 1` of every step, applied when somebody looks (see the property)
         self.extras = {}
         self.provider = provider
         self.flavor = flavor
@@ -81,6 +82,20 @@ class BaseTask:
         self._step_count = 0
         L.lib()  # fail here, loudly, if the CUDA library is missing
 
+    @property
+    def randomize_buf(self):
+        """base_task.py:67 / ten_ant.py:897: a per-env step counter only domain randomisation reads (out of scope).  The
+        per-step `+= 1` is a torch launch the host-bound step path can do without: increments are counted on the host and
+        applied when the buffer is read."""
+        if self._randomize_pending:
+            self._randomize_buf += self._randomize_pending
+            self._randomize_pending = 0
+        return self._randomize_buf
+
+    @randomize_buf.setter
+    def randomize_buf(self, value):
+        self._randomize_buf, self._randomize_pending = value, 0
+
     def step(self, actions):
         self.pre_physics_step(actions)
         for _ in range(self.control_freq_inv):
@@ -90,8 +105,11 @@ class BaseTask:
     def get_states(self):
         return self.states_buf
 
+    _agent_actions = None
+
     def pre_physics_step(self, actions):
         # forces are produced by the fused step kernel from the same read of `actions`
+        self._agent_actions = None
         self.actions = actions if actions.device == self.rew_buf.device else actions.to(self.device)
         if not self.actions.is_contiguous():
             self.actions = self.actions.contiguous()
@@ -157,6 +175,12 @@ class TenAnt(BaseTask):
     # -- reference method names ---------------------------------------------------------------
     def reset_idx(self, env_ids=None):
         """ten_ant.py:810-884 for the envs flagged in `reset_buf` (env_ids is recomputed on the device)."""
+        p = self._reset_params()
+        L.check(L.lib().mmb_reset_compact(p, L.stream_ptr()), "mmb_reset_compact")
+        self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
+        self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
+
+    def _reset_params(self):
         p = self._p_reset
         if p is None:   # built once: only the noise source and the step counter change between calls
             p = self._p_reset = L.ResetParams()
@@ -174,9 +198,7 @@ class TenAnt(BaseTask):
             p.noise_pos, p.noise_vel = L.ptr(self._noise_keep[0]), L.ptr(self._noise_keep[1])
         else:
             p.noise_mode, p.step = 1, self._step_count
-        L.check(L.lib().mmb_reset_compact(p, L.stream_ptr()), "mmb_reset_compact")
-        self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
-        self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
+        return p
 
     def _prev_root_for_replay(self):
         """The frame that preceded the replay = the task's current `root_states` (the last frame processed, or the initial
@@ -188,6 +210,32 @@ class TenAnt(BaseTask):
             return None
         self._prev_root_keep = r
         return r
+
+    def step_agent_actions(self, action_list):
+        """`step` for the ten per-agent (N, 8) action tensors of MultiVecTaskPython.step (multi_vec_task.py:94-103 hstacks
+        them first): the kernel reads them through a pointer list, `task.actions` becomes a lazy hstack nobody pays for unless
+        it is read."""
+        dev = self.rew_buf.device
+        al = [a if (a.device == dev and a.dtype == torch.float32 and a.is_contiguous()) else a.to(dev, torch.float32).contiguous()
+              for a in action_list]
+        if len(al) != 10 or any(a.shape != (self.num_envs, 8) for a in al) or _TEN_ANT_MONO:
+            return self.step(torch.cat(tuple(al), dim=1))
+        self._agent_actions, self._actions_cat = al, None
+        for _ in range(self.control_freq_inv):
+            self.provider.simulate()
+        self.post_physics_step()
+
+    @property
+    def actions(self):
+        if self._agent_actions is not None:
+            if self._actions_cat is None:
+                self._actions_cat = torch.cat(tuple(self._agent_actions), dim=1)
+            return self._actions_cat
+        return self._actions_t
+
+    @actions.setter
+    def actions(self, value):
+        self._actions_t = value
 
     def chain_errors(self) -> int:
         """Horizon-batched launches whose in-kernel progress / reset chain gave up waiting for a frame's report (~1 s:
@@ -233,10 +281,8 @@ class TenAnt(BaseTask):
 
     def post_physics_step(self):
         """ten_ant.py:894-926 (+ the fused pre_physics force scaling and wrapper clamps)."""
-        self.randomize_buf += 1
-        self.reset_idx()
+        self._randomize_pending += 1
         fr = self.provider.frame()
-        self.root_states, self.dof_state = fr["root"], fr["dof"]
         if self.obs_layout == 0:
             obs = self.obs_clamped = self._fresh_out(self.num_envs, 388)
             share = None
@@ -252,12 +298,28 @@ class TenAnt(BaseTask):
             p.rewards, p.forces = L.ptr(self.rew_buf), L.ptr(self.forces)
             p.c = self.consts
         p.obs_layout, p.clip_actions, p.clip_obs = self.obs_layout, self.clip_actions, self.clip_obs
-        p.root, p.dof, p.actions = self.root_states.data_ptr(), self.dof_state.data_ptr(), self.actions.data_ptr()
+        self.root_states, self.dof_state = fr["root"], fr["dof"]
+        p.root, p.dof = self.root_states.data_ptr(), self.dof_state.data_ptr()
+        al = self._agent_actions
+        if al is not None:               # ten per-agent tensors: pointers go to the kernel, no hstack
+            p.actions = None
+            for k in range(10):
+                p.agent_actions[k] = al[k].data_ptr()
+        else:
+            p.actions = self.actions.data_ptr()
+            if p.agent_actions[0]:
+                for k in range(10):
+                    p.agent_actions[k] = None
         p.obs_raw = self.obs_buf.data_ptr() if self.keep_raw_obs else None
         p.obs = obs.data_ptr()
         p.share_obs = share.data_ptr() if share is not None else None
-        L.check(L.lib().mmb_ten_ant_step(p, L.stream_ptr()), "mmb_ten_ant_step")
-        self.provider.set_dof_actuation_force_tensor(self.forces)
+        # reset_idx of the flagged envs (ten_ant.py:899-901) and the step in ONE host call (mmb_ten_ant_env_step)
+        pr = self._reset_params()
+        L.check(L.lib().mmb_ten_ant_env_step(pr, p, L.stream_ptr()), "mmb_ten_ant_env_step")
+        prov = self.provider
+        prov.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
+        prov.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
+        prov.set_dof_actuation_force_tensor(self.forces)
         self._step_count += 1
 
     def compute_observations(self):
@@ -401,7 +463,7 @@ class OneAnt(BaseTask):
 
     def post_physics_step(self):
         """one_ant.py:403-415"""
-        self.randomize_buf += 1
+        self._randomize_pending += 1
         self.reset_idx()
         fr = self.provider.frame()
         self.root_states, self.dof_state = fr["root"], fr["dof"]

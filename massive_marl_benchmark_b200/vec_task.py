@@ -80,9 +80,17 @@ class VecTaskPython(VecTask):
         return torch.clamp(self.task.states_buf, -self.clip_obs, self.clip_obs).to(self.rl_device)
 
     def step(self, actions):
-        self.task.step(actions)  # clamp(actions), obs/reward/reset, clamp(obs): one fused launch
-        return (self.task.obs_clamped.to(self.rl_device), self.task.rew_buf.to(self.rl_device),
-                self.task.reset_buf.to(self.rl_device), self.task.extras)
+        t = self.task
+        t.step(actions)  # clamp(actions), obs/reward/reset, clamp(obs): one fused launch
+        if self._same_device(t):     # `.to(rl_device)` is the identity then; three dispatcher round trips less per step
+            return t.obs_clamped, t.rew_buf, t.reset_buf, t.extras
+        return (t.obs_clamped.to(self.rl_device), t.rew_buf.to(self.rl_device), t.reset_buf.to(self.rl_device), t.extras)
+
+    def _same_device(self, t):
+        same = self.__dict__.get("_same_dev")
+        if same is None:
+            same = self._same_dev = torch.device(self.rl_device) == t.rew_buf.device
+        return same
 
     def reset(self):
         actions = 0.01 * (1 - 2 * torch.rand([self.task.num_envs, self.task.num_actions], dtype=torch.float32,
@@ -165,9 +173,12 @@ class MultiVecTaskPython(MultiVecTask):
         return obs_all, state_all
 
     def step(self, actions):
-        if isinstance(actions, (list, tuple)):
-            actions = torch.cat(tuple(actions), dim=1)   # hstack of the per-agent (N, act) tensors
-        self.task.step(actions)
+        if isinstance(actions, (list, tuple)) and hasattr(self.task, "step_agent_actions"):
+            self.task.step_agent_actions(actions)        # the kernel reads the per-agent tensors through a pointer list
+        else:
+            if isinstance(actions, (list, tuple)):
+                actions = torch.cat(tuple(actions), dim=1)   # hstack of the per-agent (N, act) tensors
+            self.task.step(actions)
         N, A = self.num_environments, self.num_agents
         obs_all, state_all = self._views()
         reward_all = self.task.rew_buf.view(N, 1, 1).expand(N, A, 1)
