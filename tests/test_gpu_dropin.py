@@ -202,6 +202,11 @@ def recording_step(a):
     rec["actions"].append(a.detach().clone().cpu())
     return task_step(a)
 task.step = recording_step
+task_step_agents = task.step_agent_actions
+def recording_step_agents(al):                          # the multi-agent wrapper hands the per-agent tensors over unstacked
+    rec["actions"].append(torch.cat([a.detach() for a in al], dim=1).clone().cpu())
+    return task_step_agents(al)
+task.step_agent_actions = recording_step_agents
 torch.manual_seed(0)
 with contextlib.redirect_stdout(io.StringIO()):
     runner = refrunner.Runner(vec_env=env, config=config, model_dir="")
@@ -300,6 +305,11 @@ def recording_step(a):
     rec["actions"].append(a.detach().clone().cpu())
     return task_step(a)
 task.step = recording_step
+task_step_agents = task.step_agent_actions
+def recording_step_agents(al):
+    rec["actions"].append(torch.cat([a.detach() for a in al], dim=1).clone().cpu())
+    return task_step_agents(al)
+task.step_agent_actions = recording_step_agents
 torch.manual_seed(0)
 class Args: algo = ALGO
 with contextlib.redirect_stdout(io.StringIO()):
