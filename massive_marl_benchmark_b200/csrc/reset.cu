@@ -130,6 +130,8 @@ __device__ __forceinline__ void rerandomise_dofs(const mmb_reset_params& p, cons
   }
 }
 
+constexpr int INGENUITY_FILL_CTAS = 8;   // extra CTAs (blockIdx.y >= 1) that spread the all-envs rotor-speed write of MultiIngenuity
+
 __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_reset_params p) {
   __shared__ int warp_tot[RNT / 32];
   __shared__ int s_chunk_total;
@@ -139,6 +141,24 @@ __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_
   const TaskShape sh = shape_of(p.task);
   const int64_t* f64 = p.flags_i64 ? p.flags_i64 + (int64_t)f * p.flags_i64_row_stride : nullptr;
   const uint8_t* f8 = p.flags_u8 ? p.flags_u8 + (int64_t)f * p.flags_u8_row_stride : nullptr;
+  if (blockIdx.y > 0) {
+    // MultiIngenuity only (multi_ingenuity.py:234-241): whenever reset_idx runs - i.e. any flag of the row is set - the rotor
+    // speeds of EVERY env are rewritten.  One CTA doing that for 4 N helicopters (two scattered 4-byte stores each) took ~30 us;
+    // here each fill CTA finds out by itself whether the row has a flag (the flags are a few KB, L2-resident) and writes its
+    // slice.
+    float* dof = p.dof_state ? p.dof_state + (int64_t)f * p.dof_state_row_stride : nullptr;
+    if (!dof) return;
+    int any = 0;
+    for (int e0 = RFPT * tid; e0 < N; e0 += RCHUNK) any |= load_flags16(f64, f8, e0, N) != 0;
+    if (!__syncthreads_or(any)) return;
+    const int fills = gridDim.y - 1, me = blockIdx.y - 1;
+    for (int it = me * RNT + tid; it < N * 4; it += fills * RNT) {
+      float* d = dof + (int64_t)it * 8;  // 4 dofs x (pos, vel) per helicopter
+      d[3] = -50.0f;
+      d[7] = 50.0f;
+    }
+    return;
+  }
   int64_t* env_ids = p.env_ids + (int64_t)f * p.env_ids_row_stride;
   int32_t* ia = p.index_a ? p.index_a + (int64_t)f * p.index_a_row_stride : nullptr;
   int32_t* ib = p.index_b ? p.index_b + (int64_t)f * p.index_b_row_stride : nullptr;
@@ -162,13 +182,7 @@ __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_
   float* dof = p.dof_state ? p.dof_state + (int64_t)f * p.dof_state_row_stride : nullptr;
   if (sh.ants > 0 && dof) rerandomise_dofs(p, sh, f, 0, count, env_ids, dof);
   if (p.task == MMB_TASK_INGENUITY) {
-    if (dof) {  // multi_ingenuity.py:234-241: every env, whenever reset_idx runs
-      for (int it = tid; it < N * 4; it += RNT) {
-        float* d = dof + (int64_t)it * 8;  // 4 dofs x (pos, vel) per helicopter
-        d[3] = -50.0f;
-        d[7] = 50.0f;
-      }
-    }
+    // (the all-envs rotor-speed write of multi_ingenuity.py:234-241 is done by the fill CTAs, blockIdx.y >= 1)
     if (p.forces_state) {  // multi_ingenuity.py:243-244
       const int items = count * 72;
       for (int it = tid; it < items; it += RNT) {
@@ -252,7 +266,8 @@ extern "C" int32_t mmb_reset_compact(const mmb_reset_params* pp, void* stream) {
     if (p.scan_scratch && chunks > 1 && p.task != MMB_TASK_INGENUITY)
       reset_scan_kernel<<<dim3(chunks, p.num_rows), RNT, 0, (cudaStream_t)stream>>>(p);
     else
-      reset_kernel<<<p.num_rows, RNT, 0, (cudaStream_t)stream>>>(p);
+      reset_kernel<<<dim3(p.num_rows, (p.task == MMB_TASK_INGENUITY && p.dof_state) ? 1 + INGENUITY_FILL_CTAS : 1), RNT, 0,
+                     (cudaStream_t)stream>>>(p);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
