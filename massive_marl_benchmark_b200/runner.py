@@ -57,7 +57,12 @@ def process_MultiAgentRL(args, env, config, model_dir=""):
 
 
 class Runner:
-    def __init__(self, vec_env, config, model_dir="", fused_update=False, writer=True):
+    def __init__(self, vec_env, config, model_dir="", fused_update=False, writer=True, team_forward=False, shared_buffer=False):
+        """`team_forward=True`: `collect` evaluates all agents' actors and critics as two grouped tensor-core forwards
+        (`mlp.MarlTeamForward`, bf16 operands; kept in step with the policies' live parameters) instead of 2 x num_agents
+        torch module calls of ~10 kernels each (runner.py:205-217) - at N = 4096 the per-step cost of the reference's loop is
+        those ~300 launches, not the environment.  `shared_buffer=True` (centralised critic only): one `SharedReplayBuffer`
+        for the team - `share_obs` stored once per env, one insert for all agents - whose per-agent views the trainers use."""
         L.lib()
         self.envs = vec_env
         self.eval_envs = vec_env
@@ -113,11 +118,24 @@ class Runner:
                        for a in range(self.num_agents)]
         if self.model_dir != "":
             self.restore()
-        self.trainer, self.buffer = [], []
+        self.trainer, self.buffer, self.shared = [], [], None
+        if shared_buffer:
+            if not self.use_centralized_V:
+                raise ValueError("shared_buffer needs a centralised critic (one share_obs row per env for all agents)")
+            from .shared_buffer import SharedReplayBuffer
+            self.shared = SharedReplayBuffer(config, self.num_agents, self.envs.observation_space[0], cent_space(0),
+                                             self.envs.action_space[0], self.device)
         for a in range(self.num_agents):
             self.trainer.append(TrainAlgo(config, self.policy[a], device=self.device))
-            self.buffer.append(SeparatedReplayBuffer(config, self.envs.observation_space[a], cent_space(a), self.envs.action_space[a],
+            self.buffer.append(self.shared.agent(a) if self.shared is not None else
+                               SeparatedReplayBuffer(config, self.envs.observation_space[a], cent_space(a), self.envs.action_space[a],
                                                      self.device))
+        self.team = None
+        if team_forward:
+            from .mlp import MarlTeamForward
+            head = self.policy[0].actor.act.action_out
+            self.team = MarlTeamForward([p.actor.state_dict() for p in self.policy], [p.critic.state_dict() for p in self.policy],
+                                        std_x_coef=float(head.std_x_coef), std_y_coef=float(head.std_y_coef), device=self.device)
         self.episodes = EpisodeTracker(self.n_rollout_threads, self.device)
         self._finished_before = 0
         self._masks = torch.ones(self.n_rollout_threads, self.num_agents, 1, device=self.device)
@@ -175,12 +193,29 @@ class Runner:
         obs, share_obs, _ = self.envs.reset()
         if not self.use_centralized_V:
             share_obs = obs
+        if self.shared is not None:
+            self.shared.share_obs[0].copy_(share_obs[:, 0])
+            self.shared.obs[:, 0].copy_(obs.transpose(0, 1))
+            return
         for a in range(self.num_agents):
             self.buffer[a].share_obs[0].copy_(share_obs[:, a])
             self.buffer[a].obs[0].copy_(obs[:, a])
 
     @torch.no_grad()
     def collect(self, step):
+        if self.team is not None:
+            # two grouped forwards for the whole team; the rnn states of a feed-forward policy are the zeros it was given
+            A = self.num_agents
+            obs = [self.buffer[a].obs[step] for a in range(A)]
+            share = self.buffer[0].share_obs[step] if (self.use_centralized_V and self.shared is not None) else \
+                [self.buffer[a].share_obs[step] for a in range(A)]
+            if isinstance(share, list):
+                share = torch.stack(share)
+            values, actions, logps = self.team.get_actions(share, obs)           # [A, N, 1], [A, N, act], [A, N, act]
+            self._team_out = (actions, logps)                                    # agent-major: what the shared insert wants
+            b0 = self.buffer[0]
+            rnn = b0.rnn_states[step].unsqueeze(1).expand(-1, A, -1, -1)
+            return values.transpose(0, 1), list(actions.unbind(0)), list(logps.unbind(0)), rnn, rnn
         values, actions, logps, rnn, rnn_c = [], [], [], [], []
         for a in range(self.num_agents):
             self.trainer[a].prep_rollout()
@@ -197,6 +232,17 @@ class Runner:
         runner_insert_masks(dones, self._masks, self._active)             # runner.py:232-241 in one launch
         if not self.use_centralized_V:
             share_obs = obs
+        if self.shared is not None:                                       # the whole team in one insert; share_obs once per env
+            team_out = self.__dict__.pop("_team_out", None)
+            if team_out is not None:                                      # (N, A, .) views of the agent-major forward outputs
+                acts, logps = team_out[0].transpose(0, 1), team_out[1].transpose(0, 1)
+            else:
+                stack = lambda xs: xs if torch.is_tensor(xs) else torch.stack(tuple(xs), dim=1)  # noqa: E731  per-agent list -> (N, A, .)
+                acts, logps = stack(actions), stack(action_log_probs)
+            self.shared.insert(share_obs[:, 0], obs, acts, logps, values, rewards, self._masks, None, self._active)
+            for a in range(self.num_agents):
+                self.buffer[a].step = self.shared.step
+            return
         for a in range(self.num_agents):
             # feed-forward policies return the rnn states they were given (zeros): the planes stay as allocated
             self.buffer[a].insert(share_obs[:, a], obs[:, a], None, None, actions[a], action_log_probs[a], values[:, a],
@@ -204,6 +250,11 @@ class Runner:
 
     @torch.no_grad()
     def compute(self):
+        if self.team is not None and self.shared is not None:             # bootstrap values of all agents: one grouped forward,
+            nv = self.team.get_values(self.shared.share_obs[-1])          # returns of all agents: one launch
+            self.shared.compute_returns(nv.transpose(0, 1), [t.value_normalizer for t in self.trainer]
+                                        if self.trainer[0].value_normalizer is not None else None)
+            return
         for a in range(self.num_agents):
             self.trainer[a].prep_rollout()
             b = self.buffer[a]
@@ -226,7 +277,10 @@ class Runner:
                 new_logp = self._evaluate(a)
                 act_dim = b.actions.shape[-1]
                 factor = factor * torch.exp((new_logp - old_logp).reshape(T, N, act_dim).sum(dim=-1, keepdim=True)).detach()
-            b.after_update()
+            if self.shared is None:
+                b.after_update()
+        if self.shared is not None:
+            self.shared.after_update()
         return train_infos
 
     @torch.no_grad()

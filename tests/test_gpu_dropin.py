@@ -277,7 +277,8 @@ def test_reference_marl_runner_drives_the_dropins(cuda_device, tmp_path):
 
 _IPPO_SCRIPT = r'''
 import contextlib, io, os, sys, torch, yaml
-ROOT, REF, OUT, ALGO, FUSED = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] == "1"
+ROOT, REF, OUT, ALGO, FUSED = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] in ("1", "2")
+TEAM = sys.argv[5] == "2"          # grouped tensor-core forward for collect() + one shared buffer for the team
 sys.path.insert(0, ROOT)
 from oracle import refshim
 refshim.install(REF)
@@ -313,7 +314,8 @@ task.step_agent_actions = recording_step_agents
 torch.manual_seed(0)
 class Args: algo = ALGO
 with contextlib.redirect_stdout(io.StringIO()):
-    runner = Runner(vec_env=env, config=config, model_dir="", fused_update=FUSED)
+    runner = Runner(vec_env=env, config=config, model_dir="", fused_update=FUSED, team_forward=TEAM,
+                    shared_buffer=TEAM and config["use_centralized_V"])
 TrainAlgo, Policy = resolve_algorithm(ALGO)
 assert all(isinstance(t, TrainAlgo) for t in runner.trainer) and all(isinstance(p, Policy) for p in runner.policy)
 compute = runner.compute
@@ -379,12 +381,12 @@ print("RUNNER_OK algo=%s fused=%s episodes=%d" % (ALGO, FUSED, EPISODES))
 
 
 @needs_ref
-@pytest.mark.parametrize("algo,fused", [("ippo", False), ("ippo", True), ("mappo", True), ("happo", True)])
+@pytest.mark.parametrize("algo,fused", [("ippo", 0), ("ippo", 1), ("mappo", 1), ("happo", 1), ("mappo", 2), ("ippo", 2)])
 def test_runner_mirror_with_ippo_dispatch(cuda_device, tmp_path, algo, fused):
     """`runner.Runner` (the reference's Runner interface + the `ippo` branch its dispatch lacks, device-side insert masks and
     episode bookkeeping) trains TenAnt for 2 episodes with the reference's own trainers / policies - optionally with this
-    library's fused update bodies - and the first episode it stored equals the reference's own env classes on the same
-    frames and actions."""
-    res = subprocess.run([sys.executable, "-c", _IPPO_SCRIPT, ROOT, REF, str(tmp_path), algo, "1" if fused else "0"],
+    library's fused update bodies (1), and with the team forward + shared buffer for the rollout (2) - and the first episode
+    it stored equals the reference's own env classes on the same frames and actions."""
+    res = subprocess.run([sys.executable, "-c", _IPPO_SCRIPT, ROOT, REF, str(tmp_path), algo, str(int(fused))],
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "RUNNER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
