@@ -532,6 +532,8 @@ class MarlTeamForward:
         self._set_std()
 
     def _agent_major(self, x, width):
+        if isinstance(x, (list, tuple)):                  # already one [N, .] tensor per agent (buffer slots)
+            return list(x)
         if x.dim() == 2:                                  # one shared row per env: the same input for every critic
             return [x] * self.A
         if x.shape[0] != self.A:                          # (N, A, .) as MultiVecTaskPython returns it
