@@ -605,7 +605,11 @@ MMB_API int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t 
  * boundary is a cluster barrier, activations pass through L2).  `overlap_prev` of layers[0] as in mmb_mlp_layer.
  * MMB_EUNSUPPORTED for other geometries: run the layers with mmb_mlp_layer / mmb_mlp_layer_group instead. */
 #define MMB_MLP_MAX_LAYERS 6
-MMB_API int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, void* stream);
+/* x_fp32 != NULL: `count` pointers to the fp32 [M][K] inputs (row pitch K, K % 4 == 0, 16-byte aligned): the cast to the
+ * bf16 operand of layer 0 happens inside the kernel (the otherwise idle epilogue warps write the swizzled tiles) and
+ * layers[.][0].x is ignored - no mmb_ln_cast launch, nothing to wait for. */
+MMB_API int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, const float* const* x_fp32,
+                              void* stream);
 /* diagnostic of the experimental cta_group::2 mode (MMB_MLP_PAIR=1): first barrier wait that timed out {code, block x, block y,
  * parity}, all zero if none; clears the record */
 MMB_API int32_t mmb_mlp_debug_status(uint32_t* out4);

@@ -798,12 +798,13 @@ struct ChainLayer {
 static_assert(sizeof(ChainLayer) % 64 == 0, "tensor maps need 64-byte alignment");
 struct ChainArgs {
   ChainLayer l[CHAIN_MAX_NETS][MMB_MLP_MAX_LAYERS];
-  int num_layers, M, overlap_prev, pad_;
+  const float* x32[CHAIN_MAX_NETS];   // != NULL: layer 0's A operand is cast from this fp32 [M][K0] matrix inside the kernel
+  int num_layers, M, overlap_prev, K0;
 };
 
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_bar[CHAIN_STAGES], empty_bar[CHAIN_STAGES], acc_bar;
+  __shared__ uint64_t full_bar[CHAIN_STAGES], empty_bar[CHAIN_STAGES], a_bar[CHAIN_STAGES], acc_bar;
   __shared__ uint32_t tmem_slot;
   constexpr int S = CHAIN_STAGES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -813,9 +814,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
   const ChainLayer* Ls = g.l[blockIdx.z];
   const int L = g.num_layers;
   uint8_t* out_buf = smem + S * CHAIN_STAGE_BYTES;
+  // Input cast folded into layer 0: the eight epilogue warps - idle until the first accumulator is complete - convert the
+  // fp32 rows of this row block into the bf16 SWIZZLE_128B operand tiles themselves (one arrival per warp on a_bar), instead
+  // of a separate cast kernel whose completion the whole forward had to wait for.
+  const float* x32 = g.x32[blockIdx.z];
 
   if (tid == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&a_bar[i], 8); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int l = 0; l < L; ++l) {
@@ -840,23 +845,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
     if (warp == 0) {
       // ===== TMA producer =====
       if (elect_one()) {
-        auto load_w = [&](const ChainLayer& D, int kb, int itx) {   // claims ring slot itx for k-block kb of layer D: weight slice now
+        auto load_w = [&](const ChainLayer& D, int kb, int itx, bool a_by_tma = true) {   // claims ring slot itx for k-block kb of layer D: weight slice now
           const int s = itx % S, u = itx / S;
           if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
-          mbar_expect_tx(&full_bar[s], (uint32_t)(A_STAGE_BYTES + D.n_tile * BK * 2));
+          mbar_expect_tx(&full_bar[s], (uint32_t)((a_by_tma ? A_STAGE_BYTES : 0) + D.n_tile * BK * 2));
           tma_load_2d(smem + s * CHAIN_STAGE_BYTES + A_STAGE_BYTES, &D.map_w, kb * BK, (int)crank * D.n_tile, &full_bar[s]);
         };
         const int pre = nkb < S ? nkb : S;   // k-blocks whose weight slices were requested ahead (before the data they multiply existed)
+        const bool a_tma = !(l == 0 && x32 != nullptr);
         if (l == 0) {
-          for (int kb = 0; kb < pre; ++kb) load_w(C, kb, it_p + kb);
-          if (g.overlap_prev) griddep_wait();                 // the input cast is the previous kernel in the stream
+          for (int kb = 0; kb < pre; ++kb) load_w(C, kb, it_p + kb, a_tma);
+          if (g.overlap_prev && a_tma) griddep_wait();        // the input cast is the previous kernel in the stream
         } else {
           asm volatile("fence.proxy.async;" ::: "memory");    // peers' TMA stores (ordered by the cluster barrier) before our TMA loads
         }
         for (int kb = 0; kb < nkb; ++kb) {
           const int itx = it_p + kb;
-          if (kb >= pre) load_w(C, kb, itx);
-          tma_load_2d(smem + (itx % S) * CHAIN_STAGE_BYTES, &C.map_x, kb * BK, m0, &full_bar[itx % S]);
+          if (kb >= pre) load_w(C, kb, itx, a_tma);
+          if (a_tma) tma_load_2d(smem + (itx % S) * CHAIN_STAGE_BYTES, &C.map_x, kb * BK, m0, &full_bar[itx % S]);
         }
         if (l + 1 < L) {          // the next layer's first weight slices: in flight while this layer computes and stores
           const ChainLayer& D = Ls[l + 1];
@@ -872,6 +878,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
         for (int kb = 0; kb < nkb; ++kb) {
           const int itx = it_m + kb, s = itx % S, u = itx / S;
           mbar_wait(&full_bar[s], (uint32_t)(u & 1));
+          if (l == 0 && x32 != nullptr) mbar_wait(&a_bar[s], (uint32_t)(u & 1));   // the A tile the epilogue warps converted
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * CHAIN_STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
@@ -884,6 +891,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
       __syncwarp();
     } else {
       // ===== epilogue warps: TMEM lane quarter = warp % 4, two warps per quarter split the columns =====
+      if (l == 0 && x32 != nullptr) {
+        // layer 0's A tiles from the fp32 input: thread = (row, 32-column half) of the 128 x 64 tile of every k-block
+        if (g.overlap_prev) griddep_wait();                   // the input may come from the previous kernel in the stream
+        const int e = tid - 64, r = e >> 1, hf = e & 1;
+        const int K0 = g.K0;
+        const bool row_ok = m0 + r < g.M;
+        const float* xr = x32 + (int64_t)(m0 + r) * K0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % S, u = kb / S;
+          if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
+          uint8_t* rowp = smem + s * CHAIN_STAGE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+          const int c0 = kb * BK + hf * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {                        // four 16-byte chunks = 8 bf16 each
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            const int col = c0 + 8 * c;
+            if (row_ok && col < K0) v0 = __ldg(reinterpret_cast<const float4*>(xr + col));          // K0 % 4 == 0 (host)
+            if (row_ok && col + 4 < K0) v1 = __ldg(reinterpret_cast<const float4*>(xr + col + 4));
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
+            *reinterpret_cast<uint4*>(rowp + (((hf * 4 + c) ^ (r & 7)) << 4)) =
+                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                           *reinterpret_cast<uint32_t*>(&h3));
+          }
+          fence_async_smem();                                  // generic-proxy tile writes -> visible to the tensor core's reads
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_bar[s])) : "memory");
+        }
+      }
       mbar_wait(&acc_bar, (uint32_t)(l & 1));
       tc_fence_after();
       const int q = warp & 3, half = (warp - 2) >> 2;
@@ -1301,17 +1337,27 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
 }
 
 
-extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, void* stream) {
+extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, const float* const* x_fp32,
+                                 void* stream) {
   if (!layers || num_layers < 2 || num_layers > MMB_MLP_MAX_LAYERS || count < 1) return MMB_EINVAL;
   if (count > CHAIN_MAX_NETS) return MMB_EUNSUPPORTED;
   static thread_local ChainArgs g;
   const mmb_mlp_layer_params& f = layers[0];
   if (f.M <= 0 || f.Mpad % BM || f.Mpad < f.M) return MMB_EINVAL;
+  for (int a = 0; a < CHAIN_MAX_NETS; ++a) g.x32[a] = nullptr;
+  if (x_fp32) {     // fp32 [M][K] input of layer 0, cast inside the kernel: rows must be 16-byte addressable
+    if (f.K % 4) return MMB_EUNSUPPORTED;
+    for (int a = 0; a < count; ++a) {
+      if (!x_fp32[a] || (reinterpret_cast<uintptr_t>(x_fp32[a]) & 15u)) return MMB_EUNSUPPORTED;
+      g.x32[a] = x_fp32[a];
+    }
+  }
+  g.K0 = f.K;
   for (int a = 0; a < count; ++a) {
     for (int l = 0; l < num_layers; ++l) {
       const mmb_mlp_layer_params& p = layers[a * num_layers + l];
       const mmb_mlp_layer_params& r = layers[l];                       // network 0 defines the geometry
-      if (!p.x || !p.w || !p.bias || !p.y || p.M != f.M || p.Mpad != f.Mpad || p.N <= 0 || p.K <= 0) return MMB_EINVAL;
+      if ((!p.x && !(l == 0 && x_fp32)) || !p.w || !p.bias || !p.y || p.M != f.M || p.Mpad != f.Mpad || p.N <= 0 || p.K <= 0) return MMB_EINVAL;
       if (p.N != r.N || p.K != r.K || p.Kpad != r.Kpad || p.epilogue != r.epilogue || p.y_stride != r.y_stride) return MMB_EINVAL;
       if (p.Kpad % BK || p.Kpad < p.K) return MMB_EINVAL;
       if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.y)) & 15u) return MMB_EALIGN;
@@ -1335,9 +1381,9 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
       }
       // weights [Npad rows >= N][Kpad]: slices beyond the allocated rows are zero-filled by the TMA (out-of-bounds box rows)
       if (p.Npad < p.N) return MMB_EINVAL;
-      if (!make_map_bf16_2d(&c.map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
-          !make_map_bf16_2d(&c.map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)c.n_tile))
-        return MMB_ECUDA;
+      if (!make_map_bf16_2d(&c.map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)c.n_tile)) return MMB_ECUDA;
+      if (l == 0 && x_fp32) c.map_x = c.map_w;              // unused: layer 0's A tiles are cast in the kernel
+      else if (!make_map_bf16_2d(&c.map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM)) return MMB_ECUDA;
     }
   }
   g.num_layers = num_layers; g.M = f.M; g.overlap_prev = f.overlap_prev;

@@ -17,6 +17,7 @@ as one grouped launch per layer), `GroupedMLP` / `MarlTeamForward` (all agents' 
 Numerics: bf16 operands, fp32 accumulation and fp32 bias / ELU / LayerNorm; the reference is fp32 SGEMM, so
 outputs agree to bf16 operand precision (tests/test_gpu_mlp.py states the tolerances).
 """
+import ctypes as C
 import os
 from typing import List, Optional
 
@@ -96,13 +97,13 @@ class _Layer:
 _CHAIN_ENABLED = os.environ.get("MMB_MLP_CHAIN", "1") != "0"
 
 
-def _chain_launch(owner, arr, num_layers, count, stream):
+def _chain_launch(owner, arr, num_layers, count, stream, x_fp32=None):
     """The whole chain in ONE launch (`mmb_mlp_chain`: a cluster of 4 CTAs per 128-row block walks all layers) when the
     geometry allows it - plain Linear-ELU chains with hidden widths that are multiples of 256 (the PPO networks) - else False
     and the caller launches layer by layer.  The verdict of the library is remembered per object."""
     if not _CHAIN_ENABLED or owner.__dict__.get("_chain_ok") is False or num_layers < 2:
         return False
-    rc = L.lib().mmb_mlp_chain(arr, num_layers, count, stream)
+    rc = L.lib().mmb_mlp_chain(arr, num_layers, count, x_fp32, stream)
     if rc == 0:
         owner._chain_ok = True
         return True
@@ -238,9 +239,6 @@ class FusedMLP:
         lib, st = L.lib(), L.stream_ptr()
         l0 = self.layers[0]
         use_ln = self.in_ln is not None
-        L.check(lib.mmb_ln_cast(L.ptr(x), M, Mpad, l0.K, l0.Kpad, L.ptr(self.in_gamma) if use_ln else None,
-                                L.ptr(self.in_beta) if use_ln else None, self.in_eps if use_ln else 0.0, int(use_ln),
-                                L.ptr(acts[0]), st), "mmb_ln_cast")
         if out is None:
             out = torch.empty(M, self.out_dim, dtype=torch.float32, device=self.device)
         nl = len(self.layers)
@@ -257,7 +255,17 @@ class FusedMLP:
                 p.y, p.y_stride = L.ptr(out), out.stride(0)
             else:
                 p.y, p.y_stride = L.ptr(acts[i + 1]), acts[i + 1].stride(0)
-        if _chain_launch(self, arr, nl, 1, st):
+        # single launch with the input cast folded in (no LayerNorm in front, 16-byte addressable fp32 rows) ...
+        folded = False
+        if not use_ln and l0.K % 4 == 0 and x.data_ptr() % 16 == 0:
+            folded = True
+            if _chain_launch(self, arr, nl, 1, st, (C.c_void_p * 1)(x.data_ptr())):
+                return out
+        L.check(lib.mmb_ln_cast(L.ptr(x), M, Mpad, l0.K, l0.Kpad, L.ptr(self.in_gamma) if use_ln else None,
+                                L.ptr(self.in_beta) if use_ln else None, self.in_eps if use_ln else 0.0, int(use_ln),
+                                L.ptr(acts[0]), st), "mmb_ln_cast")
+        # ... or behind the cast / LayerNorm launch, or layer by layer
+        if not folded and _chain_launch(self, arr, nl, 1, st):
             return out
         for i in range(nl):
             L.check(lib.mmb_mlp_layer(arr[i], st), "mmb_mlp_layer")
@@ -317,13 +325,14 @@ class GroupedMLP:
         l0 = a0.layers[0]
         use_ln = a0.in_ln is not None
         shared_input = shared_input and not use_ln           # per-network input LayerNorms make the operands differ
-        if shared_input:                                     # one cast serves every network: slot 0 of the first operand buffer
-            L.check(lib.mmb_ln_cast(xs[0].data_ptr(), M, Mpad, l0.K, l0.Kpad, None, None, 0.0, 0, acts[0][0].data_ptr(), st), "mmb_ln_cast")
-        else:
-            if len(xs) != G:
-                xs = xs * G
+
+        def cast_inputs():
+            if shared_input:                                 # one cast serves every network: slot 0 of the first operand buffer
+                L.check(lib.mmb_ln_cast(xs[0].data_ptr(), M, Mpad, l0.K, l0.Kpad, None, None, 0.0, 0, acts[0][0].data_ptr(), st), "mmb_ln_cast")
+                return
+            xl = xs if len(xs) == G else xs * G
             vp = C.c_void_p * G
-            L.check(lib.mmb_ln_cast_group(vp(*[x.data_ptr() for x in xs]), G, M, Mpad, l0.K, l0.Kpad,
+            L.check(lib.mmb_ln_cast_group(vp(*[x.data_ptr() for x in xl]), G, M, Mpad, l0.K, l0.Kpad,
                                           vp(*[m.in_gamma.data_ptr() for m in self.mlps]) if use_ln else None,
                                           vp(*[m.in_beta.data_ptr() for m in self.mlps]) if use_ln else None,
                                           a0.in_eps if use_ln else 0.0, int(use_ln), vp(*[acts[0][g].data_ptr() for g in range(G)]), st),
@@ -345,13 +354,23 @@ class GroupedMLP:
             else:
                 p.y, p.y_stride = acts[i + 1][g].data_ptr(), acts[i + 1].stride(1)
 
+        casted = False
         if G <= 2 and self.__dict__.get("_chain_ok") is not False:       # network-major array: [G][layers]
             net_major = (L.MlpLayerParams * (G * nl))()
             for g in range(G):
                 for i in range(nl):
                     fill(net_major[g * nl + i], g, i)
-            if _chain_launch(self, net_major, nl, G, st):
-                return out
+            xl = xs if len(xs) == G else xs * G
+            if not use_ln and l0.K % 4 == 0 and all(x.data_ptr() % 16 == 0 for x in xl):
+                if _chain_launch(self, net_major, nl, G, st, (C.c_void_p * G)(*[x.data_ptr() for x in xl])):   # cast folded in
+                    return out
+            else:
+                cast_inputs()
+                casted = True
+                if _chain_launch(self, net_major, nl, G, st):
+                    return out
+        if not casted:
+            cast_inputs()
         for i in range(nl):
             arr = (L.MlpLayerParams * G)()
             for g in range(G):
