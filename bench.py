@@ -109,9 +109,9 @@ def ncu_traffic_bytes():
     for name in ("r02_ten_ant_ncu_summary.csv", "r01_ten_ant_v7_ncu_summary.csv"):
         path = os.path.join(ROOT, "profiles", name)
         try:
-            vals = {r[0]: (float(r[1]), r[2]) for r in csv.reader(open(path)) if len(r) == 3 and r[0].startswith("dram__bytes")}
+            vals = {r[0]: (float(r[1]), r[2]) for r in csv.reader(open(path)) if len(r) == 3 and r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum")}
             scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
-            if vals:
+            if len(vals) == 2:
                 return int(sum(v * scale[u] for v, u in vals.values())), os.path.relpath(path, ROOT)
         except Exception:
             continue
@@ -308,7 +308,7 @@ def mlp_forward_bench(dev, M, iters=200):
     tf = flops / (best * 1e-3) / 1e12
     return {"op": "PPO ActorCritic.act forward (actor + critic, bf16 operands / fp32 accumulate, tcgen05)", "batch": M,
             "ms_eager": ms, "ms_graph_replay": ms_graph, "tflops": tf, "peak_tflops": peak, "frac": (tf / peak) if peak else None,
-            "note": "input cast + 4 grouped layer launches (actor and critic side by side) + the sampling / log-prob kernel; "
+            "note": "ONE clustered launch for both networks (mmb_mlp_chain, input cast folded into layer 0) + the sampling / log-prob kernel; "
                     "TFLOP/s from the graph-replayed time; not part of the headline metric"}
 
 

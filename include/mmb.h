@@ -437,6 +437,11 @@ typedef struct {
   float* grad_mu;                          /* [B][A] d loss / d mean, or NULL */
   float* grad_value;                       /* [B] d loss / d value, or NULL */
   double* sums;                            /* [4 + A], zeroed by the caller */
+  float* out;                              /* optional [5 + A]: the finalised fp32 terms {loss, mean surrogate, mean value   */
+                                           /* loss, mean kl, entropy} and d loss / d log_std[A], written by the last block   */
+                                           /* to finish - which then leaves `sums` and `*ticket` zeroed again, so that one  */
+                                           /* scratch serves every later call on the same stream.  NULL = sums only          */
+  uint32_t* ticket;                        /* with `out`: a zero-initialised word that lives beside `sums`                  */
 } mmb_ppo_loss_params;
 MMB_API int32_t mmb_ppo_loss(const mmb_ppo_loss_params* p, void* stream);
 

@@ -132,7 +132,8 @@ class PpoLossParams(C.Structure):
                 ("mu", c_vp), ("mu_stride", c_i64), ("log_std", c_vp), ("actions", c_vp), ("old_logp", c_vp),
                 ("advantages", c_vp), ("value", c_vp), ("target_values", c_vp), ("returns", c_vp), ("old_mu", c_vp),
                 ("old_sigma", c_vp), ("clip_param", c_f), ("ratio_lo", c_f), ("ratio_hi", c_f), ("value_loss_coef", c_f),
-                ("entropy_coef", c_f), ("k_log_2pi", c_f), ("logp", c_vp), ("grad_mu", c_vp), ("grad_value", c_vp), ("sums", c_vp)]
+                ("entropy_coef", c_f), ("k_log_2pi", c_f), ("logp", c_vp), ("grad_mu", c_vp), ("grad_value", c_vp), ("sums", c_vp),
+                ("out", c_vp), ("ticket", c_vp)]
 
 
 class MappoLossParams(C.Structure):

@@ -157,7 +157,31 @@ __global__ void __launch_bounds__(LOSS_THREADS) ppo_loss_kernel(const __grid_con
     if (blockIdx.x == 0) v -= 2.0 * (double)p.entropy_coef;     // entropy = const + sum_j 2 log_std_j, equal on every row
     atomicAdd(p.sums + 4 + j, v);
   }
-  if (blockIdx.x == 0 && tid == 0) p.sums[3] = 0.5 * (double)A * (1.0 + (double)LOG_2PI) + (double)half_log_det;
+  const double entropy = 0.5 * (double)A * (1.0 + (double)LOG_2PI) + (double)half_log_det;
+  if (p.out == nullptr) {
+    if (blockIdx.x == 0 && tid == 0) p.sums[3] = entropy;
+    return;
+  }
+  // Finalisation by the last block to finish (ticket): the fp32 terms torch would compute from the sums
+  // (ppo.py:285-302: means over the batch, total loss) - and the scratch is handed back zeroed.
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  volatile double* sums = p.sums;
+  if (tid == 0) {
+    const float s0 = (float)sums[0], s1 = (float)sums[1], s2 = (float)sums[2], ent = (float)entropy;
+    const float fb = (float)p.num_rows;
+    p.out[0] = s0 * (1.0f / fb) + s1 * (p.value_loss_coef / fb) - p.entropy_coef * ent;
+    p.out[1] = s0 / fb; p.out[2] = s1 / fb; p.out[3] = s2 / fb; p.out[4] = ent;
+  }
+  for (int j = tid; j < A; j += LOSS_THREADS) p.out[5 + j] = (float)sums[4 + j];
+  __syncthreads();
+  for (int j = tid; j < 4 + A; j += LOSS_THREADS) p.sums[j] = 0.0;
+  if (tid == 0) *p.ticket = 0u;
 }
 
 template <int G>
@@ -334,6 +358,7 @@ extern "C" int32_t mmb_ppo_loss(const mmb_ppo_loss_params* pp, void* stream) {
   if (!p.mu || !p.log_std || !p.actions || !p.old_logp || !p.advantages || !p.value || !p.returns || !p.sums) return MMB_EINVAL;
   if (p.use_clipped_value_loss && !p.target_values) return MMB_EINVAL;
   if ((p.old_mu == nullptr) != (p.old_sigma == nullptr)) return MMB_EINVAL;
+  if (p.out && !p.ticket) return MMB_EINVAL;
   p.k_log_2pi = (float)((double)p.act_dim * 1.8378770664093453);   // torch: the Python double k * log(2 pi), then cast
   cudaStream_t st = (cudaStream_t)stream;
   const int G = p.act_dim <= 8 ? 8 : (p.act_dim <= 16 ? 16 : 32);

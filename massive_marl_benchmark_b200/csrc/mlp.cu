@@ -892,32 +892,41 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
     } else {
       // ===== epilogue warps: TMEM lane quarter = warp % 4, two warps per quarter split the columns =====
       if (l == 0 && x32 != nullptr) {
-        // layer 0's A tiles from the fp32 input: thread = (row, 32-column half) of the 128 x 64 tile of every k-block
+        // layer 0's A tiles from the fp32 input.  A warp owns 16 rows of the 128 x 64 tile of every k-block; one load
+        // instruction covers two whole 256-byte row segments (coalesced), and the loads of k-block kb + 1 are in flight
+        // while k-block kb is converted and handed to the tensor core.
         if (g.overlap_prev) griddep_wait();                   // the input may come from the previous kernel in the stream
-        const int e = tid - 64, r = e >> 1, hf = e & 1;
+        const int w8 = (tid - 64) >> 5, sub = lane >> 4, c4 = lane & 15;
         const int K0 = g.K0;
-        const bool row_ok = m0 + r < g.M;
-        const float* xr = x32 + (int64_t)(m0 + r) * K0;
+        const float* xbase = x32 + (int64_t)(m0 + w8 * 16 + sub) * K0 + c4 * 4;
+        const int rows_left = g.M - (m0 + w8 * 16 + sub);     // row i of this thread exists iff 2 i < rows_left
+        auto load_tile = [&](int kb, float4 (&v)[8]) {
+          const bool col_ok = kb * BK + c4 * 4 < K0;          // K0 % 4 == 0 (host): the float4 is inside the row or outside it
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && 2 * i < rows_left) v[i] = __ldg(reinterpret_cast<const float4*>(xbase + (int64_t)(2 * i) * K0 + kb * BK));
+          }
+        };
+        float4 cur[8], nxt[8];
+        load_tile(0, cur);
         for (int kb = 0; kb < nkb; ++kb) {
           const int s = kb % S, u = kb / S;
+          if (kb + 1 < nkb) load_tile(kb + 1, nxt);
           if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
-          uint8_t* rowp = smem + s * CHAIN_STAGE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-          const int c0 = kb * BK + hf * 32;
+          uint8_t* tile = smem + s * CHAIN_STAGE_BYTES;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {                        // four 16-byte chunks = 8 bf16 each
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            const int col = c0 + 8 * c;
-            if (row_ok && col < K0) v0 = __ldg(reinterpret_cast<const float4*>(xr + col));          // K0 % 4 == 0 (host)
-            if (row_ok && col + 4 < K0) v1 = __ldg(reinterpret_cast<const float4*>(xr + col + 4));
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
-            *reinterpret_cast<uint4*>(rowp + (((hf * 4 + c) ^ (r & 7)) << 4)) =
-                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
-                           *reinterpret_cast<uint32_t*>(&h3));
+          for (int i = 0; i < 8; ++i) {
+            const int r = w8 * 16 + 2 * i + sub;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(cur[i].x, cur[i].y), h1 = __floats2bfloat162_rn(cur[i].z, cur[i].w);
+            *reinterpret_cast<uint2*>(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((((c4 >> 1) ^ (r & 7)) << 4) | ((c4 & 1) << 3))) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
           }
           fence_async_smem();                                  // generic-proxy tile writes -> visible to the tensor core's reads
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_bar[s])) : "memory");
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
       }
       mbar_wait(&acc_bar, (uint32_t)(l & 1));

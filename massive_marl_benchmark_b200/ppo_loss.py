@@ -22,51 +22,63 @@ from . import _lib as L
 PpoLossOut = namedtuple("PpoLossOut", "loss surrogate_loss value_loss kl_mean logp entropy")
 
 
+def _f32(t):
+    return t if (t.dtype is torch.float32 and t.is_contiguous()) else t.detach().float().contiguous()
+
+
 def _rows(t, B, name):
-    t = t.detach()
     if t.numel() != B:
         raise ValueError("%s: expected %d elements, got %s" % (name, B, tuple(t.shape)))
-    return t.reshape(B).float().contiguous()
+    return _f32(t)
 
 
-def ppo_loss_raw(mu, log_std, value, actions, old_logp, advantages, target_values, returns, old_mu=None, old_sigma=None,
-                 clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.0, use_clipped_value_loss=True, need_grads=True):
-    """One `mmb_ppo_loss` launch.  Returns (sums [4 + A] fp64: {sum surrogate, sum value loss, sum kl, entropy} followed by
-    d loss / d log_std, logp [B], grad_mu [B, A] | None, grad_value [B] | None)."""
+def _fill(p, keep, mu, log_std, value, actions, old_logp, advantages, target_values, returns, old_mu, old_sigma,
+          clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss):
+    """Inputs of one `mmb_ppo_loss` launch into the params struct `p`; tensors that had to be converted go to `keep`."""
     if not mu.is_cuda:
         raise L.MmbError("ppo_loss needs CUDA tensors (there is no CPU path)")
     B, A = mu.shape
-    mu_ = mu.detach().float()
-    if mu_.stride(1) != 1:
-        mu_ = mu_.contiguous()
-    keep = [mu_]
-    p = L.PpoLossParams()
+    mu_ = mu if (mu.dtype is torch.float32 and mu.stride(1) == 1) else mu.detach().float().contiguous()
     p.num_rows, p.act_dim, p.use_clipped_value_loss = B, A, int(bool(use_clipped_value_loss))
     p.mu, p.mu_stride = mu_.data_ptr(), mu_.stride(0)
+    keep.append(mu_)
 
     def put(field, t):
         keep.append(t)
         setattr(p, field, t.data_ptr())
 
-    put("log_std", log_std.detach().reshape(A).float().contiguous())
-    act = actions.detach().float().contiguous()
-    if tuple(act.shape) != (B, A):
-        raise ValueError("actions: expected %s, got %s" % ((B, A), tuple(act.shape)))
-    put("actions", act)
+    put("log_std", _rows(log_std, A, "log_std"))
+    if tuple(actions.shape) != (B, A):
+        raise ValueError("actions: expected %s, got %s" % ((B, A), tuple(actions.shape)))
+    put("actions", _f32(actions))
     put("old_logp", _rows(old_logp, B, "old_logp"))
     put("advantages", _rows(advantages, B, "advantages"))
     put("value", _rows(value, B, "value"))
     put("returns", _rows(returns, B, "returns"))
     if use_clipped_value_loss:
         put("target_values", _rows(target_values, B, "target_values"))
+    else:
+        p.target_values = None
     if (old_mu is None) != (old_sigma is None):
         raise ValueError("old_mu and old_sigma go together")
     if old_mu is not None:
-        put("old_mu", old_mu.detach().float().reshape(B, A).contiguous())
-        put("old_sigma", old_sigma.detach().float().reshape(B, A).contiguous())
+        put("old_mu", _rows(old_mu, B * A, "old_mu"))
+        put("old_sigma", _rows(old_sigma, B * A, "old_sigma"))
+    else:
+        p.old_mu = p.old_sigma = None
     p.clip_param = float(clip_param)
     p.ratio_lo, p.ratio_hi = 1.0 - clip_param, 1.0 + clip_param     # rounded to fp32 like the reference's Python scalars
     p.value_loss_coef, p.entropy_coef = float(value_loss_coef), float(entropy_coef)
+    return B, A
+
+
+def ppo_loss_raw(mu, log_std, value, actions, old_logp, advantages, target_values, returns, old_mu=None, old_sigma=None,
+                 clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.0, use_clipped_value_loss=True, need_grads=True):
+    """One `mmb_ppo_loss` launch.  Returns (sums [4 + A] fp64: {sum surrogate, sum value loss, sum kl, entropy} followed by
+    d loss / d log_std, logp [B], grad_mu [B, A] | None, grad_value [B] | None)."""
+    p, keep = L.PpoLossParams(), []
+    B, A = _fill(p, keep, mu, log_std, value, actions, old_logp, advantages, target_values, returns, old_mu, old_sigma,
+                 clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss)
     dev = mu.device
     sums = torch.zeros(4 + A, dtype=torch.float64, device=dev)
     logp = torch.empty(B, dtype=torch.float32, device=dev)
@@ -80,41 +92,54 @@ def ppo_loss_raw(mu, log_std, value, actions, old_logp, advantages, target_value
     return sums, logp, grad_mu, grad_value
 
 
+_SCRATCH = {}     # (device, stream, A) -> (params struct, fp64 sums + ticket word): the kernel hands the scratch back zeroed
+
+
+def _scratch(dev, stream, A):
+    key = (dev.index, stream, A)
+    e = _SCRATCH.get(key)
+    if e is None:
+        if len(_SCRATCH) > 64:
+            _SCRATCH.clear()
+        buf = torch.zeros(4 + A + 1, dtype=torch.float64, device=dev)
+        p = L.PpoLossParams()
+        p.sums, p.ticket = buf.data_ptr(), buf.data_ptr() + 8 * (4 + A)
+        e = _SCRATCH[key] = (p, buf)
+    return e[0]
+
+
 class _FusedPPOLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mu, log_std, value, actions, old_logp, advantages, target_values, returns, old_mu, old_sigma,
                 clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss):
-        B, A = mu.shape
-        sums, logp, grad_mu, grad_value = ppo_loss_raw(mu, log_std, value, actions, old_logp, advantages, target_values,
-                                                       returns, old_mu, old_sigma, clip_param, value_loss_coef,
-                                                       entropy_coef, use_clipped_value_loss)
-        # three small launches instead of a dozen (the wrapper, not the 26 us kernel, was the cost of this op):
-        # fp32 copy of the sums; loss = <sums[:4], (1/B, c_v/B, 0, -c_e)> (ppo.py:302); the three reported means
-        s32 = sums.float()
-        w = _loss_weights(mu.device, B, float(value_loss_coef), float(entropy_coef))
-        loss = torch.dot(s32[:4], w)
-        means = s32[:3] / B
-        ctx.save_for_backward(grad_mu, s32[4:].reshape(log_std.shape), grad_value.reshape(value.shape))
-        ctx.mark_non_differentiable(logp)
-        return loss, means[0], means[1], means[2], logp, s32[3]
+        # ONE launch: the kernel's last block finalises the fp32 terms (loss = mean surrogate + c_v mean value loss -
+        # c_e entropy, ppo.py:302; the three reported means; d loss / d log_std) into `out`; everything below is views.
+        st = L.stream_ptr()
+        A = mu.shape[1]
+        p = _scratch(mu.device, st, A)
+        keep = []
+        B, A = _fill(p, keep, mu, log_std, value, actions, old_logp, advantages, target_values, returns, old_mu, old_sigma,
+                     clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss)
+        dev = mu.device
+        # gradients and finalised terms share one buffer, so that backward scales all of them with ONE multiply
+        o_val = (B * A + 3) & ~3
+        o_out = (o_val + B + 3) & ~3
+        flat = torch.empty(o_out + 5 + A, dtype=torch.float32, device=dev)
+        logp = torch.empty(B, dtype=torch.float32, device=dev)
+        base = flat.data_ptr()
+        p.grad_mu, p.grad_value, p.out, p.logp = base, base + 4 * o_val, base + 4 * o_out, logp.data_ptr()
+        L.check(L.lib().mmb_ppo_loss(p, st), "mmb_ppo_loss")
+        loss, surrogate, value_loss, kl_mean, entropy = flat[o_out:o_out + 5].unbind(0)
+        ctx.save_for_backward(flat)
+        ctx.geom = (B, A, o_val, o_out, log_std.shape, value.shape)
+        ctx.mark_non_differentiable(logp, surrogate, value_loss, kl_mean, entropy)   # only the total is differentiated (ppo.py:306)
+        return loss, surrogate, value_loss, kl_mean, logp, entropy
 
     @staticmethod
     def backward(ctx, g_loss, *_unused):
-        grads = torch._foreach_mul(list(ctx.saved_tensors), g_loss)       # one multi-tensor launch
-        return tuple(grads) + (None,) * 11
-
-
-_WEIGHTS = {}
-
-
-def _loss_weights(device, B, value_loss_coef, entropy_coef):
-    key = (str(device), B, value_loss_coef, entropy_coef)
-    w = _WEIGHTS.get(key)
-    if w is None:
-        if len(_WEIGHTS) > 64:
-            _WEIGHTS.clear()
-        w = _WEIGHTS[key] = torch.tensor([1.0 / B, value_loss_coef / B, 0.0, -entropy_coef], dtype=torch.float32, device=device)
-    return w
+        B, A, o_val, o_out, ls_shape, v_shape = ctx.geom
+        g = ctx.saved_tensors[0] * g_loss
+        return (g[:B * A].view(B, A), g[o_out + 5:].view(ls_shape), g[o_val:o_val + B].view(v_shape)) + (None,) * 11
 
 
 def ppo_loss(mu, log_std, value, actions, old_logp, advantages, target_values, returns, old_mu=None, old_sigma=None,
