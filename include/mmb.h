@@ -615,6 +615,12 @@ MMB_API int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t 
  * layers[.][0].x is ignored - no mmb_ln_cast launch, nothing to wait for. */
 MMB_API int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, const float* const* x_fp32,
                               void* stream);
+/* Diagnostics: with MMB_CHAIN_TRACE=1 in the environment the first eight CTAs of every mmb_mlp_chain launch stamp
+   %globaltimer (ns): [cta 0..7][layer 0..5][event 0..7: layer begin (producer), first operands in shared memory, last MMA
+   issued, accumulator complete, output slices computed and their stores issued, stores landed (wait_group 0), cluster
+   barrier passed, -], followed by [cta 0..7][layer 0..5][i 0..15]: operands of the i-th k-block in shared memory.
+   Synchronises the device and copies the 8 x 6 x 24 words of the latest launch to `out`; MMB_EINVAL when tracing is off. */
+MMB_API int32_t mmb_mlp_chain_trace(uint64_t* out, int32_t words);
 /* diagnostic of the experimental cta_group::2 mode (MMB_MLP_PAIR=1): first barrier wait that timed out {code, block x, block y,
  * parity}, all zero if none; clears the record */
 MMB_API int32_t mmb_mlp_debug_status(uint32_t* out4);

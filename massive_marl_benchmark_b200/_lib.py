@@ -220,6 +220,7 @@ SYMBOLS = {
     "mmb_grad_sumsq_group": (c_i32, [C.POINTER(AdamParams), c_vp]),
     "mmb_adam_group": (c_i32, [C.POINTER(AdamParams), c_vp]),
     "mmb_mlp_layer": (c_i32, [C.POINTER(MlpLayerParams), c_vp]),
+    "mmb_mlp_chain_trace": (c_i32, [c_vp, c_i32]),
     "mmb_mlp_chain": (c_i32, [C.POINTER(MlpLayerParams), c_i32, c_i32, C.POINTER(c_vp), c_vp]),
     "mmb_mlp_debug_status": (c_i32, [C.POINTER(C.c_uint32)]),
     "mmb_mlp_layer_group": (c_i32, [C.POINTER(MlpLayerParams), c_i32, c_vp]),

@@ -95,6 +95,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load without the wait: the registers are valid after tmem_ld_wait(r) (which names them, so that the compiler
+// cannot move their uses above the wait).  Lets the next 32 columns travel while the current ones are processed.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+
 // nn.ELU(alpha=1).  The negative branch is exp(x) - 1 through ex2.approx (2 ulp): its absolute error of ~1e-7 is far below
 // the bf16 rounding of the stored activation (2^-9 relative) even where x -> 0 and the subtraction cancels; expm1f costs
 // ~35 instructions per element and made the epilogue, not the MMA, the longest phase of a tile.
@@ -800,11 +821,28 @@ struct ChainArgs {
   ChainLayer l[CHAIN_MAX_NETS][MMB_MLP_MAX_LAYERS];
   const float* x32[CHAIN_MAX_NETS];   // != NULL: layer 0's A operand is cast from this fp32 [M][K0] matrix inside the kernel
   int num_layers, M, overlap_prev, K0;
+  unsigned long long* trace;          // diagnostics (MMB_CHAIN_TRACE=1): %globaltimer stamps, see mmb_mlp_chain_trace; else NULL
 };
+enum { TR_LAYER_BEGIN = 0, TR_FIRST_OPERANDS = 1, TR_MMA_ISSUED = 2, TR_ACC_COMPLETE = 3, TR_COMPUTED = 4, TR_LANDED = 5, TR_BOUNDARY = 6 };
+[[maybe_unused]] constexpr int CHAIN_TRACE_EVENTS = 8 * MMB_MLP_MAX_LAYERS * 8;      // then [8 CTAs][6 layers][16]: operands of the i-th k-block in smem
+constexpr int CHAIN_TRACE_WORDS = 8 * MMB_MLP_MAX_LAYERS * (8 + 16);
+// Compiled in only with -DMMB_CHAIN_TRACE_BUILD (make EXTRA=-DMMB_CHAIN_TRACE_BUILD; tools/probe/chain_trace.py): even
+// predicated-off, the stamps cost the kernel ~4 us of scheduling freedom.
+__device__ __forceinline__ void chain_trace(const ChainArgs& g, int l, int ev, int kb = -1) {
+#ifdef MMB_CHAIN_TRACE_BUILD
+  if (g.trace != nullptr && blockIdx.x < 8 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (kb < 0) g.trace[(blockIdx.x * MMB_MLP_MAX_LAYERS + l) * 8 + ev] = t;
+    else if (kb < 16) g.trace[CHAIN_TRACE_EVENTS + (blockIdx.x * MMB_MLP_MAX_LAYERS + l) * 16 + kb] = t;
+  }
+#endif
+}
 
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[CHAIN_STAGES], empty_bar[CHAIN_STAGES], a_bar[CHAIN_STAGES], acc_bar;
+  __shared__ __align__(16) float bias_s[256];       // this CTA's bias slice of the current hidden layer
   __shared__ uint32_t tmem_slot;
   constexpr int S = CHAIN_STAGES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -845,6 +883,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
     if (warp == 0) {
       // ===== TMA producer =====
       if (elect_one()) {
+        chain_trace(g, l, TR_LAYER_BEGIN);
         auto load_w = [&](const ChainLayer& D, int kb, int itx, bool a_by_tma = true) {   // claims ring slot itx for k-block kb of layer D: weight slice now
           const int s = itx % S, u = itx / S;
           if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
@@ -879,6 +918,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           const int itx = it_m + kb, s = itx % S, u = itx / S;
           mbar_wait(&full_bar[s], (uint32_t)(u & 1));
           if (l == 0 && x32 != nullptr) mbar_wait(&a_bar[s], (uint32_t)(u & 1));   // the A tile the epilogue warps converted
+          if (kb == 0) chain_trace(g, l, TR_FIRST_OPERANDS);
+          chain_trace(g, l, 0, kb);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * CHAIN_STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
@@ -887,6 +928,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&acc_bar);
+        chain_trace(g, l, TR_MMA_ISSUED);
       }
       __syncwarp();
     } else {
@@ -929,10 +971,72 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
       }
-      mbar_wait(&acc_bar, (uint32_t)(l & 1));
-      tc_fence_after();
       const int q = warp & 3, half = (warp - 2) >> 2;
       const int row = q * 32 + lane;
+      if (l + 1 < L) {
+        // ---- hidden layer: bias + ELU -> bf16, 64-column sub-tiles through this half's staging buffer ----
+        // The bias slice waits in shared memory before the accumulator is complete, the next 32 accumulator columns travel
+        // from tensor memory while the current ones are processed, and a sub-tile's store is only waited for when its
+        // buffer is needed again: the epilogue is the serial part of a layer (the MMAs of layer l + 1 need all of it).
+        { const int e = tid - 64; if (e < n_tile) bias_s[e] = __ldg(C.bias + n0 + e); }      // N % 256 == 0 (host): all columns exist
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(&acc_bar, (uint32_t)(l & 1));
+        tc_fence_after();
+        if (tid == 64) chain_trace(g, l, TR_ACC_COMPLETE);
+        const int n_sub = n_tile >> 6, halves = n_sub >= 2 ? 2 : 1, per_half = n_sub / halves;
+        const bool leader = q == 0 && lane == 0;
+        if (half < halves) {
+          const int cbeg = half * per_half * 64;
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+          uint8_t* buf = out_buf + half * (BM * 128);
+          uint8_t* rowp = buf + (row >> 3) * 1024 + (row & 7) * 128;
+          uint32_t ra[32], rb[32], pk[32];
+          auto act32 = [&](const uint32_t (&r)[32], int col, uint32_t* out16) {      // 32 columns: bias + ELU -> 16 packed bf16 pairs
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = b4[i];
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(elu1(__uint_as_float(r[4 * i]) + b.x), elu1(__uint_as_float(r[4 * i + 1]) + b.y));
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(elu1(__uint_as_float(r[4 * i + 2]) + b.z), elu1(__uint_as_float(r[4 * i + 3]) + b.w));
+              out16[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
+              out16[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+          };
+          tmem_ld32_issue(taddr, ra);
+          for (int js = 0; js < per_half; ++js) {
+            tmem_ld_wait(ra);
+            tmem_ld32_issue(taddr + js * 64 + 32, rb);
+            act32(ra, cbeg + js * 64, pk);
+            tmem_ld_wait(rb);
+            if (js + 1 < per_half) tmem_ld32_issue(taddr + js * 64 + 64, ra);
+            act32(rb, cbeg + js * 64 + 32, pk + 16);
+            if (js > 0) {                                       // the buffer fed the previous sub-tile's store
+              if (leader) tma_store_wait_read();
+              if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+              else asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            fence_async_smem();
+            if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (leader) {
+              tma_store_2d(&C.map_y, buf, n0 + cbeg + js * 64, m0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (leader && half == 0) chain_trace(g, l, TR_COMPUTED);
+          // the slices must have LANDED (not only left shared memory) before the peers are told to read them
+          if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          if (leader && half == 0) chain_trace(g, l, TR_LANDED);
+        }
+        tc_fence_before();
+        __syncwarp();
+      } else {
+      mbar_wait(&acc_bar, (uint32_t)(l & 1));
+      tc_fence_after();
+      if (tid == 64) chain_trace(g, l, TR_ACC_COMPLETE);
       const int sub_cols = (C.epilogue == 0) ? 32 : 64;
       int cb = 0, ce = half ? 0 : n_tile;
       if (n_tile >= 2 * sub_cols) { cb = half ? n_tile / 2 : 0; ce = half ? n_tile : n_tile / 2; }
@@ -953,10 +1057,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           else asm volatile("bar.sync 2, 128;" ::: "memory");
         }, 0);
         // the slice must have LANDED (not only left shared memory) before the peers are told to read it
+        if (q == 0 && lane == 0 && half == 0) chain_trace(g, l, TR_COMPUTED);   // all sub-tiles of this half computed, staged, stores issued
         if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (q == 0 && lane == 0 && half == 0) chain_trace(g, l, TR_LANDED);
       }
       tc_fence_before();
       __syncwarp();
+      }
     }
     it_p += nkb;
     it_m += nkb;
@@ -964,6 +1071,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
       tc_fence_before();
       cluster_sync_all();
       tc_fence_after();
+      if (tid == 64) chain_trace(g, l, TR_BOUNDARY);
     }
   }
   tc_fence_before();
@@ -1346,6 +1454,30 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
 }
 
 
+namespace {
+unsigned long long* chain_trace_buffer() {          // one buffer on the device that first asks (diagnostics only)
+  static unsigned long long* buf = [] {
+    unsigned long long* b = nullptr;
+    const char* v = getenv("MMB_CHAIN_TRACE");
+#ifndef MMB_CHAIN_TRACE_BUILD
+    v = nullptr;
+#endif
+    if (v && atoi(v) && cudaMalloc(&b, CHAIN_TRACE_WORDS * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(b, 0, CHAIN_TRACE_WORDS * sizeof(unsigned long long));
+    else b = nullptr;
+    return b;
+  }();
+  return buf;
+}
+}  // namespace
+
+extern "C" int32_t mmb_mlp_chain_trace(uint64_t* out, int32_t words) {
+  unsigned long long* b = chain_trace_buffer();
+  if (!b || !out || words < CHAIN_TRACE_WORDS) return MMB_EINVAL;
+  if (cudaDeviceSynchronize() != cudaSuccess) return MMB_ECUDA;
+  return cudaMemcpy(out, b, CHAIN_TRACE_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
 extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num_layers, int32_t count, const float* const* x_fp32,
                                  void* stream) {
   if (!layers || num_layers < 2 || num_layers > MMB_MLP_MAX_LAYERS || count < 1) return MMB_EINVAL;
@@ -1396,6 +1528,7 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
     }
   }
   g.num_layers = num_layers; g.M = f.M; g.overlap_prev = f.overlap_prev;
+  g.trace = chain_trace_buffer();
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= MMB_MAX_DEVICES) return MMB_EUNSUPPORTED;
