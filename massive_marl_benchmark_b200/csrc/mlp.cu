@@ -797,13 +797,19 @@ struct LnCastGroupArgs {
 // Whole-MLP forward in ONE launch (PPO ActorCritic.actor / .critic: Linear-ELU chains, module.py:25-55).
 // A cluster of 4 CTAs owns one 128-row block for ALL layers; CTA r of the cluster computes columns [r * N_l / 4, (r + 1) *
 // N_l / 4) of every layer l.  Layer l + 1 of a row block needs exactly the four column slices its own cluster produced, so
-// the layer boundary is a `barrier.cluster` instead of a kernel boundary: activations travel through L2 (TMA store ->
-// cp.async.bulk.wait_group 0 -> cluster barrier -> TMA load), the operand ring and its mbarrier phases run on across the
-// layers, the next layer's first weight tiles are already in flight while this layer's epilogue runs (the output is staged
-// outside the ring), and launch prologue / pipeline drain are paid once per forward instead of once per layer.
+// there is no kernel boundary between the layers and no barrier that every thread waits at either: activations travel
+// through L2 (TMA store -> cp.async.bulk.wait_group 0), then the storing thread of each epilogue half arrives on two
+// single-use mbarriers - `own_bar[l]` of its CTA and `peer_bar[l]` of all four CTAs (release.cluster) - and only the TMA
+// producer thread waits: for own_bar before it requests the k-blocks this CTA produced itself (every CTA starts the next
+// layer with its own slices), for peer_bar before the peers' k-blocks.  The operand ring and its mbarrier phases run on
+// across the layers, the next layer's first weight tiles are in flight while this layer's epilogue runs (the output is
+// staged outside the ring), and launch prologue / pipeline drain are paid once per forward instead of once per layer.
+// The epilogue of a hidden layer is the serial part (the next layer's MMAs need all of it): bias slice staged in shared
+// memory beforehand, tensor-memory loads one 32-column chunk ahead, store waits deferred to the buffer's next use.
 // Same warp roles as mlp_layer_ws_kernel (TMA producer, MMA issuer, 8 epilogue warps), one accumulator in tensor memory.
 // grid = (4 x row blocks, 1, networks): blockIdx.z selects one of up to two networks of identical geometry (actor and
 // critic side by side).  Geometry: hidden widths multiples of 256, <= 1024; TMA-addressable fp32 output.
+// Timeline of a launch (tools/probe/chain_trace.py, build with EXTRA=-DMMB_CHAIN_TRACE_BUILD): profiles/r02_chain_trace.json.
 // ------------------------------------------------------------------------------------------------------
 constexpr int CHAIN_CLUSTER = 4;
 constexpr int CHAIN_STAGES = 4;
@@ -839,9 +845,24 @@ __device__ __forceinline__ void chain_trace(const ChainArgs& g, int l, int ev, i
 #endif
 }
 
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {   // same barrier, CTA cta_rank of the cluster
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta_rank));
+  // relaxed: what the peer is told about are TMA stores this warp has seen complete (async proxy, already in L2) - a
+  // release at cluster scope here costs ~0.8 us per arrival (measured)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// The i-th k-block layer l > 0 consumes in CTA `crank`: its own n_own output sub-tiles of layer l - 1 first, then the peers'.
+__device__ __forceinline__ int chain_kb(int i, int n_own, int crank, int nkb) {
+  const int kb = i + crank * n_own;
+  return kb >= nkb ? kb - nkb : kb;
+}
+
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[CHAIN_STAGES], empty_bar[CHAIN_STAGES], a_bar[CHAIN_STAGES], acc_bar;
+  __shared__ uint64_t own_bar[MMB_MLP_MAX_LAYERS];   // single use: this CTA's own slices of layer l have landed (one arrival per epilogue half)
+  __shared__ uint64_t peer_bar[MMB_MLP_MAX_LAYERS];  // single use: ALL slices of layer l have landed (one arrival per epilogue half of each CTA)
   __shared__ __align__(16) float bias_s[256];       // this CTA's bias slice of the current hidden layer
   __shared__ uint32_t tmem_slot;
   constexpr int S = CHAIN_STAGES;
@@ -860,6 +881,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&a_bar[i], 8); }
     mbar_init(&acc_bar, 1);
+    for (int l = 0; l < L; ++l) {
+      const uint32_t halves = (Ls[l].n_tile >> 6) >= 2 ? 2 : 1;
+      mbar_init(&own_bar[l], halves);
+      mbar_init(&peer_bar[l], halves * CHAIN_CLUSTER);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int l = 0; l < L; ++l) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&Ls[l].map_x) : "memory");
@@ -873,6 +899,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();              // every CTA's barriers exist before a peer arrives on them
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
@@ -892,21 +919,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
         };
         const int pre = nkb < S ? nkb : S;   // k-blocks whose weight slices were requested ahead (before the data they multiply existed)
         const bool a_tma = !(l == 0 && x32 != nullptr);
+        // Layers l > 0 take their k-blocks starting with the ones this CTA produced itself (chain_kb): they are requested as
+        // soon as this CTA's own stores have landed (own_bar), the peers' slices once every epilogue half of the cluster has
+        // reported (peer_bar: remote arrivals, release.cluster).  No other warp waits at a layer boundary.  Stores and
+        // loads are both the async proxy and meet in L2 (a fence.proxy.async here would drain the loads in flight: 0.8 us).
+        const int n_own = l == 0 ? 0 : (Ls[l - 1].n_tile >> 6);
         if (l == 0) {
           for (int kb = 0; kb < pre; ++kb) load_w(C, kb, it_p + kb, a_tma);
           if (g.overlap_prev && a_tma) griddep_wait();        // the input cast is the previous kernel in the stream
         } else {
-          asm volatile("fence.proxy.async;" ::: "memory");    // peers' TMA stores (ordered by the cluster barrier) before our TMA loads
+          mbar_wait(&own_bar[l - 1], 0u);
         }
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int itx = it_p + kb;
-          if (kb >= pre) load_w(C, kb, itx, a_tma);
+        for (int i = 0; i < nkb; ++i) {
+          const int itx = it_p + i, kb = chain_kb(i, n_own, (int)crank, nkb);
+          if (i >= pre) load_w(C, kb, itx, a_tma);
+          if (l > 0 && i == n_own) mbar_wait(&peer_bar[l - 1], 0u);
           if (a_tma) tma_load_2d(smem + (itx % S) * CHAIN_STAGE_BYTES, &C.map_x, kb * BK, m0, &full_bar[itx % S]);
         }
         if (l + 1 < L) {          // the next layer's first weight slices: in flight while this layer computes and stores
           const ChainLayer& D = Ls[l + 1];
           const int pre1 = D.nkb < S ? D.nkb : S;
-          for (int kb = 0; kb < pre1; ++kb) load_w(D, kb, it_p + nkb + kb);
+          for (int i = 0; i < pre1; ++i) load_w(D, chain_kb(i, n_tile >> 6, (int)crank, D.nkb), it_p + nkb + i);
         }
       }
       __syncwarp();
@@ -950,11 +983,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
             if (col_ok && 2 * i < rows_left) v[i] = __ldg(reinterpret_cast<const float4*>(xbase + (int64_t)(2 * i) * K0 + kb * BK));
           }
         };
-        float4 cur[8], nxt[8];
-        load_tile(0, cur);
-        for (int kb = 0; kb < nkb; ++kb) {
+        // three k-blocks of this thread's rows in registers: 2 x 32 KB per CTA in flight hide the ~1 us the rows take
+        // to arrive (one k-block ahead left the tensor core waiting 0.5 us per k-block)
+        float4 t0[8], t1[8], t2[8];
+        load_tile(0, t0);
+        if (nkb > 1) load_tile(1, t1);
+        auto convert = [&](int kb, const float4 (&cur)[8]) {
           const int s = kb % S, u = kb / S;
-          if (kb + 1 < nkb) load_tile(kb + 1, nxt);
           if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
           uint8_t* tile = smem + s * CHAIN_STAGE_BYTES;
 #pragma unroll
@@ -967,8 +1002,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           fence_async_smem();                                  // generic-proxy tile writes -> visible to the tensor core's reads
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_bar[s])) : "memory");
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        };
+        for (int kb = 0; kb < nkb; kb += 3) {                   // the three buffers rotate: no register copies
+          if (kb + 2 < nkb) load_tile(kb + 2, t2);
+          convert(kb, t0);
+          if (kb + 1 >= nkb) break;
+          if (kb + 3 < nkb) load_tile(kb + 3, t0);
+          convert(kb + 1, t1);
+          if (kb + 2 >= nkb) break;
+          if (kb + 4 < nkb) load_tile(kb + 4, t1);
+          convert(kb + 2, t2);
         }
       }
       const int q = warp & 3, half = (warp - 2) >> 2;
@@ -978,6 +1021,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
         // The bias slice waits in shared memory before the accumulator is complete, the next 32 accumulator columns travel
         // from tensor memory while the current ones are processed, and a sub-tile's store is only waited for when its
         // buffer is needed again: the epilogue is the serial part of a layer (the MMAs of layer l + 1 need all of it).
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // the other half may still be reading the previous layer's slice
         { const int e = tid - 64; if (e < n_tile) bias_s[e] = __ldg(C.bias + n0 + e); }      // N % 256 == 0 (host): all columns exist
         asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(&acc_bar, (uint32_t)(l & 1));
@@ -1028,7 +1072,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           }
           if (leader && half == 0) chain_trace(g, l, TR_COMPUTED);
           // the slices must have LANDED (not only left shared memory) before the peers are told to read them
-          if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          if (q == 0) {           // the storing lane's warp: lane 0 reports to this CTA, lanes 1-4 to the four CTAs in parallel
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&own_bar[l])) : "memory");
+            else if (lane <= CHAIN_CLUSTER) mbar_arrive_remote(&peer_bar[l], (uint32_t)(lane - 1));
+          }
           if (leader && half == 0) chain_trace(g, l, TR_LANDED);
         }
         tc_fence_before();
@@ -1067,15 +1116,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
     }
     it_p += nkb;
     it_m += nkb;
-    if (l + 1 < L) {             // layer boundary: every thread of the four CTAs (release / acquire at cluster scope)
-      tc_fence_before();
-      cluster_sync_all();
-      tc_fence_after();
-      if (tid == 64) chain_trace(g, l, TR_BOUNDARY);
-    }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();              // no CTA leaves while a peer's arrival may still be on its way to the barriers here
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
@@ -1510,6 +1554,7 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
         if (p.epilogue != 1 || p.N % (CHAIN_CLUSTER * 64) || p.N > CHAIN_CLUSTER * 256) return MMB_EUNSUPPORTED;
         const mmb_mlp_layer_params& nx = layers[a * num_layers + l + 1];
         if (nx.x != p.y || nx.Kpad != p.y_stride || p.y_stride < p.N || p.y_stride % 8) return MMB_EINVAL;
+        if (p.y_stride != p.N) return MMB_EUNSUPPORTED;   // the next layer's k-blocks are exactly this layer's 64-column sub-tiles
         c.n_tile = p.N / CHAIN_CLUSTER;
         if (!make_map_bf16_2d(&c.map_y, p.y, (uint64_t)p.Mpad, (uint64_t)p.y_stride, BM)) return MMB_ECUDA;
       } else {

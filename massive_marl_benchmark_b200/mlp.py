@@ -242,6 +242,12 @@ class FusedMLP:
         if out is None:
             out = torch.empty(M, self.out_dim, dtype=torch.float32, device=self.device)
         nl = len(self.layers)
+        # steady state of a rollout loop: same batch, same buffers -> the filled parameter array of the last such call
+        key = (M, x.data_ptr(), out.data_ptr(), out.stride(0))
+        hit = self.__dict__.setdefault("_chain_cache", {}).get(key)
+        if hit is not None and _CHAIN_ENABLED:
+            L.check(lib.mmb_mlp_chain(hit[0], nl, 1, hit[1], st), "mmb_mlp_chain")
+            return out
         arr = (L.MlpLayerParams * nl)()
         for i, l in enumerate(self.layers):
             p = arr[i]
@@ -259,7 +265,11 @@ class FusedMLP:
         folded = False
         if not use_ln and l0.K % 4 == 0 and x.data_ptr() % 16 == 0:
             folded = True
-            if _chain_launch(self, arr, nl, 1, st, (C.c_void_p * 1)(x.data_ptr())):
+            xp = (C.c_void_p * 1)(x.data_ptr())
+            if _chain_launch(self, arr, nl, 1, st, xp):
+                if len(self._chain_cache) >= 8:
+                    self._chain_cache.clear()
+                self._chain_cache[key] = (arr, xp)
                 return out
         L.check(lib.mmb_ln_cast(L.ptr(x), M, Mpad, l0.K, l0.Kpad, L.ptr(self.in_gamma) if use_ln else None,
                                 L.ptr(self.in_beta) if use_ln else None, self.in_eps if use_ln else 0.0, int(use_ln),
@@ -355,6 +365,11 @@ class GroupedMLP:
                 p.y, p.y_stride = acts[i + 1][g].data_ptr(), acts[i + 1].stride(1)
 
         casted = False
+        key = (M, tuple(x.data_ptr() for x in xs), out.data_ptr(), out.stride(0), out.stride(1))
+        hit = self.__dict__.setdefault("_chain_cache", {}).get(key)
+        if hit is not None and _CHAIN_ENABLED:
+            L.check(lib.mmb_mlp_chain(hit[0], nl, G, hit[1], st), "mmb_mlp_chain")
+            return out
         if G <= 2 and self.__dict__.get("_chain_ok") is not False:       # network-major array: [G][layers]
             net_major = (L.MlpLayerParams * (G * nl))()
             for g in range(G):
@@ -362,7 +377,11 @@ class GroupedMLP:
                     fill(net_major[g * nl + i], g, i)
             xl = xs if len(xs) == G else xs * G
             if not use_ln and l0.K % 4 == 0 and all(x.data_ptr() % 16 == 0 for x in xl):
-                if _chain_launch(self, net_major, nl, G, st, (C.c_void_p * G)(*[x.data_ptr() for x in xl])):   # cast folded in
+                xp = (C.c_void_p * G)(*[x.data_ptr() for x in xl])
+                if _chain_launch(self, net_major, nl, G, st, xp):   # cast folded in
+                    if len(self._chain_cache) >= 8:
+                        self._chain_cache.clear()
+                    self._chain_cache[key] = (net_major, xp)
                     return out
             else:
                 cast_inputs()

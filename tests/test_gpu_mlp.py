@@ -336,8 +336,11 @@ def test_forward_follows_the_parameters_across_optimizer_steps(cuda_device):
 @pytest.mark.parametrize("M", [1, 130, 4096, 5000])
 def test_single_launch_chain_equals_layer_by_layer(cuda_device, M):
     """`mmb_mlp_chain` (one launch: clusters of 4 CTAs walk all layers, cluster barrier at the layer boundaries) gives the
-    numbers of the layer-by-layer launches bit for bit - same operands, same k order, same epilogue - for one network and
-    for the actor / critic pair; geometries outside the fused kernel fall back silently."""
+    numbers of the layer-by-layer launches - same bf16 operands, same epilogue; every CTA accumulates the k-blocks it
+    produced itself first, so the fp32 sums differ in the last bits and a hidden activation can round to the neighbouring
+    bf16 value (a few 1e-3 of the row scale at the output; bf16 ulp = 3.9e-3) - for one network and for the actor / critic
+    pair, with the same bits on every repetition (a stale operand tile would show up here); geometries outside the fused
+    kernel fall back silently."""
     from massive_marl_benchmark_b200 import mlp as mm
     dev = cuda_device
     gen = torch.Generator().manual_seed(M)
@@ -355,8 +358,12 @@ def test_single_launch_chain_equals_layer_by_layer(cuda_device, M):
         assert fa.__dict__.get("_chain_ok") is (True if chain else None)
         outs[chain] = (y.clone(), pair.clone())
     mm._CHAIN_ENABLED = True
-    assert torch.equal(outs[True][0], outs[False][0]), float((outs[True][0] - outs[False][0]).abs().max())
-    assert torch.equal(outs[True][1], outs[False][1])
+    assert _rowmax_err(outs[True][0], outs[False][0]) <= 5e-3, _rowmax_err(outs[True][0], outs[False][0])
+    assert _rowmax_err(outs[True][1][0], outs[False][1][0]) <= 5e-3 and _rowmax_err(outs[True][1][1], outs[False][1][1]) <= 5e-3
+    fa = mm.FusedMLP.from_sequential(actor, dev)
+    first = fa(x).clone()
+    for _ in range(20):                                   # identical bits on every repetition
+        assert torch.equal(fa(x), first)
     with torch.no_grad():
         assert _rowmax_err(outs[True][0], actor(x)) <= 3e-2
     # a geometry the fused kernel does not take (hidden width 96): falls back, same interface
