@@ -593,7 +593,9 @@ typedef struct {
   int32_t overlap_prev; /* != 0: programmatic dependent launch - prologue and the first weight tiles are fetched while the
                          * preceding kernel in the stream drains; only the loads of x wait for it.  The caller asserts
                          * that w / bias / ln_* are not written by that preceding kernel (true inside a forward chain). */
-  int32_t _reserved;
+  int32_t operand_type; /* 0: bf16 operands (above).  1 (mmb_mlp_chain only): tf32 - x, w and the hidden layers' y are fp32 and
+                         * nothing is padded or copied: x = the observations [M][K] / the previous layer's output [Mpad][K], w = the
+                         * nn.Linear weight [N][K] as it is, Kpad = their row pitch in elements (multiple of 4), Npad = N. */
 } mmb_mlp_layer_params;
 MMB_API int32_t mmb_mlp_layer(const mmb_mlp_layer_params* p, void* stream);
 

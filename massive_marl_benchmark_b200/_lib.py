@@ -183,7 +183,7 @@ class MlpLayerParams(C.Structure):
     _fields_ = [("M", c_i32), ("N", c_i32), ("K", c_i32), ("Mpad", c_i32), ("Kpad", c_i32), ("Npad", c_i32),
                 ("n_tile", c_i32), ("epilogue", c_i32), ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("ln_gamma", c_vp),
                 ("ln_beta", c_vp), ("ln_eps", c_f), ("stages", c_i32), ("y", c_vp), ("y_stride", c_i64),
-                ("overlap_prev", c_i32), ("_reserved", c_i32)]
+                ("overlap_prev", c_i32), ("operand_type", c_i32)]
 
 
 # name -> (restype, argtypes); every symbol include/mmb.h declares

@@ -73,6 +73,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory (the tensor core reads the upper 19 bits), 8 elements of K per instruction =
+// the same 32 bytes of a SWIZZLE_128B row as 16 bf16, at half the rate.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int umma_n, int umma_m = BM) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -466,7 +483,7 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.n_tile;
   const int n_tile = p.n_tile;
-  // p._reserved == 1: cta_group::2 - the CTA pair (cluster of 2 along M) runs one 256 x n_tile MMA; each CTA holds its
+  // PAIR: cta_group::2 - the CTA pair (cluster of 2 along M) runs one 256 x n_tile MMA; each CTA holds its
   // 128 rows of A and HALF of the weight tile, so 32 KB instead of 48 KB enter each SM per k-block (the measured bound)
   constexpr bool pair = PAIR;
   const int b_bytes = (pair ? n_tile / 2 : n_tile) * BK * 2;
@@ -858,7 +875,12 @@ __device__ __forceinline__ int chain_kb(int i, int n_own, int crank, int nkb) {
   return kb >= nkb ? kb - nkb : kb;
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainArgs g) {
+// TF32: operands stay fp32 end to end (the observations, the nn.Linear weights as they are, fp32 hidden activations):
+// 32-element k-blocks and 32-column sub-tiles instead of 64, kind::tf32 MMAs, no input cast and no kernel-side weight copies.
+template <bool TF32>
+__device__ __forceinline__ void mlp_chain_body(const ChainArgs& g) {
+  constexpr int KBE = TF32 ? 32 : BK;                // elements of K per k-block (one 128-byte swizzled row)
+  constexpr int SUB_SHIFT = TF32 ? 5 : 6;            // log2(columns of a hidden sub-tile = elements of the next layer's k-block)
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[CHAIN_STAGES], empty_bar[CHAIN_STAGES], a_bar[CHAIN_STAGES], acc_bar;
   __shared__ uint64_t own_bar[MMB_MLP_MAX_LAYERS];   // single use: this CTA's own slices of layer l have landed (one arrival per epilogue half)
@@ -882,7 +904,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
     for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&a_bar[i], 8); }
     mbar_init(&acc_bar, 1);
     for (int l = 0; l < L; ++l) {
-      const uint32_t halves = (Ls[l].n_tile >> 6) >= 2 ? 2 : 1;
+      const uint32_t halves = (Ls[l].n_tile >> SUB_SHIFT) >= 2 ? 2 : 1;
       mbar_init(&own_bar[l], halves);
       mbar_init(&peer_bar[l], halves * CHAIN_CLUSTER);
     }
@@ -915,7 +937,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           const int s = itx % S, u = itx / S;
           if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
           mbar_expect_tx(&full_bar[s], (uint32_t)((a_by_tma ? A_STAGE_BYTES : 0) + D.n_tile * BK * 2));
-          tma_load_2d(smem + s * CHAIN_STAGE_BYTES + A_STAGE_BYTES, &D.map_w, kb * BK, (int)crank * D.n_tile, &full_bar[s]);
+          tma_load_2d(smem + s * CHAIN_STAGE_BYTES + A_STAGE_BYTES, &D.map_w, kb * KBE, (int)crank * D.n_tile, &full_bar[s]);
         };
         const int pre = nkb < S ? nkb : S;   // k-blocks whose weight slices were requested ahead (before the data they multiply existed)
         const bool a_tma = !(l == 0 && x32 != nullptr);
@@ -923,7 +945,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
         // soon as this CTA's own stores have landed (own_bar), the peers' slices once every epilogue half of the cluster has
         // reported (peer_bar: remote arrivals, release.cluster).  No other warp waits at a layer boundary.  Stores and
         // loads are both the async proxy and meet in L2 (a fence.proxy.async here would drain the loads in flight: 0.8 us).
-        const int n_own = l == 0 ? 0 : (Ls[l - 1].n_tile >> 6);
+        const int n_own = l == 0 ? 0 : (Ls[l - 1].n_tile >> SUB_SHIFT);
         if (l == 0) {
           for (int kb = 0; kb < pre; ++kb) load_w(C, kb, it_p + kb, a_tma);
           if (g.overlap_prev && a_tma) griddep_wait();        // the input cast is the previous kernel in the stream
@@ -934,19 +956,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           const int itx = it_p + i, kb = chain_kb(i, n_own, (int)crank, nkb);
           if (i >= pre) load_w(C, kb, itx, a_tma);
           if (l > 0 && i == n_own) mbar_wait(&peer_bar[l - 1], 0u);
-          if (a_tma) tma_load_2d(smem + (itx % S) * CHAIN_STAGE_BYTES, &C.map_x, kb * BK, m0, &full_bar[itx % S]);
+          if (a_tma) tma_load_2d(smem + (itx % S) * CHAIN_STAGE_BYTES, &C.map_x, kb * KBE, m0, &full_bar[itx % S]);
         }
         if (l + 1 < L) {          // the next layer's first weight slices: in flight while this layer computes and stores
           const ChainLayer& D = Ls[l + 1];
           const int pre1 = D.nkb < S ? D.nkb : S;
-          for (int i = 0; i < pre1; ++i) load_w(D, chain_kb(i, n_tile >> 6, (int)crank, D.nkb), it_p + nkb + i);
+          for (int i = 0; i < pre1; ++i) load_w(D, chain_kb(i, n_tile >> SUB_SHIFT, (int)crank, D.nkb), it_p + nkb + i);
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       // ===== MMA issuer =====
       if (elect_one()) {
-        const uint32_t idesc = umma_idesc_bf16(n_tile);
+        const uint32_t idesc = TF32 ? umma_idesc_tf32(n_tile) : umma_idesc_bf16(n_tile);
         for (int kb = 0; kb < nkb; ++kb) {
           const int itx = it_m + kb, s = itx % S, u = itx / S;
           mbar_wait(&full_bar[s], (uint32_t)(u & 1));
@@ -957,7 +979,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
           const uint32_t a_addr = smem_u32(smem + s * CHAIN_STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j)
-            umma_bf16(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
+            if constexpr (TF32) umma_tf32(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
+            else umma_bf16(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&acc_bar);
@@ -1027,8 +1050,55 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
         mbar_wait(&acc_bar, (uint32_t)(l & 1));
         tc_fence_after();
         if (tid == 64) chain_trace(g, l, TR_ACC_COMPLETE);
-        const int n_sub = n_tile >> 6, halves = n_sub >= 2 ? 2 : 1, per_half = n_sub / halves;
+        const int n_sub = n_tile >> SUB_SHIFT, halves = n_sub >= 2 ? 2 : 1, per_half = n_sub / halves;
         const bool leader = q == 0 && lane == 0;
+        if constexpr (TF32) {
+          if (half < halves) {     // fp32 sub-tiles of 32 columns = one tensor-memory chunk each
+            const int cbeg = half * per_half * 32;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+            uint8_t* buf = out_buf + half * (BM * 128);
+            uint8_t* rowp = buf + (row >> 3) * 1024 + (row & 7) * 128;
+            uint32_t ra[32], rb[32];
+            auto sub_tile = [&](int js, uint32_t (&r)[32], uint32_t (&nxt)[32]) {
+              tmem_ld_wait(r);
+              if (js + 1 < per_half) tmem_ld32_issue(taddr + (js + 1) * 32, nxt);
+              const float4* b4 = reinterpret_cast<const float4*>(bias_s + cbeg + js * 32);
+              float4 x[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = b4[i];
+                // rounded to tf32 here (round-to-nearest): the tensor core itself truncates its fp32 operands
+                x[i] = make_float4(rn_tf32(elu1(__uint_as_float(r[4 * i]) + b.x)), rn_tf32(elu1(__uint_as_float(r[4 * i + 1]) + b.y)),
+                                   rn_tf32(elu1(__uint_as_float(r[4 * i + 2]) + b.z)), rn_tf32(elu1(__uint_as_float(r[4 * i + 3]) + b.w)));
+              }
+              if (js > 0) {                                     // the buffer fed the previous sub-tile's store
+                if (leader) tma_store_wait_read();
+                if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x[c];
+              fence_async_smem();
+              if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+              else asm volatile("bar.sync 2, 128;" ::: "memory");
+              if (leader) {
+                tma_store_2d(&C.map_y, buf, n0 + cbeg + js * 32, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            };
+            tmem_ld32_issue(taddr, ra);
+            for (int js = 0; js < per_half; js += 2) {
+              sub_tile(js, ra, rb);
+              if (js + 1 < per_half) sub_tile(js + 1, rb, ra);
+            }
+            if (q == 0) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&own_bar[l])) : "memory");
+              else if (lane <= CHAIN_CLUSTER) mbar_arrive_remote(&peer_bar[l], (uint32_t)(lane - 1));
+            }
+          }
+        } else
         if (half < halves) {
           const int cbeg = half * per_half * 64;
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
@@ -1123,6 +1193,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_c
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainArgs g) { mlp_chain_body<false>(g); }
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_tf32_kernel(const __grid_constant__ ChainArgs g) { mlp_chain_body<true>(g); }
+
 // ---- host: 2-D tensor maps (rows x Kpad bf16, box = box_rows x 64, SWIZZLE_128B) through the driver entry point ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1168,6 +1241,18 @@ inline bool make_map_f32_out(CUtensorMap* map, const void* base, uint64_t rows, 
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// fp32 operand [rows][cols], row pitch ld elements, box = box_rows x 32 columns (128 bytes), SWIZZLE_128B; columns and rows
+// outside the matrix read as zeros (the tf32 chain pads nothing)
+inline bool make_map_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 inline bool make_map_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
@@ -1409,7 +1494,7 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   // free, which costs the overlap with the previous layer's drain) - hence opt-in.
   static const int pair_pref = [] { const char* v = getenv("MMB_MLP_PAIR"); return v ? atoi(v) : 0; }();
   const bool pair = pair_pref && (p.Mpad / BM) % 2 == 0 && p.n_tile <= 256 && p.n_tile % 32 == 0 && p.n_tile >= 64;
-  p._reserved = pair ? 1 : 0;
+  if (p.operand_type != 0) return MMB_EUNSUPPORTED;   // tf32 operands: mmb_mlp_chain only
   if (pair) {
     cm = 2;
     const int sb = A_STAGE_BYTES + (p.n_tile / 2) * BK * 2;
@@ -1529,6 +1614,10 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
   static thread_local ChainArgs g;
   const mmb_mlp_layer_params& f = layers[0];
   if (f.M <= 0 || f.Mpad % BM || f.Mpad < f.M) return MMB_EINVAL;
+  const bool tf32 = f.operand_type == 1;
+  if (f.operand_type != 0 && f.operand_type != 1) return MMB_EINVAL;
+  if (tf32 && x_fp32) return MMB_EINVAL;               // the fp32 input IS layer 0's x
+  const int kbe = tf32 ? 32 : BK;                      // elements per k-block (128 bytes)
   for (int a = 0; a < CHAIN_MAX_NETS; ++a) g.x32[a] = nullptr;
   if (x_fp32) {     // fp32 [M][K] input of layer 0, cast inside the kernel: rows must be 16-byte addressable
     if (f.K % 4) return MMB_EUNSUPPORTED;
@@ -1544,11 +1633,12 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
       const mmb_mlp_layer_params& r = layers[l];                       // network 0 defines the geometry
       if ((!p.x && !(l == 0 && x_fp32)) || !p.w || !p.bias || !p.y || p.M != f.M || p.Mpad != f.Mpad || p.N <= 0 || p.K <= 0) return MMB_EINVAL;
       if (p.N != r.N || p.K != r.K || p.Kpad != r.Kpad || p.epilogue != r.epilogue || p.y_stride != r.y_stride) return MMB_EINVAL;
-      if (p.Kpad % BK || p.Kpad < p.K) return MMB_EINVAL;
+      if (p.operand_type != f.operand_type) return MMB_EINVAL;
+      if (tf32 ? (p.Kpad % 4 || p.Kpad < p.K) : (p.Kpad % BK || p.Kpad < p.K)) return MMB_EINVAL;
       if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.y)) & 15u) return MMB_EALIGN;
       const bool last = l == num_layers - 1;
       ChainLayer& c = g.l[a][l];
-      c.bias = p.bias; c.N = p.N; c.nkb = p.Kpad / BK; c.epilogue = p.epilogue;
+      c.bias = p.bias; c.N = p.N; c.nkb = tf32 ? (p.K + kbe - 1) / kbe : p.Kpad / BK; c.epilogue = p.epilogue;
       if (!last) {
         // hidden layer: bias + ELU -> bf16, the next layer's operand; its four column slices must be whole 64-column sub-tiles
         if (p.epilogue != 1 || p.N % (CHAIN_CLUSTER * 64) || p.N > CHAIN_CLUSTER * 256) return MMB_EUNSUPPORTED;
@@ -1556,7 +1646,8 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
         if (nx.x != p.y || nx.Kpad != p.y_stride || p.y_stride < p.N || p.y_stride % 8) return MMB_EINVAL;
         if (p.y_stride != p.N) return MMB_EUNSUPPORTED;   // the next layer's k-blocks are exactly this layer's 64-column sub-tiles
         c.n_tile = p.N / CHAIN_CLUSTER;
-        if (!make_map_bf16_2d(&c.map_y, p.y, (uint64_t)p.Mpad, (uint64_t)p.y_stride, BM)) return MMB_ECUDA;
+        if (tf32 ? !make_map_f32_2d(&c.map_y, p.y, (uint64_t)p.Mpad, (uint64_t)p.N, (uint64_t)p.y_stride, BM)
+                 : !make_map_bf16_2d(&c.map_y, p.y, (uint64_t)p.Mpad, (uint64_t)p.y_stride, BM)) return MMB_ECUDA;
       } else {
         // last layer: bias -> fp32 [M][N], TMA-addressable; the cluster splits round_up(N, 128) columns
         if (p.epilogue != 0 || (p.y_stride & 3) || p.y_stride < p.N) return MMB_EUNSUPPORTED;
@@ -1567,9 +1658,16 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
       }
       // weights [Npad rows >= N][Kpad]: slices beyond the allocated rows are zero-filled by the TMA (out-of-bounds box rows)
       if (p.Npad < p.N) return MMB_EINVAL;
-      if (!make_map_bf16_2d(&c.map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)c.n_tile)) return MMB_ECUDA;
-      if (l == 0 && x_fp32) c.map_x = c.map_w;              // unused: layer 0's A tiles are cast in the kernel
-      else if (!make_map_bf16_2d(&c.map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM)) return MMB_ECUDA;
+      if (tf32) {
+        // fp32 operands as they are: w = the nn.Linear weight [N][K] (pitch Kpad), x = the observations [M][K] (layer 0) or the
+        // previous layer's fp32 output [Mpad][K]; the K tail and missing rows are zero-filled by the TMA
+        if (!make_map_f32_2d(&c.map_w, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.Kpad, (uint32_t)c.n_tile)) return MMB_ECUDA;
+        if (!make_map_f32_2d(&c.map_x, p.x, (uint64_t)(l == 0 ? p.M : p.Mpad), (uint64_t)p.K, (uint64_t)p.Kpad, BM)) return MMB_ECUDA;
+      } else {
+        if (!make_map_bf16_2d(&c.map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)c.n_tile)) return MMB_ECUDA;
+        if (l == 0 && x_fp32) c.map_x = c.map_w;              // unused: layer 0's A tiles are cast in the kernel
+        else if (!make_map_bf16_2d(&c.map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM)) return MMB_ECUDA;
+      }
     }
   }
   g.num_layers = num_layers; g.M = f.M; g.overlap_prev = f.overlap_prev;
@@ -1580,6 +1678,7 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
   static bool attr_done[MMB_MAX_DEVICES] = {};
   if (!attr_done[dev]) {
     if (cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) != cudaSuccess) return MMB_ECUDA;
+    if (cudaFuncSetAttribute(mlp_chain_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) != cudaSuccess) return MMB_ECUDA;
     attr_done[dev] = true;
   }
   {
@@ -1601,7 +1700,7 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, mlp_chain_kernel, g);
+    const cudaError_t le = tf32 ? cudaLaunchKernelEx(&cfg, mlp_chain_tf32_kernel, g) : cudaLaunchKernelEx(&cfg, mlp_chain_kernel, g);
     if (le != cudaSuccess) {
       if (getenv("MMB_DEBUG")) fprintf(stderr, "mmb_mlp_chain: launch failed: %s\n", cudaGetErrorString(le));
       (void)cudaGetLastError();

@@ -227,6 +227,45 @@ class FusedMLP:
                 return t
         return cands[-1]
 
+    def forward_tf32(self, x, out=None):
+        """The same forward with tf32 tensor-core operands (`mmb_mlp_chain`, operand_type 1): the fp32 observations, the LIVE
+        fp32 nn.Linear weights and fp32 hidden activations go to the tensor core as they are (it reads 19 of the 32 bits) -
+        no cast launch, no kernel-side weight copies, nothing to refresh after an optimiser step.  About half the rate of
+        the bf16 path and ~20x closer to the reference's fp32 SGEMM (tests/test_gpu_mlp.py::test_tf32_chain).  Geometries
+        the single-launch kernel does not take raise (there is no per-layer tf32 kernel)."""
+        if x.device.type != "cuda":
+            raise L.MmbError("FusedMLP runs on CUDA tensors only")
+        if self.in_ln is not None or any(l.epilogue == 2 for l in self.layers):
+            raise L.MmbError("forward_tf32: Linear-ELU chains only")
+        M = x.shape[0]
+        x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        Mpad = _round_up(M, 128)
+        bufs = self.__dict__.setdefault("_bufs32", {})
+        if M not in bufs:
+            bufs[M] = [torch.zeros(Mpad, l.N, dtype=torch.float32, device=self.device) for l in self.layers[:-1]]
+        acts = bufs[M]
+        if out is None:
+            out = torch.empty(M, self.out_dim, dtype=torch.float32, device=self.device)
+        nl = len(self.layers)
+        arr = (L.MlpLayerParams * nl)()
+        keep = []
+        for i, l in enumerate(self.layers):
+            w, b = l._src
+            if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and b.is_cuda and b.dtype == torch.float32):
+                raise L.MmbError("forward_tf32 reads the live fp32 parameters: they must be contiguous CUDA tensors")
+            if l.n_src != l.N:
+                raise L.MmbError("forward_tf32: zero-padded heads are a bf16-path feature")
+            p = arr[i]
+            src = x if i == 0 else acts[i - 1]
+            p.M, p.N, p.K, p.Mpad, p.Kpad, p.Npad, p.n_tile, p.epilogue = M, l.N, l.K, Mpad, src.stride(0), l.N, 0, l.epilogue
+            p.x, p.w, p.bias = src.data_ptr(), w.data_ptr(), b.data_ptr()
+            p.overlap_prev, p.operand_type = 0, 1
+            dst = out if i == nl - 1 else acts[i]
+            p.y, p.y_stride = dst.data_ptr(), dst.stride(0)
+            keep += [w, b]
+        L.check(L.lib().mmb_mlp_chain(arr, nl, 1, None, L.stream_ptr()), "mmb_mlp_chain (tf32)")
+        return out
+
     def forward(self, x, out=None):
         """x fp32 [M, in_dim] on the device -> fp32 [M, out_dim]."""
         if x.device.type != "cuda":

@@ -374,3 +374,34 @@ def test_single_launch_chain_equals_layer_by_layer(cuda_device, M):
     assert fs._chain_ok is False
     with torch.no_grad():
         assert _rowmax_err(ys, small(xs)) <= 3e-2
+
+
+@pytest.mark.parametrize("M", [1, 130, 4096])
+def test_tf32_chain(cuda_device, M):
+    """`FusedMLP.forward_tf32`: the single-launch chain with kind::tf32 MMAs on the fp32 observations and the LIVE fp32
+    nn.Linear weights (no casts, no copies).  Against torch's fp32 SGEMM forward (the reference's path, allow_tf32 off) the
+    error is well below the bf16 path's on the same inputs, and an in-place optimiser step is seen without
+    any refresh."""
+    from massive_marl_benchmark_b200 import mlp as mm
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(100 + M)
+    torch.manual_seed(M)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    actor = _ppo_net(388, [1024, 1024, 512], 80, 1.0, gen).to(dev)
+    x = torch.clamp(torch.randn(M, 388, generator=gen) * 2.0, -5, 5).to(dev)
+    f = mm.FusedMLP.from_sequential(actor, dev)
+    with torch.no_grad():
+        ref = actor(x)
+    e_tf32 = _rowmax_err(f.forward_tf32(x), ref)
+    e_bf16 = _rowmax_err(f(x), ref)
+    print("tf32 %.2e  bf16 %.2e" % (e_tf32, e_bf16))
+    assert e_tf32 <= 5e-3, e_tf32            # the tensor core truncates fp32 operands to tf32 (weights and observations go in as they are)
+    assert e_tf32 < 0.6 * e_bf16
+    first = f.forward_tf32(x).clone()
+    for _ in range(10):
+        assert torch.equal(f.forward_tf32(x), first)
+    with torch.no_grad():
+        for prm in actor.parameters():
+            prm.add_(0.01 * torch.randn(prm.shape, generator=gen).to(dev))
+        ref2 = actor(x)
+    assert _rowmax_err(f.forward_tf32(x), ref2) <= 5e-3

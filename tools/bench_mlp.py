@@ -55,6 +55,26 @@ for name, dims in (("ppo_actor", [388, 1024, 1024, 512, 80]), ("ppo_critic", [38
     out[name] = {"M": M, "dims": dims, "gflop": flops / 1e9, "ours_ms": t_ours, "torch_fp32_ms": t_fp32, "torch_bf16_ms": t_bf16,
                  "ours_tflops": flops / t_ours / 1e9, "torch_fp32_tflops": flops / t_fp32 / 1e9,
                  "kernel_ms": {k: v[0] / v[1] for k, v in prof.items()}, "kernel_launches": {k: v[1] / 20 for k, v in prof.items()}}
+# ---- the tf32 variant of the single-launch chain: error and rate beside the bf16 path, both against torch fp32 ----
+dims = [388, 1024, 1024, 512, 80]
+n32 = net(dims).to(dev)
+x = torch.clamp(torch.randn(M, dims[0], device=dev) * 2.0, -5, 5)
+f = FusedMLP.from_sequential(n32, dev)
+with torch.no_grad():
+    ref = n32(x)
+
+
+def rowmax_err(a, b):
+    floor = b.pow(2).mean().sqrt().clamp(min=1e-6)
+    return float(((a - b).abs().amax(dim=1) / torch.maximum(b.abs().amax(dim=1), floor)).max())
+
+
+flops = 2 * M * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+t_tf32, t_bf16c = timeit(lambda: f.forward_tf32(x)), timeit(lambda: f(x))
+out["ppo_actor_tf32"] = {"M": M, "dims": dims, "tf32_ms": t_tf32, "tf32_tflops": flops / t_tf32 / 1e9, "bf16_ms": t_bf16c,
+                         "rowmax_err_vs_torch_fp32": {"tf32": rowmax_err(f.forward_tf32(x), ref), "bf16": rowmax_err(f(x), ref)},
+                         "max_abs_err_vs_torch_fp32": {"tf32": float((f.forward_tf32(x) - ref).abs().max()), "bf16": float((f(x) - ref).abs().max())},
+                         "output_rms": float(ref.pow(2).mean().sqrt())}
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bench_mlp.json", "w"), indent=1)
