@@ -280,6 +280,11 @@ typedef struct {
    * With it a flag row is scanned by one CTA per 4096 envs (chunk totals published to the scratch, every CTA looks back at
    * its predecessors) instead of by a single CTA: needed from ~16 k envs per row upwards.  NULL: one CTA per row. */
   uint64_t* scan_scratch;
+  /* Optional (noise_mode 1): the Philox counter base lives in DEVICE memory - read by the launch instead of `step`, then
+   * advanced by num_rows (by the launch itself when it is a single CTA - one row of <= 8192 envs -, else by a one-thread
+   * kernel behind it) - so that a captured CUDA graph of the per-step path draws fresh numbers on every replay.
+   * NULL: `step`. */
+  uint64_t* step_counter;
   mmb_ant_consts c;
 } mmb_reset_params;
 

@@ -86,7 +86,8 @@ class ResetParams(C.Structure):
         ("index_b", c_vp), ("index_b_row_stride", c_i64), ("counts", c_vp),
         ("dof_state", c_vp), ("dof_state_row_stride", c_i64),
         ("noise_pos", c_vp), ("noise_vel", c_vp), ("noise_row_stride", c_i64),
-        ("seed", c_u64), ("step", c_u64), ("forces_state", c_vp), ("scan_scratch", c_vp), ("c", AntConsts)]
+        ("seed", c_u64), ("step", c_u64), ("forces_state", c_vp), ("scan_scratch", c_vp), ("step_counter", c_vp),
+        ("c", AntConsts)]
 
 
 class RolloutAddParams(C.Structure):

@@ -98,7 +98,7 @@ __device__ __forceinline__ void write_lists(unsigned bits, int e0, int i, const 
 // ten_ant.py:822-857 / one_ant.py:371-376 for the reset envs with row ordinals [seg0, seg0 + count): one item per
 // (reset env, DOF pair); the pair's (pos, vel, pos, vel) goes out as one 128-bit store per ant
 __device__ __forceinline__ void rerandomise_dofs(const mmb_reset_params& p, const TaskShape& sh, int f, int seg0, int count,
-                                                 const int64_t* env_ids, float* dof) {
+                                                 const int64_t* env_ids, float* dof, uint64_t step) {
   const float* npos = p.noise_pos ? p.noise_pos + (int64_t)f * p.noise_row_stride : nullptr;
   const float* nvel = p.noise_vel ? p.noise_vel + (int64_t)f * p.noise_row_stride : nullptr;
   const bool al16 = (reinterpret_cast<uintptr_t>(dof) & 15u) == 0;
@@ -110,7 +110,7 @@ __device__ __forceinline__ void rerandomise_dofs(const mmb_reset_params& p, cons
       np0 = npos[(int64_t)i * 8 + j0]; np1 = npos[(int64_t)i * 8 + j0 + 1];
       nv0 = nvel[(int64_t)i * 8 + j0]; nv1 = nvel[(int64_t)i * 8 + j0 + 1];
     } else {  // torch_rand_float(lo, hi) = (hi - lo) * U[0,1) + lo, keyed by env so every ant shares the draw
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(p.step + f), (uint32_t)jp, 0u),
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(step + f), (uint32_t)jp, 0u),
                                     make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
       np0 = fadd(fmul(0.4f, u01(r.x)), -0.2f); nv0 = fadd(fmul(0.2f, u01(r.y)), -0.1f);
       np1 = fadd(fmul(0.4f, u01(r.z)), -0.2f); nv1 = fadd(fmul(0.2f, u01(r.w)), -0.1f);
@@ -135,6 +135,9 @@ constexpr int INGENUITY_FILL_CTAS = 8;   // extra CTAs (blockIdx.y >= 1) that sp
 __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_reset_params p) {
   __shared__ int warp_tot[RNT / 32];
   __shared__ int s_chunk_total;
+  // per-step path (mmb_ten_ant_env_step): the step kernel behind this launch is a programmatic dependent - it may load and
+  // compute its frame while this CTA compacts, and waits for this grid only before it touches the task state
+  griddep_launch_dependents();
   const int f = blockIdx.x;
   const int tid = threadIdx.x;
   const int N = p.num_envs;
@@ -162,6 +165,8 @@ __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_
   int64_t* env_ids = p.env_ids + (int64_t)f * p.env_ids_row_stride;
   int32_t* ia = p.index_a ? p.index_a + (int64_t)f * p.index_a_row_stride : nullptr;
   int32_t* ib = p.index_b ? p.index_b + (int64_t)f * p.index_b_row_stride : nullptr;
+  // Philox counter base: the device-resident word (CUDA-graph replays draw fresh numbers) or the host's value
+  const uint64_t step = p.step_counter ? *p.step_counter : p.step;
 
   // ordered rank of a flagged env = flagged envs of the earlier passes + exclusive scan of the per-thread counts + its
   // rank among the thread's sixteen.  One pass and two barriers for N <= 4096.
@@ -176,11 +181,14 @@ __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_
   }
   const int count = running;
   if (tid == 0 && p.counts) p.counts[f] = count;
+  // a single-CTA launch (the per-step path) advances the device counter itself: every thread has read it before the
+  // barriers of the scan above.  Larger grids leave it to the one-thread kernel behind the launch.
+  if (tid == 0 && p.step_counter && p.noise_mode == 1 && gridDim.x * gridDim.y == 1) *p.step_counter = step + 1;
   if (count == 0) return;
   __syncthreads();                        // env_ids of this row (written by this CTA) are read back below
 
   float* dof = p.dof_state ? p.dof_state + (int64_t)f * p.dof_state_row_stride : nullptr;
-  if (sh.ants > 0 && dof) rerandomise_dofs(p, sh, f, 0, count, env_ids, dof);
+  if (sh.ants > 0 && dof) rerandomise_dofs(p, sh, f, 0, count, env_ids, dof, step);
   if (p.task == MMB_TASK_INGENUITY) {
     // (the all-envs rotor-speed write of multi_ingenuity.py:234-241 is done by the fill CTAs, blockIdx.y >= 1)
     if (p.forces_state) {  // multi_ingenuity.py:243-244
@@ -193,6 +201,11 @@ __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_
   }
 }
 
+__global__ void bump_step_counter_kernel(uint64_t* counter, uint64_t by) {
+  griddep_launch_dependents();
+  *counter += by;
+}
+
 // One CTA per 4096-env chunk of a flag row (grid = chunks x rows), decoupled look-back: every CTA publishes its chunk total
 // to the caller's scratch, sums the totals of the chunks before it (earlier CTAs in launch order: forward progress as in
 // any single-pass scan), and writes its own ordered segment.  The CTA that completes the row's look-backs last clears
@@ -200,6 +213,7 @@ __global__ void __launch_bounds__(RNT) reset_kernel(const __grid_constant__ mmb_
 __global__ void __launch_bounds__(RNT) reset_scan_kernel(const __grid_constant__ mmb_reset_params p) {
   __shared__ int warp_tot[RNT / 32];
   __shared__ int s_running, s_chunk_total;
+  griddep_launch_dependents();            // (see reset_kernel)
   const int f = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   unsigned long long* status = reinterpret_cast<unsigned long long*>(p.scan_scratch) + (size_t)f * (chunks + 1);   // [chunks] totals, [chunks] done counter
   const int tid = threadIdx.x, lane = tid & 31;
@@ -211,6 +225,9 @@ __global__ void __launch_bounds__(RNT) reset_scan_kernel(const __grid_constant__
   int32_t* ia = p.index_a ? p.index_a + (int64_t)f * p.index_a_row_stride : nullptr;
   int32_t* ib = p.index_b ? p.index_b + (int64_t)f * p.index_b_row_stride : nullptr;
 
+  // Philox counter base, read before this CTA publishes anything: the CTA that sees every look-back of the row complete
+  // (below) may then advance the device-resident word
+  const uint64_t step = p.step_counter ? *reinterpret_cast<const volatile uint64_t*>(p.step_counter) : p.step;
   const int e0 = chunk * RCHUNK + RFPT * tid;
   const unsigned bits = load_flags16(f64, f8, e0, N);
   const int excl = block_exclusive_scan(__popc(bits), warp_tot, &s_chunk_total);
@@ -238,13 +255,14 @@ __global__ void __launch_bounds__(RNT) reset_scan_kernel(const __grid_constant__
     __threadfence();
     if (atomicAdd(status + chunks, 1ull) == (unsigned long long)chunks - 1ull) {   // every CTA of the row has looked back
       for (int j = 0; j <= chunks; ++j) status[j] = 0ull;
+      if (p.step_counter && p.noise_mode == 1 && gridDim.y == 1) *p.step_counter = step + 1;   // single row: no kernel behind
     }
   }
   if (seg_n == 0) return;
   __syncthreads();                        // this CTA's env_ids segment is read back below
 
   float* dof = p.dof_state ? p.dof_state + (int64_t)f * p.dof_state_row_stride : nullptr;
-  if (sh.ants > 0 && dof) rerandomise_dofs(p, sh, f, seg0, seg_n, env_ids, dof);
+  if (sh.ants > 0 && dof) rerandomise_dofs(p, sh, f, seg0, seg_n, env_ids, dof, step);
 }
 
 }  // namespace
@@ -268,6 +286,11 @@ extern "C" int32_t mmb_reset_compact(const mmb_reset_params* pp, void* stream) {
     else
       reset_kernel<<<dim3(p.num_rows, (p.task == MMB_TASK_INGENUITY && p.dof_state) ? 1 + INGENUITY_FILL_CTAS : 1), RNT, 0,
                      (cudaStream_t)stream>>>(p);
+    // a single-row launch advances the device counter itself (reset_kernel: its only CTA; reset_scan_kernel: the CTA that
+    // completes the row); several rows - the horizon-batched reset lists - leave it to a one-thread kernel behind the launch
+    const bool in_kernel = p.num_rows == 1 && p.task != MMB_TASK_INGENUITY;
+    if (p.step_counter && p.noise_mode == 1 && !in_kernel)
+      bump_step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p.step_counter, (uint64_t)p.num_rows);
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

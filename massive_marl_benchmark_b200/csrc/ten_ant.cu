@@ -1176,7 +1176,14 @@ extern "C" int32_t mmb_ten_ant_env_step(const mmb_reset_params* reset, const mmb
   if (!reset || !step) return MMB_EINVAL;
   const int32_t rc = mmb_reset_compact(reset, stream);
   if (rc != MMB_OK) return rc;
-  return mmb_ten_ant_step(step, stream);
+  // The step kernel reads nothing the reset launch writes (index lists, staged DOF rows, counts) and the reset launch reads
+  // only the flags the step kernel REPLACES at its very end, behind griddepcontrol.wait: so the step is launched as a
+  // programmatic dependent of the reset launch - frame loads, observations and partial rewards overlap the compaction, the
+  // task-state part (progress / reset flags / carry) is ordered behind it.  Everything older than the reset launch has
+  // completed before that launch started (it is an ordinary launch), so the early part races with nothing.
+  mmb_ten_ant_params s = *step;
+  if (s.num_frames == 1) s.overlap_prev = 1;
+  return mmb_ten_ant_step(&s, stream);
 }
 
 #ifdef MMB_TRACE

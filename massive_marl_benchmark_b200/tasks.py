@@ -80,7 +80,16 @@ class BaseTask:
         self.reset_noise = None          # parity mode: (positions [N,8], velocities [N,8]); None -> Philox
         self.reset_seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
         self._step_count = 0
+        self._step_counter_dev = None    # device-resident Philox counter (CUDA-graph replays of the per-step path)
         L.lib()  # fail here, loudly, if the CUDA library is missing
+
+    def use_device_step_counter(self):
+        """From now on the reset noise's Philox counter lives on the device (read and incremented by the launches themselves,
+        include/mmb.h `step_counter`): a captured CUDA graph of `step` then draws fresh numbers on every replay.  The
+        sequence continues where the host-side counter stood."""
+        if self._step_counter_dev is None:
+            self._step_counter_dev = torch.tensor([self._step_count], dtype=torch.int64, device=self.device)
+        return self._step_counter_dev
 
     @property
     def randomize_buf(self):
@@ -198,6 +207,7 @@ class TenAnt(BaseTask):
             p.noise_pos, p.noise_vel = L.ptr(self._noise_keep[0]), L.ptr(self._noise_keep[1])
         else:
             p.noise_mode, p.step = 1, self._step_count
+            p.step_counter = L.ptr(self._step_counter_dev)
         return p
 
     def _prev_root_for_replay(self):
@@ -424,20 +434,24 @@ class OneAnt(BaseTask):
 
     def reset_idx(self, env_ids=None):
         """one_ant.py:363-391"""
-        p = L.ResetParams()
-        p.task, p.num_envs, p.num_rows = L.TASK_ONE_ANT, self.num_envs, 1
-        p.flags_i64 = L.ptr(self.reset_buf)
-        p.env_ids, p.index_a, p.index_b, p.counts = (L.ptr(self.env_ids), L.ptr(self.ant_box_indices),
-                                                     L.ptr(self.ant_indices), L.ptr(self.reset_count))
-        p.dof_state = L.ptr(self.dof_reset_staging)
+        p = self.__dict__.get("_p_reset")
+        if p is None:   # built once: only the noise source and the step counter change between calls
+            p = self._p_reset = L.ResetParams()
+            p.task, p.num_envs, p.num_rows = L.TASK_ONE_ANT, self.num_envs, 1
+            p.flags_i64 = L.ptr(self.reset_buf)
+            p.env_ids, p.index_a, p.index_b, p.counts = (L.ptr(self.env_ids), L.ptr(self.ant_box_indices),
+                                                         L.ptr(self.ant_indices), L.ptr(self.reset_count))
+            p.dof_state = L.ptr(self.dof_reset_staging)
+            p.seed = self.reset_seed
+            p.c = self.consts
+            p.scan_scratch = L.ptr(_reset_scan_scratch(self, 1))
         if self.reset_noise is not None:
             p.noise_mode = 0
             self._noise_keep = tuple(t.contiguous() for t in self.reset_noise)
             p.noise_pos, p.noise_vel = L.ptr(self._noise_keep[0]), L.ptr(self._noise_keep[1])
         else:
-            p.noise_mode, p.seed, p.step = 1, self.reset_seed, self._step_count
-        p.c = self.consts
-        p.scan_scratch = L.ptr(_reset_scan_scratch(self, 1))
+            p.noise_mode, p.step = 1, self._step_count
+            p.step_counter = L.ptr(self._step_counter_dev)
         L.check(L.lib().mmb_reset_compact(p, L.stream_ptr()), "mmb_reset_compact")
         self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
         self.provider.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)
@@ -523,12 +537,14 @@ class MultiIngenuity(BaseTask):
 
     def reset_idx(self, env_ids=None):
         """multi_ingenuity.py:231-266"""
-        p = L.ResetParams()
-        p.task, p.num_envs, p.num_rows = L.TASK_INGENUITY, self.num_envs, 1
-        p.flags_i64 = L.ptr(self.reset_buf)
-        p.env_ids, p.index_a, p.counts = L.ptr(self.env_ids), L.ptr(self.actor_indices), L.ptr(self.reset_count)
+        p = self.__dict__.get("_p_reset")
+        if p is None:   # nothing in it changes between calls (no noise in this reset)
+            p = self._p_reset = L.ResetParams()
+            p.task, p.num_envs, p.num_rows = L.TASK_INGENUITY, self.num_envs, 1
+            p.flags_i64 = L.ptr(self.reset_buf)
+            p.env_ids, p.index_a, p.counts = L.ptr(self.env_ids), L.ptr(self.actor_indices), L.ptr(self.reset_count)
+            p.noise_mode = 1
         p.dof_state = L.ptr(self.dof_state)
-        p.noise_mode = 1
         L.check(L.lib().mmb_reset_compact(p, L.stream_ptr()), "mmb_reset_compact")
         self.provider.set_actor_root_state_tensor_indexed(self.initial_root_states, self.actor_indices, self.reset_count)
         self.provider.set_dof_state_tensor_indexed(self.dof_state, self.actor_indices, self.reset_count)
@@ -605,6 +621,7 @@ def reset_replay(task, flags_u8, dof_out=None, noise=None, out=None):
         p.noise_pos, p.noise_vel, p.noise_row_stride = L.ptr(noise[0]), L.ptr(noise[1]), noise[0].stride(0)
     else:
         p.noise_mode, p.seed, p.step = 1, task.reset_seed, task._step_count
+        p.step_counter = L.ptr(task._step_counter_dev)      # set -> the launch reads and advances the device-side counter
     if kind != L.TASK_INGENUITY:
         p.c = task.consts
         p.scan_scratch = L.ptr(_reset_scan_scratch(task, F))

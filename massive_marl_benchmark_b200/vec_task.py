@@ -192,3 +192,132 @@ class MultiVecTaskPython(MultiVecTask):
         self.task.step(actions)
         obs_all, state_all = self._views()
         return obs_all, state_all, None
+
+
+class _GraphedStep:
+    """CUDA-graphed `task.step` over a looping `ReplayProvider` ring (B200-native addition; the reference has no counterpart:
+    its `step` is ~40 eager torch launches).  One graph per frame slot of the ring, captured the first time the slot comes
+    up: reset compaction + fused step kernel exactly as the eager call enqueues them, reading the actions from ONE static
+    tensor (`actions_in`) and writing the observation into ONE static tensor per output shape.  A later step of the same slot
+    is a single `cudaGraphLaunch` plus a few host assignments.
+
+    What makes the capture replayable: the reset noise's Philox counter lives in device memory and is advanced by the reset
+    launch itself (`task.use_device_step_counter`, include/mmb.h `step_counter`), progress / reset flags / carries are device
+    state anyway, and everything the host tracks (`provider.cursor`, the lazy `randomize_buf` count, `root_states` /
+    `dof_state` views) is re-applied here per replay.
+
+    Ownership differs from the eager path and is the usual CUDA-graph contract: the observation tensors returned by `step`
+    are the SAME tensors every step (overwritten by the next step); `reset()` returns a clone, so the reference's
+    `current_obs = reset(); ...; current_obs.copy_(next_obs)` loop (ppo.py:128-139) stays correct."""
+
+    def __init__(self, task):
+        from .providers import ReplayProvider
+        prov = task.provider
+        if not isinstance(prov, ReplayProvider) or not prov.loop:
+            raise TypeError("graphed stepping needs frames resident in HBM (a looping ReplayProvider)")
+        self.task = task
+        n_act = getattr(task, "num_actions_total", None) or task.actions.shape[1]
+        self.actions_in = torch.zeros(task.num_envs, n_act, device=task.device)
+        self._outs = {}
+        self._graphs = {}
+        self._pool = None
+        self._eager_left = 1          # one eager step first: modules loaded, function attributes set before any capture
+        self.captures = 0
+        task.use_device_step_counter()
+
+    def _static_out(self, *shape):
+        out = self._outs.get(shape)
+        if out is None:
+            out = self._outs[shape] = torch.zeros(shape, device=self.task.device, dtype=torch.float)
+        return out
+
+    _FRAME_ATTRS = ("root_states", "dof_state", "vec_sensor_tensor")
+
+    def step(self):
+        t = self.task
+        prov = t.provider
+        if self._eager_left > 0:
+            self._eager_left -= 1
+            t._fresh_out = self._static_out
+            try:
+                t.step(self.actions_in)
+            finally:
+                del t._fresh_out
+            return
+        slot = (prov.cursor + t.control_freq_inv) % prov.num_frames
+        rec = self._graphs.get(slot)
+        if rec is None:
+            pending = t._randomize_pending
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            t._fresh_out = self._static_out
+            try:
+                with torch.cuda.graph(g, pool=self._pool):
+                    t.step(self.actions_in)        # advances the host-side state once; the kernels run at the replay below
+            finally:
+                del t._fresh_out
+            rec = self._graphs[slot] = (g, tuple((k, getattr(t, k)) for k in self._FRAME_ATTRS if hasattr(t, k)),
+                                        t._randomize_pending - pending)
+            self.captures += 1
+        else:
+            prov.cursor += t.control_freq_inv
+            t._step_count += 1
+            t._randomize_pending += rec[2]
+            for k, v in rec[1]:
+                setattr(t, k, v)
+        rec[0].replay()
+
+
+class GraphedVecTaskPython(VecTaskPython):
+    """`VecTaskPython` whose `step` replays a CUDA graph (see `_GraphedStep`): same arguments and return tuple as
+    vec_task.py:121-139.  `actions_in` is the static action tensor the graphs read: a policy that writes its clamped sample
+    there (`step()` without argument, or `step(env.actions_in)`) saves the copy `step(actions)` otherwise makes."""
+
+    def __init__(self, task, rl_device, clip_observations=5.0, clip_actions=1.0):
+        super().__init__(task, rl_device, clip_observations, clip_actions)
+        self._g = _GraphedStep(task)
+        self.actions_in = self._g.actions_in
+
+    def step(self, actions=None):
+        if actions is not None and actions is not self.actions_in:
+            self.actions_in.copy_(actions)
+        self._g.step()
+        t = self.task
+        if self._same_device(t):
+            return t.obs_clamped, t.rew_buf, t.reset_buf, t.extras
+        return (t.obs_clamped.to(self.rl_device), t.rew_buf.to(self.rl_device), t.reset_buf.to(self.rl_device), t.extras)
+
+    def reset(self):
+        torch.rand(self.actions_in.shape, dtype=torch.float32, device=self.actions_in.device, out=self.actions_in)
+        self.actions_in.mul_(-2.0).add_(1.0).mul_(0.01)        # 0.01 * (1 - 2 u), vec_task.py:133-134, same roundings
+        self._g.step()
+        return self.task.obs_clamped.clone().to(self.rl_device)
+
+
+class GraphedMultiVecTaskPython(MultiVecTaskPython):
+    """`MultiVecTaskPython` whose `step` replays a CUDA graph (see `_GraphedStep`); a list of per-agent action tensors is
+    gathered into `actions_in` by one `torch.cat(..., out=)`."""
+
+    def __init__(self, task, rl_device, clip_observations=7.0, clip_actions=1.0):
+        super().__init__(task, rl_device, clip_observations, clip_actions)
+        self._g = _GraphedStep(task)
+        self.actions_in = self._g.actions_in
+
+    def step(self, actions=None):
+        if isinstance(actions, (list, tuple)):
+            torch.cat(tuple(actions), dim=1, out=self.actions_in)
+        elif actions is not None and actions is not self.actions_in:
+            self.actions_in.copy_(actions)
+        self._g.step()
+        N, A = self.num_environments, self.num_agents
+        obs_all, state_all = self._views()
+        reward_all = self.task.rew_buf.view(N, 1, 1).expand(N, A, 1)
+        done_all = self.task.reset_buf.view(N, 1).expand(N, A)
+        return obs_all, state_all, reward_all, done_all, torch.zeros(A, 0), None
+
+    def reset(self):
+        self.actions_in.zero_()
+        self._g.step()
+        obs_all, state_all = self._views()
+        return obs_all.clone(), state_all.clone(), None

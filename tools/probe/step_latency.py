@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from massive_marl_benchmark_b200 import synthetic
 from massive_marl_benchmark_b200.providers import ReplayProvider
 from massive_marl_benchmark_b200.tasks import TenAnt
-from massive_marl_benchmark_b200.vec_task import VecTaskPython
+from massive_marl_benchmark_b200.vec_task import GraphedVecTaskPython, VecTaskPython
 dev = torch.device("cuda:0")
 root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PEAK = json.load(open(os.path.join(root, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(root, "MEASURED_PEAKS.json")) else 6540.0
@@ -27,6 +27,19 @@ for N in (4096, 16384, 65536, 262144):
     for i in range(K): env.step(acts[i % F])
     e1.record(); torch.cuda.synchronize(); wall = (time.perf_counter() - t0) / K * 1e6
     us = e0.elapsed_time(e1) / K * 1e3
+    # the CUDA-graphed step (one graph per ring slot; actions written into the static tensor by the caller / passed in)
+    tg = TenAnt({"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1},
+                provider=ReplayProvider({"root": fr["root"], "dof": fr["dof"]}, device=dev))
+    genv = GraphedVecTaskPython(tg, dev)
+    for i in range(2 * F + 4): genv.step(acts[i % F])
+    torch.cuda.synchronize()
+    res = {}
+    for name, arg in (("copy", lambda i: acts[i % F]), ("static", lambda i: None)):
+        t0 = time.perf_counter(); e0.record()
+        for i in range(K): genv.step(arg(i))
+        e1.record(); torch.cuda.synchronize()
+        res[name] = (e0.elapsed_time(e1) / K * 1e3, (time.perf_counter() - t0) / K * 1e6)
+    del tg, genv
     T = 16
     obs = torch.zeros(T, N, 388, device=dev); rew = torch.zeros(T, N, device=dev); d8 = torch.zeros(T, N, device=dev, dtype=torch.uint8)
     fo = torch.zeros(T, N, 80, device=dev)
@@ -36,7 +49,10 @@ for N in (4096, 16384, 65536, 262144):
     for _ in range(R): task.replay(frd, acts, obs, rew, d8, None, fo)
     e1.record(); torch.cuda.synchronize()
     ub = e0.elapsed_time(e1) / R * 1e3
-    row = {"envs": N, "per_step_api_us": round(us, 1), "per_step_api_host_us": round(wall, 1), "per_step_api_env_steps_per_s": N / us * 1e6,
+    row = {"envs": N, "graphed_step_us": round(res["static"][0], 1), "graphed_step_host_us": round(res["static"][1], 1),
+           "graphed_step_with_action_copy_us": round(res["copy"][0], 1),
+           "graphed_step_env_steps_per_s": N / res["static"][0] * 1e6, "graphed_step_frac_of_hbm_peak": 3456 * N / res["static"][0] / 1e3 / PEAK,
+           "per_step_api_us": round(us, 1), "per_step_api_host_us": round(wall, 1), "per_step_api_env_steps_per_s": N / us * 1e6,
            "per_step_api_frac_of_hbm_peak": 3456 * N / us / 1e3 / PEAK, "batched16_us_per_launch": round(ub, 1),
            "batched16_env_steps_per_s": T * N / ub * 1e6, "batched16_frac_of_hbm_peak": 3409 * T * N / ub / 1e3 / PEAK}
     out.append(row); print(row, flush=True)
