@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(RNT) reset_scan_kernel(const __grid_constant__
 
   // Philox counter base, read before this CTA publishes anything: the CTA that sees every look-back of the row complete
   // (below) may then advance the device-resident word
-  const uint64_t step = p.step_counter ? *reinterpret_cast<const volatile uint64_t*>(p.step_counter) : p.step;
+  // (not a conditional expression: with a volatile operand its result is a volatile lvalue, and nvcc 12.9 then reads
+  // p.step - a __grid_constant__ member - through a generic address it computes from a null base: a fault)
+  uint64_t step = p.step;
+  if (p.step_counter) step = *reinterpret_cast<const volatile uint64_t*>(p.step_counter);
   const int e0 = chunk * RCHUNK + RFPT * tid;
   const unsigned bits = load_flags16(f64, f8, e0, N);
   const int excl = block_exclusive_scan(__popc(bits), warp_tot, &s_chunk_total);

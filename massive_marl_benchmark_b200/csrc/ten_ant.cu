@@ -224,8 +224,16 @@ __device__ __forceinline__ void finish_env(const mmb_ten_ant_params& p, int t, i
   const float total_r = env_reward(c, pt, bo, fallen);
   if (p.rewards) p.rewards[(int64_t)t * p.rewards_frame_stride + en] = total_r;
   if (T == 1) {
-    p.box_before[(int64_t)en * 2] = bo[2];
-    p.box_before[(int64_t)en * 2 + 1] = bo[3];
+    // carry out (ten_ant.py:905-925).  Role-split kernel: the whole env's carry from the tiles, here - behind barrier B3 -
+    // because the dof thread of an ant reads goal_before (frame 0 without prev_root) after B2: the core thread's write,
+    // which used to follow its own read at once, raced with that read (the reward's goal-distance term saw the NEW goal
+    // whenever the dof warp left griddepcontrol.wait late).  One-thread-per-ant kernel: written by the ant's own thread.
+    if (root_env) {
+      carry_from_tile(p, en, bo, root_env);
+    } else {
+      p.box_before[(int64_t)en * 2] = bo[2];
+      p.box_before[(int64_t)en * 2 + 1] = bo[3];
+    }
     // ten_ant.py:896-901 (progress += 1; reset_idx zeroes progress/reset of flagged envs) + :1296-1299
     int64_t prog = p.progress_buf[en] + 1;
     if (p.reset_buf[en] != 0) prog = 0;
@@ -875,11 +883,6 @@ __global__ void __launch_bounds__(352, MMB_SPLIT_MIN_CTAS) ten_ant_split_kernel(
       float* pt = part_s + a * PART_W;
       pt[0] = adr; pt[2] = up;
       pt[6] = __int_as_float(fallen ? 1 : 0);
-      if (p.num_frames == 1) {  // carry out (ten_ant.py:905-925); T > 1: written once per env by the chain executor
-        float* pb = p.pos_before + ((int64_t)e * A + k) * 2;
-        float* gb = p.goal_before + ((int64_t)e * A + k) * 2;
-        pb[0] = px; pb[1] = py; gb[0] = gx; gb[1] = gy;
-      }
     }
   }
   if (tid == 40) MMB_TR(7);
@@ -1182,7 +1185,8 @@ extern "C" int32_t mmb_ten_ant_env_step(const mmb_reset_params* reset, const mmb
   // task-state part (progress / reset flags / carry) is ordered behind it.  Everything older than the reset launch has
   // completed before that launch started (it is an ordinary launch), so the early part races with nothing.
   mmb_ten_ant_params s = *step;
-  if (s.num_frames == 1) s.overlap_prev = 1;
+  static const bool pdl = [] { const char* v = getenv("MMB_STEP_PDL"); return !(v && v[0] == '0'); }();   // MMB_STEP_PDL=0: plain launch order
+  if (s.num_frames == 1 && pdl) s.overlap_prev = 1;
   return mmb_ten_ant_step(&s, stream);
 }
 

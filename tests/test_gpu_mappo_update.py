@@ -148,3 +148,97 @@ def test_mappo_update_refuses_what_it_does_not_cover(cuda_device):
         mappo_ppo_update(_trainer(actor, critic, None, _use_recurrent_policy=True), sample)
     with pytest.raises(NotImplementedError):
         mappo_ppo_update(_trainer(actor, critic, None), sample[:11] + (torch.ones(16, 4, device=dev), None))
+
+
+def _compare_updates(out_c, out_g, tag):
+    for a, b, name in zip(out_c, out_g, ("value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm")):
+        a, b = float(a), float(b)
+        assert abs(a - b) <= 2e-4 * abs(a) + 2e-6, (tag, name, a, b)
+    assert torch.allclose(out_g[5].cpu(), out_c[5], rtol=2e-4, atol=1e-6), tag          # importance weights
+
+
+def _compare_parameters(pairs, initial):
+    for nets, w0 in zip(pairs, initial):
+        moved = 0
+        for k, w in w0.items():
+            d_c = nets[0].state_dict()[k] - w
+            d_g = nets[1].state_dict()[k].cpu() - w
+            scale = float(d_c.abs().max())
+            ulp = 1.1920929e-07 * float(w.abs().max())
+            assert float((d_g - d_c).abs().max()) <= 2e-4 * scale + 2 * ulp + 1e-9, k
+            moved += scale > 0
+        assert moved == len(w0)
+
+
+def test_ippo_update_matches_the_reference_pinned_oracle(cuda_device):
+    """`ippo_ppo_update` with the fused loss KERNEL (ippo_trainer.py:101-170: ValueNorm.update once, both value error
+    terms on the same moments, the agent's own observation as the critic input) against the oracle that
+    tests/test_oracle_vs_reference.py pins on the reference's IPPO trainer."""
+    from massive_marl_benchmark_b200.mappo_update import ippo_ppo_update
+    from oracle.mappo_loss_oracle import mappo_update_oracle, popart_update
+    dev = cuda_device
+
+    class _ValueNorm(_PopArt):                           # valuenorm.py:39-55: update() only in training mode
+        def update(self, x):
+            popart_update(self.state, x)
+
+        def __call__(self, x):
+            raise AssertionError("IPPO never calls the normaliser in training mode")
+
+    obs_dim, A, B = 46, 8, 512
+    torch.manual_seed(6)
+    actor_c, critic_c = _Actor(obs_dim, A), _Critic(obs_dim)
+    actor_g, critic_g = copy.deepcopy(actor_c).to(dev), copy.deepcopy(critic_c).to(dev)
+    initial = [copy.deepcopy(actor_c.state_dict()), copy.deepcopy(critic_c.state_dict())]
+
+    def state(device):
+        return {"running_mean": torch.zeros(1, device=device), "running_mean_sq": torch.zeros(1, device=device),
+                "debiasing_term": torch.tensor(0.0, device=device)}
+
+    cpu = _trainer(actor_c, critic_c, state("cpu"), _use_popart=False, _use_valuenorm=True)
+    gpu = _trainer(actor_g, critic_g, state(dev), _use_popart=False, _use_valuenorm=True)
+    gpu.value_normalizer = _ValueNorm(gpu.popart)
+    for it in range(3):
+        sample = _sample(actor_c, critic_c, B, obs_dim, obs_dim, A, seed=400 + it)
+        out_c = mappo_update_oracle(cpu, sample, ippo=True)
+        out_g = ippo_ppo_update(gpu, tuple(None if t is None else t.to(dev) for t in sample))
+        _compare_updates(out_c, out_g, it)
+    _compare_parameters(((actor_c, actor_g), (critic_c, critic_g)), initial)
+    assert float(cpu.popart["debiasing_term"]) > 0
+    for k in cpu.popart:
+        assert torch.allclose(gpu.popart[k].cpu(), cpu.popart[k], rtol=1e-6, atol=0), k
+
+
+@pytest.mark.parametrize("over", [dict(), dict(_use_policy_active_masks=True)])
+def test_happo_update_matches_the_reference_pinned_oracle(cuda_device, over):
+    """`happo_ppo_update` with the fused loss KERNEL (happo_trainer.py:93-170: the sequential-update factor inside the
+    surrogate; the drop-in folds a positive factor into the advantage) against the reference-pinned oracle; a per-action
+    factor (first iteration) and a per-row factor."""
+    from massive_marl_benchmark_b200.mappo_update import happo_ppo_update
+    from oracle.mappo_loss_oracle import mappo_update_oracle
+    dev = cuda_device
+    obs_dim, share_dim, A, B = 46, 388, 8, 512
+    torch.manual_seed(7)
+    actor_c, critic_c = _Actor(obs_dim, A), _Critic(share_dim)
+    actor_g, critic_g = copy.deepcopy(actor_c).to(dev), copy.deepcopy(critic_c).to(dev)
+    initial = [copy.deepcopy(actor_c.state_dict()), copy.deepcopy(critic_c.state_dict())]
+
+    def state(device):
+        deb = torch.tensor(1.0 - 0.99999 ** 300)
+        return {"running_mean": (torch.tensor([0.9]) * deb).to(device), "running_mean_sq": (torch.tensor([4.5]) * deb).to(device),
+                "debiasing_term": deb.to(device)}
+
+    cpu = _trainer(actor_c, critic_c, state("cpu"), **over)
+    gpu = _trainer(actor_g, critic_g, state(dev), **over)
+    del gpu._use_valuenorm                               # the HAPPO trainer has no such attribute (happo_trainer.py:30-42)
+    for it in range(3):
+        sample = _sample(actor_c, critic_c, B, obs_dim, share_dim, A, seed=700 + it)
+        g = torch.Generator().manual_seed(800 + it)
+        factor = torch.exp(0.3 * torch.randn(B, 1, generator=g))
+        sample = sample[:12] + (factor if it else factor.repeat(1, A) / A,)
+        out_c = mappo_update_oracle(cpu, sample, happo=True)
+        out_g = happo_ppo_update(gpu, tuple(None if t is None else t.to(dev) for t in sample))
+        _compare_updates(out_c, out_g, (over, it))
+    _compare_parameters(((actor_c, actor_g), (critic_c, critic_g)), initial)
+    for k in cpu.popart:
+        assert torch.allclose(gpu.popart[k].cpu(), cpu.popart[k], rtol=1e-6, atol=0), k
