@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmb_b200.so")
+LIB_PATH = os.environ.get("MMB_LIB_PATH") or os.path.join(_HERE, "libmmb_b200.so")   # MMB_LIB_PATH: diagnostics builds (tools/probe)
 ABI_VERSION = 2
 MAX_GATHER_FIELDS = 16
 

@@ -250,6 +250,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 // multicast variants for thread-block clusters: the tile lands at the same shared-memory offset, and completes on the
 // mbarrier at the same offset, in every CTA of `cta_mask`
 __device__ __forceinline__ void tma_load_2d_mc(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
@@ -833,11 +837,15 @@ constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BK * 2;   // 48 KB: the widest slice (256 columns)
 constexpr int CHAIN_SMEM = CHAIN_STAGES * CHAIN_STAGE_BYTES + 2 * BM * 128;   // ring + two 16 KB output staging buffers = 224 KB
 constexpr int CHAIN_MAX_NETS = 2;
+constexpr int DUO_MAX_STAGES = 8;   // mlp_chain_duo_kernel: stages of the narrowest slices (20 KB each)
+constexpr int DUO_A_WARP = 10;      // its second TMA producer (activation tiles)
+constexpr int DUO_THREADS = WS_THREADS + 32;
 struct ChainLayer {
   CUtensorMap map_x, map_w, map_y;
   const float* bias;
   int N, nkb, n_tile, epilogue;
-  int pad_[10];     // keeps the next element's tensor maps 64-byte aligned
+  int kgroup;       // mlp_chain_duo_kernel: k-blocks per tensor load (map_x / map_w are then 3-D maps, see make_map_bf16_kgroup)
+  int pad_[9];      // keeps the next element's tensor maps 64-byte aligned
 };
 static_assert(sizeof(ChainLayer) % 64 == 0, "tensor maps need 64-byte alignment");
 struct ChainArgs {
@@ -1196,6 +1204,407 @@ __device__ __forceinline__ void mlp_chain_body(const ChainArgs& g) {
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainArgs g) { mlp_chain_body<false>(g); }
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_tf32_kernel(const __grid_constant__ ChainArgs g) { mlp_chain_body<true>(g); }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Two networks on the SAME rows in one CTA (PPO act(): actor and critic of module.py:25-55 read the same observations).
+// Same cluster-of-4 / column-slice decomposition as mlp_chain_kernel, but a CTA walks BOTH networks, alternating
+// between them layer by layer - task (net n, layer l) in the order (0,0) (1,0) (0,1) (1,1) ... - with one 256-column
+// accumulator per network in tensor memory (512 columns = all of it).  The two chains are independent, so the serial part
+// of one network's layer (accumulator -> bias / ELU -> bf16 -> L2 -> peers, ~4 us of the tensor core idling in
+// mlp_chain_kernel) runs UNDER the other network's k-loop: from layer 1 on the tensor core only waits for operands.
+// grid z = 1: 4 x row blocks CTAs do the work 8 x row blocks CTAs of the side-by-side launch did in two waves.
+// Layer 0: the fp32 rows are cast ONCE per k-block and feed both networks - ring slot 2 kb holds [A(kb) | W0(kb)], slot
+// 2 kb + 1 holds [unused | W1(kb)]: 80 KB instead of 96 KB enter the SM per k-block pair, and both accumulators complete
+// together.  Requires x_fp32[0] == x_fp32[1] (cast folded in) and bf16 operands; anything else takes mlp_chain_kernel.
+// Every mbarrier wait is bounded (50 ms, then the CTA stops waiting altogether and records a code for
+// mmb_mlp_debug_status): a protocol error yields garbage, never a hung GPU.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void duo_wait(uint64_t* bar, uint32_t parity, unsigned code, volatile int* abort_flag) {
+  const long long t0 = clock64();
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done) {
+      if (*abort_flag) return;
+      if (clock64() - t0 > 100000000ll) {   // ~50 ms
+        *abort_flag = 1;
+        if (atomicCAS(&g_pair_dbg[0], 0u, code) == 0u) { g_pair_dbg[1] = blockIdx.x; g_pair_dbg[2] = threadIdx.x; g_pair_dbg[3] = parity; }
+        return;
+      }
+    }
+  }
+}
+
+// diagnostics (-DMMB_CHAIN_TRACE_BUILD + MMB_CHAIN_TRACE=1, tools/probe/duo_trace.py): [4 CTAs][16 tasks][8 events]
+enum { DT_PRODUCER = 0, DT_FIRST_OPERANDS = 1, DT_MMA_ISSUED = 2, DT_ACC_COMPLETE = 3, DT_COMPUTED = 4, DT_LANDED = 5, DT_PEERS = 6, DT_EPI_BEGIN = 7 };
+__device__ __forceinline__ void duo_trace(const ChainArgs& g, int task, int ev) {
+#ifdef MMB_CHAIN_TRACE_BUILD
+  if (g.trace != nullptr && blockIdx.x < 4 && task < 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[(blockIdx.x * 16 + task) * 8 + ev] = t;
+  }
+#endif
+}
+__device__ __forceinline__ void duo_trace_kb(const ChainArgs& g, int task, int kb) {     // CTA 0: operands of k-block kb in shared memory
+#ifdef MMB_CHAIN_TRACE_BUILD
+  if (g.trace != nullptr && blockIdx.x == 0 && task < 32 && kb < 16) {   // tasks 16..31: the producer's requests
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[512 + task * 16 + kb] = t;
+  }
+#endif
+}
+
+__global__ void __launch_bounds__(DUO_THREADS, 1) mlp_chain_duo_kernel(const __grid_constant__ ChainArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int SMAX = DUO_MAX_STAGES;
+  __shared__ uint64_t full_bar[SMAX], empty_bar[SMAX], a_bar[SMAX], acc_bar[2];
+  __shared__ uint64_t own_bar[2][MMB_MLP_MAX_LAYERS], peer_bar[2][MMB_MLP_MAX_LAYERS];
+  __shared__ __align__(16) float bias_s[256];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_abort;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(crank));
+  const int m0 = (blockIdx.x / CHAIN_CLUSTER) * BM;
+  const int L = g.num_layers;
+  uint8_t* out_buf = smem + CHAIN_STAGES * CHAIN_STAGE_BYTES;
+  const float* x32 = g.x32[0];
+  volatile int* ab = &s_abort;
+
+  if (tid == 0) {
+    s_abort = 0;
+    for (int i = 0; i < SMAX; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&a_bar[i], 8); }
+    mbar_init(&acc_bar[0], 1); mbar_init(&acc_bar[1], 1);
+    for (int n = 0; n < 2; ++n)
+      for (int l = 0; l < L; ++l) {
+        const uint32_t halves = (g.l[n][l].n_tile >> 6) >= 2 ? 2 : 1;
+        mbar_init(&own_bar[n][l], halves);
+        mbar_init(&peer_bar[n][l], halves * CHAIN_CLUSTER);
+      }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int n = 0; n < 2; ++n)
+      for (int l = 0; l < L; ++l) {
+        if (l > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&g.l[n][l].map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&g.l[n][l].map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&g.l[n][l].map_y) : "memory");
+      }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();              // every CTA's barriers exist before a peer arrives on them
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int nkb0 = g.l[0][0].nkb;
+  // Ring geometry per layer.  What paces a k-loop here is the TMA unit: every tensor load costs it ~0.16 us whatever its
+  // size (0.35 / 0.38 / 0.42 us per k-block = two loads of 160 / 256 / 384 rows: measured with 4, 6 and 8 stages, with one
+  // and with two issuing threads, with and without the MMAs - always the same).  So layers >= 1 load k-blocks in GROUPS of
+  // kgroup (2) through 3-D tensor maps - one load for the activation tiles, one for the weight slices of the group - and a
+  // stage holds a group: [A tile x G | W slice x G].  The stage size of layer l is that of its widest remaining group, so
+  // beyond layer 1 sizes only shrink along the chain: a new stage j then only overlaps old stages of index <= j, whose
+  // barriers the producers re-claim - i.e. wait for - in order before they reach stage j; where stages GROW (layer 0's
+  // single k-blocks -> layer 1's groups) the producers first wait for every barrier's last use.  Barrier s serves stage s of
+  // every geometry; its phase parities are tracked in bit masks.
+  auto stage_bytes = [&](int l) {
+    if (l == 0) return CHAIN_STAGE_BYTES;
+    int sz = 0;
+    for (int j = l; j < L; ++j) sz = max(sz, g.l[0][j].kgroup * (A_STAGE_BYTES + g.l[0][j].n_tile * BK * 2));
+    return sz;
+  };
+  auto stages_of = [](int sz) { const int s = (CHAIN_STAGES * CHAIN_STAGE_BYTES) / sz; return s > SMAX ? SMAX : s; };
+
+  if (warp == 0 || warp == DUO_A_WARP) {
+    // ===== two TMA producers: warp 0 requests the WEIGHT slices, warp 10 the ACTIVATION tiles =====
+    // Both walk the same stage sequence and wait for a stage to be free on their own (non-consuming parity waits); the
+    // weight thread arms the full barrier with the bytes of both loads (an activation group that lands first only drives
+    // the transaction count negative until then).  The weight thread depends on no activations at all, so every layer's
+    // first weight slices are in flight while the previous layer's outputs still travel.
+    if (elect_one()) {
+      const bool wprod = warp == 0;
+      int nxt = 0, sz = stage_bytes(0), S = CHAIN_STAGES;    // nxt: the stage the next claim takes (no division in this loop:
+      uint32_t used = 0, par = 0;                            // a single thread's instruction latencies show in the k-loop)
+      auto claim = [&](bool wait) {          // the next stage of the sequence; waits until it is free
+        const int s = nxt;
+        const uint32_t bit = 1u << s;
+        if (used & bit) { if (wait) duo_wait(&empty_bar[s], (par >> s) & 1u, wprod ? 101u : 104u, ab); par ^= bit; }
+        used |= bit;
+        nxt = (s + 1 == S) ? 0 : s + 1;
+        return s;
+      };
+      for (int kb = 0; kb < nkb0; ++kb)
+        for (int n = 0; n < 2; ++n) {
+          const ChainLayer& C = g.l[n][0];
+          const int s = claim(wprod);        // (layer 0's A tiles are converted by the epilogue warps: the A thread only counts)
+          if (wprod) {
+            mbar_expect_tx(&full_bar[s], (uint32_t)(C.n_tile * BK * 2));
+            tma_load_2d(smem + s * sz + A_STAGE_BYTES, &C.map_w, kb * BK, (int)crank * C.n_tile, &full_bar[s]);
+          }
+        }
+      for (int l = 1; l < L; ++l) {
+        const int nsz = stage_bytes(l);
+        if (nsz != sz) {
+          if (nsz > sz)                      // stages grow: every old stage must have been consumed
+            for (int k = 0; k < S; ++k)
+              if (used & (1u << k)) duo_wait(&empty_bar[k], (par >> k) & 1u, 105u, ab);
+          sz = nsz; S = stages_of(sz); nxt = 0;
+        }
+        for (int n = 0; n < 2; ++n) {
+          const ChainLayer& C = g.l[n][l];
+          const int nkb = C.nkb, n_own = g.l[n][l - 1].n_tile >> 6, G = C.kgroup;
+          const uint32_t a_bytes = (uint32_t)(G * A_STAGE_BYTES), w_bytes = (uint32_t)(G * C.n_tile * BK * 2);
+          if (wprod) {
+            for (int i = 0; i < nkb; i += G) {
+              const int kb = chain_kb(i, n_own, (int)crank, nkb);
+              const int s = claim(true);
+              mbar_expect_tx(&full_bar[s], a_bytes + w_bytes);
+              duo_trace_kb(g, 16 + 2 * l + n, i);
+              if (G == 1) tma_load_2d(smem + s * sz + a_bytes, &C.map_w, kb * BK, (int)crank * C.n_tile, &full_bar[s]);
+              else tma_load_3d(smem + s * sz + a_bytes, &C.map_w, 0, (int)crank * C.n_tile, kb, &full_bar[s]);
+            }
+          } else {
+            // own slices first (requested as soon as this CTA's stores of layer l - 1 have landed), then the peers'
+            duo_wait(&own_bar[n][l - 1], 0u, 102u, ab);
+            duo_trace(g, 2 * l + n, DT_PRODUCER);
+            for (int i = 0; i < nkb; i += G) {
+              const int kb = chain_kb(i, n_own, (int)crank, nkb);
+              if (i == n_own) { duo_wait(&peer_bar[n][l - 1], 0u, 103u, ab); duo_trace(g, 2 * l + n, DT_PEERS); }
+              const int s = claim(true);
+              if (G == 1) tma_load_2d(smem + s * sz, &C.map_x, kb * BK, m0, &full_bar[s]);
+              else tma_load_3d(smem + s * sz, &C.map_x, 0, m0, kb, &full_bar[s]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      int nxt = 0, sz = stage_bytes(0), S = CHAIN_STAGES;
+      uint32_t par = 0;                      // per barrier: parity of the next full phase
+      {
+        const uint32_t idesc = umma_idesc_bf16(g.l[0][0].n_tile);
+        for (int kb = 0; kb < nkb0; ++kb) {
+          const int s0 = nxt, s1 = nxt + 1;  // (four stages: slots in pairs)
+          duo_wait(&full_bar[s0], (par >> s0) & 1u, 111u, ab);
+          duo_wait(&a_bar[s0], (par >> s0) & 1u, 112u, ab);            // the A tile the epilogue warps converted
+          if (kb == 0) { duo_trace(g, 0, DT_FIRST_OPERANDS); duo_trace(g, 1, DT_FIRST_OPERANDS); }
+          duo_trace_kb(g, 0, kb);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s0 * sz);
+          const uint32_t b0_addr = a_addr + A_STAGE_BYTES, b1_addr = smem_u32(smem + s1 * sz) + A_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j)
+            umma_bf16(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b0_addr + j * 32), idesc, (kb > 0) || (j > 0));
+          duo_wait(&full_bar[s1], (par >> s1) & 1u, 113u, ab);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j)
+            umma_bf16(tmem + 256, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b1_addr + j * 32), idesc, (kb > 0) || (j > 0));
+          umma_commit(&empty_bar[s0]);       // (a commit covers every MMA issued before it: slot s0's A tile fed both)
+          umma_commit(&empty_bar[s1]);
+          par ^= (1u << s0) | (1u << s1);
+          nxt = (s1 + 1 == S) ? 0 : s1 + 1;
+        }
+        umma_commit(&acc_bar[0]);
+        umma_commit(&acc_bar[1]);
+        duo_trace(g, 0, DT_MMA_ISSUED); duo_trace(g, 1, DT_MMA_ISSUED);
+      }
+      for (int l = 1; l < L; ++l) {
+        const int nsz = stage_bytes(l);
+        if (nsz != sz) { sz = nsz; S = stages_of(sz); nxt = 0; }
+        for (int n = 0; n < 2; ++n) {
+          const ChainLayer& C = g.l[n][l];
+          const uint32_t idesc = umma_idesc_bf16(C.n_tile);
+          const uint32_t acc = tmem + (uint32_t)(n * 256);
+          const int G = C.kgroup;
+          const uint32_t b_off = (uint32_t)(G * A_STAGE_BYTES), b_step = (uint32_t)(C.n_tile * BK * 2);
+          for (int kb = 0; kb < C.nkb; kb += G) {
+            const int s = nxt;
+            nxt = (s + 1 == S) ? 0 : s + 1;
+            duo_wait(&full_bar[s], (par >> s) & 1u, 114u, ab);
+            par ^= 1u << s;
+            if (kb == 0) duo_trace(g, 2 * l + n, DT_FIRST_OPERANDS);
+            duo_trace_kb(g, 2 * l + n, kb);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + s * sz), b_addr = a_addr + b_off;
+            for (int q = 0; q < G; ++q) {
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j)
+                umma_bf16(acc, umma_desc_k_sw128(a_addr + q * A_STAGE_BYTES + j * 32), umma_desc_k_sw128(b_addr + q * b_step + j * 32), idesc,
+                          (kb > 0) || (q > 0) || (j > 0));
+            }
+            umma_commit(&empty_bar[s]);
+          }
+          umma_commit(&acc_bar[n]);
+          duo_trace(g, 2 * l + n, DT_MMA_ISSUED);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, two warps per quarter split the columns =====
+    {
+      // layer 0's A tiles from the fp32 input, once for both networks (see mlp_chain_body): slot of k-block kb = 2 kb
+      if (g.overlap_prev) griddep_wait();
+      const int w8 = (tid - 64) >> 5, sub = lane >> 4, c4 = lane & 15;
+      const int K0 = g.K0;
+      const float* xbase = x32 + (int64_t)(m0 + w8 * 16 + sub) * K0 + c4 * 4;
+      const int rows_left = g.M - (m0 + w8 * 16 + sub);
+      auto load_tile = [&](int kb, float4 (&v)[8]) {
+        const bool col_ok = kb * BK + c4 * 4 < K0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && 2 * i < rows_left) v[i] = __ldg(reinterpret_cast<const float4*>(xbase + (int64_t)(2 * i) * K0 + kb * BK));
+        }
+      };
+      float4 t0[8], t1[8], t2[8];
+      load_tile(0, t0);
+      if (nkb0 > 1) load_tile(1, t1);
+      constexpr int sz0 = CHAIN_STAGE_BYTES, S0 = CHAIN_STAGES;
+      auto convert = [&](int kb, const float4 (&cur)[8]) {
+        const int s = (2 * kb) % S0, u = (2 * kb) / S0;
+        if (u > 0) duo_wait(&empty_bar[s], (uint32_t)((u - 1) & 1), 121u, ab);
+        uint8_t* tile = smem + s * sz0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = w8 * 16 + 2 * i + sub;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(cur[i].x, cur[i].y), h1 = __floats2bfloat162_rn(cur[i].z, cur[i].w);
+          *reinterpret_cast<uint2*>(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((((c4 >> 1) ^ (r & 7)) << 4) | ((c4 & 1) << 3))) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_bar[s])) : "memory");
+      };
+      for (int kb = 0; kb < nkb0; kb += 3) {
+        if (kb + 2 < nkb0) load_tile(kb + 2, t2);
+        convert(kb, t0);
+        if (kb + 1 >= nkb0) break;
+        if (kb + 3 < nkb0) load_tile(kb + 3, t0);
+        convert(kb + 1, t1);
+        if (kb + 2 >= nkb0) break;
+        if (kb + 4 < nkb0) load_tile(kb + 4, t1);
+        convert(kb + 2, t2);
+      }
+    }
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const bool leader = q == 0 && lane == 0;
+    for (int l = 0; l < L; ++l)
+      for (int n = 0; n < 2; ++n) {
+        const ChainLayer& C = g.l[n][l];
+        const int n_tile = C.n_tile, n0 = (int)crank * n_tile;
+        const uint32_t acc = tmem + (uint32_t)(n * 256);
+        uint8_t* buf = out_buf + half * (BM * 128);
+        // all eight warps: the previous task's last stores have left the staging buffers (their leaders waited before
+        // arriving here) and nobody reads the previous bias slice any more
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 64) duo_trace(g, 2 * l + n, DT_EPI_BEGIN);
+        if (l + 1 < L) {
+          // ---- hidden layer: bias + ELU -> bf16, 64-column sub-tiles through this half's staging buffer (mlp_chain_body) ----
+          { const int e = tid - 64; if (e < n_tile) bias_s[e] = __ldg(C.bias + n0 + e); }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          duo_wait(&acc_bar[n], (uint32_t)(l & 1), 131u, ab);
+          tc_fence_after();
+          if (tid == 64) duo_trace(g, 2 * l + n, DT_ACC_COMPLETE);
+          const int n_sub = n_tile >> 6, halves = n_sub >= 2 ? 2 : 1, per_half = n_sub / halves;
+          if (half < halves) {
+            const int cbeg = half * per_half * 64;
+            const uint32_t taddr = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+            uint8_t* rowp = buf + (row >> 3) * 1024 + (row & 7) * 128;
+            uint32_t ra[32], rb[32], pk[32];
+            auto act32 = [&](const uint32_t (&r)[32], int col, uint32_t* out16) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias_s + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = b4[i];
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(elu1(__uint_as_float(r[4 * i]) + b.x), elu1(__uint_as_float(r[4 * i + 1]) + b.y));
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(elu1(__uint_as_float(r[4 * i + 2]) + b.z), elu1(__uint_as_float(r[4 * i + 3]) + b.w));
+                out16[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
+                out16[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+              }
+            };
+            tmem_ld32_issue(taddr, ra);
+            for (int js = 0; js < per_half; ++js) {
+              tmem_ld_wait(ra);
+              tmem_ld32_issue(taddr + js * 64 + 32, rb);
+              act32(ra, cbeg + js * 64, pk);
+              tmem_ld_wait(rb);
+              if (js + 1 < per_half) tmem_ld32_issue(taddr + js * 64 + 64, ra);
+              act32(rb, cbeg + js * 64 + 32, pk + 16);
+              if (js > 0) {                                       // the buffer fed the previous sub-tile's store
+                if (leader) tma_store_wait_read();
+                if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+              fence_async_smem();
+              if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+              else asm volatile("bar.sync 2, 128;" ::: "memory");
+              if (leader) {
+                tma_store_2d(&C.map_y, buf, n0 + cbeg + js * 64, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+            if (leader && half == 0) duo_trace(g, 2 * l + n, DT_COMPUTED);
+            // the slices must have LANDED (not only left shared memory) before anybody is told to read them
+            if (q == 0) {           // lane 0 reports to this CTA, lanes 1-4 to the four CTAs of the cluster in parallel
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+              if (leader && half == 0) duo_trace(g, 2 * l + n, DT_LANDED);
+              __syncwarp();
+              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&own_bar[n][l])) : "memory");
+              else if (lane <= CHAIN_CLUSTER) mbar_arrive_remote(&peer_bar[n][l], (uint32_t)(lane - 1));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+        } else {
+          // ---- last layer: bias -> fp32 [M][N] ----
+          duo_wait(&acc_bar[n], (uint32_t)(l & 1), 132u, ab);
+          tc_fence_after();
+          if (tid == 64) duo_trace(g, 2 * l + n, DT_ACC_COMPLETE);
+          const int sub_cols = (C.epilogue == 0) ? 32 : 64;
+          int cb = 0, ce = half ? 0 : n_tile;
+          if (n_tile >= 2 * sub_cols) { cb = half ? n_tile / 2 : 0; ce = half ? n_tile : n_tile / 2; }
+          mmb_mlp_layer_params p = {};
+          p.M = g.M; p.N = C.N; p.epilogue = C.epilogue; p.bias = C.bias;
+          if (cb < ce) {
+            epilogue_row_staged(p, acc + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, buf, [&](int j) {
+              fence_async_smem();
+              if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+              else asm volatile("bar.sync 2, 128;" ::: "memory");
+              if (leader) {
+                tma_store_2d(&C.map_y, buf, n0 + j * sub_cols, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                tma_store_wait_read();
+              }
+              if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+              else asm volatile("bar.sync 2, 128;" ::: "memory");
+            }, 0);
+            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (leader && half == 0) duo_trace(g, 2 * l + n, DT_LANDED);
+          }
+          tc_fence_before();
+          __syncwarp();
+        }
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();              // no CTA leaves while a peer's arrival may still be on its way to the barriers here
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 // ---- host: 2-D tensor maps (rows x Kpad bf16, box = box_rows x 64, SWIZZLE_128B) through the driver entry point ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1253,6 +1662,29 @@ inline bool make_map_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, u
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// [rows][kpad] bf16 seen as (64 elements, rows, kpad / 64): box = 64 x box_rows x group, i.e. `group` consecutive k-blocks
+// of box_rows rows as consecutive SWIZZLE_128B tiles in shared memory - ONE tensor load instead of `group` (the TMA unit
+// spends ~0.16 us per load whatever its size: mlp_chain_duo_kernel)
+inline bool make_map_bf16_kgroup(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows, uint32_t group) {
+  constexpr int kEntries = 128;
+  static thread_local MapCacheEntry cache[kEntries];
+  const uint32_t key = box_rows | (group << 16);
+  const uint64_t h = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull + rows * 31 + kpad * 7 + key;
+  MapCacheEntry& e = cache[(h >> 32) % kEntries];
+  if (e.base != base || e.rows != rows || e.kpad != kpad || e.box_rows != key) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)BK, rows, kpad / BK};
+    cuuint64_t strides[2] = {kpad * 2, (cuuint64_t)BK * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, box_rows, group};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (fn(&e.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    e.base = base; e.rows = rows; e.kpad = kpad; e.box_rows = key;
+  }
+  memcpy(map, &e.map, sizeof(CUtensorMap));
+  return true;
 }
 inline bool make_map_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
@@ -1679,13 +2111,37 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
   if (!attr_done[dev]) {
     if (cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) != cudaSuccess) return MMB_ECUDA;
     if (cudaFuncSetAttribute(mlp_chain_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) != cudaSuccess) return MMB_ECUDA;
+    if (cudaFuncSetAttribute(mlp_chain_duo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM) != cudaSuccess) return MMB_ECUDA;
     attr_done[dev] = true;
+  }
+  for (int a = 0; a < count; ++a)
+    for (int l = 0; l < num_layers; ++l) g.l[a][l].kgroup = 1;
+  // two networks on the same fp32 rows (PPO act(): actor + critic): one CTA walks both, alternating (mlp_chain_duo_kernel)
+  static const bool duo_on = [] { const char* v = getenv("MMB_MLP_DUO"); return !(v && v[0] == '0'); }();
+  // (when the side-by-side launch fits one wave of clusters - M <= 2304 on 148 SMs - it is the faster one: twice the CTAs at work)
+  static const bool duo_force = [] { const char* v = getenv("MMB_MLP_DUO"); return v && v[0] == '2'; }();
+  const bool duo = duo_on && !tf32 && count == 2 && x_fp32 && x_fp32[0] == x_fp32[1] &&
+                   (duo_force || 2 * (f.Mpad / BM) > sm_count() / CHAIN_CLUSTER);
+  if (duo) {
+    // layers >= 1: k-blocks in groups of two per tensor load (3-D maps) where the own / peer split and K allow it
+    static const int kgroup_max = [] { const char* v = getenv("MMB_MLP_KGROUP"); return v ? atoi(v) : 2; }();
+    for (int l = 1; l < num_layers; ++l) {
+      const int n_own = g.l[0][l - 1].n_tile / 64, nkb = g.l[0][l].nkb;
+      const int G = (kgroup_max >= 2 && n_own % 2 == 0 && nkb % 2 == 0) ? 2 : 1;
+      for (int a = 0; a < count && G > 1; ++a) {
+        const mmb_mlp_layer_params& p = layers[a * num_layers + l];
+        ChainLayer& c = g.l[a][l];
+        c.kgroup = G;
+        if (!make_map_bf16_kgroup(&c.map_w, p.w, (uint64_t)p.Npad, (uint64_t)p.Kpad, (uint32_t)c.n_tile, (uint32_t)G)) return MMB_ECUDA;
+        if (!make_map_bf16_kgroup(&c.map_x, p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM, (uint32_t)G)) return MMB_ECUDA;
+      }
+    }
   }
   {
     LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CHAIN_CLUSTER * (f.Mpad / BM), 1, count);
-    cfg.blockDim = dim3(WS_THREADS);
+    cfg.gridDim = dim3(CHAIN_CLUSTER * (f.Mpad / BM), 1, duo ? 1 : count);
+    cfg.blockDim = dim3(duo ? DUO_THREADS : WS_THREADS);
     cfg.dynamicSmemBytes = CHAIN_SMEM;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[2];
@@ -1700,7 +2156,8 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const cudaError_t le = tf32 ? cudaLaunchKernelEx(&cfg, mlp_chain_tf32_kernel, g) : cudaLaunchKernelEx(&cfg, mlp_chain_kernel, g);
+    const cudaError_t le = duo ? cudaLaunchKernelEx(&cfg, mlp_chain_duo_kernel, g)
+                               : (tf32 ? cudaLaunchKernelEx(&cfg, mlp_chain_tf32_kernel, g) : cudaLaunchKernelEx(&cfg, mlp_chain_kernel, g));
     if (le != cudaSuccess) {
       if (getenv("MMB_DEBUG")) fprintf(stderr, "mmb_mlp_chain: launch failed: %s\n", cudaGetErrorString(le));
       (void)cudaGetLastError();

@@ -405,3 +405,41 @@ def test_tf32_chain(cuda_device, M):
             prm.add_(0.01 * torch.randn(prm.shape, generator=gen).to(dev))
         ref2 = actor(x)
     assert _rowmax_err(f.forward_tf32(x), ref2) <= 5e-3
+
+
+@pytest.mark.parametrize("M", [1, 130, 4096, 5000])
+def test_dual_network_chain_equals_single_network_chains(cuda_device, M):
+    """`mlp_chain_duo_kernel` (actor and critic on the same observations: one CTA walks both networks, alternating layer by
+    layer, the fp32 rows cast once) accumulates every network's k-blocks in the order the single-network chain does, so the
+    pair's outputs equal the two single launches BIT FOR BIT - on every repetition (a stale operand tile, a staging buffer
+    reused too early or an accumulator overwritten under its epilogue would show up here) - and no bounded wait expired."""
+    import ctypes as C
+    from massive_marl_benchmark_b200 import _lib as L
+    from massive_marl_benchmark_b200 import mlp as mm
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(100 + M)
+    actor = _ppo_net(388, [1024, 1024, 512], 80, 0.01, gen).to(dev)
+    critic = _ppo_net(388, [1024, 1024, 512], 80, 1.0, gen).to(dev)
+    x = torch.clamp(torch.randn(M, 388, generator=gen) * 2.0, -5, 5).to(dev)
+    fa, fc = mm.FusedMLP.from_sequential(actor, dev), mm.FusedMLP.from_sequential(critic, dev)
+    ya, yc = fa(x).clone(), fc(x).clone()
+    assert fa._chain_ok is True
+    pair = mm.GroupedMLP([fa, fc])
+    st = (C.c_uint32 * 4)()
+    L.check(L.lib().mmb_mlp_debug_status(st), "mmb_mlp_debug_status")      # (clears the record)
+    for rep in range(10):
+        out = pair([x, x])
+        assert torch.equal(out[0], ya) and torch.equal(out[1], yc), rep
+    torch.cuda.synchronize()
+    L.check(L.lib().mmb_mlp_debug_status(st), "mmb_mlp_debug_status")
+    assert list(st) == [0, 0, 0, 0], [hex(v) for v in st]
+    with torch.no_grad():
+        assert _rowmax_err(out[0], actor(x)) <= 3e-2 and _rowmax_err(out[1], critic(x)) <= 3e-2
+    # a three-layer geometry whose slices are narrower (256-wide hidden layers: 64 columns per CTA, one epilogue half)
+    a2 = _ppo_net(60, [256, 256], 8, 0.05, gen).to(dev)
+    c2 = _ppo_net(60, [256, 256], 8, 1.0, gen).to(dev)
+    x2 = torch.randn(M, 60, generator=gen).to(dev)
+    f2a, f2c = mm.FusedMLP.from_sequential(a2, dev), mm.FusedMLP.from_sequential(c2, dev)
+    y2a, y2c = f2a(x2).clone(), f2c(x2).clone()
+    out2 = mm.GroupedMLP([f2a, f2c])([x2, x2])
+    assert torch.equal(out2[0], y2a) and torch.equal(out2[1], y2c)
