@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMB_ABI_VERSION 2
+#define MMB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MMB_API __attribute__((visibility("default")))
@@ -489,6 +489,12 @@ typedef struct {
   float* grad_mean;                        /* [B][A] d policy_loss / d mean, or NULL */
   float* grad_values;                      /* [B] d value_loss / d values, or NULL */
   double* sums;                            /* [2 + A], zeroed by the caller */
+  /* Optional in-kernel finalisation (as mmb_ppo_loss): the last block to finish writes out[0] = policy_loss, out[1] =
+   * value_loss - the sums over the reference's denominators (B, or *mask_sum where the matching mask flag is set),
+   * rounded to fp32 once - and out[2 + j] = d policy_loss / d std[j] in fp32, then hands `sums` and `*ticket` (zero before
+   * the first launch) back zeroed: one launch, no follow-up kernels, the scratch is reusable at once. NULL: `sums` only. */
+  float* out;                              /* [2 + A] or NULL */
+  unsigned int* ticket;                    /* required with `out` */
 } mmb_mappo_loss_params;
 MMB_API int32_t mmb_mappo_loss(const mmb_mappo_loss_params* p, void* stream);
 

@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMB_LIB_PATH") or os.path.join(_HERE, "libmmb_b200.so")   # MMB_LIB_PATH: diagnostics builds (tools/probe)
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_GATHER_FIELDS = 16
 
 FLAVOR_CUDA, FLAVOR_CPU = 0, 1
@@ -144,7 +144,8 @@ class MappoLossParams(C.Structure):
                 ("adv_targ", c_vp), ("values", c_vp), ("value_preds", c_vp), ("returns", c_vp), ("active_masks", c_vp),
                 ("mask_sum", c_vp), ("ret_mean", c_vp), ("ret_var", c_vp), ("ret_mean_orig", c_vp), ("ret_var_orig", c_vp),
                 ("clip_param", c_f), ("ratio_lo", c_f), ("ratio_hi", c_f), ("huber_delta", c_f),
-                ("imp_weights", c_vp), ("logp", c_vp), ("grad_mean", c_vp), ("grad_values", c_vp), ("sums", c_vp)]
+                ("imp_weights", c_vp), ("logp", c_vp), ("grad_mean", c_vp), ("grad_values", c_vp), ("sums", c_vp),
+                ("out", c_vp), ("ticket", c_vp)]
 
 
 class GaeMarlParams(C.Structure):

@@ -328,6 +328,26 @@ __global__ void __launch_bounds__(LOSS_THREADS) mappo_loss_kernel(const __grid_c
   __syncthreads();
   if (tid < 2) atomicAdd(p.sums + tid, s_sum[tid]);
   for (int j = tid; j < A; j += LOSS_THREADS) atomicAdd(p.sums + 2 + j, s_gstd[j]);
+  if (p.out == nullptr) return;
+  // Finalisation by the last block to finish (ticket): the two means over the reference's denominators
+  // (mappo_trainer.py:139-144, 98-101: .sum() / active_masks.sum() or .mean()) - and the scratch is handed back zeroed.
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  volatile double* sums = p.sums;
+  if (tid == 0) {
+    const double msum = p.mask_sum ? (double)__ldg(p.mask_sum) : 0.0;
+    p.out[0] = (float)(sums[0] / (p.use_policy_active_masks ? msum : (double)B));
+    p.out[1] = (float)(sums[1] / (p.use_value_active_masks ? msum : (double)B));
+  }
+  for (int j = tid; j < A; j += LOSS_THREADS) p.out[2 + j] = (float)sums[2 + j];
+  __syncthreads();
+  for (int j = tid; j < 2 + A; j += LOSS_THREADS) p.sums[j] = 0.0;
+  if (tid == 0) *p.ticket = 0u;
 }
 
 template <int G>
@@ -383,6 +403,7 @@ extern "C" int32_t mmb_mappo_loss(const mmb_mappo_loss_params* pp, void* stream)
   if ((p.use_value_active_masks || p.use_policy_active_masks) && (!p.active_masks || !p.mask_sum)) return MMB_EINVAL;
   if ((p.ret_mean == nullptr) != (p.ret_var == nullptr)) return MMB_EINVAL;
   if ((p.ret_mean_orig == nullptr) != (p.ret_var_orig == nullptr) || (p.ret_mean_orig && !p.ret_mean)) return MMB_EINVAL;
+  if (p.out && !p.ticket) return MMB_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int G = p.act_dim <= 8 ? 8 : (p.act_dim <= 16 ? 16 : 32);
   const int kmax = (p.act_dim + G - 1) / G;

@@ -49,11 +49,26 @@ def _rows(t, B, name):
     return t.reshape(B).float().contiguous()
 
 
+_SCRATCH = {}     # (device, stream, A) -> fp64 sums + ticket word: the finalising kernel hands the scratch back zeroed
+
+
+def _scratch(dev, stream, A):
+    key = (dev.index, stream, A)
+    buf = _SCRATCH.get(key)
+    if buf is None:
+        if len(_SCRATCH) > 64:
+            _SCRATCH.clear()
+        buf = _SCRATCH[key] = torch.zeros(2 + A + 1, dtype=torch.float64, device=dev)
+    return buf
+
+
 def mappo_loss_raw(mean, std, values, actions, old_logp, adv_targ, value_preds, returns, active_masks=None, ret_mean=None,
                    ret_var=None, ret_mean_orig=None, ret_var_orig=None, clip_param=0.2, huber_delta=10.0, use_huber_loss=True, use_clipped_value_loss=True,
-                   use_value_active_masks=False, use_policy_active_masks=False):
+                   use_value_active_masks=False, use_policy_active_masks=False, finalise=True):
     """One `mmb_mappo_loss` launch.  Returns (policy_loss, value_loss [0-dim fp32 tensors], imp_weights [B, 1], logp [B, A],
-    grad_mean [B, A], grad_std [A], grad_values [B])."""
+    grad_mean [B, A], grad_std [A], grad_values [B]).  finalise=True (default): the kernel's last block computes the two
+    fp32 loss values and the fp32 std gradient itself (include/mmb.h, `out`) - one launch, everything returned is a view of
+    its outputs; False: the fp64 sums are reduced by torch ops afterwards (the first version, kept for the parity test)."""
     if not mean.is_cuda:
         raise L.MmbError("mappo_loss needs CUDA tensors (there is no CPU path)")
     B, A = mean.shape
@@ -100,14 +115,26 @@ def mappo_loss_raw(mean, std, values, actions, old_logp, adv_targ, value_preds, 
             put(name, t.detach().reshape(-1)[:1].float().contiguous().to(dev))
     p.clip_param, p.huber_delta = float(clip_param), float(huber_delta)
     p.ratio_lo, p.ratio_hi = 1.0 - clip_param, 1.0 + clip_param
-    sums = torch.zeros(2 + A, dtype=torch.float64, device=dev)
     imp = torch.empty(B, 1, dtype=torch.float32, device=dev)
     logp = torch.empty(B, A, dtype=torch.float32, device=dev)
+    p.imp_weights, p.logp = imp.data_ptr(), logp.data_ptr()
+    st = L.stream_ptr()
+    if finalise:
+        o_val = (B * A + 3) & ~3
+        o_out = (o_val + B + 3) & ~3
+        flat = torch.empty(o_out + 2 + A, dtype=torch.float32, device=dev)     # gradients and finalised terms: one allocation
+        base = flat.data_ptr()
+        scratch = _scratch(dev, st, A)
+        p.sums, p.ticket = scratch.data_ptr(), scratch.data_ptr() + 8 * (2 + A)
+        p.grad_mean, p.grad_values, p.out = base, base + 4 * o_val, base + 4 * o_out
+        L.check(L.lib().mmb_mappo_loss(p, st), "mmb_mappo_loss")
+        return (flat[o_out], flat[o_out + 1], imp, logp, flat[:B * A].view(B, A), flat[o_out + 2:], flat[o_val:o_val + B])
+    sums = torch.zeros(2 + A, dtype=torch.float64, device=dev)
     grad_mean = torch.empty(B, A, dtype=torch.float32, device=dev)
     grad_values = torch.empty(B, dtype=torch.float32, device=dev)
-    p.sums, p.imp_weights, p.logp = sums.data_ptr(), imp.data_ptr(), logp.data_ptr()
+    p.sums = sums.data_ptr()
     p.grad_mean, p.grad_values = grad_mean.data_ptr(), grad_values.data_ptr()
-    L.check(L.lib().mmb_mappo_loss(p, L.stream_ptr()), "mmb_mappo_loss")
+    L.check(L.lib().mmb_mappo_loss(p, st), "mmb_mappo_loss")
     den_p = mask_sum[0].double() if use_policy_active_masks else den
     den_v = mask_sum[0].double() if use_value_active_masks else den
     return ((sums[0] / den_p).float(), (sums[1] / den_v).float(), imp, logp, grad_mean, sums[2:].float(), grad_values)

@@ -133,3 +133,27 @@ def test_mappo_loss_argument_errors(cuda_device):
     a = mappo_loss_raw(wide[:, :8], std, d["values"], d["actions"], d["old_logp"], d["adv_targ"], d["value_preds"], d["returns"])
     b = mappo_loss_raw(d["mean"], std, d["values"], d["actions"], d["old_logp"], d["adv_targ"], d["value_preds"], d["returns"])
     assert torch.equal(a[4], b[4]) and torch.equal(a[2], b[2]) and torch.equal(a[6], b[6])
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_mappo_loss_in_kernel_finalisation(cuda_device, masks):
+    """finalise=True (the default: the last block computes the two fp32 losses and the fp32 std gradient, and hands the
+    fp64 scratch back zeroed) against the first version (fp64 sums reduced by torch ops): the same numbers, repeatedly (a
+    scratch that did not come back zeroed would show up on the second call), for several batch sizes sharing the scratch."""
+    from massive_marl_benchmark_b200.mappo_loss import mappo_loss_raw
+    from oracle.mappo_loss_oracle import synthetic_minibatch
+    dev = cuda_device
+    for B in (64, 1000, 20000):
+        mb = synthetic_minibatch(B, 8, seed=B)
+        d = {k: v.to(dev) for k, v in mb.items() if not k.startswith("popart_")}
+        std = torch.sigmoid(d["log_std"]) * 0.5
+        args = (d["mean"], std, d["values"], d["actions"], d["old_logp"], d["adv_targ"], d["value_preds"], d["returns"])
+        kw = dict(active_masks=d["active_masks"], use_value_active_masks=masks, use_policy_active_masks=masks)
+        want = mappo_loss_raw(*args, finalise=False, **kw)
+        for rep in range(3):
+            got = mappo_loss_raw(*args, finalise=True, **kw)
+            for i, (w, g) in enumerate(zip(want, got)):
+                if i in (2, 3, 4, 6):                            # imp_weights, logp, grad_mean, grad_values: per-row, no reduction
+                    assert torch.equal(w, g), (B, rep, i)
+                else:                                            # sums of fp64 atomics in launch order: equal after the fp32 rounding
+                    assert torch.allclose(w, g, rtol=2e-6, atol=1e-9), (B, rep, i, w, g)

@@ -69,6 +69,34 @@ def floor():
 out = {"raw_launch": host_and_device(lambda: ppo_loss_raw(mu, log_std, value, actions, old_logp, adv, tv, ret, old_mu, old_sigma)),
        "function_forward": host_and_device(fwd), "forward_backward": host_and_device(fwd_bwd),
        "empty_function_forward_backward": host_and_device(floor)}
+# the MAPPO loss wrapper (B = 16384, A = 8): in-kernel finalisation against the fp64 sums reduced by torch ops
+from massive_marl_benchmark_b200.mappo_loss import mappo_loss, mappo_loss_raw  # noqa: E402
+
+Am = 8
+m_mean = (r(B, Am) * 0.3).requires_grad_(True)
+m_log_std = torch.zeros(Am, device=dev, requires_grad=True)
+m_actions = m_mean.detach() + 0.3 * r(B, Am)
+m_old_logp = r(B, Am) * 0.1 - 1.0
+m_values = r(B, 1).requires_grad_(True)
+m_vp, m_ret, m_adv = r(B, 1), r(B, 1), r(B, 1)
+
+
+def m_args():
+    return (m_mean, torch.sigmoid(m_log_std) * 0.5, m_values, m_actions, m_old_logp, m_adv, m_vp, m_ret)
+
+
+def m_fwd_bwd():
+    for t in (m_mean, m_log_std, m_values):
+        t.grad = None
+    o = mappo_loss(*m_args())
+    (o.policy_loss - o.dist_entropy * 0.01).backward()
+    o.value_loss.backward()
+
+
+out["mappo_raw_finalised"] = host_and_device(lambda: mappo_loss_raw(*m_args(), finalise=True))
+out["mappo_raw_torch_reduced"] = host_and_device(lambda: mappo_loss_raw(*m_args(), finalise=False))
+out["mappo_forward"] = host_and_device(lambda: mappo_loss(*m_args()))
+out["mappo_forward_two_backwards"] = host_and_device(m_fwd_bwd)
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/loss_overhead.json", "w"), indent=1)
