@@ -73,6 +73,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// accumulate = 1 with a constant predicate (the per-instruction setp of umma_bf16 is one of the things that made the MMA
+// issuer's loop - a single thread whose instruction latencies are the k-loop's clock - 345 ns per k-block whatever the tile)
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+               "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
 // kind::tf32: fp32 operands in shared memory (the tensor core reads the upper 19 bits), 8 elements of K per instruction =
 // the same 32 bytes of a SWIZZLE_128B row as 16 bf16, at half the rate.
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int umma_n, int umma_m = BM) {
@@ -976,20 +982,37 @@ __device__ __forceinline__ void mlp_chain_body(const ChainArgs& g) {
     } else if (warp == 1) {
       // ===== MMA issuer =====
       if (elect_one()) {
+        // This thread's instruction latencies are the k-loop's clock (tools/probe/tma_mma_rate.cu: the generic form of this
+        // loop takes 345 ns per k-block whatever the tile width, a lean one 226-315): stage descriptors advance by adding to
+        // their address field, the accumulate predicate is a constant after the first instruction, and the tcgen05 fence is
+        // only issued where generic-proxy writers (the input cast) or the epilogue's accumulator loads must be ordered.
         const uint32_t idesc = TF32 ? umma_idesc_tf32(n_tile) : umma_idesc_bf16(n_tile);
+        const bool cast_a = l == 0 && x32 != nullptr;
+        const uint64_t da0 = umma_desc_k_sw128(smem_u32(smem)), db0 = umma_desc_k_sw128(smem_u32(smem) + A_STAGE_BYTES);
+        constexpr uint32_t dstep = (uint32_t)CHAIN_STAGE_BYTES >> 4;
+        int s = it_m % S;
+        uint32_t u = (uint32_t)(it_m / S);
+        uint64_t da = da0 + (uint64_t)((uint32_t)s * dstep), db = db0 + (uint64_t)((uint32_t)s * dstep);
         for (int kb = 0; kb < nkb; ++kb) {
-          const int itx = it_m + kb, s = itx % S, u = itx / S;
-          mbar_wait(&full_bar[s], (uint32_t)(u & 1));
-          if (l == 0 && x32 != nullptr) mbar_wait(&a_bar[s], (uint32_t)(u & 1));   // the A tile the epilogue warps converted
+          mbar_wait(&full_bar[s], u & 1u);
+          if (cast_a) mbar_wait(&a_bar[s], u & 1u);   // the A tile the epilogue warps converted
           if (kb == 0) chain_trace(g, l, TR_FIRST_OPERANDS);
           chain_trace(g, l, 0, kb);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * CHAIN_STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
+          if (cast_a || kb == 0) tc_fence_after();
+          if (kb == 0) {
+            if constexpr (TF32) umma_tf32(tmem, da, db, idesc, false);
+            else umma_bf16(tmem, da, db, idesc, false);
+          } else {
+            if constexpr (TF32) umma_tf32(tmem, da, db, idesc, true);
+            else umma_bf16_acc(tmem, da, db, idesc);
+          }
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j)
-            if constexpr (TF32) umma_tf32(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
-            else umma_bf16(tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
+          for (int j = 1; j < BK / 16; ++j)
+            if constexpr (TF32) umma_tf32(tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, true);
+            else umma_bf16_acc(tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc);
           umma_commit(&empty_bar[s]);
+          if (++s == S) { s = 0; ++u; da = da0; db = db0; }
+          else { da += dstep; db += dstep; }
         }
         umma_commit(&acc_bar);
         chain_trace(g, l, TR_MMA_ISSUED);
@@ -1219,12 +1242,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_chain_tf32_kernel(const __g
 // Every mbarrier wait is bounded (50 ms, then the CTA stops waiting altogether and records a code for
 // mmb_mlp_debug_status): a protocol error yields garbage, never a hung GPU.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void duo_wait(uint64_t* bar, uint32_t parity, unsigned code, volatile int* abort_flag) {
+// `bar_addr` = shared-window address of the mbarrier.  The common case - the phase has completed or completes within the
+// hardware's own try_wait time slice - costs one instruction and a branch; only then the clock is read.
+__device__ __noinline__ void duo_wait_slow(uint32_t bar_addr, uint32_t parity, unsigned code, volatile int* abort_flag) {
   const long long t0 = clock64();
   uint32_t done = 0;
   while (!done) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+                 : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
     if (!done) {
       if (*abort_flag) return;
       if (clock64() - t0 > 100000000ll) {   // ~50 ms
@@ -1234,6 +1259,26 @@ __device__ __forceinline__ void duo_wait(uint64_t* bar, uint32_t parity, unsigne
       }
     }
   }
+}
+__device__ __forceinline__ void duo_wait_addr(uint32_t bar_addr, uint32_t parity, unsigned code, volatile int* abort_flag) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+  if (!done) duo_wait_slow(bar_addr, parity, code, abort_flag);
+}
+__device__ __forceinline__ void duo_wait(uint64_t* bar, uint32_t parity, unsigned code, volatile int* abort_flag) {
+  duo_wait_addr(smem_u32(bar), parity, code, abort_flag);
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_addr) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(map),
+               "r"(c0), "r"(c1), "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_addr(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar_addr) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(map),
+               "r"(c0), "r"(c1), "r"(c2), "r"(bar_addr) : "memory");
 }
 
 // diagnostics (-DMMB_CHAIN_TRACE_BUILD + MMB_CHAIN_TRACE=1, tools/probe/duo_trace.py): [4 CTAs][16 tasks][8 events]
@@ -1306,17 +1351,11 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) mlp_chain_duo_kernel(const __g
   // size (0.35 / 0.38 / 0.42 us per k-block = two loads of 160 / 256 / 384 rows: measured with 4, 6 and 8 stages, with one
   // and with two issuing threads, with and without the MMAs - always the same).  So layers >= 1 load k-blocks in GROUPS of
   // kgroup (2) through 3-D tensor maps - one load for the activation tiles, one for the weight slices of the group - and a
-  // stage holds a group: [A tile x G | W slice x G].  The stage size of layer l is that of its widest remaining group, so
-  // beyond layer 1 sizes only shrink along the chain: a new stage j then only overlaps old stages of index <= j, whose
-  // barriers the producers re-claim - i.e. wait for - in order before they reach stage j; where stages GROW (layer 0's
-  // single k-blocks -> layer 1's groups) the producers first wait for every barrier's last use.  Barrier s serves stage s of
-  // every geometry; its phase parities are tracked in bit masks.
-  auto stage_bytes = [&](int l) {
-    if (l == 0) return CHAIN_STAGE_BYTES;
-    int sz = 0;
-    for (int j = l; j < L; ++j) sz = max(sz, g.l[0][j].kgroup * (A_STAGE_BYTES + g.l[0][j].n_tile * BK * 2));
-    return sz;
-  };
+  // stage holds a group: [A tile x G | W slice x G].  Where the stage size SHRINKS from one layer to the next, a new stage j
+  // only overlaps old stages of index <= j, whose barriers the producers re-claim - i.e. wait for - in order before they
+  // reach stage j; where it GROWS the producers first wait for every barrier's last use (one exposed load latency).
+  // Barrier s serves stage s of every geometry; its phase parities are tracked in bit masks.
+  auto stage_bytes = [&](int l) { return l == 0 ? CHAIN_STAGE_BYTES : g.l[0][l].kgroup * (A_STAGE_BYTES + g.l[0][l].n_tile * BK * 2); };
   auto stages_of = [](int sz) { const int s = (CHAIN_STAGES * CHAIN_STAGE_BYTES) / sz; return s > SMAX ? SMAX : s; };
 
   if (warp == 0 || warp == DUO_A_WARP) {
@@ -1346,6 +1385,10 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) mlp_chain_duo_kernel(const __g
             tma_load_2d(smem + s * sz + A_STAGE_BYTES, &C.map_w, kb * BK, (int)crank * C.n_tile, &full_bar[s]);
           }
         }
+      // Layers >= 1.  These loops are kept as short as they can be made - a single thread's instruction latencies ARE the
+      // k-loop's clock here (tools/probe/tma_mma_rate.cu: ~270 ns per iteration for a producer that waits, arms and issues
+      // two tensor loads, whatever their size): stage address, barrier addresses and the k coordinate advance incrementally.
+      const uint32_t ring = smem_u32(smem), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       for (int l = 1; l < L; ++l) {
         const int nsz = stage_bytes(l);
         if (nsz != sz) {
@@ -1357,28 +1400,37 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) mlp_chain_duo_kernel(const __g
         for (int n = 0; n < 2; ++n) {
           const ChainLayer& C = g.l[n][l];
           const int nkb = C.nkb, n_own = g.l[n][l - 1].n_tile >> 6, G = C.kgroup;
-          const uint32_t a_bytes = (uint32_t)(G * A_STAGE_BYTES), w_bytes = (uint32_t)(G * C.n_tile * BK * 2);
-          if (wprod) {
-            for (int i = 0; i < nkb; i += G) {
-              const int kb = chain_kb(i, n_own, (int)crank, nkb);
-              const int s = claim(true);
-              mbar_expect_tx(&full_bar[s], a_bytes + w_bytes);
-              duo_trace_kb(g, 16 + 2 * l + n, i);
-              if (G == 1) tma_load_2d(smem + s * sz + a_bytes, &C.map_w, kb * BK, (int)crank * C.n_tile, &full_bar[s]);
-              else tma_load_3d(smem + s * sz + a_bytes, &C.map_w, 0, (int)crank * C.n_tile, kb, &full_bar[s]);
-            }
-          } else {
-            // own slices first (requested as soon as this CTA's stores of layer l - 1 have landed), then the peers'
+          const uint32_t a_bytes = (uint32_t)(G * A_STAGE_BYTES), tx = a_bytes + (uint32_t)(G * C.n_tile * BK * 2);
+          const CUtensorMap* map = wprod ? &C.map_w : &C.map_x;
+          const int row = wprod ? (int)crank * C.n_tile : m0;
+          const uint32_t off = wprod ? a_bytes : 0u;
+          int kb = (int)crank * n_own;       // chain_kb(0): this CTA's own slices first
+          if (kb >= nkb) kb -= nkb;
+          if (!wprod) {
             duo_wait(&own_bar[n][l - 1], 0u, 102u, ab);
             duo_trace(g, 2 * l + n, DT_PRODUCER);
-            for (int i = 0; i < nkb; i += G) {
-              const int kb = chain_kb(i, n_own, (int)crank, nkb);
-              if (i == n_own) { duo_wait(&peer_bar[n][l - 1], 0u, 103u, ab); duo_trace(g, 2 * l + n, DT_PEERS); }
-              const int s = claim(true);
-              if (G == 1) tma_load_2d(smem + s * sz, &C.map_x, kb * BK, m0, &full_bar[s]);
-              else tma_load_3d(smem + s * sz, &C.map_x, 0, m0, kb, &full_bar[s]);
+          }
+          int s = nxt;
+          for (int part = 0; part < 2; ++part) {           // own k-blocks, then the peers'
+            const int cnt = part == 0 ? n_own : nkb - n_own;
+            if (part == 1 && !wprod && cnt > 0) { duo_wait(&peer_bar[n][l - 1], 0u, 103u, ab); duo_trace(g, 2 * l + n, DT_PEERS); }
+            for (int i = 0; i < cnt; i += G) {
+              const uint32_t bit = 1u << s, fb = full0 + 8u * (uint32_t)s;
+              if (used & bit) { duo_wait_addr(empty0 + 8u * (uint32_t)s, (par >> s) & 1u, wprod ? 101u : 104u, ab); par ^= bit; }
+              used |= bit;
+              const uint32_t dst = ring + (uint32_t)(s * sz) + off;
+              if (wprod) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tx) : "memory");
+                duo_trace_kb(g, 16 + 2 * l + n, (part ? n_own : 0) + i);
+              }
+              if (G == 1) tma_load_2d_addr(dst, map, kb * BK, row, fb);
+              else tma_load_3d_addr(dst, map, 0, row, kb, fb);
+              kb += G;
+              if (kb >= nkb) kb -= nkb;
+              s = (s + 1 == S) ? 0 : s + 1;
             }
           }
+          nxt = s;
         }
       }
     }
@@ -1416,32 +1468,49 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) mlp_chain_duo_kernel(const __g
         umma_commit(&acc_bar[1]);
         duo_trace(g, 0, DT_MMA_ISSUED); duo_trace(g, 1, DT_MMA_ISSUED);
       }
+      // Layers >= 1: the lean loop (see the producers).  No tcgen05 fence per k-block: the operands were written by the
+      // async proxy (TMA) and are read by it (the MMA); what orders them is the mbarrier.  Descriptors advance by adding to
+      // their address field (units of 16 bytes; the ring lies below 256 KB, so no carry leaves the field).
+      const uint32_t ring = smem_u32(smem), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       for (int l = 1; l < L; ++l) {
         const int nsz = stage_bytes(l);
         if (nsz != sz) { sz = nsz; S = stages_of(sz); nxt = 0; }
+        const uint32_t dstep = (uint32_t)sz >> 4;
         for (int n = 0; n < 2; ++n) {
           const ChainLayer& C = g.l[n][l];
           const uint32_t idesc = umma_idesc_bf16(C.n_tile);
           const uint32_t acc = tmem + (uint32_t)(n * 256);
-          const int G = C.kgroup;
-          const uint32_t b_off = (uint32_t)(G * A_STAGE_BYTES), b_step = (uint32_t)(C.n_tile * BK * 2);
-          for (int kb = 0; kb < C.nkb; kb += G) {
-            const int s = nxt;
-            nxt = (s + 1 == S) ? 0 : s + 1;
-            duo_wait(&full_bar[s], (par >> s) & 1u, 114u, ab);
+          const int G = C.kgroup, groups = C.nkb / G;
+          const uint32_t wstep = (uint32_t)(C.n_tile * BK * 2) >> 4;
+          const uint64_t da0 = umma_desc_k_sw128(ring), db0 = umma_desc_k_sw128(ring + (uint32_t)(G * A_STAGE_BYTES));
+          int s = nxt;
+          uint64_t da = da0 + (uint64_t)((uint32_t)s * dstep), db = db0 + (uint64_t)((uint32_t)s * dstep);
+          bool fresh = true;
+          duo_trace(g, 2 * l + n, DT_FIRST_OPERANDS);
+          for (int i = 0; i < groups; ++i) {
+            duo_wait_addr(full0 + 8u * (uint32_t)s, (par >> s) & 1u, 114u, ab);
             par ^= 1u << s;
-            if (kb == 0) duo_trace(g, 2 * l + n, DT_FIRST_OPERANDS);
-            duo_trace_kb(g, 2 * l + n, kb);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + s * sz), b_addr = a_addr + b_off;
-            for (int q = 0; q < G; ++q) {
+            duo_trace_kb(g, 2 * l + n, i * G);
+            if (G == 1) {
 #pragma unroll
-              for (int j = 0; j < BK / 16; ++j)
-                umma_bf16(acc, umma_desc_k_sw128(a_addr + q * A_STAGE_BYTES + j * 32), umma_desc_k_sw128(b_addr + q * b_step + j * 32), idesc,
-                          (kb > 0) || (q > 0) || (j > 0));
+              for (int j = 0; j < BK / 16; ++j) {
+                if (fresh) { tc_fence_after(); umma_bf16(acc, da, db, idesc, false); fresh = false; }   // (fence: the epilogue's loads of this accumulator)
+                else umma_bf16_acc(acc, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < BK / 16; ++j) {
+                  if (fresh) { tc_fence_after(); umma_bf16(acc, da, db, idesc, false); fresh = false; }
+                  else umma_bf16_acc(acc, da + (uint64_t)(q * (A_STAGE_BYTES >> 4) + 2 * j), db + (uint64_t)(q * wstep + 2 * j), idesc);
+                }
             }
-            umma_commit(&empty_bar[s]);
+            umma_commit_addr(empty0 + 8u * (uint32_t)s);
+            if (++s == S) { s = 0; da = da0; db = db0; }
+            else { da += dstep; db += dstep; }
           }
+          nxt = s;
           umma_commit(&acc_bar[n]);
           duo_trace(g, 2 * l + n, DT_MMA_ISSUED);
         }
@@ -2127,7 +2196,8 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
     static const int kgroup_max = [] { const char* v = getenv("MMB_MLP_KGROUP"); return v ? atoi(v) : 2; }();
     for (int l = 1; l < num_layers; ++l) {
       const int n_own = g.l[0][l - 1].n_tile / 64, nkb = g.l[0][l].nkb;
-      const int G = (kgroup_max >= 2 && n_own % 2 == 0 && nkb % 2 == 0) ? 2 : 1;
+      // (256-column slices keep single k-blocks: a 96 KB group leaves two stages, and the ring's round trip then shows)
+      const int G = (kgroup_max >= 2 && n_own % 2 == 0 && nkb % 2 == 0 && (g.l[0][l].n_tile <= 128 || kgroup_max >= 3)) ? 2 : 1;
       for (int a = 0; a < count && G > 1; ++a) {
         const mmb_mlp_layer_params& p = layers[a * num_layers + l];
         ChainLayer& c = g.l[a][l];
