@@ -185,7 +185,9 @@ class MlpLayerParams(C.Structure):
     _fields_ = [("M", c_i32), ("N", c_i32), ("K", c_i32), ("Mpad", c_i32), ("Kpad", c_i32), ("Npad", c_i32),
                 ("n_tile", c_i32), ("epilogue", c_i32), ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("ln_gamma", c_vp),
                 ("ln_beta", c_vp), ("ln_eps", c_f), ("stages", c_i32), ("y", c_vp), ("y_stride", c_i64),
-                ("overlap_prev", c_i32), ("operand_type", c_i32)]
+                ("overlap_prev", c_i32), ("operand_type", c_i32),
+                ("ln_in_stats", c_vp), ("ln_in_parts", c_i32), ("ln_in_n", c_i32), ("ln_in_eps", c_f), ("ln_c", c_vp),
+                ("ln_out_stats", c_vp)]
 
 
 # name -> (restype, argtypes); every symbol include/mmb.h declares

@@ -316,6 +316,27 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Deferred LayerNorm (include/mmb.h): mean / rstd of input row m from the producing layer's partial sums (L2 reads: the
+// producer was the previous kernel in the stream), and this launch's own partials of its bf16-rounded outputs.
+__device__ __forceinline__ void ln_row_moments(const mmb_mlp_layer_params& p, int m, float& mean, float& rstd) {
+  const float2* st = reinterpret_cast<const float2*>(p.ln_in_stats) + (int64_t)m * p.ln_in_parts;
+  float s = 0.0f, q = 0.0f;
+  int i = 0;
+  for (; i + 4 <= p.ln_in_parts; i += 4) {        // four independent L2 loads in flight, the sums in chunk order
+    const float2 v0 = __ldcg(st + i), v1 = __ldcg(st + i + 1), v2 = __ldcg(st + i + 2), v3 = __ldcg(st + i + 3);
+    s += v0.x; q += v0.y; s += v1.x; q += v1.y; s += v2.x; q += v2.y; s += v3.x; q += v3.y;
+  }
+  for (; i < p.ln_in_parts; ++i) { const float2 v = __ldcg(st + i); s += v.x; q += v.y; }
+  const float inv_n = 1.0f / (float)p.ln_in_n;
+  mean = s * inv_n;
+  rstd = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.0f) + p.ln_in_eps);      // biased variance, as nn.LayerNorm
+}
+// one partial per 128 columns = one epilogue thread's share of a 256-column tile (the only tile width a producing launch
+// takes), summed in column order: 32 bytes = one sector of partials per 512-wide row for the consumer to read
+__device__ __forceinline__ void ln_store_partial(const mmb_mlp_layer_params& p, int m, int n, float psum, float psq) {
+  reinterpret_cast<float2*>(p.ln_out_stats)[(int64_t)m * (p.Npad >> 7) + (n >> 7)] = make_float2(psum, psq);
+}
+
 // epilogue of columns [cb, ce) of one accumulator row held in a TMEM lane (shared by both kernels; the LayerNorm
 // epilogue needs the whole row: cb = 0, ce = n_tile)
 __device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint32_t taddr, int m, int n0, int n_tile, int cb, int ce) {
@@ -353,9 +374,17 @@ __device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint
       }
     }
   } else {
+    float mean = 0.0f, rstd = 1.0f;
+    const bool corr = p.ln_in_stats != nullptr;
+    if (corr) ln_row_moments(p, m, mean, rstd);
+    float psum = 0.0f, psq = 0.0f;
     for (int c0 = cb; c0 < ce; c0 += 32) {
       tmem_ld32(taddr + c0, v);
       if (!row_ok) continue;
+      if (corr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (n0 + c0 + i < p.N) ? rstd * (v[i] - mean * __ldg(p.ln_c + n0 + c0 + i)) : 0.0f;
+      }
       if (p.epilogue == 1) {  // bias + ELU -> bf16
         __nv_bfloat16* y = static_cast<__nv_bfloat16*>(p.y) + (int64_t)m * p.y_stride + n0 + c0;
         if (n0 + c0 + 32 <= p.N) {  // full group: 64 contiguous bytes of the row as four 16-byte stores
@@ -366,6 +395,7 @@ __device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint
           for (int i = 0; i < 32; i += 2) {
             __nv_bfloat162 h = __floats2bfloat162_rn(elu1(v[i] + bv[i]), elu1(v[i + 1] + bv[i + 1]));
             pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            if (p.ln_out_stats) { const float2 f = __bfloat1622float2(h); psum += f.x; psq += f.x * f.x; psum += f.y; psq += f.y * f.y; }   // (column order, as the staged path)
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(y)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
@@ -376,7 +406,9 @@ __device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint
             if (n < p.N) {  // columns >= N of the (zero-initialised, K-padded) activation buffer stay zero
               const float x0 = elu1(v[i] + __ldg(p.bias + n));
               const float x1 = (n + 1) < p.N ? elu1(v[i + 1] + __ldg(p.bias + n + 1)) : 0.0f;
-              *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(x0, x1);
+              const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+              *reinterpret_cast<__nv_bfloat162*>(y + i) = h;
+              if (p.ln_out_stats) { const float2 f = __bfloat1622float2(h); psum += f.x; psq += f.x * f.x; psum += f.y; psq += f.y * f.y; }   // (column order, as the staged path)
             }
           }
         }
@@ -389,6 +421,7 @@ __device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint
         }
       }
     }
+    if (p.ln_out_stats && p.epilogue == 1 && row_ok && cb < ce) ln_store_partial(p, m, n0 + cb, psum, psq);
   }
 }
 
@@ -426,7 +459,8 @@ __device__ __forceinline__ void stage_out32(uint8_t* tile, int row, int c0, cons
 // rows has been staged: the kernel uses it to hand finished sub-tiles to the TMA store while the next ones are computed.
 template <class Flush>
 __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& p, uint32_t taddr, int row, int n0, int n_tile,
-                                                    int cb, int ce, uint8_t* tile, Flush flush, int sub_stride = BM * 128) {
+                                                    int cb, int ce, uint8_t* tile, Flush flush, int sub_stride = BM * 128, int m = 0) {
+  // m = global row (only read with the deferred LayerNorm fields of p)
   const int sub_cols = (p.epilogue == 0) ? 32 : 64;
   float v[32], bv[32], x[32];
   if (p.epilogue == 2) {  // bias + ELU + LayerNorm over the whole row (n_tile == N): two passes over TMEM
@@ -457,6 +491,9 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
     }
     return;
   }
+  float mean = 0.0f, rstd = 1.0f, psum = 0.0f, psq = 0.0f;
+  const bool corr = p.ln_in_stats != nullptr;
+  if (corr) ln_row_moments(p, m, mean, rstd);
   for (int c0 = cb; c0 < ce; c0 += 32) {
     tmem_ld32(taddr + c0, v);
     const int n = n0 + c0;
@@ -466,9 +503,23 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
 #pragma unroll
       for (int i = 0; i < 32; ++i) bv[i] = (n + i < p.N) ? __ldg(p.bias + n + i) : 0.0f;
     }
+    if (corr) {               // LN(e) . W^T = rstd * (e . (W gamma)^T - mean * c) (+ W beta, folded into the bias)
+      if (n + 32 <= p.N) {
+        load_bias32(p.ln_c + n, x);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = rstd * (v[i] - mean * x[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (n + i < p.N) ? rstd * (v[i] - mean * __ldg(p.ln_c + n + i)) : 0.0f;
+      }
+    }
     if (p.epilogue == 1) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = (n + i < p.N) ? elu1(v[i] + bv[i]) : 0.0f;
+      if (p.ln_out_stats) {   // the sums run over the values as the next layer's GEMM will see them
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { x[i] = __bfloat162float(__float2bfloat16_rn(x[i])); psum += x[i]; psq += x[i] * x[i]; }
+      }
       stage_out32<false>(tile, row, c0, x, sub_stride);
     } else {
 #pragma unroll
@@ -477,6 +528,7 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
     }
     if ((c0 + 32) % sub_cols == 0 || c0 + 32 >= ce) flush(c0 / sub_cols);
   }
+  if (p.ln_out_stats && p.epilogue == 1 && m < p.M && cb < ce) ln_store_partial(p, m, n0 + cb, psum, psq);
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src_smem, int c0, int c1) {
@@ -646,10 +698,10 @@ __device__ __forceinline__ void mlp_layer_ws_body(const mmb_mlp_layer_params& p,
             tma_store_2d(&map_y, smem + j * (BM * 128), n0 + j * sub_cols, m0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-        });
+        }, BM * 128, m0 + row);
         if (q == 0 && lane == 0) tma_store_wait_read();     // the tile must stay intact until the stores have read it
       } else {
-        epilogue_row_staged(p, tmem + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, smem, [](int) {});
+        epilogue_row_staged(p, tmem + ((uint32_t)(q * 32) << 16), row, n0, n_tile, cb, ce, smem, [](int) {}, BM * 128, m0 + row);
       }
     }
     if (!pipelined) {
@@ -684,32 +736,57 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_pair_kernel(const 
   mlp_layer_ws_body<true>(p, map_x, map_w, map_y);
 }
 
+// Grouped launch: blockIdx.z selects one of up to MMB_MAX_GROUP independent problems of identical geometry (the ten
+// per-agent networks of the MARL policies, actor_critic.py / runner.py:205-217): one launch per layer for the whole team.
+// Parameters and tensor maps travel as one large __grid_constant__ kernel argument (8 KB; CUDA 12.1+ allows 32 KB).
+struct WsGroupArgs {
+  mmb_mlp_layer_params p[MMB_MAX_GROUP];
+  CUtensorMap map_x[MMB_MAX_GROUP], map_w[MMB_MAX_GROUP], map_y[MMB_MAX_GROUP];
+};
 // Persistent variant for launches with more tiles than SMs (large batches): one CTA per SM walks tiles m-major, the operand
 // ring runs on across tiles, and TWO accumulators in tensor memory (2 x n_tile <= 512 columns) let the epilogue of tile i
 // (TMEM -> bias / ELU -> staged sub-tiles -> TMA stores) overlap the k-loop of tile i + 1.  Output staging is two 16 KB
 // sub-tile buffers (one per column half) outside the ring.  n_tile <= 256, no LayerNorm epilogue, TMA-addressable output.
-__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_kernel(const __grid_constant__ mmb_mlp_layer_params p,
-                                                                             const __grid_constant__ CUtensorMap map_x,
-                                                                             const __grid_constant__ CUtensorMap map_w,
-                                                                             const __grid_constant__ CUtensorMap map_y) {
+// `sel` hands out the parameters and tensor maps of problem a of `count` problems of identical geometry (one: the plain
+// launch; several: the per-agent networks of a team): a CTA's tile sequence runs problem-major, then m-major, across all of them.
+struct PersistOne {
+  const mmb_mlp_layer_params& p0; const CUtensorMap &mx, &mw, &my;
+  __device__ __forceinline__ const mmb_mlp_layer_params& p(int) const { return p0; }
+  __device__ __forceinline__ const CUtensorMap* map_x(int) const { return &mx; }
+  __device__ __forceinline__ const CUtensorMap* map_w(int) const { return &mw; }
+  __device__ __forceinline__ const CUtensorMap* map_y(int) const { return &my; }
+};
+struct PersistGroup {
+  const WsGroupArgs& g;
+  __device__ __forceinline__ const mmb_mlp_layer_params& p(int a) const { return g.p[a]; }
+  __device__ __forceinline__ const CUtensorMap* map_x(int a) const { return &g.map_x[a]; }
+  __device__ __forceinline__ const CUtensorMap* map_w(int a) const { return &g.map_w[a]; }
+  __device__ __forceinline__ const CUtensorMap* map_y(int a) const { return &g.map_y[a]; }
+};
+template <class Sel>
+__device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const int count) {
+  const mmb_mlp_layer_params& p = sel.p(0);           // the geometry (identical for every problem)
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[256], c_s[256];   // hidden-layer fast path: this tile's bias / c rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tile = p.n_tile;
   const int stage_bytes = A_STAGE_BYTES + n_tile * BK * 2;
   const int S = p.stages;
   const int nkb = p.Kpad / BK;
-  const int tiles_n = p.Npad / n_tile, tiles_m = p.Mpad / BM, num_tiles = tiles_m * tiles_n;
+  const int tiles_n = p.Npad / n_tile, tiles_m = p.Mpad / BM, per_problem = tiles_m * tiles_n, num_tiles = count * per_problem;
   uint8_t* out_buf = smem + S * stage_bytes;          // 2 x 16 KB, 1024-byte aligned (stage_bytes is a multiple of 1024)
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }   // 8 epilogue warps release an accumulator
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    for (int a = 0; a < count; ++a) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(sel.map_x(a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(sel.map_w(a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(sel.map_y(a)) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
@@ -727,14 +804,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_kernel(con
       if (p.overlap_prev) griddep_wait();
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * n_tile;
+        const int a = tile / per_problem, rem = tile - a * per_problem;
+        const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * n_tile;
+        const CUtensorMap* mx = sel.map_x(a);
+        const CUtensorMap* mw = sel.map_w(a);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S, u = it / S;
           if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
           uint8_t* st = smem + s * stage_bytes;
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-          tma_load_2d(st, &map_x, kb * BK, m0, &full_bar[s]);
-          tma_load_2d(st + A_STAGE_BYTES, &map_w, kb * BK, n0, &full_bar[s]);
+          tma_load_2d(st, mx, kb * BK, m0, &full_bar[s]);
+          tma_load_2d(st + A_STAGE_BYTES, mw, kb * BK, n0, &full_bar[s]);
         }
       }
     }
@@ -771,42 +851,117 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_kernel(con
     uint8_t* buf = out_buf + half * (BM * 128);
     int i = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * n_tile;
+      const int a = tile / per_problem, rem = tile - a * per_problem;
+      const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * n_tile;
+      const mmb_mlp_layer_params& pa = sel.p(a);
+      const CUtensorMap* my = sel.map_y(a);
       const int acc = i & 1, use = i >> 1;
+      const bool fast = pa.epilogue == 1 && (ce - cb) % 64 == 0 && n0 + n_tile <= pa.N;   // (the same for all eight warps: they meet at barrier 1)
+      const int m = m0 + row;
+      const bool corr = pa.ln_in_stats != nullptr;
+      float mean = 0.0f, rstd = 1.0f;
+      if (fast) {
+        // everything that does not need the accumulator happens BEFORE it is waited for: this tile's bias / c rows into shared
+        // memory (one element per thread), the row's LayerNorm moments from the producing layer's partials (L2 reads)
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the previous tile's readers of bias_s / c_s are done
+        { const int e = tid - 64; if (e < n_tile) { bias_s[e] = __ldg(pa.bias + n0 + e); c_s[e] = corr ? __ldg(pa.ln_c + n0 + e) : 0.0f; } }
+        if (corr) ln_row_moments(pa, m, mean, rstd);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(&acc_full[acc], (uint32_t)(use & 1));
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * n_tile);
+      if (fast) {
+        // Hidden layers, the hot case (the generic path below took ~12 us per 128 x 256 tile and bounded the whole launch):
+        // tensor-memory loads one 32-column chunk ahead, bias / c rows in shared memory, the staging buffer's previous store
+        // only waited for when the buffer is written again.
+        const bool stats = pa.ln_out_stats != nullptr && m < pa.M;
+        uint8_t* rowp = buf + (row >> 3) * 1024 + (row & 7) * 128;
+        const bool leader = q == 0 && lane == 0;
+        uint32_t ra[32], rb[32], pk[32];
+        float psum = 0.0f, psq = 0.0f;
+        auto chunk = [&](const uint32_t (&r)[32], int col, uint32_t* out16) {   // 32 columns from tile column col: -> 16 packed bf16 pairs
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + col);
+          const float4* c4 = reinterpret_cast<const float4*>(c_s + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = b4[i];
+            float t0 = __uint_as_float(r[4 * i]), t1 = __uint_as_float(r[4 * i + 1]), t2 = __uint_as_float(r[4 * i + 2]), t3 = __uint_as_float(r[4 * i + 3]);
+            if (corr) {
+              const float4 c = c4[i];
+              t0 = rstd * (t0 - mean * c.x); t1 = rstd * (t1 - mean * c.y); t2 = rstd * (t2 - mean * c.z); t3 = rstd * (t3 - mean * c.w);
+            }
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(elu1(t0 + b.x), elu1(t1 + b.y)), h1 = __floats2bfloat162_rn(elu1(t2 + b.z), elu1(t3 + b.w));
+            out16[2 * i] = *reinterpret_cast<const uint32_t*>(&h0);
+            out16[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+            if (stats) {
+              const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+              psum += f0.x; psq += f0.x * f0.x; psum += f0.y; psq += f0.y * f0.y;
+              psum += f1.x; psq += f1.x * f1.x; psum += f1.y; psq += f1.y * f1.y;
+            }
+          }
+        };
+        tmem_ld32_issue(taddr + cb, ra);
+        for (int c0 = cb; c0 < ce; c0 += 64) {
+          tmem_ld_wait(ra);
+          tmem_ld32_issue(taddr + c0 + 32, rb);
+          chunk(ra, c0, pk);
+          tmem_ld_wait(rb);
+          if (c0 + 64 < ce) tmem_ld32_issue(taddr + c0 + 64, ra);
+          chunk(rb, c0 + 32, pk + 16);
+          if (leader) tma_store_wait_read();                // the buffer fed the previous sub-tile's (or tile's) store
+          if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          fence_async_smem();
+          if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (leader) {
+            tma_store_2d(my, buf, n0 + c0, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (stats) ln_store_partial(pa, m, n0 + cb, psum, psq);
+      } else
       // every finished sub-tile goes out through this half's staging buffer: staged -> barrier -> one lane stores and waits
       // until the TMA has read the buffer -> barrier -> the buffer is free for the next sub-tile
-      epilogue_row_staged(p, taddr, row, n0, n_tile, cb, ce, buf - (cb / sub_cols) * 0, [&](int j) {
+      epilogue_row_staged(pa, taddr, row, n0, n_tile, cb, ce, buf - (cb / sub_cols) * 0, [&](int j) {
         fence_async_smem();
         if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         if (q == 0 && lane == 0) {
-          tma_store_2d(&map_y, buf, n0 + j * sub_cols, m0);
+          tma_store_2d(my, buf, n0 + j * sub_cols, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           tma_store_wait_read();
         }
         if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
-      }, 0);
+      }, 0, m0 + row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
     }
+    if (q == 0 && lane == 0) tma_store_wait_read();       // the fast path leaves its last store in flight: the buffer must outlive it
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_kernel(const __grid_constant__ mmb_mlp_layer_params p,
+                                                                             const __grid_constant__ CUtensorMap map_x,
+                                                                             const __grid_constant__ CUtensorMap map_w,
+                                                                             const __grid_constant__ CUtensorMap map_y) {
+  mlp_layer_ws_persist_body(PersistOne{p, map_x, map_w, map_y}, 1);
+}
+// the team's networks as ONE persistent launch per layer: 10 agents x 32 row blocks x 2 column tiles = 640 tiles walked by one
+// CTA per SM, each tile's epilogue under the next tile's k-loop (the non-persistent grouped launch paid prologue, pipeline fill
+// and an exposed epilogue per tile: 4.3 waves of ~10 us for 2.6 us of k-loop each)
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_group_kernel(const __grid_constant__ WsGroupArgs g, const int count) {
+  mlp_layer_ws_persist_body(PersistGroup{g}, count);
+}
 
-// Grouped launch: blockIdx.z selects one of up to MMB_MAX_GROUP independent problems of identical geometry (the ten
-// per-agent networks of the MARL policies, actor_critic.py / runner.py:205-217): one launch per layer for the whole team.
-// Parameters and tensor maps travel as one large __grid_constant__ kernel argument (8 KB; CUDA 12.1+ allows 32 KB).
-struct WsGroupArgs {
-  mmb_mlp_layer_params p[MMB_MAX_GROUP];
-  CUtensorMap map_x[MMB_MAX_GROUP], map_w[MMB_MAX_GROUP], map_y[MMB_MAX_GROUP];
-};
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_group_kernel(const __grid_constant__ WsGroupArgs g) {
   const int a = blockIdx.z;
   mlp_layer_ws_body<false>(g.p[a], g.map_x[a], g.map_w[a], g.map_y[a]);
@@ -1852,6 +2007,12 @@ __global__ void __launch_bounds__(256) cast_pad_group_kernel(const __grid_consta
 
 using namespace mmb;
 
+static bool ln_deferred_ok(const mmb_mlp_layer_params& p) {     // the deferred LayerNorm fields of include/mmb.h
+  if (p.ln_in_stats && (!p.ln_c || p.ln_in_parts <= 0 || p.ln_in_n <= 0 || (reinterpret_cast<uintptr_t>(p.ln_in_stats) & 7u))) return false;
+  if (p.ln_out_stats && (p.epilogue != 1 || p.n_tile != 256 || p.Npad % 256 || (reinterpret_cast<uintptr_t>(p.ln_out_stats) & 7u))) return false;
+  return true;
+}
+
 extern "C" __attribute__((visibility("default"))) int32_t mmb_mlp_debug_status(unsigned int* out4) {
   unsigned int z[4] = {0, 0, 0, 0};
   if (cudaMemcpyFromSymbol(out4, g_pair_dbg, 16) != cudaSuccess) return MMB_ECUDA;
@@ -1867,7 +2028,19 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return MMB_EUNSUPPORTED;
-  const int smem = stages * stage_bytes;
+  int smem = stages * stage_bytes;
+  // persistent, epilogue-overlapped variant over ALL problems' tiles (same conditions as the single-problem launch)
+  static const int persist_pref = [] { const char* v = getenv("MMB_MLP_PERSIST"); return v ? atoi(v) : 1; }();
+  const int num_tiles = count * (p0.Mpad / BM) * (p0.Npad / p0.n_tile);
+  const int sub_cols_h = (p0.epilogue == 0) ? 32 : 64;
+  bool persist = persist_pref && p0.epilogue != 2 && p0.n_tile <= 256 && num_tiles >= 2 * sm_count() && (p0.n_tile / 2) % sub_cols_h == 0;
+  for (int a = 0; a < count && persist; ++a)
+    persist = (p0.epilogue == 0) ? (((params[a].y_stride & 3) | (reinterpret_cast<uintptr_t>(params[a].y) & 15u)) == 0) : (p0.n_tile % 64 == 0);
+  if (persist) {
+    stages = (SMEM_BUDGET + 24 * 1024 - 2 * BM * 128) / stage_bytes;      // ring + two 16 KB staging buffers within 224 KB
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    smem = stages * stage_bytes + 2 * BM * 128;
+  }
   for (int a = 0; a < count; ++a) {
     mmb_mlp_layer_params p = params[a];
     if (p.M != p0.M || p.N != p0.N || p.K != p0.K || p.Mpad != p0.Mpad || p.Kpad != p0.Kpad || p.Npad != p0.Npad ||
@@ -1876,6 +2049,8 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
     if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.x || !p.w || !p.bias || !p.y || p.Kpad < p.K || p.Npad < p.N || p.Mpad < p.M) return MMB_EINVAL;
     if (p.epilogue < 0 || p.epilogue > 2) return MMB_EINVAL;
     if (p.epilogue == 2 && (p.n_tile != p.N || p.Npad != p.N || !p.ln_gamma || !p.ln_beta)) return MMB_EINVAL;
+    if (!ln_deferred_ok(p) || (p.ln_in_stats == nullptr) != (p0.ln_in_stats == nullptr) || (p.ln_out_stats == nullptr) != (p0.ln_out_stats == nullptr))
+      return MMB_EINVAL;
     if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w)) & 15u) return MMB_EALIGN;
     p.stages = stages;
     if (!make_map_bf16_2d(&g.map_x[a], p.x, (uint64_t)p.Mpad, (uint64_t)p.Kpad, BM) ||
@@ -1899,7 +2074,25 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
   if (!attr_done[dev]) {
     if (cudaFuncSetAttribute(mlp_layer_ws_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess)
       return MMB_ECUDA;
+    if (cudaFuncSetAttribute(mlp_layer_ws_persist_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess)
+      return MMB_ECUDA;
     attr_done[dev] = true;
+  }
+  if (persist) {
+    LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
+    cudaLaunchConfig_t cfg = {};
+    const int sms = sm_count();
+    cfg.gridDim = dim3(num_tiles < sms ? num_tiles : sms);
+    cfg.blockDim = dim3(WS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p0.overlap_prev ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, mlp_layer_ws_persist_group_kernel, g, (int)count) != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
+    return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
   }
   {
     LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
@@ -1953,6 +2146,7 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   if (p.Mpad % BM || p.Mpad < p.M) return MMB_EINVAL;
   if (p.epilogue < 0 || p.epilogue > 2) return MMB_EINVAL;
   if (p.epilogue == 2 && (p.n_tile != p.N || p.Npad != p.N || !p.ln_gamma || !p.ln_beta)) return MMB_EINVAL;
+  if (!ln_deferred_ok(p)) return MMB_EINVAL;
   if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w)) & 15u) return MMB_EALIGN;
   const int stage_bytes = A_STAGE_BYTES + p.n_tile * BK * 2;
   static const bool legacy = [] { const char* v = getenv("MMB_MLP_VARIANT"); return v && v[0] == 'l'; }();
@@ -2135,6 +2329,7 @@ extern "C" int32_t mmb_mlp_chain(const mmb_mlp_layer_params* layers, int32_t num
       if ((!p.x && !(l == 0 && x_fp32)) || !p.w || !p.bias || !p.y || p.M != f.M || p.Mpad != f.Mpad || p.N <= 0 || p.K <= 0) return MMB_EINVAL;
       if (p.N != r.N || p.K != r.K || p.Kpad != r.Kpad || p.epilogue != r.epilogue || p.y_stride != r.y_stride) return MMB_EINVAL;
       if (p.operand_type != f.operand_type) return MMB_EINVAL;
+      if (p.ln_in_stats || p.ln_out_stats) return MMB_EUNSUPPORTED;   // deferred LayerNorm: per-layer launches only
       if (tf32 ? (p.Kpad % 4 || p.Kpad < p.K) : (p.Kpad % BK || p.Kpad < p.K)) return MMB_EINVAL;
       if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.y)) & 15u) return MMB_EALIGN;
       const bool last = l == num_layers - 1;

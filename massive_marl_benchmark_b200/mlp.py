@@ -46,13 +46,20 @@ class _Layer:
     place into the existing buffers, so cached activation buffers / CUDA graphs built on them stay valid.
     `n_out` > weight.shape[0] zero-pads the output width (the critic's 1-wide head run next to the actor's)."""
 
-    def __init__(self, weight, bias, act: bool, ln=None, device="cuda", n_out=None):
+    def __init__(self, weight, bias, act: bool, ln=None, device="cuda", n_out=None, fold=None, stats_out=False):
         n_src, K = weight.shape
         N = n_src if n_out is None else int(n_out)
         self.N, self.K, self.n_src = N, K, n_src
         self.Kpad = _round_up(K, 64)
         self.act = act
         self.ln = _ln_parts(ln)
+        # Deferred LayerNorm (include/mmb.h, `ln_in_stats`): `fold` = (gamma, beta, eps) of the LayerNorm that precedes this
+        # layer's Linear - gamma is multiplied into the weight columns, W beta into the bias, c[n] = sum_k of the folded bf16
+        # weights; `stats_out`: this layer's epilogue writes the partial row sums its successor normalises with.
+        self.fold = _ln_parts(fold)
+        self.stats_out = bool(stats_out)
+        if self.fold is not None:
+            self.c = torch.zeros(N, dtype=torch.float32, device=device)
         if self.ln is not None:                  # bias + ELU + LayerNorm over the whole row: one CTA owns full rows
             if N not in (32, 64, 96, 128, 160, 192, 224, 256, 512):
                 raise L.MmbError("LayerNorm epilogue needs N <= 256 (multiple of 32) or N == 512, got %d" % N)
@@ -71,13 +78,14 @@ class _Layer:
         self.refresh(weight, bias, ln)
 
     def _sources(self):
-        return [t for t in (self._src[0], self._src[1]) + ((self.ln[0], self.ln[1]) if self.ln is not None else ())]
+        return [t for t in (self._src[0], self._src[1]) + ((self.ln[0], self.ln[1]) if self.ln is not None else ()) +
+                ((self.fold[0], self.fold[1]) if self.fold is not None else ())]
 
     def stale(self):
         return tuple(t._version for t in self._sources()) != self._ver
 
     @torch.no_grad()
-    def refresh(self, weight=None, bias=None, ln=None):
+    def refresh(self, weight=None, bias=None, ln=None, fold=None):
         """Re-cast from the (given or remembered) source tensors into the existing kernel-side buffers."""
         if weight is not None:
             if tuple(weight.shape) != (self.n_src, self.K):
@@ -85,9 +93,19 @@ class _Layer:
             self._src = (weight, bias)
             if self.ln is not None and ln is not None:
                 self.ln = _ln_parts(ln)
+            if self.fold is not None and fold is not None:
+                self.fold = _ln_parts(fold)
         w, b = self._src
-        self.w[:self.n_src, :self.K].copy_(w.detach(), non_blocking=True)       # fp32 -> bf16 in the copy kernel
-        self.bias[:self.n_src].copy_(b.detach(), non_blocking=True)
+        if self.fold is not None:
+            dev = self.w.device
+            wf32 = w.detach().to(dev, torch.float32)
+            gamma, beta = self.fold[0].detach().to(dev, torch.float32), self.fold[1].detach().to(dev, torch.float32)
+            self.w[:self.n_src, :self.K].copy_(wf32 * gamma[None, :])          # W gamma -> bf16
+            self.c[:self.n_src].copy_(self.w[:self.n_src, :self.K].float().sum(dim=1))   # of the weights AS STORED
+            self.bias[:self.n_src].copy_(b.detach().to(dev, torch.float32) + wf32 @ beta)
+        else:
+            self.w[:self.n_src, :self.K].copy_(w.detach(), non_blocking=True)       # fp32 -> bf16 in the copy kernel
+            self.bias[:self.n_src].copy_(b.detach(), non_blocking=True)
         if self.ln is not None:
             self.gamma.copy_(self.ln[0].detach(), non_blocking=True)
             self.beta.copy_(self.ln[1].detach(), non_blocking=True)
@@ -95,6 +113,7 @@ class _Layer:
 
 
 _CHAIN_ENABLED = os.environ.get("MMB_MLP_CHAIN", "1") != "0"
+_DEFER_LN = os.environ.get("MMB_MLP_DEFER_LN", "1") != "0"     # MARL trunks: LayerNorms applied by the consuming layer
 
 
 def _chain_launch(owner, arr, num_layers, count, stream, x_fp32=None):
@@ -128,7 +147,7 @@ class FusedMLP:
             self.in_beta = torch.zeros(self.in_dim, dtype=torch.float32, device=device)
             self.in_eps = self.in_ln[2]
         self._in_ver = None
-        self._bufs = {}
+        self._bufs, self._stats = {}, {}
         self.auto_refresh = True      # forward() re-casts the weights when their source tensors have changed
         self._refresh_in_ln()
 
@@ -167,6 +186,13 @@ class FusedMLP:
             self.in_ln = (sd["base.feature_norm.weight"], sd["base.feature_norm.bias"], self.in_eps)
             self._refresh_in_ln()
         names = ["base.mlp.fc1"] + ["base.mlp.fc2.%d" % i for i in range(len(self.layers) - 2)]
+        if any(l.fold is not None for l in self.layers):         # deferred LayerNorm: layer i folds the LayerNorm of layer i - 1
+            prev = None
+            for l, n in zip(self.layers[:-1], names):
+                l.refresh(sd[n + ".0.weight"], sd[n + ".0.bias"], fold=prev)
+                prev = (sd[n + ".2.weight"], sd[n + ".2.bias"], 1e-5)
+            self.layers[-1].refresh(sd[head + ".weight"], sd[head + ".bias"], fold=prev)
+            return
         for l, n in zip(self.layers[:-1], names):
             l.refresh(sd[n + ".0.weight"], sd[n + ".0.bias"], (sd[n + ".2.weight"], sd[n + ".2.bias"], l.eps))
         self.layers[-1].refresh(sd[head + ".weight"], sd[head + ".bias"])
@@ -196,12 +222,19 @@ class FusedMLP:
         def ln_of(prefix):      # live tensors (a module's state_dict() shares storage and version counters with its parameters)
             return sd[prefix + ".weight"], sd[prefix + ".bias"], 1e-5
         in_ln = ln_of("base.feature_norm") if "base.feature_norm.weight" in sd else None
-        layers = [_Layer(sd["base.mlp.fc1.0.weight"], sd["base.mlp.fc1.0.bias"], True, ln_of("base.mlp.fc1.2"), device)]
-        i = 0
-        while "base.mlp.fc2.%d.0.weight" % i in sd:
-            layers.append(_Layer(sd["base.mlp.fc2.%d.0.weight" % i], sd["base.mlp.fc2.%d.0.bias" % i], True,
-                                 ln_of("base.mlp.fc2.%d.2" % i), device))
-            i += 1
+        names = ["base.mlp.fc1"]
+        while "base.mlp.fc2.%d.0.weight" % (len(names) - 1) in sd:
+            names.append("base.mlp.fc2.%d" % (len(names) - 1))
+        if _DEFER_LN and all(sd[n + ".0.weight"].shape[0] % 256 == 0 for n in names):
+            # every hidden LayerNorm is applied by the layer that consumes it (deferred LayerNorm): free tile widths, one
+            # pass over the accumulator, and no epilogue that needs all of tensor memory
+            layers, prev = [], None
+            for n in names:
+                layers.append(_Layer(sd[n + ".0.weight"], sd[n + ".0.bias"], True, None, device, fold=prev, stats_out=True))
+                prev = ln_of(n + ".2")
+            layers.append(_Layer(sd[head + ".weight"], sd[head + ".bias"], False, None, device, fold=prev))
+            return cls(layers, in_ln, device)
+        layers = [_Layer(sd[n + ".0.weight"], sd[n + ".0.bias"], True, ln_of(n + ".2"), device) for n in names]
         layers.append(_Layer(sd[head + ".weight"], sd[head + ".bias"], False, None, device))
         return cls(layers, in_ln, device)
 
@@ -213,7 +246,19 @@ class FusedMLP:
             for l in self.layers[:-1]:
                 acts.append(torch.zeros(Mpad, _round_up(l.N, 64), dtype=torch.bfloat16, device=self.device))
             self._bufs[M] = (Mpad, acts)
+            # deferred LayerNorm: per producing layer, [Mpad][Npad / 128] (sum, sum of squares) partials
+            self._stats[M] = [torch.zeros(Mpad, l.Npad // 128, 2, dtype=torch.float32, device=self.device) if l.stats_out else None
+                              for l in self.layers]
         return self._bufs[M]
+
+    def _fill_deferred(self, p, i, stats, parts_of):
+        """The deferred-LayerNorm fields of layer i's launch parameters (stats: per layer, this network's partials)."""
+        l = self.layers[i]
+        if l.stats_out:
+            p.ln_out_stats = L.ptr(stats[i])
+        if l.fold is not None:
+            p.ln_in_stats, p.ln_in_parts, p.ln_in_n = L.ptr(stats[i - 1]), parts_of(i - 1), self.layers[i - 1].N
+            p.ln_in_eps, p.ln_c = l.fold[2], L.ptr(l.c)
 
     @staticmethod
     def _n_tile(l, Mpad, target_ctas=118):
@@ -221,6 +266,8 @@ class FusedMLP:
         (148 SMs; wide tiles reuse the A tile more, but a 64-CTA grid leaves half the GPU idle)."""
         if l.n_tile is not None:
             return l.n_tile
+        if l.stats_out:                 # deferred LayerNorm: the producer's partial sums are per 128 columns = half a 256-wide tile
+            return 256
         cands = [t for t in (256, 128, 64, 32) if l.Npad % t == 0]
         for t in cands:
             if (Mpad // 128) * (l.Npad // t) >= target_ctas:
@@ -235,7 +282,7 @@ class FusedMLP:
         the single-launch kernel does not take raise (there is no per-layer tf32 kernel)."""
         if x.device.type != "cuda":
             raise L.MmbError("FusedMLP runs on CUDA tensors only")
-        if self.in_ln is not None or any(l.epilogue == 2 for l in self.layers):
+        if self.in_ln is not None or any(l.epilogue == 2 or l.fold is not None or l.stats_out for l in self.layers):
             raise L.MmbError("forward_tf32: Linear-ELU chains only")
         M = x.shape[0]
         x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
@@ -296,6 +343,7 @@ class FusedMLP:
             if l.epilogue == 2:
                 p.ln_gamma, p.ln_beta, p.ln_eps = L.ptr(l.gamma), L.ptr(l.beta), l.eps
             p.overlap_prev = 1        # the predecessor in the stream is ln_cast / the previous layer: never writes weights
+            self._fill_deferred(p, i, self._stats[M], lambda j: self._stats[M][j].shape[1])
             if i == nl - 1:
                 p.y, p.y_stride = L.ptr(out), out.stride(0)
             else:
@@ -335,11 +383,12 @@ class GroupedMLP:
         a = mlps[0]
         for m in mlps[1:]:
             if len(m.layers) != len(a.layers) or (m.in_ln is None) != (a.in_ln is None) or any(
-                    (x.N, x.K, x.epilogue) != (y.N, y.K, y.epilogue) for x, y in zip(m.layers, a.layers)):
+                    (x.N, x.K, x.epilogue, x.fold is None, x.stats_out) != (y.N, y.K, y.epilogue, y.fold is None, y.stats_out)
+                    for x, y in zip(m.layers, a.layers)):
                 raise L.MmbError("GroupedMLP needs networks of identical architecture")
         self.mlps, self.G, self.device = list(mlps), len(mlps), a.device
         self.in_dim, self.out_dim = a.in_dim, a.out_dim
-        self._bufs = {}
+        self._bufs, self._stats = {}, {}
         self.auto_refresh = True
 
     def stale(self):
@@ -357,6 +406,8 @@ class GroupedMLP:
             for l in a.layers[:-1]:
                 acts.append(torch.zeros(self.G, Mpad, _round_up(l.N, 64), dtype=torch.bfloat16, device=self.device))
             self._bufs[M] = (Mpad, acts)
+            self._stats[M] = [torch.zeros(self.G, Mpad, l.Npad // 128, 2, dtype=torch.float32, device=self.device) if l.stats_out else None
+                              for l in a.layers]
         return self._bufs[M]
 
     def forward(self, xs, out=None):
@@ -398,6 +449,8 @@ class GroupedMLP:
             if l.epilogue == 2:
                 p.ln_gamma, p.ln_beta, p.ln_eps = l.gamma.data_ptr(), l.beta.data_ptr(), l.eps
             p.overlap_prev = 1
+            st_g = [None if t is None else t[g] for t in self._stats[M]]
+            self.mlps[g]._fill_deferred(p, i, st_g, lambda j: self._stats[M][j].shape[2])
             if i == nl - 1:
                 p.y, p.y_stride = out[g].data_ptr(), out.stride(1)
             else:
@@ -429,10 +482,20 @@ class GroupedMLP:
                     return out
         if not casted:
             cast_inputs()
-        for i in range(nl):
-            arr = (L.MlpLayerParams * G)()
-            for g in range(G):
-                fill(arr[g], g, i)
+        # steady state of a rollout loop (same batch, same buffers): the filled per-layer parameter arrays of the last such call
+        lcache = self.__dict__.setdefault("_layer_cache", {})
+        arrs = lcache.get(key)
+        if arrs is None:
+            arrs = []
+            for i in range(nl):
+                arr = (L.MlpLayerParams * G)()
+                for g in range(G):
+                    fill(arr[g], g, i)
+                arrs.append(arr)
+            if len(lcache) >= 8:
+                lcache.clear()
+            lcache[key] = arrs
+        for arr in arrs:
             L.check(lib.mmb_mlp_layer_group(arr, G, st), "mmb_mlp_layer_group")
         return out
 
