@@ -802,19 +802,20 @@ __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const 
     // ===== TMA producer: the ring position runs on across tiles =====
     if (elect_one()) {
       if (p.overlap_prev) griddep_wait();
-      int it = 0;
+      int s = 0;
+      uint32_t u = 0;                          // (no division in these single-thread loops: tools/probe/tma_mma_rate.cu)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int a = tile / per_problem, rem = tile - a * per_problem;
         const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * n_tile;
         const CUtensorMap* mx = sel.map_x(a);
         const CUtensorMap* mw = sel.map_w(a);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S, u = it / S;
-          if (u > 0) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (u > 0) mbar_wait(&empty_bar[s], (u - 1) & 1u);
           uint8_t* st = smem + s * stage_bytes;
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           tma_load_2d(st, mx, kb * BK, m0, &full_bar[s]);
           tma_load_2d(st + A_STAGE_BYTES, mw, kb * BK, n0, &full_bar[s]);
+          if (++s == S) { s = 0; ++u; }
         }
       }
     }
@@ -822,21 +823,25 @@ __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const 
     // ===== MMA issuer: accumulator i & 1 =====
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(n_tile);
-      int it = 0, i = 0;
+      const uint64_t da0 = umma_desc_k_sw128(smem_u32(smem)), db0 = umma_desc_k_sw128(smem_u32(smem) + A_STAGE_BYTES);
+      const uint32_t dstep = (uint32_t)stage_bytes >> 4;
+      int s = 0, i = 0;
+      uint32_t u = 0;
+      uint64_t da = da0, db = db0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
         const int acc = i & 1, use = i >> 1;
         if (use > 0) mbar_wait(&acc_empty[acc], (uint32_t)((use - 1) & 1));   // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem + (uint32_t)(acc * n_tile);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S, u = it / S;
-          mbar_wait(&full_bar[s], (uint32_t)(u & 1));
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes), b_addr = a_addr + A_STAGE_BYTES;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], u & 1u);
+          if (kb == 0) umma_bf16(tacc, da, db, idesc, false);
+          else umma_bf16_acc(tacc, da, db, idesc);
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j)
-            umma_bf16(tacc, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kb > 0) || (j > 0));
+          for (int j = 1; j < BK / 16; ++j) umma_bf16_acc(tacc, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc);
           umma_commit(&empty_bar[s]);
+          if (++s == S) { s = 0; ++u; da = da0; db = db0; }
+          else { da += dstep; db += dstep; }
         }
         umma_commit(&acc_full[acc]);
       }
@@ -846,8 +851,11 @@ __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const 
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int sub_cols = (p.epilogue == 0) ? 32 : 64;
-    const int mid = n_tile / 2;                         // host guarantees: mid is a multiple of sub_cols
-    const int cb = half ? mid : 0, ce = half ? n_tile : mid;
+    // the two warps of a lane quarter split the columns (host: the halves are whole sub-tiles); a tile narrower than two
+    // sub-tiles (an 8- or 1-wide head) goes to the first of them
+    const bool split = n_tile >= 2 * sub_cols;
+    const int mid = n_tile / 2;
+    const int cb = (split && half) ? mid : 0, ce = split ? (half ? n_tile : mid) : (half ? 0 : n_tile);
     uint8_t* buf = out_buf + half * (BM * 128);
     int i = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
@@ -2033,7 +2041,8 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
   static const int persist_pref = [] { const char* v = getenv("MMB_MLP_PERSIST"); return v ? atoi(v) : 1; }();
   const int num_tiles = count * (p0.Mpad / BM) * (p0.Npad / p0.n_tile);
   const int sub_cols_h = (p0.epilogue == 0) ? 32 : 64;
-  bool persist = persist_pref && p0.epilogue != 2 && p0.n_tile <= 256 && num_tiles >= 2 * sm_count() && (p0.n_tile / 2) % sub_cols_h == 0;
+  bool persist = persist_pref && p0.epilogue != 2 && p0.n_tile <= 256 && num_tiles >= 2 * sm_count() &&
+                 (p0.n_tile < 2 * sub_cols_h || (p0.n_tile / 2) % sub_cols_h == 0);
   for (int a = 0; a < count && persist; ++a)
     persist = (p0.epilogue == 0) ? (((params[a].y_stride & 3) | (reinterpret_cast<uintptr_t>(params[a].y) & 15u)) == 0) : (p0.n_tile % 64 == 0);
   if (persist) {
@@ -2203,7 +2212,7 @@ extern "C" int32_t mmb_mlp_layer(const mmb_mlp_layer_params* pp, void* stream) {
   const bool y_tma = (p.epilogue == 0) ? (((p.y_stride & 3) | (reinterpret_cast<uintptr_t>(p.y) & 15u)) == 0) : (p.n_tile % 64 == 0);
   const int sub_cols_h = (p.epilogue == 0) ? 32 : 64;
   const bool persist = persist_pref && !pair && cm == 1 && p.epilogue != 2 && p.n_tile <= 256 && y_tma && num_tiles >= 2 * sm_count() &&
-                       (p.n_tile / 2) % sub_cols_h == 0;
+                       (p.n_tile < 2 * sub_cols_h || (p.n_tile / 2) % sub_cols_h == 0);
   if (persist) {
     const int sb = A_STAGE_BYTES + p.n_tile * BK * 2;
     int st = (SMEM_BUDGET + 24 * 1024 - 2 * BM * 128) / sb;      // ring + two 16 KB staging buffers within 224 KB
