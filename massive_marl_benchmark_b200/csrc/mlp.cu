@@ -1861,7 +1861,7 @@ struct MapCacheEntry {
 };
 inline bool make_map_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows);
 inline bool make_map_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kpad, uint32_t box_rows) {
-  constexpr int kEntries = 256;
+  constexpr int kEntries = 1024;
   static thread_local MapCacheEntry cache[kEntries];
   const uint64_t h = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull + rows * 31 + kpad * 7 + box_rows;
   MapCacheEntry& e = cache[(h >> 32) % kEntries];
@@ -2029,6 +2029,43 @@ extern "C" __attribute__((visibility("default"))) int32_t mmb_mlp_debug_status(u
 
 extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32_t count, void* stream) {
   if (!params || count <= 0 || count > MMB_MAX_GROUP) return MMB_EINVAL;
+  // A rollout loop calls this with the same few parameter arrays over and over (one per layer and team): the validated
+  // arguments and their 3 x count tensor maps are kept per distinct array (compared byte for byte), so the steady state is a
+  // memcmp and a launch.  (The per-map cache alone thrashes: a team of ten has 240 maps in play, and a re-encode costs ~3 us.)
+  struct GroupSlot { bool valid; int count, persist, smem; mmb_mlp_layer_params in[MMB_MAX_GROUP]; WsGroupArgs g; };
+  constexpr int kSlots = 32;
+  static thread_local GroupSlot* slots = nullptr;
+  if (!slots) slots = static_cast<GroupSlot*>(calloc(kSlots, sizeof(GroupSlot)));
+  GroupSlot* slot = nullptr;
+  if (slots) {
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(params);
+    for (size_t i = 0; i < (size_t)count * sizeof(mmb_mlp_layer_params); i += 8) {     // (the struct is a multiple of 8 bytes)
+      uint64_t w;
+      memcpy(&w, bytes + i, 8);
+      h = (h ^ w) * 1099511628211ull;
+    }
+    slot = &slots[(h >> 20) % kSlots];
+    if (slot->valid && slot->count == count && memcmp(slot->in, params, (size_t)count * sizeof(mmb_mlp_layer_params)) == 0) {
+      const mmb_mlp_layer_params& q0 = params[0];
+      LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
+      cudaLaunchConfig_t cfg = {};
+      const int tiles = count * (q0.Mpad / BM) * (q0.Npad / q0.n_tile), sms = sm_count();
+      cfg.gridDim = slot->persist ? dim3(tiles < sms ? tiles : sms) : dim3(q0.Mpad / BM, q0.Npad / q0.n_tile, count);
+      cfg.blockDim = dim3(WS_THREADS);
+      cfg.dynamicSmemBytes = slot->smem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = q0.overlap_prev ? 1 : 0;
+      const cudaError_t le = slot->persist ? cudaLaunchKernelEx(&cfg, mlp_layer_ws_persist_group_kernel, slot->g, (int)count)
+                                           : cudaLaunchKernelEx(&cfg, mlp_layer_ws_group_kernel, slot->g);
+      if (le != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
+      return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+    }
+  }
   static thread_local WsGroupArgs g;       // 8 KB: not on the stack; the launch copies it
   const mmb_mlp_layer_params& p0 = params[0];
   if (p0.n_tile <= 0 || p0.Kpad % BK || p0.Mpad % BM || p0.Npad % p0.n_tile || p0.n_tile % 32 || p0.n_tile > 512) return MMB_EINVAL;
@@ -2086,6 +2123,13 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
     if (cudaFuncSetAttribute(mlp_layer_ws_persist_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess)
       return MMB_ECUDA;
     attr_done[dev] = true;
+  }
+  if (slot) {                              // remember the validated arguments and their maps
+    slot->valid = false;
+    slot->count = count; slot->persist = persist ? 1 : 0; slot->smem = smem;
+    memcpy(slot->in, params, (size_t)count * sizeof(mmb_mlp_layer_params));
+    memcpy(&slot->g, &g, sizeof(WsGroupArgs));
+    slot->valid = true;
   }
   if (persist) {
     LaunchScope ls(K_MLP_LAYER, (cudaStream_t)stream);
