@@ -159,17 +159,35 @@ class FusedMLP:
             self.in_beta.copy_(self.in_ln[1].detach(), non_blocking=True)
             self._in_ver = (self.in_ln[0]._version, self.in_ln[1]._version)
 
+    def _flat_sources(self):
+        """Every live tensor the kernel-side copies were cast from, in a fixed order (rebuilt after a re-binding refresh)."""
+        src = self.__dict__.get("_flat_src")
+        if src is None:
+            src = list(self.in_ln[:2]) if self.in_ln is not None else []
+            for l in self.layers:
+                src.extend(l._sources())
+            self._flat_src = src
+            self._flat_ver = None
+        return src
+
     def stale(self):
         """True when a source parameter was modified in place since the last cast (optimizer.step(), load_state_dict)."""
+        ver = tuple([t._version for t in self._flat_sources()])
+        if ver == self._flat_ver:
+            return False
         if self.in_ln is not None and (self.in_ln[0]._version, self.in_ln[1]._version) != self._in_ver:
             return True
-        return any(l.stale() for l in self.layers)
+        if any(l.stale() for l in self.layers):
+            return True
+        self._flat_ver = ver          # (the per-layer records agree: remember the flat tuple for the one-compare fast path)
+        return False
 
     def refresh(self):
         """Re-cast every layer from its source tensors, in place (buffers, pointers and captured graphs stay valid)."""
         self._refresh_in_ln()
         for l in self.layers:
             l.refresh()
+        self._flat_src = None
 
     def refresh_from_sequential(self, seq):
         """Re-bind to (and re-cast from) another nn.Sequential of the same architecture, e.g. after the module object was
@@ -179,6 +197,7 @@ class FusedMLP:
             raise L.MmbError("refresh_from_sequential: %d Linear layers, expected %d" % (len(lins), len(self.layers)))
         for l, lin in zip(self.layers, lins):
             l.refresh(lin.weight, lin.bias)
+        self._flat_src = None
 
     def refresh_from_marl_state_dict(self, sd, head="act.action_out.fc_mean"):
         """Re-bind to (and re-cast from) another Actor / Critic state dict of the same architecture; in place."""
@@ -186,6 +205,7 @@ class FusedMLP:
             self.in_ln = (sd["base.feature_norm.weight"], sd["base.feature_norm.bias"], self.in_eps)
             self._refresh_in_ln()
         names = ["base.mlp.fc1"] + ["base.mlp.fc2.%d" % i for i in range(len(self.layers) - 2)]
+        self._flat_src = None
         if any(l.fold is not None for l in self.layers):         # deferred LayerNorm: layer i folds the LayerNorm of layer i - 1
             prev = None
             for l, n in zip(self.layers[:-1], names):
@@ -329,9 +349,13 @@ class FusedMLP:
             out = torch.empty(M, self.out_dim, dtype=torch.float32, device=self.device)
         nl = len(self.layers)
         # steady state of a rollout loop: same batch, same buffers -> the filled parameter array of the last such call
-        key = (M, x.data_ptr(), out.data_ptr(), out.stride(0))
+        # (keyed by the batch size only: the input and output pointers - a fresh observation tensor and a fresh result per step
+        # in the reference's loops - are patched into the cached array)
+        key = M
         hit = self.__dict__.setdefault("_chain_cache", {}).get(key)
-        if hit is not None and _CHAIN_ENABLED:
+        if hit is not None and _CHAIN_ENABLED and x.data_ptr() % 16 == 0:
+            hit[0][nl - 1].y, hit[0][nl - 1].y_stride = out.data_ptr(), out.stride(0)
+            hit[1][0] = x.data_ptr()
             L.check(lib.mmb_mlp_chain(hit[0], nl, 1, hit[1], st), "mmb_mlp_chain")
             return out
         arr = (L.MlpLayerParams * nl)()
@@ -430,13 +454,17 @@ class GroupedMLP:
             if shared_input:                                 # one cast serves every network: slot 0 of the first operand buffer
                 L.check(lib.mmb_ln_cast(xs[0].data_ptr(), M, Mpad, l0.K, l0.Kpad, None, None, 0.0, 0, acts[0][0].data_ptr(), st), "mmb_ln_cast")
                 return
+            cc = self.__dict__.setdefault("_cast_cache", {})
+            args = cc.get(M)
+            if args is None:                                 # the static pointer arrays are built once per batch size
+                vp = C.c_void_p * G
+                args = cc[M] = (vp(), vp(*[m.in_gamma.data_ptr() for m in self.mlps]) if use_ln else None,
+                                vp(*[m.in_beta.data_ptr() for m in self.mlps]) if use_ln else None, vp(*[acts[0][g].data_ptr() for g in range(G)]))
             xl = xs if len(xs) == G else xs * G
-            vp = C.c_void_p * G
-            L.check(lib.mmb_ln_cast_group(vp(*[x.data_ptr() for x in xl]), G, M, Mpad, l0.K, l0.Kpad,
-                                          vp(*[m.in_gamma.data_ptr() for m in self.mlps]) if use_ln else None,
-                                          vp(*[m.in_beta.data_ptr() for m in self.mlps]) if use_ln else None,
-                                          a0.in_eps if use_ln else 0.0, int(use_ln), vp(*[acts[0][g].data_ptr() for g in range(G)]), st),
-                    "mmb_ln_cast_group")
+            for g in range(G):
+                args[0][g] = xl[g].data_ptr()
+            L.check(lib.mmb_ln_cast_group(args[0], G, M, Mpad, l0.K, l0.Kpad, args[1], args[2],
+                                          a0.in_eps if use_ln else 0.0, int(use_ln), args[3], st), "mmb_ln_cast_group")
         if out is None:
             out = torch.empty(G, M, self.out_dim, dtype=torch.float32, device=self.device)
         nl = len(a0.layers)
@@ -457,9 +485,14 @@ class GroupedMLP:
                 p.y, p.y_stride = acts[i + 1][g].data_ptr(), acts[i + 1].stride(1)
 
         casted = False
-        key = (M, tuple(x.data_ptr() for x in xs), out.data_ptr(), out.stride(0), out.stride(1))
+        # caches keyed by (batch size, shared input or not): the input / output pointers are patched in per call
+        key = (M, len(xs))
         hit = self.__dict__.setdefault("_chain_cache", {}).get(key)
-        if hit is not None and _CHAIN_ENABLED:
+        if hit is not None and _CHAIN_ENABLED and all(x.data_ptr() % 16 == 0 for x in xs):
+            xl = xs if len(xs) == G else xs * G
+            for g in range(G):
+                hit[1][g] = xl[g].data_ptr()
+                hit[0][g * nl + nl - 1].y, hit[0][g * nl + nl - 1].y_stride = out[g].data_ptr(), out.stride(1)
             L.check(lib.mmb_mlp_chain(hit[0], nl, G, hit[1], st), "mmb_mlp_chain")
             return out
         if G <= 2 and self.__dict__.get("_chain_ok") is not False:       # network-major array: [G][layers]
@@ -495,6 +528,9 @@ class GroupedMLP:
             if len(lcache) >= 8:
                 lcache.clear()
             lcache[key] = arrs
+        else:
+            for g in range(G):
+                arrs[-1][g].y, arrs[-1][g].y_stride = out[g].data_ptr(), out.stride(1)
         for arr in arrs:
             L.check(lib.mmb_mlp_layer_group(arr, G, st), "mmb_mlp_layer_group")
         return out
