@@ -398,9 +398,11 @@ MMB_API int32_t mmb_rollout_statistics(const uint8_t* dones, const float* reward
 /* + Box-Muller (same distribution as the reference's generator, a different stream).               */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
-  int32_t num_rows, act_dim, deterministic, _pad;
+  int32_t num_rows, act_dim, deterministic;
+  int32_t std_group_rows;                  /* 0: one std row for every row; else row r uses std row r / std_group_rows (a team's
+                                            * agent-major means [A * N][act] with per-agent std rows [A][act]: std_group_rows = N) */
   const float* mean; int64_t mean_stride;  /* [rows][act_dim] with row stride */
-  const float* std;                        /* [act_dim] standard deviation actually applied */
+  const float* std;                        /* [act_dim] (or [groups][act_dim]) standard deviation actually applied */
   const float* noise;                      /* [rows][act_dim] standard normal draws, or NULL */
   uint64_t seed, step;
   float* actions;                          /* [rows][act_dim] */

@@ -31,9 +31,10 @@ __global__ void __launch_bounds__(256) gaussian_act_kernel(const __grid_constant
   if (row >= p.num_rows) return;
   const int A = p.act_dim;
   const float* mean = p.mean + (int64_t)row * p.mean_stride;
+  const float* std = p.std + (p.std_group_rows > 0 ? (int64_t)(row / p.std_group_rows) * A : 0);
   float lp_sum = 0.0f;
   for (int j = lane; j < A; j += 32) {
-    const float sd = __ldg(p.std + j);
+    const float sd = __ldg(std + j);
     float z;
     if (p.noise) {
       z = __ldg(p.noise + (int64_t)row * A + j);
@@ -70,7 +71,7 @@ using namespace mmb;
 extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* stream) {
   if (!pp) return MMB_EINVAL;
   mmb_gaussian_act_params p = *pp;
-  if (p.num_rows <= 0 || p.act_dim <= 0 || !p.mean || !p.std || !p.actions || p.mean_stride < p.act_dim) return MMB_EINVAL;
+  if (p.num_rows <= 0 || p.act_dim <= 0 || !p.mean || !p.std || !p.actions || p.mean_stride < p.act_dim || p.std_group_rows < 0) return MMB_EINVAL;
   {
     LaunchScope ls(K_GAUSS_ACT, (cudaStream_t)stream);
     gaussian_act_kernel<<<(p.num_rows * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);

@@ -538,17 +538,20 @@ class GroupedMLP:
     __call__ = forward
 
 
-def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False):
-    """actions = mean + z * std and log-probs in one launch (`mmb_gaussian_act`).  mean [M, A] (row stride allowed), std [A].
+def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False, std_group_rows=0):
+    """actions = mean + z * std and log-probs in one launch (`mmb_gaussian_act`).  mean [M, A] (row stride allowed), std [A] -
+    or [groups, A] with std_group_rows = rows per group (a team's agent-major means with per-agent std rows).
     Returns (actions [M, A], logp): logp [M] summed over the action dims, or [M, A] with per_dim=True."""
     M, A = mean.shape
     if mean.stride(1) != 1:
         mean = mean.contiguous()
     std = std.reshape(-1).float().contiguous()
+    if std.numel() != (A if not std_group_rows else A * ((M + std_group_rows - 1) // std_group_rows)):
+        raise L.MmbError("gaussian_act: std has %d elements for %d rows x %d dims (std_group_rows %d)" % (std.numel(), M, A, std_group_rows))
     actions = torch.empty(M, A, dtype=torch.float32, device=mean.device)
     logp = torch.empty((M, A) if per_dim else (M,), dtype=torch.float32, device=mean.device)
     p = L.GaussianActParams()
-    p.num_rows, p.act_dim, p.deterministic = M, A, int(bool(deterministic))
+    p.num_rows, p.act_dim, p.deterministic, p.std_group_rows = M, A, int(bool(deterministic)), int(std_group_rows)
     p.mean, p.mean_stride, p.std = mean.data_ptr(), mean.stride(0), std.data_ptr()
     if noise is not None:
         noise = noise.float().contiguous()
@@ -720,10 +723,14 @@ class MarlTeamForward:
     def get_actions(self, share_obs, obs, deterministic=False):
         if tuple(t._version for t in self._log_stds) != self._std_ver:
             self._set_std()
-        mean = self.actors(self._agent_major(obs, self.actors.in_dim))
-        actions = mean if deterministic else mean + torch.randn_like(mean) * self.std
-        logp = -((actions - mean) ** 2) / (2 * self.std * self.std) - self.std.log() - 0.9189385332046727
-        return self.critics(self._agent_major(share_obs, self.critics.in_dim)), actions, logp
+        mean = self.actors(self._agent_major(obs, self.actors.in_dim))                     # [A, N, act], contiguous
+        # the whole team's sampling + per-dimension log-probs in ONE launch (a dozen elementwise torch launches before): the
+        # agent-major means as [A * N] rows, agent a's std row for rows a * N .. a * N + N - 1
+        A_, N_, D_ = mean.shape
+        self._calls = getattr(self, "_calls", 0) + 1
+        actions, logp = gaussian_act(mean.view(A_ * N_, D_), self.std, seed=getattr(self, "seed", 0), step=self._calls,
+                                     deterministic=deterministic, per_dim=True, std_group_rows=N_)
+        return self.critics(self._agent_major(share_obs, self.critics.in_dim)), actions.view(A_, N_, D_), logp.view(A_, N_, D_)
 
     @torch.no_grad()
     def get_values(self, share_obs):

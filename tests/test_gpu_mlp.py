@@ -230,6 +230,15 @@ def test_marl_team_forward_equals_per_agent_policies(cuda_device):
         pol = MarlPolicyForward(actor_sds[a], critic_sds[a], device=dev)
         v, act, lp = pol.get_actions(share, obs[:, a].contiguous(), deterministic=True)
         assert torch.equal(values[a], v) and torch.equal(actions[a], act) and torch.allclose(logp[a], lp)
+    # sampled: one launch for the team (per-agent std rows); the log-probs are those of Normal(mean_a, std_a) at the samples
+    _, sampled, slogp = team.get_actions(share, obs)
+    _, mean, _ = team.get_actions(share, obs, deterministic=True)
+    for a in range(A):
+        std_a = torch.sigmoid(actor_sds[a]["act.action_out.log_std"] / 1.0).to(dev) * 0.5
+        ref = torch.distributions.Normal(mean[a], std_a).log_prob(sampled[a])
+        assert torch.allclose(slogp[a], ref, rtol=1e-4, atol=1e-4), a
+        z = (sampled[a] - mean[a]) / std_a
+        assert 0.8 < float(z.std()) < 1.2 and abs(float(z.mean())) < 0.1
 
 
 def test_gaussian_act_kernel(cuda_device):
