@@ -612,17 +612,17 @@ typedef struct {
   /* Deferred LayerNorm (optional; per-layer launches only).  The MARL trunks are [Linear, ELU, LayerNorm] x 3 + head
    * (agents/algorithms/utils/mlp.py:6-65): a LayerNorm in the epilogue needs the whole row in one CTA (epilogue 2: n_tile = N =
    * 512, every tensor-memory column, two passes).  Instead the layer that PRODUCES e = ELU(.) stores it un-normalised and
-   * writes, per row and per 128 columns (one epilogue thread's share of a 256-column tile: n_tile must be 256), the partial
+   * writes, per row and per 64 columns (n_tile must be 256: an epilogue thread's share is then one or two of them), the partial
    * sums (sum e, sum e^2) of the bf16-rounded values, summed in column order (`ln_out_stats`); the layer that CONSUMES it runs on weights with the LayerNorm's gamma folded in (w[n][k] * gamma[k], by
    * the caller) and applies   LN(e) . W^T = rstd * (e . (W gamma)^T - mean * c) + W beta   in its epilogue: `ln_in_stats` = the
    * producer's partials, c[n] = sum_k w[n][k] of the folded weights AS STORED (bf16), and W beta added to `bias` by the
    * caller.  Exactly the LayerNorm of the rounded activations, with any n_tile. */
   const float* ln_in_stats; /* [Mpad][ln_in_parts][2] (sum, sum of squares) partials of the input rows, or NULL */
-  int32_t ln_in_parts;      /* partials per row (the producer's Npad / 128) */
+  int32_t ln_in_parts;      /* partials per row (the producer's Npad / 64) */
   int32_t ln_in_n;          /* features per input row the LayerNorm runs over (the producer's N) */
   float ln_in_eps;
   const float* ln_c;        /* [N], required with ln_in_stats */
-  float* ln_out_stats;      /* [Mpad][Npad / 128][2]; epilogue 1, n_tile 256 and Npad % 256 == 0 only; or NULL */
+  float* ln_out_stats;      /* [Mpad][Npad / 64][2]; epilogue 1, n_tile 256 and Npad % 256 == 0 only; or NULL */
 } mmb_mlp_layer_params;
 MMB_API int32_t mmb_mlp_layer(const mmb_mlp_layer_params* p, void* stream);
 

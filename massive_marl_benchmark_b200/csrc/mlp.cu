@@ -331,10 +331,10 @@ __device__ __forceinline__ void ln_row_moments(const mmb_mlp_layer_params& p, in
   mean = s * inv_n;
   rstd = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.0f) + p.ln_in_eps);      // biased variance, as nn.LayerNorm
 }
-// one partial per 128 columns = one epilogue thread's share of a 256-column tile (the only tile width a producing launch
-// takes), summed in column order: 32 bytes = one sector of partials per 512-wide row for the consumer to read
+// one partial per 64 columns (an epilogue thread's share of a 256-column tile is two or one of them), summed in column order:
+// 64 bytes = two sectors of partials per 512-wide row for the consumer to read, and the same bits however many warps split a tile
 __device__ __forceinline__ void ln_store_partial(const mmb_mlp_layer_params& p, int m, int n, float psum, float psq) {
-  reinterpret_cast<float2*>(p.ln_out_stats)[(int64_t)m * (p.Npad >> 7) + (n >> 7)] = make_float2(psum, psq);
+  reinterpret_cast<float2*>(p.ln_out_stats)[(int64_t)m * (p.Npad >> 6) + (n >> 6)] = make_float2(psum, psq);
 }
 
 // epilogue of columns [cb, ce) of one accumulator row held in a TMEM lane (shared by both kernels; the LayerNorm
@@ -420,8 +420,8 @@ __device__ __forceinline__ void epilogue_row(const mmb_mlp_layer_params& p, uint
           if (n < p.N) y[i] = v[i] + __ldg(p.bias + n);
         }
       }
+      if (p.ln_out_stats && p.epilogue == 1 && ((c0 + 32) & 63) == 0) { ln_store_partial(p, m, n0 + c0, psum, psq); psum = 0.0f; psq = 0.0f; }
     }
-    if (p.ln_out_stats && p.epilogue == 1 && row_ok && cb < ce) ln_store_partial(p, m, n0 + cb, psum, psq);
   }
 }
 
@@ -519,6 +519,7 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
       if (p.ln_out_stats) {   // the sums run over the values as the next layer's GEMM will see them
 #pragma unroll
         for (int i = 0; i < 32; ++i) { x[i] = __bfloat162float(__float2bfloat16_rn(x[i])); psum += x[i]; psq += x[i] * x[i]; }
+        if (((c0 + 32) & 63) == 0) { if (m < p.M) ln_store_partial(p, m, n, psum, psq); psum = 0.0f; psq = 0.0f; }
       }
       stage_out32<false>(tile, row, c0, x, sub_stride);
     } else {
@@ -528,7 +529,6 @@ __device__ __forceinline__ void epilogue_row_staged(const mmb_mlp_layer_params& 
     }
     if ((c0 + 32) % sub_cols == 0 || c0 + 32 >= ce) flush(c0 / sub_cols);
   }
-  if (p.ln_out_stats && p.epilogue == 1 && m < p.M && cb < ce) ln_store_partial(p, m, n0 + cb, psum, psq);
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src_smem, int c0, int c1) {
@@ -763,7 +763,10 @@ struct PersistGroup {
   __device__ __forceinline__ const CUtensorMap* map_w(int a) const { return &g.map_w[a]; }
   __device__ __forceinline__ const CUtensorMap* map_y(int a) const { return &g.map_y[a]; }
 };
-template <class Sel>
+// P = warps per TMEM lane quarter in the epilogue (2: 320 threads; 4: 576 threads, <= 113 registers - four warps on every
+// scheduler hide the ex2 / tensor-memory / barrier latencies two could not: the epilogue, not the k-loop, bounds these launches)
+__device__ __forceinline__ void bar_part(int part) { asm volatile("bar.sync %0, 128;" ::"r"(2 + part) : "memory"); }
+template <class Sel, int P>
 __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const int count) {
   const mmb_mlp_layer_params& p = sel.p(0);           // the geometry (identical for every problem)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -780,7 +783,7 @@ __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const 
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }   // 8 epilogue warps release an accumulator
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * P); }   // every epilogue warp releases an accumulator
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int a = 0; a < count; ++a) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(sel.map_x(a)) : "memory");
@@ -848,15 +851,15 @@ __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const 
     }
   } else {
     // ===== epilogue warps =====
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int sub_cols = (p.epilogue == 0) ? 32 : 64;
-    // the two warps of a lane quarter split the columns (host: the halves are whole sub-tiles); a tile narrower than two
-    // sub-tiles (an 8- or 1-wide head) goes to the first of them
-    const bool split = n_tile >= 2 * sub_cols;
-    const int mid = n_tile / 2;
-    const int cb = (split && half) ? mid : 0, ce = split ? (half ? n_tile : mid) : (half ? 0 : n_tile);
-    uint8_t* buf = out_buf + half * (BM * 128);
+    // the P warps of a lane quarter split the columns into whole sub-tiles; a tile too narrow for that (an 8- or 1-wide head)
+    // goes to the first of them
+    const bool split = (n_tile / P) % sub_cols == 0 && n_tile >= P * sub_cols;
+    const int share = n_tile / P;
+    const int cb = split ? part * share : 0, ce = split ? cb + share : (part ? 0 : n_tile);
+    uint8_t* buf = out_buf + part * (BM * 128);
     int i = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
       const int a = tile / per_problem, rem = tile - a * per_problem;
@@ -871,10 +874,10 @@ __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const 
       if (fast) {
         // everything that does not need the accumulator happens BEFORE it is waited for: this tile's bias / c rows into shared
         // memory (one element per thread), the row's LayerNorm moments from the producing layer's partials (L2 reads)
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the previous tile's readers of bias_s / c_s are done
+        asm volatile("bar.sync 1, %0;" ::"n"(P * 128) : "memory");      // the previous tile's readers of bias_s / c_s are done
         { const int e = tid - 64; if (e < n_tile) { bias_s[e] = __ldg(pa.bias + n0 + e); c_s[e] = corr ? __ldg(pa.ln_c + n0 + e) : 0.0f; } }
         if (corr) ln_row_moments(pa, m, mean, rstd);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(P * 128) : "memory");
       }
       mbar_wait(&acc_full[acc], (uint32_t)(use & 1));
       tc_fence_after();
@@ -911,41 +914,47 @@ __device__ __forceinline__ void mlp_layer_ws_persist_body(const Sel& sel, const 
         };
         tmem_ld32_issue(taddr + cb, ra);
         for (int c0 = cb; c0 < ce; c0 += 64) {
-          tmem_ld_wait(ra);
-          tmem_ld32_issue(taddr + c0 + 32, rb);
-          chunk(ra, c0, pk);
-          tmem_ld_wait(rb);
-          if (c0 + 64 < ce) tmem_ld32_issue(taddr + c0 + 64, ra);
-          chunk(rb, c0 + 32, pk + 16);
+          psum = 0.0f; psq = 0.0f;
+          if constexpr (P <= 2) {
+            tmem_ld_wait(ra);
+            tmem_ld32_issue(taddr + c0 + 32, rb);
+            chunk(ra, c0, pk);
+            tmem_ld_wait(rb);
+            if (c0 + 64 < ce) tmem_ld32_issue(taddr + c0 + 64, ra);
+            chunk(rb, c0 + 32, pk + 16);
+          } else {                  // four warps per scheduler: no second register buffer (113 registers), the other warps cover
+            tmem_ld_wait(ra);
+            chunk(ra, c0, pk);
+            tmem_ld32_issue(taddr + c0 + 32, ra);
+            tmem_ld_wait(ra);
+            chunk(ra, c0 + 32, pk + 16);
+            if (c0 + 64 < ce) tmem_ld32_issue(taddr + c0 + 64, ra);
+          }
+          if (stats) ln_store_partial(pa, m, n0 + c0, psum, psq);
           if (leader) tma_store_wait_read();                // the buffer fed the previous sub-tile's (or tile's) store
-          if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          bar_part(part);
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
           fence_async_smem();
-          if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          bar_part(part);
           if (leader) {
             tma_store_2d(my, buf, n0 + c0, m0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        if (stats) ln_store_partial(pa, m, n0 + cb, psum, psq);
       } else
       // every finished sub-tile goes out through this half's staging buffer: staged -> barrier -> one lane stores and waits
       // until the TMA has read the buffer -> barrier -> the buffer is free for the next sub-tile
       epilogue_row_staged(pa, taddr, row, n0, n_tile, cb, ce, buf - (cb / sub_cols) * 0, [&](int j) {
         fence_async_smem();
-        if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        bar_part(part);
         if (q == 0 && lane == 0) {
           tma_store_2d(my, buf, n0 + j * sub_cols, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           tma_store_wait_read();
         }
-        if (half) asm volatile("bar.sync 3, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        bar_part(part);
       }, 0, m0 + row);
       tc_fence_before();
       __syncwarp();
@@ -961,13 +970,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_kernel(con
                                                                              const __grid_constant__ CUtensorMap map_x,
                                                                              const __grid_constant__ CUtensorMap map_w,
                                                                              const __grid_constant__ CUtensorMap map_y) {
-  mlp_layer_ws_persist_body(PersistOne{p, map_x, map_w, map_y}, 1);
+  mlp_layer_ws_persist_body<PersistOne, 2>(PersistOne{p, map_x, map_w, map_y}, 1);
 }
 // the team's networks as ONE persistent launch per layer: 10 agents x 32 row blocks x 2 column tiles = 640 tiles walked by one
 // CTA per SM, each tile's epilogue under the next tile's k-loop (the non-persistent grouped launch paid prologue, pipeline fill
 // and an exposed epilogue per tile: 4.3 waves of ~10 us for 2.6 us of k-loop each)
-__global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_persist_group_kernel(const __grid_constant__ WsGroupArgs g, const int count) {
-  mlp_layer_ws_persist_body(PersistGroup{g}, count);
+// (four parts - sixteen epilogue warps, 96 registers - were measured: the hidden layers 40.9 -> 46.8 us, layer 0 unchanged at
+// 27 us, the head 18.3 -> 25.5 us: the epilogue's 6.3 us per tile is not a shortage of warps to switch between)
+constexpr int PERSIST_GROUP_PARTS = 2, PERSIST_GROUP_THREADS = 64 + PERSIST_GROUP_PARTS * 128;
+__global__ void __launch_bounds__(PERSIST_GROUP_THREADS, 1) mlp_layer_ws_persist_group_kernel(const __grid_constant__ WsGroupArgs g, const int count) {
+  mlp_layer_ws_persist_body<PersistGroup, PERSIST_GROUP_PARTS>(PersistGroup{g}, count);
 }
 
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_layer_ws_group_kernel(const __grid_constant__ WsGroupArgs g) {
@@ -2052,7 +2064,7 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
       cudaLaunchConfig_t cfg = {};
       const int tiles = count * (q0.Mpad / BM) * (q0.Npad / q0.n_tile), sms = sm_count();
       cfg.gridDim = slot->persist ? dim3(tiles < sms ? tiles : sms) : dim3(q0.Mpad / BM, q0.Npad / q0.n_tile, count);
-      cfg.blockDim = dim3(WS_THREADS);
+      cfg.blockDim = dim3(slot->persist ? PERSIST_GROUP_THREADS : WS_THREADS);
       cfg.dynamicSmemBytes = slot->smem;
       cfg.stream = (cudaStream_t)stream;
       cudaLaunchAttribute attr[1];
@@ -2083,9 +2095,9 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
   for (int a = 0; a < count && persist; ++a)
     persist = (p0.epilogue == 0) ? (((params[a].y_stride & 3) | (reinterpret_cast<uintptr_t>(params[a].y) & 15u)) == 0) : (p0.n_tile % 64 == 0);
   if (persist) {
-    stages = (SMEM_BUDGET + 24 * 1024 - 2 * BM * 128) / stage_bytes;      // ring + two 16 KB staging buffers within 224 KB
+    stages = (SMEM_BUDGET + 24 * 1024 - PERSIST_GROUP_PARTS * BM * 128) / stage_bytes;      // ring + one 16 KB staging buffer per part within 224 KB
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    smem = stages * stage_bytes + 2 * BM * 128;
+    smem = stages * stage_bytes + PERSIST_GROUP_PARTS * BM * 128;
   }
   for (int a = 0; a < count; ++a) {
     mmb_mlp_layer_params p = params[a];
@@ -2136,7 +2148,7 @@ extern "C" int32_t mmb_mlp_layer_group(const mmb_mlp_layer_params* params, int32
     cudaLaunchConfig_t cfg = {};
     const int sms = sm_count();
     cfg.gridDim = dim3(num_tiles < sms ? num_tiles : sms);
-    cfg.blockDim = dim3(WS_THREADS);
+    cfg.blockDim = dim3(PERSIST_GROUP_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];

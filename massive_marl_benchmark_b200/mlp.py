@@ -266,8 +266,8 @@ class FusedMLP:
             for l in self.layers[:-1]:
                 acts.append(torch.zeros(Mpad, _round_up(l.N, 64), dtype=torch.bfloat16, device=self.device))
             self._bufs[M] = (Mpad, acts)
-            # deferred LayerNorm: per producing layer, [Mpad][Npad / 128] (sum, sum of squares) partials
-            self._stats[M] = [torch.zeros(Mpad, l.Npad // 128, 2, dtype=torch.float32, device=self.device) if l.stats_out else None
+            # deferred LayerNorm: per producing layer, [Mpad][Npad / 64] (sum, sum of squares) partials
+            self._stats[M] = [torch.zeros(Mpad, l.Npad // 64, 2, dtype=torch.float32, device=self.device) if l.stats_out else None
                               for l in self.layers]
         return self._bufs[M]
 
@@ -286,7 +286,7 @@ class FusedMLP:
         (148 SMs; wide tiles reuse the A tile more, but a 64-CTA grid leaves half the GPU idle)."""
         if l.n_tile is not None:
             return l.n_tile
-        if l.stats_out:                 # deferred LayerNorm: the producer's partial sums are per 128 columns = half a 256-wide tile
+        if l.stats_out:                 # deferred LayerNorm: the producer's partial sums are per 64 columns of a 256-wide tile
             return 256
         cands = [t for t in (256, 128, 64, 32) if l.Npad % t == 0]
         for t in cands:
@@ -430,7 +430,7 @@ class GroupedMLP:
             for l in a.layers[:-1]:
                 acts.append(torch.zeros(self.G, Mpad, _round_up(l.N, 64), dtype=torch.bfloat16, device=self.device))
             self._bufs[M] = (Mpad, acts)
-            self._stats[M] = [torch.zeros(self.G, Mpad, l.Npad // 128, 2, dtype=torch.float32, device=self.device) if l.stats_out else None
+            self._stats[M] = [torch.zeros(self.G, Mpad, l.Npad // 64, 2, dtype=torch.float32, device=self.device) if l.stats_out else None
                               for l in a.layers]
         return self._bufs[M]
 
