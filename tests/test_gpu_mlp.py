@@ -521,3 +521,44 @@ def test_deferred_layernorm_matches_the_in_epilogue_layernorm(cuda_device):
     y1 = f(x)
     cpu = {k: v.cpu() for k, v in live.items()}
     assert not torch.equal(y0, y1) and _rowmax_err(y1.cpu(), torch_trunk(cpu, "act.action_out.fc_mean", x.cpu())) <= 2e-2
+
+
+def test_dual_network_chain_small_batches_forced(cuda_device):
+    """Below ~2300 rows the side-by-side launch is chosen, so the dual-network kernel's handling of partial row blocks
+    (M = 1, 130, 300: rows beyond M never stored, TMA-clipped) is exercised in a child process with MMB_MLP_DUO=2 (the switch
+    is read once per process): the pair equals the two single-network launches bit for bit there too."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from massive_marl_benchmark_b200 import mlp as mm
+import ctypes as C
+from massive_marl_benchmark_b200 import _lib as L
+dev = torch.device("cuda:0")
+def net(dims):
+    mods = []
+    for i in range(len(dims) - 1):
+        mods.append(torch.nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            mods.append(torch.nn.ELU())
+    return torch.nn.Sequential(*mods).to(dev)
+torch.manual_seed(3)
+for dims in ([388, 1024, 1024, 512, 80], [60, 256, 256, 8]):
+    a, c = net(dims), net(dims)
+    fa, fc = mm.FusedMLP.from_sequential(a, dev), mm.FusedMLP.from_sequential(c, dev)
+    pair = mm.GroupedMLP([fa, fc])
+    for M in (1, 130, 300):
+        x = torch.randn(M, dims[0], device=dev)
+        ya, yc = fa(x).clone(), fc(x).clone()
+        for rep in range(3):
+            out = pair([x, x])
+            assert torch.equal(out[0], ya) and torch.equal(out[1], yc), (dims, M, rep)
+st = (C.c_uint32 * 4)()
+L.lib().mmb_mlp_debug_status(st)
+assert list(st) == [0, 0, 0, 0], [hex(v) for v in st]
+print("forced duo ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, MMB_MLP_DUO="2"))
+    assert r.returncode == 0 and "forced duo ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
