@@ -308,6 +308,23 @@ typedef struct {
 } mmb_rollout_add_params;
 MMB_API int32_t mmb_rollout_add(const mmb_rollout_add_params* p, void* stream);
 
+/* The planes of one team insert in ONE launch: SharedReplayBuffer.insert (agents/algorithms/marl/runner.py:229-275 loops over
+ * the agents and copies share_obs, obs, actions, log-probs, value predictions, rewards and the three mask planes one by one)
+ * is up to MMB_MAX_COPY_SEGS strided copies of fp32 elements,
+ *     dst[i0 * dst_s0 + i1 * dst_s1 + i2] = src[i0 * src_s0 + i1 * src_s1 + i2],   i0 < n0, i1 < n1, i2 < n2
+ * (the (N, A, w) tensors of a step into the agent-major slots [A][T + 1][N][w]: i0 = agent, i1 = env). */
+#define MMB_MAX_COPY_SEGS 12
+typedef struct {
+  float* dst; const float* src;
+  int32_t n0, n1, n2, _pad;
+  int64_t dst_s0, dst_s1, src_s0, src_s1;   /* elements */
+} mmb_copy_seg;
+typedef struct {
+  int32_t count, _pad;
+  mmb_copy_seg seg[MMB_MAX_COPY_SEGS];
+} mmb_copy_group_params;
+MMB_API int32_t mmb_copy_group(const mmb_copy_group_params* p, void* stream);
+
 /* RolloutStorage.compute_returns (storage.py:51-65): reverse-time GAE scan, raw advantages, and the
  * sum / sum-of-squares of the raw advantages (fp64) for the normalisation.  stats[0..2] =
  * {count, sum, sumsq} are ACCUMULATED (caller zeroes them), so env shards on several GPUs can be

@@ -90,6 +90,18 @@ class ResetParams(C.Structure):
         ("c", AntConsts)]
 
 
+MAX_COPY_SEGS = 12
+
+
+class CopySeg(C.Structure):
+    _fields_ = [("dst", c_vp), ("src", c_vp), ("n0", c_i32), ("n1", c_i32), ("n2", c_i32), ("_pad", c_i32),
+                ("dst_s0", c_i64), ("dst_s1", c_i64), ("src_s0", c_i64), ("src_s1", c_i64)]
+
+
+class CopyGroupParams(C.Structure):
+    _fields_ = [("count", c_i32), ("_pad", c_i32), ("seg", CopySeg * MAX_COPY_SEGS)]
+
+
 class RolloutAddParams(C.Structure):
     _fields_ = [("num_envs", c_i32), ("obs_dim", c_i32), ("states_dim", c_i32), ("act_dim", c_i32)] + [
         (n, c_vp) for n in ("observations", "states", "actions", "rewards", "dones", "values", "actions_log_prob",
@@ -204,6 +216,7 @@ SYMBOLS = {
     "mmb_reset_compact": (c_i32, [C.POINTER(ResetParams), c_vp]),
     "mmb_ten_ant_env_step": (c_i32, [C.POINTER(ResetParams), C.POINTER(TenAntParams), c_vp]),
     "mmb_rollout_add": (c_i32, [C.POINTER(RolloutAddParams), c_vp]),
+    "mmb_copy_group": (c_i32, [C.POINTER(CopyGroupParams), c_vp]),
     "mmb_gae_ppo": (c_i32, [C.POINTER(GaePpoParams), c_vp]),
     "mmb_adv_normalize": (c_i32, [c_vp, c_i64, c_vp, c_f, c_i32, c_vp]),
     "mmb_adv_normalize_xchg": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(Xchg), c_f, c_i32, c_vp]),

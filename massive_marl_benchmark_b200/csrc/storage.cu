@@ -630,6 +630,46 @@ extern "C" int32_t mmb_rollout_add(const mmb_rollout_add_params* pp, void* strea
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }
 
+namespace mmb {
+namespace {
+// blockIdx.y = segment; rows (i0, i1) of n2 contiguous elements each, one warp per row chunk: coalesced on both sides
+__global__ void __launch_bounds__(256) copy_group_kernel(const __grid_constant__ mmb_copy_group_params p) {
+  const mmb_copy_seg& g = p.seg[blockIdx.y];
+  const int64_t rows = (int64_t)g.n0 * g.n1;
+  const int lane = threadIdx.x & 31;
+  const bool vec = (g.n2 & 3) == 0 && ((g.dst_s0 | g.dst_s1 | g.src_s0 | g.src_s1) & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(g.dst) | reinterpret_cast<uintptr_t>(g.src)) & 15u) == 0;
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t i0 = r / g.n1, i1 = r - i0 * g.n1;
+    float* d = g.dst + i0 * g.dst_s0 + i1 * g.dst_s1;
+    const float* s = g.src + i0 * g.src_s0 + i1 * g.src_s1;
+    if (vec) {
+      for (int j = lane * 4; j < g.n2; j += 128) *reinterpret_cast<float4*>(d + j) = __ldg(reinterpret_cast<const float4*>(s + j));
+    } else {
+      for (int j = lane; j < g.n2; j += 32) d[j] = __ldg(s + j);
+    }
+  }
+}
+}  // namespace
+}  // namespace mmb
+
+extern "C" int32_t mmb_copy_group(const mmb_copy_group_params* pp, void* stream) {
+  if (!pp || pp->count <= 0 || pp->count > MMB_MAX_COPY_SEGS) return MMB_EINVAL;
+  int64_t max_rows = 1;
+  for (int i = 0; i < pp->count; ++i) {
+    const mmb_copy_seg& g = pp->seg[i];
+    if (!g.dst || !g.src || g.n0 <= 0 || g.n1 <= 0 || g.n2 <= 0) return MMB_EINVAL;
+    if ((int64_t)g.n0 * g.n1 > max_rows) max_rows = (int64_t)g.n0 * g.n1;
+  }
+  int64_t bx = (max_rows + 7) / 8;
+  if (bx > mmb::sm_count() * 8) bx = mmb::sm_count() * 8;
+  {
+    mmb::LaunchScope ls(mmb::K_ROLLOUT_ADD, (cudaStream_t)stream);
+    mmb::copy_group_kernel<<<dim3((unsigned)bx, (unsigned)pp->count), 256, 0, (cudaStream_t)stream>>>(*pp);
+  }
+  return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
+}
+
 extern "C" int32_t mmb_gae_marl(const mmb_gae_marl_params* pp, void* stream) {
   if (!pp) return MMB_EINVAL;
   mmb_gae_marl_params p = *pp;

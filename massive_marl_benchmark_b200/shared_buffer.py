@@ -93,15 +93,43 @@ class SharedReplayBuffer:
         """share_obs (N, S) once; everything else (N, A, .) as `MultiVecTaskPython.step` / the policies return it
         (runner.py:229-275 loops over agents and inserts share_obs[:, agent_id] each time)."""
         s = self.step
-        self.share_obs[s + 1].copy_(share_obs)
         pairs = [(self.obs, obs, s + 1), (self.actions, actions, s), (self.action_log_probs, action_log_probs, s),
                  (self.value_preds, value_preds, s), (self.rewards, rewards, s), (self.masks, masks, s + 1)]
         if bad_masks is not None:
             pairs.append((self.bad_masks, bad_masks, s + 1))
         if active_masks is not None:
             pairs.append((self.active_masks, active_masks, s + 1))
-        for dst, src, slot in pairs:
-            dst[:, slot].copy_(src.transpose(0, 1))        # (N, A, .) -> agent-major slot, one strided copy for all agents
+        # (N, A, .) -> agent-major slots [A][slot][N][.], share_obs once: ALL planes in one launch (`mmb_copy_group`) when they
+        # are fp32 CUDA tensors with contiguous rows - nine strided torch copies otherwise.  No views are built on the way (nine
+        # slicing / transpose calls cost more host time than the launch): destination addresses from the planes' strides.
+        p = self.__dict__.get("_copy_params")
+        if p is None:
+            p = self._copy_params = L.CopyGroupParams()
+        N, A = self.n_rollout_threads, self.num_agents
+        ok = len(pairs) + 1 <= L.MAX_COPY_SEGS and share_obs.dtype is torch.float32 and share_obs.is_cuda and share_obs.dim() == 2 \
+            and share_obs.stride(1) == 1 and self.share_obs.dtype is torch.float32
+        if ok:
+            g = p.seg[0]
+            g.dst, g.src = self.share_obs.data_ptr() + 4 * (s + 1) * self.share_obs.stride(0), share_obs.data_ptr()
+            g.n0, g.n1, g.n2 = 1, N, share_obs.shape[1]
+            g.dst_s0, g.dst_s1, g.src_s0, g.src_s1 = 0, self.share_obs.stride(1), 0, share_obs.stride(0)
+            for k, (dst, src, slot) in enumerate(pairs):
+                w = dst.shape[3]
+                if (src.dtype is not torch.float32 or dst.dtype is not torch.float32 or not src.is_cuda or src.dim() != 3 or
+                        src.shape[0] != N or src.shape[1] != A or src.shape[2] != w or (w > 1 and (src.stride(2) != 1 or dst.stride(3) != 1))):
+                    ok = False
+                    break
+                g = p.seg[k + 1]
+                g.dst, g.src = dst.data_ptr() + 4 * slot * dst.stride(1), src.data_ptr()
+                g.n0, g.n1, g.n2 = A, N, w
+                g.dst_s0, g.dst_s1, g.src_s0, g.src_s1 = dst.stride(0), dst.stride(2), src.stride(1), src.stride(0)
+        if ok:
+            p.count = len(pairs) + 1
+            L.check(L.lib().mmb_copy_group(p, L.stream_ptr()), "mmb_copy_group")
+        else:
+            self.share_obs[s + 1].copy_(share_obs)
+            for dst, src, slot in pairs:
+                dst[:, slot].copy_(src.transpose(0, 1))
         self.step = (self.step + 1) % self.episode_length
 
     def after_update(self):
