@@ -50,7 +50,10 @@ def test_ctypes_structs_match_c_layout(built_lib):
               ("mmb_gae_ppo_params", L.GaePpoParams, "stats"), ("mmb_gae_marl_params", L.GaeMarlParams, "stats"),
               ("mmb_xchg", L.Xchg, "mailbox"), ("mmb_episode_params", L.EpisodeParams, "state"), ("mmb_gaussian_act_params", L.GaussianActParams, "logp_per_dim"),
               ("mmb_ppo_loss_params", L.PpoLossParams, "ticket"), ("mmb_mappo_loss_params", L.MappoLossParams, "sums"),
-              ("mmb_mlp_layer_params", L.MlpLayerParams, "overlap_prev"),
+              ("mmb_mappo_loss_params", L.MappoLossParams, "ticket"), ("mmb_gaussian_act_params", L.GaussianActParams, "std_group_rows"),
+              ("mmb_mlp_layer_params", L.MlpLayerParams, "overlap_prev"), ("mmb_mlp_layer_params", L.MlpLayerParams, "ln_in_eps"),
+              ("mmb_mlp_layer_params", L.MlpLayerParams, "ln_out_stats"), ("mmb_reset_params", L.ResetParams, "step_counter"),
+              ("mmb_copy_seg", L.CopySeg, "src_s1"), ("mmb_copy_group_params", L.CopyGroupParams, "seg"),
               ("mmb_gather_params", L.GatherParams, "group"), ("mmb_adam_params", L.AdamParams, "one_minus_beta1")]
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "mmb.h"\nint main(void){\n'
     for cname, _, field in probes:
