@@ -617,9 +617,13 @@ class PPOActorCriticForward:
     def act(self, observations, states=None, noise=None):
         """`noise` [N, act]: standard normal draws to use (parity tests); default: in-kernel Philox keyed by (seed, call #)."""
         mean, value = self._mean_value(observations, states)
-        # MultivariateNormal with scale_tril = diag(exp(log_std)^2): sample + log_prob (sum over dims) in one launch
+        # MultivariateNormal with scale_tril = diag(exp(log_std)^2): sample + log_prob (sum over dims) in one launch; the scale
+        # is recomputed only when log_std has changed (its version counter: an optimiser step bumps it)
         self._calls = getattr(self, "_calls", 0) + 1
-        actions, log_prob = gaussian_act(mean, self.log_std.exp() * self.log_std.exp(), seed=getattr(self, "seed", 0),
+        if self.__dict__.get("_scale_ver") != self.log_std._version:
+            self._scale = (self.log_std.exp() * self.log_std.exp()).float().contiguous()
+            self._scale_ver = self.log_std._version
+        actions, log_prob = gaussian_act(mean, self._scale, seed=getattr(self, "seed", 0),
                                          step=self._calls, noise=noise)
         return actions, log_prob, value, mean, self.log_std.repeat(mean.shape[0], 1)
 
