@@ -173,3 +173,41 @@ def test_ppo_checkpoint_format(tmp_path):
     bad = dict(sd); bad["critic.6.weight"] = torch.zeros(2, 512); bad["critic.6.bias"] = torch.zeros(2)
     with pytest.raises(ValueError):
         ck.ppo_modules_from_state_dict(bad)
+
+
+def test_deferred_layernorm_fold_identity_on_cpu(built_lib):
+    """Host side of the deferred LayerNorm (include/mmb.h `ln_in_stats`): with W' = bf16(W * gamma), c = row sums of W' and
+    bias' = b + W beta as `_Layer.refresh` builds them, rstd * (e . W'^T - mean * c) + bias' equals LayerNorm(e) . W^T + b up
+    to the bf16 rounding of W' - and exactly when W' is taken unrounded.  Re-folds when a source parameter changes."""
+    import torch
+    from massive_marl_benchmark_b200 import mlp as mm
+    gen = torch.Generator().manual_seed(0)
+    sd = {"base.feature_norm.weight": torch.ones(46), "base.feature_norm.bias": torch.zeros(46)}
+    for n, k in (("base.mlp.fc1", 46), ("base.mlp.fc2.0", 512), ("base.mlp.fc2.1", 512)):
+        sd[n + ".0.weight"] = torch.randn(512, k, generator=gen) / k ** 0.5
+        sd[n + ".0.bias"] = 0.1 * torch.randn(512, generator=gen)
+        sd[n + ".2.weight"] = 1.0 + 0.2 * torch.randn(512, generator=gen)
+        sd[n + ".2.bias"] = 0.1 * torch.randn(512, generator=gen)
+    sd["act.action_out.fc_mean.weight"] = 0.05 * torch.randn(8, 512, generator=gen)
+    sd["act.action_out.fc_mean.bias"] = 0.1 * torch.randn(8, generator=gen)
+    f = mm.FusedMLP.from_marl_state_dict(sd, "act.action_out.fc_mean", device="cpu")
+    assert [l.fold is not None for l in f.layers] == [False, True, True, True]
+    assert [l.stats_out for l in f.layers] == [True, True, True, False] and all(l.epilogue == (1 if l.act else 0) for l in f.layers)
+    e = torch.nn.functional.elu(torch.randn(64, 512, generator=gen))
+    for l, ln, lin in ((f.layers[1], "base.mlp.fc1.2", "base.mlp.fc2.0.0"), (f.layers[3], "base.mlp.fc2.1.2", "act.action_out.fc_mean")):
+        W, b, gamma, beta = sd[lin + ".weight"], sd[lin + ".bias"], sd[ln + ".weight"], sd[ln + ".bias"]
+        want = torch.nn.functional.layer_norm(e, (512,), gamma, beta, 1e-5) @ W.T + b
+        mean, rstd = e.mean(1, keepdim=True), torch.rsqrt(e.var(1, unbiased=False, keepdim=True) + 1e-5)
+        wf = l.w[:l.n_src, :l.K].float()
+        got = rstd * (e @ wf.T - mean * l.c[:l.n_src][None, :]) + l.bias[:l.n_src][None, :]
+        assert torch.allclose(got, want, rtol=0, atol=2e-2 * float(want.abs().max()))           # bf16 weights
+        exact = rstd * (e @ (W * gamma[None, :]).T - mean * (W * gamma[None, :]).sum(1)[None, :]) + (b + W @ beta)[None, :]
+        assert torch.allclose(exact, want, rtol=1e-4, atol=1e-4)
+        assert torch.allclose(l.c[:l.n_src], wf.sum(1)) and torch.allclose(l.bias[:l.n_src], b + W @ beta, atol=1e-6)
+    # a LayerNorm parameter changed in place -> stale -> the NEXT layer is re-folded
+    assert not f.stale()
+    old_c = f.layers[1].c.clone()
+    sd["base.mlp.fc1.2.weight"].mul_(2.0)
+    assert f.stale()
+    f.refresh()
+    assert not f.stale() and torch.allclose(f.layers[1].c, 2.0 * old_c, rtol=2e-2, atol=1e-3)
