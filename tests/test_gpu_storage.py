@@ -329,3 +329,34 @@ def test_episode_tracker_marl_runner_variant(cuda_device):
         assert int(tr.finished) == len(done_episodes_rewards)
         rr, _ = tr.deques()
         assert rr == [float(x) for x in done_episodes_rewards[-100:]]
+
+
+def test_shared_insert_with_strided_sources(cuda_device):
+    """`SharedReplayBuffer.insert` through `mmb_copy_group` with the sources as the rollout actually hands them over: the
+    env's reward / done planes as stride-0 expand views, the team forward's agent-major outputs as transposed views, a
+    column slice as share_obs - against plain torch copies of the same tensors."""
+    from massive_marl_benchmark_b200 import spaces
+    from massive_marl_benchmark_b200.shared_buffer import SharedReplayBuffer
+    dev = cuda_device
+    T, N, A, O, S, ACT = 3, 70, 5, 46, 388, 8
+    cfg = dict(episode_length=T, n_rollout_threads=N, hidden_size=16, recurrent_N=1, gamma=0.96, gae_lambda=0.95,
+               use_gae=True, use_popart=False, use_valuenorm=False, use_proper_time_limits=False)
+    ob = spaces.Box(low=-np.inf, high=np.inf, shape=(O,)); sh = spaces.Box(low=-np.inf, high=np.inf, shape=(S,))
+    ac = spaces.Box(low=-np.ones(ACT), high=np.ones(ACT))
+    buf = SharedReplayBuffer(cfg, A, ob, sh, ac, dev)
+    gen = torch.Generator().manual_seed(5)
+    for t in range(T):
+        state_all = torch.randn(N, S, generator=gen).to(dev).unsqueeze(1).expand(N, A, S)        # MultiVecTaskPython's state_all
+        obs = torch.randn(N, A, O, generator=gen).to(dev)
+        act_am = torch.randn(A, N, ACT, generator=gen).to(dev); logp_am = torch.randn(A, N, ACT, generator=gen).to(dev)
+        val_am = torch.randn(A, N, 1, generator=gen).to(dev)
+        rew = torch.randn(N, generator=gen).to(dev).view(N, 1, 1).expand(N, A, 1)
+        masks = (torch.rand(N, generator=gen) > 0.2).float().to(dev).view(N, 1, 1).expand(N, A, 1)
+        active = torch.ones(N, A, 1, device=dev)
+        s = buf.step
+        buf.insert(state_all[:, 0], obs, act_am.transpose(0, 1), logp_am.transpose(0, 1), val_am.transpose(0, 1), rew, masks, None, active)
+        assert torch.equal(buf.share_obs[s + 1], state_all[:, 0]) and torch.equal(buf.obs[:, s + 1], obs.transpose(0, 1))
+        assert torch.equal(buf.actions[:, s], act_am) and torch.equal(buf.action_log_probs[:, s], logp_am)
+        assert torch.equal(buf.value_preds[:, s], val_am) and torch.equal(buf.rewards[:, s], rew.transpose(0, 1))
+        assert torch.equal(buf.masks[:, s + 1], masks.transpose(0, 1)) and torch.equal(buf.active_masks[:, s + 1], active.transpose(0, 1))
+    assert buf.step == 0
