@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMB_ABI_VERSION 3
+#define MMB_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MMB_API __attribute__((visibility("default")))
@@ -425,6 +425,8 @@ typedef struct {
   float* actions;                          /* [rows][act_dim] */
   float* logp_sum;                         /* [rows] sum over dims (PPO), or NULL */
   float* logp_per_dim;                     /* [rows][act_dim] (MARL), or NULL */
+  const float* sigma_src;                  /* [act_dim] (or [groups][act_dim]) row to broadcast, or NULL: PPO's act() also returns */
+  float* sigma_out;                        /* [rows][act_dim] = sigma_src per row (`log_std.repeat(N, 1)`, module.py:87), or NULL */
 } mmb_gaussian_act_params;
 MMB_API int32_t mmb_gaussian_act(const mmb_gaussian_act_params* p, void* stream);
 

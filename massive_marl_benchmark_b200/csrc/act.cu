@@ -9,6 +9,7 @@
 // Philox4x32-10 keyed by (seed, step) with the element index as counter + Box-Muller: same distribution as the reference's
 // generator, a different stream (exact RNG parity with torch's global generator is not reproducible; the deterministic
 // path, `noise` supplied by the caller, is what the parity tests use).
+#include <stdlib.h>
 #include "../../include/mmb.h"
 #include "mmb_common.cuh"
 #include "mmb_math.cuh"
@@ -30,8 +31,15 @@ __global__ void __launch_bounds__(256) gaussian_act_kernel(const __grid_constant
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= p.num_rows) return;
   const int A = p.act_dim;
+  const int64_t grp = p.std_group_rows > 0 ? (int64_t)(row / p.std_group_rows) * A : 0;
+  const float* std = p.std + grp;
+  // Launched as a programmatic dependent of the kernel in front of it (the MLP that writes the means): nothing is read or
+  // WRITTEN before the wait - the outputs are fresh allocations, and the caching allocator may hand out a block the
+  // kernel in front still reads.
+  griddep_wait();
+  if (p.sigma_out)
+    for (int j = lane; j < A; j += 32) p.sigma_out[(int64_t)row * A + j] = __ldg(p.sigma_src + grp + j);
   const float* mean = p.mean + (int64_t)row * p.mean_stride;
-  const float* std = p.std + (p.std_group_rows > 0 ? (int64_t)(row / p.std_group_rows) * A : 0);
   float lp_sum = 0.0f;
   for (int j = lane; j < A; j += 32) {
     const float sd = __ldg(std + j);
@@ -72,9 +80,22 @@ extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* str
   if (!pp) return MMB_EINVAL;
   mmb_gaussian_act_params p = *pp;
   if (p.num_rows <= 0 || p.act_dim <= 0 || !p.mean || !p.std || !p.actions || p.mean_stride < p.act_dim || p.std_group_rows < 0) return MMB_EINVAL;
+  if ((p.sigma_out != nullptr) != (p.sigma_src != nullptr)) return MMB_EINVAL;
   {
     LaunchScope ls(K_GAUSS_ACT, (cudaStream_t)stream);
-    gaussian_act_kernel<<<(p.num_rows * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    // programmatic dependent launch: the grid is scheduled while the kernel in front (the MLP that writes the means) drains;
+    // everything that reads its output sits behind griddepcontrol.wait
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(((int64_t)p.num_rows * 32 + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = (cudaStream_t)stream;
+    static const bool pdl = [] { const char* e = getenv("MMB_ACT_PDL"); return !(e && e[0] == '0'); }();   // A/B switch
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, gaussian_act_kernel, p) != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

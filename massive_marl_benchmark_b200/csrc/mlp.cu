@@ -1083,6 +1083,9 @@ __device__ __forceinline__ void mlp_chain_body(const ChainArgs& g) {
   const int m0 = (blockIdx.x / CHAIN_CLUSTER) * BM;
   const ChainLayer* Ls = g.l[blockIdx.z];
   const int L = g.num_layers;
+  // a programmatically launched successor (mmb_gaussian_act: everything behind its griddepcontrol.wait) may take the SM
+  // slots this kernel leaves free and be resident when the last tile retires
+  griddep_launch_dependents();
   uint8_t* out_buf = smem + S * CHAIN_STAGE_BYTES;
   // Input cast folded into layer 0: the eight epilogue warps - idle until the first accumulator is complete - convert the
   // fp32 rows of this row block into the bf16 SWIZZLE_128B operand tiles themselves (one arrival per warp on a_bar), instead
@@ -1493,6 +1496,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) mlp_chain_duo_kernel(const __g
   uint8_t* out_buf = smem + CHAIN_STAGES * CHAIN_STAGE_BYTES;
   const float* x32 = g.x32[0];
   volatile int* ab = &s_abort;
+  griddep_launch_dependents();   // see mlp_chain_body
 
   if (tid == 0) {
     s_abort = 0;

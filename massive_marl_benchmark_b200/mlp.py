@@ -538,10 +538,12 @@ class GroupedMLP:
     __call__ = forward
 
 
-def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False, std_group_rows=0):
+def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False, std_group_rows=0, sigma_src=None):
     """actions = mean + z * std and log-probs in one launch (`mmb_gaussian_act`).  mean [M, A] (row stride allowed), std [A] -
     or [groups, A] with std_group_rows = rows per group (a team's agent-major means with per-agent std rows).
-    Returns (actions [M, A], logp): logp [M] summed over the action dims, or [M, A] with per_dim=True."""
+    Returns (actions [M, A], logp): logp [M] summed over the action dims, or [M, A] with per_dim=True.  With `sigma_src`
+    (same shape as std, fp32) a third output [M, A] holds that row broadcast over the rows - the `log_std.repeat(N, 1)` PPO's
+    `act()` returns (module.py:87) - written by the same launch."""
     M, A = mean.shape
     if mean.stride(1) != 1:
         mean = mean.contiguous()
@@ -562,8 +564,17 @@ def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per
         p.logp_per_dim = logp.data_ptr()
     else:
         p.logp_sum = logp.data_ptr()
+    sigma = None
+    if sigma_src is not None:
+        sigma_src = sigma_src.detach().reshape(-1)
+        if sigma_src.dtype != torch.float32 or not sigma_src.is_contiguous() or sigma_src.device != mean.device:
+            sigma_src = sigma_src.to(mean.device, torch.float32).contiguous()
+        if sigma_src.numel() != std.numel():
+            raise L.MmbError("gaussian_act: sigma_src has %d elements, std %d" % (sigma_src.numel(), std.numel()))
+        sigma = torch.empty(M, A, dtype=torch.float32, device=mean.device)
+        p.sigma_src, p.sigma_out = sigma_src.data_ptr(), sigma.data_ptr()
     L.check(L.lib().mmb_gaussian_act(p, L.stream_ptr()), "mmb_gaussian_act")
-    return actions, logp
+    return (actions, logp) if sigma is None else (actions, logp, sigma)
 
 
 class PPOActorCriticForward:
@@ -623,9 +634,9 @@ class PPOActorCriticForward:
         if self.__dict__.get("_scale_ver") != self.log_std._version:
             self._scale = (self.log_std.exp() * self.log_std.exp()).float().contiguous()
             self._scale_ver = self.log_std._version
-        actions, log_prob = gaussian_act(mean, self._scale, seed=getattr(self, "seed", 0),
-                                         step=self._calls, noise=noise)
-        return actions, log_prob, value, mean, self.log_std.repeat(mean.shape[0], 1)
+        actions, log_prob, sigma = gaussian_act(mean, self._scale, seed=getattr(self, "seed", 0),
+                                                step=self._calls, noise=noise, sigma_src=self.log_std)
+        return actions, log_prob, value, mean, sigma      # sigma = log_std.repeat(N, 1), written by the same launch
 
     @torch.no_grad()
     def act_inference(self, observations):

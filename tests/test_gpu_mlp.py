@@ -150,6 +150,7 @@ def test_ppo_act_interface_matches_reference_semantics(cuda_device):
     torch.manual_seed(1)
     actions, logp, value, mean, log_std = fwd.act(obs, None)
     assert actions.shape == (300, 8) and logp.shape == (300,) and value.shape == (300, 1) and log_std.shape == (300, 8)
+    assert torch.equal(log_std, ac.log_std.detach().repeat(300, 1))
     dist = MultivariateNormal(mean, scale_tril=torch.diag(ac.log_std.exp() * ac.log_std.exp()))
     assert torch.allclose(logp, dist.log_prob(actions), rtol=1e-4, atol=1e-4)
     emp_std = (actions - mean).std(dim=0)
@@ -261,6 +262,14 @@ def test_gaussian_act_kernel(cuda_device):
     assert torch.equal(act2, act) and torch.allclose(lp2, Normal(mean, std).log_prob(act), rtol=1e-4, atol=1e-4)
     det, _ = gaussian_act(mean, std, deterministic=True)
     assert torch.equal(det, mean)
+    # the broadcast output of PPO's act() (`log_std.repeat(N, 1)`, module.py:87) from the same launch, also per std group
+    log_std = torch.randn(A, generator=gen).to(dev)
+    act3, lp3, sig = gaussian_act(mean, std, noise=z, sigma_src=log_std)
+    assert torch.equal(act3, act) and torch.equal(lp3, lp) and torch.equal(sig, log_std.repeat(M, 1))
+    std_g = (0.3 + torch.rand(5, A, generator=gen)).to(dev); src_g = torch.randn(5, A, generator=gen).to(dev)
+    act4, _, sig_g = gaussian_act(mean, std_g, noise=z, std_group_rows=1000, sigma_src=src_g)
+    assert torch.equal(sig_g, src_g.repeat_interleave(1000, dim=0))
+    assert torch.allclose(act4, mean + z * std_g.repeat_interleave(1000, dim=0), rtol=1e-6, atol=1e-6)
     a1, _ = gaussian_act(mean, std, seed=7, step=1)
     a1b, _ = gaussian_act(mean, std, seed=7, step=1)
     a2, _ = gaussian_act(mean, std, seed=7, step=2)
