@@ -427,6 +427,9 @@ typedef struct {
   float* logp_per_dim;                     /* [rows][act_dim] (MARL), or NULL */
   const float* sigma_src;                  /* [act_dim] (or [groups][act_dim]) row to broadcast, or NULL: PPO's act() also returns */
   float* sigma_out;                        /* [rows][act_dim] = sigma_src per row (`log_std.repeat(N, 1)`, module.py:87), or NULL */
+  uint64_t* step_counter;                  /* NULL, or two device words {step, ticket (0)}: the launch takes `step` from word 0 instead of
+                                            * the field above and its last block advances it by one - a CUDA-graph replay of act() then
+                                            * draws fresh numbers, in the same sequence as a host counter started at the same value */
 } mmb_gaussian_act_params;
 MMB_API int32_t mmb_gaussian_act(const mmb_gaussian_act_params* p, void* stream);
 

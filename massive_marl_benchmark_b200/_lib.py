@@ -137,7 +137,7 @@ class EpisodeParams(C.Structure):
 class GaussianActParams(C.Structure):
     _fields_ = [("num_rows", c_i32), ("act_dim", c_i32), ("deterministic", c_i32), ("std_group_rows", c_i32),
                 ("mean", c_vp), ("mean_stride", c_i64), ("std", c_vp), ("noise", c_vp), ("seed", c_u64), ("step", c_u64),
-                ("actions", c_vp), ("logp_sum", c_vp), ("logp_per_dim", c_vp), ("sigma_src", c_vp), ("sigma_out", c_vp)]
+                ("actions", c_vp), ("logp_sum", c_vp), ("logp_per_dim", c_vp), ("sigma_src", c_vp), ("sigma_out", c_vp), ("step_counter", c_vp)]
 
 
 class PpoLossParams(C.Structure):

@@ -29,14 +29,15 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
 // one warp per row: lanes stride over the action dimensions; per-row log-prob sum by shuffle
 __global__ void __launch_bounds__(256) gaussian_act_kernel(const __grid_constant__ mmb_gaussian_act_params p) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= p.num_rows) return;
-  const int A = p.act_dim;
+  const int A = p.num_rows > row ? p.act_dim : 0;   // rows past the end do nothing but stay for the block's barrier below
   const int64_t grp = p.std_group_rows > 0 ? (int64_t)(row / p.std_group_rows) * A : 0;
   const float* std = p.std + grp;
   // Launched as a programmatic dependent of the kernel in front of it (the MLP that writes the means): nothing is read or
   // WRITTEN before the wait - the outputs are fresh allocations, and the caching allocator may hand out a block the
   // kernel in front still reads.
   griddep_wait();
+  // device-resident Philox counter (CUDA-graph replays): every block reads it here; the last block to retire advances it
+  const uint64_t step = p.step_counter ? __ldcg(reinterpret_cast<const unsigned long long*>(p.step_counter)) : p.step;
   if (p.sigma_out)
     for (int j = lane; j < A; j += 32) p.sigma_out[(int64_t)row * A + j] = __ldg(p.sigma_src + grp + j);
   const float* mean = p.mean + (int64_t)row * p.mean_stride;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) gaussian_act_kernel(const __grid_constant
       z = 0.0f;
     } else {
       const uint64_t idx = (uint64_t)row * (uint64_t)A + (uint64_t)j;
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)(idx >> 1), (uint32_t)(idx >> 33), (uint32_t)p.step, (uint32_t)(p.step >> 32)),
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)(idx >> 1), (uint32_t)(idx >> 33), (uint32_t)step, (uint32_t)(step >> 32)),
                                     make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
       const float2 n = box_muller(r.x, r.y);
       z = (idx & 1) ? n.y : n.x;
@@ -67,7 +68,18 @@ __global__ void __launch_bounds__(256) gaussian_act_kernel(const __grid_constant
   if (p.logp_sum) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
-    if (lane == 0) p.logp_sum[row] = lp_sum;
+    if (lane == 0 && A > 0) p.logp_sum[row] = lp_sum;
+  }
+  if (p.step_counter) {
+    __syncthreads();   // every warp of the block has read the counter
+    if (threadIdx.x == 0) {
+      unsigned long long* ctr = reinterpret_cast<unsigned long long*>(p.step_counter);
+      __threadfence();
+      if (atomicAdd(ctr + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {   // all blocks have read: advance, re-arm the ticket
+        ctr[1] = 0ull;
+        ctr[0] = step + 1ull;
+      }
+    }
   }
 }
 
@@ -83,13 +95,15 @@ extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* str
   if ((p.sigma_out != nullptr) != (p.sigma_src != nullptr)) return MMB_EINVAL;
   {
     LaunchScope ls(K_GAUSS_ACT, (cudaStream_t)stream);
-    // programmatic dependent launch: the grid is scheduled while the kernel in front (the MLP that writes the means) drains;
-    // everything that reads its output sits behind griddepcontrol.wait
+    // optionally a programmatic dependent launch: the grid is scheduled while the kernel in front (the MLP that writes the
+    // means) drains; everything that reads its output sits behind griddepcontrol.wait
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(((int64_t)p.num_rows * 32 + 255) / 256));
     cfg.blockDim = dim3(256);
     cfg.stream = (cudaStream_t)stream;
-    static const bool pdl = [] { const char* e = getenv("MMB_ACT_PDL"); return !(e && e[0] == '0'); }();   // A/B switch
+    // MMB_ACT_PDL=1: measured equal within noise to the ordinary launch behind the dual-network chain (act() graph-replayed
+    // 52.0 vs 51.1 us at M = 4096), so it is off by default
+    static const bool pdl = [] { const char* e = getenv("MMB_ACT_PDL"); return e && e[0] == '1'; }();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

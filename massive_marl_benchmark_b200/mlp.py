@@ -538,12 +538,14 @@ class GroupedMLP:
     __call__ = forward
 
 
-def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False, std_group_rows=0, sigma_src=None):
+def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False, std_group_rows=0, sigma_src=None,
+                 step_counter=None):
     """actions = mean + z * std and log-probs in one launch (`mmb_gaussian_act`).  mean [M, A] (row stride allowed), std [A] -
     or [groups, A] with std_group_rows = rows per group (a team's agent-major means with per-agent std rows).
     Returns (actions [M, A], logp): logp [M] summed over the action dims, or [M, A] with per_dim=True.  With `sigma_src`
     (same shape as std, fp32) a third output [M, A] holds that row broadcast over the rows - the `log_std.repeat(N, 1)` PPO's
-    `act()` returns (module.py:87) - written by the same launch."""
+    `act()` returns (module.py:87) - written by the same launch.  `step_counter`: int64 device tensor {step, 0}; the launch
+    takes the Philox step from it and advances it (a captured CUDA graph then draws fresh numbers on every replay)."""
     M, A = mean.shape
     if mean.stride(1) != 1:
         mean = mean.contiguous()
@@ -559,6 +561,10 @@ def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per
         noise = noise.float().contiguous()
         p.noise = noise.data_ptr()
     p.seed, p.step = int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFFFFFFFFFF
+    if step_counter is not None:
+        if step_counter.dtype != torch.int64 or step_counter.numel() < 2 or step_counter.device != mean.device or not step_counter.is_contiguous():
+            raise L.MmbError("gaussian_act: step_counter must be a contiguous int64 tensor {step, ticket} on the means' device")
+        p.step_counter = step_counter.data_ptr()
     p.actions = actions.data_ptr()
     if per_dim:
         p.logp_per_dim = logp.data_ptr()
@@ -628,15 +634,39 @@ class PPOActorCriticForward:
     def act(self, observations, states=None, noise=None):
         """`noise` [N, act]: standard normal draws to use (parity tests); default: in-kernel Philox keyed by (seed, call #)."""
         mean, value = self._mean_value(observations, states)
-        # MultivariateNormal with scale_tril = diag(exp(log_std)^2): sample + log_prob (sum over dims) in one launch; the scale
-        # is recomputed only when log_std has changed (its version counter: an optimiser step bumps it)
+        # MultivariateNormal with scale_tril = diag(exp(log_std)^2): sample + log_prob (sum over dims) in one launch
         self._calls = getattr(self, "_calls", 0) + 1
-        if self.__dict__.get("_scale_ver") != self.log_std._version:
-            self._scale = (self.log_std.exp() * self.log_std.exp()).float().contiguous()
-            self._scale_ver = self.log_std._version
-        actions, log_prob, sigma = gaussian_act(mean, self._scale, seed=getattr(self, "seed", 0),
-                                                step=self._calls, noise=noise, sigma_src=self.log_std)
+        self._refresh_scale()
+        actions, log_prob, sigma = gaussian_act(mean, self._scale, seed=getattr(self, "seed", 0), step=self._calls, noise=noise,
+                                                sigma_src=self.log_std, step_counter=self.__dict__.get("_step_counter_dev"))
         return actions, log_prob, value, mean, sigma      # sigma = log_std.repeat(N, 1), written by the same launch
+
+    def _refresh_scale(self):
+        """exp(log_std)^2, recomputed IN PLACE only when log_std has changed (its version counter: an optimiser step bumps
+        it), so a CUDA graph that captured `act()` keeps reading the right tensor."""
+        if self.__dict__.get("_scale_ver") != self.log_std._version:
+            e = self.log_std.detach().float().exp()
+            if self.__dict__.get("_scale") is None:
+                self._scale = (e * e).contiguous()
+            else:
+                torch.mul(e, e, out=self._scale)
+            self._scale_ver = self.log_std._version
+
+    def use_device_step_counter(self):
+        """From now on the sampling's Philox step lives on the device (`mmb_gaussian_act` reads and advances it,
+        include/mmb.h `step_counter`): a captured CUDA graph of `act()` draws fresh numbers on every replay.  The sequence
+        continues where the host-side call counter stood."""
+        if self.__dict__.get("_step_counter_dev") is None:
+            self._step_counter_dev = torch.tensor([getattr(self, "_calls", 0) + 1, 0], dtype=torch.int64, device=self.actor.device)
+        return self._step_counter_dev
+
+    def sync_parameters(self):
+        """What every eager forward does by itself, for callers that replay a captured graph of `act()`: re-cast the
+        kernel-side weights in place if the module's parameters have changed, and the sampling scale likewise."""
+        for m in (self.actor, self.critic) + ((self._pair,) if self._pair is not None else ()):
+            if m.stale():
+                m.refresh()
+        self._refresh_scale()
 
     @torch.no_grad()
     def act_inference(self, observations):

@@ -1,0 +1,149 @@
+"""The rollout phase of the reference's PPO loop as ONE CUDA-graph replay (B200-native addition: the reference has no
+counterpart - its loop is ~60 eager torch launches and three host syncs per env step).
+
+What is captured is, launch for launch, the loop of agents/algorithms/rl/ppo/ppo.py:127-157 on the replacement classes:
+
+    for _ in range(num_transitions_per_env):
+        actions, actions_log_prob, values, mu, sigma = actor_critic.act(current_obs, current_states)   # ppo.py:132
+        next_obs, rews, dones, infos = vec_env.step(actions)                                           # ppo.py:134
+        storage.add_transitions(current_obs, current_states, actions, rews, dones, values, ...)        # ppo.py:138
+        current_obs.copy_(next_obs)                                                                    # ppo.py:139
+    _, _, last_values, _, _ = actor_critic.act(current_obs, current_states)                            # ppo.py:153
+    storage.compute_returns(last_values, gamma, lam)                                                   # ppo.py:157
+
+i.e. per env step: the dual-network MLP chain (tcgen05), the sampling / log-prob kernel, the reset compaction, the fused
+step kernel and the nine-plane insert; per rollout the GAE scan and the advantage normalisation.  `current_obs.copy_` has
+no launch here: the step kernel alternates between two static observation buffers.  One graph per phase of the frame ring
+(captured when the phase first comes up, after one eager rollout), so `run()` costs one `cudaGraphLaunch`.
+
+What makes it replayable: both random streams keep their Philox counters in device memory, advanced by the launches
+themselves (`BaseTask.use_device_step_counter`, `PPOActorCriticForward.use_device_step_counter`); the storage slots are
+fixed per captured step; the policy's kernel-side weights are refreshed IN PLACE (`sync_parameters`, called before every
+replay, so an `optimizer.step()` between two rollouts is seen); everything the host tracks (`provider.cursor`, step counts,
+`storage.step`) is re-applied per replay.  The eager loop with the same seeds stores bit-identical planes
+(tests/test_gpu_ppo_rollout.py)."""
+import torch
+
+from . import _lib as L
+
+
+class GraphedPPORollout:
+    """`run()` = one rollout of `storage.num_transitions_per_env` env steps + `compute_returns`; afterwards `storage` is
+    full (`storage.step == T`: iterate `mini_batch_generator`, then `storage.clear()`, as ppo.py:160-166 does) and
+    `current_obs` holds the observation the next rollout starts from.
+
+    env      a `VecTaskPython` over a task whose frames are resident in HBM (a looping `ReplayProvider`), already `reset()`
+             or not (`run()` resets on first use)
+    policy   `mlp.PPOActorCriticForward`
+    storage  `storage.RolloutStorage` on the same device
+    tracker  optional `episodes.EpisodeTracker`: the episode bookkeeping of ppo.py:143-151 for the rollout's T steps, inside
+             the same graph (`tracker.means()` afterwards, no sync)"""
+
+    def __init__(self, env, policy, storage, gamma, lam, tracker=None):
+        from .providers import ReplayProvider
+        task = env.task
+        prov = task.provider
+        if not isinstance(prov, ReplayProvider) or not prov.loop:
+            raise TypeError("a graphed rollout needs frames resident in HBM (a looping ReplayProvider)")
+        if torch.device(env.rl_device) != torch.device(task.device) and torch.device(env.rl_device).index is not None:
+            raise TypeError("a graphed rollout needs rl_device == the task's device")
+        if getattr(task, "obs_layout", 0) != 0:
+            raise TypeError("a graphed rollout drives the single-agent (flat observation) wrapper")
+        if storage.process_group is not None and storage.stats_exchange is None:
+            raise TypeError("env-sharded storages: use the peer-memory statistics exchange (dist.StatsExchange), which is "
+                            "graph-replayable; the NCCL all-reduce of the moments is a host-issued collective")
+        self.env, self.task, self.policy, self.storage = env, task, policy, storage
+        self.gamma, self.lam, self.tracker = float(gamma), float(lam), tracker
+        self.T = storage.num_transitions_per_env
+        self._obs = None                  # the two static observation buffers the step kernel alternates between
+        self._flip = 0
+        self.states = torch.zeros(task.num_envs, 0, device=task.device)
+        self.current_obs = None
+        self._graphs = {}
+        self._pool = None
+        self._eager_left = 1              # one eager rollout first: modules loaded, caches built before any capture
+        self.captures = 0
+        task.use_device_step_counter()
+        policy.use_device_step_counter()
+
+    _FRAME_ATTRS = ("root_states", "dof_state", "vec_sensor_tensor")
+
+    def _next_out(self, *shape):
+        if tuple(shape) != tuple(self._obs[0].shape):
+            raise L.MmbError("unexpected step output %r (observation buffers are %r)" % (tuple(shape), tuple(self._obs[0].shape)))
+        self._flip ^= 1
+        return self._obs[self._flip]
+
+    def _body(self):
+        """The loop of ppo.py:127-157; `task._fresh_out` hands the step kernel the observation buffer `current_obs` is NOT."""
+        t, pol, st = self.task, self.policy, self.storage
+        cur = self._obs[self._flip]
+        for _ in range(self.T):
+            actions, logp, values, mu, sigma = pol.act(cur, self.states)
+            t.step(actions)
+            st.add_transitions(cur, self.states, actions, t.rew_buf, t.reset_buf, values, logp, mu, sigma)
+            cur = t.obs_clamped
+        last_values = pol.act(cur, self.states)[2]
+        st.compute_returns(last_values, self.gamma, self.lam)
+        if self.tracker is not None:
+            self.tracker.update(st.rewards, st.dones)
+        if self._flip:                    # odd horizon: back to buffer 0, so that every rollout starts from the same tensor
+            self._obs[0].copy_(cur)
+            self._flip = 0
+        self.current_obs = self._obs[0]
+
+    def start_from(self, obs):
+        """Start (or restart) from `obs` = what `env.reset()` / the last `env.step()` returned, instead of resetting on the
+        first `run()`."""
+        if self._obs is None:
+            self._obs = (obs.clone(), torch.empty_like(obs))
+        else:
+            self._obs[0].copy_(obs)
+        self._flip = 0
+        self.current_obs = self._obs[0]
+
+    def run(self):
+        t, st, prov = self.task, self.storage, self.task.provider
+        if st.step != 0:
+            raise AssertionError("Rollout buffer overflow")          # storage.py:36 (the storage was not cleared)
+        if self._obs is None:
+            self.start_from(self.env.reset())
+        self.policy.sync_parameters()
+        if self._eager_left > 0:
+            self._eager_left -= 1
+            t._fresh_out = self._next_out
+            try:
+                self._body()
+            finally:
+                del t._fresh_out
+            return
+        slot = (prov.cursor + t.control_freq_inv) % prov.num_frames
+        rec = self._graphs.get(slot)
+        if rec is None:
+            before = (prov.cursor, t._step_count, t._randomize_pending, getattr(self.policy, "_calls", 0))
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            t._fresh_out = self._next_out
+            try:
+                with torch.cuda.graph(g, pool=self._pool):
+                    self._body()          # advances the host-side state once; the kernels run at the replay below
+            finally:
+                del t._fresh_out
+            rec = self._graphs[slot] = (g, tuple((k, getattr(t, k)) for k in self._FRAME_ATTRS if hasattr(t, k)),
+                                        (prov.cursor - before[0], t._step_count - before[1], t._randomize_pending - before[2],
+                                         getattr(self.policy, "_calls", 0) - before[3]))
+            self.captures += 1
+        else:
+            d = rec[2]
+            prov.cursor += d[0]
+            t._step_count += d[1]
+            t._randomize_pending += d[2]
+            self.policy._calls = getattr(self.policy, "_calls", 0) + d[3]
+            for k, v in rec[1]:
+                setattr(t, k, v)
+            st.step = self.T
+            t.obs_clamped = self.current_obs
+        rec[0].replay()
+        if st.stats_exchange is not None:
+            st._xchg_pending = True

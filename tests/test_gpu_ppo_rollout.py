@@ -1,0 +1,138 @@
+"""`ppo_rollout.GraphedPPORollout` (the rollout phase of ppo.py:127-157 as one CUDA-graph replay) against the same loop
+written out eagerly on the replacement classes - which are themselves pinned to the reference (test_gpu_ten_ant.py,
+test_gpu_storage.py, test_gpu_mlp.py, test_gpu_dropin.py): every stored plane of every rollout bit-equal, the Philox
+streams of the policy's sampling and of the reset noise included (device-resident counters vs the host's), across several
+phases of the frame ring, with an in-place parameter update between two rollouts, for an even and an odd horizon.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+_PLANES = ("observations", "actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma", "returns", "advantages")
+
+
+def _actor_critic(dev):
+    def net(out_dim):
+        dims, mods = [388, 1024, 1024, 512, out_dim], []
+        for i in range(4):
+            mods.append(torch.nn.Linear(dims[i], dims[i + 1]))
+            if i < 3:
+                mods.append(torch.nn.ELU())
+        return torch.nn.Sequential(*mods)
+
+    class AC(torch.nn.Module):          # module.py:25-55
+        def __init__(self):
+            super().__init__()
+            self.asymmetric = False
+            self.actor, self.critic = net(80), net(1)
+            self.log_std = torch.nn.Parameter(torch.log(torch.tensor(0.8)) * torch.ones(80))
+
+    torch.manual_seed(11)
+    return AC().to(dev)
+
+
+def _setup(N, F, T, dev, ac):
+    from massive_marl_benchmark_b200 import synthetic
+    from massive_marl_benchmark_b200.mlp import PPOActorCriticForward
+    from massive_marl_benchmark_b200.providers import ReplayProvider
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    from massive_marl_benchmark_b200.tasks import TenAnt
+    from massive_marl_benchmark_b200.vec_task import VecTaskPython
+    fr = synthetic.ten_ant_frames(N, F, seed=3)
+    cfg = {"env": {"numEnvs": N, "env_name": "ten_ant", "episodeLength": 7}, "sim": {"dt": 0.0166}, "seed": 5}
+    task = TenAnt(cfg, None, None, "cuda", 0, True, False, provider=ReplayProvider({"root": fr["root"], "dof": fr["dof"]}, device=dev))
+    env = VecTaskPython(task, dev)
+    pol = PPOActorCriticForward(ac, dev)
+    pol.seed = 9
+    st = RolloutStorage(N, T, (388,), (0,), (80,), dev)
+    return env, pol, st
+
+
+def _perturb(ac, k):
+    """an in-place parameter change, as `optimizer.step()` makes it (bumps the version counters)"""
+    with torch.no_grad():
+        for i, p in enumerate(ac.parameters()):
+            p.mul_(1.0 + 0.01 * ((i + k) % 3))
+        ac.log_std.add_(0.05)
+
+
+def _snapshot(st):
+    return {k: getattr(st, k).clone() for k in _PLANES}
+
+
+@pytest.mark.parametrize("T,F", [(4, 8), (3, 6)])
+def test_graphed_rollout_equals_the_eager_loop(cuda_device, T, F):
+    from massive_marl_benchmark_b200.episodes import EpisodeTracker
+    from massive_marl_benchmark_b200.ppo_rollout import GraphedPPORollout
+    dev, N, R = cuda_device, 300, 7
+    ac = _actor_critic(dev)
+    sd0 = {k: v.clone() for k, v in ac.state_dict().items()}
+
+    # ---- the loop of ppo.py:127-157, eager ----
+    env, pol, st = _setup(N, F, T, dev, ac)
+    tr_e = EpisodeTracker(N, dev)
+    states = torch.zeros(N, 0, device=dev)
+    torch.manual_seed(1)
+    current_obs = env.reset()
+    eager = []
+    for r in range(R):
+        if r == 4:
+            _perturb(ac, r)
+        for _ in range(T):
+            actions, logp, values, mu, sigma = pol.act(current_obs, states)
+            next_obs, rews, dones, _ = env.step(actions)
+            st.add_transitions(current_obs, states, actions, rews, dones, values, logp, mu, sigma)
+            current_obs.copy_(next_obs)
+        last_values = pol.act(current_obs, states)[2]
+        st.compute_returns(last_values, 0.99, 0.95)
+        tr_e.update(st.rewards, st.dones)
+        eager.append((_snapshot(st), current_obs.clone()))
+        st.clear()
+    reset_e = env.task.reset_buf.clone(), env.task.progress_buf.clone()
+
+    # ---- the same, one graph replay per rollout ----
+    ac.load_state_dict(sd0)
+    env, pol, st = _setup(N, F, T, dev, ac)
+    tr_g = EpisodeTracker(N, dev)
+    ro = GraphedPPORollout(env, pol, st, 0.99, 0.95, tracker=tr_g)
+    torch.manual_seed(1)
+    for r in range(R):
+        if r == 4:
+            _perturb(ac, r)
+        ro.run()
+        assert st.step == T
+        snap, cur = eager[r]
+        for k in _PLANES:
+            assert torch.equal(getattr(st, k), snap[k]), "rollout %d: %s differs" % (r, k)
+        assert torch.equal(ro.current_obs, cur), "rollout %d: current_obs differs" % r
+        st.clear()
+    assert ro.captures == 2          # two phases of the frame ring; rollouts 3-6 were pure replays (the parameter change lands on one)
+    assert torch.equal(env.task.reset_buf, reset_e[0]) and torch.equal(env.task.progress_buf, reset_e[1])
+    assert int(tr_g.finished) == int(tr_e.finished) and tr_g.deques() == tr_e.deques()
+    with pytest.raises(AssertionError, match="Rollout buffer overflow"):
+        st.step = 1
+        ro.run()
+
+
+def test_gaussian_act_device_step_counter(cuda_device):
+    """`step_counter`: the launch takes the Philox step from device memory and advances it - the draws equal those of the
+    host-side counter started at the same value, also when the calls are replayed from a CUDA graph."""
+    from massive_marl_benchmark_b200.mlp import gaussian_act
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(0)
+    M, A = 1000, 80
+    mean = torch.randn(M, A, generator=gen).to(dev)
+    std = (0.3 + torch.rand(A, generator=gen)).to(dev)
+    host = [gaussian_act(mean, std, seed=4, step=s)[0] for s in range(5, 11)]
+    ctr = torch.tensor([5, 0], dtype=torch.int64, device=dev)
+    for s in range(2):
+        assert torch.equal(gaussian_act(mean, std, seed=4, step_counter=ctr)[0], host[s])
+    assert ctr.tolist() == [7, 0]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = gaussian_act(mean, std, seed=4, step_counter=ctr)[0]
+    for s in range(2, 6):
+        g.replay()
+        assert torch.equal(out, host[s]), s
+    assert ctr.tolist() == [11, 0]

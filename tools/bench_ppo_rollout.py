@@ -3,6 +3,7 @@ add_transitions -> current_obs.copy_(next_obs), then compute_returns per rollout
 N = 4096, horizon 16, frames resident in HBM:
   eager    VecTaskPython + PPOActorCriticForward.act + RolloutStorage.add_transitions
   graphed  GraphedVecTaskPython for the env part
+  graphed_rollout  ppo_rollout.GraphedPPORollout: the whole rollout (T x [act, step, insert] + compute_returns) as ONE graph replay
 and the reference's own structure on the same GPU (the torch ActorCritic module of module.py:25-107 in fp32 + the same env /
 storage replacements) for the policy's share.  Host time and device time per env step.  Writes gpurun_out/bench_ppo_rollout.json."""
 import json
@@ -16,6 +17,7 @@ import torch.nn as nn
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from massive_marl_benchmark_b200 import synthetic  # noqa: E402
 from massive_marl_benchmark_b200.mlp import PPOActorCriticForward  # noqa: E402
+from massive_marl_benchmark_b200.ppo_rollout import GraphedPPORollout  # noqa: E402
 from massive_marl_benchmark_b200.providers import ReplayProvider  # noqa: E402
 from massive_marl_benchmark_b200.storage import RolloutStorage  # noqa: E402
 from massive_marl_benchmark_b200.tasks import TenAnt  # noqa: E402
@@ -48,7 +50,8 @@ torch.manual_seed(0)
 ac = ActorCritic().to(dev)
 fr = synthetic.ten_ant_frames(N, 32, seed=3)
 out = {"envs": N, "horizon": T}
-for label, env_cls, policy in (("eager", VecTaskPython, "fused"), ("graphed_env", GraphedVecTaskPython, "fused"), ("torch_fp32_policy", VecTaskPython, "torch")):
+for label, env_cls, policy in (("eager", VecTaskPython, "fused"), ("graphed_env", GraphedVecTaskPython, "fused"),
+                               ("graphed_rollout", VecTaskPython, "fused"), ("torch_fp32_policy", VecTaskPython, "torch")):
     task = TenAnt({"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1},
                   provider=ReplayProvider({"root": fr["root"], "dof": fr["dof"]}, device=dev))
     env = env_cls(task, dev)
@@ -56,8 +59,15 @@ for label, env_cls, policy in (("eager", VecTaskPython, "fused"), ("graphed_env"
     pol = PPOActorCriticForward(ac, dev) if policy == "fused" else ac
     states = torch.zeros(N, 0, device=dev)
     current_obs = env.reset().clone()
+    ro = GraphedPPORollout(env, pol, st, 0.99, 0.95) if label == "graphed_rollout" else None
+    if ro is not None:
+        ro.start_from(current_obs)
 
     def rollout():
+        if ro is not None:
+            ro.run()
+            st.clear()
+            return
         for _ in range(T):
             actions, logp, values, mu, sigma = pol.act(current_obs, states)
             next_obs, rews, dones, _ = env.step(actions)
@@ -82,7 +92,7 @@ for label, env_cls, policy in (("eager", VecTaskPython, "fused"), ("graphed_env"
     out[label] = {"host_us_per_env_step": host / (K * T) * 1e6, "device_us_per_env_step": devt / (K * T) * 1e6,
                   "env_steps_per_s": N * K * T / wall}
     print(label, out[label], flush=True)
-    del env, task, st, pol
+    del env, task, st, pol, ro
     torch.cuda.empty_cache()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bench_ppo_rollout.json", "w"), indent=1)
