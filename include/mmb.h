@@ -305,6 +305,8 @@ typedef struct {
   const int64_t* dones; const float* values; const float* actions_log_prob; const float* mu; const float* sigma;
   float* dst_observations; float* dst_states; float* dst_actions; float* dst_rewards; uint8_t* dst_dones;
   float* dst_values; float* dst_actions_log_prob; float* dst_mu; float* dst_sigma;   /* slot `step` of each plane */
+  int64_t values_stride;                   /* elements between two envs' values (0 or 1: contiguous) - the critic column of a
+                                            * wider MLP output goes in without a `.contiguous()` launch */
 } mmb_rollout_add_params;
 MMB_API int32_t mmb_rollout_add(const mmb_rollout_add_params* p, void* stream);
 
@@ -427,10 +429,13 @@ typedef struct {
   float* logp_per_dim;                     /* [rows][act_dim] (MARL), or NULL */
   const float* sigma_src;                  /* [act_dim] (or [groups][act_dim]) row to broadcast, or NULL: PPO's act() also returns */
   float* sigma_out;                        /* [rows][act_dim] = sigma_src per row (`log_std.repeat(N, 1)`, module.py:87), or NULL */
-  uint64_t* step_counter;                  /* NULL, or two device words {step, ticket (0)}: the launch takes `step` from word 0 instead of
-                                            * the field above and its last block advances it by one - a CUDA-graph replay of act() then
-                                            * draws fresh numbers, in the same sequence as a host counter started at the same value */
+  uint64_t* step_counter;                  /* NULL, or MMB_ACT_COUNTER_WORDS device words {step, 0, 0, ...}: the launch takes `step` from
+                                            * word 0 instead of the field above and its last block advances it by one - a CUDA-graph replay
+                                            * of act() then draws fresh numbers, in the same sequence as a host counter started at the same
+                                            * value.  Words 1.. are the two-level ticket that finds the last block (zero between launches) */
 } mmb_gaussian_act_params;
+#define MMB_ACT_TICKET_LANES 64
+#define MMB_ACT_COUNTER_WORDS (2 + MMB_ACT_TICKET_LANES)
 MMB_API int32_t mmb_gaussian_act(const mmb_gaussian_act_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */

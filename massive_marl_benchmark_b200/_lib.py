@@ -106,9 +106,10 @@ class RolloutAddParams(C.Structure):
     _fields_ = [("num_envs", c_i32), ("obs_dim", c_i32), ("states_dim", c_i32), ("act_dim", c_i32)] + [
         (n, c_vp) for n in ("observations", "states", "actions", "rewards", "dones", "values", "actions_log_prob",
                             "mu", "sigma", "dst_observations", "dst_states", "dst_actions", "dst_rewards",
-                            "dst_dones", "dst_values", "dst_actions_log_prob", "dst_mu", "dst_sigma")]
+                            "dst_dones", "dst_values", "dst_actions_log_prob", "dst_mu", "dst_sigma")] + [("values_stride", c_i64)]
 
 
+ACT_COUNTER_WORDS = 2 + 64
 MAX_RANKS = 16
 MAX_GROUP = 16
 STAT_SLOTS, STAT_SLOT_STRIDE = 32, 16

@@ -393,6 +393,10 @@ __global__ void __launch_bounds__(256) rollout_add_kernel(const __grid_constant_
     return;
   }
   if (!src || !dst || n == 0) return;
+  if (field == 4 && p.values_stride > 1) {   // one column of a wider matrix
+    for (int64_t i = i0; i < N; i += stride) dst[i] = src[i * p.values_stride];
+    return;
+  }
   if (aligned16(src) && aligned16(dst)) {
     const int64_t n4 = n >> 2;
     for (int64_t i = i0; i < n4; i += stride) stg4(dst + 4 * i, ldg4(src + 4 * i));

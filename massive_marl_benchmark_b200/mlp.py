@@ -544,7 +544,7 @@ def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per
     or [groups, A] with std_group_rows = rows per group (a team's agent-major means with per-agent std rows).
     Returns (actions [M, A], logp): logp [M] summed over the action dims, or [M, A] with per_dim=True.  With `sigma_src`
     (same shape as std, fp32) a third output [M, A] holds that row broadcast over the rows - the `log_std.repeat(N, 1)` PPO's
-    `act()` returns (module.py:87) - written by the same launch.  `step_counter`: int64 device tensor {step, 0}; the launch
+    `act()` returns (module.py:87) - written by the same launch.  `step_counter`: int64 device tensor of `_lib.ACT_COUNTER_WORDS` words {step, 0, ...}; the launch
     takes the Philox step from it and advances it (a captured CUDA graph then draws fresh numbers on every replay)."""
     M, A = mean.shape
     if mean.stride(1) != 1:
@@ -562,8 +562,10 @@ def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per
         p.noise = noise.data_ptr()
     p.seed, p.step = int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFFFFFFFFFF
     if step_counter is not None:
-        if step_counter.dtype != torch.int64 or step_counter.numel() < 2 or step_counter.device != mean.device or not step_counter.is_contiguous():
-            raise L.MmbError("gaussian_act: step_counter must be a contiguous int64 tensor {step, ticket} on the means' device")
+        if (step_counter.dtype != torch.int64 or step_counter.numel() < L.ACT_COUNTER_WORDS or step_counter.device != mean.device or
+                not step_counter.is_contiguous()):
+            raise L.MmbError("gaussian_act: step_counter must be a contiguous int64 tensor of %d words {step, 0, ...} on the means' "
+                             "device" % L.ACT_COUNTER_WORDS)
         p.step_counter = step_counter.data_ptr()
     p.actions = actions.data_ptr()
     if per_dim:
@@ -657,7 +659,8 @@ class PPOActorCriticForward:
         include/mmb.h `step_counter`): a captured CUDA graph of `act()` draws fresh numbers on every replay.  The sequence
         continues where the host-side call counter stood."""
         if self.__dict__.get("_step_counter_dev") is None:
-            self._step_counter_dev = torch.tensor([getattr(self, "_calls", 0) + 1, 0], dtype=torch.int64, device=self.actor.device)
+            self._step_counter_dev = torch.zeros(L.ACT_COUNTER_WORDS, dtype=torch.int64, device=self.actor.device)
+            self._step_counter_dev[0] = getattr(self, "_calls", 0) + 1
         return self._step_counter_dev
 
     def sync_parameters(self):

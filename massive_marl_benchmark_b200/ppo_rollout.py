@@ -12,7 +12,8 @@ What is captured is, launch for launch, the loop of agents/algorithms/rl/ppo/ppo
     storage.compute_returns(last_values, gamma, lam)                                                   # ppo.py:157
 
 i.e. per env step: the dual-network MLP chain (tcgen05), the sampling / log-prob kernel, the reset compaction, the fused
-step kernel and the nine-plane insert; per rollout the GAE scan and the advantage normalisation.  `current_obs.copy_` has
+step kernel and the nine-plane insert (on a side branch of the graph, under the next step's policy forward); per rollout
+the GAE scan and the advantage normalisation.  `current_obs.copy_` has
 no launch here: the step kernel alternates between two static observation buffers.  One graph per phase of the frame ring
 (captured when the phase first comes up, after one eager rollout), so `run()` costs one `cudaGraphLaunch`.
 
@@ -60,6 +61,7 @@ class GraphedPPORollout:
         self.states = torch.zeros(task.num_envs, 0, device=task.device)
         self.current_obs = None
         self._graphs = {}
+        self._side = torch.cuda.Stream(device=task.device)
         self._pool = None
         self._eager_left = 1              # one eager rollout first: modules loaded, caches built before any capture
         self.captures = 0
@@ -75,15 +77,30 @@ class GraphedPPORollout:
         return self._obs[self._flip]
 
     def _body(self):
-        """The loop of ppo.py:127-157; `task._fresh_out` hands the step kernel the observation buffer `current_obs` is NOT."""
+        """The loop of ppo.py:127-157; `task._fresh_out` hands the step kernel the observation buffer `current_obs` is NOT.
+        The insert of step t runs on a side stream under the policy forward of step t + 1 (it only feeds the storage); the
+        step kernel of t + 1 waits for it, because it overwrites the observation / reward / reset buffers the insert reads."""
         t, pol, st = self.task, self.policy, self.storage
+        main, side = torch.cuda.current_stream(), self._side
         cur = self._obs[self._flip]
+        keep, inserted = [], None        # the policy outputs stay allocated until the last insert has been joined
         for _ in range(self.T):
-            actions, logp, values, mu, sigma = pol.act(cur, self.states)
+            outs = pol.act(cur, self.states)
+            keep.append(outs)
+            actions, logp, values, mu, sigma = outs
+            if inserted is not None:
+                main.wait_event(inserted)
             t.step(actions)
-            st.add_transitions(cur, self.states, actions, t.rew_buf, t.reset_buf, values, logp, mu, sigma)
+            stepped = torch.cuda.Event()
+            stepped.record(main)
+            side.wait_event(stepped)
+            with torch.cuda.stream(side):
+                st.add_transitions(cur, self.states, actions, t.rew_buf, t.reset_buf, values, logp, mu, sigma)
+                inserted = torch.cuda.Event()
+                inserted.record(side)
             cur = t.obs_clamped
         last_values = pol.act(cur, self.states)[2]
+        main.wait_event(inserted)
         st.compute_returns(last_values, self.gamma, self.lam)
         if self.tracker is not None:
             self.tracker.update(st.rewards, st.dones)
@@ -91,6 +108,7 @@ class GraphedPPORollout:
             self._obs[0].copy_(cur)
             self._flip = 0
         self.current_obs = self._obs[0]
+        del keep
 
     def start_from(self, obs):
         """Start (or restart) from `obs` = what `env.reset()` / the last `env.step()` returned, instead of resetting on the

@@ -99,7 +99,13 @@ class RolloutStorage:
             raise AssertionError("Rollout buffer overflow")
         s = self.step
         c = lambda t: t if t.is_contiguous() else t.contiguous()
-        keep = [c(observations), c(states), c(actions), c(rewards), c(dones), c(values), c(actions_log_prob), c(mu), c(sigma)]
+        # values as one column of a wider matrix (the critic column of the actor + critic pair's output): read with its row
+        # stride by the kernel, no `.contiguous()` launch
+        v_stride = 1
+        if values.dim() == 2 and values.shape[1] == 1 and values.stride(0) > 1 and values.dtype == torch.float32:
+            v_stride = values.stride(0)
+        keep = [c(observations), c(states), c(actions), c(rewards), c(dones), values if v_stride > 1 else c(values),
+                c(actions_log_prob), c(mu), c(sigma)]
         if keep[4].dtype != torch.int64:
             keep[4] = keep[4].to(torch.int64)
         p = self._p_add
@@ -114,6 +120,7 @@ class RolloutStorage:
          p.sigma) = [t.data_ptr() if t.numel() else None for t in keep]
         (p.dst_observations, p.dst_states, p.dst_actions, p.dst_rewards, p.dst_dones, p.dst_values, p.dst_actions_log_prob,
          p.dst_mu, p.dst_sigma) = self._dst_ptrs[s]
+        p.values_stride = v_stride
         L.check(L.lib().mmb_rollout_add(p, L.stream_ptr()), "mmb_rollout_add")
         self._keep_add = keep
         self.step += 1

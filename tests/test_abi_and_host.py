@@ -46,7 +46,7 @@ def test_ctypes_structs_match_c_layout(built_lib):
     L = built_lib
     probes = [("mmb_ant_consts", L.AntConsts, "initial_dof_pos"), ("mmb_ten_ant_params", L.TenAntParams, "c"),
               ("mmb_one_ant_params", L.OneAntParams, "c"), ("mmb_ingenuity_params", L.IngenuityParams, "forces_state"),
-              ("mmb_reset_params", L.ResetParams, "c"), ("mmb_rollout_add_params", L.RolloutAddParams, "dst_sigma"),
+              ("mmb_reset_params", L.ResetParams, "c"), ("mmb_rollout_add_params", L.RolloutAddParams, "values_stride"),
               ("mmb_gae_ppo_params", L.GaePpoParams, "stats"), ("mmb_gae_marl_params", L.GaeMarlParams, "stats"),
               ("mmb_xchg", L.Xchg, "mailbox"), ("mmb_episode_params", L.EpisodeParams, "state"), ("mmb_gaussian_act_params", L.GaussianActParams, "step_counter"),
               ("mmb_ppo_loss_params", L.PpoLossParams, "ticket"), ("mmb_mappo_loss_params", L.MappoLossParams, "sums"),

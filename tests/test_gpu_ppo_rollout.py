@@ -83,6 +83,8 @@ def test_graphed_rollout_equals_the_eager_loop(cuda_device, T, F):
             actions, logp, values, mu, sigma = pol.act(current_obs, states)
             next_obs, rews, dones, _ = env.step(actions)
             st.add_transitions(current_obs, states, actions, rews, dones, values, logp, mu, sigma)
+            assert not values.is_contiguous() and torch.equal(st.values[st.step - 1], values)      # the strided critic column
+            assert torch.equal(st.mu[st.step - 1], mu) and torch.equal(st.actions_log_prob[st.step - 1, :, 0], logp)
             current_obs.copy_(next_obs)
         last_values = pol.act(current_obs, states)[2]
         st.compute_returns(last_values, 0.99, 0.95)
@@ -125,14 +127,18 @@ def test_gaussian_act_device_step_counter(cuda_device):
     mean = torch.randn(M, A, generator=gen).to(dev)
     std = (0.3 + torch.rand(A, generator=gen)).to(dev)
     host = [gaussian_act(mean, std, seed=4, step=s)[0] for s in range(5, 11)]
-    ctr = torch.tensor([5, 0], dtype=torch.int64, device=dev)
+    from massive_marl_benchmark_b200 import _lib as L
+    ctr = torch.zeros(L.ACT_COUNTER_WORDS, dtype=torch.int64, device=dev)
+    ctr[0] = 5
     for s in range(2):
         assert torch.equal(gaussian_act(mean, std, seed=4, step_counter=ctr)[0], host[s])
-    assert ctr.tolist() == [7, 0]
+    assert ctr.tolist() == [7] + [0] * (L.ACT_COUNTER_WORDS - 1)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         out = gaussian_act(mean, std, seed=4, step_counter=ctr)[0]
     for s in range(2, 6):
         g.replay()
         assert torch.equal(out, host[s]), s
-    assert ctr.tolist() == [11, 0]
+    assert ctr.tolist() == [11] + [0] * (L.ACT_COUNTER_WORDS - 1)
+    small = gaussian_act(mean[:3], std, seed=4, step_counter=ctr)[0]          # one block: fewer blocks than ticket lanes
+    assert torch.equal(small, gaussian_act(mean[:3], std, seed=4, step=11)[0]) and ctr.tolist() == [12] + [0] * (L.ACT_COUNTER_WORDS - 1)
