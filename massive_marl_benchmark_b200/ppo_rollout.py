@@ -64,6 +64,8 @@ class GraphedPPORollout:
         self._side = torch.cuda.Stream(device=task.device)
         self._pool = None
         self._eager_left = 1              # one eager rollout first: modules loaded, caches built before any capture
+        self._ahead = hasattr(task, "reset_ahead")
+        self._steps_seen = None           # task._step_count when the last run() ended (somebody stepped the env in between?)
         self.captures = 0
         task.use_device_step_counter()
         policy.use_device_step_counter()
@@ -79,11 +81,14 @@ class GraphedPPORollout:
     def _body(self):
         """The loop of ppo.py:127-157; `task._fresh_out` hands the step kernel the observation buffer `current_obs` is NOT.
         The insert of step t runs on a side stream under the policy forward of step t + 1 (it only feeds the storage); the
-        step kernel of t + 1 waits for it, because it overwrites the observation / reward / reset buffers the insert reads."""
+        step kernel of t + 1 waits for it, because it overwrites the observation / reward / reset buffers the insert reads.
+        So does (TenAnt) the reset compaction of step t + 1, which needs nothing but the flags step t left
+        (`TenAnt.reset_ahead`): the invariant at every rollout boundary is "the next step's reset_idx() has been launched"."""
         t, pol, st = self.task, self.policy, self.storage
         main, side = torch.cuda.current_stream(), self._side
         cur = self._obs[self._flip]
         keep, inserted = [], None        # the policy outputs stay allocated until the last insert has been joined
+        ahead = self._ahead
         for _ in range(self.T):
             outs = pol.act(cur, self.states)
             keep.append(outs)
@@ -95,6 +100,8 @@ class GraphedPPORollout:
             stepped.record(main)
             side.wait_event(stepped)
             with torch.cuda.stream(side):
+                if ahead:                 # the NEXT step's reset compaction: it reads only the flags this step has just written
+                    t.reset_idx()
                 st.add_transitions(cur, self.states, actions, t.rew_buf, t.reset_buf, values, logp, mu, sigma)
                 inserted = torch.cuda.Event()
                 inserted.record(side)
@@ -127,6 +134,17 @@ class GraphedPPORollout:
         if self._obs is None:
             self.start_from(self.env.reset())
         self.policy.sync_parameters()
+        if self._ahead and self._steps_seen != t._step_count:
+            t.reset_idx()                 # first run, or the env was stepped from outside: (re-)establish the invariant
+        try:
+            t.reset_ahead = self._ahead
+            self._run()
+        finally:
+            t.reset_ahead = False
+            self._steps_seen = t._step_count
+
+    def _run(self):
+        t, st, prov = self.task, self.storage, self.task.provider
         if self._eager_left > 0:
             self._eager_left -= 1
             t._fresh_out = self._next_out

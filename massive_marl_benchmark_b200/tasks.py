@@ -289,6 +289,11 @@ class TenAnt(BaseTask):
         p.c = self.consts
         L.check(L.lib().mmb_ten_ant_step(p, L.stream_ptr()), "mmb_ten_ant_step")
 
+    # True: `post_physics_step` launches the step kernel only - the reset compaction of the step (ten_ant.py:899-901) was
+    # launched ahead by the caller through `reset_idx()`.  The step kernel reads nothing that launch writes, and that launch
+    # reads only the flags the previous step left, so it may run any time between the two step kernels.
+    reset_ahead = False
+
     def post_physics_step(self):
         """ten_ant.py:894-926 (+ the fused pre_physics force scaling and wrapper clamps)."""
         self._randomize_pending += 1
@@ -323,9 +328,14 @@ class TenAnt(BaseTask):
         p.obs_raw = self.obs_buf.data_ptr() if self.keep_raw_obs else None
         p.obs = obs.data_ptr()
         p.share_obs = share.data_ptr() if share is not None else None
-        # reset_idx of the flagged envs (ten_ant.py:899-901) and the step in ONE host call (mmb_ten_ant_env_step)
-        pr = self._reset_params()
-        L.check(L.lib().mmb_ten_ant_env_step(pr, p, L.stream_ptr()), "mmb_ten_ant_env_step")
+        if self.reset_ahead:
+            # the caller has launched this step's reset_idx() already (ppo_rollout: on a side stream, under the policy forward,
+            # ordered before this launch by an event): the step kernel alone
+            L.check(L.lib().mmb_ten_ant_step(p, L.stream_ptr()), "mmb_ten_ant_step")
+        else:
+            # reset_idx of the flagged envs (ten_ant.py:899-901) and the step in ONE host call (mmb_ten_ant_env_step)
+            pr = self._reset_params()
+            L.check(L.lib().mmb_ten_ant_env_step(pr, p, L.stream_ptr()), "mmb_ten_ant_env_step")
         prov = self.provider
         prov.set_actor_root_state_tensor_indexed(self.initial_root_states, self.ant_box_indices, self.reset_count)
         prov.set_dof_state_tensor_indexed(self.dof_reset_staging, self.ant_indices, self.reset_count)

@@ -9,6 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+_RESET_STATE = ("reset_count", "env_ids", "ant_box_indices", "ant_indices", "dof_reset_staging")
 _PLANES = ("observations", "actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma", "returns", "advantages")
 
 
@@ -92,6 +93,8 @@ def test_graphed_rollout_equals_the_eager_loop(cuda_device, T, F):
         eager.append((_snapshot(st), current_obs.clone()))
         st.clear()
     reset_e = env.task.reset_buf.clone(), env.task.progress_buf.clone()
+    env.task.reset_idx()        # the graphed rollout has launched the NEXT step's reset compaction already (TenAnt.reset_ahead)
+    lists_e = {k: getattr(env.task, k).clone() for k in _RESET_STATE}
 
     # ---- the same, one graph replay per rollout ----
     ac.load_state_dict(sd0)
@@ -111,6 +114,8 @@ def test_graphed_rollout_equals_the_eager_loop(cuda_device, T, F):
         st.clear()
     assert ro.captures == 2          # two phases of the frame ring; rollouts 3-6 were pure replays (the parameter change lands on one)
     assert torch.equal(env.task.reset_buf, reset_e[0]) and torch.equal(env.task.progress_buf, reset_e[1])
+    for k in _RESET_STATE:     # reset index lists, counts and the Philox-randomised DOF rows of the step to come
+        assert torch.equal(getattr(env.task, k), lists_e[k]), k
     assert int(tr_g.finished) == int(tr_e.finished) and tr_g.deques() == tr_e.deques()
     with pytest.raises(AssertionError, match="Rollout buffer overflow"):
         st.step = 1
