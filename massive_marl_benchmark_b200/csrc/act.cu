@@ -17,79 +17,119 @@
 namespace mmb {
 namespace {
 
+// Two standard normal draws from two 32-bit words.  Only the SAMPLE comes from here (the log-probability is computed from
+// the action with IEEE arithmetic below), so the fast intrinsics do: |error| of __logf / __sincosf on these ranges is
+// < 2^-21, far below what a random draw can resolve; the angle is taken in [-pi, pi), where __sincosf is accurate.
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
-  const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
-  const float r = sqrtf(-2.0f * logf(u1));
+  const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f) - 0.5f;     // [-0.5, 0.5)
+  const float r = sqrtf(-2.0f * __logf(u1));
   float sn, cs;
-  sincosf(6.28318530717958647692f * u2, &sn, &cs);
+  __sincosf(6.28318530717958647692f * u2, &sn, &cs);
   return make_float2(r * cs, r * sn);
 }
 
-// one warp per row: lanes stride over the action dimensions; per-row log-prob sum by shuffle
-__global__ void __launch_bounds__(256) gaussian_act_kernel(const __grid_constant__ mmb_gaussian_act_params p) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int A = p.num_rows > row ? p.act_dim : 0;   // rows past the end do nothing but stay for the block's barrier below
-  const int64_t grp = p.std_group_rows > 0 ? (int64_t)(row / p.std_group_rows) * A : 0;
-  const float* std = p.std + grp;
-  // Launched as a programmatic dependent of the kernel in front of it (the MLP that writes the means): nothing is read or
-  // WRITTEN before the wait - the outputs are fresh allocations, and the caching allocator may hand out a block the
+// log N(a; m, sd) = -z^2/2 - log(sd) - log(sqrt(2 pi)) with z = (a - m) / sd as the distribution recomputes it
+__device__ __forceinline__ float normal_logp(float a, float m, float sd) {
+  const float zz = (a - m) / sd;
+  return -0.5f * zz * zz - logf(sd) - 0.9189385332046727f;
+}
+
+constexpr int ACT_THREADS = 1024;    // 32 rows in flight per block; the grid is capped at the SM count (grid-stride over rows)
+constexpr unsigned ACT_TICKET_LANES = 16;
+static_assert(ACT_TICKET_LANES <= MMB_ACT_TICKET_LANES, "ticket words of the caller's buffer");
+
+// One warp per row.  PAIR (act_dim even, 8-byte aligned rows): a lane owns the element pairs (2 lane, 2 lane + 1) + 64 k -
+// the two elements that share one Philox call and one Box-Muller transform, so each is computed once, with 8-byte accesses.
+// Element idx of the [rows][act_dim] matrix takes word (idx & 1) of the transform of Philox counter idx >> 1: the stream
+// does not depend on the path taken.
+template <bool PAIR>
+__global__ void __launch_bounds__(ACT_THREADS) gaussian_act_kernel(const __grid_constant__ mmb_gaussian_act_params p) {
+  __shared__ unsigned long long s_step;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int A = p.act_dim;
+  // Launched (optionally) as a programmatic dependent of the kernel in front of it (the MLP that writes the means): nothing is
+  // read or WRITTEN before the wait - the outputs are fresh allocations, and the caching allocator may hand out a block the
   // kernel in front still reads.
   griddep_wait();
-  // device-resident Philox counter (CUDA-graph replays): every block reads it here; the last block to retire advances it
-  const uint64_t step = p.step_counter ? __ldcg(reinterpret_cast<const unsigned long long*>(p.step_counter)) : p.step;
-  if (p.sigma_out)
-    for (int j = lane; j < A; j += 32) p.sigma_out[(int64_t)row * A + j] = __ldg(p.sigma_src + grp + j);
-  const float* mean = p.mean + (int64_t)row * p.mean_stride;
-  float lp_sum = 0.0f;
-  for (int j = lane; j < A; j += 32) {
-    const float sd = __ldg(std + j);
-    float z;
-    if (p.noise) {
-      z = __ldg(p.noise + (int64_t)row * A + j);
-    } else if (p.deterministic) {
-      z = 0.0f;
-    } else {
-      const uint64_t idx = (uint64_t)row * (uint64_t)A + (uint64_t)j;
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)(idx >> 1), (uint32_t)(idx >> 33), (uint32_t)step, (uint32_t)(step >> 32)),
-                                    make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-      const float2 n = box_muller(r.x, r.y);
-      z = (idx & 1) ? n.y : n.x;
-    }
-    const float m = __ldg(mean + j);
-    const float a = m + z * sd;
-    p.actions[(int64_t)row * A + j] = a;
-    // log N(a; m, sd) = -z^2/2 - log(sd) - log(sqrt(2 pi)) with z = (a - m) / sd as the distribution recomputes it
-    const float zz = (a - m) / sd;
-    const float lp = -0.5f * zz * zz - logf(sd) - 0.9189385332046727f;
-    if (p.logp_per_dim) p.logp_per_dim[(int64_t)row * A + j] = lp;
-    lp_sum += lp;
-  }
-  if (p.logp_sum) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
-    if (lane == 0 && A > 0) p.logp_sum[row] = lp_sum;
-  }
+  uint64_t step = p.step;
   if (p.step_counter) {
-    // Find the last block to retire with a two-level ticket: same-address atomics retire at ~13 ns each on B200 (512 blocks
-    // on one word were 6.6 us of this kernel), so a block draws from lane blockIdx % 64 and only the last block of a lane
-    // draws from the top word.  The very last block advances the step and leaves every ticket word at zero.
-    __syncthreads();   // every warp of the block has read the counter
+    // Device-resident Philox step (CUDA-graph replays).  Thread 0 of every block reads it and THEN draws a ticket; the block
+    // that draws the last ticket knows every block has read and advances the counter - right away, under the sampling work
+    // of the whole grid, not at its end.  Two levels (same-address atomics retire at ~13 ns each on B200): a block draws from
+    // lane blockIdx % 16, the last block of a lane from the top word.  Every ticket word is left at zero.
+    unsigned long long* ctr = reinterpret_cast<unsigned long long*>(p.step_counter);
     if (threadIdx.x == 0) {
-      unsigned long long* ctr = reinterpret_cast<unsigned long long*>(p.step_counter);
-      constexpr unsigned LANES = MMB_ACT_TICKET_LANES;
-      const unsigned lane_id = blockIdx.x % LANES;
-      const unsigned lanes_used = gridDim.x < LANES ? gridDim.x : LANES;
-      const unsigned in_lane = (gridDim.x - lane_id + LANES - 1) / LANES;   // blocks that draw from this lane
+      const unsigned long long v = __ldcg(ctr);
+      s_step = v;
+      const unsigned lane_id = blockIdx.x % ACT_TICKET_LANES;
+      const unsigned lanes_used = gridDim.x < ACT_TICKET_LANES ? gridDim.x : ACT_TICKET_LANES;
+      const unsigned in_lane = (gridDim.x - lane_id + ACT_TICKET_LANES - 1) / ACT_TICKET_LANES;   // blocks that draw from this lane
       __threadfence();
       if (atomicAdd(ctr + 2 + lane_id, 1ull) == (unsigned long long)in_lane - 1ull) {
         ctr[2 + lane_id] = 0ull;
         __threadfence();
         if (atomicAdd(ctr + 1, 1ull) == (unsigned long long)lanes_used - 1ull) {
           ctr[1] = 0ull;
-          ctr[0] = step + 1ull;
+          ctr[0] = v + 1ull;
         }
       }
+    }
+    __syncthreads();
+    step = s_step;
+  }
+  const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  const int mode = p.noise ? 0 : (p.deterministic ? 1 : 2);
+  for (int64_t row = (int64_t)blockIdx.x * (ACT_THREADS / 32) + warp; row < p.num_rows; row += (int64_t)gridDim.x * (ACT_THREADS / 32)) {
+    const int64_t grp = p.std_group_rows > 0 ? (row / p.std_group_rows) * A : 0;
+    const float* std = p.std + grp;
+    const float* mean = p.mean + row * p.mean_stride;
+    const int64_t base = row * A;
+    float lp_sum = 0.0f;
+    if (PAIR) {
+      for (int j = 2 * lane; j < A; j += 64) {
+        const float2 sd = __ldg(reinterpret_cast<const float2*>(std + j));
+        const float2 m = __ldg(reinterpret_cast<const float2*>(mean + j));
+        float2 z = make_float2(0.0f, 0.0f);
+        if (mode == 0) {
+          z = __ldg(reinterpret_cast<const float2*>(p.noise + base + j));
+        } else if (mode == 2) {
+          const uint64_t c = (uint64_t)(base + j) >> 1;
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+          z = box_muller(r.x, r.y);
+        }
+        const float2 a = make_float2(m.x + z.x * sd.x, m.y + z.y * sd.y);
+        *reinterpret_cast<float2*>(p.actions + base + j) = a;
+        const float2 lp = make_float2(normal_logp(a.x, m.x, sd.x), normal_logp(a.y, m.y, sd.y));
+        if (p.logp_per_dim) *reinterpret_cast<float2*>(p.logp_per_dim + base + j) = lp;
+        if (p.sigma_out) *reinterpret_cast<float2*>(p.sigma_out + base + j) = __ldg(reinterpret_cast<const float2*>(p.sigma_src + grp + j));
+        lp_sum += lp.x + lp.y;
+      }
+    } else {
+      for (int j = lane; j < A; j += 32) {
+        const float sd = __ldg(std + j);
+        const float m = __ldg(mean + j);
+        float z = 0.0f;
+        if (mode == 0) {
+          z = __ldg(p.noise + base + j);
+        } else if (mode == 2) {
+          const uint64_t idx = (uint64_t)(base + j), c = idx >> 1;
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+          const float2 n = box_muller(r.x, r.y);
+          z = (idx & 1) ? n.y : n.x;
+        }
+        const float a = m + z * sd;
+        p.actions[base + j] = a;
+        const float lp = normal_logp(a, m, sd);
+        if (p.logp_per_dim) p.logp_per_dim[base + j] = lp;
+        if (p.sigma_out) p.sigma_out[base + j] = __ldg(p.sigma_src + grp + j);
+        lp_sum += lp;
+      }
+    }
+    if (p.logp_sum) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
+      if (lane == 0) p.logp_sum[row] = lp_sum;
     }
   }
 }
@@ -109,8 +149,10 @@ extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* str
     // optionally a programmatic dependent launch: the grid is scheduled while the kernel in front (the MLP that writes the
     // means) drains; everything that reads its output sits behind griddepcontrol.wait
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(((int64_t)p.num_rows * 32 + 255) / 256));
-    cfg.blockDim = dim3(256);
+    int64_t blocks = ((int64_t)p.num_rows + ACT_THREADS / 32 - 1) / (ACT_THREADS / 32);
+    if (blocks > sm_count()) blocks = sm_count();
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(ACT_THREADS);
     cfg.stream = (cudaStream_t)stream;
     // MMB_ACT_PDL=1: measured equal within noise to the ordinary launch behind the dual-network chain (act() graph-replayed
     // 52.0 vs 51.1 us at M = 4096), so it is off by default
@@ -120,7 +162,11 @@ extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* str
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, gaussian_act_kernel, p) != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
+    auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+    const bool pair = (p.act_dim & 1) == 0 && (p.mean_stride & 1) == 0 && al8(p.mean) && al8(p.std) && al8(p.actions) && al8(p.noise) &&
+                      al8(p.logp_per_dim) && al8(p.sigma_src) && al8(p.sigma_out);
+    const cudaError_t le = pair ? cudaLaunchKernelEx(&cfg, gaussian_act_kernel<true>, p) : cudaLaunchKernelEx(&cfg, gaussian_act_kernel<false>, p);
+    if (le != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;
 }

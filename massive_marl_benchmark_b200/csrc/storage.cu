@@ -622,8 +622,12 @@ extern "C" int32_t mmb_rollout_add(const mmb_rollout_add_params* pp, void* strea
   if (!pp) return MMB_EINVAL;
   mmb_rollout_add_params p = *pp;
   if (p.num_envs <= 0 || p.obs_dim < 0 || p.states_dim < 0 || p.act_dim < 0) return MMB_EINVAL;
-  int64_t maxn = (int64_t)p.num_envs * (p.obs_dim > p.act_dim ? p.obs_dim : p.act_dim);
-  if (maxn < p.num_envs) maxn = p.num_envs;
+  // the grid follows the widest plane that is actually copied (a NULL source = the producer wrote the slot itself)
+  int64_t maxn = p.num_envs;
+  if (p.observations && p.dst_observations && (int64_t)p.num_envs * p.obs_dim > maxn) maxn = (int64_t)p.num_envs * p.obs_dim;
+  if (p.states && p.dst_states && (int64_t)p.num_envs * p.states_dim > maxn) maxn = (int64_t)p.num_envs * p.states_dim;
+  if (((p.actions && p.dst_actions) || (p.mu && p.dst_mu) || (p.sigma && p.dst_sigma)) && (int64_t)p.num_envs * p.act_dim > maxn)
+    maxn = (int64_t)p.num_envs * p.act_dim;
   int64_t bx = (maxn / 4 + 255) / 256;
   if (bx < 1) bx = 1;
   if (bx > sm_count() * 8) bx = sm_count() * 8;

@@ -539,21 +539,31 @@ class GroupedMLP:
 
 
 def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per_dim=False, std_group_rows=0, sigma_src=None,
-                 step_counter=None):
+                 step_counter=None, out=None):
     """actions = mean + z * std and log-probs in one launch (`mmb_gaussian_act`).  mean [M, A] (row stride allowed), std [A] -
     or [groups, A] with std_group_rows = rows per group (a team's agent-major means with per-agent std rows).
     Returns (actions [M, A], logp): logp [M] summed over the action dims, or [M, A] with per_dim=True.  With `sigma_src`
     (same shape as std, fp32) a third output [M, A] holds that row broadcast over the rows - the `log_std.repeat(N, 1)` PPO's
     `act()` returns (module.py:87) - written by the same launch.  `step_counter`: int64 device tensor of `_lib.ACT_COUNTER_WORDS` words {step, 0, ...}; the launch
-    takes the Philox step from it and advances it (a captured CUDA graph then draws fresh numbers on every replay)."""
+    takes the Philox step from it and advances it (a captured CUDA graph then draws fresh numbers on every replay).
+    `out` = (actions, logp, sigma or None): contiguous fp32 tensors to write into (rollout-storage slots) instead of fresh ones."""
     M, A = mean.shape
     if mean.stride(1) != 1:
         mean = mean.contiguous()
     std = std.reshape(-1).float().contiguous()
     if std.numel() != (A if not std_group_rows else A * ((M + std_group_rows - 1) // std_group_rows)):
         raise L.MmbError("gaussian_act: std has %d elements for %d rows x %d dims (std_group_rows %d)" % (std.numel(), M, A, std_group_rows))
-    actions = torch.empty(M, A, dtype=torch.float32, device=mean.device)
-    logp = torch.empty((M, A) if per_dim else (M,), dtype=torch.float32, device=mean.device)
+    if out is not None:
+        actions, logp = out[0], out[1]
+        want = {"actions": (actions, M * A), "logp": (logp, M * A if per_dim else M)}
+        if sigma_src is not None:
+            want["sigma"] = (out[2], M * A)
+        for k, (t_, n_) in want.items():
+            if t_.dtype != torch.float32 or not t_.is_contiguous() or t_.numel() != n_ or t_.device != mean.device:
+                raise L.MmbError("gaussian_act: out %s must be a contiguous fp32 tensor of %d elements on the means' device" % (k, n_))
+    else:
+        actions = torch.empty(M, A, dtype=torch.float32, device=mean.device)
+        logp = torch.empty((M, A) if per_dim else (M,), dtype=torch.float32, device=mean.device)
     p = L.GaussianActParams()
     p.num_rows, p.act_dim, p.deterministic, p.std_group_rows = M, A, int(bool(deterministic)), int(std_group_rows)
     p.mean, p.mean_stride, p.std = mean.data_ptr(), mean.stride(0), std.data_ptr()
@@ -579,7 +589,7 @@ def gaussian_act(mean, std, seed=0, step=0, noise=None, deterministic=False, per
             sigma_src = sigma_src.to(mean.device, torch.float32).contiguous()
         if sigma_src.numel() != std.numel():
             raise L.MmbError("gaussian_act: sigma_src has %d elements, std %d" % (sigma_src.numel(), std.numel()))
-        sigma = torch.empty(M, A, dtype=torch.float32, device=mean.device)
+        sigma = out[2] if out is not None else torch.empty(M, A, dtype=torch.float32, device=mean.device)
         p.sigma_src, p.sigma_out = sigma_src.data_ptr(), sigma.data_ptr()
     L.check(L.lib().mmb_gaussian_act(p, L.stream_ptr()), "mmb_gaussian_act")
     return (actions, logp) if sigma is None else (actions, logp, sigma)
@@ -633,14 +643,16 @@ class PPOActorCriticForward:
         return self.actor(observations), self.critic(states if self.asymmetric else observations)
 
     @torch.no_grad()
-    def act(self, observations, states=None, noise=None):
-        """`noise` [N, act]: standard normal draws to use (parity tests); default: in-kernel Philox keyed by (seed, call #)."""
+    def act(self, observations, states=None, noise=None, out=None):
+        """`noise` [N, act]: standard normal draws to use (parity tests); default: in-kernel Philox keyed by (seed, call #).
+        `out` = (actions [N, act], log_prob [N] or [N, 1], sigma [N, act]): write these three into the given tensors (slots of a
+        `RolloutStorage`) instead of fresh ones."""
         mean, value = self._mean_value(observations, states)
         # MultivariateNormal with scale_tril = diag(exp(log_std)^2): sample + log_prob (sum over dims) in one launch
         self._calls = getattr(self, "_calls", 0) + 1
         self._refresh_scale()
         actions, log_prob, sigma = gaussian_act(mean, self._scale, seed=getattr(self, "seed", 0), step=self._calls, noise=noise,
-                                                sigma_src=self.log_std, step_counter=self.__dict__.get("_step_counter_dev"))
+                                                sigma_src=self.log_std, step_counter=self.__dict__.get("_step_counter_dev"), out=out)
         return actions, log_prob, value, mean, sigma      # sigma = log_std.repeat(N, 1), written by the same launch
 
     def _refresh_scale(self):

@@ -12,9 +12,10 @@ What is captured is, launch for launch, the loop of agents/algorithms/rl/ppo/ppo
     storage.compute_returns(last_values, gamma, lam)                                                   # ppo.py:157
 
 i.e. per env step: the dual-network MLP chain (tcgen05), the sampling / log-prob kernel, the reset compaction, the fused
-step kernel and the nine-plane insert (on a side branch of the graph, under the next step's policy forward); per rollout
-the GAE scan and the advantage normalisation.  `current_obs.copy_` has
-no launch here: the step kernel alternates between two static observation buffers.  One graph per phase of the frame ring
+step kernel and the insert (on a side branch of the graph, under the next step's policy forward); per rollout
+the GAE scan and the advantage normalisation.  `current_obs.copy_` has no launch here, and the insert carries four small
+planes only: the step kernel writes observation t + 1 straight into `storage.obs_slots[t + 1]`, the sampling kernel writes
+actions / log-probs / sigma into their storage slots.  One graph per phase of the frame ring
 (captured when the phase first comes up, after one eager rollout), so `run()` costs one `cudaGraphLaunch`.
 
 What makes it replayable: both random streams keep their Philox counters in device memory, advanced by the launches
@@ -23,6 +24,8 @@ fixed per captured step; the policy's kernel-side weights are refreshed IN PLACE
 replay, so an `optimizer.step()` between two rollouts is seen); everything the host tracks (`provider.cursor`, step counts,
 `storage.step`) is re-applied per replay.  The eager loop with the same seeds stores bit-identical planes
 (tests/test_gpu_ppo_rollout.py)."""
+import os
+
 import torch
 
 from . import _lib as L
@@ -56,12 +59,13 @@ class GraphedPPORollout:
         self.env, self.task, self.policy, self.storage = env, task, policy, storage
         self.gamma, self.lam, self.tracker = float(gamma), float(lam), tracker
         self.T = storage.num_transitions_per_env
-        self._obs = None                  # the two static observation buffers the step kernel alternates between
-        self._flip = 0
         self.states = torch.zeros(task.num_envs, 0, device=task.device)
         self.current_obs = None
         self._graphs = {}
         self._side = torch.cuda.Stream(device=task.device)
+        # the graph's main branch is captured on a high-priority stream (kernel nodes keep it): when a step ends, the next
+        # policy forward - whole SMs per CTA - and the side branch become ready together, and the forward must go first
+        self._main = torch.cuda.Stream(device=task.device, priority=-1) if os.environ.get("MMB_ROLLOUT_PRIO", "1") != "0" else None
         self._pool = None
         self._eager_left = 1              # one eager rollout first: modules loaded, caches built before any capture
         self._ahead = hasattr(task, "reset_ahead")
@@ -73,24 +77,30 @@ class GraphedPPORollout:
     _FRAME_ATTRS = ("root_states", "dof_state", "vec_sensor_tensor")
 
     def _next_out(self, *shape):
-        if tuple(shape) != tuple(self._obs[0].shape):
-            raise L.MmbError("unexpected step output %r (observation buffers are %r)" % (tuple(shape), tuple(self._obs[0].shape)))
-        self._flip ^= 1
-        return self._obs[self._flip]
+        """`task._fresh_out` during a rollout: the step kernel writes the next observation straight into the storage slot it
+        belongs to (`storage.step` counts the inserts made so far)."""
+        slot = self.storage.obs_slots[self.storage.step + 1]
+        if tuple(shape) != tuple(slot.shape):
+            raise L.MmbError("unexpected step output %r (observation slots are %r)" % (tuple(shape), tuple(slot.shape)))
+        return slot
 
     def _body(self):
-        """The loop of ppo.py:127-157; `task._fresh_out` hands the step kernel the observation buffer `current_obs` is NOT.
-        The insert of step t runs on a side stream under the policy forward of step t + 1 (it only feeds the storage); the
-        step kernel of t + 1 waits for it, because it overwrites the observation / reward / reset buffers the insert reads.
-        So does (TenAnt) the reset compaction of step t + 1, which needs nothing but the flags step t left
-        (`TenAnt.reset_ahead`): the invariant at every rollout boundary is "the next step's reset_idx() has been launched"."""
+        """The loop of ppo.py:127-157 without its copies: observation t lives in `storage.obs_slots[t]` (written there by the
+        step kernel; slot T of the previous rollout becomes slot 0 first), the sampling kernel writes actions / log-probs /
+        sigma into their slots, so the insert of step t only carries mu, values, rewards and dones.  It runs on a side stream
+        under the policy forward of step t + 1; the step kernel of t + 1 waits for it, because it overwrites the reward /
+        reset buffers the insert reads.  So does (TenAnt) the reset compaction of step t + 1, which needs nothing but the
+        flags step t left (`TenAnt.reset_ahead`): the invariant at every rollout boundary is "the next step's reset_idx() has
+        been launched"."""
         t, pol, st = self.task, self.policy, self.storage
         main, side = torch.cuda.current_stream(), self._side
-        cur = self._obs[self._flip]
+        slots = st.obs_slots
+        slots[0].copy_(slots[self.T])
         keep, inserted = [], None        # the policy outputs stay allocated until the last insert has been joined
         ahead = self._ahead
-        for _ in range(self.T):
-            outs = pol.act(cur, self.states)
+        for k in range(self.T):
+            cur = slots[k]
+            outs = pol.act(cur, self.states, out=(st.actions[k], st.actions_log_prob[k], st.sigma[k]))
             keep.append(outs)
             actions, logp, values, mu, sigma = outs
             if inserted is not None:
@@ -105,33 +115,25 @@ class GraphedPPORollout:
                 st.add_transitions(cur, self.states, actions, t.rew_buf, t.reset_buf, values, logp, mu, sigma)
                 inserted = torch.cuda.Event()
                 inserted.record(side)
-            cur = t.obs_clamped
-        last_values = pol.act(cur, self.states)[2]
+        self.current_obs = slots[self.T]
+        last_values = pol.act(self.current_obs, self.states)[2]
         main.wait_event(inserted)
         st.compute_returns(last_values, self.gamma, self.lam)
         if self.tracker is not None:
             self.tracker.update(st.rewards, st.dones)
-        if self._flip:                    # odd horizon: back to buffer 0, so that every rollout starts from the same tensor
-            self._obs[0].copy_(cur)
-            self._flip = 0
-        self.current_obs = self._obs[0]
         del keep
 
     def start_from(self, obs):
         """Start (or restart) from `obs` = what `env.reset()` / the last `env.step()` returned, instead of resetting on the
         first `run()`."""
-        if self._obs is None:
-            self._obs = (obs.clone(), torch.empty_like(obs))
-        else:
-            self._obs[0].copy_(obs)
-        self._flip = 0
-        self.current_obs = self._obs[0]
+        self.storage.obs_slots[self.T].copy_(obs)
+        self.current_obs = self.storage.obs_slots[self.T]
 
     def run(self):
         t, st, prov = self.task, self.storage, self.task.provider
         if st.step != 0:
             raise AssertionError("Rollout buffer overflow")          # storage.py:36 (the storage was not cleared)
-        if self._obs is None:
+        if self.current_obs is None:
             self.start_from(self.env.reset())
         self.policy.sync_parameters()
         if self._ahead and self._steps_seen != t._step_count:
@@ -162,7 +164,7 @@ class GraphedPPORollout:
                 self._pool = torch.cuda.graph_pool_handle()
             t._fresh_out = self._next_out
             try:
-                with torch.cuda.graph(g, pool=self._pool):
+                with torch.cuda.graph(g, pool=self._pool, **({"stream": self._main} if self._main is not None else {})):
                     self._body()          # advances the host-side state once; the kernels run at the replay below
             finally:
                 del t._fresh_out
@@ -179,7 +181,7 @@ class GraphedPPORollout:
             for k, v in rec[1]:
                 setattr(t, k, v)
             st.step = self.T
-            t.obs_clamped = self.current_obs
+            t.obs_clamped = self.current_obs = st.obs_slots[self.T]
         rec[0].replay()
         if st.stats_exchange is not None:
             st._xchg_pending = True

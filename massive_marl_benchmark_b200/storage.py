@@ -116,10 +116,13 @@ class RolloutStorage:
                       self.actions_log_prob, self.mu, self.sigma)
             self._dst_ptrs = [[(pl[t].data_ptr() if pl.numel() else None) for pl in planes]
                               for t in range(self.num_transitions_per_env)]
+        dst = self._dst_ptrs[s]
+        # a plane the producer has written straight into this slot (the step kernel's observation, the sampling kernel's
+        # actions / log-probs / sigma: ppo_rollout.GraphedPPORollout) is not copied onto itself
         (p.observations, p.states, p.actions, p.rewards, p.dones, p.values, p.actions_log_prob, p.mu,
-         p.sigma) = [t.data_ptr() if t.numel() else None for t in keep]
+         p.sigma) = [(t.data_ptr() if t.numel() and t.data_ptr() != d else None) for t, d in zip(keep, dst)]
         (p.dst_observations, p.dst_states, p.dst_actions, p.dst_rewards, p.dst_dones, p.dst_values, p.dst_actions_log_prob,
-         p.dst_mu, p.dst_sigma) = self._dst_ptrs[s]
+         p.dst_mu, p.dst_sigma) = dst
         p.values_stride = v_stride
         L.check(L.lib().mmb_rollout_add(p, L.stream_ptr()), "mmb_rollout_add")
         self._keep_add = keep

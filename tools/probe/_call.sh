@@ -1,3 +1,3 @@
-timeout 300 python -m pytest tests/test_gpu_ppo_rollout.py tests/test_gpu_graphed_step.py -x -q -m gpu > gpurun_out/r2s4_pytest_d.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2s4_pytest_d.log
-tail -15 gpurun_out/r2s4_pytest_d.log
-timeout 200 python tools/bench_ppo_rollout.py > gpurun_out/r2s4_ppo_rollout_d.log 2>&1; tail -6 gpurun_out/r2s4_ppo_rollout_d.log
+timeout 300 python -m pytest tests/test_gpu_ppo_rollout.py tests/test_gpu_storage.py tests/test_gpu_dropin.py -x -q -m gpu > gpurun_out/r2s4_pytest_f.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2s4_pytest_f.log
+tail -12 gpurun_out/r2s4_pytest_f.log
+timeout 200 python tools/bench_ppo_rollout.py 2>&1 | grep -v torch_fp32
