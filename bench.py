@@ -312,6 +312,57 @@ def mlp_forward_bench(dev, M, iters=200):
                     "TFLOP/s from the graph-replayed time; not part of the headline metric"}
 
 
+def ppo_rollout_bench(dev, frames, N, T, rollouts=10):
+    """frames: list of frame sets (dicts of [T, rows, cols] device tensors), concatenated into one ring.  The rollout phase of the reference's PPO loop WITH the policy in it (ppo.py:127-157: act -> step -> add_transitions per
+    env step, compute_returns per rollout) as one CUDA-graph replay per rollout (`ppo_rollout.GraphedPPORollout`), frames
+    resident in HBM: env-steps/s over `rollouts` replays, CUDA events.  Secondary figure (the headline metric has no policy)."""
+    from massive_marl_benchmark_b200.mlp import PPOActorCriticForward
+    from massive_marl_benchmark_b200.ppo_rollout import GraphedPPORollout
+    from massive_marl_benchmark_b200.providers import ReplayProvider
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    from massive_marl_benchmark_b200.tasks import TenAnt
+    from massive_marl_benchmark_b200.vec_task import VecTaskPython
+
+    def net(out_dim):
+        dims, mods = [388, 1024, 1024, 512, out_dim], []
+        for i in range(4):
+            mods.append(torch.nn.Linear(dims[i], dims[i + 1]))
+            if i < 3:
+                mods.append(torch.nn.ELU())
+        return torch.nn.Sequential(*mods)
+
+    class AC(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.asymmetric = False
+            self.actor, self.critic = net(80), net(1)
+            self.log_std = torch.nn.Parameter(torch.log(torch.tensor(0.8)) * torch.ones(80))
+
+    torch.manual_seed(0)
+    prov = ReplayProvider({"root": torch.cat([f["root"] for f in frames]), "dof": torch.cat([f["dof"] for f in frames])}, device=dev)
+    n_frames = prov.num_frames
+    task = TenAnt({"env": {"numEnvs": N, "env_name": "ten_ant"}, "sim": {"dt": 0.0166}, "seed": 1}, provider=prov)
+    st = RolloutStorage(N, T, (388,), (0,), (80,), dev)
+    ro = GraphedPPORollout(VecTaskPython(task, dev), PPOActorCriticForward(AC().to(dev), dev), st, GAMMA, LAM)
+    phases = max(1, n_frames // T) + 2
+    for _ in range(phases + 1):          # one eager rollout, then every phase of the frame ring captured
+        ro.run()
+        st.clear()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rollouts):
+        ro.run()
+        st.clear()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / rollouts
+    return {"op": "PPO rollout phase with the policy in the loop (act -> step -> add_transitions x %d, compute_returns), one CUDA-graph "
+                  "replay per rollout" % T, "num_envs": N, "horizon": T, "us_per_env_step": ms * 1e3 / T,
+            "env_steps_per_s": N * T / (ms * 1e-3), "graphs_captured": ro.captures,
+            "note": "frames resident in HBM; actor + critic 388-1024-1024-512-80/1 on tcgen05 (bf16 operands); not the headline metric"}
+
+
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
@@ -580,6 +631,12 @@ def run_ours(args, rank, world, local_rank):
             mlp = mlp_forward_bench(dev, N)
         except Exception as ex:  # pragma: no cover
             mlp = {"error": repr(ex)}
+    ppo_ro = None
+    if world == 1 and not args.no_mlp:
+        try:
+            ppo_ro = ppo_rollout_bench(dev, dev_frames[:2], N, T)
+        except Exception as ex:  # pragma: no cover
+            ppo_ro = {"error": repr(ex)}
 
     xchg_errors = int(mdist.sum_over_ranks(float(xchg.errors), dev)) if xchg is not None else 0
     chain_errors = int(mdist.sum_over_ranks(float(chain_errors), dev))
@@ -645,6 +702,7 @@ def run_ours(args, rank, world, local_rank):
                                     "achieved": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak}},
         "cpu_baseline": cpu,
         "mlp_forward": mlp,
+        "ppo_rollout": ppo_ro,
         "clocks": sampler.summary(t_host0, t_host1),
     }
     print(json.dumps(line), flush=True)

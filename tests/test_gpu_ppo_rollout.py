@@ -122,6 +122,64 @@ def test_graphed_rollout_equals_the_eager_loop(cuda_device, T, F):
         ro.run()
 
 
+def test_graphed_rollout_one_ant(cuda_device):
+    """BASELINE configs[0] (OneAnt PPO, 64 envs): the same comparison on a task without the reset-ahead split."""
+    from massive_marl_benchmark_b200 import synthetic
+    from massive_marl_benchmark_b200.mlp import PPOActorCriticForward
+    from massive_marl_benchmark_b200.ppo_rollout import GraphedPPORollout
+    from massive_marl_benchmark_b200.providers import ReplayProvider
+    from massive_marl_benchmark_b200.storage import RolloutStorage
+    from massive_marl_benchmark_b200.tasks import OneAnt
+    from massive_marl_benchmark_b200.vec_task import VecTaskPython
+    dev, N, T, F, R = cuda_device, 64, 8, 16, 6
+
+    def net(out_dim):
+        return torch.nn.Sequential(torch.nn.Linear(60, 256), torch.nn.ELU(), torch.nn.Linear(256, 256), torch.nn.ELU(),
+                                   torch.nn.Linear(256, out_dim))
+
+    class AC(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.asymmetric = False
+            self.actor, self.critic = net(8), net(1)
+            self.log_std = torch.nn.Parameter(torch.log(torch.tensor(0.8)) * torch.ones(8))
+
+    torch.manual_seed(2)
+    ac = AC().to(dev)
+
+    def setup():
+        fr = synthetic.one_ant_frames(N, F, seed=3)
+        cfg = {"env": {"numEnvs": N, "env_name": "one_ant", "episodeLength": 9}, "sim": {"dt": 0.0166}, "seed": 5}
+        task = OneAnt(cfg, None, None, "cuda", 0, True, False, provider=ReplayProvider(fr, device=dev))
+        pol = PPOActorCriticForward(ac, dev)
+        pol.seed = 3
+        return VecTaskPython(task, dev), pol, RolloutStorage(N, T, (60,), (0,), (8,), dev)
+
+    env, pol, st = setup()
+    states = torch.zeros(N, 0, device=dev)
+    torch.manual_seed(1)
+    current_obs = env.reset()
+    eager = []
+    for r in range(R):
+        for _ in range(T):
+            actions, logp, values, mu, sigma = pol.act(current_obs, states)
+            next_obs, rews, dones, _ = env.step(actions)
+            st.add_transitions(current_obs, states, actions, rews, dones, values, logp, mu, sigma)
+            current_obs.copy_(next_obs)
+        st.compute_returns(pol.act(current_obs, states)[2], 0.99, 0.95)
+        eager.append(_snapshot(st))
+        st.clear()
+    env, pol, st = setup()
+    ro = GraphedPPORollout(env, pol, st, 0.99, 0.95)
+    torch.manual_seed(1)
+    for r in range(R):
+        ro.run()
+        for k in _PLANES:
+            assert torch.equal(getattr(st, k), eager[r][k]), "rollout %d: %s differs" % (r, k)
+        st.clear()
+    assert ro.captures == 2 and not ro._ahead
+
+
 def test_gaussian_act_device_step_counter(cuda_device):
     """`step_counter`: the launch takes the Philox step from device memory and advances it - the draws equal those of the
     host-side counter started at the same value, also when the calls are replayed from a CUDA graph."""
