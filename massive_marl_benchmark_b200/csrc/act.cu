@@ -39,14 +39,16 @@ constexpr int ACT_THREADS = 1024;    // 32 rows in flight per block; the grid is
 constexpr unsigned ACT_TICKET_LANES = 16;
 static_assert(ACT_TICKET_LANES <= MMB_ACT_TICKET_LANES, "ticket words of the caller's buffer");
 
-// One warp per row.  PAIR (act_dim even, 8-byte aligned rows): a lane owns the element pairs (2 lane, 2 lane + 1) + 64 k -
-// the two elements that share one Philox call and one Box-Muller transform, so each is computed once, with 8-byte accesses.
+// PAIR (act_dim even, 8-byte aligned rows): the unit of work is the element pair (2 k, 2 k + 1) - the two elements that share
+// one Philox call and one Box-Muller transform, so each is computed once, with 8-byte accesses; a warp walks the pairs of R
+// consecutive rows.  Otherwise: one warp per row, one element per lane and pass.
 // Element idx of the [rows][act_dim] matrix takes word (idx & 1) of the transform of Philox counter idx >> 1: the stream
 // does not depend on the path taken.
 template <bool PAIR>
-__global__ void __launch_bounds__(ACT_THREADS) gaussian_act_kernel(const __grid_constant__ mmb_gaussian_act_params p) {
+__global__ void __launch_bounds__(ACT_THREADS) gaussian_act_kernel(const __grid_constant__ mmb_gaussian_act_params p, const int R) {
+  extern __shared__ float lp_s[];        // PAIR, R > 1: [warps][R * act_dim / 2] log-probs of the pairs of a warp's row group
   __shared__ unsigned long long s_step;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int A = p.act_dim;
   // Launched (optionally) as a programmatic dependent of the kernel in front of it (the MLP that writes the means): nothing is
   // read or WRITTEN before the wait - the outputs are fresh allocations, and the caching allocator may hand out a block the
@@ -80,57 +82,93 @@ __global__ void __launch_bounds__(ACT_THREADS) gaussian_act_kernel(const __grid_
   }
   const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
   const int mode = p.noise ? 0 : (p.deterministic ? 1 : 2);
-  for (int64_t row = (int64_t)blockIdx.x * (ACT_THREADS / 32) + warp; row < p.num_rows; row += (int64_t)gridDim.x * (ACT_THREADS / 32)) {
-    const int64_t grp = p.std_group_rows > 0 ? (row / p.std_group_rows) * A : 0;
-    const float* std = p.std + grp;
-    const float* mean = p.mean + row * p.mean_stride;
-    const int64_t base = row * A;
-    float lp_sum = 0.0f;
-    if (PAIR) {
-      for (int j = 2 * lane; j < A; j += 64) {
-        const float2 sd = __ldg(reinterpret_cast<const float2*>(std + j));
-        const float2 m = __ldg(reinterpret_cast<const float2*>(mean + j));
+  if (PAIR) {
+    // A warp owns R consecutive rows = R * hp element pairs and walks them 32 at a time, so no lane idles when a row's pair
+    // count is not a multiple of 32 (80 actions: four rows in five full passes instead of eight partial ones; 8 actions:
+    // eight rows per pass).  Row sums in a fixed order (lane partials over pairs k, k + 32, ... of the row, then the tree).
+    const int hp = A >> 1;
+    float* my = lp_s + (size_t)warp * R * hp;
+    const int l_r = lane / hp, l_c = lane - l_r * hp;        // (row, pair) of this lane's first pair; advance per pass below
+    const int d_r = 32 / hp, d_c = 32 - d_r * hp;
+    for (int64_t row0 = ((int64_t)blockIdx.x * warps + warp) * R; row0 < p.num_rows; row0 += (int64_t)gridDim.x * warps * R) {
+      const int nr = (p.num_rows - row0) < R ? (int)(p.num_rows - row0) : R;
+      const int total = nr * hp;
+      int r = l_r, c = l_c;
+      float lp_sum = 0.0f;
+      for (int q = lane; q < total; q += 32) {
+        const int row = (int)row0 + r, j = 2 * c;
+        const int64_t grp = p.std_group_rows > 0 ? (int64_t)(row / p.std_group_rows) * A : 0;
+        const int64_t base = (int64_t)row * A;
+        const float2 sd = __ldg(reinterpret_cast<const float2*>(p.std + grp + j));
+        const float2 m = __ldg(reinterpret_cast<const float2*>(p.mean + (int64_t)row * p.mean_stride + j));
         float2 z = make_float2(0.0f, 0.0f);
         if (mode == 0) {
           z = __ldg(reinterpret_cast<const float2*>(p.noise + base + j));
         } else if (mode == 2) {
-          const uint64_t c = (uint64_t)(base + j) >> 1;
-          const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
-          z = box_muller(r.x, r.y);
+          const uint64_t cnt = (uint64_t)(base + j) >> 1;
+          const uint4 rnd = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+          z = box_muller(rnd.x, rnd.y);
         }
         const float2 a = make_float2(m.x + z.x * sd.x, m.y + z.y * sd.y);
         *reinterpret_cast<float2*>(p.actions + base + j) = a;
         const float2 lp = make_float2(normal_logp(a.x, m.x, sd.x), normal_logp(a.y, m.y, sd.y));
         if (p.logp_per_dim) *reinterpret_cast<float2*>(p.logp_per_dim + base + j) = lp;
         if (p.sigma_out) *reinterpret_cast<float2*>(p.sigma_out + base + j) = __ldg(reinterpret_cast<const float2*>(p.sigma_src + grp + j));
-        lp_sum += lp.x + lp.y;
+        if (R > 1) my[q] = lp.x + lp.y;
+        else lp_sum += lp.x + lp.y;
+        r += d_r; c += d_c;
+        if (c >= hp) { c -= hp; ++r; }
       }
-    } else {
-      for (int j = lane; j < A; j += 32) {
-        const float sd = __ldg(std + j);
-        const float m = __ldg(mean + j);
-        float z = 0.0f;
-        if (mode == 0) {
-          z = __ldg(p.noise + base + j);
-        } else if (mode == 2) {
-          const uint64_t idx = (uint64_t)(base + j), c = idx >> 1;
-          const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
-          const float2 n = box_muller(r.x, r.y);
-          z = (idx & 1) ? n.y : n.x;
+      if (p.logp_sum) {
+        if (R > 1) {
+          __syncwarp();
+          for (int rr = 0; rr < nr; ++rr) {
+            float s = 0.0f;
+            for (int k = lane; k < hp; k += 32) s += my[rr * hp + k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) p.logp_sum[row0 + rr] = s;
+          }
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
+          if (lane == 0) p.logp_sum[row0] = lp_sum;
         }
-        const float a = m + z * sd;
-        p.actions[base + j] = a;
-        const float lp = normal_logp(a, m, sd);
-        if (p.logp_per_dim) p.logp_per_dim[base + j] = lp;
-        if (p.sigma_out) p.sigma_out[base + j] = __ldg(p.sigma_src + grp + j);
-        lp_sum += lp;
       }
+    }
+  } else {
+  for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < p.num_rows; row += (int64_t)gridDim.x * warps) {
+    const int64_t grp = p.std_group_rows > 0 ? (row / p.std_group_rows) * A : 0;
+    const float* std = p.std + grp;
+    const float* mean = p.mean + row * p.mean_stride;
+    const int64_t base = row * A;
+    float lp_sum = 0.0f;
+    for (int j = lane; j < A; j += 32) {
+      const float sd = __ldg(std + j);
+      const float m = __ldg(mean + j);
+      float z = 0.0f;
+      if (mode == 0) {
+        z = __ldg(p.noise + base + j);
+      } else if (mode == 2) {
+        const uint64_t idx = (uint64_t)(base + j), c = idx >> 1;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+        const float2 n = box_muller(r.x, r.y);
+        z = (idx & 1) ? n.y : n.x;
+      }
+      const float a = m + z * sd;
+      p.actions[base + j] = a;
+      const float lp = normal_logp(a, m, sd);
+      if (p.logp_per_dim) p.logp_per_dim[base + j] = lp;
+      if (p.sigma_out) p.sigma_out[base + j] = __ldg(p.sigma_src + grp + j);
+      lp_sum += lp;
     }
     if (p.logp_sum) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
       if (lane == 0) p.logp_sum[row] = lp_sum;
     }
+  }
   }
 }
 
@@ -148,11 +186,38 @@ extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* str
     LaunchScope ls(K_GAUSS_ACT, (cudaStream_t)stream);
     // optionally a programmatic dependent launch: the grid is scheduled while the kernel in front (the MLP that writes the
     // means) drains; everything that reads its output sits behind griddepcontrol.wait
+    auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+    const bool pair = (p.act_dim & 1) == 0 && (p.mean_stride & 1) == 0 && al8(p.mean) && al8(p.std) && al8(p.actions) && al8(p.noise) &&
+                      al8(p.logp_per_dim) && al8(p.sigma_src) && al8(p.sigma_out);
+    // rows per warp (pair path): the smallest R <= 16 whose R * act_dim / 2 pairs fill the 32-lane passes to >= 95 %, else the
+    // best; the row group's log-probs go through shared memory (R > 1), which bounds R for wide rows
+    // ... and never so large that the grid runs short of warps: the kernel hides its latencies (Philox chains, IEEE log /
+    // divide sequences) by parallelism - at 4096 x 80 one row per warp (4096 warps, 5/8 of the lanes busy) measured 1.7 us
+    // FASTER than four rows per warp (1024 warps, every lane busy)
+    int R = 1;
+    if (pair) {
+      const int hp = p.act_dim / 2;
+      const int64_t r_cap = (int64_t)p.num_rows / ((int64_t)sm_count() * 28);
+      double best = 0.0;
+      for (int r = 1; r <= 16 && r <= (r_cap < 1 ? 1 : r_cap); ++r) {
+        if (r > 1 && (int64_t)r * hp * 4 * 4 > 40 * 1024) break;            // four warps at least
+        const double eff = (double)r * hp / (32.0 * ((r * hp + 31) / 32));
+        if (eff > best + 1e-9) { best = eff; R = r; }
+        if (eff >= 0.95) break;
+      }
+    }
+    // block size: the largest that still gives (nearly) every SM a block and fits the shared memory
+    int threads = ACT_THREADS;
+    const int64_t per_warp = R;
+    while (threads > 128 && (((int64_t)p.num_rows + (threads / 32) * per_warp - 1) / ((threads / 32) * per_warp) < (int64_t)(sm_count() * 4) / 5 ||
+                             (R > 1 && (int64_t)(threads / 32) * R * (p.act_dim / 2) * 4 > 40 * 1024)))
+      threads >>= 1;
     cudaLaunchConfig_t cfg = {};
-    int64_t blocks = ((int64_t)p.num_rows + ACT_THREADS / 32 - 1) / (ACT_THREADS / 32);
+    int64_t blocks = ((int64_t)p.num_rows + (threads / 32) * per_warp - 1) / ((threads / 32) * per_warp);
     if (blocks > sm_count()) blocks = sm_count();
     cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3(ACT_THREADS);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (pair && R > 1) ? (size_t)(threads / 32) * R * (p.act_dim / 2) * 4 : 0;
     cfg.stream = (cudaStream_t)stream;
     // MMB_ACT_PDL=1: measured equal within noise to the ordinary launch behind the dual-network chain (act() graph-replayed
     // 52.0 vs 51.1 us at M = 4096), so it is off by default
@@ -162,10 +227,7 @@ extern "C" int32_t mmb_gaussian_act(const mmb_gaussian_act_params* pp, void* str
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
-    const bool pair = (p.act_dim & 1) == 0 && (p.mean_stride & 1) == 0 && al8(p.mean) && al8(p.std) && al8(p.actions) && al8(p.noise) &&
-                      al8(p.logp_per_dim) && al8(p.sigma_src) && al8(p.sigma_out);
-    const cudaError_t le = pair ? cudaLaunchKernelEx(&cfg, gaussian_act_kernel<true>, p) : cudaLaunchKernelEx(&cfg, gaussian_act_kernel<false>, p);
+    const cudaError_t le = pair ? cudaLaunchKernelEx(&cfg, gaussian_act_kernel<true>, p, R) : cudaLaunchKernelEx(&cfg, gaussian_act_kernel<false>, p, R);
     if (le != cudaSuccess) { (void)cudaGetLastError(); return MMB_ECUDA; }
   }
   return cudaGetLastError() == cudaSuccess ? MMB_OK : MMB_ECUDA;

@@ -205,3 +205,38 @@ def test_gaussian_act_device_step_counter(cuda_device):
     assert ctr.tolist() == [11] + [0] * (L.ACT_COUNTER_WORDS - 1)
     small = gaussian_act(mean[:3], std, seed=4, step_counter=ctr)[0]          # one block: fewer blocks than ticket lanes
     assert torch.equal(small, gaussian_act(mean[:3], std, seed=4, step=11)[0]) and ctr.tolist() == [12] + [0] * (L.ACT_COUNTER_WORDS - 1)
+
+
+@pytest.mark.parametrize("M,A", [(4099, 80), (40961, 8), (517, 6), (300, 64), (1000, 7), (5, 80), (70, 200)])
+def test_gaussian_act_shapes_and_paths(cuda_device, M, A):
+    """Every row-grouping of the pair path (rows per warp 1 ... 16, ragged last group, widths below / above / multiple of a
+    warp's 32 pairs) and the element-per-lane path (odd width) against torch with supplied draws; and the Philox stream does
+    not depend on the path: an odd row stride of the means forces the element path, the draws stay the same."""
+    from massive_marl_benchmark_b200.mlp import gaussian_act
+    from torch.distributions import Normal
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(M + A)
+    mean = torch.randn(M, A, generator=gen).to(dev)
+    std = (0.3 + torch.rand(A, generator=gen)).to(dev)
+    z = torch.randn(M, A, generator=gen).to(dev)
+    src = torch.randn(A, generator=gen).to(dev)
+    act, lp, sig = gaussian_act(mean, std, noise=z, sigma_src=src)
+    assert torch.allclose(act, mean + z * std, rtol=1e-6, atol=1e-6) and torch.equal(sig, src.repeat(M, 1))
+    ref = Normal(mean, std).log_prob(act)
+    assert torch.allclose(lp, ref.sum(1), rtol=1e-4, atol=2e-3)
+    act2, lp2 = gaussian_act(mean, std, noise=z, per_dim=True)
+    assert torch.equal(act2, act) and torch.allclose(lp2, ref, rtol=1e-4, atol=1e-4)
+    groups = 3
+    rows = (M + groups - 1) // groups
+    std_g = (0.3 + torch.rand(groups, A, generator=gen)).to(dev)
+    act3, lp3 = gaussian_act(mean, std_g, noise=z, std_group_rows=rows, per_dim=True)
+    sd_rows = std_g.repeat_interleave(rows, dim=0)[:M]
+    assert torch.allclose(act3, mean + z * sd_rows, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(lp3, Normal(mean, sd_rows).log_prob(act3), rtol=1e-4, atol=1e-4)
+    a_pair, l_pair = gaussian_act(mean, std, seed=3, step=9)
+    wide = torch.zeros(M, A + 1, device=dev)
+    wide[:, :A] = mean
+    a_elem, l_elem = gaussian_act(wide[:, :A], std, seed=3, step=9)          # row stride A + 1
+    if A % 2 == 0:
+        assert wide[:, :A].stride(0) % 2 == 1
+    assert torch.equal(a_pair, a_elem) and torch.allclose(l_pair, l_elem, rtol=1e-5, atol=1e-5)
