@@ -298,7 +298,10 @@ MMB_API int32_t mmb_ten_ant_env_step(const mmb_reset_params* reset, const mmb_te
 /* Rollout storage: PPO (agents/algorithms/rl/ppo/storage.py)                                    */
 /* ------------------------------------------------------------------------------------------ */
 /* RolloutStorage.add_transitions (storage.py:32-46) for callers that cannot use the step kernel's
- * direct write into the rollout slot: nine copies fused in one launch, dones int64 -> uint8. */
+ * direct write into the rollout slot: nine copies fused in one launch, dones int64 -> uint8.
+ * A NULL source (or destination) skips that plane - the producer has written the slot itself (the step
+ * kernel's observation, mmb_gaussian_act's actions / log-probs / sigma) - and the grid follows the
+ * widest plane actually copied. */
 typedef struct {
   int32_t num_envs, obs_dim, states_dim, act_dim;
   const float* observations; const float* states; const float* actions; const float* rewards;
