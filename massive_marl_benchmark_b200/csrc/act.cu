@@ -138,37 +138,37 @@ __global__ void __launch_bounds__(ACT_THREADS) gaussian_act_kernel(const __grid_
       }
     }
   } else {
-  for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < p.num_rows; row += (int64_t)gridDim.x * warps) {
-    const int64_t grp = p.std_group_rows > 0 ? (row / p.std_group_rows) * A : 0;
-    const float* std = p.std + grp;
-    const float* mean = p.mean + row * p.mean_stride;
-    const int64_t base = row * A;
-    float lp_sum = 0.0f;
-    for (int j = lane; j < A; j += 32) {
-      const float sd = __ldg(std + j);
-      const float m = __ldg(mean + j);
-      float z = 0.0f;
-      if (mode == 0) {
-        z = __ldg(p.noise + base + j);
-      } else if (mode == 2) {
-        const uint64_t idx = (uint64_t)(base + j), c = idx >> 1;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
-        const float2 n = box_muller(r.x, r.y);
-        z = (idx & 1) ? n.y : n.x;
+    for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < p.num_rows; row += (int64_t)gridDim.x * warps) {
+      const int64_t grp = p.std_group_rows > 0 ? (row / p.std_group_rows) * A : 0;
+      const float* std = p.std + grp;
+      const float* mean = p.mean + row * p.mean_stride;
+      const int64_t base = row * A;
+      float lp_sum = 0.0f;
+      for (int j = lane; j < A; j += 32) {
+        const float sd = __ldg(std + j);
+        const float m = __ldg(mean + j);
+        float z = 0.0f;
+        if (mode == 0) {
+          z = __ldg(p.noise + base + j);
+        } else if (mode == 2) {
+          const uint64_t idx = (uint64_t)(base + j), c = idx >> 1;
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+          const float2 n = box_muller(r.x, r.y);
+          z = (idx & 1) ? n.y : n.x;
+        }
+        const float a = m + z * sd;
+        p.actions[base + j] = a;
+        const float lp = normal_logp(a, m, sd);
+        if (p.logp_per_dim) p.logp_per_dim[base + j] = lp;
+        if (p.sigma_out) p.sigma_out[base + j] = __ldg(p.sigma_src + grp + j);
+        lp_sum += lp;
       }
-      const float a = m + z * sd;
-      p.actions[base + j] = a;
-      const float lp = normal_logp(a, m, sd);
-      if (p.logp_per_dim) p.logp_per_dim[base + j] = lp;
-      if (p.sigma_out) p.sigma_out[base + j] = __ldg(p.sigma_src + grp + j);
-      lp_sum += lp;
-    }
-    if (p.logp_sum) {
+      if (p.logp_sum) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
-      if (lane == 0) p.logp_sum[row] = lp_sum;
+        for (int o = 16; o > 0; o >>= 1) lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
+        if (lane == 0) p.logp_sum[row] = lp_sum;
+      }
     }
-  }
   }
 }
 
