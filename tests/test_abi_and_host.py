@@ -58,6 +58,7 @@ def test_ctypes_structs_match_c_layout(built_lib):
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "mmb.h"\nint main(void){\n'
     for cname, _, field in probes:
         src += 'printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (cname, cname, field)
+    src += 'printf("%d %d\\n", (int)MMB_ACT_COUNTER_WORDS, (int)MMB_ABI_VERSION);\n'
     src += "return 0;}\n"
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
@@ -67,6 +68,8 @@ def test_ctypes_structs_match_c_layout(built_lib):
         size, off = map(int, line.split())
         assert ctypes.sizeof(cls) == size, cname
         assert getattr(cls, field).offset == off, (cname, field)
+    words, abi = map(int, out[len(probes)].split())
+    assert words == L.ACT_COUNTER_WORDS and abi == L.ABI_VERSION      # constants the binding restates
 
 
 def test_no_cpu_fallback(built_lib):
