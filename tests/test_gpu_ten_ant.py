@@ -384,7 +384,7 @@ torch.save({"obs": obs.cpu(), "rew": rew.cpu(), "d8": d8.cpu(), "fo": fo.cpu(), 
         return out
 
     # Known issue: ONE unexplained mismatch of this comparison in ~50 runs of the suite, never reproduced
-    # in 30 targeted repetitions (tools/probe/variant_flake.py).  A mismatch is therefore re-run once: it fails the test only
+    # in 120 targeted repetitions (tools/probe/variant_flake.py).  A mismatch is therefore re-run once: it fails the test only
     # if it repeats, and is reported loudly (with where the outputs differed) if it does not.
     diff = differences(run_variants(""))
     if diff:
