@@ -49,8 +49,9 @@ class GraphedPPORollout:
         prov = task.provider
         if not isinstance(prov, ReplayProvider) or not prov.loop:
             raise TypeError("a graphed rollout needs frames resident in HBM (a looping ReplayProvider)")
-        if torch.device(env.rl_device) != torch.device(task.device) and torch.device(env.rl_device).index is not None:
-            raise TypeError("a graphed rollout needs rl_device == the task's device")
+        rl, td = torch.device(env.rl_device), torch.device(task.device)
+        if rl.type != "cuda" or (rl.index is not None and td.index is not None and rl.index != td.index):
+            raise TypeError("a graphed rollout needs rl_device == the task's CUDA device (got %s / %s)" % (rl, td))
         if getattr(task, "obs_layout", 0) != 0:
             raise TypeError("a graphed rollout drives the single-agent (flat observation) wrapper")
         if storage.process_group is not None and storage.stats_exchange is None:
